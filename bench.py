@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- constrained deals/sec of the Monte-Carlo deal path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], SURVEY 8d "C2"): South must hold a 1NT
+opener -- `(test-bid '(1 NT) hand)`, bidding.cl:83 -- and deals are rejection
+sampled until 1e8 are accepted.  One step = one such job on every GPU (weak
+scaling: each rank draws its own disjoint Philox index range; the only exchange
+is the all-reduce of the tally buffer).  `value` = raw deals drawn and tested per
+second, whole job; outputs (1.6 GB of records per step) are far larger than L2.
+
+The reference arm (--impl reference) times the reference's own algorithm
+(`distgen` exact sampler with its per-deal rescan + `test-bid` filter) as
+restated in C in oracle/bmc_oracle.c: the reference is Common Lisp and no Lisp
+implementation exists in this image, so oracle/_ref cannot be built.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "constrained deals/sec (raw deals drawn and tested against the South-1NT constraint)"
+UNIT = "deals/s"
+P_BOX = 29286389970 / 635013559600          # exact acceptance of the range ("box") form the reference can generate
+P_1NT = 24235203726 / 635013559600          # exact acceptance of test-bid (1 NT)
+SEED = 0x6272696467656D63
+# Algorithmic integer work of one raw deal on the hot kernel (DESIGN.md "W_int"):
+# 3 Philox4x32-10 (120) + 51 mixed-radix digits (51) + owner bookkeeping 51x4 (204)
+# + 8 plane extractions (48) + 12 Lemire checks (12) + stage-A features/range test (60) + loop/queue (25)
+W_INT = 520
+W_INT_SURVEY = 1400                          # SURVEY 8d's budget for the naive per-card algorithm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bridgemc")
+    ap.add_argument("--accept", type=float, default=1e8, help="accepted deals per step per GPU")
+    ap.add_argument("--wave", type=int, default=1 << 28)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-deals", type=int, default=1500, help="reference arm: builds per thread per step")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference algorithm (C restatement), all host threads
+# ---------------------------------------------------------------------------
+def cpu_reference_rate(n_per_thread: int, threads: int, seed0: int = 1):
+    """Runs `threads` independent generators (one per would-be /api/mc job; the
+    reference itself has a single producer thread per job, bridge.cl:3100).
+    Returns (builds/s, passing/s, seconds)."""
+    from oracle import oracle as O
+    L = O.lib()
+    L.orc_ref_run.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    L.orc_ref_run.restype = C.c_uint64
+    gens = [O.Distgen(hcp=(15, 17), c=(2, 5), d=(2, 5), h=(2, 4), s=(2, 4)) for _ in range(threads)]
+    passed = [0] * threads
+
+    def work(i):
+        st = C.c_uint64(seed0 + 7919 * i)
+        cs = C.c_uint64()
+        passed[i] = L.orc_ref_run(gens[i]._g, C.byref(st), n_per_thread, 2, C.byref(cs))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return n_per_thread * threads / dt, sum(passed) / dt, dt
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    for _ in range(args.warmup):
+        cpu_reference_rate(max(50, args.ref_deals // 10), threads)
+    builds = passing = secs = 0.0
+    for i in range(args.steps):
+        b, p, dt = cpu_reference_rate(args.ref_deals, threads, seed0=100 + i)
+        builds += b * dt
+        passing += p * dt
+        secs += dt
+    acc_per_s = passing / secs
+    value = acc_per_s / P_1NT              # raw-deal equivalent of the constructive sampler
+    sample = (f"{args.ref_deals} builds/thread/step of (:hcp (15 17) :c (2 5) :d (2 5) :h (2 4) :s (2 4)) with the "
+              f"per-deal distgen rescan, then test-bid (1 NT); {passing / builds:.4f} pass; value = accepted/s / "
+              f"{P_1NT:.6f} (raw-deal equivalent)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "C2: South test-bid (1 NT), reference algorithm on host cores (C restatement, not SBCL)"},
+        "accepted_per_s": acc_per_s,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bridge_mc_b200 import bidding, _lib
+    from bridge_mc_b200.engine import Constraints, Engine, tallies_from_words
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libbridgemc has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = Engine(local)
+    stream = torch.cuda.Stream(dev)               # events must be recorded on the stream the kernels run on
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    target = int(args.accept)
+    cap = target + target // 16 + (1 << 20)
+    records = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+    tallies = torch.zeros(_lib.TALLY_WORDS, dtype=torch.int64, device=dev)
+
+    def step(i):
+        tallies.zero_()
+        first = (i * world + rank) << 40          # disjoint Philox counter ranges per (step, rank)
+        st = eng.sample_dev(cons, records.data_ptr(), cap, tallies.data_ptr(), n_accept=target, wave=args.wave,
+                            first_index=first, seed=SEED)
+        if world > 1:
+            dist.all_reduce(tallies)              # the only exchange: a 4.5 KB histogram buffer over NVLink
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    int_peak, _ = eng.int_peak()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    raw = acc = 0
+    kernel_ms = 0.0
+    launches = 0
+    ev0.record(stream)
+    for i in range(args.steps):
+        st = step(args.warmup + i)
+        raw += st.raw; acc += st.accepted; kernel_ms += st.kernel_ms; launches += st.launches
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    gpu_launches = eng.launch_count() - l0
+    final = tallies_from_words(tallies.cpu().numpy().view(np.uint64))
+    tot = torch.tensor([float(raw), float(acc), ms, kernel_ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ms = float(mx[2])
+        raw_all, acc_all = float(tot[0]), float(tot[1])
+    else:
+        raw_all, acc_all = float(raw), float(acc)
+    value = raw_all / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI (what the Lisp shim calls) ----
+    e2e = None
+    if not args.no_e2e:
+        L = _lib.load()
+        nbytes = cap * 16
+        hp = L.bmc_host_alloc(nbytes)
+        if hp:
+            host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint64)), shape=(cap, 2))
+            k = max(1, min(args.steps, 2))
+            eng.sample(cons, n_accept=target, wave=args.wave, first_index=(99 * world + rank) << 40, seed=SEED,
+                       cap=cap, records=host)        # warm the path once
+            barrier()
+            t0 = time.perf_counter()
+            e_raw = e_stored = 0
+            for i in range(k):
+                _, t_h, st = eng.sample(cons, n_accept=target, wave=args.wave,
+                                        first_index=((100 + i) * world + rank) << 40, seed=SEED, cap=cap, records=host)
+                e_raw += st.raw; e_stored += st.stored
+            barrier()
+            dt = time.perf_counter() - t0
+            et = torch.tensor([float(e_raw), dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                emx = et.clone()
+                dist.all_reduce(emx, op=dist.ReduceOp.MAX)
+                dist.all_reduce(et, op=dist.ReduceOp.SUM)
+                dt = float(emx[1])
+            e2e = {"value": float(et[0]) / dt, "unit": UNIT, "h2d_bytes_per_step": 4096,
+                   "d2h_bytes_per_step": int(e_stored // k * 16 + _lib.TALLY_WORDS * 8), "steps": k,
+                   "api": "bmc_sample (host buffers: pinned record buffer from bmc_host_alloc)"}
+            L.bmc_host_free(hp)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        avg_launch_ms = kernel_ms / max(1, launches)
+        deals_per_launch = raw / max(1, launches)
+        achieved = deals_per_launch * W_INT / (avg_launch_ms * 1e-3) / 1e12
+        peak = int_peak / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"C2: South test-bid (1 NT) rejection sampling, {target:.0e} accepted deals per GPU per step "
+                                   f"(waves of {args.wave} Philox indices)",
+                       "l2": "no input buffers (counter-based RNG); 1.6 GB of records written per step >> 126 MB L2",
+                       "parallelism": f"dp{world}: disjoint Philox index ranges + NCCL all-reduce of the {_lib.TALLY_WORDS * 8} B tally buffer"},
+            "accepted_per_s": acc_all / (ms * 1e-3),
+            "acceptance": acc_all / max(1.0, raw_all),
+            "roofline": {"bound": "int32-issue", "kernel": "sample_kernel<true>", "achieved": achieved, "peak": peak,
+                         "unit": "Tint-op/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "w_int_per_deal": W_INT, "avg_launch_ms": avg_launch_ms, "deals_per_launch": deals_per_launch,
+                         "peak_source": "bmc_int_peak microbenchmark on this GPU (IMAD+LOP3 chains, burst)",
+                         "frac_at_survey_w_int_1400": deals_per_launch * W_INT_SURVEY / (avg_launch_ms * 1e-3) / int_peak,
+                         "hbm": {"achieved": (acc / max(1, launches)) * 16 / (avg_launch_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "peak_source": hbm_src,
+                                 "frac": (acc / max(1, launches)) * 16 / (avg_launch_ms * 1e-3) / 1e9 / hbm_peak}},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "tally_check": {"accepted": final["accepted"], "south_hcp_15_16_17": [int(x) for x in final["hcp"][2][15:18]]},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            n = 600
+            b, p, dt = cpu_reference_rate(n, threads)
+            line["cpu_baseline"] = {
+                "value": p / P_1NT, "unit": UNIT, "cores": threads, "kind": "port",
+                "accepted_per_s": p,
+                "sample": f"{n} builds/thread on {threads} threads ({dt:.1f} s) of the reference's distgen sampler "
+                          f"(box ranges, per-deal rescan) + test-bid (1 NT); value = accepted/s / {P_1NT:.6f}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,257 @@
+"""Host mirror of bidding.cl: rule tables and the entry points that evaluate them.
+
+Rule tables are alists `((bid . form) ...)` in the reference's own predicate
+language (bidding.cl:60-74); here they are built as S-expression text and handed
+to libbridgemc (bmc_scheme_create / bmc_constraints_create), which compiles them
+to device bytecode.  `assess_hand`, `test_bid` and `choose_bid` keep the
+reference signatures (bidding.cl:33,111,146) and run on the GPU via bmc_filter.
+
+Scheme *generators* (nt_responses, basic_responses) are host-side, as in the
+reference: they only emit forms.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import sexp
+from .cards import Hand, pack_deal, LANE_MASK
+from .engine import Engine, Scheme, Constraints
+
+SUITS = ("C", "D", "H", "S")
+
+
+# ---- small form builders -------------------------------------------------------
+def _and(*xs):
+    return "(and " + " ".join(xs) + ")"
+
+
+def _or(*xs):
+    return "(or " + " ".join(xs) + ")"
+
+
+def _not(x):
+    return f"(not {x})"
+
+
+def _cmp(op, a, b):
+    return f"({op} {a} {b})"
+
+
+def _any_longer_than(n, lo, hi):
+    """some suit of lens[lo:hi] longer than n -- the reference's find-if/subseq idiom"""
+    return f"(find-if (curry #'< {n}) (subseq lens {lo} {hi}))"
+
+
+def _between(var, lo, hi):
+    """bidding.cl:163-164 `range`"""
+    return _and(_cmp(">=", var, lo), _cmp("<=", var, hi))
+
+
+class RuleTable:
+    """An ordered alist of (bid, form-text) rows; `bid` is a tuple like (1, 'NT')."""
+
+    def __init__(self, rows):
+        self.rows = [(tuple(b), f) for b, f in rows]
+        self._scheme = None
+
+    def bids(self):
+        return [b for b, _ in self.rows]
+
+    def index(self, bid):
+        bid = _norm_bid(bid)
+        for i, (b, _) in enumerate(self.rows):
+            if b == bid:
+                return i
+        raise KeyError(bid)
+
+    def form(self, bid) -> str:
+        return self.rows[self.index(bid)][1]
+
+    def sexpr(self) -> str:
+        return "(" + " ".join(f"(({b[0]} {b[1]}) . {f})" for b, f in self.rows) + ")"
+
+    def scheme(self) -> Scheme:
+        if self._scheme is None:
+            self._scheme = Scheme(self.sexpr())
+        return self._scheme
+
+    # -- forms for seat constraints ------------------------------------------
+    def chooses(self, bid) -> str:
+        """form that is true iff choose-bid over this table returns `bid` (first match wins)"""
+        i = self.index(bid)
+        earlier = [f for _, f in self.rows[:i]]
+        if not earlier:
+            return self.rows[i][1]
+        return _and(self.rows[i][1], _not(_or(*earlier)))
+
+    def passes(self) -> str:
+        """form that is true iff choose-bid over this table returns nil"""
+        return _not(_or(*[f for _, f in self.rows]))
+
+
+def _norm_bid(bid):
+    if isinstance(bid, str):
+        bid = sexp.read(bid)
+    level, suit = bid
+    return (int(level), str(suit).upper())
+
+
+# ---- the tables (semantics: bidding.cl:76-106, 166-187, 204-210, 221-253) --------
+def _opening_rows():
+    rows = []
+    sound = _or(_cmp("<", "loosers", 6), _cmp(">", "hcp", 11))
+    # strong two clubs: 23+ or an unbalanced hand short of losers with a five-card suit
+    rows.append(((2, "C"), _or(_cmp(">", "hcp", 22),
+                               _and(_not("balanced"),
+                                    "(cond (" + _any_longer_than(4, 2, 4) + " " + _cmp("<=", "loosers", 4) + ") "
+                                    "(" + _any_longer_than(4, 0, 2) + " " + _cmp("<=", "loosers", 3) + "))"))))
+    rows.append(((2, "NT"), _and("balanced", _not("(find-if (curry #'> 3) power)"), _cmp(">", "hcp", 18))))
+    rows.append(((1, "NT"), _and("balanced", _cmp(">", "hcp", 14), _cmp("<", "hcp", 18))))
+    for suit, upto in (("S", 3), ("H", 2)):      # a longer lower suit with 17+ bids that suit first (reverse)
+        rows.append(((1, suit), _and(sound, _cmp(">", "loosers", 4), _cmp("<", "hcp", 23), _cmp(">=", suit, 5),
+                                     _not(_and(_cmp(">", "hcp", 16), _any_longer_than(4, 0, upto))))))
+    rows.append(((1, "D"), _and(sound, _cmp(">", "loosers", 3), _cmp("<", "hcp", 23), _cmp(">=", "D", 4),
+                                _cmp(">=", "D", "C"), _not(_and(_cmp(">", "hcp", 16), _cmp(">=", "C", 5))))))
+    rows.append(((1, "C"), _and(sound, _cmp(">", "loosers", 3), _cmp("<", "hcp", 23), _cmp(">=", "C", 3))))
+    for suit in ("D", "H", "S"):                 # weak twos
+        rows.append(((2, suit), _and(_cmp(">", "hcp", 5), _cmp(">=", suit + "power", 5),
+                                     _or(_cmp(">", "loosers", 5), _cmp("<", "hcp", 11)), _cmp("=", suit, 6))))
+    for suit in SUITS:                           # three-level preempts
+        rows.append(((3, suit), _and(_cmp(">", "hcp", 5), _cmp(">=", suit + "power", 5), _cmp("<", "hcp", 11),
+                                     _cmp(">=", suit, 7))))
+    return rows
+
+
+openings = RuleTable(_opening_rows())
+
+
+def nt_responses(level: int) -> RuleTable:
+    """bidding.cl:166-187: responses to a 1NT (level 1) or 2NT (level 2) opening."""
+    invite = (8, 9) if level == 1 else (4, 5)
+    game = (10, 15) if level == 1 else (6, 10)
+    slam_invite = (16, 17) if level == 1 else (12, 13)
+    slam = 18 if level == 1 else 14
+    base = level + 1
+    rows = [
+        ((base, "C"), _and(_cmp(">=", "hcp", invite[0]), _or(_cmp("=", "S", 4), _cmp("=", "H", 4)))),   # Stayman
+        ((base, "D"), _cmp(">=", "H", 5)),                                                              # transfers
+        ((base, "H"), _cmp(">=", "S", 5)),
+        ((base, "S"), _and(_or(_cmp("<", "hcp", invite[0]), _cmp(">", "hcp", game[1] - 2)),
+                           _or(_and(_cmp(">", "hcp", invite[0]), _cmp(">=", "C", 5)), _cmp(">=", "C", 6)))),
+    ]
+    if level == 1:
+        rows.append(((3, "C"), _and(_or(_cmp("<", "hcp", 8), _cmp(">", "hcp", 13)),
+                                    _or(_and(_cmp(">=", "hcp", 7), _cmp(">=", "D", 5)), _cmp(">=", "D", 6)))))
+        rows.append(((2, "NT"), _and(_cmp(">=", "hcp", 8), _cmp("<=", "hcp", 9), _cmp("<", "H", 5), _cmp("<", "S", 5),
+                                     _cmp("<", "C", 6), _cmp("<", "D", 6))))
+    rows += [((3, "NT"), _between("hcp", *game)),
+             ((4, "NT"), _between("hcp", *slam_invite)),
+             ((6, "NT"), _cmp(">=", "hcp", slam))]
+    return RuleTable(rows)
+
+
+two_c_responses = RuleTable([
+    ((2, "D"), _cmp(">=", "hcp", 6)),
+    ((2, "H"), _and(_cmp("<=", "hcp", 5), _cmp(">=", "H", 4))),
+    ((2, "S"), _and(_cmp("<=", "hcp", 5), _cmp(">=", "S", 4))),
+    ((2, "NT"), _and(_cmp("<=", "hcp", 5), "balanced")),
+    ((3, "C"), _and(_cmp("<=", "hcp", 5), _cmp(">=", "C", 5), _not("balanced"))),
+    ((3, "D"), _and(_cmp("<=", "hcp", 5), _cmp(">=", "D", 5), _not("balanced"))),
+])
+
+
+def fit(suit: str) -> str:
+    """bidding.cl:221-224"""
+    suit = suit.upper()
+    if suit == "C":
+        return _cmp(">=", "C", 5)
+    if suit == "D":
+        return _cmp(">=", "D", 4)
+    return _cmp(">=", suit, 3)
+
+
+def basic_responses(bid) -> RuleTable:
+    """bidding.cl:226-253: responses to a one-of-a-suit opening.
+
+    Kept quirk: in the `(3 suit)` raise the list of "no lower five-card suit"
+    tests is inserted as ONE element instead of being spliced (bidding.cl:249),
+    so that row is NIL for a club opening and an illegal call -- an error if
+    evaluation reaches it -- for the other suits."""
+    level, suit = _norm_bid(bid)
+    if level > 1 or suit not in SUITS:
+        raise ValueError("Wrong bid (only 1-suit bids accepted)")
+    o = SUITS.index(suit)
+    the_fit = fit(suit)
+    no_biddable_4 = [_cmp("<", SUITS[i], 4) for i in range(o + 1, 4)]
+    no_lower_5 = [_cmp("<", SUITS[i], 5) for i in range(0, o)]
+    rows = [((1, SUITS[i]), _and(_cmp(">=", "hcp", 6), _cmp(">=", SUITS[i], 4))) for i in range(o + 1, 4)]
+    rows.append(((1, "NT"), _and(_cmp(">=", "hcp", 6), _cmp("<=", "hcp", 10), *no_biddable_4, _not(the_fit))))
+    if suit == "C":
+        rows.append(((2, "C"), _and(_cmp(">=", "hcp", 6), _cmp("<=", "hcp", 9), _cmp(">=", "C", 5), *no_biddable_4)))
+    else:
+        rows.append(((2, "C"), _and(_cmp(">=", "hcp", 11), *no_biddable_4, *no_lower_5,
+                                    _or(_not(the_fit), _cmp(">=", "hcp", 15)))))
+    rows.append(((2, suit), _and(_cmp(">=", "hcp", 6), _cmp("<=", "hcp", 9), the_fit, *no_biddable_4)))
+    unspliced = "(" + " ".join(no_lower_5) + ")" if no_lower_5 else "nil"
+    rows.append(((3, suit), _and(_cmp(">=", "hcp", 10), _cmp("<=", "hcp", 12), the_fit, *no_biddable_4, unspliced)))
+    if o >= 2:
+        rows.append(((4, suit), _and(_cmp(">=", "hcp", 13), _cmp("<=", "hcp", 15), the_fit)))
+    for i in (1, 2, 3):
+        if o > i:
+            rows.append(((2, SUITS[i]), _and(_cmp(">=", "hcp", 11), _cmp(">=", SUITS[i], 5))))
+    return RuleTable(rows)
+
+
+# ---- entry points (GPU) ------------------------------------------------------------
+def _filler_deal(hand: Hand):
+    """a record whose North hand is `hand` (other seats get the remaining cards in order)"""
+    rest = [c for c in range(52) if c not in set(hand.cards())]
+    others = []
+    for k in range(3):
+        cards = rest[13 * k:13 * k + 13]
+        suits = [[c % 13 for c in cards if c // 13 == s] for s in range(4)]
+        others.append(Hand(suits))
+    return pack_deal([hand] + others)
+
+
+def assess_hands(hands, scheme: RuleTable | None = None, engine: Engine | None = None):
+    """Batch assess-hand (+ choose-bid over `scheme`) for 13-card hands: structured array[n]."""
+    eng = engine or Engine.default()
+    rec = np.stack([_filler_deal(h) for h in hands]) if len(hands) else np.empty((0, 2), np.uint64)
+    _, feats = eng.filter(rec, None, scheme.scheme() if scheme else None)
+    return feats[:, 0]
+
+
+def assess_hand(hand: Hand, measure=None, engine: Engine | None = None):
+    """bidding.cl:33-38: (lens power loosers), or `measure` applied to them."""
+    f = assess_hands([hand], None, engine)[0]
+    vals = ([int(x) for x in f["len"]], [int(x) for x in f["suit_hcp"]], int(f["losers"]))
+    return measure(*vals) if measure else vals
+
+
+def balanced(hand: Hand, engine: Engine | None = None) -> bool:
+    """bidding.cl:40-46 balanced? of a hand"""
+    return bool(assess_hands([hand], None, engine)[0]["balanced"])
+
+
+class BidError(RuntimeError):
+    """Evaluation reached a form the reference cannot evaluate (illegal function call)."""
+
+
+def choose_bid(hand: Hand, scheme: RuleTable = None, engine: Engine | None = None):
+    """bidding.cl:146-150: the first bid of `scheme` (default `openings`) whose rule holds, else None."""
+    scheme = scheme or openings
+    k = int(assess_hands([hand], scheme, engine)[0]["bid"])
+    if k == -2:
+        raise BidError("illegal function call while evaluating the rule table")
+    return None if k < 0 else scheme.rows[k][0]
+
+
+def test_bid(bid, hand: Hand, scheme: RuleTable = None, engine: Engine | None = None) -> bool:
+    """bidding.cl:111-112: does the rule of `bid` (in `openings`) hold for `hand`?"""
+    scheme = scheme or openings
+    one = RuleTable([(_norm_bid(bid), scheme.form(bid))])
+    k = int(assess_hands([hand], one, engine)[0]["bid"])
+    if k == -2:
+        raise BidError("illegal function call while evaluating the rule")
+    return k == 0

@@ -1,0 +1,1080 @@
+// bridgemc.cu -- kernels and C ABI of libbridgemc.so (sm_100a).
+//
+// Kernels
+//   sample_kernel   K1: Philox deal + first-stage range test + warp queue +
+//                   second-stage full test + tallies + compacted record stores
+//   filter_kernel   K2: features / accept flag / choose-bid on given records
+//   score_kernel    K4: base-score over (contract, tricks) tables
+//   imps_kernel     K4: match-points
+//   score_tally_kernel  K4 fused drill tally
+//   int_peak_kernel INT32 issue-rate microbenchmark (roofline denominator)
+// Nothing here is a contraction, so no tensor cores; the binding resource is
+// integer issue.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bridgemc.h"
+#include "deal.cuh"
+#include "features.cuh"
+#include "rules.hpp"
+
+using namespace bmc;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(BMC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device-side constraint / tally layout
+// ---------------------------------------------------------------------------
+struct ConsDev {
+    SeatC seat[4];
+    uint32_t n_active;       // number of constrained seats
+    uint32_t primary;        // seat tested in stage A
+    uint32_t pad[2];
+    const uint32_t *code;    // device pointer, programs of all seats
+};
+
+// shared-memory histogram (per warp): hcp[4][40] | len[4][4][16] | shape[4][40]
+constexpr int SH_HCP = 0, SH_LEN = 160, SH_SHAPE = 160 + 256, SH_WORDS = 160 + 256 + 160;
+constexpr int WARPS_PER_BLOCK = 8, THREADS = WARPS_PER_BLOCK * 32;
+constexpr int QCAP = 64;     // per-warp queue of stage-A survivors
+
+__constant__ uint8_t c_shape_lut[14 * 14 * 14];   // (len_c, len_d, len_h) -> sorted-shape class
+
+struct SampleArgs {
+    ConsDev cons;
+    PhiloxKey key;
+    uint64_t first, n;
+    uint4 *records;          // may be null
+    uint64_t cap;
+    unsigned long long *tallies;   // bmc_tallies as u64 words
+    uint32_t tally_mask;
+    uint32_t iters;          // warp-iterations per warp
+};
+
+__device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0, uint32_t &m1)
+{
+    const uint32_t xl = (k & 1) ? 0u : 0xFFFFFFFFu, xh = (k & 2) ? 0u : 0xFFFFFFFFu;
+    m0 = (pl.lo0 ^ xl) & (pl.hi0 ^ xh) & 0x1FFF1FFFu;
+    m1 = (pl.lo1 ^ xl) & (pl.hi1 ^ xh) & 0x1FFF1FFFu;
+}
+
+// Stage B: full test of every constrained seat, tallies, compacted store.
+__device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
+                                        const uint8_t *shape_lut, unsigned lane, unsigned long long &n_acc)
+{
+    bool ok = active;
+    Feat f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t m0, m1;
+        seat_words(pl, k, m0, m1);
+        f[k] = hand_features(m0, m1);
+        const SeatC &c = a.cons.seat[k];
+        if (c.active) {
+            ok = ok && seat_ranges_ok(c, f[k]);
+            if (c.prog != 0xFFFFFFFFu) {
+                bool err = false;
+                const bool v = run_program(a.cons.code + c.prog, f[k], err);
+                ok = ok && v && !err;
+            }
+        }
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+    if (bal == 0u) return;
+    const unsigned cnt = __popc(bal);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&a.tallies[2], (unsigned long long)cnt);      // accepted (also the slot cursor)
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    n_acc += lane == 0 ? cnt : 0;
+    if (ok) {
+        const unsigned long long slot = base + __popc(bal & ((1u << lane) - 1u));
+        if (a.records != nullptr && slot < a.cap) a.records[slot] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+        if (a.tally_mask) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (a.tally_mask & BMC_TALLY_HCP) atomicAdd(&hist[SH_HCP + k * 40 + (f[k].f2 & 0xFFu)], 1u);
+                if (a.tally_mask & BMC_TALLY_LEN) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) atomicAdd(&hist[SH_LEN + (k * 4 + s) * 16 + ((f[k].f0 >> (8 * s)) & 0xFFu)], 1u);
+                }
+                if (a.tally_mask & BMC_TALLY_SHAPE) {
+                    const uint32_t L = f[k].f0;
+                    const uint32_t cls = shape_lut[(L & 0xFFu) * 196u + ((L >> 8) & 0xFFu) * 14u + ((L >> 16) & 0xFFu)];
+                    atomicAdd(&hist[SH_SHAPE + k * 40 + cls], 1u);
+                }
+            }
+        }
+    }
+}
+
+template <bool HAS_CONS>
+__global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__ SampleArgs a)
+{
+    __shared__ uint32_t s_hist[WARPS_PER_BLOCK][SH_WORDS];
+    __shared__ uint4 s_queue[HAS_CONS ? WARPS_PER_BLOCK : 1][QCAP];
+    __shared__ uint8_t s_shape[14 * 14 * 14];
+
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < WARPS_PER_BLOCK * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
+    __syncthreads();
+
+    uint32_t *hist = s_hist[warp];
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
+    unsigned long long n_raw = 0, n_void = 0, n_acc = 0;
+    unsigned q_head = 0, q_tail = 0;          // warp-uniform
+
+    for (uint32_t it = 0; it < a.iters; ++it) {
+        const unsigned long long off = ((unsigned long long)it * total_warps + gwarp) * 32ull + lane;
+        const bool valid = off < a.n;
+        const unsigned long long idx = a.first + off;
+        Planes pl;
+        const bool voided = deal52(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
+        n_raw += valid ? 1u : 0u;
+        n_void += (valid && voided) ? 1u : 0u;
+        bool ok = valid && !voided;
+        if (HAS_CONS) {
+            // Stage A: cheap range test of the primary seat
+            const SeatC &c = a.cons.seat[a.cons.primary];
+            uint32_t m0, m1;
+            seat_words(pl, (int)a.cons.primary, m0, m1);
+            const Feat f = hand_features(m0, m1);
+            ok = ok && seat_ranges_ok(c, f);
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+            if (bal) {
+                if (ok) {
+                    const unsigned pos = (q_tail + __popc(bal & ((1u << lane) - 1u))) % QCAP;
+                    s_queue[warp][pos] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+                }
+                q_tail += __popc(bal);
+                __syncwarp();
+                if (q_tail - q_head >= 32u) {
+                    const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
+                    q_head += 32u;
+                    __syncwarp();
+                    Planes p2 = {r.x, r.y, r.z, r.w};
+                    stage_b(a, p2, true, hist, s_shape, lane, n_acc);
+                }
+            }
+        } else {
+            stage_b(a, pl, ok, hist, s_shape, lane, n_acc);
+        }
+    }
+    if (HAS_CONS) {
+        const unsigned left = q_tail - q_head;       // < 32
+        if (left) {
+            const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
+            Planes p2 = {r.x, r.y, r.z, r.w};
+            stage_b(a, p2, lane < left, hist, s_shape, lane, n_acc);
+        }
+    }
+
+    // flush counters and histograms
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_raw += __shfl_xor_sync(0xFFFFFFFFu, n_raw, o);
+        n_void += __shfl_xor_sync(0xFFFFFFFFu, n_void, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.tallies[0], n_raw);
+        if (n_void) atomicAdd(&a.tallies[1], n_void);
+    }
+    __syncthreads();
+    if (a.tally_mask) {
+        for (int i = threadIdx.x; i < SH_WORDS; i += THREADS) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS_PER_BLOCK; ++w) v += s_hist[w][i];
+            if (v == 0u) continue;
+            // map the padded shared layout to bmc_tallies words
+            int word;
+            if (i < SH_LEN) word = 4 + i;                                            // hcp[4][40]
+            else if (i < SH_SHAPE) {
+                const int j = i - SH_LEN, bin = j & 15;
+                if (bin >= BMC_LEN_BINS) continue;
+                word = 4 + 160 + (j >> 4) * BMC_LEN_BINS + bin;                       // len[4][4][14]
+            } else word = 4 + 160 + 224 + (i - SH_SHAPE);                            // shape[4][40]
+            atomicAdd(&a.tallies[word], (unsigned long long)v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: features / accept / choose-bid on given records
+// ---------------------------------------------------------------------------
+struct SchemeDev {
+    const uint32_t *code;
+    const uint32_t *row_off;     // offsets into code, n_rows entries
+    uint32_t n_rows;
+};
+
+__global__ void __launch_bounds__(256) filter_kernel(const __grid_constant__ ConsDev cons, int has_cons,
+                                                     const __grid_constant__ SchemeDev sch, const uint4 *__restrict__ rec,
+                                                     unsigned long long n, uint8_t *__restrict__ accept,
+                                                     bmc_features *__restrict__ feats)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (live) r = rec[i];
+    const Planes pl = {r.x, r.y, r.z, r.w};
+    bool ok = true;
+    bmc_features out;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t m0, m1;
+        seat_words(pl, k, m0, m1);
+        const Feat f = hand_features(m0, m1);
+        if (has_cons) {
+            const SeatC &c = cons.seat[k];
+            if (c.active) {
+                ok = ok && seat_ranges_ok(c, f);
+                if (c.prog != 0xFFFFFFFFu) {
+                    bool err = false;
+                    const bool v = run_program(cons.code + c.prog, f, err);
+                    ok = ok && v && !err;
+                }
+            }
+        }
+        int bid = -1;
+        if (sch.n_rows) {
+            // choose-bid: first row whose form is true; -2 where the reference would
+            // signal an error before finding one
+            bool done = false;
+            for (uint32_t row = 0; row < sch.n_rows; ++row) {
+                bool err = false;
+                const bool v = run_program(sch.code + __ldg(sch.row_off + row), f, err);
+                if (!done) {
+                    if (err) { bid = -2; done = true; }
+                    else if (v) { bid = (int)row; done = true; }
+                }
+                if (__all_sync(0xFFFFFFFFu, done)) break;
+            }
+        }
+        bmc_seat_features &o = out.seat[k];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            o.len[s] = (uint8_t)((f.f0 >> (8 * s)) & 0xFFu);
+            o.suit_hcp[s] = (uint8_t)((f.f1 >> (8 * s)) & 0xFFu);
+        }
+        o.hcp = (uint8_t)(f.f2 & 0xFFu);
+        o.losers = (uint8_t)((f.f2 >> 8) & 0xFFu);
+        o.balanced = (uint8_t)((f.f2 >> 16) & 0xFFu);
+        o.bid = (int8_t)bid;
+    }
+    if (!live) return;
+    if (accept) accept[i] = ok ? 1 : 0;
+    if (feats) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&out);
+        uint4 *dst = reinterpret_cast<uint4 *>(feats + i);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4: scoring
+// ---------------------------------------------------------------------------
+// contract-score (bridge.cl:3045-3069), written out from the rules of the
+// reference text (incl. its non-standard branches)
+__host__ __device__ inline int contract_score_dev(int suit, int tricks, int vul, int dbl, int level)
+{
+    if (level == 0) level = tricks - 6 > 1 ? tricks - 6 : 1;
+    const int r = tricks - level - 6;
+    const int mult = dbl == 2 ? 4 : (dbl ? 2 : 1);
+    if (r < 0) {
+        if (!dbl) return r * (vul ? 100 : 50);
+        int pen;
+        if (vul) pen = -200 + 300 * (r + 1);
+        else pen = r >= -3 ? 100 + 200 * r : -800 + 300 * (r + 3);      // -100 -300 -500, then -1100 ...
+        return pen * (dbl == 2 ? 2 : 1);
+    }
+    const int per = suit <= 1 ? 20 : 30;
+    const int trick_pts = ((suit == 4 ? 10 : 0) + per * level) * mult;
+    int bonus;
+    if (level == 7) bonus = vul ? 2000 : 1300;
+    else if (level == 6) bonus = vul ? 1250 : 800;
+    else bonus = trick_pts >= 100 ? (vul ? 500 : 300) : 50;
+    const int over = dbl ? (dbl == 2 ? 100 : 50) + (vul ? 200 : 100) * r : per * r;
+    return trick_pts + bonus + over;
+}
+__host__ __device__ inline int base_score_dev(bmc_contract c, int tricks, int vul)
+{
+    const int s = contract_score_dev(c.suit, tricks, vul, c.dbl, c.level);
+    return (c.declarer == 1 || c.declarer == 3) ? -s : s;
+}
+__constant__ int c_imp_pts[24] = {20, 50, 90, 130, 170, 220, 270, 320, 370, 430, 500, 600, 750, 900,
+                                  1100, 1300, 1500, 1750, 2000, 2300, 2500, 3000, 3500, 4000};
+__device__ __forceinline__ int imps_dev(int diff, bool &bad)
+{
+    const int a = diff < 0 ? -diff : diff;
+    int pos = 24;
+#pragma unroll
+    for (int i = 23; i >= 0; --i) if (a < c_imp_pts[i]) pos = i;
+    bad = pos == 24;
+    return bad ? 0 : (diff < 0 ? -pos : pos);
+}
+
+struct ContractTable { bmc_contract c[8]; uint8_t vul[8]; uint8_t pairs[16]; uint32_t n, n_pairs; };
+
+__global__ void __launch_bounds__(256) score_kernel(const bmc_contract *__restrict__ contracts, const uint8_t *__restrict__ vul,
+                                                    uint32_t nc, const uint8_t *__restrict__ tricks, unsigned long long total,
+                                                    int32_t *__restrict__ scores)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t c = (uint32_t)(i % nc);
+        scores[i] = base_score_dev(contracts[c], tricks[i], vul ? vul[c] : 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) imps_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b,
+                                                   unsigned long long n, int8_t *__restrict__ imps, uint8_t *__restrict__ status)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool bad;
+        const int v = imps_dev(a[i] - b[i], bad);
+        imps[i] = (int8_t)v;
+        if (status) status[i] = bad ? 1 : 0;
+    }
+}
+
+// tricks for deal `idx`, contract c: 16-bit lane c of Philox(stream 1), mapped to
+// 0..13 by multiply-shift; lanes whose low product part is < 65536 mod 14 (=2)
+// are biased and take the next lane (8..15) instead.
+__global__ void __launch_bounds__(256) score_tally_kernel(const __grid_constant__ ContractTable t, const __grid_constant__ PhiloxKey key,
+                                                          unsigned long long first, unsigned long long n,
+                                                          unsigned long long *__restrict__ tricks_hist,
+                                                          unsigned long long *__restrict__ imp_hist)
+{
+    __shared__ uint32_t s_tr[8 * 14];
+    __shared__ uint32_t s_imp[8 * 49];
+    __shared__ int s_score[8 * 14];
+    for (int i = threadIdx.x; i < 8 * 14; i += blockDim.x) {
+        s_tr[i] = 0;
+        const int c = i / 14;
+        s_score[i] = c < (int)t.n ? base_score_dev(t.c[c], i % 14, t.vul[c]) : 0;
+    }
+    for (int i = threadIdx.x; i < 8 * 49; i += blockDim.x) s_imp[i] = 0;
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long idx = first + i;
+        uint32_t w[4];
+        philox4x32_10(key, (uint32_t)idx, (uint32_t)(idx >> 32), 0u, 1u, w);
+        int tr[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t lane16 = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+            uint32_t prod = lane16 * 14u;
+            if ((prod & 0xFFFFu) < 2u) {       // biased lane: deterministic redraw from a second block
+                uint32_t w2[4];
+                philox4x32_10(key, (uint32_t)idx, (uint32_t)(idx >> 32), 1u + c, 1u, w2);
+                prod = (w2[0] >> 16) * 14u;    // residual bias 2^-16 * 2/65536 -- below any observable level
+            }
+            tr[c] = (int)(prod >> 16);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < (int)t.n) atomicAdd(&s_tr[c * 14 + tr[c]], 1u);
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+            if (p < (int)t.n_pairs) {
+                const int ca = t.pairs[2 * p], cb = t.pairs[2 * p + 1];
+                bool bad;
+                const int v = imps_dev(s_score[ca * 14 + tr[ca]] - s_score[cb * 14 + tr[cb]], bad);
+                if (!bad) atomicAdd(&s_imp[p * 49 + 24 + v], 1u);
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 14; i += blockDim.x)
+        if (s_tr[i]) atomicAdd(&tricks_hist[i], (unsigned long long)s_tr[i]);
+    for (int i = threadIdx.x; i < 8 * 49; i += blockDim.x)
+        if (s_imp[i]) atomicAdd(&imp_hist[i], (unsigned long long)s_imp[i]);
+}
+
+// ---------------------------------------------------------------------------
+// INT32 issue-rate microbenchmark: per thread, 8 independent chains mixing the
+// fma pipe (IMAD) and the alu pipe (LOP3 / IADD3), the two pipes the deal uses.
+// ---------------------------------------------------------------------------
+constexpr int PEAK_ITERS = 4096, PEAK_OPS_PER_ITER = 32;
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t seed, uint32_t *out)
+{
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u;
+    uint32_t b0 = a0 ^ 0x1234u, b1 = a1 ^ 0x5678u, b2 = a2 ^ 0x9ABCu, b3 = a3 ^ 0xDEF0u;
+#pragma unroll 1
+    for (int i = 0; i < PEAK_ITERS; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a0 = a0 * 0x010101u + b0; b0 = b0 ^ a1 ^ 0x9E3779B9u;
+            a1 = a1 * 0x010103u + b1; b1 = b1 ^ a2 ^ 0x7F4A7C15u;
+            a2 = a2 * 0x010105u + b2; b2 = b2 ^ a3 ^ 0x85EBCA6Bu;
+            a3 = a3 * 0x010107u + b3; b3 = b3 ^ a0 ^ 0xC2B2AE35u;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
+}
+
+// ---------------------------------------------------------------------------
+// host objects
+// ---------------------------------------------------------------------------
+struct bmc_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long *d_tallies = nullptr;     // scratch tallies for the host-buffer API
+    uint64_t launches = 0;
+    int blocks_cons = 0, blocks_free = 0;
+    std::mutex mu;
+};
+
+struct bmc_constraints {
+    ConsDev dev{};               // dev.code filled lazily per device
+    std::vector<uint32_t> code;
+    uint32_t *d_code = nullptr;
+    int d_device = -1;
+    bool has_cons = false;
+    bool has_fixed = false;
+    std::mutex mu;
+};
+
+struct bmc_scheme {
+    std::vector<uint32_t> code, row_off;
+    std::vector<std::string> bids;
+    uint32_t *d_code = nullptr, *d_off = nullptr;
+    int d_device = -1;
+    std::mutex mu;
+};
+
+static std::once_flag g_lut_once[16];
+static uint8_t g_shapes[39][4];
+static uint8_t g_shape_lut[14 * 14 * 14];
+static std::once_flag g_shape_once;
+
+static void init_shapes()
+{
+    int n = 0;
+    for (int a = 4; a <= 13; ++a)
+        for (int b = 0; b <= a; ++b)
+            for (int c = 0; c <= b; ++c) {
+                const int d = 13 - a - b - c;
+                if (d < 0 || d > c) continue;
+                g_shapes[n][0] = (uint8_t)a; g_shapes[n][1] = (uint8_t)b; g_shapes[n][2] = (uint8_t)c; g_shapes[n][3] = (uint8_t)d;
+                ++n;
+            }
+    memset(g_shape_lut, 0xFF, sizeof g_shape_lut);
+    for (int x = 0; x <= 13; ++x)
+        for (int y = 0; x + y <= 13; ++y)
+            for (int z = 0; x + y + z <= 13; ++z) {
+                int v[4] = {x, y, z, 13 - x - y - z};
+                for (int i = 0; i < 4; ++i)
+                    for (int j = i + 1; j < 4; ++j)
+                        if (v[j] > v[i]) { int t = v[i]; v[i] = v[j]; v[j] = t; }
+                for (int k = 0; k < 39; ++k)
+                    if (g_shapes[k][0] == v[0] && g_shapes[k][1] == v[1] && g_shapes[k][2] == v[2] && g_shapes[k][3] == v[3])
+                        g_shape_lut[x * 196 + y * 14 + z] = (uint8_t)k;
+            }
+}
+
+extern "C" {
+
+const char *bmc_last_error(void) { return g_err.c_str(); }
+const char *bmc_version(void) { return "bridgemc 0.1 (sm_100a)"; }
+
+void bmc_shape_table(uint8_t out[39][4])
+{
+    std::call_once(g_shape_once, init_shapes);
+    memcpy(out, g_shapes, sizeof g_shapes);
+}
+
+int bmc_init(int device, bmc_ctx **out)
+{
+    if (!out) return fail(BMC_E_INVALID, "bmc_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BMC_E_CUDA, std::string("no CUDA device (") + cudaGetErrorString(e) + "); libbridgemc has no CPU fallback");
+    if (device < 0 || device >= count) return fail(BMC_E_INVALID, "bmc_init: device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    std::call_once(g_shape_once, init_shapes);
+    bmc_ctx *c = new bmc_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaMalloc(&c->d_tallies, sizeof(bmc_tallies)));
+    if (device < 16) {
+        cudaError_t le = cudaSuccess;
+        std::call_once(g_lut_once[device], [&] { le = cudaMemcpyToSymbol(c_shape_lut, g_shape_lut, sizeof g_shape_lut); });
+        if (le != cudaSuccess) return fail(BMC_E_CUDA, std::string("shape LUT upload: ") + cudaGetErrorString(le));
+    } else {
+        CUDA_TRY(cudaMemcpyToSymbol(c_shape_lut, g_shape_lut, sizeof g_shape_lut));
+    }
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<true>, THREADS, 0));
+    c->blocks_cons = c->sms * (occ > 0 ? occ : 1);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<false>, THREADS, 0));
+    c->blocks_free = c->sms * (occ > 0 ? occ : 1);
+    *out = c;
+    return BMC_OK;
+}
+
+void bmc_shutdown(bmc_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tallies);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int bmc_set_stream(bmc_ctx *c, void *s)
+{
+    if (!c) return fail(BMC_E_INVALID, "ctx is NULL");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return BMC_OK;
+}
+
+uint64_t bmc_launch_count(const bmc_ctx *c) { return c ? c->launches : 0; }
+
+void *bmc_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+void bmc_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- constraints ------------------------------------------------------------
+static int spec_to_ranges(const bmc_seat_spec &sp, SeatRanges &r, std::string &why)
+{
+    auto apply = [&](int f, int lo, int hi, int cap) {
+        if (lo >= 0 && lo > r.lo[f]) r.lo[f] = lo;
+        if (hi >= 0 && hi < r.hi[f]) r.hi[f] = hi;
+        (void)cap;
+    };
+    apply(F_HCP, sp.hcp[0], sp.hcp[1], 37);
+    for (int s = 0; s < 4; ++s) {
+        apply(F_C + s, sp.len[s][0], sp.len[s][1], 13);
+        apply(F_CP + s, sp.suit_hcp[s][0], sp.suit_hcp[s][1], 10);
+    }
+    apply(F_LOS, sp.losers[0], sp.losers[1], 12);
+    for (int f = 0; f < F_BAL; ++f)
+        if (r.lo[f] > r.hi[f]) {
+            why = "empty range for feature " + std::to_string(f) + ": <" + std::to_string(r.lo[f]) + "-" + std::to_string(r.hi[f]) + ">";
+            return BMC_E_BAD_RANGE;
+        }
+    return BMC_OK;
+}
+
+static void ranges_to_seatc(const SeatRanges &r, SeatC &c)
+{
+    int lo[12], hi[12];
+    for (int f = 0; f < 12; ++f) { lo[f] = 0; hi[f] = 127; }
+    for (int f = 0; f < F_BAL; ++f) { lo[f] = r.lo[f]; hi[f] = r.hi[f] > 127 ? 127 : r.hi[f]; }
+    lo[F_BAL] = r.bal_req == 1 ? 1 : 0;
+    hi[F_BAL] = r.bal_req == 2 ? 0 : 1;
+    c.need = 0;
+    for (int w = 0; w < 3; ++w) {
+        uint32_t A = 0, B = 0;
+        for (int b = 0; b < 4; ++b) {
+            const int f = 4 * w + b;
+            A |= (uint32_t)(0x80 - lo[f]) << (8 * b);
+            B |= (uint32_t)(0x7F - hi[f]) << (8 * b);
+        }
+        c.A[w] = A;
+        c.B[w] = B;
+    }
+}
+
+int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules[4], bmc_constraints **out)
+{
+    if (!out) return fail(BMC_E_INVALID, "out is NULL");
+    *out = nullptr;
+    std::unique_ptr<bmc_constraints> c(new bmc_constraints());
+    RuleCompiler rc;
+    uint64_t fixed_union = 0;
+    int total_lo[F_COUNT] = {0};
+    double selectivity[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) {
+        SeatC &sc = c->dev.seat[k];
+        sc.prog = 0xFFFFFFFFu;
+        sc.active = 0;
+        SeatRanges r;
+        bool has_spec = false;
+        if (specs) {
+            const bmc_seat_spec &sp = specs[k];
+            if (sp.fixed) {
+                if ((sp.fixed_mask & ~BMC_LANE_MASK) || __builtin_popcountll(sp.fixed_mask) != 13)
+                    return fail(BMC_E_INVALID, "fixed hand of seat " + std::to_string(k) + " is not 13 cards in lane-mask layout");
+                if (sp.fixed_mask & fixed_union) return fail(BMC_E_INVALID, "fixed hands overlap");
+                fixed_union |= sp.fixed_mask;
+                c->has_fixed = true;
+            }
+            std::string why;
+            int rcode = spec_to_ranges(sp, r, why);
+            if (rcode != BMC_OK) return fail(rcode, "seat " + std::to_string(k) + ": " + why);
+            for (int f = 0; f < F_BAL; ++f) if (r.lo[f] > 0 || r.hi[f] < 63) has_spec = true;
+        }
+        bool has_rule = rules && rules[k] && rules[k][0];
+        bool exact = true;
+        if (has_rule) {
+            try {
+                SxReader rd(rules[k]);
+                Sx form = rd.read();
+                if (form.is_list() && form.items.size() == 2 && form.items[0].is_sym("QUOTE")) form = form.items[1];
+                std::vector<uint32_t> code;
+                rc.compile(form, code, &r, &exact);
+                if (!exact) {
+                    sc.prog = (uint32_t)c->code.size();
+                    c->code.insert(c->code.end(), code.begin(), code.end());
+                }
+            } catch (const RuleError &e) {
+                return fail(BMC_E_PARSE, "seat " + std::to_string(k) + " rule: " + e.what());
+            }
+            if (r.empty())
+                return fail(BMC_E_BAD_RANGE, "seat " + std::to_string(k) + ": rule and ranges exclude every hand");
+        }
+        // clamp to what a 13-card hand can hold (keeps the byte arithmetic in range)
+        for (int s = 0; s < 4; ++s) { if (r.hi[F_C + s] > 13) r.hi[F_C + s] = 13; if (r.hi[F_CP + s] > 10) r.hi[F_CP + s] = 10; }
+        if (r.hi[F_HCP] > 37) r.hi[F_HCP] = 37;
+        if (r.hi[F_LOS] > 12) r.hi[F_LOS] = 12;
+        if (r.empty()) return fail(BMC_E_BAD_RANGE, "seat " + std::to_string(k) + ": empty range");
+        ranges_to_seatc(r, sc);
+        sc.active = (has_spec || has_rule) ? 1u : 0u;
+        if (sc.active) {
+            c->has_cons = true;
+            c->dev.n_active++;
+            // crude selectivity score for choosing the stage-A seat: narrower hcp and
+            // length windows reject more
+            double sel = (double)(r.hi[F_HCP] - r.lo[F_HCP] + 1) / 38.0;
+            for (int s = 0; s < 4; ++s) sel *= (double)(r.hi[F_C + s] - r.lo[F_C + s] + 1) / 14.0;
+            if (r.bal_req) sel *= 0.5;
+            selectivity[k] = sel;
+            for (int f = 0; f < F_BAL; ++f) total_lo[f] += r.lo[f];
+        }
+    }
+    // necessary joint conditions (the sums the reference's infer-* narrow with,
+    // bridge.cl:1126-1234): minimum HCP over all seats <= 40, minimum lengths <= 13
+    if (total_lo[F_HCP] > 40) return fail(BMC_E_BAD_RANGE, "Can't infer correct limit!: minimum HCP of the seats exceeds 40");
+    for (int s = 0; s < 4; ++s)
+        if (total_lo[F_C + s] > 13) return fail(BMC_E_BAD_RANGE, "Can't infer correct limit!: minimum suit lengths exceed 13");
+    c->dev.primary = 0;
+    double best = 2.0;
+    for (int k = 0; k < 4; ++k)
+        if (c->dev.seat[k].active && selectivity[k] < best) { best = selectivity[k]; c->dev.primary = (uint32_t)k; }
+    c->code.push_back(enc(OP_END));
+    *out = c.release();
+    return BMC_OK;
+}
+
+void bmc_constraints_destroy(bmc_constraints *c)
+{
+    if (!c) return;
+    if (c->d_code) { cudaSetDevice(c->d_device); cudaFree(c->d_code); }
+    delete c;
+}
+
+static int cons_upload(bmc_ctx *ctx, const bmc_constraints *cc, ConsDev &dev)
+{
+    bmc_constraints *c = const_cast<bmc_constraints *>(cc);
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->d_code && c->d_device != ctx->device) {
+        cudaSetDevice(c->d_device);
+        cudaFree(c->d_code);
+        c->d_code = nullptr;
+        cudaSetDevice(ctx->device);
+    }
+    if (!c->d_code) {
+        CUDA_TRY(cudaMalloc(&c->d_code, c->code.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(c->d_code, c->code.data(), c->code.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        c->d_device = ctx->device;
+    }
+    dev = c->dev;
+    dev.code = c->d_code;
+    return BMC_OK;
+}
+
+// ---- schemes ------------------------------------------------------------------
+int bmc_scheme_create(const char *table, bmc_scheme **out)
+{
+    if (!out || !table) return fail(BMC_E_INVALID, "bmc_scheme_create: NULL argument");
+    *out = nullptr;
+    try {
+        SchemeRows rows = compile_scheme(table);
+        std::unique_ptr<bmc_scheme> s(new bmc_scheme());
+        for (size_t i = 0; i < rows.progs.size(); ++i) {
+            s->row_off.push_back((uint32_t)s->code.size());
+            s->code.insert(s->code.end(), rows.progs[i].begin(), rows.progs[i].end());
+        }
+        s->bids = rows.bids;
+        if (s->row_off.size() > 120) return fail(BMC_E_CAPACITY, "rule table has more than 120 rows");
+        *out = s.release();
+    } catch (const RuleError &e) {
+        return fail(BMC_E_PARSE, std::string("rule table: ") + e.what());
+    }
+    return BMC_OK;
+}
+int bmc_scheme_size(const bmc_scheme *s) { return s ? (int)s->row_off.size() : 0; }
+void bmc_scheme_destroy(bmc_scheme *s)
+{
+    if (!s) return;
+    if (s->d_code) { cudaSetDevice(s->d_device); cudaFree(s->d_code); cudaFree(s->d_off); }
+    delete s;
+}
+static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
+{
+    dev.code = nullptr; dev.row_off = nullptr; dev.n_rows = 0;
+    if (!ss || ss->row_off.empty()) return BMC_OK;
+    bmc_scheme *s = const_cast<bmc_scheme *>(ss);
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->d_code && s->d_device != ctx->device) {
+        cudaSetDevice(s->d_device);
+        cudaFree(s->d_code); cudaFree(s->d_off);
+        s->d_code = s->d_off = nullptr;
+        cudaSetDevice(ctx->device);
+    }
+    if (!s->d_code) {
+        CUDA_TRY(cudaMalloc(&s->d_code, s->code.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&s->d_off, s->row_off.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(s->d_code, s->code.data(), s->code.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_off, s->row_off.data(), s->row_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        s->d_device = ctx->device;
+    }
+    dev.code = s->d_code; dev.row_off = s->d_off; dev.n_rows = (uint32_t)s->row_off.size();
+    return BMC_OK;
+}
+
+// ---- sampling -------------------------------------------------------------------
+static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, uint64_t seed, uint64_t first, uint64_t n,
+                       uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev)
+{
+    SampleArgs a;
+    a.cons = cons;
+    a.key = philox_key(seed);
+    a.first = first;
+    a.n = n;
+    a.records = (uint4 *)records_dev;
+    a.cap = records_dev ? cap : 0;
+    a.tallies = (unsigned long long *)tallies_dev;
+    a.tally_mask = tally_mask;
+    int blocks = has_cons ? ctx->blocks_cons : ctx->blocks_free;
+    const uint64_t per_iter = (uint64_t)blocks * THREADS;
+    if (n < per_iter) blocks = (int)((n + THREADS - 1) / THREADS);
+    if (blocks < 1) blocks = 1;
+    const uint64_t chunk = (uint64_t)blocks * THREADS;
+    a.iters = (uint32_t)((n + chunk - 1) / chunk);
+    if (has_cons) sample_kernel<true><<<blocks, THREADS, 0, ctx->stream>>>(a);
+    else sample_kernel<false><<<blocks, THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BMC_OK;
+}
+
+int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                   uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records_dev, uint64_t cap,
+                   void *tallies_dev, bmc_stats *stats)
+{
+    if (!ctx || !tallies_dev) return fail(BMC_E_INVALID, "bmc_sample_dev: ctx / tallies_dev is NULL");
+    if (cons && cons->has_fixed) return fail(BMC_E_INVALID, "fixed (:=) hands are not supported by the sampling kernel yet");
+    if (n_accept_target == 0 && n_raw == 0) return fail(BMC_E_INVALID, "nothing to do: n_raw == 0 and no accept target");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    auto t0 = std::chrono::steady_clock::now();
+    ConsDev dev{};
+    const bool has_cons = cons && cons->has_cons;
+    if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
+    if (wave == 0) wave = 1ull << 26;
+    uint32_t waves = 0;
+    uint64_t launches0 = ctx->launches;
+    unsigned long long head[4] = {0, 0, 0, 0}, start_acc = 0;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (n_accept_target == 0) {
+        // split only so that a warp's iteration counter stays 32-bit and launches stay bounded
+        uint64_t done = 0;
+        const uint64_t max_launch = 1ull << 36;
+        while (done < n_raw) {
+            const uint64_t n = n_raw - done < max_launch ? n_raw - done : max_launch;
+            int rc = launch_wave(ctx, dev, has_cons, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
+            if (rc) return rc;
+            done += n;
+            ++waves;
+        }
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        start_acc = head[2];
+        uint64_t done = 0;
+        for (;;) {
+            if (n_raw && done >= n_raw) break;
+            uint64_t n = wave;
+            if (n_raw && n_raw - done < n) n = n_raw - done;
+            int rc = launch_wave(ctx, dev, has_cons, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
+            if (rc) return rc;
+            done += n;
+            ++waves;
+            CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (head[2] - start_acc >= n_accept_target) break;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        stats->raw = head[0]; stats->voided = head[1]; stats->accepted = head[2];
+        stats->stored = records_dev ? (head[2] < cap ? head[2] : cap) : 0;
+        stats->waves = waves;
+        stats->launches = (uint32_t)(ctx->launches - launches0);
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return BMC_OK;
+}
+
+int bmc_sample(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+               uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, bmc_record *records, uint64_t cap,
+               bmc_tallies *tallies, bmc_stats *stats)
+{
+    if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
+    auto t0 = std::chrono::steady_clock::now();
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    void *d_rec = nullptr;
+    if (records && cap) CUDA_TRY(cudaMalloc(&d_rec, cap * sizeof(bmc_record)));
+    unsigned long long *d_tal = nullptr;
+    CUDA_TRY(cudaMalloc(&d_tal, sizeof(bmc_tallies)));
+    cudaMemsetAsync(d_tal, 0, sizeof(bmc_tallies), ctx->stream);
+    bmc_stats st{};
+    int rc = bmc_sample_dev(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, d_rec, cap, d_tal, &st);
+    if (rc == BMC_OK) {
+        cudaError_t e = cudaSuccess;
+        if (d_rec && st.stored) e = cudaMemcpyAsync(records, d_rec, st.stored * sizeof(bmc_record), cudaMemcpyDeviceToHost, ctx->stream);
+        bmc_tallies host_t;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&host_t, d_tal, sizeof host_t, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(BMC_E_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
+        else {
+            host_t.stored = st.stored;
+            if (tallies) *tallies = host_t;
+        }
+    }
+    cudaFree(d_rec);
+    cudaFree(d_tal);
+    if (stats && rc == BMC_OK) {
+        *stats = st;
+        stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return rc;
+}
+
+// ---- filter ---------------------------------------------------------------------
+int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme, const bmc_record *records, uint64_t n,
+               uint8_t *accept, bmc_features *feats)
+{
+    if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
+    if (n == 0) return BMC_OK;
+    if (!records) return fail(BMC_E_INVALID, "records is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ConsDev dev{};
+    const bool has_cons = cons && cons->has_cons;
+    if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
+    SchemeDev sd;
+    { int rc = scheme_upload(ctx, scheme, sd); if (rc) return rc; }
+    const uint64_t chunk = 1ull << 22;       // bounded device footprint: 4 Mi deals per pass
+    uint4 *d_rec = nullptr;
+    uint8_t *d_acc = nullptr;
+    bmc_features *d_feat = nullptr;
+    const uint64_t m = n < chunk ? n : chunk;
+    CUDA_TRY(cudaMalloc(&d_rec, m * sizeof(uint4)));
+    cudaError_t e = cudaSuccess;
+    if (accept) e = cudaMalloc(&d_acc, m);
+    if (e == cudaSuccess && feats) e = cudaMalloc(&d_feat, m * sizeof(bmc_features));
+    int rc = BMC_OK;
+    for (uint64_t off = 0; off < n && e == cudaSuccess; off += chunk) {
+        const uint64_t k = n - off < chunk ? n - off : chunk;
+        e = cudaMemcpyAsync(d_rec, records + off, k * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) break;
+        filter_kernel<<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(dev, has_cons ? 1 : 0, sd, d_rec, k, d_acc, d_feat);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess && accept) e = cudaMemcpyAsync(accept + off, d_acc, k, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && feats) e = cudaMemcpyAsync(feats + off, d_feat, k * sizeof(bmc_features), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) rc = fail(BMC_E_CUDA, std::string("bmc_filter: ") + cudaGetErrorString(e));
+    cudaFree(d_rec); cudaFree(d_acc); cudaFree(d_feat);
+    return rc;
+}
+
+// ---- scoring --------------------------------------------------------------------
+static int check_contracts(const bmc_contract *c, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; ++i)
+        if (c[i].level < 0 || c[i].level > 7 || c[i].suit < 0 || c[i].suit > 4 || c[i].dbl < 0 || c[i].dbl > 2 || c[i].declarer < -1 || c[i].declarer > 3)
+            return fail(BMC_E_INVALID, "contract " + std::to_string(i) + " out of range");
+    return BMC_OK;
+}
+
+int bmc_score(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulnerable, uint32_t nc, const uint8_t *tricks,
+              uint64_t n, int32_t *scores)
+{
+    if (!ctx || !contracts || !tricks || !scores || nc == 0) return fail(BMC_E_INVALID, "bmc_score: NULL argument");
+    if (n == 0) return BMC_OK;
+    { int rc = check_contracts(contracts, nc); if (rc) return rc; }
+    const uint64_t total = n * nc;
+    for (uint64_t i = 0; i < total; ++i) if (tricks[i] > 13) return fail(BMC_E_INVALID, "tricks out of 0..13");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    bmc_contract *d_c = nullptr; uint8_t *d_v = nullptr, *d_t = nullptr; int32_t *d_s = nullptr;
+    cudaError_t e = cudaMalloc(&d_c, nc * sizeof(bmc_contract));
+    if (e == cudaSuccess) e = cudaMalloc(&d_v, nc);
+    if (e == cudaSuccess) e = cudaMalloc(&d_t, total);
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, total * sizeof(int32_t));
+    std::vector<uint8_t> vul(nc, 0);
+    if (vulnerable) memcpy(vul.data(), vulnerable, nc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, contracts, nc * sizeof(bmc_contract), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, vul.data(), nc, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_t, tricks, total, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((total + 255) / 256 < (uint64_t)ctx->sms * 16 ? (total + 255) / 256 : (uint64_t)ctx->sms * 16);
+        score_kernel<<<blocks, 256, 0, ctx->stream>>>(d_c, d_v, nc, d_t, total, d_s);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores, d_s, total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_c); cudaFree(d_v); cudaFree(d_t); cudaFree(d_s);
+    if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("bmc_score: ") + cudaGetErrorString(e));
+    return BMC_OK;
+}
+
+int bmc_match_points(bmc_ctx *ctx, const int32_t *a, const int32_t *b, uint64_t n, int8_t *imps, uint8_t *status)
+{
+    if (!ctx || !a || !b || !imps) return fail(BMC_E_INVALID, "bmc_match_points: NULL argument");
+    if (n == 0) return BMC_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int32_t *d_a = nullptr, *d_b = nullptr; int8_t *d_i = nullptr; uint8_t *d_s = nullptr;
+    cudaError_t e = cudaMalloc(&d_a, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_b, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_i, n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_a, a, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, b, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((n + 255) / 256 < (uint64_t)ctx->sms * 16 ? (n + 255) / 256 : (uint64_t)ctx->sms * 16);
+        imps_kernel<<<blocks, 256, 0, ctx->stream>>>(d_a, d_b, n, d_i, d_s);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(imps, d_i, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_s, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_i); cudaFree(d_s);
+    if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("bmc_match_points: ") + cudaGetErrorString(e));
+    return BMC_OK;
+}
+
+int bmc_score_tally(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulnerable, uint32_t nc, const uint8_t *pairs,
+                    uint32_t n_pairs, uint64_t seed, uint64_t first_index, uint64_t n, uint64_t *tricks_hist, uint64_t *imp_hist,
+                    int32_t *score_table)
+{
+    if (!ctx || !contracts || nc == 0 || nc > 8 || n_pairs > 8 || !tricks_hist) return fail(BMC_E_INVALID, "bmc_score_tally: bad argument");
+    if (n_pairs && (!pairs || !imp_hist)) return fail(BMC_E_INVALID, "bmc_score_tally: pairs / imp_hist is NULL");
+    { int rc = check_contracts(contracts, nc); if (rc) return rc; }
+    ContractTable t{};
+    t.n = nc; t.n_pairs = n_pairs;
+    for (uint32_t i = 0; i < nc; ++i) { t.c[i] = contracts[i]; t.vul[i] = vulnerable ? vulnerable[i] : 0; }
+    for (uint32_t i = 0; i < 2 * n_pairs; ++i) {
+        if (pairs[i] >= nc) return fail(BMC_E_INVALID, "pair index out of range");
+        t.pairs[i] = pairs[i];
+    }
+    if (score_table)
+        for (uint32_t c = 0; c < nc; ++c)
+            for (int tr = 0; tr < 14; ++tr) score_table[c * 14 + tr] = base_score_dev(t.c[c], tr, t.vul[c]);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (8 * 14 + 8 * 49) * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, (8 * 14 + 8 * 49) * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess && n) {
+        uint64_t want = (n + 255) / 256;
+        const unsigned blocks = (unsigned)(want < (uint64_t)ctx->sms * 8 ? want : (uint64_t)ctx->sms * 8);
+        score_tally_kernel<<<blocks, 256, 0, ctx->stream>>>(t, philox_key(seed), first_index, n, d, d + 8 * 14);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    std::vector<unsigned long long> h(8 * 14 + 8 * 49);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("bmc_score_tally: ") + cudaGetErrorString(e));
+    for (uint32_t c = 0; c < nc; ++c)
+        for (int tr = 0; tr < 14; ++tr) tricks_hist[c * 14 + tr] = h[c * 14 + tr];
+    for (uint32_t p = 0; p < n_pairs; ++p)
+        for (int v = 0; v < 49; ++v) imp_hist[p * 49 + v] = h[8 * 14 + p * 49 + v];
+    return BMC_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------
+int bmc_int_peak(bmc_ctx *ctx, double *ops_per_s, float *ms_out)
+{
+    if (!ctx || !ops_per_s) return fail(BMC_E_INVALID, "bmc_int_peak: NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sms * 8;
+    uint32_t *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(uint32_t)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        int_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(12345u + rep, d);
+        ctx->launches++;
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d); return fail(BMC_E_CUDA, std::string("int_peak: ") + cudaGetErrorString(e)); }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    const double ops = (double)blocks * 256.0 * PEAK_ITERS * PEAK_OPS_PER_ITER;
+    *ops_per_s = ops / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return BMC_OK;
+}
+
+}  // extern "C"

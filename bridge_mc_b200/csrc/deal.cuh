@@ -1,0 +1,134 @@
+// deal.cuh -- Philox4x32-10 and the in-register 52-card deal (device side).
+//
+// Replaces the reference's `deal`/`take`/`deal-all` list shuffles
+// (bridge.cl:627-658): one thread draws one complete deal as two owner
+// bit-planes (4 x 32-bit registers), with no memory traffic and no dynamic
+// register indexing.
+//
+// Algorithm (mirrored bit-for-bit on the CPU by orc_gpu_deal in
+// oracle/bmc_oracle.c):
+//   * 3 Philox4x32-10 calls (key = seed, counter = (index_lo, index_hi, block, 0))
+//     give 12 random words.
+//   * Cards are dealt in id order (suit c..s, rank 2..A).  Card p (n = 52-p cards
+//     left) goes to seat k with probability remaining_k / n: a bounded draw
+//     u in [0,n) is compared with the running prefix sums of the remaining
+//     capacities.  This is the sequential form of a Fisher-Yates shuffle of the
+//     multiset N^13 E^13 S^13 W^13.
+//   * The 51 bounded draws are taken as mixed-radix digits of 12 words: word g
+//     yields the digits n = GRP_HI[g] .. GRP_LO[g] by successive 32x32->64
+//     multiplies (hi = digit, lo = next fraction).  The final low word is the
+//     Lemire remainder of x * N_g, N_g = prod n: if it is below 2^32 mod N_g the
+//     draw would be biased and the whole index is VOIDED (p = 0.48 %), so every
+//     surviving deal is exactly uniform over the 52!/(13!)^4 deals.
+//   * Owner bookkeeping is SWAR on one register Q whose bytes hold
+//     128 - prefix_j (j = 0..2): E = Q + u*0x010101 has bit 7 of byte j set iff
+//     u >= prefix_j; T7 = ~E & 0x808080 marks the prefixes that shrink.  Five
+//     instructions per card: IMAD.WIDE, IMAD, LOP3, 2 x LEA.HI.
+#pragma once
+#include <cstdint>
+
+namespace bmc {
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+struct PhiloxKey { uint32_t k0[10], k1[10]; };   // round keys, precomputed on the host
+
+__host__ __device__ inline PhiloxKey philox_key(uint64_t seed)
+{
+    PhiloxKey k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += PHILOX_W0; b += PHILOX_W1; }
+    return k;
+}
+
+__device__ __forceinline__ void philox4x32_10(const PhiloxKey &key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// digit groups (n = cards left when the card is dealt)
+__host__ __device__ constexpr int grp_hi(int g)
+{
+    constexpr int t[12] = {52, 48, 44, 40, 36, 32, 28, 24, 20, 16, 11, 5};
+    return t[g];
+}
+__host__ __device__ constexpr int grp_lo(int g)
+{
+    constexpr int t[12] = {49, 45, 41, 37, 33, 29, 25, 21, 17, 12, 6, 2};
+    return t[g];
+}
+__host__ __device__ constexpr int grp_of(int n)
+{
+    for (int g = 0; g < 12; ++g) if (n <= grp_hi(g) && n >= grp_lo(g)) return g;
+    return -1;
+}
+__host__ __device__ constexpr uint32_t grp_thresh(int g)
+{
+    uint64_t N = 1;
+    for (int n = grp_lo(g); n <= grp_hi(g); ++n) N *= (uint64_t)n;
+    return (uint32_t)((1ull << 32) % N);
+}
+
+struct Planes { uint32_t lo0, lo1, hi0, hi1; };   // lo plane (c,d | h,s), hi plane (c,d | h,s)
+
+// Returns true when the index is void.  caps_q = initial Q (bytes 128 - prefix_j).
+__device__ __forceinline__ bool deal52(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, Planes &pl)
+{
+    uint32_t w[4];
+    uint32_t x = 0;
+    uint32_t Q = (128u - 13u) | ((128u - 26u) << 8) | ((128u - 39u) << 16);
+    uint32_t acc = 0;
+    uint32_t lo[2] = {0u, 0u}, hi[2] = {0u, 0u};
+    bool voided = false;
+#pragma unroll
+    for (int p = 0; p < 52; ++p) {
+        const int n = 52 - p;
+        uint32_t u = 0;
+        if (n >= 2) {
+            const int g = grp_of(n);
+            if (n == grp_hi(g)) {
+                if ((g & 3) == 0) philox4x32_10(key, idx_lo, idx_hi, (uint32_t)(g >> 2), 0u, w);
+                x = w[g & 3];
+            }
+            uint64_t prod = (uint64_t)x * (uint32_t)n;
+            u = (uint32_t)(prod >> 32);
+            x = (uint32_t)prod;
+            if (n == grp_lo(g)) voided |= x < grp_thresh(g);
+        }
+        const uint32_t E = u * 0x010101u + Q;
+        const uint32_t T7 = ~E & 0x808080u;      // bit 7 of byte j: u < prefix_j
+        Q += T7 >> 7;
+        const int rank = p % 13, suit = p / 13;
+        const int i = rank < 8 ? rank : rank - 8;           // position inside the byte group
+        acc += T7 >> (7 - i);
+        if (rank == 7 || rank == 12) {
+            const uint32_t mask = rank == 7 ? 0xFFu : 0x1Fu;
+            const uint32_t par = acc ^ (acc >> 8) ^ (acc >> 16);
+            const uint32_t lob = ~par & mask;               // owner bit 0 = !(t0^t1^t2)
+            const uint32_t hib = ~(acc >> 8) & mask;        // owner bit 1 = !t1
+            const int sh = 16 * (suit & 1) + (rank == 7 ? 0 : 8);
+            lo[suit >> 1] |= lob << sh;
+            hi[suit >> 1] |= hib << sh;
+            acc = 0;
+        }
+    }
+    pl.lo0 = lo[0]; pl.lo1 = lo[1]; pl.hi0 = hi[0]; pl.hi1 = hi[1];
+    return voided;
+}
+
+// bounded draw helper for the score tally: uniform 0..13 from 16 random bits
+// (exact: 65536 mod 14 = 2 -> values below 2 in the low half are redrawn by the caller)
+}  // namespace bmc

@@ -1,0 +1,107 @@
+// features.cuh -- hand features, range test and the rule interpreter (device).
+//
+// Replaces assess-hand / suit-hcp / suit-loosers / balanced? (bidding.cl:20-46,
+// bridge.cl:667-670,2986-2987) and good-opening?'s sublis+eval (bidding.cl:60-74).
+// A seat's hand is two 32-bit words of 16-bit suit lanes (m0 = clubs|diamonds<<16,
+// m1 = hearts|spades<<16).  All eleven features are produced SWAR, one byte per
+// suit:
+//     f0 = lens   (bytes c d h s)         f1 = power / suit HCP (bytes c d h s)
+//     f2 = hcp | losers<<8 | balanced<<16
+#pragma once
+#include <cstdint>
+#include "rules.hpp"
+
+namespace bmc {
+
+struct Feat { uint32_t f0, f1, f2; };
+
+// Per-seat compiled constraint.  Range test on packed bytes: with
+// A = 0x80 - lo and B = 0x7F - hi per byte, v in [lo,hi] for every byte iff
+// ((v + A) & ~(v + B) & 0x80808080) == 0x80808080.
+struct SeatC {
+    uint32_t A[3], B[3];
+    uint32_t prog;          // offset of the seat's program in the code buffer, 0xFFFFFFFF = none
+    uint32_t active;        // 0: seat unconstrained
+    uint32_t need;          // bit0 lens ranged, bit1 power ranged, bit2 f2 ranged (incl. losers/balanced)
+    uint32_t pad;
+};
+
+__device__ __forceinline__ Feat hand_features(uint32_t m0, uint32_t m1)
+{
+    const uint32_t M = 0x01010101u;
+    // lengths
+    const uint32_t lc = __popc(m0 & 0xFFFFu), ld = __popc(m0 >> 16), lh = __popc(m1 & 0xFFFFu), ls = __popc(m1 >> 16);
+    const uint32_t L = lc | (ld << 8) | (lh << 16) | (ls << 24);
+    // honour nibbles (J Q K A = lane bits 9..12), one per byte in order c d h s
+    const uint32_t x0 = (m0 >> 9) & 0x000F000Fu;          // c at byte 0, d at byte 2
+    const uint32_t x1 = (m1 >> 9) & 0x000F000Fu;          // h at byte 0, s at byte 2
+    const uint32_t X = __byte_perm(x0, x1, 0x6420);       // bytes: c, d, h, s
+    const uint32_t J = X & M, Qn = (X >> 1) & M, K = (X >> 2) & M, A = (X >> 3) & M;
+    const uint32_t P = J + 2u * Qn + 3u * K + 4u * A;     // rank-hcp: J1 Q2 K3 A4, <= 10 per byte
+    const uint32_t hcp = (P * M) >> 24;
+    // losers (bidding.cl:20-23): [no A & len>=1] + [no K & len>=2] + [no Q & len>=3]
+    const uint32_t g1 = ((L + 0x7F7F7F7Fu) >> 7) & M;
+    const uint32_t g2 = ((L + 0x7E7E7E7Eu) >> 7) & M;
+    const uint32_t g3 = ((L + 0x7D7D7D7Du) >> 7) & M;
+    const uint32_t lb = (g1 & ~A) + (g2 & ~K) + (g3 & ~Qn);
+    const uint32_t losers = (lb * M) >> 24;
+    // balanced? (bidding.cl:40-46)
+    const bool shape_ok = g2 == M && ((L + 0x7B7B7A7Au) & 0x80808080u) == 0u;   // all >= 2; c,d <= 5; h,s <= 4
+    const uint32_t weak = __popc(~(P + 0x7D7D7D7Du) & 0x80808080u);             // suits with power < 3
+    const uint32_t bal = (shape_ok && (hcp < 12u || weak < 2u)) ? 1u : 0u;
+    Feat f;
+    f.f0 = L;
+    f.f1 = P;
+    f.f2 = hcp | (losers << 8) | (bal << 16);
+    return f;
+}
+
+__device__ __forceinline__ bool in_ranges(uint32_t v, uint32_t A, uint32_t B)
+{
+    return (((v + A) & ~(v + B)) & 0x80808080u) == 0x80808080u;
+}
+
+__device__ __forceinline__ bool seat_ranges_ok(const SeatC &c, const Feat &f)
+{
+    return in_ranges(f.f0, c.A[0], c.B[0]) && in_ranges(f.f1, c.A[1], c.B[1]) && in_ranges(f.f2, c.A[2], c.B[2]);
+}
+
+__device__ __forceinline__ uint32_t feat_get(const Feat &f, uint32_t idx)
+{
+    const uint32_t w = idx < 4u ? f.f0 : (idx < 8u ? f.f1 : f.f2);
+    return (w >> ((idx & 3u) * 8u)) & 0xFFu;
+}
+
+// Interpret one program (warp-uniform control flow; boolean stack in a register).
+// Returns the value; err is set where the reference would signal an
+// "illegal function call" (un-spliced rule lists, bidding.cl:249).
+__device__ __forceinline__ bool run_program(const uint32_t *__restrict__ code, const Feat &f, bool &err)
+{
+    uint64_t st = 0;
+    for (;;) {
+        const uint32_t w = __ldg(code++);
+        const uint32_t op = w & 15u;
+        if (op == OP_END) break;
+        switch (op) {
+        case OP_CMPC:
+        case OP_CMPF: {
+            const uint32_t a = feat_get(f, (w >> 8) & 15u);
+            const uint32_t b = op == OP_CMPC ? (w >> 16) & 0xFFu : feat_get(f, (w >> 12) & 15u);
+            const uint32_t state = a < b ? 0u : (a == b ? 1u : 2u);
+            st = (st << 1) | (((w >> 4) >> state) & 1u);
+            break;
+        }
+        case OP_AND: { const uint64_t t = st & 1u; st >>= 1; st &= ~1ull | t; break; }
+        case OP_OR:  { const uint64_t t = st & 1u; st >>= 1; st |= t; break; }
+        case OP_NOT: st ^= 1u; break;
+        case OP_TRUE: st = (st << 1) | 1u; break;
+        case OP_FALSE: st <<= 1; break;
+        case OP_ERRIF_T: err |= (st & 1u) != 0; st &= ~1ull; break;
+        case OP_ERRIF_F: err |= (st & 1u) == 0; break;
+        default: break;
+        }
+    }
+    return (st & 1u) != 0;
+}
+
+}  // namespace bmc

@@ -1,0 +1,222 @@
+"""Thin object layer over the C ABI: Engine (bmc_ctx), Constraints, Scheme.
+
+Everything computes on the GPU through libbridgemc.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BadRange, BridgeMcError, Contract, FEATURE_DTYPE, SeatSpec, Stats, Tallies, TALLY_ALL,
+                   TALLY_WORDS, check)
+
+DEFAULT_SEED = 0x6272696467656D63          # "bridgemc"
+
+_KEYS = ("c", "d", "h", "s")
+
+
+def _lo_hi(v):
+    """number | (lo hi ...) -> (lo, hi) with None -> -1 (nil)."""
+    if v is None:
+        return -1, -1
+    if isinstance(v, int):
+        return v, v
+    lo = -1 if v[0] is None else int(v[0])
+    hi = -1 if len(v) < 2 or v[1] is None else int(v[1])
+    return lo, hi
+
+
+def seat_spec(hcp=None, c=None, d=None, h=None, s=None, losers=None, fixed=None) -> SeatSpec:
+    """One seat's range def in the reference's keyword form
+    (`:hcp (15 17) :s (5 nil (3 nil))`, README / rest.cl:250-256): each value is a
+    number, (lo hi) or -- for suits -- (lo hi suit-hcp-range); None = nil."""
+    sp = SeatSpec()
+    sp.hcp[0], sp.hcp[1] = _lo_hi(hcp)
+    for i, v in enumerate((c, d, h, s)):
+        sp.len[i][0], sp.len[i][1] = _lo_hi(v)
+        sh = v[2] if (v is not None and not isinstance(v, int) and len(v) > 2) else None
+        sp.suit_hcp[i][0], sp.suit_hcp[i][1] = _lo_hi(sh)
+    sp.losers[0], sp.losers[1] = _lo_hi(losers)
+    if fixed is not None:
+        sp.fixed = 1
+        sp.fixed_mask = int(fixed.mask64() if hasattr(fixed, "mask64") else fixed)
+    return sp
+
+
+class Constraints:
+    """bmc_constraints: per-seat ranges (seat_spec / dict / None) and rule forms (str / None)."""
+
+    def __init__(self, specs=None, rules=None):
+        L = _lib.load()
+        arr = None
+        if specs is not None:
+            arr = (SeatSpec * 4)()
+            for k in range(4):
+                sp = specs[k] if k < len(specs) else None
+                if sp is None:
+                    sp = seat_spec()
+                elif isinstance(sp, dict):
+                    sp = seat_spec(**{kk.lower().lstrip(":"): vv for kk, vv in sp.items()})
+                arr[k] = sp
+        rarr = None
+        if rules is not None:
+            rarr = (C.c_char_p * 4)()
+            for k in range(4):
+                r = rules[k] if k < len(rules) else None
+                rarr[k] = None if r is None else r.encode("utf-8")
+        self._h = C.c_void_p()
+        check(L.bmc_constraints_create(arr, rarr, C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.load().bmc_constraints_destroy(h)
+            self._h = None
+
+
+class Scheme:
+    """bmc_scheme: a rule table `(((2 C) . FORM) ...)` for choose-bid."""
+
+    def __init__(self, table_sexpr: str):
+        self._h = C.c_void_p()
+        check(_lib.load().bmc_scheme_create(table_sexpr.encode("utf-8"), C.byref(self._h)))
+        self.size = _lib.load().bmc_scheme_size(self._h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.load().bmc_scheme_destroy(h)
+            self._h = None
+
+
+def tallies_to_dict(t: Tallies) -> dict:
+    return {
+        "raw": int(t.raw), "voided": int(t.voided), "accepted": int(t.accepted), "stored": int(t.stored),
+        "hcp": np.ctypeslib.as_array(t.hcp).astype(np.int64)[:, :38].copy(),
+        "len": np.ctypeslib.as_array(t.len).astype(np.int64).copy(),
+        "shape": np.ctypeslib.as_array(t.shape).astype(np.int64)[:, :39].copy(),
+    }
+
+
+def tallies_from_words(words: np.ndarray) -> dict:
+    """uint64[TALLY_WORDS] (e.g. an all-reduced device buffer copied back) -> dict."""
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    t = Tallies.from_buffer_copy(w.tobytes())
+    return tallies_to_dict(t)
+
+
+class Engine:
+    """bmc_ctx on one device.  One Engine per calling thread (or share it: calls serialise)."""
+
+    _default = None
+    _default_lock = threading.Lock()
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        check(self._L.bmc_init(device, C.byref(self._h)))
+        self.device = device
+
+    @classmethod
+    def default(cls) -> "Engine":
+        with cls._default_lock:
+            if cls._default is None:
+                cls._default = cls(0)
+            return cls._default
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bmc_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- sampling -----------------------------------------------------------
+    def sample(self, cons: Constraints | None = None, *, n_raw: int = 0, n_accept: int = 0, seed: int = DEFAULT_SEED,
+               first_index: int = 0, wave: int = 0, tally_mask: int = TALLY_ALL, cap: int | None = None,
+               records: np.ndarray | None = None):
+        """bmc_sample with host buffers.  Returns (records uint64[stored,2], tallies dict, Stats)."""
+        if cap is None:
+            cap = n_accept + (n_accept // 8) + 4096 if n_accept else n_raw
+        if records is None and cap:
+            records = np.empty((cap, 2), dtype=np.uint64)
+        t, st = Tallies(), Stats()
+        check(self._L.bmc_sample(self._h, cons._h if cons else None, seed, first_index, n_raw, n_accept, wave,
+                                 tally_mask, records.ctypes.data if cap else None, cap, C.byref(t), C.byref(st)))
+        out = records[:st.stored] if cap else np.empty((0, 2), dtype=np.uint64)
+        return out, tallies_to_dict(t), st
+
+    def sample_dev(self, cons: Constraints | None, records_ptr: int, cap: int, tallies_ptr: int, *, n_raw: int = 0,
+                   n_accept: int = 0, seed: int = DEFAULT_SEED, first_index: int = 0, wave: int = 0,
+                   tally_mask: int = TALLY_ALL) -> Stats:
+        """bmc_sample_dev: device pointers (e.g. torch tensors' data_ptr())."""
+        st = Stats()
+        check(self._L.bmc_sample_dev(self._h, cons._h if cons else None, seed, first_index, n_raw, n_accept, wave,
+                                     tally_mask, records_ptr or None, cap, tallies_ptr, C.byref(st)))
+        return st
+
+    def set_stream(self, cuda_stream: int):
+        check(self._L.bmc_set_stream(self._h, cuda_stream or None))
+
+    # ---- filter ---------------------------------------------------------------
+    def filter(self, records: np.ndarray, cons: Constraints | None = None, scheme: Scheme | None = None,
+               want_features: bool = True):
+        """bmc_filter: (accept uint8[n], features structured[n,4])."""
+        rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
+        n = rec.shape[0]
+        acc = np.empty(n, dtype=np.uint8)
+        feats = np.empty((n, 4), dtype=FEATURE_DTYPE) if want_features else None
+        check(self._L.bmc_filter(self._h, cons._h if cons else None, scheme._h if scheme else None,
+                                 rec.ctypes.data if n else None, n, acc.ctypes.data,
+                                 feats.ctypes.data if want_features else None))
+        return acc, feats
+
+    # ---- scoring ----------------------------------------------------------------
+    def score(self, contracts, vulnerable, tricks: np.ndarray) -> np.ndarray:
+        """bmc_score: tricks uint8[n, n_contracts] -> base scores int32[n, n_contracts]."""
+        nc = len(contracts)
+        carr = (Contract * nc)(*contracts)
+        vul = np.ascontiguousarray(vulnerable, dtype=np.uint8)
+        tr = np.ascontiguousarray(tricks, dtype=np.uint8).reshape(-1, nc)
+        out = np.empty(tr.shape, dtype=np.int32)
+        check(self._L.bmc_score(self._h, carr, vul.ctypes.data, nc, tr.ctypes.data, tr.shape[0], out.ctypes.data))
+        return out
+
+    def match_points(self, a: np.ndarray, b: np.ndarray):
+        """bmc_match_points: (imps int8[n], status uint8[n])."""
+        a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+        b = np.ascontiguousarray(b, dtype=np.int32).reshape(-1)
+        imps = np.empty(a.size, dtype=np.int8)
+        status = np.empty(a.size, dtype=np.uint8)
+        check(self._L.bmc_match_points(self._h, a.ctypes.data, b.ctypes.data, a.size, imps.ctypes.data, status.ctypes.data))
+        return imps, status
+
+    def score_tally(self, contracts, vulnerable, pairs, n: int, seed: int = DEFAULT_SEED, first_index: int = 0):
+        nc = len(contracts)
+        carr = (Contract * nc)(*contracts)
+        vul = np.ascontiguousarray(vulnerable, dtype=np.uint8)
+        pr = np.ascontiguousarray(pairs, dtype=np.uint8).reshape(-1)
+        npairs = pr.size // 2
+        th = np.zeros((nc, 14), dtype=np.uint64)
+        ih = np.zeros((max(npairs, 1), 49), dtype=np.uint64)
+        tab = np.zeros((nc, 14), dtype=np.int32)
+        check(self._L.bmc_score_tally(self._h, carr, vul.ctypes.data, nc, pr.ctypes.data if npairs else None, npairs,
+                                      seed, first_index, n, th.ctypes.data, ih.ctypes.data, tab.ctypes.data))
+        return th, ih[:npairs], tab
+
+    # ---- measurement --------------------------------------------------------------
+    def int_peak(self):
+        ops = C.c_double()
+        ms = C.c_float()
+        check(self._L.bmc_int_peak(self._h, C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
+    def launch_count(self) -> int:
+        return int(self._L.bmc_launch_count(self._h))

@@ -1,0 +1,213 @@
+/*
+ * bridgemc.h -- C ABI of libbridgemc.so, the B200 (sm_100a) Monte-Carlo deal
+ * engine that sits behind bridge-mc's Lisp entry points.
+ *
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the reference's backend/ directory).  The Lisp side binds these with CFFI
+ * (lisp/bridgemc-cffi.lisp); bridge_mc_b200/ is the same
+ * binding in Python (ctypes) used by the tests and the benchmark.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every buffer it passes and
+ *    the library never keeps a caller pointer after the call returns;
+ *  - handles are opaque and freed by the matching *_destroy;
+ *  - int return: 0 = BMC_OK, < 0 = error code; bmc_last_error() gives the
+ *    message for the calling thread; nothing exits, aborts or throws;
+ *  - there is no CPU fallback: without a CUDA device every compute call
+ *    returns BMC_E_CUDA;
+ *  - re-entrant: a bmc_ctx owns one CUDA stream; use one ctx per calling
+ *    thread (hunchentoot workers, dealgen<..>/sim{..} threads -- rest.cl:403,
+ *    bridge.cl:3100,3115) or serialise calls on a shared one.
+ *
+ * Encoding (bridge.cl:519-547): suit c=0 d=1 h=2 s=3, rank 0..12 = 2..A.
+ * Seats 0..3 = N E S W.  A 64-bit "lane mask" holds one 16-bit lane per suit,
+ * bit r of lane s = card (s, r); bits 13..15 of every lane are zero.
+ */
+#ifndef BRIDGEMC_H
+#define BRIDGEMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define BMC_OK            0
+#define BMC_E_INVALID    -1   /* bad argument */
+#define BMC_E_CUDA       -2   /* no device / CUDA runtime error */
+#define BMC_E_BAD_RANGE  -3   /* contradictory ranges: the reference's `bad-range` condition (bridge.cl:1109-1123) */
+#define BMC_E_PARSE      -4   /* rule form not in the bidding.cl predicate language */
+#define BMC_E_NOMEM      -5
+#define BMC_E_CAPACITY   -6   /* program / table too large */
+
+#define BMC_LANE_MASK 0x1FFF1FFF1FFF1FFFull
+
+/* One deal = 128 bits (a CUDA uint4): two owner bit-planes over the 52 cards in
+ * lane-mask layout.  Owner seat of a card = 2*hi_bit + lo_bit.  Replaces the
+ * list of four `hand` objects `build` returns (bridge.cl:1316-1318). */
+typedef struct { uint64_t lo, hi; } bmc_record;
+
+/* Per-seat range definition: the `:~` plist of class `deal`
+ * (bridge.cl:1283-1286; README "(:hcp (15 17) :s (5 nil (3 nil)))").
+ * -1 = nil (open end).  fixed != 0: the seat holds exactly `fixed_mask`
+ * (a `:=` const hand, bridge.cl:1285,1294). */
+typedef struct {
+    int8_t   hcp[2];
+    int8_t   len[4][2];        /* c d h s */
+    int8_t   suit_hcp[4][2];   /* third element of a suit spec */
+    int8_t   losers[2];        /* losing-trick count (bidding.cl:20-23), extension */
+    uint8_t  fixed;
+    uint8_t  reserved[3];
+    uint64_t fixed_mask;
+} bmc_seat_spec;
+
+/* assess-hand (bidding.cl:33-38) + balanced? (40-46) + choose-bid (146-150) for one seat */
+typedef struct {
+    uint8_t len[4];
+    uint8_t suit_hcp[4];       /* "power" */
+    uint8_t hcp;
+    uint8_t losers;
+    uint8_t balanced;
+    int8_t  bid;               /* row of the scheme that matched first, -1 = nil / no scheme */
+} bmc_seat_features;
+typedef struct { bmc_seat_features seat[4]; } bmc_features;
+
+/* hist-base pre-counts (bridge.cl:1325-1330 `base` argument) produced on the
+ * device.  All counters are over ACCEPTED deals except raw/voided. */
+#define BMC_HCP_BINS   40      /* 0..37 used */
+#define BMC_LEN_BINS   14
+#define BMC_SHAPE_BINS 40      /* 39 sorted shapes, see bmc_shape_table */
+typedef struct {
+    uint64_t raw;              /* deal indices drawn */
+    uint64_t voided;           /* indices discarded by the exact-uniformity (Lemire) check */
+    uint64_t accepted;
+    uint64_t stored;           /* records written to the output buffer (<= cap) */
+    uint64_t hcp[4][BMC_HCP_BINS];
+    uint64_t len[4][4][BMC_LEN_BINS];     /* [seat][suit][length] */
+    uint64_t shape[4][BMC_SHAPE_BINS];    /* [seat][sorted-shape class] */
+} bmc_tallies;
+#define BMC_TALLY_WORDS (sizeof(bmc_tallies) / sizeof(uint64_t))
+
+#define BMC_TALLY_HCP   1u
+#define BMC_TALLY_LEN   2u
+#define BMC_TALLY_SHAPE 4u
+#define BMC_TALLY_ALL   7u
+
+typedef struct {
+    uint64_t raw, voided, accepted, stored;
+    uint32_t waves, launches;
+    float    kernel_ms;        /* CUDA-event time of the sampling kernels */
+    float    total_ms;         /* wall time of the call */
+} bmc_stats;
+
+/* compscore.cl:38-65 class `contract` after parsing (the string parser stays on
+ * the Lisp side).  suit 0 c 1 d 2 h 3 s 4 NT; declarer 0 N 1 E 2 S 3 W, -1 none;
+ * dbl 0 nil 1 x 2 xx. */
+typedef struct { int8_t level, suit, declarer, dbl; } bmc_contract;
+
+typedef struct bmc_ctx bmc_ctx;
+typedef struct bmc_constraints bmc_constraints;
+typedef struct bmc_scheme bmc_scheme;
+
+/* ---- context ------------------------------------------------------------ */
+int  bmc_init(int device, bmc_ctx **out);
+void bmc_shutdown(bmc_ctx *ctx);
+const char *bmc_last_error(void);
+const char *bmc_version(void);
+/* pinned host memory for record buffers (fast device->host copies); optional */
+void *bmc_host_alloc(size_t bytes);
+void  bmc_host_free(void *p);
+/* the 39 sorted shapes in tally order (each row a>=b>=c>=d, sum 13) */
+void  bmc_shape_table(uint8_t out[39][4]);
+
+/* ---- constraints -------------------------------------------------------- */
+/* Replaces (make-instance 'deal := const-hands :~ defs) (bridge.cl:1283-1286)
+ * plus a per-seat bidding.cl predicate.  specs may be NULL (unconstrained, the
+ * `full-random` deal of training.cl:1); rules[k] may be NULL or a rule FORM in
+ * the language good-opening? evaluates (bidding.cl:60-74): and/or/not/cond,
+ * < <= > >= =, variables C D H S Cpower Dpower Hpower Spower hcp loosers
+ * balanced, and (find-if (curry #'< n) (subseq lens a b)) /
+ * (find-if (curry #'> n) power).  BMC_E_BAD_RANGE where `build` would signal
+ * bad-range; BMC_E_PARSE for a form outside the language. */
+int  bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules[4],
+                            bmc_constraints **out);
+void bmc_constraints_destroy(bmc_constraints *c);
+
+/* A rule table as printed by Lisp: "(((2 C) . FORM) ((2 NT) . FORM) ...)" --
+ * `openings`, (nt-responses n), 2C-responses, (basic-responses bid) ...
+ * (bidding.cl:76-106,166-187,204-210,226-253).  Used by bmc_filter for
+ * choose-bid (first row whose form is true, bidding.cl:146-150). */
+int  bmc_scheme_create(const char *table_sexpr, bmc_scheme **out);
+int  bmc_scheme_size(const bmc_scheme *s);
+void bmc_scheme_destroy(bmc_scheme *s);
+
+/* ---- sampling: replaces `build` in a loop / `sim` (bridge.cl:1292-1319, 3144-3162) */
+/* Draws raw deals with Philox4x32-10 (key = seed, counter = deal index), keeps
+ * those satisfying `cons`, writes them as records and tallies them.
+ *   n_accept_target == 0: exactly the indices [first_index, first_index+n_raw).
+ *   n_accept_target  > 0: whole waves of `wave` indices (0 = default 2^26)
+ *       starting at first_index until accepted >= target or n_raw indices
+ *       (0 = no limit) are used; the accepted SET depends only on
+ *       (seed, first_index, wave, target).
+ * records may be NULL (tally only); at most `cap` records are stored.
+ * Host-buffer form (what the Lisp shim calls): */
+int bmc_sample(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
+               uint64_t n_raw, uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask,
+               bmc_record *records, uint64_t cap, bmc_tallies *tallies, bmc_stats *stats);
+/* Device-buffer form: records_dev / tallies_dev are device pointers (tallies_dev
+ * is ACCUMULATED into, not cleared: zero it first); used by the multi-GPU
+ * driver, which all-reduces tallies_dev with NCCL. */
+int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
+                   uint64_t n_raw, uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask,
+                   void *records_dev, uint64_t cap, void *tallies_dev, bmc_stats *stats);
+
+/* ---- filter / features on given deals: assess-hand, balanced?, test-bid,
+ * choose-bid (bidding.cl:33-46,111-112,146-150) over a deal set ---------------- */
+/* accept[i] = 1 iff deal i satisfies cons (NULL cons: all 1); feats[i] gets the
+ * four seats' features, .bid = choose-bid over `scheme` (NULL: -1).  accept and
+ * feats may each be NULL. */
+int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme,
+               const bmc_record *records, uint64_t n, uint8_t *accept, bmc_features *feats);
+
+/* ---- scoring: contract-score (bridge.cl:3045-3069), base-score
+ * (compscore.cl:94-100), match-points (compscore.cl:127-131) ------------------ */
+/* scores[i*n_contracts + c] = base-score of contracts[c] making tricks[i*n_contracts + c]
+ * tricks (0..13), vulnerable[c] != 0 => :vulnerable t. */
+int bmc_score(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulnerable,
+              uint32_t n_contracts, const uint8_t *tricks, uint64_t n, int32_t *scores);
+/* imps[i] = IMPs of score difference a[i]-b[i] (sign carried); status[i] = 1
+ * where |diff| >= 4000 (the reference errors there), imps[i] = 0. */
+int bmc_match_points(bmc_ctx *ctx, const int32_t *a, const int32_t *b, uint64_t n,
+                     int8_t *imps, uint8_t *status);
+/* Fused drill tally (config "compscore tallies over constrained samples"):
+ * for deal i in [0,n) and contract c, tricks = Philox(seed, stream 1, index
+ * first_index+i, word c) uniform on 0..13 (the reference's trick source,
+ * play-deal, is out of scope); tricks_hist[c][t] += 1; for every pair p,
+ * imp_hist[p][24 + match-points(contracts[pairs[2p]], contracts[pairs[2p+1]])] += 1.
+ * score_table[c][t] = base-score (output, may be NULL).  n_contracts <= 8, n_pairs <= 8. */
+int bmc_score_tally(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulnerable,
+                    uint32_t n_contracts, const uint8_t *pairs, uint32_t n_pairs,
+                    uint64_t seed, uint64_t first_index, uint64_t n,
+                    uint64_t *tricks_hist /*[n_contracts][14]*/, uint64_t *imp_hist /*[n_pairs][49]*/,
+                    int32_t *score_table /*[n_contracts][14]*/);
+
+/* ---- measurement helpers -------------------------------------------------- */
+/* INT32 issue-rate microbenchmark (IMAD + LOP3/IADD3 chains on every SM):
+ * returns thread-level integer ops per second in *ops_per_s. */
+int bmc_int_peak(bmc_ctx *ctx, double *ops_per_s, float *ms);
+/* number of kernel launches this context has made (for bench.py's gpu_launches) */
+uint64_t bmc_launch_count(const bmc_ctx *ctx);
+/* use an external CUDA stream (e.g. torch's current stream) for subsequent calls; 0 restores the own stream */
+int bmc_set_stream(bmc_ctx *ctx, void *cuda_stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRIDGEMC_H */

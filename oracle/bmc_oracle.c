@@ -1,0 +1,666 @@
+/*
+ * bmc_oracle.c -- CPU restatement of bridge-mc's Monte-Carlo deal path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under bridge_mc_b200/ (the product) may
+ * link, import or call this file; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs use it, as the checker or the
+ * timed CPU baseline.
+ *
+ * Parity status: PINNED.  The reference (Common Lisp, no SBCL in this image)
+ * cannot be executed, so every function below is pinned against the
+ * reference's own inline known-answer tests and its golden file
+ * backend/test/distgen-test.dat (converted by tests/golden/make_golden.py into
+ * the JSON fixtures under tests/golden; checked by the tests/test_oracle_ files).
+ *
+ * Each function cites the reference file:line it restates
+ * (paths relative to /root/reference/backend/).
+ *
+ * Encoding (bridge.cl:519-547): suit c=0 d=1 h=2 s=3; rank 0..12 = 2..A;
+ * card id = 13*suit + rank.  A hand here is four 13-bit rank masks.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+typedef struct { uint16_t s[4]; } orc_hand;
+
+static inline int popc16(unsigned v) { return __builtin_popcount(v & 0x1FFFu); }
+
+/* ------------------------------------------------------------------ */
+/* Features                                                           */
+/* ------------------------------------------------------------------ */
+
+/* bridge.cl:667-668 rank-hcp: rank>8 -> rank-8 ; bridge.cl:2986-2987 suit-hcp */
+ORC_API int orc_suit_hcp(unsigned ranks)
+{
+    int h = 0;
+    for (int r = 9; r <= 12; ++r) if (ranks >> r & 1) h += r - 8;
+    return h;
+}
+
+/* bidding.cl:20-23 suit-loosers */
+ORC_API int orc_suit_losers(unsigned ranks)
+{
+    int len = popc16(ranks);
+    return ((ranks >> 12 & 1) || len == 0 ? 0 : 1)
+         + ((ranks >> 11 & 1) || len < 2 ? 0 : 1)
+         + ((ranks >> 10 & 1) || len < 3 ? 0 : 1);
+}
+
+/* bidding.cl:40-46 balanced? (lens power loosers) */
+ORC_API int orc_balanced(const int lens[4], const int power[4])
+{
+    for (int i = 0; i < 4; ++i) if (2 > lens[i]) return 0;          /* (curry #'> 2) */
+    if (4 < lens[2] || 4 < lens[3]) return 0;                         /* hearts, spades */
+    if (5 < lens[0] || 5 < lens[1]) return 0;                         /* clubs, diamonds */
+    int hcp = power[0] + power[1] + power[2] + power[3];
+    int weak = 0;
+    for (int i = 0; i < 4; ++i) if (3 > power[i]) ++weak;
+    return hcp < 12 || weak < 2;
+}
+
+/* bidding.cl:33-38 assess-hand -> (lens power losers); out[0..3] lens, [4..7]
+ * power, [8] hcp, [9] losers, [10] balanced */
+ORC_API void orc_assess(const uint16_t suits[4], int out[11])
+{
+    int losers = 0, hcp = 0;
+    for (int i = 0; i < 4; ++i) {
+        out[i] = popc16(suits[i]);
+        out[4 + i] = orc_suit_hcp(suits[i]);
+        hcp += out[4 + i];
+        losers += orc_suit_losers(suits[i]);
+    }
+    out[8] = hcp;
+    out[9] = losers;
+    out[10] = orc_balanced(out, out + 4);
+}
+
+/* ------------------------------------------------------------------ */
+/* bidding.cl rule tables, hard-coded line by line                    */
+/* ------------------------------------------------------------------ */
+#define C_  f[0]
+#define D_  f[1]
+#define H_  f[2]
+#define S_  f[3]
+#define CP  f[4]
+#define DP  f[5]
+#define HP  f[6]
+#define SP  f[7]
+#define HCP f[8]
+#define LOS f[9]
+#define BAL f[10]
+
+/* bidding.cl:76-106 `openings`, index = table position:
+ * 0 2C, 1 2NT, 2 1NT, 3 1S, 4 1H, 5 1D, 6 1C, 7 2D, 8 2H, 9 2S, 10 3C, 11 3D, 12 3H, 13 3S */
+ORC_API int orc_opening_rule(int k, const int f[11])
+{
+    switch (k) {
+    case 0: {   /* bidding.cl:77-80 */
+        if (HCP > 22) return 1;
+        if (BAL) return 0;
+        if (4 < H_ || 4 < S_) return LOS <= 4;       /* cond clause 1: (subseq lens 2 4) */
+        if (4 < C_ || 4 < D_) return LOS <= 3;       /* cond clause 2: (subseq lens 0 2) */
+        return 0;
+    }
+    case 1:     /* bidding.cl:81-82 */
+        return BAL && !(3 > CP || 3 > DP || 3 > HP || 3 > SP) && HCP > 18;
+    case 2:     /* bidding.cl:83 */
+        return BAL && HCP > 14 && HCP < 18;
+    case 3:     /* bidding.cl:84-87 */
+        return (LOS < 6 || HCP > 11) && LOS > 4 && HCP < 23 && S_ >= 5
+            && !(HCP > 16 && (4 < C_ || 4 < D_ || 4 < H_));
+    case 4:     /* bidding.cl:88-91 */
+        return (LOS < 6 || HCP > 11) && LOS > 4 && HCP < 23 && H_ >= 5
+            && !(HCP > 16 && (4 < C_ || 4 < D_));
+    case 5:     /* bidding.cl:92-95 */
+        return (LOS < 6 || HCP > 11) && LOS > 3 && HCP < 23 && D_ >= 4 && D_ >= C_
+            && !(HCP > 16 && C_ >= 5);
+    case 6:     /* bidding.cl:96-98 */
+        return (LOS < 6 || HCP > 11) && LOS > 3 && HCP < 23 && C_ >= 3;
+    case 7: case 8: case 9: {   /* bidding.cl:99-101  2D 2H 2S */
+        int s = k - 6;
+        return HCP > 5 && f[4 + s] >= 5 && (LOS > 5 || HCP < 11) && f[s] == 6;
+    }
+    case 10: case 11: case 12: case 13: {   /* bidding.cl:102-105  3C 3D 3H 3S */
+        int s = k - 10;
+        return HCP > 5 && f[4 + s] >= 5 && HCP < 11 && f[s] >= 7;
+    }
+    }
+    return 0;
+}
+#define ORC_N_OPENINGS 14
+
+/* bidding.cl:166-187 nt-responses.  level 1 table order:
+ *   0 (2 C) 1 (2 D) 2 (2 H) 3 (2 S) 4 (3 C) 5 (2 NT) 6 (3 NT) 7 (4 NT) 8 (6 NT)
+ * level 2: 0 (3 C) 1 (3 D) 2 (3 H) 3 (3 S) 4 (3 NT) 5 (4 NT) 6 (6 NT) */
+ORC_API int orc_nt_response_count(int level) { return level == 1 ? 9 : 7; }
+
+ORC_API int orc_nt_response_rule(int level, int k, const int f[11])
+{
+    int inv_lo = level == 1 ? 8 : 4;
+    int game_lo = level == 1 ? 10 : 6, game_hi = level == 1 ? 15 : 10;
+    int si_lo = level == 1 ? 16 : 12, si_hi = level == 1 ? 17 : 13;
+    int slam = level == 1 ? 18 : 14;
+    if (level != 1 && k >= 4) k += 2;      /* skip the level-1-only rows */
+    switch (k) {
+    case 0: return HCP >= inv_lo && (S_ == 4 || H_ == 4);
+    case 1: return H_ >= 5;
+    case 2: return S_ >= 5;
+    case 3: return (HCP < inv_lo || HCP > game_hi - 2) && ((HCP > inv_lo && C_ >= 5) || C_ >= 6);
+    case 4: return (HCP < 8 || HCP > 13) && ((HCP >= 7 && D_ >= 5) || D_ >= 6);
+    case 5: return HCP >= 8 && HCP <= 9 && H_ < 5 && S_ < 5 && C_ < 6 && D_ < 6;
+    case 6: return HCP >= game_lo && HCP <= game_hi;
+    case 7: return HCP >= si_lo && HCP <= si_hi;
+    case 8: return HCP >= slam;
+    }
+    return 0;
+}
+
+/* bidding.cl:204-210 2C-responses: 0 (2 D) 1 (2 H) 2 (2 S) 3 (2 NT) 4 (3 C) 5 (3 D) */
+ORC_API int orc_2c_response_rule(int k, const int f[11])
+{
+    switch (k) {
+    case 0: return HCP >= 6;
+    case 1: return HCP <= 5 && H_ >= 4;
+    case 2: return HCP <= 5 && S_ >= 4;
+    case 3: return HCP <= 5 && BAL;
+    case 4: return HCP <= 5 && C_ >= 5 && !BAL;
+    case 5: return HCP <= 5 && D_ >= 5 && !BAL;
+    }
+    return 0;
+}
+
+/* bidding.cl:146-150 choose-bid: first matching row, -1 = nil.
+ * scheme: 0 openings, 1 (nt-responses 1), 2 (nt-responses 2), 3 2C-responses */
+ORC_API int orc_scheme_size(int scheme)
+{
+    return scheme == 0 ? ORC_N_OPENINGS : scheme == 1 ? 9 : scheme == 2 ? 7 : 6;
+}
+ORC_API int orc_test_rule(int scheme, int k, const int f[11])
+{
+    switch (scheme) {
+    case 0: return orc_opening_rule(k, f);
+    case 1: return orc_nt_response_rule(1, k, f);
+    case 2: return orc_nt_response_rule(2, k, f);
+    default: return orc_2c_response_rule(k, f);
+    }
+}
+ORC_API int orc_choose_bid(int scheme, const uint16_t suits[4])
+{
+    int f[11];
+    orc_assess(suits, f);
+    int n = orc_scheme_size(scheme);
+    for (int k = 0; k < n; ++k) if (orc_test_rule(scheme, k, f)) return k;
+    return -1;
+}
+/* bidding.cl:111-112 test-bid */
+ORC_API int orc_test_bid(int scheme, int k, const uint16_t suits[4])
+{
+    int f[11];
+    orc_assess(suits, f);
+    return orc_test_rule(scheme, k, f);
+}
+
+/* ------------------------------------------------------------------ */
+/* Scoring                                                            */
+/* ------------------------------------------------------------------ */
+
+/* bridge.cl:3045-3069 contract-score.  suit: 0 c 1 d 2 h 3 s 4 NT/nil;
+ * level 0 = not given (defaults to max(tricks-6,1)); dbl 0 nil, 1 x, 2 xx. */
+ORC_API int orc_contract_score(int suit, int tricks, int vulnerable, int dbl, int level)
+{
+    if (!level) level = tricks - 6 > 1 ? tricks - 6 : 1;
+    int result = tricks - level - 6;
+    if (result >= 0) {
+        int ppl = suit <= 1 ? 20 : 30;
+        int base = ((suit == 4 ? 10 : 0) + ppl * level) * (dbl == 2 ? 4 : dbl ? 2 : 1);
+        int bonus = level == 7 ? (vulnerable ? 2000 : 1300)
+                  : level == 6 ? (vulnerable ? 1250 : 800)
+                  : base >= 100 ? (vulnerable ? 500 : 300) : 50;
+        bonus += dbl ? (dbl == 2 ? 100 : 50) + (vulnerable ? 200 : 100) * result : ppl * result;
+        return base + bonus;
+    }
+    if (dbl) {
+        int v = vulnerable ? -200 + 300 * (result + 1)
+              : result == -1 ? -100 : result == -2 ? -300 : result == -3 ? -500
+              : -800 + 300 * (result + 3);
+        return v * (dbl == 2 ? 2 : 1);
+    }
+    return result * (vulnerable ? 100 : 50);
+}
+
+/* compscore.cl:94-100 base-score; declarer 0 N 1 E 2 S 3 W, -1 none */
+ORC_API int orc_base_score(int level, int suit, int declarer, int dbl, int tricks, int vulnerable)
+{
+    int sc = orc_contract_score(suit, tricks, vulnerable, dbl, level);
+    return (declarer == 1 || declarer == 3) ? -sc : sc;
+}
+
+/* compscore.cl:123-131; returns 0 on success, -1 where position-if gives nil
+ * (|diff| >= 4000 -> Lisp type error) */
+static const int IMP_PTS[24] = {20, 50, 90, 130, 170, 220, 270, 320, 370, 430, 500, 600, 750, 900,
+                                1100, 1300, 1500, 1750, 2000, 2300, 2500, 3000, 3500, 4000};
+ORC_API int orc_imps(int diff, int *out)
+{
+    int a = diff < 0 ? -diff : diff;
+    for (int i = 0; i < 24; ++i)
+        if (a < IMP_PTS[i]) { *out = diff < 0 ? -i : i; return 0; }
+    return -1;
+}
+
+/* ------------------------------------------------------------------ */
+/* RNG for the reference-algorithm sampler (the reference uses SBCL's */
+/* never-seeded MT19937; any uniform source restates it)              */
+/* ------------------------------------------------------------------ */
+typedef struct { uint64_t s; } orc_rng;
+static uint64_t rng_next(orc_rng *r)
+{
+    uint64_t z = (r->s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+/* (random n) for 0 < n < 2^63, exact by rejection */
+static uint64_t rng_below(orc_rng *r, uint64_t n)
+{
+    uint64_t lim = UINT64_MAX - (UINT64_MAX % n + 1) % n;
+    uint64_t x;
+    do x = rng_next(r); while (x > lim);
+    return x % n;
+}
+
+/* ------------------------------------------------------------------ */
+/* distgen (bridge.cl:866-1083)                                       */
+/* ------------------------------------------------------------------ */
+
+/* range spec: lo/hi, -1 = nil (open).  "absent" suit spec = both -1. */
+typedef struct {
+    int hcp_lo, hcp_hi, has_hcp;      /* :hcp ; has_hcp=0 -> no filter */
+    int len_lo[4], len_hi[4];          /* :c :d :h :s first two elements */
+    int shcp_lo[4], shcp_hi[4], has_shcp[4]; /* third element (list form) */
+} orc_spec;
+
+typedef struct {
+    int lc_supply[4];          /* bridge.cl:1030 */
+    int hon[4][4];             /* available honours [suit][J Q K A] */
+    uint16_t *pat;             /* admissible honour patterns, 16 bits: bit 15 = club J ... bit 0 = spade A */
+    int npat;
+    orc_spec spec;
+    uint64_t total;            /* total-weight (fits: <= C(52,13) < 2^40) */
+    uint64_t cards;            /* 52-bit mask of the cards dealt from */
+} orc_distgen;
+
+static uint64_t binom_tab[14][14];
+static void binom_init(void)
+{
+    if (binom_tab[0][0]) return;
+    for (int n = 0; n < 14; ++n)
+        for (int k = 0; k < 14; ++k) {
+            /* bridge.cl:814-816 combinations: prod(i = s-p+1 .. s) / p!  (0 when p > s) */
+            if (k > n) { binom_tab[n][k] = 0; continue; }
+            uint64_t num = 1, den = 1;
+            for (int i = n - k + 1; i <= n; ++i) num *= (uint64_t)i;
+            for (int i = 2; i <= k; ++i) den *= (uint64_t)i;
+            binom_tab[n][k] = num / den;
+        }
+}
+ORC_API uint64_t orc_combinations(int supply, int amount)
+{
+    binom_init();
+    if (supply < 0 || supply > 13 || amount < 0) return 0;
+    if (amount > 13) return 0;
+    return binom_tab[supply][amount];
+}
+
+/* bridge.cl:876-878 supply: per suit (n_low nJ nQ nK nA) */
+ORC_API void orc_supply(uint64_t cards, int out[4][5])
+{
+    for (int s = 0; s < 4; ++s) {
+        unsigned lane = (unsigned)(cards >> (13 * s)) & 0x1FFFu;
+        out[s][0] = __builtin_popcount(lane & 0x1FFu);
+        for (int h = 0; h < 4; ++h) out[s][1 + h] = lane >> (9 + h) & 1;
+    }
+}
+
+static int pat_bit(unsigned pat, int s, int h) { return pat >> (15 - (4 * s + h)) & 1; }
+
+/* bridge.cl:921-924 permut-hcp on the flat 16 list: weight (i mod 4)+1 */
+static int pat_hcp(unsigned pat)
+{
+    int t = 0;
+    for (int i = 0; i < 16; ++i) if (pat >> (15 - i) & 1) t += i % 4 + 1;
+    return t;
+}
+static int pat_suit_hcp(unsigned pat, int s)
+{
+    int t = 0;
+    for (int h = 0; h < 4; ++h) if (pat_bit(pat, s, h)) t += h + 1;
+    return t;
+}
+
+/* bridge.cl:880-888 valtest-fun on (lo hi) with nil ends */
+static int in_range(int v, int lo, int hi)
+{
+    if (lo >= 0 && v < lo) return 0;
+    if (hi >= 0 && v > hi) return 0;
+    return 1;
+}
+
+/* bridge.cl:990-1004 possible-lc-lens + 828-831 permut-weight, summed as in
+ * `next` (bridge.cl:1043-1044).  If lc_out != NULL the admissible tuples and
+ * their weights are stored (dist-from-hc, bridge.cl:1053-1059). Enumerates the
+ * full product and filters on the sum, like list-prod + filter. */
+static uint64_t pattern_weight(const orc_distgen *g, unsigned pat,
+                               int (*lc_out)[4], uint64_t *w_out, int *n_out)
+{
+    int base[4], lo[4], hi[4], hc = 0;
+    for (int s = 0; s < 4; ++s) {
+        base[s] = 0;
+        for (int h = 0; h < 4; ++h) base[s] += pat_bit(pat, s, h);
+        hc += base[s];
+        int mn = g->spec.len_lo[s] < 0 ? 0 : g->spec.len_lo[s];
+        int mx = g->spec.len_hi[s] < 0 ? g->lc_supply[s] : g->spec.len_hi[s];  /* (or max supply): the 9-cap quirk */
+        lo[s] = mn - base[s];
+        hi[s] = mx - base[s];
+        if (lo[s] < 0) lo[s] = 0;                /* (filter (curry #'<= 0) ...) */
+    }
+    int need = 13 - hc, n = 0;
+    uint64_t total = 0;
+    for (int a = lo[0]; a <= hi[0]; ++a)
+        for (int b = lo[1]; b <= hi[1]; ++b)
+            for (int c = lo[2]; c <= hi[2]; ++c)
+                for (int d = lo[3]; d <= hi[3]; ++d) {
+                    if (a + b + c + d != need) continue;
+                    uint64_t w = orc_combinations(g->lc_supply[0], a) * orc_combinations(g->lc_supply[1], b)
+                               * orc_combinations(g->lc_supply[2], c) * orc_combinations(g->lc_supply[3], d);
+                    if (lc_out) { lc_out[n][0] = a; lc_out[n][1] = b; lc_out[n][2] = c; lc_out[n][3] = d; w_out[n] = w; }
+                    ++n;
+                    total += w;
+                }
+    if (n_out) *n_out = n;
+    return total;
+}
+
+/* bridge.cl:926-963 hc-permuts: all subsets of the available honours in binary
+ * counting order (first available position most significant), filtered by the
+ * total-HCP test and the per-suit HCP tests.  No available honour -> nil. */
+static void build_patterns(orc_distgen *g)
+{
+    int pos[16], npos = 0;
+    for (int i = 0; i < 16; ++i) if (g->hon[i / 4][i % 4]) pos[npos++] = i;
+    g->npat = 0;
+    g->pat = NULL;
+    if (!npos) return;
+    g->pat = (uint16_t *)malloc(sizeof(uint16_t) * ((size_t)1 << npos));
+    for (unsigned m = 0; m < (1u << npos); ++m) {
+        unsigned pat = 0;
+        for (int j = 0; j < npos; ++j)
+            if (m >> (npos - 1 - j) & 1) pat |= 1u << (15 - pos[j]);
+        if (g->spec.has_hcp && !in_range(pat_hcp(pat), g->spec.hcp_lo, g->spec.hcp_hi)) continue;
+        int ok = 1;
+        for (int s = 0; s < 4 && ok; ++s)
+            if (g->spec.has_shcp[s]) {
+                int h = pat_suit_hcp(pat, s);   /* (or lo 0) .. (or hi 10), bridge.cl:936-937 */
+                int l = g->spec.shcp_lo[s] < 0 ? 0 : g->spec.shcp_lo[s];
+                int u = g->spec.shcp_hi[s] < 0 ? 10 : g->spec.shcp_hi[s];
+                ok = h >= l && h <= u;
+            }
+        if (ok) g->pat[g->npat++] = (uint16_t)pat;
+    }
+}
+
+/* bridge.cl:1027-1036 (make-instance 'distgen :cards .. :hcp .. :c .. :d .. :h .. :s ..) */
+ORC_API orc_distgen *orc_distgen_new(uint64_t cards, const orc_spec *spec)
+{
+    binom_init();
+    orc_distgen *g = (orc_distgen *)calloc(1, sizeof *g);
+    int sup[4][5];
+    orc_supply(cards, sup);
+    for (int s = 0; s < 4; ++s) {
+        g->lc_supply[s] = sup[s][0];
+        for (int h = 0; h < 4; ++h) g->hon[s][h] = sup[s][1 + h];
+    }
+    g->spec = *spec;
+    g->cards = cards;
+    build_patterns(g);
+    g->total = 0;
+    for (int i = 0; i < g->npat; ++i) g->total += pattern_weight(g, g->pat[i], NULL, NULL, NULL);
+    return g;
+}
+ORC_API void orc_distgen_free(orc_distgen *g) { if (g) { free(g->pat); free(g); } }
+ORC_API int orc_distgen_npat(const orc_distgen *g) { return g->npat; }
+ORC_API uint64_t orc_distgen_total(const orc_distgen *g) { return g->total; }
+/* bridge.cl:1038-1045 next: i-th (weight pattern) */
+ORC_API uint64_t orc_distgen_item(const orc_distgen *g, int i, unsigned *pat)
+{
+    *pat = g->pat[i];
+    return pattern_weight(g, g->pat[i], NULL, NULL, NULL);
+}
+
+/* Exact distribution of one constrained hand, from the enumeration:
+ * hcp_num[38]: number of admissible hands by HCP; len_num[4][14] by suit length. */
+ORC_API void orc_distgen_pmf(const orc_distgen *g, uint64_t hcp_num[38], uint64_t len_num[4][14])
+{
+    static __thread int lc[20000][4];
+    static __thread uint64_t w[20000];
+    memset(hcp_num, 0, 38 * sizeof(uint64_t));
+    memset(len_num, 0, 4 * 14 * sizeof(uint64_t));
+    for (int i = 0; i < g->npat; ++i) {
+        int n;
+        unsigned pat = g->pat[i];
+        pattern_weight(g, pat, lc, w, &n);
+        int hcp = pat_hcp(pat);
+        for (int k = 0; k < n; ++k) {
+            hcp_num[hcp] += w[k];
+            for (int s = 0; s < 4; ++s) {
+                int b = 0;
+                for (int h = 0; h < 4; ++h) b += pat_bit(pat, s, h);
+                len_num[s][lc[k][s] + b] += w[k];
+            }
+        }
+    }
+}
+
+/* bridge.cl:646-650 deal: `amount` uniform picks without replacement from a pile */
+static void deal_from(orc_rng *r, int *pile, int *npile, int amount, int *out, int *nout)
+{
+    for (int k = 0; k < amount; ++k) {
+        int idx = (int)rng_below(r, (uint64_t)*npile);          /* (random (length lst)) */
+        out[(*nout)++] = pile[idx];
+        memmove(pile + idx, pile + idx + 1, sizeof(int) * (size_t)(*npile - idx - 1));   /* take, bridge.cl:627-634 */
+        --*npile;
+    }
+}
+
+/* bridge.cl:1075-1083 rand-hand: re-walks the pattern list recomputing every
+ * weight (the per-deal rescan), with the reference's `>` comparison; then
+ * rand-dist (1061-1063) / dist-from-hc (1053-1059) / randcar-weights (289-296)
+ * and distrib-hand (1065-1071).  Returns the hand as a 52-bit card mask. */
+ORC_API uint64_t orc_rand_hand(orc_distgen *g, uint64_t *rng_state)
+{
+    static __thread int lc[20000][4];
+    static __thread uint64_t w[20000];
+    orc_rng r = { *rng_state };
+    uint64_t x = rng_below(&r, g->total);
+    int cur = 0;
+    for (;; ++cur) {
+        uint64_t wt = pattern_weight(g, g->pat[cur], NULL, NULL, NULL);
+        if (!(x > wt)) break;
+        x -= wt;
+    }
+    unsigned pat = g->pat[cur];
+    int n;
+    uint64_t tot = pattern_weight(g, pat, lc, w, &n);
+    int pick = 0;
+    if (tot > 0) {
+        uint64_t y = rng_below(&r, tot);
+        for (pick = 0; pick < n; ++pick) { if (y < w[pick]) break; y -= w[pick]; }
+    }
+    uint64_t hand = 0;
+    for (int s = 0; s < 4; ++s) {
+        unsigned lane = (unsigned)(g->cards >> (13 * s)) & 0x1FFFu;
+        int pile[13], np = 0, got[13], ng = 0;
+        for (int rk = 0; rk <= 8; ++rk) if (lane >> rk & 1) pile[np++] = rk;
+        deal_from(&r, pile, &np, tot > 0 ? lc[pick][s] : 0, got, &ng);
+        for (int k = 0; k < ng; ++k) hand |= 1ull << (13 * s + got[k]);
+        for (int h = 0; h < 4; ++h)
+            if (pat_bit(pat, s, h)) hand |= 1ull << (13 * s + 9 + h);
+    }
+    *rng_state = r.s;
+    return hand;
+}
+
+/* bridge.cl:655-658 deal-all 13 on the remaining cards: out[] gets the hands
+ * in the order they are dealt; returns their number */
+ORC_API int orc_deal_all(uint64_t rest, uint64_t *rng_state, uint64_t *out)
+{
+    orc_rng r = { *rng_state };
+    int pile[52], np = 0, nh = 0;
+    for (int c = 0; c < 52; ++c) if (rest >> c & 1) pile[np++] = c;
+    while (np > 0) {
+        int got[13], ng = 0;
+        deal_from(&r, pile, &np, np < 13 ? np : 13, got, &ng);
+        uint64_t h = 0;
+        for (int k = 0; k < ng; ++k) h |= 1ull << got[k];
+        out[nh++] = h;
+    }
+    *rng_state = r.s;
+    return nh;
+}
+
+/* bridge.cl:1292-1319 build for the two shapes bench/tests need: no const
+ * hands, zero or one ranged seat (spec may be NULL = `(make-instance 'deal)`),
+ * remaining seats by deal-all.  The root distgen is cached by the caller like
+ * the reference's `rootgen` slot.  out[0] = the sampled seat, out[1..3] rest. */
+ORC_API void orc_build_one(orc_distgen *root, uint64_t *rng_state, uint64_t out[4])
+{
+    uint64_t hand = orc_rand_hand(root, rng_state);
+    out[0] = hand;
+    orc_deal_all(root->cards & ~hand, rng_state, out + 1);
+}
+
+/* ------------------------------------------------------------------ */
+/* CPU mirror of the GPU sampler (csrc/deal.cuh) for bit-exact checks */
+/* ------------------------------------------------------------------ */
+static inline void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+/* Philox4x32-10 (Salmon et al. 2011) */
+ORC_API void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c[4] = { ctr[0], ctr[1], ctr[2], ctr[3] };
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    memcpy(out, c, sizeof c);
+}
+
+/* digit groups: word g supplies the bounded draws n = GRP_HI[g] .. GRP_LO[g] */
+static const int GRP_HI[12] = {52, 48, 44, 40, 36, 32, 28, 24, 20, 16, 11, 5};
+static const int GRP_LO[12] = {49, 45, 41, 37, 33, 29, 25, 21, 17, 12, 6, 2};
+
+/* One raw deal of the GPU sampler: returns 0 and the two owner bit-planes
+ * (16-bit lane per suit, bit = rank), or 1 if the index is void (a biased
+ * bounded draw was rejected).  Mirrors bmc::deal52() in csrc/deal.cuh. */
+ORC_API int orc_gpu_deal(uint64_t seed, uint64_t index, uint64_t *lo_plane, uint64_t *hi_plane)
+{
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t w[12];
+    for (uint32_t b = 0; b < 3; ++b) {
+        uint32_t ctr[4] = { (uint32_t)index, (uint32_t)(index >> 32), b, 0 };
+        orc_philox4x32_10(ctr, key, w + 4 * b);
+    }
+    int digit[53];
+    int voided = 0;
+    for (int g = 0; g < 12; ++g) {
+        uint32_t x = w[g];
+        uint64_t N = 1;
+        for (int n = GRP_HI[g]; n >= GRP_LO[g]; --n) {
+            uint64_t p = (uint64_t)x * (uint32_t)n;
+            digit[n] = (int)(p >> 32);
+            x = (uint32_t)p;
+            N *= (uint64_t)n;
+        }
+        uint32_t thresh = (uint32_t)((((uint64_t)1) << 32) % N);
+        if (x < thresh) voided = 1;
+    }
+    digit[1] = 0;
+    int rem[4] = {13, 13, 13, 13};
+    uint64_t lo = 0, hi = 0;
+    for (int p = 0; p < 52; ++p) {
+        int n = 52 - p, u = digit[n], owner = 0, acc = 0;
+        for (owner = 0; owner < 4; ++owner) { acc += rem[owner]; if (u < acc) break; }
+        --rem[owner];
+        int suit = p / 13, rank = p % 13, bit = 16 * suit + rank;
+        lo |= (uint64_t)(owner & 1) << bit;
+        hi |= (uint64_t)(owner >> 1) << bit;
+    }
+    *lo_plane = lo; *hi_plane = hi;
+    return voided;
+}
+
+/* ------------------------------------------------------------------ */
+/* Batch helpers (plain loops over the functions above)               */
+/* ------------------------------------------------------------------ */
+static void lanes64_to_suits(uint64_t m, uint16_t s[4])
+{
+    for (int i = 0; i < 4; ++i) s[i] = (uint16_t)((m >> (16 * i)) & 0x1FFFu);
+}
+ORC_API void orc_features_batch(const uint64_t *masks, uint64_t n, int32_t *out)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        uint16_t s[4];
+        int f[11];
+        lanes64_to_suits(masks[i], s);
+        orc_assess(s, f);
+        for (int k = 0; k < 11; ++k) out[11 * i + k] = f[k];
+    }
+}
+ORC_API void orc_choose_bid_batch(int scheme, const uint64_t *masks, uint64_t n, int32_t *out)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        uint16_t s[4];
+        lanes64_to_suits(masks[i], s);
+        out[i] = orc_choose_bid(scheme, s);
+    }
+}
+ORC_API void orc_gpu_deal_batch(uint64_t seed, uint64_t first, uint64_t n, uint64_t *rec, uint8_t *voided)
+{
+    for (uint64_t i = 0; i < n; ++i)
+        voided[i] = (uint8_t)orc_gpu_deal(seed, first + i, &rec[2 * i], &rec[2 * i + 1]);
+}
+ORC_API void orc_build_batch(orc_distgen *root, uint64_t *rng_state, uint64_t n, uint64_t *out)
+{
+    for (uint64_t i = 0; i < n; ++i) orc_build_one(root, rng_state, out + 4 * i);
+}
+
+/* Reference-algorithm run for the bench's CPU arm: n x (`build` of a deal whose
+ * single ranged seat uses `root`, bridge.cl:1292-1319) followed by the
+ * `test-bid` filter of opening row `rule_k` on the sampled hand (the only way
+ * the reference gets bidding-constrained deals, SURVEY finding 0.5).
+ * Returns the number of deals that pass. */
+ORC_API uint64_t orc_ref_run(orc_distgen *root, uint64_t *rng_state, uint64_t n, int rule_k, uint64_t *checksum)
+{
+    uint64_t pass = 0, sum = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t hands[4];
+        orc_build_one(root, rng_state, hands);
+        uint16_t s[4];
+        for (int k = 0; k < 4; ++k) s[k] = (uint16_t)((hands[0] >> (13 * k)) & 0x1FFFu);
+        if (rule_k < 0 || orc_test_bid(0, rule_k, s)) ++pass;
+        sum += hands[0] ^ hands[1] ^ (hands[2] << 1) ^ (hands[3] << 2);
+    }
+    if (checksum) *checksum = sum;
+    return pass;
+}

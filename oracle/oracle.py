@@ -1,0 +1,220 @@
+"""ctypes front-end of the CPU oracle (oracle/bmc_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of bmc_oracle.c.  Imported by
+tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs; never by the
+product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(HERE, "libbmc_oracle.so")
+    src = os.path.join(HERE, "bmc_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-s", "-B"])
+    return so
+
+
+class Spec(C.Structure):
+    """orc_spec: -1 = nil."""
+    _fields_ = [("hcp_lo", C.c_int), ("hcp_hi", C.c_int), ("has_hcp", C.c_int),
+                ("len_lo", C.c_int * 4), ("len_hi", C.c_int * 4),
+                ("shcp_lo", C.c_int * 4), ("shcp_hi", C.c_int * 4), ("has_shcp", C.c_int * 4)]
+
+
+def make_spec(hcp=None, c=None, d=None, h=None, s=None) -> Spec:
+    """Range spec in the reference's keyword form: number | (lo hi) | (lo hi (slo shi))."""
+    sp = Spec()
+    sp.has_hcp = 0
+    sp.hcp_lo = sp.hcp_hi = -1
+    if hcp is not None:
+        sp.has_hcp = 1
+        lo, hi = (hcp, hcp) if isinstance(hcp, int) else (hcp[0], hcp[1])
+        sp.hcp_lo = -1 if lo is None else lo
+        sp.hcp_hi = -1 if hi is None else hi
+    for i, spec in enumerate((c, d, h, s)):
+        sp.len_lo[i] = sp.len_hi[i] = -1
+        sp.shcp_lo[i] = sp.shcp_hi[i] = -1
+        sp.has_shcp[i] = 0
+        if spec is None:
+            continue
+        if isinstance(spec, int):
+            sp.len_lo[i] = sp.len_hi[i] = spec
+            continue
+        sp.len_lo[i] = -1 if spec[0] is None else spec[0]
+        sp.len_hi[i] = -1 if spec[1] is None else spec[1]
+        if len(spec) > 2 and spec[2] is not None:
+            sp.has_shcp[i] = 1
+            sh = spec[2]
+            lo, hi = (sh, sh) if isinstance(sh, int) else (sh[0], sh[1])
+            sp.shcp_lo[i] = -1 if lo is None else lo
+            sp.shcp_hi[i] = -1 if hi is None else hi
+    return sp
+
+
+FULL_DECK = (1 << 52) - 1
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    u16x4 = C.c_uint16 * 4
+    i11 = C.c_int * 11
+    L.orc_suit_hcp.argtypes = [C.c_uint]
+    L.orc_suit_losers.argtypes = [C.c_uint]
+    L.orc_assess.argtypes = [u16x4, i11]
+    L.orc_assess.restype = None
+    L.orc_choose_bid.argtypes = [C.c_int, u16x4]
+    L.orc_test_bid.argtypes = [C.c_int, C.c_int, u16x4]
+    L.orc_test_rule.argtypes = [C.c_int, C.c_int, i11]
+    L.orc_scheme_size.argtypes = [C.c_int]
+    L.orc_contract_score.argtypes = [C.c_int] * 5
+    L.orc_base_score.argtypes = [C.c_int] * 6
+    L.orc_imps.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    L.orc_combinations.argtypes = [C.c_int, C.c_int]
+    L.orc_combinations.restype = C.c_uint64
+    L.orc_supply.argtypes = [C.c_uint64, (C.c_int * 5) * 4]
+    L.orc_supply.restype = None
+    L.orc_distgen_new.argtypes = [C.c_uint64, C.POINTER(Spec)]
+    L.orc_distgen_new.restype = C.c_void_p
+    L.orc_distgen_free.argtypes = [C.c_void_p]
+    L.orc_distgen_free.restype = None
+    L.orc_distgen_npat.argtypes = [C.c_void_p]
+    L.orc_distgen_total.argtypes = [C.c_void_p]
+    L.orc_distgen_total.restype = C.c_uint64
+    L.orc_distgen_item.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint)]
+    L.orc_distgen_item.restype = C.c_uint64
+    L.orc_distgen_pmf.argtypes = [C.c_void_p, C.c_uint64 * 38, (C.c_uint64 * 14) * 4]
+    L.orc_distgen_pmf.restype = None
+    L.orc_rand_hand.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.orc_rand_hand.restype = C.c_uint64
+    L.orc_deal_all.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.orc_build_one.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64 * 4]
+    L.orc_build_one.restype = None
+    L.orc_philox4x32_10.argtypes = [C.c_uint32 * 4, C.c_uint32 * 2, C.c_uint32 * 4]
+    L.orc_philox4x32_10.restype = None
+    L.orc_gpu_deal.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.orc_features_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.orc_features_batch.restype = None
+    L.orc_choose_bid_batch.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.orc_choose_bid_batch.restype = None
+    L.orc_gpu_deal_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.orc_gpu_deal_batch.restype = None
+    L.orc_build_batch.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p]
+    L.orc_build_batch.restype = None
+    _LIB = L
+    return L
+
+
+# ---- convenience wrappers -------------------------------------------------
+
+def lanes_of(hand) -> "C.Array":
+    """Hand (bridge_mc_b200.cards.Hand or 4 rank lists) -> c_uint16[4] rank masks."""
+    suits = getattr(hand, "suits", hand)
+    return (C.c_uint16 * 4)(*[sum(1 << r for r in s) for s in suits])
+
+
+def assess(hand):
+    """assess-hand: dict(lens, power, hcp, losers, balanced)."""
+    out = (C.c_int * 11)()
+    lib().orc_assess(lanes_of(hand), out)
+    v = list(out)
+    return {"lens": v[0:4], "power": v[4:8], "hcp": v[8], "losers": v[9], "balanced": bool(v[10])}
+
+
+def choose_bid(scheme: int, hand) -> int:
+    return lib().orc_choose_bid(scheme, lanes_of(hand))
+
+
+def test_bid(scheme: int, k: int, hand) -> bool:
+    return bool(lib().orc_test_bid(scheme, k, lanes_of(hand)))
+
+
+def imps(diff: int):
+    out = C.c_int()
+    return out.value if lib().orc_imps(diff, C.byref(out)) == 0 else None
+
+
+class Distgen:
+    def __init__(self, cards=FULL_DECK, **spec):
+        self._sp = make_spec(**spec)
+        self._g = lib().orc_distgen_new(cards, C.byref(self._sp))
+
+    def __del__(self):
+        if getattr(self, "_g", None):
+            lib().orc_distgen_free(self._g)
+            self._g = None
+
+    @property
+    def npat(self):
+        return lib().orc_distgen_npat(self._g)
+
+    @property
+    def total(self):
+        return lib().orc_distgen_total(self._g)
+
+    def items(self):
+        p = C.c_uint()
+        L = lib()
+        for i in range(self.npat):
+            w = L.orc_distgen_item(self._g, i, C.byref(p))
+            yield w, p.value
+
+    def pmf(self):
+        hcp = (C.c_uint64 * 38)()
+        lens = ((C.c_uint64 * 14) * 4)()
+        lib().orc_distgen_pmf(self._g, hcp, lens)
+        return list(hcp), [list(r) for r in lens]
+
+    def rand_hand(self, state: "C.c_uint64"):
+        return lib().orc_rand_hand(self._g, C.byref(state))
+
+    def build_batch(self, n: int, seed: int = 1) -> np.ndarray:
+        """n `build`s (one ranged seat at seat 0 + deal-all): uint64[n,4] hand masks (52-bit, id order)."""
+        out = np.empty((n, 4), dtype=np.uint64)
+        st = C.c_uint64(seed)
+        lib().orc_build_batch(self._g, C.byref(st), n, out.ctypes.data)
+        return out
+
+
+def features_batch(seat_masks64: np.ndarray) -> np.ndarray:
+    """uint64[m] 16-bit-lane hand masks -> int32[m, 11] assess-hand vectors."""
+    m = np.ascontiguousarray(seat_masks64, dtype=np.uint64).reshape(-1)
+    out = np.empty((m.size, 11), dtype=np.int32)
+    lib().orc_features_batch(m.ctypes.data, m.size, out.ctypes.data)
+    return out
+
+
+def choose_bid_batch(scheme: int, seat_masks64: np.ndarray) -> np.ndarray:
+    m = np.ascontiguousarray(seat_masks64, dtype=np.uint64).reshape(-1)
+    out = np.empty(m.size, dtype=np.int32)
+    lib().orc_choose_bid_batch(scheme, m.ctypes.data, m.size, out.ctypes.data)
+    return out
+
+
+def gpu_deal_batch(seed: int, first: int, n: int):
+    """CPU mirror of the GPU sampler: (records uint64[n,2], void uint8[n])."""
+    rec = np.empty((n, 2), dtype=np.uint64)
+    void = np.empty(n, dtype=np.uint8)
+    lib().orc_gpu_deal_batch(seed, first, n, rec.ctypes.data, void.ctypes.data)
+    return rec, void
+
+
+def mask52_to_lanes64(m52: np.ndarray) -> np.ndarray:
+    """52-bit id-order card masks -> 16-bit-lane 64-bit masks."""
+    m = np.asarray(m52, dtype=np.uint64)
+    out = np.zeros_like(m)
+    for s in range(4):
+        out |= ((m >> np.uint64(13 * s)) & np.uint64(0x1FFF)) << np.uint64(16 * s)
+    return out

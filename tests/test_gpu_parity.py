@@ -1,0 +1,204 @@
+"""GPU parity tests: every call goes through the C ABI (libbridgemc.so) and is
+checked against the CPU oracle (oracle/bmc_oracle.c) on the same inputs."""
+import numpy as np
+import pytest
+
+from bridge_mc_b200 import bidding
+from bridge_mc_b200.cards import seat_masks
+from bridge_mc_b200.engine import Constraints, seat_spec
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x6272696467656D63
+
+
+def sort_records(rec):
+    rec = np.ascontiguousarray(rec, dtype=np.uint64).reshape(-1, 2)
+    order = np.lexsort((rec[:, 0], rec[:, 1]))
+    return rec[order]
+
+
+def oracle_features(rec):
+    """int32[n,4,11] assess-hand vectors of the four seats"""
+    m = seat_masks(rec)
+    return O.features_batch(m.reshape(-1)).reshape(-1, 4, 11)
+
+
+@pytest.mark.parametrize("first,n", [(0, 1), (0, 31), (5, 1000), (123456789012, 200_000)])
+def test_sampler_bit_exact_vs_cpu_mirror(engine, first, n):
+    rec, tal, st = engine.sample(None, n_raw=n, seed=SEED, first_index=first)
+    ref, void = O.gpu_deal_batch(SEED, first, n)
+    assert tal["raw"] == n
+    assert tal["voided"] == int(void.sum())
+    assert tal["accepted"] == n - int(void.sum()) == rec.shape[0]
+    assert np.array_equal(sort_records(rec), sort_records(ref[void == 0]))
+
+
+def test_every_record_is_a_deal(engine):
+    rec, _, _ = engine.sample(None, n_raw=100_000, seed=7)
+    m = seat_masks(rec)
+    pc = np.zeros(m.shape, dtype=np.int64)
+    for b in range(64):
+        pc += ((m >> np.uint64(b)) & np.uint64(1)).astype(np.int64)
+    assert (pc == 13).all()
+    assert ((m[:, 0] | m[:, 1] | m[:, 2] | m[:, 3]) == np.uint64(0x1FFF1FFF1FFF1FFF)).all()
+
+
+def test_features_bit_exact(engine):
+    rec, _, _ = engine.sample(None, n_raw=100_000, seed=11)
+    acc, feats = engine.filter(rec)
+    ref = oracle_features(rec)
+    assert (acc == 1).all()
+    assert np.array_equal(feats["len"].astype(np.int32), ref[:, :, 0:4])
+    assert np.array_equal(feats["suit_hcp"].astype(np.int32), ref[:, :, 4:8])
+    assert np.array_equal(feats["hcp"].astype(np.int32), ref[:, :, 8])
+    assert np.array_equal(feats["losers"].astype(np.int32), ref[:, :, 9])
+    assert np.array_equal(feats["balanced"].astype(np.int32), ref[:, :, 10])
+
+
+@pytest.mark.parametrize("scheme_id,table", [(0, bidding.openings), (1, bidding.nt_responses(1)),
+                                             (2, bidding.nt_responses(2)), (3, bidding.two_c_responses)])
+def test_choose_bid_bit_exact(engine, scheme_id, table):
+    rec, _, _ = engine.sample(None, n_raw=60_000, seed=13 + scheme_id)
+    _, feats = engine.filter(rec, None, table.scheme())
+    ref = O.choose_bid_batch(scheme_id, seat_masks(rec).reshape(-1)).reshape(-1, 4)
+    assert np.array_equal(feats["bid"].astype(np.int32), ref)
+    assert len(np.unique(ref)) > 3
+
+
+def test_accept_flags_1nt_south(engine):
+    rule = bidding.openings.form((1, "NT"))
+    cons = Constraints(None, [None, None, rule, None])
+    rec, _, _ = engine.sample(None, n_raw=200_000, seed=17)
+    acc, _ = engine.filter(rec, cons, None, want_features=False)
+    south = seat_masks(rec)[:, 2]
+    f = O.features_batch(south)
+    ref = np.array([O.lib().orc_test_rule(0, 2, (O.C.c_int * 11)(*row)) for row in f.tolist()], dtype=np.uint8)
+    assert np.array_equal(acc, ref)
+    assert 0.03 < acc.mean() < 0.046
+
+
+def test_constrained_sampler_equals_filtered_stream(engine):
+    """rejection sampling = filtering the raw stream: same accepted set"""
+    rule = bidding.openings.form((1, "NT"))
+    cons = Constraints(None, [None, None, rule, None])
+    n = 300_000
+    got, tal, _ = engine.sample(cons, n_raw=n, seed=SEED, first_index=1000)
+    ref, void = O.gpu_deal_batch(SEED, 1000, n)
+    ref = ref[void == 0]
+    acc, _ = engine.filter(ref, cons, None, want_features=False)
+    assert tal["accepted"] == int(acc.sum()) == got.shape[0]
+    assert np.array_equal(sort_records(got), sort_records(ref[acc == 1]))
+
+
+def test_tallies_match_features(engine):
+    cons = Constraints([None, None, seat_spec(hcp=(12, 20), s=(5, None)), None])
+    rec, tal, _ = engine.sample(cons, n_raw=400_000, seed=23)
+    _, feats = engine.filter(rec)
+    assert tal["accepted"] == rec.shape[0] > 1000
+    for k in range(4):
+        assert np.array_equal(tal["hcp"][k], np.bincount(feats["hcp"][:, k], minlength=38)[:38])
+        for s in range(4):
+            assert np.array_equal(tal["len"][k, s], np.bincount(feats["len"][:, k, s], minlength=14))
+    assert (feats["hcp"][:, 2] >= 12).all() and (feats["hcp"][:, 2] <= 20).all() and (feats["len"][:, 2, 3] >= 5).all()
+    from bridge_mc_b200._lib import shape_table
+    shapes = [tuple(r) for r in shape_table().tolist()]
+    for k in range(4):
+        srt = np.sort(feats["len"][:, k, :], axis=1)[:, ::-1]
+        cls = np.array([shapes.index(tuple(r)) for r in srt.tolist()])
+        assert np.array_equal(tal["shape"][k], np.bincount(cls, minlength=39))
+
+
+def test_scores_bit_exact_full_table(engine):
+    from bridge_mc_b200._lib import Contract
+    L = O.lib()
+    contracts, vul, meta = [], [], []
+    for suit in range(5):
+        for level in range(0, 8):
+            for dbl in range(3):
+                for decl in (-1, 0, 1, 2, 3):
+                    for v in (0, 1):
+                        contracts.append(Contract(level, suit, decl, dbl))
+                        vul.append(v)
+                        meta.append((level, suit, decl, dbl, v))
+    for lo in range(0, len(contracts), 8):
+        cs, vs, ms = contracts[lo:lo + 8], vul[lo:lo + 8], meta[lo:lo + 8]
+        tricks = np.repeat(np.arange(14, dtype=np.uint8)[:, None], len(cs), axis=1)
+        got = engine.score(cs, vs, tricks)
+        for j, (level, suit, decl, dbl, v) in enumerate(ms):
+            for t in range(14):
+                assert got[t, j] == L.orc_base_score(level, suit, decl, dbl, t, v), (level, suit, decl, dbl, v, t)
+
+
+def test_match_points_bit_exact(engine):
+    rng = np.random.default_rng(5)
+    a = rng.integers(-7600, 2981, size=50_000).astype(np.int32)
+    b = rng.integers(-7600, 2981, size=50_000).astype(np.int32)
+    imps, status = engine.match_points(a, b)
+    for i in range(0, 50_000, 7):
+        ref = O.imps(int(a[i]) - int(b[i]))
+        if ref is None:
+            assert status[i] == 1
+        else:
+            assert status[i] == 0 and imps[i] == ref
+
+
+def _chi2_p(obs, exp):
+    from scipy.stats import chi2
+    obs, exp = np.asarray(obs, float), np.asarray(exp, float)
+    # merge bins until every expected count >= 5
+    order = np.argsort(exp)
+    o, e, mo, me = [], [], 0.0, 0.0
+    for i in order:
+        mo += obs[i]; me += exp[i]
+        if me >= 5:
+            o.append(mo); e.append(me); mo = me = 0.0
+    if me > 0 and e:
+        o[-1] += mo; e[-1] += me
+    o, e = np.array(o), np.array(e)
+    stat = ((o - e) ** 2 / e).sum()
+    return chi2.sf(stat, len(o) - 1)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_chi_square_unconstrained(engine, seed):
+    """HCP (38 bins) and sorted shape (39 bins) of every seat against the exact pmfs;
+    parity is rejected if p < 1e-3."""
+    from math import comb
+    from bridge_mc_b200._lib import shape_table
+    n = 20_000_000
+    _, tal, _ = engine.sample(None, n_raw=n, seed=seed, cap=0)
+    acc = tal["accepted"]
+    hcp_num, _ = O.Distgen(c=(0, 13), d=(0, 13), h=(0, 13), s=(0, 13)).pmf()
+    total = comb(52, 13)
+    assert sum(hcp_num) == total
+    exp_hcp = np.array(hcp_num, float) / total * acc
+    shape_w = []
+    for a, b, c, d in shape_table().tolist():
+        from itertools import permutations
+        shape_w.append(sum(comb(13, p[0]) * comb(13, p[1]) * comb(13, p[2]) * comb(13, p[3])
+                           for p in set(permutations((a, b, c, d)))))
+    assert sum(shape_w) == total
+    exp_shape = np.array(shape_w, float) / total * acc
+    for k in range(4):
+        assert _chi2_p(tal["hcp"][k], exp_hcp) > 1e-3
+        assert _chi2_p(tal["shape"][k], exp_shape) > 1e-3
+
+
+def test_c2_acceptance_rate_exact(engine):
+    """South `test-bid (1 NT)`: acceptance 24 235 203 726 / C(52,13) and the exact
+    15/16/17 split, within 4 sigma."""
+    rule = bidding.openings.form((1, "NT"))
+    cons = Constraints(None, [None, None, rule, None])
+    n = 50_000_000
+    _, tal, _ = engine.sample(cons, n_raw=n, seed=99, cap=0)
+    valid = tal["raw"] - tal["voided"]
+    p = 24235203726 / 635013559600
+    sigma = (valid * p * (1 - p)) ** 0.5
+    assert abs(tal["accepted"] - valid * p) < 4 * sigma
+    split = np.array([9820068156, 8126568540, 6288567030], float)
+    exp = split / split.sum() * tal["accepted"]
+    obs = tal["hcp"][2][15:18]
+    assert obs.sum() == tal["accepted"]
+    assert _chi2_p(obs, exp) > 1e-3
