@@ -26,6 +26,7 @@
 //     instructions per card: IMAD.WIDE, IMAD, LOP3, 2 x LEA.HI.
 #pragma once
 #include <cstdint>
+#include <utility>
 
 namespace bmc {
 
@@ -82,51 +83,80 @@ __host__ __device__ constexpr uint32_t grp_thresh(int g)
     return (uint32_t)((1ull << 32) % N);
 }
 
+// 32x32 -> 64 multiply split into (lo, hi).  Written in PTX so that the compiler
+// keeps one IMAD.WIDE per digit (the C form picks up a redundant mask and add).
+__device__ __forceinline__ void mul_wide(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
+{
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+
 struct Planes { uint32_t lo0, lo1, hi0, hi1; };   // lo plane (c,d | h,s), hi plane (c,d | h,s)
 
-// Returns true when the index is void.  caps_q = initial Q (bytes 128 - prefix_j).
-__device__ __forceinline__ bool deal52(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, Planes &pl)
+struct DealState {
+    uint32_t w[4];      // current Philox block
+    uint32_t x;         // running fraction of the current word
+    uint32_t Q;         // bytes 128 - prefix_j
+    uint32_t acc;       // t-bit history of the current byte group
+    uint32_t lo[2], hi[2];
+    bool voided;
+};
+
+// One card.  P is a true compile-time constant so that every table lookup, the
+// Lemire threshold and all shift counts fold to immediates.
+template <int P>
+__device__ __forceinline__ void deal_step(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, DealState &s)
 {
-    uint32_t w[4];
-    uint32_t x = 0;
-    uint32_t Q = (128u - 13u) | ((128u - 26u) << 8) | ((128u - 39u) << 16);
-    uint32_t acc = 0;
-    uint32_t lo[2] = {0u, 0u}, hi[2] = {0u, 0u};
-    bool voided = false;
-#pragma unroll
-    for (int p = 0; p < 52; ++p) {
-        const int n = 52 - p;
-        uint32_t u = 0;
-        if (n >= 2) {
-            const int g = grp_of(n);
-            if (n == grp_hi(g)) {
-                if ((g & 3) == 0) philox4x32_10(key, idx_lo, idx_hi, (uint32_t)(g >> 2), 0u, w);
-                x = w[g & 3];
-            }
-            uint64_t prod = (uint64_t)x * (uint32_t)n;
-            u = (uint32_t)(prod >> 32);
-            x = (uint32_t)prod;
-            if (n == grp_lo(g)) voided |= x < grp_thresh(g);
+    constexpr int n = 52 - P;
+    uint32_t u = 0;
+    if constexpr (n >= 2) {
+        constexpr int g = grp_of(n);
+        if constexpr (n == grp_hi(g)) {
+            if constexpr ((g & 3) == 0) philox4x32_10(key, idx_lo, idx_hi, (uint32_t)(g >> 2), 0u, s.w);
+            s.x = s.w[g & 3];
         }
-        const uint32_t E = u * 0x010101u + Q;
-        const uint32_t T7 = ~E & 0x808080u;      // bit 7 of byte j: u < prefix_j
-        Q += T7 >> 7;
-        const int rank = p % 13, suit = p / 13;
-        const int i = rank < 8 ? rank : rank - 8;           // position inside the byte group
-        acc += T7 >> (7 - i);
-        if (rank == 7 || rank == 12) {
-            const uint32_t mask = rank == 7 ? 0xFFu : 0x1Fu;
-            const uint32_t par = acc ^ (acc >> 8) ^ (acc >> 16);
-            const uint32_t lob = ~par & mask;               // owner bit 0 = !(t0^t1^t2)
-            const uint32_t hib = ~(acc >> 8) & mask;        // owner bit 1 = !t1
-            const int sh = 16 * (suit & 1) + (rank == 7 ? 0 : 8);
-            lo[suit >> 1] |= lob << sh;
-            hi[suit >> 1] |= hib << sh;
-            acc = 0;
+        mul_wide(s.x, (uint32_t)n, s.x, u);
+        if constexpr (n == grp_lo(g)) {
+            constexpr uint32_t thresh = grp_thresh(g);
+            s.voided |= s.x < thresh;
         }
     }
-    pl.lo0 = lo[0]; pl.lo1 = lo[1]; pl.hi0 = hi[0]; pl.hi1 = hi[1];
-    return voided;
+    const uint32_t E = u * 0x010101u + s.Q;
+    const uint32_t T7 = ~E & 0x808080u;          // bit 7 of byte j: u < prefix_j
+    s.Q += T7 >> 7;
+    constexpr int rank = P % 13, suit = P / 13;
+    constexpr int i = rank < 8 ? rank : rank - 8;   // position inside the byte group
+    s.acc += T7 >> (7 - i);
+    if constexpr (rank == 7 || rank == 12) {
+        constexpr uint32_t mask = rank == 7 ? 0xFFu : 0x1Fu;
+        const uint32_t par = s.acc ^ (s.acc >> 8) ^ (s.acc >> 16);
+        const uint32_t lob = ~par & mask;               // owner bit 0 = !(t0^t1^t2)
+        const uint32_t hib = ~(s.acc >> 8) & mask;      // owner bit 1 = !t1
+        constexpr int sh = 16 * (suit & 1) + (rank == 7 ? 0 : 8);
+        s.lo[suit >> 1] |= lob << sh;
+        s.hi[suit >> 1] |= hib << sh;
+        s.acc = 0;
+    }
+}
+
+template <int... P>
+__device__ __forceinline__ void deal_all_steps(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, DealState &s,
+                                               std::integer_sequence<int, P...>)
+{
+    (deal_step<P>(key, idx_lo, idx_hi, s), ...);
+}
+
+// Returns true when the index is void.
+__device__ __forceinline__ bool deal52(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, Planes &pl)
+{
+    DealState s;
+    s.x = 0;
+    s.Q = (128u - 13u) | ((128u - 26u) << 8) | ((128u - 39u) << 16);
+    s.acc = 0;
+    s.lo[0] = s.lo[1] = s.hi[0] = s.hi[1] = 0u;
+    s.voided = false;
+    deal_all_steps(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 52>{});
+    pl.lo0 = s.lo[0]; pl.lo1 = s.lo[1]; pl.hi0 = s.hi[0]; pl.hi1 = s.hi[1];
+    return s.voided;
 }
 
 // bounded draw helper for the score tally: uniform 0..13 from 16 random bits
