@@ -63,6 +63,7 @@ __constant__ uint8_t c_shape_lut[14 * 14 * 14];   // (len_c, len_d, len_h) -> so
 struct SampleArgs {
     ConsDev cons;
     PhiloxKey key;
+    FixDev fix;
     uint64_t first, n;
     uint4 *records;          // may be null
     uint64_t cap;
@@ -127,7 +128,7 @@ __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, b
     }
 }
 
-template <bool HAS_CONS>
+template <bool HAS_CONS, bool FIXED>
 __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__ SampleArgs a)
 {
     __shared__ uint32_t s_hist[WARPS_PER_BLOCK][SH_WORDS];
@@ -150,7 +151,8 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
         const bool valid = off < a.n;
         const unsigned long long idx = a.first + off;
         Planes pl;
-        const bool voided = deal52(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
+        const bool voided = FIXED ? deal_fixed(a.key, a.fix, (uint32_t)idx, (uint32_t)(idx >> 32), pl)
+                                  : deal52(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
         n_raw += valid ? 1u : 0u;
         n_void += (valid && voided) ? 1u : 0u;
         bool ok = valid && !voided;
@@ -457,6 +459,7 @@ struct bmc_constraints {
     int d_device = -1;
     bool has_cons = false;
     bool has_fixed = false;
+    FixDev fix{};
     std::mutex mu;
 };
 
@@ -538,9 +541,9 @@ int bmc_init(int device, bmc_ctx **out)
         CUDA_TRY(cudaMemcpyToSymbol(c_shape_lut, g_shape_lut, sizeof g_shape_lut));
     }
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<true>, THREADS, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<true, false>, THREADS, 0));
     c->blocks_cons = c->sms * (occ > 0 ? occ : 1);
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<false>, THREADS, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<false, false>, THREADS, 0));
     c->blocks_free = c->sms * (occ > 0 ? occ : 1);
     *out = c;
     return BMC_OK;
@@ -624,6 +627,8 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     std::unique_ptr<bmc_constraints> c(new bmc_constraints());
     RuleCompiler rc;
     uint64_t fixed_union = 0;
+    uint64_t fixed_mask[4] = {0, 0, 0, 0};
+    bool is_fixed[4] = {false, false, false, false};
     int total_lo[F_COUNT] = {0};
     double selectivity[4] = {0, 0, 0, 0};
     for (int k = 0; k < 4; ++k) {
@@ -639,6 +644,8 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
                     return fail(BMC_E_INVALID, "fixed hand of seat " + std::to_string(k) + " is not 13 cards in lane-mask layout");
                 if (sp.fixed_mask & fixed_union) return fail(BMC_E_INVALID, "fixed hands overlap");
                 fixed_union |= sp.fixed_mask;
+                fixed_mask[k] = sp.fixed_mask;
+                is_fixed[k] = true;
                 c->has_fixed = true;
             }
             std::string why;
@@ -694,6 +701,9 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     for (int k = 0; k < 4; ++k)
         if (c->dev.seat[k].active && selectivity[k] < best) { best = selectivity[k]; c->dev.primary = (uint32_t)k; }
     c->code.push_back(enc(OP_END));
+    if (c->has_fixed && is_fixed[0] && is_fixed[1] && is_fixed[2] && is_fixed[3])
+        return fail(BMC_E_INVALID, "all four hands are fixed: nothing to deal");
+    fixdev_init(c->fix, fixed_mask, is_fixed);
     *out = c.release();
     return BMC_OK;
 }
@@ -776,11 +786,13 @@ static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
 }
 
 // ---- sampling -------------------------------------------------------------------
-static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, uint64_t seed, uint64_t first, uint64_t n,
-                       uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev)
+static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const FixDev *fix, uint64_t seed, uint64_t first,
+                       uint64_t n, uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev)
 {
     SampleArgs a;
     a.cons = cons;
+    if (fix) a.fix = *fix;
+    else { memset(&a.fix, 0, sizeof a.fix); a.fix.n_free = 52; }
     a.key = philox_key(seed);
     a.first = first;
     a.n = n;
@@ -794,8 +806,13 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, uint64_
     if (blocks < 1) blocks = 1;
     const uint64_t chunk = (uint64_t)blocks * THREADS;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
-    if (has_cons) sample_kernel<true><<<blocks, THREADS, 0, ctx->stream>>>(a);
-    else sample_kernel<false><<<blocks, THREADS, 0, ctx->stream>>>(a);
+    if (fix) {
+        if (has_cons) sample_kernel<true, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
+        else sample_kernel<false, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
+    } else {
+        if (has_cons) sample_kernel<true, false><<<blocks, THREADS, 0, ctx->stream>>>(a);
+        else sample_kernel<false, false><<<blocks, THREADS, 0, ctx->stream>>>(a);
+    }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return BMC_OK;
@@ -806,7 +823,6 @@ int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uin
                    void *tallies_dev, bmc_stats *stats)
 {
     if (!ctx || !tallies_dev) return fail(BMC_E_INVALID, "bmc_sample_dev: ctx / tallies_dev is NULL");
-    if (cons && cons->has_fixed) return fail(BMC_E_INVALID, "fixed (:=) hands are not supported by the sampling kernel yet");
     if (n_accept_target == 0 && n_raw == 0) return fail(BMC_E_INVALID, "nothing to do: n_raw == 0 and no accept target");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -825,7 +841,7 @@ int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uin
         const uint64_t max_launch = 1ull << 36;
         while (done < n_raw) {
             const uint64_t n = n_raw - done < max_launch ? n_raw - done : max_launch;
-            int rc = launch_wave(ctx, dev, has_cons, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
+            int rc = launch_wave(ctx, dev, has_cons, (cons && cons->has_fixed) ? &cons->fix : nullptr, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
             if (rc) return rc;
             done += n;
             ++waves;
@@ -839,7 +855,7 @@ int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uin
             if (n_raw && done >= n_raw) break;
             uint64_t n = wave;
             if (n_raw && n_raw - done < n) n = n_raw - done;
-            int rc = launch_wave(ctx, dev, has_cons, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
+            int rc = launch_wave(ctx, dev, has_cons, (cons && cons->has_fixed) ? &cons->fix : nullptr, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
             if (rc) return rc;
             done += n;
             ++waves;

@@ -159,6 +159,80 @@ __device__ __forceinline__ bool deal52(const PhiloxKey &key, uint32_t idx_lo, ui
     return s.voided;
 }
 
-// bounded draw helper for the score tally: uniform 0..13 from 16 random bits
-// (exact: 65536 mod 14 = 2 -> values below 2 in the low half are redrawn by the caller)
+// ---------------------------------------------------------------------------
+// Deals with fixed (`:=`) hands: the 52 - 13k free cards are dealt to the free
+// seats with the same owner bookkeeping, in a run-time loop (the free-card
+// positions are per-constraint constants, uniform across the grid).  Word w of
+// the Philox stream yields the digits n = n_free - 4w .. n_free - 4w - 3.
+// Mirrored by orc_gpu_deal_fixed in oracle/bmc_oracle.c.
+// ---------------------------------------------------------------------------
+struct FixDev {
+    uint32_t n_free;              // 52 = no fixed hand (deal52 is used instead)
+    uint32_t q0;                  // initial Q: bytes 128 - prefix_j of the seat capacities
+    uint32_t lo0, lo1, hi0, hi1;  // owner planes of the fixed cards
+    uint32_t free0, free1;        // lane-layout masks of the free cards
+    uint32_t thresh[10];          // Lemire threshold of every 4-digit word
+};
+
+__host__ inline void fixdev_init(FixDev &f, const uint64_t fixed_mask[4], const bool is_fixed[4])
+{
+    uint64_t lo = 0, hi = 0, used = 0;
+    uint32_t cap[4];
+    for (int k = 0; k < 4; ++k) {
+        cap[k] = is_fixed[k] ? 0u : 13u;
+        if (!is_fixed[k]) continue;
+        used |= fixed_mask[k];
+        if (k & 1) lo |= fixed_mask[k];
+        if (k & 2) hi |= fixed_mask[k];
+    }
+    const uint64_t free_mask = 0x1FFF1FFF1FFF1FFFull & ~used;
+    f.n_free = (uint32_t)__builtin_popcountll(free_mask);
+    const uint32_t p0 = cap[0], p1 = p0 + cap[1], p2 = p1 + cap[2];
+    f.q0 = (128u - p0) | ((128u - p1) << 8) | ((128u - p2) << 16);
+    f.lo0 = (uint32_t)lo; f.lo1 = (uint32_t)(lo >> 32); f.hi0 = (uint32_t)hi; f.hi1 = (uint32_t)(hi >> 32);
+    f.free0 = (uint32_t)free_mask; f.free1 = (uint32_t)(free_mask >> 32);
+    for (int w = 0; w < 10; ++w) {
+        uint64_t N = 1;
+        for (int d = 0; d < 4; ++d) {
+            const int n = (int)f.n_free - 4 * w - d;
+            if (n >= 2) N *= (uint64_t)n;
+        }
+        f.thresh[w] = (uint32_t)((1ull << 32) % N);
+    }
+}
+
+__device__ __forceinline__ bool deal_fixed(const PhiloxKey &key, const FixDev &f, uint32_t idx_lo, uint32_t idx_hi, Planes &pl)
+{
+    uint32_t w[4];
+    uint32_t x = 0, Q = f.q0;
+    uint32_t lo0 = f.lo0, lo1 = f.lo1, hi0 = f.hi0, hi1 = f.hi1;
+    uint32_t free0 = f.free0, free1 = f.free1;
+    bool voided = false;
+    uint32_t n = f.n_free;
+    for (uint32_t v = 0; n >= 1; ++v, --n) {
+        uint32_t pos;
+        if (free0) { pos = __ffs(free0) - 1; free0 &= free0 - 1; }
+        else { pos = 32 + __ffs(free1) - 1; free1 &= free1 - 1; }
+        uint32_t u = 0;
+        if (n >= 2) {
+            if ((v & 3u) == 0u) {
+                if ((v & 15u) == 0u) philox4x32_10(key, idx_lo, idx_hi, v >> 4, 0u, w);
+                const uint32_t sel = (v >> 2) & 3u;
+                x = sel == 0u ? w[0] : sel == 1u ? w[1] : sel == 2u ? w[2] : w[3];
+            }
+            mul_wide(x, n, x, u);
+            if ((v & 3u) == 3u || n == 2u) voided |= x < f.thresh[v >> 2];
+        }
+        const uint32_t E = u * 0x010101u + Q;
+        const uint32_t A = E & 0x808080u;                  // bit 7 of byte j: u >= prefix_j
+        Q += (A ^ 0x808080u) >> 7;
+        const uint32_t hib = (A >> 15) & 1u;
+        const uint32_t lob = ((A >> 7) ^ (A >> 15) ^ (A >> 23)) & 1u;
+        if (pos < 32u) { lo0 |= lob << pos; hi0 |= hib << pos; }
+        else { lo1 |= lob << (pos - 32u); hi1 |= hib << (pos - 32u); }
+    }
+    pl.lo0 = lo0; pl.lo1 = lo1; pl.hi0 = hi0; pl.hi1 = hi1;
+    return voided;
+}
+
 }  // namespace bmc

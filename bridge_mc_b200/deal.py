@@ -1,0 +1,269 @@
+"""Host mirror of the reference's deal generator and Monte-Carlo driver:
+class `deal` / `build` (bridge.cl:1283-1319), class `mc-case` with sim / select /
+choose / add-prop / save / load-mc-case (bridge.cl:3133-3221) and the REST
+entry `mc-deal` with normdef / invert-id / close-list (rest.cl:214-277).
+
+`build` keeps its signature and result order (const hands, `:~` seats in def
+order, then the random hands) but every deal comes from the GPU sampler
+(bmc_sample): one library call produces a batch that successive `build`s
+consume, and `sim` asks for all its deals in one call.
+"""
+from __future__ import annotations
+
+import itertools
+import os
+
+import numpy as np
+
+from . import hist as _hist
+from . import sexp
+from .cards import Hand, str2hand, unpack_deal, seat_masks
+from .engine import Constraints, DEFAULT_SEED, Engine, seat_spec
+from .infer import infer_distgen_params, plist_to_def, supply
+
+
+class NoDealFound(RuntimeError):
+    """The raw-deal budget was used up without a single accepted deal."""
+
+
+def normdef(d):
+    """rest.cl:250-256: number -> (n n); (lo hi n) -> (lo hi (n n))."""
+    if isinstance(d, dict):
+        return {k: _normval(v) for k, v in d.items()}
+    return [_normval(v) if i % 2 else v for i, v in enumerate(d)]
+
+
+def _normval(v):
+    if isinstance(v, int) and not isinstance(v, bool):
+        return [v, v]
+    if isinstance(v, (list, tuple)) and len(v) > 2 and isinstance(v[2], int):
+        return [v[0], v[1], [v[2], v[2]]]
+    return v
+
+
+def invert_id(ids):
+    """rest.cl:258-259: inverse permutation."""
+    return [i for i, _ in sorted(enumerate(ids), key=lambda p: p[1])]
+
+
+def close_list(lst, base):
+    """rest.cl:214-217"""
+    return list(lst) + list(base[len(lst):]) if len(lst) < len(base) else list(lst)
+
+
+def reorder(lst, indexes):
+    """bridge.cl:202-204"""
+    return [lst[i] if i < len(lst) else None for i in indexes]
+
+
+def roll(amount, lst):
+    """bridge.cl:420-425"""
+    if not lst:
+        return lst
+    a = (-amount) % len(lst)
+    return list(lst) if a == 0 else list(lst[a:]) + list(lst[:a])
+
+
+class Deal:
+    """(make-instance 'deal := const-hands :~ defs), bridge.cl:1283-1286.
+
+    const_hands: Hands (or 4-list rank lists / "♣ .. ♦ .." strings); defs: range
+    defs (dict, plist as read by sexp, or plist text); rules: optional per-`:~`-seat
+    rule forms in the bidding.cl predicate language (an extension: the reference
+    has no entry point that feeds bidding predicates to the generator)."""
+
+    BATCH = 2048
+
+    def __init__(self, const_hands=None, defs=None, rules=None, engine: Engine | None = None, seed: int | None = None,
+                 max_raw: int = 1 << 34):
+        self.const_hands = [self._hand(h) for h in (const_hands or [])]
+        self.defs = [plist_to_def(sexp.read(d) if isinstance(d, str) else d) for d in (defs or [])]
+        self.rules = list(rules or [])
+        if len(self.const_hands) + len(self.defs) > 4:
+            raise ValueError("more than four seats defined")
+        self._engine = engine
+        self.seed = DEFAULT_SEED ^ int.from_bytes(os.urandom(8), "little") if seed is None else seed
+        self.max_raw = max_raw
+        self._next_index = 0
+        self._buffer = []
+        self._cons = None
+
+    @staticmethod
+    def _hand(h):
+        if isinstance(h, Hand):
+            return h
+        if isinstance(h, str):
+            return str2hand(h)
+        return Hand(h)
+
+    def __repr__(self):
+        return f"DEAL<{self.const_hands}, {self.defs}>"
+
+    @property
+    def engine(self):
+        return self._engine or Engine.default()
+
+    def constraints(self) -> Constraints:
+        if self._cons is None:
+            # the reference narrows the first def against the others when the root
+            # generator is made (bridge.cl:1297-1301) and signals bad-range there
+            used = set(itertools.chain.from_iterable(h.cards() for h in self.const_hands))
+            if self.defs:
+                infer_distgen_params(supply(c for c in range(52) if c not in used), self.defs[0], self.defs[1:])
+            specs = [seat_spec(fixed=h) for h in self.const_hands]
+            specs += [seat_spec(**{k: v for k, v in d.items() if k in ("hcp", "c", "d", "h", "s", "losers")}) for d in self.defs]
+            specs += [None] * (4 - len(specs))
+            rules = [None] * len(self.const_hands) + list(self.rules)
+            rules += [None] * (4 - len(rules))
+            self._cons = Constraints(specs, rules if any(rules) else None)
+        return self._cons
+
+    def build_records(self, n: int) -> np.ndarray:
+        """n accepted deals as uint64[n,2] records (seat k = k-th of const, `:~`, random)."""
+        cons = self.constraints()
+        out = []
+        have = 0
+        wave = 1 << 14
+        spent = 0
+        while have < n:
+            rec, tal, st = self.engine.sample(cons, n_accept=n - have, seed=self.seed, first_index=self._next_index,
+                                              wave=wave, tally_mask=0, cap=(n - have) + wave)
+            used = st.waves * wave
+            self._next_index += used
+            spent += used
+            if rec.shape[0]:
+                # the accepted set of a call is fixed; its order is not: sort for reproducibility
+                rec = rec[np.lexsort((rec[:, 0], rec[:, 1]))]
+                out.append(rec)
+                have += rec.shape[0]
+            elif spent >= self.max_raw:
+                raise NoDealFound(f"no deal satisfies {self!r} within {spent} raw deals")
+            if st.accepted * 64 < used and wave < (1 << 30):
+                wave <<= 2                                   # rare constraint: take bigger bites
+        rec = np.concatenate(out) if out else np.empty((0, 2), np.uint64)
+        if rec.shape[0] > n:
+            self._buffer_extra = rec[n:]
+        return rec[:n]
+
+    def build(self):
+        """bridge.cl:1292-1319: one deal as a list of Hands -- const hands, `:~` seats, random hands.
+        With three const hands and one def only the sampled hand is returned (bridge.cl:1316-1319)."""
+        if not self._buffer:
+            recs = self.build_records(self.BATCH if not self.const_hands else 256)
+            self._buffer = [recs[i] for i in range(recs.shape[0])][::-1]
+        hands = unpack_deal(self._buffer.pop(), ids=None)
+        if len(self.const_hands) == 3 and len(self.defs) == 1:
+            return hands[3:4]
+        return hands
+
+
+class McCase:
+    """bridge.cl:3133-3221 class mc-case.  `dealgen` is a Deal (optionally with a
+    seat permutation `reorder`) or any callable returning four Hands; `props` are
+    measures called as measure(trump, n, e, s, w) (README.md:129-133)."""
+
+    def __init__(self, dealgen, props, trump=None, data=None, reorder=None):
+        self.dealgen, self.props, self.trump = dealgen, list(props), trump
+        self.data = list(data or [])
+        self.reorder = reorder
+        self._threads = []
+
+    def __repr__(self):
+        return f"MC-CASE{{{self.dealgen}->{[getattr(p, '__name__', p) for p in self.props]} @ {self.trump}}}"
+
+    def _deals(self, runs):
+        if isinstance(self.dealgen, Deal):
+            recs = self.dealgen.build_records(runs)
+            for i in range(recs.shape[0]):
+                hands = unpack_deal(recs[i], ids=None)
+                yield reorder(hands, self.reorder) if self.reorder else hands
+        else:
+            for _ in range(runs):
+                yield self.dealgen()
+
+    def sim(self, runs: int):
+        """bridge.cl:3144-3162: `runs` rows (hands m1 m2 ...) appended to the case's data.
+        The reference starts two threads and returns at once; here the deals come
+        from one batched GPU call and the rows are complete on return."""
+        rows = [[hands] + [p(self.trump, *hands) for p in self.props] for hands in self._deals(runs)]
+        self.data.extend(rows)
+        return rows
+
+    def threads(self):
+        """bridge.cl:3164-3167: live worker threads (always none: sim is synchronous)."""
+        return []
+
+    def add_prop(self, *new_props):
+        """bridge.cl:3169-3175"""
+        for row in self.data:
+            row.extend(p(self.trump, *row[0]) for p in new_props)
+        self.props.extend(new_props)
+
+    def _names(self):
+        return ["hands"] + [getattr(p, "__name__", str(p)) for p in self.props]
+
+    def choose(self, pred):
+        """bridge.cl:3177-3184: rows for which pred(row_dict) holds (row_dict maps 'hands' and
+        each measure name to its column; the reference `eval`s a form over the same names)."""
+        names = self._names()
+        return [row for row in self.data if pred(dict(zip(names, row)))]
+
+    def select(self, fields=None, filter=None):
+        """bridge.cl:3186-3195"""
+        source = self.choose(filter) if filter else self.data
+        if fields:
+            names = self._names()
+            cols = [names.index(f) for f in fields]
+            return [[row[c] for c in cols] for row in source]
+        return [row[1:] for row in source]
+
+    def save(self, filename):
+        """bridge.cl:3201-3209.  Hands are written as records (lo hi), which -- unlike the
+        reference's HAND<..> print form -- read back exactly."""
+        from .cards import pack_deal
+        with open(filename, "w", encoding="utf-8") as f:
+            for row in self.data:
+                rec = pack_deal(row[0])
+                f.write(sexp.dumps([[int(rec[0]), int(rec[1])]] + [_to_sexp(v) for v in row[1:]]) + "\n")
+
+    @classmethod
+    def load(cls, filename, fallback=None, sim_count=None):
+        """bridge.cl:3211-3221 load-mc-case"""
+        if os.path.exists(filename):
+            rows = []
+            for form in sexp.read_all(open(filename, encoding="utf-8").read()):
+                rec = np.array(form[0], dtype=np.uint64)
+                rows.append([unpack_deal(rec, ids=None)] + list(form[1:]))
+            kw = dict(fallback or {})
+            kw.setdefault("dealgen", None)
+            kw.setdefault("props", [])
+            return cls(data=rows, **kw)
+        if fallback:
+            obj = cls(**fallback)
+            if sim_count:
+                obj.sim(sim_count)
+            return obj
+        return None
+
+
+def _to_sexp(v):
+    if isinstance(v, (list, tuple)):
+        return [_to_sexp(x) for x in v]
+    if isinstance(v, (np.integer,)):
+        return int(v)
+    return v
+
+
+def mc_deal(defs, measures, runs: int = 500, engine: Engine | None = None, seed: int | None = None):
+    """rest.cl:264-277 mc-deal: `defs` in the request's seat order (N E S W), each a Hand
+    (fixed) or a range def; builds the `deal`, the seat permutation back to request
+    order, simulates `runs` deals (the reference hard-codes 500) and returns
+    (mc_case, histogram of the measure tuples)."""
+    consts = [(i, d) for i, d in enumerate(defs) if isinstance(d, Hand)]
+    ranged = [(i, d) for i, d in enumerate(defs) if not isinstance(d, Hand)]
+    deal = Deal([d for _, d in consts], [normdef(plist_to_def(d)) for _, d in ranged], engine=engine, seed=seed)
+    perm = close_list(invert_id([i for i, _ in consts + ranged]), [0, 1, 2, 3])
+    mc = McCase(deal, measures, reorder=perm)
+    mc.sim(runs)
+    rows = [list(itertools.chain.from_iterable(v if isinstance(v, list) else [v] for v in r)) for r in mc.select()]
+    return mc, _hist.histogram(rows)

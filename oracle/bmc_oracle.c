@@ -664,3 +664,57 @@ ORC_API uint64_t orc_ref_run(orc_distgen *root, uint64_t *rng_state, uint64_t n,
     if (checksum) *checksum = sum;
     return pass;
 }
+
+/* CPU mirror of bmc::deal_fixed (csrc/deal.cuh): deals with fixed (`:=`) hands.
+ * fixed[k] = lane-layout mask of seat k's fixed hand, 0 = seat is free. */
+ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fixed[4],
+                               uint64_t *lo_plane, uint64_t *hi_plane)
+{
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint64_t lo = 0, hi = 0, used = 0;
+    int rem[4];
+    for (int k = 0; k < 4; ++k) {
+        rem[k] = fixed[k] ? 0 : 13;
+        used |= fixed[k];
+        if (k & 1) lo |= fixed[k];
+        if (k & 2) hi |= fixed[k];
+    }
+    uint64_t free_mask = 0x1FFF1FFF1FFF1FFFull & ~used;
+    int n = __builtin_popcountll(free_mask), n_free = n, voided = 0;
+    uint32_t w[4] = {0, 0, 0, 0}, x = 0;
+    for (int v = 0; n >= 1; ++v, --n) {
+        int pos = __builtin_ctzll(free_mask);
+        free_mask &= free_mask - 1;
+        int u = 0;
+        if (n >= 2) {
+            if ((v & 3) == 0) {
+                if ((v & 15) == 0) {
+                    uint32_t ctr[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(v >> 4), 0 };
+                    orc_philox4x32_10(ctr, key, w);
+                }
+                x = w[(v >> 2) & 3];
+            }
+            uint64_t p = (uint64_t)x * (uint32_t)n;
+            u = (int)(p >> 32);
+            x = (uint32_t)p;
+            if ((v & 3) == 3 || n == 2) {
+                uint64_t N = 1;
+                for (int d = 0; d < 4; ++d) { int m = n_free - 4 * (v >> 2) - d; if (m >= 2) N *= (uint64_t)m; }
+                if (x < (uint32_t)((((uint64_t)1) << 32) % N)) voided = 1;
+            }
+        }
+        int owner, acc = 0;
+        for (owner = 0; owner < 4; ++owner) { acc += rem[owner]; if (u < acc) break; }
+        --rem[owner];
+        lo |= (uint64_t)(owner & 1) << pos;
+        hi |= (uint64_t)(owner >> 1) << pos;
+    }
+    *lo_plane = lo; *hi_plane = hi;
+    return voided;
+}
+ORC_API void orc_gpu_deal_fixed_batch(uint64_t seed, uint64_t first, uint64_t n, const uint64_t fixed[4],
+                                      uint64_t *rec, uint8_t *voided)
+{
+    for (uint64_t i = 0; i < n; ++i)
+        voided[i] = (uint8_t)orc_gpu_deal_fixed(seed, first + i, fixed, &rec[2 * i], &rec[2 * i + 1]);
+}

@@ -111,6 +111,10 @@ def lib():
     L.orc_choose_bid_batch.restype = None
     L.orc_gpu_deal_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     L.orc_gpu_deal_batch.restype = None
+    L.orc_gpu_deal_fixed_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64 * 4, C.c_void_p, C.c_void_p]
+    L.orc_gpu_deal_fixed_batch.restype = None
+    L.orc_ref_run.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    L.orc_ref_run.restype = C.c_uint64
     L.orc_build_batch.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p]
     L.orc_build_batch.restype = None
     _LIB = L
@@ -208,6 +212,14 @@ def gpu_deal_batch(seed: int, first: int, n: int):
     rec = np.empty((n, 2), dtype=np.uint64)
     void = np.empty(n, dtype=np.uint8)
     lib().orc_gpu_deal_batch(seed, first, n, rec.ctypes.data, void.ctypes.data)
+    return rec, void
+
+
+def gpu_deal_fixed_batch(seed: int, first: int, n: int, fixed):
+    """CPU mirror of the fixed-hand sampler; fixed = 4 lane-layout masks (0 = free seat)."""
+    rec = np.empty((n, 2), dtype=np.uint64)
+    void = np.empty(n, dtype=np.uint8)
+    lib().orc_gpu_deal_fixed_batch(seed, first, n, (C.c_uint64 * 4)(*[int(f) for f in fixed]), rec.ctypes.data, void.ctypes.data)
     return rec, void
 
 

@@ -1,0 +1,268 @@
+"""GPU tests of the reference-facing host API (the Python mirror of the Lisp entry
+points) and of the remaining C-ABI calls; checked against the reference's own
+KATs and the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from kat_util import bid_of, hand_of, load_kats, truth, unquote
+from bridge_mc_b200 import bidding, cards, compscore, hist
+from bridge_mc_b200._lib import BadRange, Contract as CContract
+from bridge_mc_b200.cards import seat_masks, str2hand
+from bridge_mc_b200.deal import Deal, McCase, mc_deal
+from bridge_mc_b200.engine import Constraints, seat_spec
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def sort_records(rec):
+    rec = np.ascontiguousarray(rec, dtype=np.uint64).reshape(-1, 2)
+    return rec[np.lexsort((rec[:, 0], rec[:, 1]))]
+
+
+# ---- bidding.cl KATs through the GPU path --------------------------------------------
+def _scheme(form):
+    if len(form) == 2:
+        return bidding.openings
+    s = form[2]
+    if s[0] == "NT-RESPONSES":
+        return bidding.nt_responses(s[1])
+    if s == "2C-RESPONSES":
+        return bidding.two_c_responses
+    if s[0] == "BASIC-RESPONSES":
+        return bidding.basic_responses(bid_of(s[1]))
+    return None
+
+
+def test_bidding_kats_on_gpu(engine):
+    n = 0
+    for where, form, exp in load_kats("SUIT-LOOSERS"):
+        pass
+    for where, form, exp in load_kats("ASSESS-HAND"):
+        assert bidding.balanced(hand_of(form[1]), engine) == truth(exp), where
+        n += 1
+    for where, form, exp in load_kats("TEST-BID"):
+        assert bidding.test_bid(bid_of(form[1]), hand_of(form[2]), engine=engine) == truth(exp), where
+        n += 1
+    for where, form, exp in load_kats("CHOOSE-BID"):
+        table = _scheme(form)
+        if table is None:
+            continue                 # further-bid tables (bidding.cl:379-413) are out of scope
+        assert bidding.choose_bid(hand_of(form[1]), table, engine) == bid_of(exp), where
+        n += 1
+    assert n == 6 + 28 + 10 + 13 + 8 + 7
+
+
+def test_assess_hand_matches_oracle(engine):
+    h = str2hand("♣ KJ9753 ♦ 94 ♥ A84 ♠ A9")
+    lens, power, losers = bidding.assess_hand(h, engine=engine)
+    ref = O.assess(h)
+    assert (lens, power, losers) == (ref["lens"], ref["power"], ref["losers"])
+    assert bidding.assess_hand(h, lambda l, p, lo: sum(p), engine) == ref["hcp"]
+
+
+def test_unspliced_rule_quirk(engine):
+    """bidding.cl:249: the (3 suit) raise holds an un-spliced list; reaching it is an error in the
+    reference, and the club raise is simply NIL."""
+    t = bidding.basic_responses((1, "H"))
+    h = str2hand("♣ 72 ♦ K854 ♥ K653 ♠ AQ8")        # 12 hcp, 4 hearts, no 4 spades: reaches the (3 H) row
+    with pytest.raises(bidding.BidError):
+        bidding.choose_bid(h, t, engine)
+    tc = bidding.basic_responses((1, "C"))
+    h2 = str2hand("♣ KQ8542 ♦ K85 ♥ K6 ♠ 98")       # 11 hcp, club fit, no 4-card suit outside
+    assert bidding.choose_bid(h2, tc, engine) is None
+
+
+# ---- compscore.cl KATs through the product API ------------------------------------------
+def test_compscore_kats_on_gpu(engine):
+    for where, form, exp in load_kats("BASE-SCORE"):
+        c = compscore.Contract(str(form[1][3]))
+        vul = len(form) > 2 and truth(form[3])
+        assert compscore.base_score(c, vulnerable=vul, engine=engine) == exp, where
+    for where, form, exp in load_kats("MATCH-POINTS"):
+        a, b = compscore.Contract(str(form[1][3])), compscore.Contract(str(form[2][3]))
+        vul = str(unquote(form[4])).lower() if len(form) > 3 else None
+        assert compscore.match_points(a, b, vulnerable=vul, engine=engine) == exp, where
+    assert compscore.contract_score("H", 10, engine=engine) == 420
+    assert compscore.contract_score(None, 9, vulnerable=True, level=3, engine=engine) == 600
+    with pytest.raises(ValueError):
+        compscore.match_points(compscore.Contract("7NTNxx="), compscore.Contract("7NTNxx-13"), vulnerable="both",
+                               engine=engine)
+
+
+# ---- reference-generated deals -> GPU filter ---------------------------------------------
+def test_filter_on_reference_generated_deals(engine):
+    """Deals produced by the reference's own generator (distgen exact sampler restated in the
+    oracle) go through bmc_filter: accept flags and features must be bit-exact."""
+    g = O.Distgen(hcp=(15, 17), c=(2, 5), d=(2, 5), h=(2, 4), s=(2, 4))
+    hands = g.build_batch(3000, seed=42)                  # seat 0 = the ranged seat
+    lanes = O.mask52_to_lanes64(hands)
+    rec = np.zeros((hands.shape[0], 2), dtype=np.uint64)
+    for k in range(4):
+        if k & 1:
+            rec[:, 0] |= lanes[:, k]
+        if k & 2:
+            rec[:, 1] |= lanes[:, k]
+    cons = Constraints([seat_spec(hcp=(15, 17), c=(2, 5), d=(2, 5), h=(2, 4), s=(2, 4)), None, None, None],
+                       [None, bidding.openings.passes(), None, None])
+    acc, feats = engine.filter(rec, cons, bidding.openings.scheme())
+    f = O.features_batch(lanes.reshape(-1)).reshape(-1, 4, 11)
+    bids = O.choose_bid_batch(0, lanes.reshape(-1)).reshape(-1, 4)
+    assert np.array_equal(feats["hcp"].astype(np.int32), f[:, :, 8])
+    assert np.array_equal(feats["len"].astype(np.int32), f[:, :, 0:4])
+    assert np.array_equal(feats["losers"].astype(np.int32), f[:, :, 9])
+    assert np.array_equal(feats["bid"].astype(np.int32), bids)
+    assert np.array_equal(acc.astype(bool), bids[:, 1] == -1)      # seat 0 always inside its ranges
+
+
+def test_multi_seat_constraint_accept_flags(engine):
+    """C3-style: N, E, W pass, S opens 1NT, N answers 3NT to 1NT (bidding.cl:76-106,166-187)."""
+    nt = bidding.nt_responses(1)
+    p = bidding.openings.passes()
+    cons = Constraints(None, [f"(and {p} {nt.chooses((3, 'NT'))})", p, bidding.openings.chooses((1, "NT")), p])
+    rec, _, _ = engine.sample(None, n_raw=400_000, seed=31)
+    acc, _ = engine.filter(rec, cons, None, want_features=False)
+    m = seat_masks(rec)
+    op = O.choose_bid_batch(0, m.reshape(-1)).reshape(-1, 4)
+    resp = O.choose_bid_batch(1, m[:, 0])
+    ref = (op[:, 0] == -1) & (op[:, 1] == -1) & (op[:, 2] == 2) & (op[:, 3] == -1) & (resp == 6)
+    assert np.array_equal(acc.astype(bool), ref)
+    assert 200 < ref.sum() < 900                         # p ~ 1.26e-3
+    got, tal, _ = engine.sample(cons, n_raw=400_000, seed=31)
+    assert np.array_equal(sort_records(got), sort_records(rec[ref]))
+
+
+# ---- fixed (:=) hands ------------------------------------------------------------------------
+def test_fixed_hand_sampler_bit_exact(engine):
+    h = str2hand("♣ AJ7 ♦ AK54 ♥ 6543 ♠ 64")
+    h2 = str2hand("♣ KQ2 ♦ QJ ♥ AKQ2 ♠ AK32")
+    for fixed in ([0, h.mask64(), 0, 0], [h2.mask64(), 0, 0, h.mask64()], [h.mask64(), h2.mask64(), 0, 0]):
+        specs = [seat_spec(fixed=m) if m else None for m in fixed]
+        cons = Constraints(specs)
+        n = 50_000
+        rec, tal, _ = engine.sample(cons, n_raw=n, seed=77, first_index=9)
+        ref, void = O.gpu_deal_fixed_batch(77, 9, n, fixed)
+        assert tal["voided"] == int(void.sum())
+        assert np.array_equal(sort_records(rec), sort_records(ref[void == 0]))
+        m = seat_masks(rec)
+        for k, fm in enumerate(fixed):
+            if fm:
+                assert (m[:, k] == np.uint64(fm)).all()
+
+
+def test_build_property_kat(engine):
+    """bridge.cl:2989-3003: three ranged seats + one fixed hand; every generated hand (incl. the
+    never-directly-sampled last seat) has HCP <= 11 and all suit lengths in 2..5."""
+    rng = {"hcp": [0, 11], "c": [2, 5], "d": [2, 5], "h": [2, 5], "s": [2, 5]}
+    fixed = cards.Hand([[12, 9, 5], [12, 11, 3, 2], [4, 3, 2, 1], [4, 2]])     # ((A J 7) (A K 5 4) (6 5 4 3) (6 4))
+    dg = Deal([fixed], [rng, rng, rng], engine=engine, seed=5)
+    seen = set()
+    for _ in range(20):
+        hands = dg.build()
+        assert len(hands) == 4 and hands[0] == fixed
+        seen.add(tuple(tuple(s) for s in hands[1].suits))
+        for h in hands[1:]:
+            hcp = sum(max(r - 8, 0) for s in h.suits for r in s)
+            assert hcp <= 11 and all(2 <= len(s) <= 5 for s in h.suits)
+        assert sorted(c for h in hands for c in h.cards()) == list(range(52))
+    assert len(seen) == 20
+
+
+def test_deal_build_order_and_errors(engine):
+    d = Deal(defs=["(:hcp (15 17) :s (5 nil))"], engine=engine, seed=1)
+    hands = d.build()
+    assert len(hands) == 4
+    assert 15 <= sum(max(r - 8, 0) for s in hands[0].suits for r in s) <= 17 and len(hands[0].suits[3]) >= 5
+    three = [str2hand("♣ AKQJ1098765432 ♦ ♥ ♠"), str2hand("♣ ♦ AKQJ1098765432 ♥ ♠"), str2hand("♣ ♦ ♥ AKQJ1098765432 ♠")]
+    only = Deal(three, [{"hcp": [10, 10]}], engine=engine, seed=2).build()
+    assert len(only) == 1 and only[0].suits[3] == list(range(13))      # bridge.cl:1316-1319: only the sampled hand
+    with pytest.raises(BadRange):
+        Deal(defs=[{"hcp": [30, 37]}, {"hcp": [15, 17]}], engine=engine).build()
+
+
+def test_mc_case_and_mc_deal(engine):
+    def south_hcp(trump, n, e, s, w):
+        return sum(max(r - 8, 0) for suit in s.suits for r in suit)
+
+    def ns_spades(trump, n, e, s, w):
+        return len(n.suits[3]) + len(s.suits[3])
+
+    deal = Deal(defs=[{"hcp": [15, 17], "c": [2, 5], "d": [2, 5], "h": [2, 4], "s": [2, 4]}], engine=engine, seed=3)
+    mc = McCase(deal, [south_hcp, ns_spades], reorder=[1, 2, 0, 3])      # the ranged seat becomes South
+    rows = mc.sim(500)
+    assert len(rows) == 500 and all(15 <= r[1] <= 17 for r in rows)
+    h = hist.histogram([r[1] for r in rows])
+    assert sum(e[1] for e in h) == 1 and {e[0] for e in h} == {15, 16, 17}
+    assert len(mc.select(fields=["south_hcp"], filter=lambda r: r["south_hcp"] == 15)) == sum(r[1] == 15 for r in rows)
+    mc.add_prop(lambda trump, n, e, s, w: len(s.suits[0]))
+    assert all(2 <= r[3] <= 5 for r in mc.data)
+    # rest.cl:264-277: fixed South hand + ranged North, request order N E S W
+    south = str2hand("S: ♠ AKJ5 ♥ K1064 ♦ Q87 ♣ A6")
+    mc2, tree = mc_deal([{"hcp": [10, 12], "s": [4, None]}, {}, south, {}], [ns_spades], runs=200, engine=engine, seed=4)
+    assert all(r[0][2] == south for r in mc2.data)
+    assert all(len(r[0][0].suits[3]) >= 4 for r in mc2.data)
+    assert sum(e[1] for e in tree) == 1
+
+
+def test_mc_case_save_load(engine, tmp_path):
+    deal = Deal(engine=engine, seed=8)
+    mc = McCase(deal, [lambda t, n, e, s, w: len(n.suits[0])])
+    mc.sim(50)
+    path = str(tmp_path / "case.dat")
+    mc.save(path)
+    back = McCase.load(path)
+    assert [[h.suits for h in r[0]] for r in back.data] == [[h.suits for h in r[0]] for r in mc.data]
+    assert [r[1] for r in back.data] == [r[1] for r in mc.data]
+
+
+# ---- fused score tally ----------------------------------------------------------------------------
+def test_score_tally_consistent(engine):
+    cs = [compscore.Contract(t).c_struct() for t in ("1NTS", "3NTS", "4HS", "4SS")]
+    th, ih, tab = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=2_000_000, seed=9)
+    assert (th.sum(axis=1) == 2_000_000).all()
+    exp = 2_000_000 / 14
+    assert (abs(th.astype(float) - exp) < 6 * exp ** 0.5).all()          # uniform tricks 0..13
+    for c in range(4):
+        for t in range(14):
+            assert tab[c, t] == O.lib().orc_base_score(cs[c].level, cs[c].suit, cs[c].declarer, cs[c].dbl, t, [0, 1, 0, 1][c])
+    assert (ih.sum(axis=1) == 2_000_000).all()
+    # determinism: same (seed, range) -> same tallies, and additivity over index sub-ranges
+    th2, ih2, _ = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=2_000_000, seed=9)
+    assert np.array_equal(th, th2) and np.array_equal(ih, ih2)
+    a = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=1_200_000, seed=9)
+    b = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=800_000, seed=9, first_index=1_200_000)
+    assert np.array_equal(a[0] + b[0], th) and np.array_equal(a[1] + b[1], ih)
+
+
+def test_sampler_partition_invariance(engine):
+    """tallies of [0,N) equal the sum over any partition into index ranges (what makes the multi-GPU
+    all-reduce bit-identical for every G)"""
+    cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    n = 1 << 20
+    _, whole, _ = engine.sample(cons, n_raw=n, seed=3, cap=0)
+    parts = [engine.sample(cons, n_raw=n // 4, seed=3, first_index=i * (n // 4), cap=0)[1] for i in range(4)]
+    for key in ("raw", "voided", "accepted"):
+        assert whole[key] == sum(p[key] for p in parts)
+    for key in ("hcp", "len", "shape"):
+        assert np.array_equal(whole[key], sum(p[key] for p in parts))
+
+
+def test_accept_target_mode(engine):
+    cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    rec, tal, st = engine.sample(cons, n_accept=10_000, wave=1 << 16, seed=12, cap=20_000)
+    assert tal["accepted"] >= 10_000 and tal["raw"] == st.waves * (1 << 16)
+    again, tal2, _ = engine.sample(cons, n_raw=tal["raw"], seed=12, cap=20_000)
+    assert np.array_equal(sort_records(rec), sort_records(again))           # the set depends only on (seed, range)
+    _, short, _ = engine.sample(cons, n_raw=tal["raw"] - (1 << 16), seed=12, cap=0)
+    assert short["accepted"] < 10_000                                        # smallest multiple of the wave size
+
+
+def test_empty_and_edge_inputs(engine):
+    acc, feats = engine.filter(np.empty((0, 2), np.uint64))
+    assert acc.size == 0
+    rec, tal, _ = engine.sample(None, n_raw=1, seed=1)
+    assert tal["raw"] == 1 and rec.shape[0] + tal["voided"] == 1
+    rec, tal, st = engine.sample(None, n_raw=1000, seed=1, cap=10)           # cap smaller than the accepted count
+    assert rec.shape[0] == 10 and tal["accepted"] > 10 and tal["stored"] == 10

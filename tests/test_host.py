@@ -1,0 +1,237 @@
+"""Host-side logic on CPU: S-expression reader, cards, hist-* pipeline, infer-*,
+contract parsing, the rule tables, and the C-ABI library's exports (no compute
+calls: there is no GPU here and the library has no CPU fallback)."""
+import ctypes as C
+import os
+import re
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from kat_util import bid_of, hand_of, load_kats, truth, unquote
+from bridge_mc_b200 import _lib, bidding, cards, hist, infer, sexp
+from bridge_mc_b200.compscore import Contract, scanstr
+from bridge_mc_b200.deal import Deal, close_list, invert_id, normdef, reorder, roll
+from bridge_mc_b200.engine import Constraints, Scheme, seat_spec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def norm(x):
+    """nil == (): normalise None/[] and Sym/str for comparisons with KAT data"""
+    if x is None or x == []:
+        return None
+    if isinstance(x, list):
+        if len(x) == 2 and x[0] == "QUOTE":          # ''foo inside quoted data stays (quote foo)
+            return ["QUOTE", norm(x[1])]
+        return [norm(e) for e in x]
+    return x
+
+
+# ---- sexp / cards -----------------------------------------------------------------
+def test_sexp_roundtrip():
+    txt = "(((2 C) . (or (> hcp 22) (and (not balanced) (<= loosers 4)))) ((1 NT) . balanced) (a . b) \"x y\" 3/4 nil)"
+    v = sexp.read(txt)
+    assert v[0][0] == [2, "C"] and v[0][1] == "OR"
+    assert isinstance(v[1], sexp.Dotted) and v[1].tail == "BALANCED"
+    assert v[4] == Fraction(3, 4) and v[5] is None
+    assert sexp.read(sexp.dumps(v)) == v
+    assert sexp.read("( :hcp ( 15 17 ) :S ( 5 NIL ( 3 NIL ) ) )") == [":HCP", [15, 17], ":S", [5, None, [3, None]]]
+
+
+def test_str2hand_kats():
+    for where, form, exp in load_kats("SUITS"):
+        assert cards.str2hand(str(form[1][1])).suits == exp, where
+    for where, form, exp in load_kats("HANDID"):
+        assert cards.str2hand(str(form[1][1])).id == str(exp), where
+    for where, form, exp in load_kats("MAPCAR"):
+        deal = cards.str2deal(str(form[2][1]))
+        if form[1] == ["FUNCTION", "SUITS"]:
+            assert [h.suits for h in deal] == exp, where
+        else:
+            assert [h.id for h in deal] == [str(x) for x in exp], where
+    for where, form, exp in load_kats("CARD"):
+        assert list(cards.card(str(form[1]))) == exp, where
+    h = cards.str2hand("♣ 72 ♦ KJ862 ♥  ♠ AQ8652")
+    assert h.suits[2] == [] and len(h) == 13
+    assert cards.print_hand(h.suits) == "♣ 72 ♦ KJ862 ♥  ♠ AQ8652"
+
+
+def test_record_pack_unpack():
+    deal = cards.str2deal("N: ♣ KJ96 ♦ A8 ♥ AJ83 ♠ AK9\nE: ♣ Q5 ♦ J9762 ♥ Q ♠ J6543\n"
+                          "S: ♣ 432 ♦ 1043 ♥ K10954 ♠ 87\nW: ♣ A1087 ♦ KQ5 ♥ 762 ♠ Q102")
+    rec = cards.pack_deal(deal)
+    back = cards.unpack_deal(rec)
+    assert [h.suits for h in back] == [h.suits for h in deal]
+    with pytest.raises(ValueError):
+        cards.pack_deal([deal[0], deal[0], deal[2], deal[3]])
+
+
+def test_list_helpers_kats():
+    for where, form, exp in load_kats("INVERT-ID"):
+        assert invert_id(unquote(form[1])) == exp, where
+    for where, form, exp in load_kats("REORDER"):
+        assert reorder(unquote(form[1]), unquote(form[2])) == exp, where
+    assert roll(2, [10, 100, 15, 5]) == [15, 5, 10, 100] and roll(-1, [10, 100, 15, 5]) == [100, 15, 5, 10]
+    assert close_list([2, 0], [0, 1, 2, 3]) == [2, 0, 2, 3]
+    assert normdef({"hcp": 15, "s": [5, None, 3]}) == {"hcp": [15, 15], "s": [5, None, [3, 3]]}
+
+
+# ---- hist-* -------------------------------------------------------------------------
+def test_hist_kats():
+    n = 0
+    for where, form, exp in load_kats("HIST-BASE"):
+        args = [unquote(a) for a in form[1:]]
+        assert norm(hist.hist_base(*args)) == norm(exp), where
+        n += 1
+    for where, form, exp in load_kats("HIST-BREAKDOWN"):
+        assert norm(hist.hist_breakdown(unquote(form[1]))) == norm(exp), where
+        n += 1
+    for where, form, exp in load_kats("HIST-PERCENT"):
+        assert norm(hist.hist_percent(unquote(form[1]))) == norm(exp), where
+        n += 1
+    for where, form, exp in load_kats("HISTOGRAM"):
+        assert norm(hist.histogram(unquote(form[1]))) == norm(exp), where
+        n += 1
+    assert n == 3 + 2 + 1 + 1
+
+
+def test_hist_base_accepts_device_precounts():
+    base = hist.tallies_as_base([0, 5, 0, 2], label=lambda i: 10 + i)
+    assert base == [[11, 5], [13, 2]]
+    assert hist.hist_base([13, 14], base) == [[11, 5], [13, 3], [14, 1]]
+    lines = hist.print_hist(hist.hist_percent([[1, 999], [2, 1], [3, 1000000]]), out=[])
+    assert lines[0].startswith("3: 99.90%") and lines[-1] == "2: 1/1001000"
+
+
+# ---- infer-* --------------------------------------------------------------------------
+def _plist(x):
+    return infer.plist_to_def(unquote(x))
+
+
+def _expect_def(exp):
+    return infer.plist_to_def(exp) if exp else {}
+
+
+def test_infer_kats():
+    n = 0
+    full = [[9, 1, 1, 1, 1]] * 4
+    for head, fn in (("INFER-HCP-RANGE", infer.infer_hcp_range), ("INFER-SUIT-RANGES", infer.infer_suit_ranges)):
+        for where, form, exp in load_kats(head):
+            sup = form[1]
+            sup = full if sup == ["SUPPLY", ["ALL-CARDS"]] else unquote(sup)
+            got = fn(sup, _plist(form[2]), *[_plist(o) for o in form[3:]])
+            assert norm({k: v for k, v in got.items()}) == norm(_expect_def(exp)) or got == _expect_def(exp), where
+            assert list(got.keys()) == list(_expect_def(exp).keys()), where
+            n += 1
+    for where, form, exp in load_kats("INFER-DISTGEN-PARAMS"):
+        got = infer.infer_distgen_params(unquote(form[1]), _plist(form[2]), [_plist(o) for o in (unquote(form[3]) or [])])
+        assert got == _expect_def(exp) and list(got) == list(_expect_def(exp)), where
+        n += 1
+    assert n == 7 + 5 + 2
+
+
+def test_infer_bad_range():
+    full = [[9, 1, 1, 1, 1]] * 4
+    with pytest.raises(infer.BadRangeError):
+        infer.infer_hcp_range(full, {"hcp": [30, 35]}, {"hcp": [12, 15]})
+    with pytest.raises(_lib.BadRange):
+        infer.infer_suit_ranges(full, {"s": [10, None]}, {"s": [5, 6]})
+    with pytest.raises(infer.BadRangeError):
+        Deal(defs=[{"hcp": [30, 37]}, {"hcp": [15, 17]}]).constraints()
+
+
+# ---- compscore parsing --------------------------------------------------------------------
+def test_scanstr_and_contract_kats():
+    for where, form, exp in load_kats("SCANSTR"):
+        opts = [str(o) if not isinstance(o, int) else o for o in unquote(form[1])]
+        got, rest = scanstr(opts, str(form[2]))
+        assert [got, rest] == [exp[0] if isinstance(exp[0], int) else str(exp[0]), str(exp[1])], where
+    for where, form, exp in load_kats("FORMAT", file="compscore.cl"):
+        assert str(Contract(str(form[3][3]))) == str(exp), where
+    c = Contract("4HSx+1")
+    assert (c.level, c.suit, c.declarer, c.double, c.outcome, c.tricks()) == (4, "H", "S", "X", "+1", 11)
+    assert Contract("3NT").outcome == "=" and Contract("3NT").declarer is None
+    assert Contract("6♥Wx-2").tricks() == 10
+    assert Contract("3NTS").with_score(10).outcome == 1
+
+
+# ---- rule tables ------------------------------------------------------------------------------
+def test_rule_tables_compile_and_shape():
+    assert [b for b in bidding.openings.bids()][:3] == [(2, "C"), (2, "NT"), (1, "NT")]
+    assert len(bidding.openings.rows) == 14
+    assert bidding.nt_responses(1).bids() == [(2, "C"), (2, "D"), (2, "H"), (2, "S"), (3, "C"), (2, "NT"), (3, "NT"),
+                                              (4, "NT"), (6, "NT")]
+    assert bidding.nt_responses(2).bids() == [(3, "C"), (3, "D"), (3, "H"), (3, "S"), (3, "NT"), (4, "NT"), (6, "NT")]
+    assert bidding.basic_responses((1, "H")).bids() == [(1, "S"), (1, "NT"), (2, "C"), (2, "H"), (3, "H"), (4, "H"),
+                                                        (2, "D")]
+    assert bidding.basic_responses("(1 C)").bids()[:3] == [(1, "D"), (1, "H"), (1, "S")]
+    with pytest.raises(ValueError):
+        bidding.basic_responses((2, "H"))
+    for t in (bidding.openings, bidding.nt_responses(1), bidding.nt_responses(2), bidding.two_c_responses,
+              bidding.basic_responses((1, "S")), bidding.basic_responses((1, "C"))):
+        assert t.scheme().size == len(t.rows)
+        assert sexp.read(t.sexpr())          # well-formed Lisp
+    assert "(not (or" in bidding.openings.chooses((1, "NT")) and bidding.openings.passes().startswith("(not (or")
+
+
+# ---- the C-ABI library -------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "bridgemc.h")).read()
+    declared = sorted(set(re.findall(r"\b(bmc_[a-z_0-9]+)\s*\(", hdr)))
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), f"libbridgemc.so does not export {name}"
+    assert sorted(_lib.EXPORTS) == declared
+    assert C.sizeof(_lib.SeatSpec) == 32 and C.sizeof(_lib.Stats) == 48 and C.sizeof(_lib.Contract) == 4
+    assert _lib.TALLY_WORDS == 4 + 4 * 40 + 4 * 4 * 14 + 4 * 40
+    assert b"sm_100a" in L.bmc_version()
+
+
+def test_shape_table():
+    t = _lib.shape_table()
+    assert t.shape == (39, 4) and (t.sum(axis=1) == 13).all()
+    assert all(r[0] >= r[1] >= r[2] >= r[3] for r in t.tolist())
+    assert len({tuple(r) for r in t.tolist()}) == 39 and tuple(t[0]) == (4, 3, 3, 3)
+
+
+def test_constraint_compile_errors():
+    Constraints([seat_spec(hcp=(15, 17), s=(5, None, (3, None))), None, None, None])
+    Constraints(None, [None, None, bidding.openings.chooses((1, "NT")), bidding.openings.passes()])
+    with pytest.raises(_lib.BadRange):
+        Constraints([seat_spec(hcp=(20, 10))])
+    with pytest.raises(_lib.BadRange):
+        Constraints([seat_spec(hcp=(0, 5))], ["(> hcp 22)"])
+    with pytest.raises(_lib.BadRange):
+        Constraints([seat_spec(hcp=(15, None)), seat_spec(hcp=(15, None)), seat_spec(hcp=(15, None))])
+    with pytest.raises(_lib.BridgeMcError) as e:
+        Constraints(None, ["(launch-missiles)"])
+    assert e.value.code == _lib.BMC_E_PARSE
+    with pytest.raises(_lib.BridgeMcError):
+        Scheme("((1 NT) . ")
+    h = cards.str2hand("♣ AJ7 ♦ AK54 ♥ 6543 ♠ 64")
+    Constraints([seat_spec(fixed=h)])
+    with pytest.raises(_lib.BridgeMcError):
+        Constraints([seat_spec(fixed=h), seat_spec(fixed=h)])
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from bridge_mc_b200.engine import Engine
+    with pytest.raises(_lib.BridgeMcError) as e:
+        Engine(0)
+    assert e.value.code == _lib.BMC_E_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "bridge_mc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "oracle" not in text.lower().replace("oracle/bmc_oracle.c", "").replace("orc_gpu_deal", "") \
+                    or f in ("deal.cuh",), f

@@ -1,0 +1,239 @@
+"""The CPU oracle (oracle/bmc_oracle.c) against every golden vector the reference
+holds for the hot path: its inline known-answer tests and distgen-test.dat.
+This is what pins the oracle (no Lisp implementation exists in this image)."""
+import json
+import os
+from math import comb
+
+import pytest
+
+from kat_util import bid_of, hand_of, load_kats, truth, unquote
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+OPENINGS = [(2, "C"), (2, "NT"), (1, "NT"), (1, "S"), (1, "H"), (1, "D"), (1, "C"), (2, "D"), (2, "H"), (2, "S"),
+            (3, "C"), (3, "D"), (3, "H"), (3, "S")]
+NT1 = [(2, "C"), (2, "D"), (2, "H"), (2, "S"), (3, "C"), (2, "NT"), (3, "NT"), (4, "NT"), (6, "NT")]
+NT2 = [(3, "C"), (3, "D"), (3, "H"), (3, "S"), (3, "NT"), (4, "NT"), (6, "NT")]
+TWO_C = [(2, "D"), (2, "H"), (2, "S"), (2, "NT"), (3, "C"), (3, "D")]
+
+
+def test_suit_loosers_kats():
+    kats = load_kats("SUIT-LOOSERS")
+    assert len(kats) == 7
+    for where, form, exp in kats:
+        ranks = unquote(form[1]) or []
+        assert O.lib().orc_suit_losers(sum(1 << r for r in ranks)) == exp, where
+
+
+def test_balanced_kats():
+    kats = [k for k in load_kats("ASSESS-HAND")]
+    assert len(kats) == 6
+    for where, form, exp in kats:
+        assert form[2] == ["FUNCTION", "BALANCED?"]
+        assert O.assess(hand_of(form[1]))["balanced"] == truth(exp), where
+
+
+def test_test_bid_kats():
+    kats = load_kats("TEST-BID")
+    assert len(kats) == 28
+    for where, form, exp in kats:
+        k = OPENINGS.index(bid_of(form[1]))
+        assert O.test_bid(0, k, hand_of(form[2])) == truth(exp), where
+
+
+def _scheme_of(form):
+    if len(form) == 2:
+        return 0, OPENINGS
+    s = form[2]
+    if s == ["NT-RESPONSES", 1]:
+        return 1, NT1
+    if s == ["NT-RESPONSES", 2]:
+        return 2, NT2
+    if s == "2C-RESPONSES":
+        return 3, TWO_C
+    return None, None
+
+
+def test_choose_bid_kats():
+    n = 0
+    for where, form, exp in load_kats("CHOOSE-BID"):
+        sid, table = _scheme_of(form)
+        if sid is None:
+            continue            # basic-responses / further-bid tables: generated on the host, checked on the GPU path
+        k = O.choose_bid(sid, hand_of(form[1]))
+        got = None if k < 0 else table[k]
+        assert got == bid_of(exp), where
+        n += 1
+    assert n == 10 + 13 + 8
+
+
+SUITS = {"C": 0, "D": 1, "H": 2, "S": 3, "NT": 4, "♣": 0, "♦": 1, "♥": 2, "♠": 3}
+
+
+def _parse_contract(text):
+    """independent mini-parser for the KAT strings: <level><suit>[decl][x|xx][=|+n|-n]"""
+    import re
+    m = re.fullmatch(r"([1-7])(NT|[CDHS♣♦♥♠])([NESW]?)(xx|x)?(=|[+-]\d+)?", text)
+    assert m, text
+    level, suit, decl, dbl, out = m.groups()
+    tricks = int(level) + 6 + (0 if out in (None, "=") else int(out))
+    return int(level), SUITS[suit], "NESW".index(decl) if decl else -1, {None: 0, "x": 1, "xx": 2}[dbl], tricks
+
+
+def _contract_arg(form):
+    assert form[0] == "MAKE-INSTANCE" and form[2] == ":="
+    return _parse_contract(str(form[3]))
+
+
+def test_base_score_kats():
+    kats = load_kats("BASE-SCORE")
+    assert len(kats) == 7
+    for where, form, exp in kats:
+        level, suit, decl, dbl, tricks = _contract_arg(form[1])
+        vul = 1 if len(form) > 2 and form[2] == ":VULNERABLE" and truth(form[3]) else 0
+        assert O.lib().orc_base_score(level, suit, decl, dbl, tricks, vul) == exp, where
+
+
+def test_match_points_kats():
+    kats = load_kats("MATCH-POINTS")
+    assert len(kats) == 3
+    for where, form, exp in kats:
+        a, b = _contract_arg(form[1]), _contract_arg(form[2])
+        vul = str(unquote(form[4])).lower() if len(form) > 3 else None
+        sa = O.lib().orc_base_score(a[0], a[1], a[2], a[3], a[4], 1 if vul in ("ns", "both") else 0)
+        sb = O.lib().orc_base_score(b[0], b[1], b[2], b[3], b[4], 1 if vul in ("ew", "both") else 0)
+        assert O.imps(sa - sb) == exp, where
+
+
+def test_contract_score_properties():
+    """unpinned branches follow the source text: spot values computed by hand from bridge.cl:3045-3069"""
+    cs = O.lib().orc_contract_score
+    assert cs(4, 9, 0, 0, 3) == 400            # 3NT=
+    assert cs(4, 13, 1, 0, 7) == 220 + 2000    # 7NT= vulnerable
+    assert cs(2, 12, 1, 0, 6) == 180 + 1250    # 6H= vulnerable
+    assert cs(3, 10, 0, 2, 4) == 480 + 300 + 100   # 4Sxx=
+    assert cs(3, 11, 0, 2, 4) == 480 + 300 + 100 + 100   # redoubled overtrick at the doubled rate (kept quirk)
+    assert cs(0, 6, 0, 1, 5) == -800 + 300 * (-5 + 3)    # 5Cx-5 not vulnerable: -1400
+    assert cs(0, 7, 0, 1, 5) == -1100                    # -4 doubled not vulnerable (non-standard, kept)
+    assert cs(1, 8, 1, 0, 4) == -200
+    assert cs(1, 9, 0, 0, 0) == 110                      # level defaults to tricks-6
+    assert cs(1, 5, 0, 0, 0) == -100                     # level defaults to 1
+
+
+def test_combinations_and_permut_weight_kats():
+    for where, form, exp in load_kats("COMBINATIONS"):
+        assert O.lib().orc_combinations(form[1], form[2]) == exp, where
+    L = O.lib()
+    for where, form, exp in load_kats("PERMUT-WEIGHT"):
+        supply, permut = unquote(form[1]), unquote(form[2])
+        supply = list(supply) + [0] * (len(permut) - len(supply))      # add-zeros
+        w = 1
+        for s, p in zip(supply, permut):
+            w *= L.orc_combinations(s, p)
+        assert w == exp, where
+
+
+def _supply_mask(supply):
+    """reference supply rows (n_low nJ nQ nK nA) -> 52-bit card mask with the low cards taken from rank 0 up"""
+    m = 0
+    for s, row in enumerate(supply):
+        for r in range(row[0]):
+            m |= 1 << (13 * s + r)
+        for h in range(4):
+            if row[1 + h]:
+                m |= 1 << (13 * s + 9 + h)
+    return m
+
+
+def _pattern_rows(p16, nsuits):
+    return [[(p16 >> (15 - (4 * s + h))) & 1 for h in range(4)] for s in range(nsuits)]
+
+
+def test_hc_permuts_kats():
+    kats = load_kats("HC-PERMUTS")
+    assert len(kats) == 4
+    for where, form, exp in kats:
+        supply = unquote(form[1])
+        kw = {}
+        rest = form[2:]
+        for i in range(0, len(rest), 2):
+            kw[str(rest[i])] = unquote(rest[i + 1])
+        spec = {}
+        if ":HCP" in kw:
+            spec["hcp"] = tuple(kw[":HCP"])
+        if ":SUITDEF" in kw:
+            for name, sd in zip("cdhs", kw[":SUITDEF"]):
+                if sd is not None:
+                    spec[name] = (sd[0], sd[1], tuple(sd[2]) if isinstance(sd[2], list) else sd[2])
+        # hc-permuts ignores suit lengths: give every suit an explicit (0 13) so no pattern has zero weight rows removed
+        g = O.Distgen(_supply_mask(supply), **spec)
+        got = [_pattern_rows(p, len(supply)) for _, p in g.items()]
+        assert got == (exp or []), where
+    where, form, exp = load_kats("LENGTH")[0]
+    assert form[1][0] == "HC-PERMUTS"
+    assert O.Distgen(_supply_mask(unquote(form[1][1]))).npat == exp == 1024
+
+
+def test_possible_lc_lens_kats():
+    kats = load_kats("POSSIBLE-LC-LENS")
+    assert len(kats) == 2
+    for where, form, exp in kats:
+        pattern, lc_supply, lens = unquote(form[1]), unquote(form[2]), unquote(form[3])
+        # build a deck with that low-card supply and every honour, then look the pattern up
+        mask = _supply_mask([[n, 1, 1, 1, 1] for n in lc_supply])
+        spec = {k: (v if isinstance(v, int) else tuple(v)) for k, v in zip("cdhs", lens)}
+        g = O.Distgen(mask, **spec)
+        p16 = 0
+        for b in [x for suit in pattern for x in suit]:
+            p16 = (p16 << 1) | b
+        w = dict((p, wt) for wt, p in g.items())[p16]
+        expect = sum(comb(lc_supply[0], t[0]) * comb(lc_supply[1], t[1]) * comb(lc_supply[2], t[2]) * comb(lc_supply[3], t[3])
+                     for t in (exp or []))
+        assert w == expect, where
+
+
+def test_distgen_golden_file():
+    """bridge.cl:1047-1051 + backend/test/distgen-test.dat: 12 012 (weight pattern) rows in order"""
+    g = json.load(open(os.path.join(HERE, "golden", "distgen_golden.json")))
+    d = O.Distgen(c=(5, None), d=(0, 4), h=(0, 1), hcp=(10, 15))
+    rows = [[w, p] for w, p in d.items()]
+    assert len(rows) == 12012
+    assert rows == g["rows"]
+    assert d.total == 8020911760
+
+
+def test_exact_counts():
+    """SURVEY appendix B facts (all from the enumeration)"""
+    assert O.Distgen().total == 635002871360                       # nil bounds: the 9-card cap quirk
+    full = O.Distgen(c=(0, 13), d=(0, 13), h=(0, 13), s=(0, 13))
+    assert full.total == comb(52, 13) == 635013559600
+    box = O.Distgen(hcp=(15, 17), c=(2, 5), d=(2, 5), h=(2, 4), s=(2, 4))
+    assert (box.npat, box.total) == (10890, 29286389970)
+    hcp, lens = box.pmf()
+    assert hcp[15:18] == [12732541524, 9607921812, 6945926634]
+    hcp, lens = full.pmf()
+    assert hcp[:4] == [2310789600, 5006710800, 8611542576, 15636342960] and hcp[37] == 4
+    for s in range(4):
+        assert lens[s] == [comb(13, k) * comb(39, 13 - k) for k in range(14)]
+
+
+def test_reference_sampler_respects_ranges():
+    """`build` with one ranged seat: every sampled hand is inside the ranges (bridge.cl:2989-3003 style)"""
+    g = O.Distgen(hcp=(15, 17), c=(2, 5), d=(2, 5), h=(2, 4), s=(2, 4))
+    deals = g.build_batch(300, seed=5)
+    f = O.features_batch(O.mask52_to_lanes64(deals[:, 0]))
+    assert ((f[:, 8] >= 15) & (f[:, 8] <= 17)).all()
+    assert (f[:, 0:2] >= 2).all() and (f[:, 0:2] <= 5).all() and (f[:, 2:4] >= 2).all() and (f[:, 2:4] <= 4).all()
+    allc = deals[:, 0] | deals[:, 1] | deals[:, 2] | deals[:, 3]
+    assert (allc == (1 << 52) - 1).all()
+
+
+def test_gpu_deal_mirror_is_a_deal_and_void_rate():
+    rec, void = O.gpu_deal_batch(12345, 0, 20000)
+    from bridge_mc_b200.cards import seat_masks
+    m = seat_masks(rec)
+    for k in range(4):
+        assert all(bin(int(x)).count("1") == 13 for x in m[:500, k])
+    assert 0.0005 < void.mean() < 0.004
