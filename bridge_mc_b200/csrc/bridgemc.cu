@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) score_tally_kernel(const __grid_constant_
 // INT32 issue-rate microbenchmark: per thread, 8 independent chains mixing the
 // fma pipe (IMAD) and the alu pipe (LOP3 / IADD3), the two pipes the deal uses.
 // ---------------------------------------------------------------------------
-constexpr int PEAK_ITERS = 4096, PEAK_OPS_PER_ITER = 32;
+constexpr int PEAK_ITERS = 1024, PEAK_OPS_PER_ITER = 128;
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t seed, uint32_t *out)
 {
     uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t seed, uint32_t *
 #pragma unroll 1
     for (int i = 0; i < PEAK_ITERS; ++i) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 16; ++j) {
             a0 = a0 * 0x010101u + b0; b0 = b0 ^ a1 ^ 0x9E3779B9u;
             a1 = a1 * 0x010103u + b1; b1 = b1 ^ a2 ^ 0x7F4A7C15u;
             a2 = a2 * 0x010105u + b2; b2 = b2 ^ a3 ^ 0x85EBCA6Bu;
@@ -444,7 +444,9 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t seed, uint32_t *
 struct bmc_ctx {
     int device = 0;
     int sms = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    bmc_record *d_rec = nullptr;                 // grow-only record scratch of the host-buffer API
+    uint64_t rec_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long *d_tallies = nullptr;     // scratch tallies for the host-buffer API
     uint64_t launches = 0;
@@ -530,6 +532,7 @@ int bmc_init(int device, bmc_ctx **out)
     c->sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaMalloc(&c->d_tallies, sizeof(bmc_tallies)));
@@ -555,6 +558,8 @@ void bmc_shutdown(bmc_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tallies);
+    if (c->d_rec) cudaFree(c->d_rec);
+    cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->own_stream);
@@ -818,55 +823,58 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     return BMC_OK;
 }
 
-int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
-                   uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records_dev, uint64_t cap,
-                   void *tallies_dev, bmc_stats *stats)
+// Common driver.  host_out != NULL: records are streamed to the caller's buffer on a
+// second stream while the next wave computes (the copy of wave k overlaps wave k+1).
+static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                       uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records_dev, uint64_t cap,
+                       void *tallies_dev, bmc_stats *stats, bmc_record *host_out)
 {
-    if (!ctx || !tallies_dev) return fail(BMC_E_INVALID, "bmc_sample_dev: ctx / tallies_dev is NULL");
     if (n_accept_target == 0 && n_raw == 0) return fail(BMC_E_INVALID, "nothing to do: n_raw == 0 and no accept target");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CUDA_TRY(cudaSetDevice(ctx->device));
     auto t0 = std::chrono::steady_clock::now();
     ConsDev dev{};
     const bool has_cons = cons && cons->has_cons;
     if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
+    const FixDev *fix = (cons && cons->has_fixed) ? &cons->fix : nullptr;
+    const bool stream_copy = host_out && records_dev && cap;
+    const bool stepwise = n_accept_target != 0 || stream_copy;
     if (wave == 0) wave = 1ull << 26;
+    const uint64_t max_launch = stepwise ? wave : (1ull << 36);   // 2^36: keeps a warp's iteration counter in 32 bits
     uint32_t waves = 0;
-    uint64_t launches0 = ctx->launches;
+    const uint64_t launches0 = ctx->launches;
     unsigned long long head[4] = {0, 0, 0, 0}, start_acc = 0;
-    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (n_accept_target == 0) {
-        // split only so that a warp's iteration counter stays 32-bit and launches stay bounded
-        uint64_t done = 0;
-        const uint64_t max_launch = 1ull << 36;
-        while (done < n_raw) {
-            const uint64_t n = n_raw - done < max_launch ? n_raw - done : max_launch;
-            int rc = launch_wave(ctx, dev, has_cons, (cons && cons->has_fixed) ? &cons->fix : nullptr, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
-            if (rc) return rc;
-            done += n;
-            ++waves;
-        }
-    } else {
+    if (stepwise) {
         CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         start_acc = head[2];
-        uint64_t done = 0;
-        for (;;) {
-            if (n_raw && done >= n_raw) break;
-            uint64_t n = wave;
-            if (n_raw && n_raw - done < n) n = n_raw - done;
-            int rc = launch_wave(ctx, dev, has_cons, (cons && cons->has_fixed) ? &cons->fix : nullptr, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
-            if (rc) return rc;
-            done += n;
-            ++waves;
-            CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            if (head[2] - start_acc >= n_accept_target) break;
+    }
+    uint64_t copied = start_acc < cap ? start_acc : cap;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    uint64_t done = 0;
+    for (;;) {
+        if (n_raw && done >= n_raw) break;
+        uint64_t n = max_launch;
+        if (n_raw && n_raw - done < n) n = n_raw - done;
+        int rc = launch_wave(ctx, dev, has_cons, fix, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
+        if (rc) return rc;
+        done += n;
+        ++waves;
+        if (!stepwise) continue;
+        CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (stream_copy) {
+            const uint64_t upto = head[2] < cap ? head[2] : cap;
+            if (upto > copied) {
+                CUDA_TRY(cudaMemcpyAsync(host_out + copied, (const bmc_record *)records_dev + copied,
+                                         (upto - copied) * sizeof(bmc_record), cudaMemcpyDeviceToHost, ctx->copy_stream));
+                copied = upto;
+            }
         }
+        if (n_accept_target && head[2] - start_acc >= n_accept_target) break;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stream_copy) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     if (stats) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
@@ -880,39 +888,49 @@ int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uin
     return BMC_OK;
 }
 
+int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                   uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records_dev, uint64_t cap,
+                   void *tallies_dev, bmc_stats *stats)
+{
+    if (!ctx || !tallies_dev) return fail(BMC_E_INVALID, "bmc_sample_dev: ctx / tallies_dev is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, records_dev, cap, tallies_dev,
+                       stats, nullptr);
+}
+
 int bmc_sample(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
                uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, bmc_record *records, uint64_t cap,
                bmc_tallies *tallies, bmc_stats *stats)
 {
     if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
     auto t0 = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    void *d_rec = nullptr;
-    if (records && cap) CUDA_TRY(cudaMalloc(&d_rec, cap * sizeof(bmc_record)));
-    unsigned long long *d_tal = nullptr;
-    CUDA_TRY(cudaMalloc(&d_tal, sizeof(bmc_tallies)));
-    cudaMemsetAsync(d_tal, 0, sizeof(bmc_tallies), ctx->stream);
-    bmc_stats st{};
-    int rc = bmc_sample_dev(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, d_rec, cap, d_tal, &st);
-    if (rc == BMC_OK) {
-        cudaError_t e = cudaSuccess;
-        if (d_rec && st.stored) e = cudaMemcpyAsync(records, d_rec, st.stored * sizeof(bmc_record), cudaMemcpyDeviceToHost, ctx->stream);
-        bmc_tallies host_t;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&host_t, d_tal, sizeof host_t, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(BMC_E_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
-        else {
-            host_t.stored = st.stored;
-            if (tallies) *tallies = host_t;
-        }
+    if (!records) cap = 0;
+    // device scratch for the records is kept by the context and only ever grows
+    if (cap > ctx->rec_cap) {
+        if (ctx->d_rec) cudaFree(ctx->d_rec);
+        ctx->d_rec = nullptr;
+        ctx->rec_cap = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_rec, cap * sizeof(bmc_record)));
+        ctx->rec_cap = cap;
     }
-    cudaFree(d_rec);
-    cudaFree(d_tal);
-    if (stats && rc == BMC_OK) {
+    CUDA_TRY(cudaMemsetAsync(ctx->d_tallies, 0, sizeof(bmc_tallies), ctx->stream));
+    bmc_stats st{};
+    int rc = sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, cap ? ctx->d_rec : nullptr, cap,
+                         ctx->d_tallies, &st, cap ? records : nullptr);
+    if (rc != BMC_OK) return rc;
+    bmc_tallies host_t;
+    CUDA_TRY(cudaMemcpyAsync(&host_t, ctx->d_tallies, sizeof host_t, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    host_t.stored = st.stored;
+    if (tallies) *tallies = host_t;
+    if (stats) {
         *stats = st;
         stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
-    return rc;
+    return BMC_OK;
 }
 
 // ---- filter ---------------------------------------------------------------------
