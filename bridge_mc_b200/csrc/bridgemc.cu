@@ -22,6 +22,7 @@
 #include "../../include/bridgemc.h"
 #include "deal.cuh"
 #include "features.cuh"
+#include "seatfirst.cuh"
 #include "rules.hpp"
 
 using namespace bmc;
@@ -70,6 +71,8 @@ struct SampleArgs {
     unsigned long long *tallies;   // bmc_tallies as u64 words
     uint32_t tally_mask;
     uint32_t iters;          // warp-iterations per warp
+    uint32_t sf_q0;          // seat-first mode: initial Q of stage B (capacity 0 for the primary seat)
+    uint32_t pad;
 };
 
 __device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0, uint32_t &m1)
@@ -125,6 +128,26 @@ __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, b
                 }
             }
         }
+    }
+}
+
+// block-level flush of the per-warp shared histograms into bmc_tallies (u64 atomics)
+__device__ __forceinline__ void flush_hist(const SampleArgs &a, const uint32_t *s_hist)
+{
+    if (!a.tally_mask) return;
+    for (int i = threadIdx.x; i < SH_WORDS; i += THREADS) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS_PER_BLOCK; ++w) v += s_hist[w * SH_WORDS + i];
+        if (v == 0u) continue;
+        int word;                                                                    // padded shared layout -> bmc_tallies words
+        if (i < SH_LEN) word = 4 + i;                                                // hcp[4][40]
+        else if (i < SH_SHAPE) {
+            const int j = i - SH_LEN, bin = j & 15;
+            if (bin >= BMC_LEN_BINS) continue;
+            word = 4 + 160 + (j >> 4) * BMC_LEN_BINS + bin;                          // len[4][4][14]
+        } else word = 4 + 160 + 224 + (i - SH_SHAPE);                                // shape[4][40]
+        atomicAdd(&a.tallies[word], (unsigned long long)v);
     }
 }
 
@@ -203,23 +226,106 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
         if (n_void) atomicAdd(&a.tallies[1], n_void);
     }
     __syncthreads();
-    if (a.tally_mask) {
-        for (int i = threadIdx.x; i < SH_WORDS; i += THREADS) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS_PER_BLOCK; ++w) v += s_hist[w][i];
-            if (v == 0u) continue;
-            // map the padded shared layout to bmc_tallies words
-            int word;
-            if (i < SH_LEN) word = 4 + i;                                            // hcp[4][40]
-            else if (i < SH_SHAPE) {
-                const int j = i - SH_LEN, bin = j & 15;
-                if (bin >= BMC_LEN_BINS) continue;
-                word = 4 + 160 + (j >> 4) * BMC_LEN_BINS + bin;                       // len[4][4][14]
-            } else word = 4 + 160 + 224 + (i - SH_SHAPE);                            // shape[4][40]
-            atomicAdd(&a.tallies[word], (unsigned long long)v);
+    flush_hist(a, &s_hist[0][0]);
+}
+
+// ---------------------------------------------------------------------------
+// K1b: seat-first sampler (seatfirst.cuh): stages A1 -> A2 -> B with two per-warp
+// compaction queues, so each stage runs on full warps.
+// ---------------------------------------------------------------------------
+__constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
+                                        thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
+
+__global__ void __launch_bounds__(THREADS, 5) sample_seatfirst_kernel(const __grid_constant__ SampleArgs a)
+{
+    __shared__ uint32_t s_hist[WARPS_PER_BLOCK][SH_WORDS];
+    __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (H | r << 16, idx_lo, idx_hi, -)
+    __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, idx_lo, idx_hi)
+    __shared__ uint8_t s_shape[14 * 14 * 14];
+
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < WARPS_PER_BLOCK * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
+    __syncthreads();
+
+    uint32_t *hist = s_hist[warp];
+    uint4 *q1 = s_q1[warp], *q2 = s_q2[warp];
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
+    unsigned long long n_raw = 0, n_void = 0, n_acc = 0;
+    unsigned h1 = 0, t1 = 0, h2 = 0, t2 = 0;         // queue cursors, warp-uniform
+    const uint32_t P = a.cons.primary;
+    const SeatC &c = a.cons.seat[P];
+    const uint32_t A2h = (c.A[2] & 0xFFu) | 0x80808000u, B2h = c.B[2] & 0xFFu;   // HCP byte only
+
+    // ---- stage B on up to 32 queued hands ------------------------------------------
+    auto run_b = [&](unsigned count) {
+        const uint4 r = q2[(h2 + lane) % QCAP];
+        h2 += count;
+        __syncwarp();
+        const bool active = lane < count;
+        Planes pl;
+        const uint32_t xl = (P & 1u) ? 0xFFFFFFFFu : 0u, xh = (P & 2u) ? 0xFFFFFFFFu : 0u;
+        const bool voided = deal_fixed_core(a.key, STREAM_SEATFIRST_B, 39u, a.sf_q0, r.x & xl, r.y & xl, r.x & xh, r.y & xh,
+                                            ~r.x & 0x1FFF1FFFu, ~r.y & 0x1FFF1FFFu, c_thresh39, r.z, r.w, pl);
+        n_void += (active && voided) ? 1u : 0u;
+        stage_b(a, pl, active && !voided, hist, s_shape, lane, n_acc);
+    };
+    // ---- stage A2 on up to 32 queued honour sets ---------------------------------------
+    auto run_a2 = [&](unsigned count) {
+        const uint4 r = q1[(h1 + lane) % QCAP];
+        h1 += count;
+        __syncwarp();
+        const bool active = lane < count;
+        bool voided = false;
+        uint32_t m0, m1;
+        sf_lows(a.key, r.y, r.z, r.x & 0xFFFFu, (int)(r.x >> 16), voided, m0, m1);
+        n_void += (active && voided) ? 1u : 0u;
+        const Feat f = hand_features(m0, m1);
+        const bool ok = active && !voided && seat_ranges_ok(c, f);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+        if (bal) {
+            if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, r.y, r.z);
+            t2 += __popc(bal);
+            __syncwarp();
+            if (t2 - h2 >= 32u) run_b(32u);
+        }
+    };
+
+    for (uint32_t it = 0; it < a.iters; ++it) {
+        const unsigned long long off = ((unsigned long long)it * total_warps + gwarp) * 32ull + lane;
+        const bool valid = off < a.n;
+        const unsigned long long idx = a.first + off;
+        SeatFirstState s;
+        const uint32_t H = sf_honours(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), s);
+        n_raw += valid ? 1u : 0u;
+        n_void += (valid && s.voided) ? 1u : 0u;
+        uint32_t Pw, hcp;
+        honour_features(H, Pw, hcp);
+        const bool ok = valid && !s.voided && in_ranges(Pw, c.A[1], c.B[1]) && in_ranges(hcp, A2h, B2h);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+        if (bal) {
+            if (ok) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] =
+                        make_uint4(H | ((uint32_t)s.r << 16), (uint32_t)idx, (uint32_t)(idx >> 32), 0u);
+            t1 += __popc(bal);
+            __syncwarp();
+            if (t1 - h1 >= 32u) run_a2(32u);
         }
     }
+    if (t1 - h1) run_a2(t1 - h1);
+    if (t2 - h2) run_b(t2 - h2);
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_raw += __shfl_xor_sync(0xFFFFFFFFu, n_raw, o);
+        n_void += __shfl_xor_sync(0xFFFFFFFFu, n_void, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.tallies[0], n_raw);
+        if (n_void) atomicAdd(&a.tallies[1], n_void);
+    }
+    __syncthreads();
+    flush_hist(a, &s_hist[0][0]);
 }
 
 // ---------------------------------------------------------------------------
@@ -450,7 +556,7 @@ struct bmc_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long *d_tallies = nullptr;     // scratch tallies for the host-buffer API
     uint64_t launches = 0;
-    int blocks_cons = 0, blocks_free = 0;
+    int blocks_cons = 0, blocks_free = 0, blocks_sf = 0;
     std::mutex mu;
 };
 
@@ -462,6 +568,9 @@ struct bmc_constraints {
     bool has_cons = false;
     bool has_fixed = false;
     FixDev fix{};
+    int mode = 0;                // requested: 0 auto, 1 full deal (deal52), 2 seat-first
+    int resolved = 0;            // 0 = not calibrated yet
+    double stage_a_pass = -1.0;  // measured pass rate of the primary seat's ranges
     std::mutex mu;
 };
 
@@ -548,6 +657,8 @@ int bmc_init(int device, bmc_ctx **out)
     c->blocks_cons = c->sms * (occ > 0 ? occ : 1);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<false, false>, THREADS, 0));
     c->blocks_free = c->sms * (occ > 0 ? occ : 1);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_seatfirst_kernel, THREADS, 0));
+    c->blocks_sf = c->sms * (occ > 0 ? occ : 1);
     *out = c;
     return BMC_OK;
 }
@@ -713,6 +824,17 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     return BMC_OK;
 }
 
+int bmc_constraints_set_mode(bmc_constraints *c, int mode)
+{
+    if (!c || mode < 0 || mode > 2) return fail(BMC_E_INVALID, "bmc_constraints_set_mode: bad argument");
+    if (mode == 2 && (c->has_fixed || !c->has_cons)) return fail(BMC_E_INVALID, "seat-first mode needs a constrained seat and no fixed hands");
+    c->mode = mode;
+    c->resolved = 0;
+    return BMC_OK;
+}
+int bmc_constraints_mode(const bmc_constraints *c) { return c ? c->resolved : 0; }
+int bmc_constraints_primary(const bmc_constraints *c) { return c ? (int)c->dev.primary : -1; }
+
 void bmc_constraints_destroy(bmc_constraints *c)
 {
     if (!c) return;
@@ -791,8 +913,8 @@ static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
 }
 
 // ---- sampling -------------------------------------------------------------------
-static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const FixDev *fix, uint64_t seed, uint64_t first,
-                       uint64_t n, uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev)
+static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const FixDev *fix, bool seatfirst, uint64_t seed,
+                       uint64_t first, uint64_t n, uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev)
 {
     SampleArgs a;
     a.cons = cons;
@@ -805,13 +927,21 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     a.cap = records_dev ? cap : 0;
     a.tallies = (unsigned long long *)tallies_dev;
     a.tally_mask = tally_mask;
-    int blocks = has_cons ? ctx->blocks_cons : ctx->blocks_free;
+    {   // stage B of the seat-first sampler: the primary seat has no capacity left
+        uint32_t cap4[4] = {13, 13, 13, 13};
+        cap4[cons.primary & 3u] = 0;
+        const uint32_t p0 = cap4[0], p1 = p0 + cap4[1], p2 = p1 + cap4[2];
+        a.sf_q0 = (128u - p0) | ((128u - p1) << 8) | ((128u - p2) << 16);
+        a.pad = 0;
+    }
+    int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
     const uint64_t per_iter = (uint64_t)blocks * THREADS;
     if (n < per_iter) blocks = (int)((n + THREADS - 1) / THREADS);
     if (blocks < 1) blocks = 1;
     const uint64_t chunk = (uint64_t)blocks * THREADS;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
-    if (fix) {
+    if (seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a);
+    else if (fix) {
         if (has_cons) sample_kernel<true, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
         else sample_kernel<false, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
     } else {
@@ -835,6 +965,34 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     const bool has_cons = cons && cons->has_cons;
     if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
     const FixDev *fix = (cons && cons->has_fixed) ? &cons->fix : nullptr;
+    bool seatfirst = false;
+    if (has_cons && !fix) {
+        bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
+        if (cc->resolved == 0) {
+            if (cc->mode != 0) cc->resolved = cc->mode;
+            else {
+                // calibrate once: pass rate of the primary seat's RANGES alone over 2^16 raw deals
+                ConsDev cal = dev;
+                for (int k = 0; k < 4; ++k) {
+                    cal.seat[k].prog = 0xFFFFFFFFu;
+                    if ((uint32_t)k != dev.primary) cal.seat[k].active = 0;
+                }
+                unsigned long long *d_cal = nullptr, h4[4] = {0, 0, 0, 0};
+                CUDA_TRY(cudaMalloc(&d_cal, sizeof(bmc_tallies)));
+                cudaMemsetAsync(d_cal, 0, sizeof(bmc_tallies), ctx->stream);
+                int rc = launch_wave(ctx, cal, true, nullptr, false, 0x63616C6962726174ull, 0, 1u << 16, 0, nullptr, 0, d_cal);
+                cudaError_t e = cudaMemcpyAsync(h4, d_cal, sizeof h4, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                cudaFree(d_cal);
+                if (rc) return rc;
+                if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("calibration: ") + cudaGetErrorString(e));
+                cc->stage_a_pass = (double)h4[2] / (double)(h4[0] ? h4[0] : 1);
+                // seat-first pays off when most deals die on the primary seat's ranges
+                cc->resolved = cc->stage_a_pass < 0.30 ? 2 : 1;
+            }
+        }
+        seatfirst = cc->resolved == 2;
+    }
     const bool stream_copy = host_out && records_dev && cap;
     const bool stepwise = n_accept_target != 0 || stream_copy;
     if (wave == 0) wave = 1ull << 26;
@@ -848,19 +1006,27 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         start_acc = head[2];
     }
     uint64_t copied = start_acc < cap ? start_acc : cap;
-    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    float kernel_ms = 0.f;
+    if (!stepwise) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     uint64_t done = 0;
     for (;;) {
         if (n_raw && done >= n_raw) break;
         uint64_t n = max_launch;
         if (n_raw && n_raw - done < n) n = n_raw - done;
-        int rc = launch_wave(ctx, dev, has_cons, fix, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
+        if (stepwise) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        int rc = launch_wave(ctx, dev, has_cons, fix, seatfirst, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
         if (rc) return rc;
         done += n;
         ++waves;
         if (!stepwise) continue;
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);       // device time of this wave's kernel only
+            kernel_ms += ms;
+        }
         if (stream_copy) {
             const uint64_t upto = head[2] < cap ? head[2] : cap;
             if (upto > copied) {
@@ -871,13 +1037,13 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         }
         if (n_accept_target && head[2] - start_acc >= n_accept_target) break;
     }
-    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!stepwise) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (stream_copy) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     if (stats) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        float ms = kernel_ms;
+        if (!stepwise) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         stats->raw = head[0]; stats->voided = head[1]; stats->accepted = head[2];
         stats->stored = records_dev ? (head[2] < cap ? head[2] : cap) : 0;
         stats->waves = waves;

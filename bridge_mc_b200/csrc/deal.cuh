@@ -201,14 +201,17 @@ __host__ inline void fixdev_init(FixDev &f, const uint64_t fixed_mask[4], const 
     }
 }
 
-__device__ __forceinline__ bool deal_fixed(const PhiloxKey &key, const FixDev &f, uint32_t idx_lo, uint32_t idx_hi, Planes &pl)
+// Core loop.  All arguments but (idx, masks of the v2 path) are grid-uniform; the
+// seat-first sampler calls it with PER-LANE masks (the primary seat's hand).
+__device__ __forceinline__ bool deal_fixed_core(const PhiloxKey &key, uint32_t stream, uint32_t n_free, uint32_t q0,
+                                                uint32_t lo0, uint32_t lo1, uint32_t hi0, uint32_t hi1, uint32_t free0,
+                                                uint32_t free1, const uint32_t *__restrict__ thresh, uint32_t idx_lo,
+                                                uint32_t idx_hi, Planes &pl)
 {
     uint32_t w[4];
-    uint32_t x = 0, Q = f.q0;
-    uint32_t lo0 = f.lo0, lo1 = f.lo1, hi0 = f.hi0, hi1 = f.hi1;
-    uint32_t free0 = f.free0, free1 = f.free1;
+    uint32_t x = 0, Q = q0;
     bool voided = false;
-    uint32_t n = f.n_free;
+    uint32_t n = n_free;
     for (uint32_t v = 0; n >= 1; ++v, --n) {
         uint32_t pos;
         if (free0) { pos = __ffs(free0) - 1; free0 &= free0 - 1; }
@@ -216,12 +219,12 @@ __device__ __forceinline__ bool deal_fixed(const PhiloxKey &key, const FixDev &f
         uint32_t u = 0;
         if (n >= 2) {
             if ((v & 3u) == 0u) {
-                if ((v & 15u) == 0u) philox4x32_10(key, idx_lo, idx_hi, v >> 4, 0u, w);
+                if ((v & 15u) == 0u) philox4x32_10(key, idx_lo, idx_hi, v >> 4, stream, w);
                 const uint32_t sel = (v >> 2) & 3u;
                 x = sel == 0u ? w[0] : sel == 1u ? w[1] : sel == 2u ? w[2] : w[3];
             }
             mul_wide(x, n, x, u);
-            if ((v & 3u) == 3u || n == 2u) voided |= x < f.thresh[v >> 2];
+            if ((v & 3u) == 3u || n == 2u) voided |= x < thresh[v >> 2];
         }
         const uint32_t E = u * 0x010101u + Q;
         const uint32_t A = E & 0x808080u;                  // bit 7 of byte j: u >= prefix_j
@@ -233,6 +236,11 @@ __device__ __forceinline__ bool deal_fixed(const PhiloxKey &key, const FixDev &f
     }
     pl.lo0 = lo0; pl.lo1 = lo1; pl.hi0 = hi0; pl.hi1 = hi1;
     return voided;
+}
+
+__device__ __forceinline__ bool deal_fixed(const PhiloxKey &key, const FixDev &f, uint32_t idx_lo, uint32_t idx_hi, Planes &pl)
+{
+    return deal_fixed_core(key, 0u, f.n_free, f.q0, f.lo0, f.lo1, f.hi0, f.hi1, f.free0, f.free1, f.thresh, idx_lo, idx_hi, pl);
 }
 
 }  // namespace bmc

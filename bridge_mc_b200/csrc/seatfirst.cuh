@@ -1,0 +1,140 @@
+// seatfirst.cuh -- lazy, seat-first dealing for rejection sampling (device).
+//
+// A uniformly random deal factorises as
+//     P(primary seat's honours) x P(its low cards | honours) x P(other three hands | primary hand)
+// and a constraint that rejects most deals on the primary seat alone never needs
+// the later factors.  The sampler therefore runs three stages with a warp-level
+// compaction queue between them, so every stage executes on full warps:
+//   A1  16 honour cards, primary seat vs the rest (1 Philox call)  -> HCP / suit-HCP ranges
+//   A2  36 low cards, primary seat vs the rest (2 Philox calls)     -> all ranges of the seat
+//   B   the other 39 cards to the other three seats (deal_fixed with the primary
+//       hand as a per-lane fixed hand, 3 Philox calls)            -> every seat's full test
+// Each factor is sampled exactly (mixed-radix digits + Lemire rejection, see
+// deal.cuh), so accepted deals are exactly uniform over the deals that satisfy the
+// constraint -- the same distribution as dealing all 52 cards and rejecting.
+// Mirrored bit for bit by orc_gpu_seatfirst_hand / orc_gpu_deal_fixed in
+// oracle/bmc_oracle.c.
+//
+// Binary step (seat gets the card iff u < r, r = cards the seat still needs):
+//     d = u - r ; mask = (mask << 1) | sign(d) ; r += d >> 31        (4 instructions with the digit)
+#pragma once
+#include <cstdint>
+#include <utility>
+#include "deal.cuh"
+
+namespace bmc {
+
+constexpr uint32_t STREAM_SEATFIRST_A = 2u, STREAM_SEATFIRST_B = 3u;
+
+// ---- digit schedule of stage A: 52 cards, n = 52 - i cards left at step i ----------
+// words 0..3 (Philox block 0): n = 52..37 in fours; words 4..7 (block 1): 36..21 in fours;
+// words 8..10 (block 2): 20..16, 15..10, 9..2.
+__host__ __device__ constexpr int sf_grp_hi(int g)
+{
+    constexpr int t[11] = {52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9};
+    return t[g];
+}
+__host__ __device__ constexpr int sf_grp_lo(int g)
+{
+    constexpr int t[11] = {49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2};
+    return t[g];
+}
+__host__ __device__ constexpr int sf_grp_of(int n)
+{
+    for (int g = 0; g < 11; ++g) if (n <= sf_grp_hi(g) && n >= sf_grp_lo(g)) return g;
+    return -1;
+}
+__host__ __device__ constexpr uint32_t sf_grp_thresh(int g)
+{
+    uint64_t N = 1;
+    for (int n = sf_grp_lo(g); n <= sf_grp_hi(g); ++n) N *= (uint64_t)n;
+    return (uint32_t)((1ull << 32) % N);
+}
+
+struct SeatFirstState {
+    uint32_t w[4];
+    uint32_t x;
+    uint32_t mask;      // ownership bits of the cards dealt so far (first card = highest bit)
+    int r;              // cards the primary seat still needs
+    bool voided;
+};
+
+// step I of 52: I = 0..15 honours (spade A first ... club J last), I = 16..51 low cards
+// (spade 10 first ... club 2 last)
+template <int I>
+__device__ __forceinline__ void sf_step(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s)
+{
+    constexpr int n = 52 - I;
+    uint32_t u = 0;
+    if constexpr (n >= 2) {
+        constexpr int g = sf_grp_of(n);
+        if constexpr (n == sf_grp_hi(g)) {
+            if constexpr ((g & 3) == 0) philox4x32_10(key, idx_lo, idx_hi, (uint32_t)(g >> 2), STREAM_SEATFIRST_A, s.w);
+            s.x = s.w[g & 3];
+        }
+        mul_wide(s.x, (uint32_t)n, s.x, u);
+        if constexpr (n == sf_grp_lo(g)) {
+            constexpr uint32_t thresh = sf_grp_thresh(g);
+            s.voided |= s.x < thresh;
+        }
+    }
+    const int d = (int)u - s.r;                         // < 0: the seat takes the card
+    s.mask = __funnelshift_l((uint32_t)d, s.mask, 1);   // (mask << 1) | sign bit
+    s.r += d >> 31;
+}
+
+template <int Base, int... K>
+__device__ __forceinline__ void sf_steps(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s,
+                                         std::integer_sequence<int, K...>)
+{
+    (sf_step<Base + K>(key, idx_lo, idx_hi, s), ...);
+}
+
+// Stage A1: returns H (bit h = honour h = 4*suit + (rank-9)), leaves the RNG state for A2.
+__device__ __forceinline__ uint32_t sf_honours(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s)
+{
+    s.x = 0; s.mask = 0; s.r = 13; s.voided = false;
+    sf_steps<0>(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 16>{});
+    return s.mask & 0xFFFFu;
+}
+
+// Features available after A1: power bytes (c d h s) and HCP.
+__device__ __forceinline__ void honour_features(uint32_t H, uint32_t &P, uint32_t &hcp)
+{
+    const uint32_t M = 0x01010101u;
+    const uint32_t X = (H & 0xFu) | ((H & 0xF0u) << 4) | ((H & 0xF00u) << 8) | ((H & 0xF000u) << 12);
+    const uint32_t J = X & M, Qn = (X >> 1) & M, K = (X >> 2) & M, A = (X >> 3) & M;
+    P = J + 2u * Qn + 3u * K + 4u * A;
+    hcp = (P * M) >> 24;
+}
+
+// Stage A2: continues from the A1 state (H, r, voided restored by the caller); returns the
+// seat's hand as lane-layout words.
+__device__ __forceinline__ void sf_lows(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, uint32_t H, int r, bool &voided,
+                                        uint32_t &m0, uint32_t &m1)
+{
+    SeatFirstState s;
+    s.x = 0; s.r = r; s.voided = voided;
+    s.mask = 0;
+    sf_steps<16>(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 18>{});     // lows 35..18: hearts, spades
+    const uint32_t hs = s.mask & 0x3FFFFu;
+    s.mask = 0;
+    sf_steps<34>(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 18>{});     // lows 17..0: clubs, diamonds
+    const uint32_t cd = s.mask & 0x3FFFFu;
+    voided = s.voided;
+    m0 = (cd & 0x1FFu) | ((cd & 0x3FE00u) << 7) | ((H & 0xFu) << 9) | ((H & 0xF0u) << 21);
+    m1 = (hs & 0x1FFu) | ((hs & 0x3FE00u) << 7) | ((H & 0xF00u) << 1) | ((H & 0xF000u) << 13);
+}
+
+// Lemire thresholds of deal_fixed's words for 39 free cards (4 digits per word)
+__host__ __device__ constexpr uint32_t thresh39(int w)
+{
+    uint64_t N = 1;
+    for (int d = 0; d < 4; ++d) {
+        const int n = 39 - 4 * w - d;
+        if (n >= 2) N *= (uint64_t)n;
+    }
+    return (uint32_t)((1ull << 32) % N);
+}
+
+}  // namespace bmc

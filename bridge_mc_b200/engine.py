@@ -70,6 +70,21 @@ class Constraints:
         self._h = C.c_void_p()
         check(L.bmc_constraints_create(arr, rarr, C.byref(self._h)))
 
+    MODE_AUTO, MODE_FULL, MODE_SEAT_FIRST = 0, 1, 2
+
+    def set_mode(self, mode: int):
+        """bmc_constraints_set_mode: 0 auto, 1 full deal, 2 seat-first (see bridgemc.h)."""
+        check(_lib.load().bmc_constraints_set_mode(self._h, mode))
+        return self
+
+    @property
+    def mode(self) -> int:
+        return _lib.load().bmc_constraints_mode(self._h)
+
+    @property
+    def primary(self) -> int:
+        return _lib.load().bmc_constraints_primary(self._h)
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:

@@ -136,6 +136,18 @@ void  bmc_shape_table(uint8_t out[39][4]);
 int  bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules[4],
                             bmc_constraints **out);
 void bmc_constraints_destroy(bmc_constraints *c);
+/* How raw deals are drawn (both are exactly uniform; they consume the Philox stream
+ * differently, so the deal behind a given index depends on the mode):
+ *   1 full deal   all 52 cards, then test (best when most deals pass the primary seat)
+ *   2 seat-first  the primary (most selective) seat's honours, then its low cards, then
+ *                 the other three hands -- each stage only for survivors of the previous one
+ *   0 auto        (default) calibrates the primary seat's pass rate on 2^16 deals at the
+ *                 first sampling call and picks 2 when it is below 0.30.
+ * bmc_constraints_mode returns the resolved mode (0 before the first call),
+ * bmc_constraints_primary the seat tested first. */
+int  bmc_constraints_set_mode(bmc_constraints *c, int mode);
+int  bmc_constraints_mode(const bmc_constraints *c);
+int  bmc_constraints_primary(const bmc_constraints *c);
 
 /* A rule table as printed by Lisp: "(((2 C) . FORM) ((2 NT) . FORM) ...)" --
  * `openings`, (nt-responses n), 2C-responses, (basic-responses bid) ...

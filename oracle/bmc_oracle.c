@@ -667,8 +667,8 @@ ORC_API uint64_t orc_ref_run(orc_distgen *root, uint64_t *rng_state, uint64_t n,
 
 /* CPU mirror of bmc::deal_fixed (csrc/deal.cuh): deals with fixed (`:=`) hands.
  * fixed[k] = lane-layout mask of seat k's fixed hand, 0 = seat is free. */
-ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fixed[4],
-                               uint64_t *lo_plane, uint64_t *hi_plane)
+static int gpu_deal_fixed_stream(uint64_t seed, uint64_t index, const uint64_t fixed[4], uint32_t stream,
+                                 uint64_t *lo_plane, uint64_t *hi_plane)
 {
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     uint64_t lo = 0, hi = 0, used = 0;
@@ -689,7 +689,7 @@ ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fix
         if (n >= 2) {
             if ((v & 3) == 0) {
                 if ((v & 15) == 0) {
-                    uint32_t ctr[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(v >> 4), 0 };
+                    uint32_t ctr[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(v >> 4), stream };
                     orc_philox4x32_10(ctr, key, w);
                 }
                 x = w[(v >> 2) & 3];
@@ -712,6 +712,72 @@ ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fix
     *lo_plane = lo; *hi_plane = hi;
     return voided;
 }
+ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fixed[4],
+                               uint64_t *lo_plane, uint64_t *hi_plane)
+{
+    return gpu_deal_fixed_stream(seed, index, fixed, 0, lo_plane, hi_plane);
+}
+
+/* CPU mirror of the seat-first sampler (csrc/seatfirst.cuh).  Stage A: the
+ * primary seat's hand, 52 binary steps (16 honours spade-A-first, then 36 low
+ * cards spade-10-first), Philox stream 2.  Returns the hand as a lane mask and
+ * sets *voided: bit 0 = a Lemire check failed in A1 (honours), bit 1 = in A2 (low cards). */
+static const int SF_HI[11] = {52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9};
+static const int SF_LO[11] = {49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2};
+ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int *voided)
+{
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t w[4] = {0, 0, 0, 0}, x = 0;
+    int r = 13, vd = 0;
+    uint64_t hand = 0;
+    for (int i = 0; i < 52; ++i) {
+        int n = 52 - i, u = 0;
+        if (n >= 2) {
+            int g = 0;
+            while (!(n <= SF_HI[g] && n >= SF_LO[g])) ++g;
+            if (n == SF_HI[g]) {
+                if ((g & 3) == 0) {
+                    uint32_t ctr[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(g >> 2), 2 };
+                    orc_philox4x32_10(ctr, key, w);
+                }
+                x = w[g & 3];
+            }
+            uint64_t p = (uint64_t)x * (uint32_t)n;
+            u = (int)(p >> 32);
+            x = (uint32_t)p;
+            if (n == SF_LO[g]) {
+                uint64_t N = 1;
+                for (int m = SF_LO[g]; m <= SF_HI[g]; ++m) N *= (uint64_t)m;
+                if (x < (uint32_t)((((uint64_t)1) << 32) % N)) vd |= g < 4 ? 1 : 2;   /* stage A1 : A2 */
+            }
+        }
+        if (u < r) {
+            --r;
+            int suit, rank;
+            if (i < 16) { int h = 15 - i; suit = h / 4; rank = 9 + h % 4; }
+            else { int l = 35 - (i - 16); suit = l / 9; rank = l % 9; }
+            hand |= 1ull << (16 * suit + rank);
+        }
+    }
+    *voided = vd;
+    return hand;
+}
+/* Full seat-first deal: primary seat P from stage A, the other 39 cards by the
+ * fixed-hand dealer on Philox stream 3.  Return: bit 0 = void in A1, bit 1 = void in A2, bit 2 = void in B. */
+ORC_API int orc_gpu_deal_seatfirst(uint64_t seed, uint64_t index, int primary, uint64_t *lo_plane, uint64_t *hi_plane)
+{
+    int va = 0;
+    uint64_t fixed[4] = {0, 0, 0, 0};
+    fixed[primary] = orc_gpu_seatfirst_hand(seed, index, &va);
+    int vb = gpu_deal_fixed_stream(seed, index, fixed, 3, lo_plane, hi_plane);
+    return va | (vb << 2);
+}
+ORC_API void orc_gpu_deal_seatfirst_batch(uint64_t seed, uint64_t first, uint64_t n, int primary, uint64_t *rec, uint8_t *flags)
+{
+    for (uint64_t i = 0; i < n; ++i)
+        flags[i] = (uint8_t)orc_gpu_deal_seatfirst(seed, first + i, primary, &rec[2 * i], &rec[2 * i + 1]);
+}
+
 ORC_API void orc_gpu_deal_fixed_batch(uint64_t seed, uint64_t first, uint64_t n, const uint64_t fixed[4],
                                       uint64_t *rec, uint8_t *voided)
 {

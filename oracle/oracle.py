@@ -113,6 +113,8 @@ def lib():
     L.orc_gpu_deal_batch.restype = None
     L.orc_gpu_deal_fixed_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64 * 4, C.c_void_p, C.c_void_p]
     L.orc_gpu_deal_fixed_batch.restype = None
+    L.orc_gpu_deal_seatfirst_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_gpu_deal_seatfirst_batch.restype = None
     L.orc_ref_run.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.orc_ref_run.restype = C.c_uint64
     L.orc_build_batch.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p]
@@ -221,6 +223,15 @@ def gpu_deal_fixed_batch(seed: int, first: int, n: int, fixed):
     void = np.empty(n, dtype=np.uint8)
     lib().orc_gpu_deal_fixed_batch(seed, first, n, (C.c_uint64 * 4)(*[int(f) for f in fixed]), rec.ctypes.data, void.ctypes.data)
     return rec, void
+
+
+def gpu_deal_seatfirst_batch(seed: int, first: int, n: int, primary: int):
+    """CPU mirror of the seat-first sampler: (records, flags); flags bit0 / bit1 / bit2 = a Lemire check failed in
+    stage A1 / A2 / B."""
+    rec = np.empty((n, 2), dtype=np.uint64)
+    flags = np.empty(n, dtype=np.uint8)
+    lib().orc_gpu_deal_seatfirst_batch(seed, first, n, primary, rec.ctypes.data, flags.ctypes.data)
+    return rec, flags
 
 
 def mask52_to_lanes64(m52: np.ndarray) -> np.ndarray:

@@ -130,6 +130,7 @@ def test_multi_seat_constraint_accept_flags(engine):
     ref = (op[:, 0] == -1) & (op[:, 1] == -1) & (op[:, 2] == 2) & (op[:, 3] == -1) & (resp == 6)
     assert np.array_equal(acc.astype(bool), ref)
     assert 200 < ref.sum() < 900                         # p ~ 1.26e-3
+    cons.set_mode(1)
     got, tal, _ = engine.sample(cons, n_raw=400_000, seed=31)
     assert np.array_equal(sort_records(got), sort_records(rec[ref]))
 

@@ -79,17 +79,62 @@ def test_accept_flags_1nt_south(engine):
     assert 0.03 < acc.mean() < 0.046
 
 
-def test_constrained_sampler_equals_filtered_stream(engine):
-    """rejection sampling = filtering the raw stream: same accepted set"""
+def mirror_stream(cons, seed, first, n):
+    """CPU mirror of the raw stream the sampler draws for `cons` (after its first sampling call):
+    (records, void_a, void_b)"""
+    if cons is not None and cons.mode == 2:
+        rec, fl = O.gpu_deal_seatfirst_batch(seed, first, n, cons.primary)
+        return rec, (fl & 3) != 0, (fl & 4) != 0
+    rec, void = O.gpu_deal_batch(seed, first, n)
+    return rec, void.astype(bool), np.zeros(n, dtype=bool)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_constrained_sampler_equals_filtered_stream(engine, mode):
+    """rejection sampling = filtering the raw stream: same accepted set, in both dealing modes"""
     rule = bidding.openings.form((1, "NT"))
-    cons = Constraints(None, [None, None, rule, None])
+    cons = Constraints(None, [None, None, rule, None]).set_mode(mode)
     n = 300_000
     got, tal, _ = engine.sample(cons, n_raw=n, seed=SEED, first_index=1000)
-    ref, void = O.gpu_deal_batch(SEED, 1000, n)
-    ref = ref[void == 0]
+    assert cons.mode == mode and cons.primary == 2
+    ref, va, vb = mirror_stream(cons, SEED, 1000, n)
     acc, _ = engine.filter(ref, cons, None, want_features=False)
-    assert tal["accepted"] == int(acc.sum()) == got.shape[0]
-    assert np.array_equal(sort_records(got), sort_records(ref[acc == 1]))
+    keep = (acc == 1) & ~va & ~vb
+    assert tal["raw"] == n
+    assert tal["accepted"] == int(keep.sum()) == got.shape[0]
+    assert np.array_equal(sort_records(got), sort_records(ref[keep]))
+    # voided = indices discarded by a Lemire check in a stage that was actually executed
+    if mode == 1:
+        assert tal["voided"] == int(va.sum())
+    else:
+        _, fl = O.gpu_deal_seatfirst_batch(SEED, 1000, n, 2)
+        f = O.features_batch(seat_masks(ref)[:, 2])
+        pass_a1 = (f[:, 8] >= 15) & (f[:, 8] <= 17)                 # stage A1 tests HCP (and suit HCP) only
+        v1, v2, v3 = (fl & 1) != 0, (fl & 2) != 0, (fl & 4) != 0
+        expect = v1.sum() + (~v1 & pass_a1 & v2).sum() + (~v1 & ~v2 & (acc == 1) & v3).sum()
+        assert tal["voided"] == int(expect)      # this rule is exactly its ranges: passing stage A2 == accepted
+
+
+def test_auto_mode_picks_by_pass_rate(engine):
+    tight = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    loose = Constraints([None, seat_spec(hcp=(0, 20)), None, None])
+    engine.sample(tight, n_raw=1000, cap=0)
+    engine.sample(loose, n_raw=1000, cap=0)
+    assert (tight.mode, tight.primary) == (2, 2)
+    assert (loose.mode, loose.primary) == (1, 1)
+
+
+def test_seat_first_multi_seat_and_programs(engine):
+    """seat-first with rule programs on every seat (C3-style), against the CPU mirror + filter"""
+    p = bidding.openings.passes()
+    cons = Constraints(None, [p, p, bidding.openings.chooses((1, "NT")), p]).set_mode(2)
+    n = 400_000
+    got, tal, _ = engine.sample(cons, n_raw=n, seed=21)
+    ref, va, vb = mirror_stream(cons, 21, 0, n)
+    acc, _ = engine.filter(ref, cons, None, want_features=False)
+    keep = (acc == 1) & ~va & ~vb
+    assert np.array_equal(sort_records(got), sort_records(ref[keep]))
+    assert 0.012 < keep.mean() < 0.020                      # P-P-1NT-P: 0.01605
 
 
 def test_tallies_match_features(engine):
@@ -192,6 +237,7 @@ def test_c2_acceptance_rate_exact(engine):
     rule = bidding.openings.form((1, "NT"))
     cons = Constraints(None, [None, None, rule, None])
     n = 50_000_000
+    cons.set_mode(1)                      # full deal: every void index is seen, so raw - voided is exact
     _, tal, _ = engine.sample(cons, n_raw=n, seed=99, cap=0)
     valid = tal["raw"] - tal["voided"]
     p = 24235203726 / 635013559600
@@ -202,3 +248,40 @@ def test_c2_acceptance_rate_exact(engine):
     obs = tal["hcp"][2][15:18]
     assert obs.sum() == tal["accepted"]
     assert _chi2_p(obs, exp) > 1e-3
+
+
+def test_c2_acceptance_rate_exact_seat_first(engine):
+    """same exact acceptance in seat-first mode; the survival factors of the Lemire checks are
+    computed exactly from the digit schedules"""
+    from math import prod
+    rule = bidding.openings.form((1, "NT"))
+    cons = Constraints(None, [None, None, rule, None]).set_mode(2)
+    n = 50_000_000
+    _, tal, _ = engine.sample(cons, n_raw=n, seed=123, cap=0)
+    hi = [52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9]
+    lo = [49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2]
+    surv_a = prod(1 - ((1 << 32) % prod(range(l, h + 1))) / 2 ** 32 for h, l in zip(hi, lo))
+    surv_b = prod(1 - ((1 << 32) % prod(m for m in range(39 - 4 * w - 3, 39 - 4 * w + 1) if m >= 2)) / 2 ** 32
+                  for w in range(10))
+    p = 24235203726 / 635013559600 * surv_a * surv_b
+    sigma = (n * p * (1 - p)) ** 0.5
+    assert abs(tal["accepted"] - n * p) < 4 * sigma
+    split = np.array([9820068156, 8126568540, 6288567030], float)
+    obs = tal["hcp"][2][15:18]
+    assert obs.sum() == tal["accepted"]
+    assert _chi2_p(obs, split / split.sum() * tal["accepted"]) > 1e-3
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_chi_square_seat_first_other_seats(engine, seed):
+    """seat-first deals: given South's 1NT hand the other three hands must be uniform -- their HCP
+    sums to 40 - South's and their suit lengths follow the exact hypergeometric marginals; here:
+    the three seats are exchangeable (pairwise chi-square homogeneity of HCP and shape tallies)."""
+    rule = bidding.openings.form((1, "NT"))
+    cons = Constraints(None, [None, None, rule, None]).set_mode(2)
+    _, tal, _ = engine.sample(cons, n_raw=100_000_000, seed=seed, cap=0)
+    from scipy.stats import chi2_contingency
+    for key in ("hcp", "shape"):
+        table = np.stack([tal[key][0], tal[key][1], tal[key][3]])
+        table = table[:, table.sum(axis=0) >= 15]
+        assert chi2_contingency(table)[1] > 1e-3

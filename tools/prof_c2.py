@@ -14,7 +14,9 @@ elif cfg == "c3":
     cons = Constraints(None, [f"(and {p} T)", p, bidding.openings.chooses((1, "NT")), p])
 else:
     cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+if len(sys.argv) > 3 and cons is not None:
+    cons.set_mode(int(sys.argv[3]))
 for i in range(3):
-    rec, tal, st = eng.sample(cons, n_raw=n, first_index=i << 40, cap=n if cfg == "c1" else n // 16)
+    rec, tal, st = eng.sample(cons, n_raw=n, first_index=i << 40, cap=0)
     print(cfg, "raw", tal["raw"], "acc", tal["accepted"], "ms", round(st.kernel_ms, 3),
-          "deals/s %.3e" % (tal["raw"] / st.kernel_ms * 1e3))
+          "deals/s %.3e" % (tal["raw"] / st.kernel_ms * 1e3), "mode", cons.mode if cons else 1)
