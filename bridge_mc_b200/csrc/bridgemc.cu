@@ -84,7 +84,7 @@ __device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0
 
 // Stage B: full test of every constrained seat, tallies, compacted store.
 __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
-                                        const uint8_t *shape_lut, unsigned lane, unsigned long long &n_acc)
+                                        const uint8_t *shape_lut, unsigned lane)
 {
     bool ok = active;
     Feat f[4];
@@ -109,7 +109,6 @@ __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, b
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&a.tallies[2], (unsigned long long)cnt);      // accepted (also the slot cursor)
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    n_acc += lane == 0 ? cnt : 0;
     if (ok) {
         const unsigned long long slot = base + __popc(bal & ((1u << lane) - 1u));
         if (a.records != nullptr && slot < a.cap) a.records[slot] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
@@ -132,13 +131,13 @@ __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, b
 }
 
 // block-level flush of the per-warp shared histograms into bmc_tallies (u64 atomics)
-__device__ __forceinline__ void flush_hist(const SampleArgs &a, const uint32_t *s_hist)
+__device__ __forceinline__ void flush_hist(const SampleArgs &a, const uint32_t *s_hist, int copies = WARPS_PER_BLOCK)
 {
     if (!a.tally_mask) return;
     for (int i = threadIdx.x; i < SH_WORDS; i += THREADS) {
         uint32_t v = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS_PER_BLOCK; ++w) v += s_hist[w * SH_WORDS + i];
+        for (int w = 0; w < copies; ++w) v += s_hist[w * SH_WORDS + i];
         if (v == 0u) continue;
         int word;                                                                    // padded shared layout -> bmc_tallies words
         if (i < SH_LEN) word = 4 + i;                                                // hcp[4][40]
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
     uint32_t *hist = s_hist[warp];
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    unsigned long long n_raw = 0, n_void = 0, n_acc = 0;
+    uint32_t n_raw = 0, n_void = 0;           // per thread: at most `iters` each
     unsigned q_head = 0, q_tail = 0;          // warp-uniform
 
     for (uint32_t it = 0; it < a.iters; ++it) {
@@ -199,11 +198,11 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
                     q_head += 32u;
                     __syncwarp();
                     Planes p2 = {r.x, r.y, r.z, r.w};
-                    stage_b(a, p2, true, hist, s_shape, lane, n_acc);
+                    stage_b(a, p2, true, hist, s_shape, lane);
                 }
             }
         } else {
-            stage_b(a, pl, ok, hist, s_shape, lane, n_acc);
+            stage_b(a, pl, ok, hist, s_shape, lane);
         }
     }
     if (HAS_CONS) {
@@ -211,19 +210,22 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
         if (left) {
             const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
             Planes p2 = {r.x, r.y, r.z, r.w};
-            stage_b(a, p2, lane < left, hist, s_shape, lane, n_acc);
+            stage_b(a, p2, lane < left, hist, s_shape, lane);
         }
     }
 
     // flush counters and histograms
+    {
+        unsigned long long r64 = n_raw, v64 = n_void;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_raw += __shfl_xor_sync(0xFFFFFFFFu, n_raw, o);
-        n_void += __shfl_xor_sync(0xFFFFFFFFu, n_void, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&a.tallies[0], n_raw);
-        if (n_void) atomicAdd(&a.tallies[1], n_void);
+        for (int o = 16; o > 0; o >>= 1) {
+            r64 += __shfl_xor_sync(0xFFFFFFFFu, r64, o);
+            v64 += __shfl_xor_sync(0xFFFFFFFFu, v64, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.tallies[0], r64);
+            if (v64) atomicAdd(&a.tallies[1], v64);
+        }
     }
     __syncthreads();
     flush_hist(a, &s_hist[0][0]);
@@ -233,26 +235,30 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
 // K1b: seat-first sampler (seatfirst.cuh): stages A1 -> A2 -> B with two per-warp
 // compaction queues, so each stage runs on full warps.
 // ---------------------------------------------------------------------------
+#ifndef SF_MIN_BLOCKS
+#define SF_MIN_BLOCKS 6
+#endif
+constexpr int SF_HIST_COPIES = 2;
 __constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
                                         thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
 
-__global__ void __launch_bounds__(THREADS, 5) sample_seatfirst_kernel(const __grid_constant__ SampleArgs a)
+__global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kernel(const __grid_constant__ SampleArgs a)
 {
-    __shared__ uint32_t s_hist[WARPS_PER_BLOCK][SH_WORDS];
+    __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];   // stage B is rare here: few copies suffice
     __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (H | r << 16, idx_lo, idx_hi, -)
     __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, idx_lo, idx_hi)
     __shared__ uint8_t s_shape[14 * 14 * 14];
 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < WARPS_PER_BLOCK * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < SF_HIST_COPIES * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
     for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
     __syncthreads();
 
-    uint32_t *hist = s_hist[warp];
+    uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
     uint4 *q1 = s_q1[warp], *q2 = s_q2[warp];
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    unsigned long long n_raw = 0, n_void = 0, n_acc = 0;
+    uint32_t n_raw = 0, n_void = 0;                  // per thread: at most `iters` each
     unsigned h1 = 0, t1 = 0, h2 = 0, t2 = 0;         // queue cursors, warp-uniform
     const uint32_t P = a.cons.primary;
     const SeatC &c = a.cons.seat[P];
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 5) sample_seatfirst_kernel(const __gr
         const bool voided = deal_fixed_core(a.key, STREAM_SEATFIRST_B, 39u, a.sf_q0, r.x & xl, r.y & xl, r.x & xh, r.y & xh,
                                             ~r.x & 0x1FFF1FFFu, ~r.y & 0x1FFF1FFFu, c_thresh39, r.z, r.w, pl);
         n_void += (active && voided) ? 1u : 0u;
-        stage_b(a, pl, active && !voided, hist, s_shape, lane, n_acc);
+        stage_b(a, pl, active && !voided, hist, s_shape, lane);
     };
     // ---- stage A2 on up to 32 queued honour sets ---------------------------------------
     auto run_a2 = [&](unsigned count) {
@@ -315,17 +321,20 @@ __global__ void __launch_bounds__(THREADS, 5) sample_seatfirst_kernel(const __gr
     if (t1 - h1) run_a2(t1 - h1);
     if (t2 - h2) run_b(t2 - h2);
 
+    {
+        unsigned long long r64 = n_raw, v64 = n_void;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_raw += __shfl_xor_sync(0xFFFFFFFFu, n_raw, o);
-        n_void += __shfl_xor_sync(0xFFFFFFFFu, n_void, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&a.tallies[0], n_raw);
-        if (n_void) atomicAdd(&a.tallies[1], n_void);
+        for (int o = 16; o > 0; o >>= 1) {
+            r64 += __shfl_xor_sync(0xFFFFFFFFu, r64, o);
+            v64 += __shfl_xor_sync(0xFFFFFFFFu, v64, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.tallies[0], r64);
+            if (v64) atomicAdd(&a.tallies[1], v64);
+        }
     }
     __syncthreads();
-    flush_hist(a, &s_hist[0][0]);
+    flush_hist(a, &s_hist[0][0], SF_HIST_COPIES);
 }
 
 // ---------------------------------------------------------------------------
