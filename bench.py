@@ -33,11 +33,16 @@ UNIT = "deals/s"
 P_BOX = 29286389970 / 635013559600          # exact acceptance of the range ("box") form the reference can generate
 P_1NT = 24235203726 / 635013559600          # exact acceptance of test-bid (1 NT)
 SEED = 0x6272696467656D63
-# Algorithmic integer work of one raw deal on the hot kernel (DESIGN.md "W_int"):
-# 3 Philox4x32-10 (120) + 51 mixed-radix digits (51) + owner bookkeeping 51x4 (204)
-# + 8 plane extractions (48) + 12 Lemire checks (12) + stage-A features/range test (60) + loop/queue (25)
-W_INT = 520
-W_INT_SURVEY = 1400                          # SURVEY 8d's budget for the naive per-card algorithm
+# Algorithmic integer work of one raw deal on the hot kernel for this workload ("W_int"):
+# thread-level integer instructions per raw deal, counted by ncu on the committed kernels
+# (sass__thread_inst_executed / raw deals of the launch):
+#   seat-first sampler  312  profiles/r01_prof_c2_sf1.txt   (per warp-iteration of 32 deals: stage A1 177,
+#                            A2 67, B 91, other 15 warp instructions)
+#   full-deal sampler   649  profiles/r01_c2_sample_kernel_v1.txt
+W_INT_BY_MODE = {1: 649, 2: 312}
+KERNEL_BY_MODE = {1: "sample_kernel<true,false>", 2: "sample_seatfirst_kernel"}
+W_INT_SURVEY = 1400                          # SURVEY 8d's budget for a naive per-card full deal
+INT_PEAK_NOMINAL = 148 * 128 * 1.965e9       # SMs x INT32 lanes x max SM clock
 
 
 def parse():
@@ -51,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-deals", type=int, default=1500, help="reference arm: builds per thread per step")
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 full deal, 2 seat-first (bmc_constraints_set_mode)")
     return ap.parse_args()
 
 
@@ -194,6 +200,8 @@ def run_gpu(args):
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    if args.mode:
+        cons.set_mode(args.mode)
     target = int(args.accept)
     cap = target + target // 16 + (1 << 20)
     records = torch.empty((cap, 2), dtype=torch.int64, device=dev)
@@ -286,6 +294,7 @@ def run_gpu(args):
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         avg_launch_ms = kernel_ms / max(1, launches)
         deals_per_launch = raw / max(1, launches)
+        W_INT = W_INT_BY_MODE[cons.mode]
         achieved = deals_per_launch * W_INT / (avg_launch_ms * 1e-3) / 1e12
         peak = int_peak / 1e12
         line = {
@@ -295,14 +304,20 @@ def run_gpu(args):
             "config": {"workload": f"C2: South test-bid (1 NT) rejection sampling, {target:.0e} accepted deals per GPU per step "
                                    f"(waves of {args.wave} Philox indices)",
                        "l2": "no input buffers (counter-based RNG); 1.6 GB of records written per step >> 126 MB L2",
+                       "e2e_note": "e2e copies all 1.6 GB of accepted records to pinned host memory every step (overlapped "
+                                   "with the next wave); it is PCIe-bound, the device number is integer-issue bound",
                        "parallelism": f"dp{world}: disjoint Philox index ranges + NCCL all-reduce of the {_lib.TALLY_WORDS * 8} B tally buffer"},
             "accepted_per_s": acc_all / (ms * 1e-3),
             "acceptance": acc_all / max(1.0, raw_all),
-            "roofline": {"bound": "int32-issue", "kernel": "sample_kernel<true>", "achieved": achieved, "peak": peak,
+            "sampler_mode": {1: "full-deal", 2: "seat-first"}[cons.mode],
+            "roofline": {"bound": "int32-issue", "kernel": KERNEL_BY_MODE[cons.mode], "achieved": achieved, "peak": peak,
                          "unit": "Tint-op/s", "frac": achieved / peak if peak else None, "traffic": None,
                          "w_int_per_deal": W_INT, "avg_launch_ms": avg_launch_ms, "deals_per_launch": deals_per_launch,
-                         "peak_source": "bmc_int_peak microbenchmark on this GPU (IMAD+LOP3 chains, burst)",
-                         "frac_at_survey_w_int_1400": deals_per_launch * W_INT_SURVEY / (avg_launch_ms * 1e-3) / int_peak,
+                         "peak_source": "bmc_int_peak microbenchmark on this GPU (IMAD+LOP3 chains, burst); "
+                                        "MEASURED_PEAKS.json has no integer figure",
+                         "peak_nominal": INT_PEAK_NOMINAL / 1e12, "frac_of_nominal": achieved * 1e12 / INT_PEAK_NOMINAL,
+                         "w_int_source": "ncu sass__thread_inst_executed / raw deals, profiles/ (see bench.py W_INT_BY_MODE)",
+                         "full_deal_equivalent_at_survey_w_int_1400": deals_per_launch * W_INT_SURVEY / (avg_launch_ms * 1e-3) / int_peak,
                          "hbm": {"achieved": (acc / max(1, launches)) * 16 / (avg_launch_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "peak_source": hbm_src,
                                  "frac": (acc / max(1, launches)) * 16 / (avg_launch_ms * 1e-3) / 1e9 / hbm_peak}},
@@ -314,7 +329,8 @@ def run_gpu(args):
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            n = 600
+            _, _, dt0 = cpu_reference_rate(200, threads)                 # size the bounded sample for ~12 s of CPU work
+            n = max(600, int(200 * 12.0 / max(dt0, 1e-3)))
             b, p, dt = cpu_reference_rate(n, threads)
             line["cpu_baseline"] = {
                 "value": p / P_1NT, "unit": UNIT, "cores": threads, "kind": "port",

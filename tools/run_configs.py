@@ -1,0 +1,121 @@
+"""Run the five BASELINE.json configurations and print one JSON object per config.
+
+    python tools/run_configs.py [c1 c2 c3 c4 c5] [--scale 1.0]
+    python -m torch.distributed.run --nproc-per-node N ... tools/run_configs.py c3 c5
+
+Under torchrun the raw index range of a config is split evenly over the ranks
+(disjoint Philox ranges) and the tallies are all-reduced with NCCL; rank 0 prints.
+Times are CUDA-event times of the sampling kernels, max over ranks.
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from bridge_mc_b200 import _lib, bidding, compscore
+from bridge_mc_b200.engine import Constraints, Engine, tallies_from_words
+
+SEED = 0x6272696467656D63
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    scale = 1.0
+    for i, a in enumerate(sys.argv):
+        if a == "--scale":
+            scale = float(sys.argv[i + 1])
+    which = [a for a in args if a.startswith("c")] or ["c1", "c2", "c3", "c4", "c5"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    tallies = torch.zeros(_lib.TALLY_WORDS, dtype=torch.int64, device=dev)
+
+    def run(name, cons, n_raw, note, tally_mask=7, records=False):
+        per = n_raw // world
+        first = rank * per
+        cap = 0
+        rec = None
+        if records:
+            cap = per
+            rec = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+        tallies.zero_()
+        eng.sample_dev(cons, rec.data_ptr() if records else 0, cap, tallies.data_ptr(), n_raw=min(per, 1 << 20),
+                       first_index=1 << 50, seed=SEED, tally_mask=tally_mask)            # warm-up + calibration
+        tallies.zero_()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st = eng.sample_dev(cons, rec.data_ptr() if records else 0, cap, tallies.data_ptr(), n_raw=per, first_index=first,
+                            seed=SEED, tally_mask=tally_mask)
+        if world > 1:
+            dist.all_reduce(tallies)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([st.kernel_ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        t = tallies_from_words(tallies.cpu().numpy().view(np.uint64))
+        if rank == 0:
+            print(json.dumps({
+                "config": name, "note": note, "n_gpus": world, "mode": (cons.mode if cons else 1),
+                "raw": t["raw"], "voided": t["voided"], "accepted": t["accepted"], "acceptance": t["accepted"] / max(1, t["raw"]),
+                "kernel_ms": float(ms[0]), "wall_ms_incl_allreduce": float(ms[1]),
+                "raw_deals_per_s": t["raw"] / (float(ms[0]) * 1e-3), "accepted_per_s": t["accepted"] / (float(ms[0]) * 1e-3),
+                "hcp_seat2_15_17": [int(x) for x in t["hcp"][2][15:18]],
+                "tally_checksum": int(t["hcp"].sum() + 3 * t["len"].sum() + 7 * t["shape"].sum()) % (1 << 61),
+            }))
+        return t
+
+    p = bidding.openings.passes()
+    if "c1" in which:
+        run("C1", None, 1_000_000, "1M unconstrained deals, HCP + suit-length histograms, records stored", tally_mask=3,
+            records=True)
+        run("C1-1e9", None, int(1e9 * scale), "unconstrained, all tallies, no records")
+    if "c2" in which:
+        cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+        run("C2", cons, int(2_684_354_560 * scale), "South test-bid (1 NT); 10 x 2^28 raw = 1.02e8 accepted; records stored",
+            records=True)
+    if "c3" in which:
+        nt = bidding.nt_responses(1)
+        cons = Constraints(None, [f"(and {p} {nt.chooses((3, 'NT'))})", p, bidding.openings.chooses((1, "NT")), p])
+        run("C3", cons, int(1e10 * scale), "N E W pass, S chooses 1NT, N answers 3NT over (nt-responses 1)")
+    if "c5" in which:
+        nt2 = bidding.nt_responses(2)
+        cons = Constraints(None, [nt2.chooses((6, "NT")), None, bidding.openings.chooses((2, "NT")), None])
+        run("C5", cons, int(1e11 * scale), "S chooses 2NT, N answers 6NT over (nt-responses 2)")
+    if "c4" in which and rank == 0:
+        cs = [compscore.Contract(t).c_struct() for t in ("1NTS", "3NTS", "4HS", "4SS")] * 2
+        vul = [0, 0, 0, 0, 1, 1, 1, 1]
+        pairs = [0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6, 7]
+        n = int(1e8 * scale)
+        eng.score_tally(cs, vul, pairs, n=1 << 20, seed=SEED)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th, ih, tab = eng.score_tally(cs, vul, pairs, n=n, seed=SEED)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"config": "C4", "note": "base-score / match-points tallies, 8 contract x vulnerability rows, 6 IMP pairs, "
+                          "tricks = Philox stream 1 (the reference's trick source is out of scope)", "n_gpus": 1,
+                          "deals": n, "wall_ms": dt * 1e3, "deals_per_s": n / dt, "contract_evals_per_s": 8 * n / dt,
+                          "tricks_hist_row0": [int(x) for x in th[0]], "score_table_3NTS_vul": [int(x) for x in tab[5]]}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
