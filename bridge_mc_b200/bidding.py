@@ -51,7 +51,7 @@ class RuleTable:
     """An ordered alist of (bid, form-text) rows; `bid` is a tuple like (1, 'NT')."""
 
     def __init__(self, rows):
-        self.rows = [(tuple(b), f) for b, f in rows]
+        self.rows = [((tuple(b) if b is not None else None), f) for b, f in rows]     # bid None: a NIL row, never matches
         self._scheme = None
 
     def bids(self):
@@ -68,7 +68,7 @@ class RuleTable:
         return self.rows[self.index(bid)][1]
 
     def sexpr(self) -> str:
-        return "(" + " ".join(f"(({b[0]} {b[1]}) . {f})" for b, f in self.rows) + ")"
+        return "(" + " ".join("nil" if b is None else f"(({b[0]} {b[1]}) . {f})" for b, f in self.rows) + ")"
 
     def scheme(self) -> Scheme:
         if self._scheme is None:
@@ -255,3 +255,222 @@ def test_bid(bid, hand: Hand, scheme: RuleTable = None, engine: Engine | None = 
     if k == -2:
         raise BidError("illegal function call while evaluating the rule")
     return k == 0
+
+
+# ---- second-round bid generators (bidding.cl:263-413), host-side list manipulation ----------
+# Rule forms here are S-expression lists as read by sexp.read (symbols upper-cased); the
+# generated tables are turned into RuleTable text for the GPU like every other scheme.
+class LispCallError(RuntimeError):
+    """The reference would signal a wrong-number-of-arguments error here."""
+
+
+def _sym(x):
+    return sexp.Sym(str(x).upper())
+
+
+def _form(x):
+    return sexp.read(x) if isinstance(x, str) else x
+
+
+def matchlist(pattern, mapper, lst, args=()):
+    """bridge.cl:183-190: match `pattern` against the head of `lst`; `_` captures."""
+    if not pattern:
+        return mapper(*reversed(args))
+    if not lst:
+        return None
+    if pattern[0] == "_":
+        return matchlist(pattern[1:], mapper, lst[1:], (lst[0],) + tuple(args))
+    if pattern[0] == lst[0]:
+        return matchlist(pattern[1:], mapper, lst[1:], args)
+    return None
+
+
+def match_smaller(sym, lst):
+    """bidding.cl:263-265"""
+    r = matchlist([_sym("<"), sym, "_"], lambda v: v - 1, lst)
+    return r if r is not None else matchlist([_sym("<="), sym, "_"], lambda v: v, lst)
+
+
+def match_greater(sym, lst):
+    """bidding.cl:267-269"""
+    r = matchlist([_sym(">"), sym, "_"], lambda v: v + 1, lst)
+    return r if r is not None else matchlist([_sym(">="), sym, "_"], lambda v: v, lst)
+
+
+def match_longer(lst):
+    """bidding.cl:271-275.  The `(> _ _)` branch applies a one-argument lambda* to two
+    arguments in the reference, i.e. it signals an error; only `(>= suit n)` works."""
+    def bad(*_):
+        raise LispCallError("match-longer: lambda* applied to 2 arguments (bidding.cl:272)")
+    ans = matchlist([_sym(">"), "_", "_"], bad, lst)
+    if ans is None:
+        ans = matchlist([_sym(">="), "_", "_"], lambda *x: list(x), lst)
+    if ans and ans[0] in ("C", "D", "H", "S"):
+        return ans
+    return None
+
+
+def and_condition(conds):
+    """bidding.cl:277-279"""
+    sig = [c for c in conds if c is not None]
+    if len(sig) > 1:
+        return [_sym("AND")] + sig
+    return sig[0] if sig else None
+
+
+def combine_shapes(a, b):
+    """bidding.cl:281-297: add the bounds two partners have shown."""
+    a, b = _form(a), _form(b)
+
+    def self(base, other):
+        if not base:
+            return None
+        if base[0] == "AND":
+            if other[0] == "AND":
+                out = []
+                for conj in base[1:]:
+                    op, measure, val = (list(conj) + [None, None, None])[:3]
+                    extractor = match_greater if op in (">", ">=") else match_smaller
+                    otherval = next((v for v in (extractor(measure, o) for o in other[1:]) if v is not None), None)
+                    out.append([op, measure, val + otherval] if otherval is not None else None)
+                return and_condition(out)
+            return self(base, [_sym("AND"), other])
+        return self([_sym("AND"), base], other)
+
+    return self(a, b)
+
+
+def _find_in_bid(meaning, fn):
+    """bidding.cl:314-318: only AND/OR meanings work (anything else applies fn to the spread form)"""
+    if meaning and meaning[0] in ("AND", "OR"):
+        return next((v for v in (fn(m) for m in meaning[1:]) if v is not None), None)
+    raise LispCallError("find-in-bid: function applied to a spread form (bidding.cl:318)")
+
+
+def _filter_bid(meaning, fn):
+    """bidding.cl:320-324"""
+    if meaning and meaning[0] in ("AND", "OR"):
+        return [v for v in (fn(m) for m in meaning[1:]) if v is not None]
+    raise LispCallError("filter-bid: function applied to a spread form (bidding.cl:324)")
+
+
+def max_hcp(meaning):
+    return _find_in_bid(_form(meaning), lambda m: match_smaller(_sym("HCP"), m))
+
+
+def min_hcp(meaning):
+    return _find_in_bid(_form(meaning), lambda m: match_greater(_sym("HCP"), m))
+
+
+def longers(meaning):
+    return _filter_bid(_form(meaning), match_longer)
+
+
+def _suitno_star(suit):
+    """bidding.cl:345-348: nil / NT rank above spades"""
+    if suit is None or str(suit).upper() == "NT":
+        return 4
+    return SUITS.index(str(suit).upper())
+
+
+def game_in(suit):
+    """bidding.cl:335-338"""
+    if suit is None:
+        return (3, "NT")
+    return (5, str(suit)) if str(suit) in ("C", "D") else (4, str(suit))
+
+
+def invite_in(suit):
+    """bidding.cl:340-343"""
+    if suit is None:
+        return (2, "NT")
+    return (4, str(suit)) if str(suit) in ("C", "D") else (3, str(suit))
+
+
+def closest_bid(suit, base):
+    """bidding.cl:350-353"""
+    base = _norm_bid(base)
+    return (base[0], str(suit)) if SUITS.index(str(suit)) > _suitno_star(base[1]) else (base[0] + 1, str(suit))
+
+
+def jump_bid(suit, base, levels):
+    """bidding.cl:355-358"""
+    base = _norm_bid(base)
+    extra = 0 if SUITS.index(str(suit)) > _suitno_star(base[1]) else 1
+    return (base[0] + levels + extra, str(suit))
+
+
+def bid_jump(base, bid):
+    """bidding.cl:360-363"""
+    base, bid = _norm_bid(base), _norm_bid(bid)
+    return (bid[0] - base[0]) + (0 if _suitno_star(bid[1]) > _suitno_star(base[1]) else -1)
+
+
+def suit_biddef(bid, lo_hcp, hi_hcp, min_losers, max_losers, length):
+    """bidding.cl:371-377 -> (bid, form text)"""
+    suit = bid[1]
+    return (bid, _and(_or(_cmp(">=", "hcp", lo_hcp), _cmp("<=", "loosers", max_losers)), _cmp("<=", "hcp", hi_hcp),
+                      _cmp(">=", "loosers", min_losers), _cmp(">=", suit, 8 - length)))
+
+
+def further_bid(known_shape, partner_shape, last_bid) -> RuleTable:
+    """bidding.cl:379-413: rebids after partner showed `partner_shape`; NIL rows of the
+    reference's table (rows that never match) are kept as such."""
+    last = _norm_bid(last_bid)
+    my_min = min_hcp(known_shape)
+    p_min = min_hcp(partner_shape)
+    rows = []
+    third = p_min // 3
+    for suit, length in longers(partner_shape):
+        suit = str(suit)
+        minor = suit in ("C", "D")
+        game_hcp, game_losers = (27, 2) if minor else (25, 3)
+        inv_jump = bid_jump(last, invite_in(suit))
+        rows.append(suit_biddef(game_in(suit), game_hcp - p_min, 29 - p_min, 2 + third, game_losers + third, length))
+        rows.append(suit_biddef(invite_in(suit), game_hcp - p_min - 2, game_hcp - p_min, 3 + third, game_losers + 1 + third,
+                                length) if inv_jump > 1 else (None, "nil"))
+        rows.append(suit_biddef(jump_bid(suit, last, 0 if inv_jump == 0 else 1), my_min + 3, game_hcp - p_min - 1, 3 + third,
+                                game_losers + 1 + third, length) if inv_jump >= 0 else (None, "nil"))
+        rows.append(suit_biddef((5, suit), 31 - p_min - 2, 30 - p_min, 1 + third, 1 + third, length))
+        if suit != last[1] or last[0] == 1:
+            rows.append((closest_bid(suit, last), _cmp(">=", suit, 8 - length)))
+    return RuleTable(rows)
+
+
+class Bidding:
+    """bidding.cl:457-480 class `bidding`: finds the first seat (0..3) that has an opening bid,
+    rolls the deal so that the opener sits first and selects the response scheme."""
+
+    def __init__(self, deal, engine: Engine | None = None):
+        self.deal = list(deal)
+        self.bids = None
+        self.meanings = None
+        self.bid_scheme = openings
+        self._engine = engine
+
+    def next(self):
+        feats = assess_hands(self.deal, self.bid_scheme, self._engine)
+        found = None
+        for seat in range(4):
+            k = int(feats[seat]["bid"])
+            if k == -2:
+                raise BidError("illegal function call while evaluating the rule table")
+            if k >= 0:
+                found = (seat, self.bid_scheme.rows[k][0])
+                break
+        if not found:
+            return None
+        passes, bid = found
+        from .deal import roll
+        self.deal = roll(-passes, self.deal)
+        self.bids = [bid]
+        self.meanings = [(bid, self.bid_scheme.form(bid)), None]
+        if bid == (2, "C"):
+            self.bid_scheme = two_c_responses
+        elif bid[1] == "NT":
+            self.bid_scheme = nt_responses(bid[0])
+        elif bid[0] == 1:
+            self.bid_scheme = basic_responses(bid)
+        else:
+            self.bid_scheme = None             # the reference's cond has no live clause here ((nil ...), bidding.cl:479)
+        return self.bids

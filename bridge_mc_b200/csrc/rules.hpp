@@ -479,6 +479,11 @@ inline SchemeRows compile_scheme(const std::string &text)
     if (!table.is_list()) throw RuleError("rule table must be a list of (bid . form) rows");
     RuleCompiler rc;
     for (const Sx &row : table.items) {
+        if (row.kind == Sx::NIL) {               // a NIL row (further-bid emits them): never matches
+            out.bids.push_back("NIL");
+            out.progs.push_back({enc(OP_FALSE), enc(OP_END)});
+            continue;
+        }
         if (!row.is_list() || row.items.empty()) throw RuleError("bad rule row: " + sx_to_string(row));
         // (bid . form): after reading, a proper-list form is spliced: (bid op args...)
         Sx form;

@@ -33,6 +33,8 @@ def _scheme(form):
         return bidding.two_c_responses
     if s[0] == "BASIC-RESPONSES":
         return bidding.basic_responses(bid_of(s[1]))
+    if s[0] == "FURTHER-BID":
+        return bidding.further_bid(unquote(s[1]), unquote(s[2]), bid_of(s[3]))
     return None
 
 
@@ -48,11 +50,23 @@ def test_bidding_kats_on_gpu(engine):
         n += 1
     for where, form, exp in load_kats("CHOOSE-BID"):
         table = _scheme(form)
-        if table is None:
-            continue                 # further-bid tables (bidding.cl:379-413) are out of scope
+        assert table is not None, where
         assert bidding.choose_bid(hand_of(form[1]), table, engine) == bid_of(exp), where
         n += 1
-    assert n == 6 + 28 + 10 + 13 + 8 + 7
+    assert n == 6 + 28 + 10 + 13 + 8 + 7 + 6
+
+
+def test_bidding_class_next(engine):
+    """bidding.cl:482-487: the reference's own example deal; North (seat 0) opens 1D"""
+    deal = [str2hand("N: ♠ Q1097 ♥ 3 ♦ KJ1063 ♣ K102"), str2hand("E: ♠ 62 ♥ AJ75 ♦ A942 ♣ 987"),
+            str2hand("S: ♠ AKJ5 ♥ K1064 ♦ Q87 ♣ A6"), str2hand("W: ♠ 843 ♥ Q982 ♦ 5 ♣ QJ543")]
+    b = bidding.Bidding(deal, engine)
+    bids = b.next()
+    ref = [O.choose_bid(0, h) for h in deal]
+    first = next(i for i, k in enumerate(ref) if k >= 0)
+    assert bids == [bidding.openings.rows[ref[first]][0]]
+    assert b.deal[0] == deal[first]
+    assert b.bid_scheme is not None and b.bid_scheme.bids()
 
 
 def test_assess_hand_matches_oracle(engine):

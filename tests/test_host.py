@@ -235,3 +235,33 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "oracle" not in text.lower().replace("oracle/bmc_oracle.c", "").replace("orc_gpu_deal", "") \
                     or f in ("deal.cuh",), f
+
+
+# ---- second-round generators (bidding.cl:263-413) -------------------------------------------
+def test_bid_jump_and_combine_shapes_kats():
+    n = 0
+    for where, form, exp in load_kats("BID-JUMP"):
+        assert bidding.bid_jump(bid_of(form[1]), bid_of(form[2])) == exp, where
+        n += 1
+    for where, form, exp in load_kats("COMBINE-SHAPES"):
+        assert bidding.combine_shapes(unquote(form[1]), unquote(form[2])) == exp, where
+        n += 1
+    assert n == 5 + 3
+    assert bidding.min_hcp("(and (>= hcp 12) (<= hcp 22) (>= D 5))") == 12
+    assert bidding.max_hcp("(and (>= hcp 12) (< hcp 23))") == 22
+    assert bidding.longers("(and (>= hcp 6) (>= S 4) (>= H 5))") == [["S", 4], ["H", 5]]
+    with pytest.raises(bidding.LispCallError):
+        bidding.min_hcp("(>= hcp 6)")                    # bidding.cl:318 applies fn to the spread form
+    with pytest.raises(bidding.LispCallError):
+        bidding.longers("(and (> S 4))")                 # bidding.cl:272 lambda* arity
+    assert bidding.game_in(None) == (3, "NT") and bidding.game_in("D") == (5, "D") and bidding.invite_in("S") == (3, "S")
+    assert bidding.closest_bid("S", (1, "H")) == (1, "S") and bidding.closest_bid("C", (1, "H")) == (2, "C")
+    assert bidding.jump_bid("S", (1, "S"), 1) == (3, "S")
+
+
+def test_further_bid_table_shape():
+    t = bidding.further_bid("(and (>= hcp 12) (<= hcp 22) (>= D 5))", "(and (>= hcp 6) (>= S 4))", (1, "S"))
+    assert t.bids() == [(4, "S"), None, (3, "S"), (5, "S"), (2, "S")]        # NIL row kept: invite-jump = 1
+    t2 = bidding.further_bid("(and (>= hcp 6) (>= S 4))", "(and (>= hcp 12) (<= hcp 22) (>= D 5) (>= S 4))", (2, "S"))
+    assert t2.bids() == [(5, "D"), None, (4, "D"), (5, "D"), (3, "D"), (4, "S"), None, (3, "S"), (5, "S")]
+    assert t2.scheme().size == len(t2.rows)
