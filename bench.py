@@ -182,18 +182,15 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from bridge_mc_b200 import bidding, _lib
+    from bridge_mc_b200 import dist as bdist
     from bridge_mc_b200.engine import Constraints, Engine, tallies_from_words
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = bdist.env_rank_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libbridgemc has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    bdist.init_process_group("nccl", dev)
 
     eng = Engine(local)
     stream = torch.cuda.Stream(dev)               # events must be recorded on the stream the kernels run on
@@ -209,11 +206,10 @@ def run_gpu(args):
 
     def step(i):
         tallies.zero_()
-        first = (i * world + rank) << 40          # disjoint Philox counter ranges per (step, rank)
+        first = bdist.step_first_index(i, rank, world)      # disjoint Philox counter ranges per (step, rank)
         st = eng.sample_dev(cons, records.data_ptr(), cap, tallies.data_ptr(), n_accept=target, wave=args.wave,
                             first_index=first, seed=SEED)
-        if world > 1:
-            dist.all_reduce(tallies)              # the only exchange: a 4.5 KB histogram buffer over NVLink
+        bdist.allreduce_tallies(tallies)                    # the only exchange: a 4.4 KB histogram buffer over NVLink
         return st
 
     def barrier():
@@ -263,14 +259,15 @@ def run_gpu(args):
         if hp:
             host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint64)), shape=(cap, 2))
             k = max(1, min(args.steps, 2))
-            eng.sample(cons, n_accept=target, wave=args.wave, first_index=(99 * world + rank) << 40, seed=SEED,
+            eng.sample(cons, n_accept=target, wave=args.wave, first_index=bdist.step_first_index(99, rank, world), seed=SEED,
                        cap=cap, records=host)        # warm the path once
             barrier()
             t0 = time.perf_counter()
             e_raw = e_stored = 0
             for i in range(k):
                 _, t_h, st = eng.sample(cons, n_accept=target, wave=args.wave,
-                                        first_index=((100 + i) * world + rank) << 40, seed=SEED, cap=cap, records=host)
+                                        first_index=bdist.step_first_index(100 + i, rank, world), seed=SEED, cap=cap,
+                                        records=host)
                 e_raw += st.raw; e_stored += st.stored
             barrier()
             dt = time.perf_counter() - t0

@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 from bridge_mc_b200 import _lib, bidding, compscore
+from bridge_mc_b200 import dist as bdist
 from bridge_mc_b200.engine import Constraints, Engine, tallies_from_words
 
 SEED = 0x6272696467656D63
@@ -46,8 +47,7 @@ def main():
     tallies = torch.zeros(_lib.TALLY_WORDS, dtype=torch.int64, device=dev)
 
     def run(name, cons, n_raw, note, tally_mask=7, records=False):
-        per = n_raw // world
-        first = rank * per
+        first, per = bdist.rank_range(0, n_raw, rank, world)
         cap = 0
         rec = None
         if records:
@@ -63,8 +63,7 @@ def main():
         t0 = time.perf_counter()
         st = eng.sample_dev(cons, rec.data_ptr() if records else 0, cap, tallies.data_ptr(), n_raw=per, first_index=first,
                             seed=SEED, tally_mask=tally_mask)
-        if world > 1:
-            dist.all_reduce(tallies)
+        bdist.allreduce_tallies(tallies)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = torch.tensor([st.kernel_ms, wall * 1e3], dtype=torch.float64, device=dev)
