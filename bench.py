@@ -48,7 +48,7 @@ INT_PEAK_NOMINAL = 148 * 128 * 1.965e9       # SMs x INT32 lanes x max SM clock
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="bridgemc")
     ap.add_argument("--accept", type=float, default=1e8, help="accepted deals per step per GPU")
@@ -130,48 +130,69 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed region (NVML in a
+    thread, every 10 ms; the sampling calls release the GIL while the bench thread sits in ctypes)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+               "hw_power_brake": 0x80}
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remapping: resolve through the CUDA device's UUID / PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self._h = h
+                        break
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                          # pragma: no cover
+            self._err = repr(e)
+            self._h = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                mw = nv.nvmlDeviceGetPowerUsage(self._h)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((mhz, mw / 1000.0, rs))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        if self._h is None:
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self._h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable: {getattr(self, '_err', '')}"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        sm = sorted(x[0] for x in self.samples)
+        bits = 0
+        for x in self.samples:
+            bits |= x[2]
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.max_mhz),
+                "power_w_max": max((x[1] for x in self.samples), default=None), "samples": len(self.samples),
+                "reasons": sorted(k for k, v in self.REASONS.items() if bits & v)}
 
 
 # ---------------------------------------------------------------------------

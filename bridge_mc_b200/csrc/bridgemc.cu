@@ -553,6 +553,14 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t seed, uint32_t *
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
 }
 
+// Publishes the four leading counters into host-mapped pinned memory, so the per-wave
+// read-back does not occupy the device->host copy engine (which streams the records).
+__global__ void publish_counters_kernel(const unsigned long long *__restrict__ tallies, volatile unsigned long long *mapped)
+{
+    if (threadIdx.x < 4) mapped[threadIdx.x] = tallies[threadIdx.x];
+    __threadfence_system();
+}
+
 // ---------------------------------------------------------------------------
 // host objects
 // ---------------------------------------------------------------------------
@@ -560,6 +568,8 @@ struct bmc_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    unsigned long long *h_head = nullptr;        // pinned + mapped: per-wave read-back of the four counters
+    unsigned long long *h_head_dev = nullptr;    // its device alias
     bmc_record *d_rec = nullptr;                 // grow-only record scratch of the host-buffer API
     uint64_t rec_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -654,6 +664,8 @@ int bmc_init(int device, bmc_ctx **out)
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaMalloc(&c->d_tallies, sizeof(bmc_tallies)));
+    CUDA_TRY(cudaHostAlloc(&c->h_head, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void **)&c->h_head_dev, c->h_head, 0));
     if (device < 16) {
         cudaError_t le = cudaSuccess;
         std::call_once(g_lut_once[device], [&] { le = cudaMemcpyToSymbol(c_shape_lut, g_shape_lut, sizeof g_shape_lut); });
@@ -668,6 +680,14 @@ int bmc_init(int device, bmc_ctx **out)
     c->blocks_free = c->sms * (occ > 0 ? occ : 1);
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_seatfirst_kernel, THREADS, 0));
     c->blocks_sf = c->sms * (occ > 0 ? occ : 1);
+    if (const char *e = getenv("BMC_BLOCKS_PER_SM")) {        // tuning knob: cap the resident blocks per SM
+        const int cap = atoi(e);
+        if (cap > 0) {
+            if (c->blocks_sf > c->sms * cap) c->blocks_sf = c->sms * cap;
+            if (c->blocks_cons > c->sms * cap) c->blocks_cons = c->sms * cap;
+            if (c->blocks_free > c->sms * cap) c->blocks_free = c->sms * cap;
+        }
+    }
     *out = c;
     return BMC_OK;
 }
@@ -678,6 +698,7 @@ void bmc_shutdown(bmc_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tallies);
+    cudaFreeHost(c->h_head);
     if (c->d_rec) cudaFree(c->d_rec);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->ev0);
@@ -1008,10 +1029,21 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     const uint64_t max_launch = stepwise ? wave : (1ull << 36);   // 2^36: keeps a warp's iteration counter in 32 bits
     uint32_t waves = 0;
     const uint64_t launches0 = ctx->launches;
-    unsigned long long head[4] = {0, 0, 0, 0}, start_acc = 0;
+    // The counters are read back through host-mapped memory written by a tiny kernel: a memcpy on
+    // the compute stream would queue on the same device->host copy engine as the record copies of
+    // copy_stream and was measured to serialise the waves behind them.
+    volatile unsigned long long *head = ctx->h_head;
+    unsigned long long start_acc = 0;
+    head[0] = head[1] = head[2] = head[3] = 0;
+    auto read_head = [&]() -> cudaError_t {
+        publish_counters_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)tallies_dev, ctx->h_head_dev);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(ctx->stream);
+    };
     if (stepwise) {
-        CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(read_head());
         start_acc = head[2];
     }
     uint64_t copied = start_acc < cap ? start_acc : cap;
@@ -1029,8 +1061,7 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         ++waves;
         if (!stepwise) continue;
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(read_head());
         {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);       // device time of this wave's kernel only
@@ -1039,17 +1070,26 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         if (stream_copy) {
             const uint64_t upto = head[2] < cap ? head[2] : cap;
             if (upto > copied) {
+                auto tc0 = std::chrono::steady_clock::now();
                 CUDA_TRY(cudaMemcpyAsync(host_out + copied, (const bmc_record *)records_dev + copied,
                                          (upto - copied) * sizeof(bmc_record), cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (getenv("BMC_DEBUG"))
+                    fprintf(stderr, "[bmc] wave %u: copy of %.1f MB enqueued in %.3f ms at t=%.2f ms (kernel_ms so far %.2f)\n", waves,
+                            (upto - copied) * 16e-6,
+                            std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - tc0).count(),
+                            std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(), kernel_ms);
                 copied = upto;
             }
         }
         if (n_accept_target && head[2] - start_acc >= n_accept_target) break;
     }
     if (!stepwise) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(head, tallies_dev, sizeof head, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(read_head());
+    if (getenv("BMC_DEBUG"))
+        fprintf(stderr, "[bmc] compute done at t=%.2f ms\n", std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (stream_copy) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    if (getenv("BMC_DEBUG"))
+        fprintf(stderr, "[bmc] copies done at t=%.2f ms\n", std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (stats) {
         float ms = kernel_ms;
         if (!stepwise) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
