@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
     unsigned h1 = 0, t1 = 0, h2 = 0, t2 = 0;         // queue cursors, warp-uniform
     const uint32_t P = a.cons.primary;
     const SeatC &c = a.cons.seat[P];
-    const uint32_t A2h = (c.A[2] & 0xFFu) | 0x80808000u, B2h = c.B[2] & 0xFFu;   // HCP byte only
 
     // ---- stage B on up to 32 queued hands ------------------------------------------
     auto run_b = [&](unsigned count) {
@@ -298,17 +297,24 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
         }
     };
 
-    for (uint32_t it = 0; it < a.iters; ++it) {
-        const unsigned long long off = ((unsigned long long)it * total_warps + gwarp) * 32ull + lane;
-        const bool valid = off < a.n;
+    // Only the last warp-iteration can hold indices past the end: the others skip the bounds test.
+    const unsigned long long stride = total_warps * 32ull;
+    unsigned long long off = gwarp * 32ull + lane;
+    const uint32_t full_iters = (uint32_t)(a.n / stride);
+    const uint32_t hcp_lo = c.hcp_lo_span & 0xFFu, hcp_span = c.hcp_lo_span >> 8;
+    const bool need_power = (c.need & 2u) != 0u;
+    for (uint32_t it = 0; it < a.iters; ++it, off += stride) {
+        const bool valid = it < full_iters || off < a.n;
         const unsigned long long idx = a.first + off;
         SeatFirstState s;
         const uint32_t H = sf_honours(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), s);
-        n_raw += valid ? 1u : 0u;
         n_void += (valid && s.voided) ? 1u : 0u;
-        uint32_t Pw, hcp;
-        honour_features(H, Pw, hcp);
-        const bool ok = valid && !s.voided && in_ranges(Pw, c.A[1], c.B[1]) && in_ranges(hcp, A2h, B2h);
+        bool ok = valid && !s.voided && (honour_hcp(H) - hcp_lo) <= hcp_span;
+        if (need_power) {
+            uint32_t Pw, hcp;
+            honour_features(H, Pw, hcp);
+            ok = ok && in_ranges(Pw, c.A[1], c.B[1]);
+        }
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
             if (ok) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] =
@@ -320,6 +326,7 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
     }
     if (t1 - h1) run_a2(t1 - h1);
     if (t2 - h2) run_b(t2 - h2);
+    n_raw = full_iters + ((a.iters > full_iters && (unsigned long long)full_iters * stride + gwarp * 32ull + lane < a.n) ? 1u : 0u);
 
     {
         unsigned long long r64 = n_raw, v64 = n_void;
@@ -754,6 +761,8 @@ static void ranges_to_seatc(const SeatRanges &r, SeatC &c)
     lo[F_BAL] = r.bal_req == 1 ? 1 : 0;
     hi[F_BAL] = r.bal_req == 2 ? 0 : 1;
     c.need = 0;
+    for (int s = 0; s < 4; ++s) if (r.lo[F_CP + s] > 0 || r.hi[F_CP + s] < 10) c.need |= 2u;
+    c.hcp_lo_span = (uint32_t)r.lo[F_HCP] | ((uint32_t)(hi[F_HCP] - r.lo[F_HCP]) << 8);
     for (int w = 0; w < 3; ++w) {
         uint32_t A = 0, B = 0;
         for (int b = 0; b < 4; ++b) {

@@ -22,8 +22,8 @@ struct SeatC {
     uint32_t A[3], B[3];
     uint32_t prog;          // offset of the seat's program in the code buffer, 0xFFFFFFFF = none
     uint32_t active;        // 0: seat unconstrained
-    uint32_t need;          // bit0 lens ranged, bit1 power ranged, bit2 f2 ranged (incl. losers/balanced)
-    uint32_t pad;
+    uint32_t need;          // bit 1: some suit-HCP (power) range is not the default
+    uint32_t hcp_lo_span;   // hcp_lo | (hcp_hi - hcp_lo) << 8: one subtract + compare in the seat-first stage A1
 };
 
 __device__ __forceinline__ Feat hand_features(uint32_t m0, uint32_t m1)

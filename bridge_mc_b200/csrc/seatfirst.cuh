@@ -98,6 +98,12 @@ __device__ __forceinline__ uint32_t sf_honours(const PhiloxKey &key, uint32_t id
     return s.mask & 0xFFFFu;
 }
 
+// HCP alone from the honour mask: J1 Q2 K3 A4 over the four suit nibbles (XU pipe is idle here).
+__device__ __forceinline__ uint32_t honour_hcp(uint32_t H)
+{
+    return __popc(H & 0x1111u) + 2u * __popc(H & 0x2222u) + 3u * __popc(H & 0x4444u) + 4u * __popc(H & 0x8888u);
+}
+
 // Features available after A1: power bytes (c d h s) and HCP.
 __device__ __forceinline__ void honour_features(uint32_t H, uint32_t &P, uint32_t &hcp)
 {
