@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
 #define SF_MIN_BLOCKS 6
 #endif
 constexpr int SF_HIST_COPIES = 2;
+#ifndef SF_ILP
+#define SF_ILP 1
+#endif
 __constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
                                         thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
 
@@ -297,36 +300,50 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
         }
     };
 
-    // Only the last warp-iteration can hold indices past the end: the others skip the bounds test.
-    const unsigned long long stride = total_warps * 32ull;
-    unsigned long long off = gwarp * 32ull + lane;
+    // Each thread draws SF_ILP independent deals per iteration (two interleaved dependency chains keep
+    // both integer pipes fed).  Only the last iteration can hold indices past the end.
+    const unsigned long long stride = total_warps * (32ull * SF_ILP);
+    unsigned long long off = gwarp * (32ull * SF_ILP) + lane;
     const uint32_t full_iters = (uint32_t)(a.n / stride);
     const uint32_t hcp_lo = c.hcp_lo_span & 0xFFu, hcp_span = c.hcp_lo_span >> 8;
     const bool need_power = (c.need & 2u) != 0u;
     for (uint32_t it = 0; it < a.iters; ++it, off += stride) {
-        const bool valid = it < full_iters || off < a.n;
-        const unsigned long long idx = a.first + off;
-        SeatFirstState s;
-        const uint32_t H = sf_honours(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), s);
-        n_void += (valid && s.voided) ? 1u : 0u;
-        bool ok = valid && !s.voided && (honour_hcp(H) - hcp_lo) <= hcp_span;
-        if (need_power) {
-            uint32_t Pw, hcp;
-            honour_features(H, Pw, hcp);
-            ok = ok && in_ranges(Pw, c.A[1], c.B[1]);
+        SeatFirstState s[SF_ILP];
+        uint32_t H[SF_ILP];
+        bool ok[SF_ILP];
+#pragma unroll
+        for (int j = 0; j < SF_ILP; ++j) {
+            const unsigned long long idx = a.first + off + 32ull * j;
+            H[j] = sf_honours(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), s[j]);
         }
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-        if (bal) {
-            if (ok) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] =
-                        make_uint4(H | ((uint32_t)s.r << 16), (uint32_t)idx, (uint32_t)(idx >> 32), 0u);
-            t1 += __popc(bal);
-            __syncwarp();
-            if (t1 - h1 >= 32u) run_a2(32u);
+#pragma unroll
+        for (int j = 0; j < SF_ILP; ++j) {
+            const bool valid = it < full_iters || off + 32ull * j < a.n;
+            n_raw += (it >= full_iters && valid) ? 1u : 0u;
+            n_void += (valid && s[j].voided) ? 1u : 0u;
+            ok[j] = valid && !s[j].voided && (honour_hcp(H[j]) - hcp_lo) <= hcp_span;
+            if (need_power) {
+                uint32_t Pw, hcp;
+                honour_features(H[j], Pw, hcp);
+                ok[j] = ok[j] && in_ranges(Pw, c.A[1], c.B[1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SF_ILP; ++j) {
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok[j]);
+            if (bal) {
+                const unsigned long long idx = a.first + off + 32ull * j;
+                if (ok[j]) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] =
+                               make_uint4(H[j] | ((uint32_t)s[j].r << 16), (uint32_t)idx, (uint32_t)(idx >> 32), 0u);
+                t1 += __popc(bal);
+                __syncwarp();
+                if (t1 - h1 >= 32u) run_a2(32u);
+            }
         }
     }
     if (t1 - h1) run_a2(t1 - h1);
     if (t2 - h2) run_b(t2 - h2);
-    n_raw = full_iters + ((a.iters > full_iters && (unsigned long long)full_iters * stride + gwarp * 32ull + lane < a.n) ? 1u : 0u);
+    n_raw += full_iters * SF_ILP;
 
     {
         unsigned long long r64 = n_raw, v64 = n_void;
@@ -974,10 +991,11 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
         a.pad = 0;
     }
     int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
-    const uint64_t per_iter = (uint64_t)blocks * THREADS;
-    if (n < per_iter) blocks = (int)((n + THREADS - 1) / THREADS);
+    const uint64_t per_thread = seatfirst ? SF_ILP : 1;           // raw deals per thread per iteration
+    const uint64_t per_iter = (uint64_t)blocks * THREADS * per_thread;
+    if (n < per_iter) blocks = (int)((n + THREADS * per_thread - 1) / (THREADS * per_thread));
     if (blocks < 1) blocks = 1;
-    const uint64_t chunk = (uint64_t)blocks * THREADS;
+    const uint64_t chunk = (uint64_t)blocks * THREADS * per_thread;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
     if (seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a);
     else if (fix) {
