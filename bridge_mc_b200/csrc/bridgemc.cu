@@ -50,7 +50,9 @@ struct ConsDev {
     SeatC seat[4];
     uint32_t n_active;       // number of constrained seats
     uint32_t primary;        // seat tested in stage A
-    uint32_t pad[2];
+    uint32_t b1_mask;        // seat-first mode: seats fully tested right after the deal is completed (0xF: all of them);
+                             // the others are tested after one more compaction
+    uint32_t pad;
     const uint32_t *code;    // device pointer, programs of all seats
 };
 
@@ -82,27 +84,33 @@ __device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0
     m1 = (pl.lo1 ^ xl) & (pl.hi1 ^ xh) & 0x1FFF1FFFu;
 }
 
-// Stage B: full test of every constrained seat, tallies, compacted store.
-__device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
-                                        const uint8_t *shape_lut, unsigned lane)
+// Full test (ranges + rule program) of the constrained seats selected by `mask`.
+__device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl, uint32_t mask)
 {
-    bool ok = active;
-    Feat f[4];
+    bool ok = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        uint32_t m0, m1;
-        seat_words(pl, k, m0, m1);
-        f[k] = hand_features(m0, m1);
         const SeatC &c = a.cons.seat[k];
-        if (c.active) {
-            ok = ok && seat_ranges_ok(c, f[k]);
+        if (c.active && ((mask >> k) & 1u)) {
+            uint32_t m0, m1;
+            seat_words(pl, k, m0, m1);
+            const Feat f = hand_features(m0, m1);
+            ok = ok && seat_ranges_ok(c, f);
             if (c.prog != 0xFFFFFFFFu) {
                 bool err = false;
-                const bool v = run_program(a.cons.code + c.prog, f[k], err);
+                const bool v = run_program(a.cons.code + c.prog, f, err);
                 ok = ok && v && !err;
             }
         }
     }
+    return ok;
+}
+
+// Stage B: full test of the seats in `mask`, then tallies and the compacted store.
+__device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
+                                        const uint8_t *shape_lut, unsigned lane, uint32_t mask = 0xFu)
+{
+    const bool ok = seats_pass(a, pl, mask) && active;
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
     if (bal == 0u) return;
     const unsigned cnt = __popc(bal);
@@ -115,13 +123,16 @@ __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, b
         if (a.tally_mask) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (a.tally_mask & BMC_TALLY_HCP) atomicAdd(&hist[SH_HCP + k * 40 + (f[k].f2 & 0xFFu)], 1u);
+                uint32_t m0, m1;
+                seat_words(pl, k, m0, m1);
+                const Feat f = hand_features(m0, m1);
+                if (a.tally_mask & BMC_TALLY_HCP) atomicAdd(&hist[SH_HCP + k * 40 + (f.f2 & 0xFFu)], 1u);
                 if (a.tally_mask & BMC_TALLY_LEN) {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) atomicAdd(&hist[SH_LEN + (k * 4 + s) * 16 + ((f[k].f0 >> (8 * s)) & 0xFFu)], 1u);
+                    for (int s = 0; s < 4; ++s) atomicAdd(&hist[SH_LEN + (k * 4 + s) * 16 + ((f.f0 >> (8 * s)) & 0xFFu)], 1u);
                 }
                 if (a.tally_mask & BMC_TALLY_SHAPE) {
-                    const uint32_t L = f[k].f0;
+                    const uint32_t L = f.f0;
                     const uint32_t cls = shape_lut[(L & 0xFFu) * 196u + ((L >> 8) & 0xFFu) * 14u + ((L >> 16) & 0xFFu)];
                     atomicAdd(&hist[SH_SHAPE + k * 40 + cls], 1u);
                 }
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
     __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];   // stage B is rare here: few copies suffice
     __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (H | r << 16, idx_lo, idx_hi, -)
     __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, idx_lo, idx_hi)
+    __shared__ uint4 s_q3[WARPS_PER_BLOCK][QCAP];     // B1 survivors: complete deals (planes)
     __shared__ uint8_t s_shape[14 * 14 * 14];
 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -258,7 +270,9 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
     __syncthreads();
 
     uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
-    uint4 *q1 = s_q1[warp], *q2 = s_q2[warp];
+    uint4 *q1 = s_q1[warp], *q2 = s_q2[warp], *q3 = s_q3[warp];
+    unsigned h3 = 0, t3 = 0;
+    const uint32_t b1_mask = a.cons.b1_mask & 0xFu, b2_mask = ~b1_mask & 0xFu;
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
     uint32_t n_raw = 0, n_void = 0;                  // per thread: at most `iters` each
@@ -277,7 +291,26 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
         const bool voided = deal_fixed_core(a.key, STREAM_SEATFIRST_B, 39u, a.sf_q0, r.x & xl, r.y & xl, r.x & xh, r.y & xh,
                                             ~r.x & 0x1FFF1FFFu, ~r.y & 0x1FFF1FFFu, c_thresh39, r.z, r.w, pl);
         n_void += (active && voided) ? 1u : 0u;
-        stage_b(a, pl, active && !voided, hist, s_shape, lane);
+        if (b2_mask == 0u) {
+            stage_b(a, pl, active && !voided, hist, s_shape, lane);
+            return;
+        }
+        // B1: the primary seat's program and the most selective other seat; survivors are compacted
+        // once more so that the remaining (expensive, rarely needed) programs run on full warps
+        const bool ok = seats_pass(a, pl, b1_mask) && active && !voided;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+        if (bal) {
+            if (ok) q3[(t3 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+            t3 += __popc(bal);
+            __syncwarp();
+            if (t3 - h3 >= 32u) {
+                const uint4 r3 = q3[(h3 + lane) % QCAP];
+                h3 += 32u;
+                __syncwarp();
+                const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
+                stage_b(a, p3, true, hist, s_shape, lane, b2_mask);
+            }
+        }
     };
     // ---- stage A2 on up to 32 queued honour sets ---------------------------------------
     auto run_a2 = [&](unsigned count) {
@@ -343,6 +376,11 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
     }
     if (t1 - h1) run_a2(t1 - h1);
     if (t2 - h2) run_b(t2 - h2);
+    if (t3 - h3) {
+        const uint4 r3 = q3[(h3 + lane) % QCAP];
+        const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
+        stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, b2_mask);
+    }
     n_raw += full_iters * SF_ILP;
 
     {
@@ -478,12 +516,35 @@ __device__ __forceinline__ int imps_dev(int diff, bool &bad)
 
 struct ContractTable { bmc_contract c[8]; uint8_t vul[8]; uint8_t pairs[16]; uint32_t n, n_pairs; };
 
+// HBM-bound (1 B in, 4 B out per element): each thread scores four consecutive elements
+// (one 32-bit load, one 128-bit store); the contract index advances without a division.
 __global__ void __launch_bounds__(256) score_kernel(const bmc_contract *__restrict__ contracts, const uint8_t *__restrict__ vul,
                                                     uint32_t nc, const uint8_t *__restrict__ tricks, unsigned long long total,
                                                     int32_t *__restrict__ scores)
 {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    __shared__ bmc_contract s_c[64];
+    __shared__ uint8_t s_v[64];
+    const bool cached = nc <= 64u;
+    if (cached)
+        for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) { s_c[i] = contracts[i]; s_v[i] = vul ? vul[i] : 0; }
+    __syncthreads();
+    const unsigned long long quads = total >> 2, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+        const uint32_t t4 = reinterpret_cast<const uint32_t *>(tricks)[q];
+        uint32_t c = (uint32_t)((q << 2) % nc);
+        int4 out;
+        int *o = &out.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bmc_contract ct = cached ? s_c[c] : contracts[c];
+            const int v = cached ? s_v[c] : (vul ? vul[c] : 0);
+            o[k] = base_score_dev(ct, (int)((t4 >> (8 * k)) & 0xFFu), v);
+            c = c + 1u == nc ? 0u : c + 1u;
+        }
+        reinterpret_cast<int4 *>(scores)[q] = out;
+    }
+    // tail (total not a multiple of 4)
+    for (unsigned long long i = (quads << 2) + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const uint32_t c = (uint32_t)(i % nc);
         scores[i] = base_score_dev(contracts[c], tricks[i], vul ? vul[c] : 0);
     }
@@ -869,6 +930,7 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     for (int s = 0; s < 4; ++s)
         if (total_lo[F_C + s] > 13) return fail(BMC_E_BAD_RANGE, "Can't infer correct limit!: minimum suit lengths exceed 13");
     c->dev.primary = 0;
+    c->dev.b1_mask = 0xFu;
     double best = 2.0;
     for (int k = 0; k < 4; ++k)
         if (c->dev.seat[k].active && selectivity[k] < best) { best = selectivity[k]; c->dev.primary = (uint32_t)k; }
@@ -1025,29 +1087,53 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     bool seatfirst = false;
     if (has_cons && !fix) {
         bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
+        // pass rate of `cal` over 2^16 raw deals of the full-deal kernel (a fixed calibration seed:
+        // the outcome, hence the mode and the stream behind each index, is reproducible)
+        auto pass_rate = [&](const ConsDev &cal, double &rate) -> int {
+            unsigned long long *d_cal = nullptr, h4[4] = {0, 0, 0, 0};
+            CUDA_TRY(cudaMalloc(&d_cal, sizeof(bmc_tallies)));
+            cudaMemsetAsync(d_cal, 0, sizeof(bmc_tallies), ctx->stream);
+            int rc = launch_wave(ctx, cal, true, nullptr, false, 0x63616C6962726174ull, 0, 1u << 16, 0, nullptr, 0, d_cal);
+            cudaError_t e = cudaMemcpyAsync(h4, d_cal, sizeof h4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_cal);
+            if (rc) return rc;
+            if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("calibration: ") + cudaGetErrorString(e));
+            rate = (double)h4[2] / (double)(h4[0] ? h4[0] : 1);
+            return BMC_OK;
+        };
         if (cc->resolved == 0) {
             if (cc->mode != 0) cc->resolved = cc->mode;
             else {
-                // calibrate once: pass rate of the primary seat's RANGES alone over 2^16 raw deals
+                // the primary seat's RANGES alone: seat-first pays off when most deals die on them
                 ConsDev cal = dev;
                 for (int k = 0; k < 4; ++k) {
                     cal.seat[k].prog = 0xFFFFFFFFu;
                     if ((uint32_t)k != dev.primary) cal.seat[k].active = 0;
                 }
-                unsigned long long *d_cal = nullptr, h4[4] = {0, 0, 0, 0};
-                CUDA_TRY(cudaMalloc(&d_cal, sizeof(bmc_tallies)));
-                cudaMemsetAsync(d_cal, 0, sizeof(bmc_tallies), ctx->stream);
-                int rc = launch_wave(ctx, cal, true, nullptr, false, 0x63616C6962726174ull, 0, 1u << 16, 0, nullptr, 0, d_cal);
-                cudaError_t e = cudaMemcpyAsync(h4, d_cal, sizeof h4, cudaMemcpyDeviceToHost, ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-                cudaFree(d_cal);
+                int rc = pass_rate(cal, cc->stage_a_pass);
                 if (rc) return rc;
-                if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("calibration: ") + cudaGetErrorString(e));
-                cc->stage_a_pass = (double)h4[2] / (double)(h4[0] ? h4[0] : 1);
-                // seat-first pays off when most deals die on the primary seat's ranges
                 cc->resolved = cc->stage_a_pass < 0.30 ? 2 : 1;
             }
+            cc->dev.b1_mask = 0xFu;
+            if (cc->resolved == 2 && dev.n_active >= 3) {
+                // choose the most selective other seat to be tested together with the primary seat
+                double best = 2.0;
+                int second = -1;
+                for (int k = 0; k < 4; ++k) {
+                    if ((uint32_t)k == dev.primary || !dev.seat[k].active) continue;
+                    ConsDev cal = dev;
+                    for (int j = 0; j < 4; ++j) if (j != k) cal.seat[j].active = 0;
+                    cal.primary = (uint32_t)k;
+                    double r = 1.0;
+                    int rc = pass_rate(cal, r);
+                    if (rc) return rc;
+                    if (r < best) { best = r; second = k; }
+                }
+                if (second >= 0) cc->dev.b1_mask = (1u << dev.primary) | (1u << second);
+            }
         }
+        dev.b1_mask = cc->dev.b1_mask;
         seatfirst = cc->resolved == 2;
     }
     const bool stream_copy = host_out && records_dev && cap;
@@ -1245,7 +1331,8 @@ int bmc_score(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulner
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, vul.data(), nc, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_t, tricks, total, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
-        const unsigned blocks = (unsigned)((total + 255) / 256 < (uint64_t)ctx->sms * 16 ? (total + 255) / 256 : (uint64_t)ctx->sms * 16);
+        const uint64_t want = (total / 4 + 255) / 256 + 1;
+        const unsigned blocks = (unsigned)(want < (uint64_t)ctx->sms * 16 ? want : (uint64_t)ctx->sms * 16);
         score_kernel<<<blocks, 256, 0, ctx->stream>>>(d_c, d_v, nc, d_t, total, d_s);
         ctx->launches++;
         e = cudaGetLastError();
