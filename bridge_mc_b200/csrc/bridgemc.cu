@@ -85,7 +85,7 @@ __device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0
 }
 
 // Full test (ranges + rule program) of the constrained seats selected by `mask`.
-__device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl, uint32_t mask)
+__device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl, uint32_t mask, uint32_t *scratch, unsigned lane)
 {
     bool ok = true;
 #pragma unroll
@@ -98,7 +98,7 @@ __device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl
             ok = ok && seat_ranges_ok(c, f);
             if (c.prog != 0xFFFFFFFFu) {
                 bool err = false;
-                const bool v = run_program(a.cons.code + c.prog, f, err);
+                const bool v = run_program(a.cons.code + c.prog, feat_store(scratch, lane, f), err);
                 ok = ok && v && !err;
             }
         }
@@ -108,9 +108,9 @@ __device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl
 
 // Stage B: full test of the seats in `mask`, then tallies and the compacted store.
 __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
-                                        const uint8_t *shape_lut, unsigned lane, uint32_t mask = 0xFu)
+                                        const uint8_t *shape_lut, unsigned lane, uint32_t *scratch, uint32_t mask = 0xFu)
 {
-    const bool ok = seats_pass(a, pl, mask) && active;
+    const bool ok = seats_pass(a, pl, mask, scratch, lane) && active;
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
     if (bal == 0u) return;
     const unsigned cnt = __popc(bal);
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
 {
     __shared__ uint32_t s_hist[WARPS_PER_BLOCK][SH_WORDS];
     __shared__ uint4 s_queue[HAS_CONS ? WARPS_PER_BLOCK : 1][QCAP];
+    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
     __shared__ uint8_t s_shape[14 * 14 * 14];
 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -209,11 +210,11 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
                     q_head += 32u;
                     __syncwarp();
                     Planes p2 = {r.x, r.y, r.z, r.w};
-                    stage_b(a, p2, true, hist, s_shape, lane);
+                    stage_b(a, p2, true, hist, s_shape, lane, s_feat[warp]);
                 }
             }
         } else {
-            stage_b(a, pl, ok, hist, s_shape, lane);
+            stage_b(a, pl, ok, hist, s_shape, lane, s_feat[warp]);
         }
     }
     if (HAS_CONS) {
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
         if (left) {
             const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
             Planes p2 = {r.x, r.y, r.z, r.w};
-            stage_b(a, p2, lane < left, hist, s_shape, lane);
+            stage_b(a, p2, lane < left, hist, s_shape, lane, s_feat[warp]);
         }
     }
 
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
     __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (H | r << 16, idx_lo, idx_hi, -)
     __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, idx_lo, idx_hi)
     __shared__ uint4 s_q3[WARPS_PER_BLOCK][QCAP];     // B1 survivors: complete deals (planes)
+    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
     __shared__ uint8_t s_shape[14 * 14 * 14];
 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -292,12 +294,12 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
                                             ~r.x & 0x1FFF1FFFu, ~r.y & 0x1FFF1FFFu, c_thresh39, r.z, r.w, pl);
         n_void += (active && voided) ? 1u : 0u;
         if (b2_mask == 0u) {
-            stage_b(a, pl, active && !voided, hist, s_shape, lane);
+            stage_b(a, pl, active && !voided, hist, s_shape, lane, s_feat[warp]);
             return;
         }
         // B1: the primary seat's program and the most selective other seat; survivors are compacted
         // once more so that the remaining (expensive, rarely needed) programs run on full warps
-        const bool ok = seats_pass(a, pl, b1_mask) && active && !voided;
+        const bool ok = seats_pass(a, pl, b1_mask, s_feat[warp], lane) && active && !voided;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
             if (ok) q3[(t3 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
                 h3 += 32u;
                 __syncwarp();
                 const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-                stage_b(a, p3, true, hist, s_shape, lane, b2_mask);
+                stage_b(a, p3, true, hist, s_shape, lane, s_feat[warp], b2_mask);
             }
         }
     };
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
     if (t3 - h3) {
         const uint4 r3 = q3[(h3 + lane) % QCAP];
         const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-        stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, b2_mask);
+        stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, s_feat[warp], b2_mask);
     }
     n_raw += full_iters * SF_ILP;
 
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(256) filter_kernel(const __grid_constant__ Con
                                                      unsigned long long n, uint8_t *__restrict__ accept,
                                                      bmc_features *__restrict__ feats)
 {
+    __shared__ uint32_t s_feat[8][FEAT_SCRATCH_WORDS];
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     uint4 r = make_uint4(0, 0, 0, 0);
@@ -425,13 +428,14 @@ __global__ void __launch_bounds__(256) filter_kernel(const __grid_constant__ Con
         uint32_t m0, m1;
         seat_words(pl, k, m0, m1);
         const Feat f = hand_features(m0, m1);
+        const uint8_t *fb = feat_store(s_feat[threadIdx.x >> 5], threadIdx.x & 31u, f);
         if (has_cons) {
             const SeatC &c = cons.seat[k];
             if (c.active) {
                 ok = ok && seat_ranges_ok(c, f);
                 if (c.prog != 0xFFFFFFFFu) {
                     bool err = false;
-                    const bool v = run_program(cons.code + c.prog, f, err);
+                    const bool v = run_program(cons.code + c.prog, fb, err);
                     ok = ok && v && !err;
                 }
             }
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(256) filter_kernel(const __grid_constant__ Con
             bool done = false;
             for (uint32_t row = 0; row < sch.n_rows; ++row) {
                 bool err = false;
-                const bool v = run_program(sch.code + __ldg(sch.row_off + row), f, err);
+                const bool v = run_program(sch.code + __ldg(sch.row_off + row), fb, err);
                 if (!done) {
                     if (err) { bid = -2; done = true; }
                     else if (v) { bid = (int)row; done = true; }
@@ -993,6 +997,7 @@ int bmc_scheme_create(const char *table, bmc_scheme **out)
             s->code.insert(s->code.end(), rows.progs[i].begin(), rows.progs[i].end());
         }
         s->bids = rows.bids;
+        s->code.push_back(enc(OP_END));          // spare word: the interpreter prefetches one word ahead
         if (s->row_off.size() > 120) return fail(BMC_E_CAPACITY, "rule table has more than 120 rows");
         *out = s.release();
     } catch (const RuleError &e) {

@@ -66,42 +66,45 @@ __device__ __forceinline__ bool seat_ranges_ok(const SeatC &c, const Feat &f)
     return in_ranges(f.f0, c.A[0], c.B[0]) && in_ranges(f.f1, c.A[1], c.B[1]) && in_ranges(f.f2, c.A[2], c.B[2]);
 }
 
-__device__ __forceinline__ uint32_t feat_get(const Feat &f, uint32_t idx)
+// Per-lane scratch for the interpreter: the eleven feature bytes of the hand under test live in
+// shared memory (12 bytes per lane, lane stride 3 words: conflict-free), so an operand fetch is
+// one LDS.U8 with a warp-uniform offset instead of a register select + shift.
+constexpr int FEAT_SCRATCH_WORDS = 32 * 3;     // per warp
+
+__device__ __forceinline__ uint8_t *feat_store(uint32_t *warp_scratch, unsigned lane, const Feat &f)
 {
-    const uint32_t w = idx < 4u ? f.f0 : (idx < 8u ? f.f1 : f.f2);
-    return (w >> ((idx & 3u) * 8u)) & 0xFFu;
+    uint32_t *p = warp_scratch + 3u * lane;
+    p[0] = f.f0; p[1] = f.f1; p[2] = f.f2;
+    return reinterpret_cast<uint8_t *>(p);
 }
 
-// Interpret one program (warp-uniform control flow; boolean stack in a register).
-// Returns the value; err is set where the reference would signal an
+// Interpret one program (warp-uniform control flow; boolean stack in one 32-bit register, depth
+// checked by the compiler).  `fb` = this lane's feature bytes (feat_store).  The next word is
+// fetched while the current one executes.  err is set where the reference would signal an
 // "illegal function call" (un-spliced rule lists, bidding.cl:249).
-__device__ __forceinline__ bool run_program(const uint32_t *__restrict__ code, const Feat &f, bool &err)
+__device__ __forceinline__ bool run_program(const uint32_t *__restrict__ code, const uint8_t *fb, bool &err)
 {
-    uint64_t st = 0;
+    uint32_t st = 0;
+    uint32_t w = __ldg(code);
     for (;;) {
-        const uint32_t w = __ldg(code++);
         const uint32_t op = w & 15u;
         if (op == OP_END) break;
-        switch (op) {
-        case OP_CMPC:
-        case OP_CMPF: {
-            const uint32_t a = feat_get(f, (w >> 8) & 15u);
-            const uint32_t b = op == OP_CMPC ? (w >> 16) & 0xFFu : feat_get(f, (w >> 12) & 15u);
+        const uint32_t next = __ldg(++code);          // every code buffer ends with a spare OP_END
+        if (op <= OP_CMPF) {                          // OP_CMPC / OP_CMPF
+            const uint32_t a = fb[(w >> 8) & 15u];
+            const uint32_t b = op == OP_CMPC ? (w >> 16) & 0xFFu : (uint32_t)fb[(w >> 12) & 15u];
             const uint32_t state = a < b ? 0u : (a == b ? 1u : 2u);
             st = (st << 1) | (((w >> 4) >> state) & 1u);
-            break;
-        }
-        case OP_AND: { const uint64_t t = st & 1u; st >>= 1; st &= ~1ull | t; break; }
-        case OP_OR:  { const uint64_t t = st & 1u; st >>= 1; st |= t; break; }
-        case OP_NOT: st ^= 1u; break;
-        case OP_TRUE: st = (st << 1) | 1u; break;
-        case OP_FALSE: st <<= 1; break;
-        case OP_ERRIF_T: err |= (st & 1u) != 0; st &= ~1ull; break;
-        case OP_ERRIF_F: err |= (st & 1u) == 0; break;
-        default: break;
-        }
+        } else if (op == OP_AND) { const uint32_t t = st & 1u; st >>= 1; st &= ~1u | t; }
+        else if (op == OP_OR) { const uint32_t t = st & 1u; st >>= 1; st |= t; }
+        else if (op == OP_NOT) st ^= 1u;
+        else if (op == OP_TRUE) st = (st << 1) | 1u;
+        else if (op == OP_FALSE) st <<= 1;
+        else if (op == OP_ERRIF_T) { err |= (st & 1u) != 0u; st &= ~1u; }
+        else if (op == OP_ERRIF_F) err |= (st & 1u) == 0u;
+        w = next;
     }
-    return (st & 1u) != 0;
+    return (st & 1u) != 0u;
 }
 
 }  // namespace bmc

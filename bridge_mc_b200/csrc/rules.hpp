@@ -167,7 +167,7 @@ public:
             code.push_back(enc(OP_ERRIF_T));
         }
         code.push_back(enc(OP_END));
-        // boolean stack lives in one 64-bit register
+        // boolean stack lives in one 32-bit register
         int depth = 0, maxd = 0;
         for (size_t i = start; i < code.size(); ++i) {
             uint32_t op = code[i] & 15u;
@@ -175,7 +175,7 @@ public:
             else if (op == OP_AND || op == OP_OR) --depth;
             if (depth > maxd) maxd = depth;
         }
-        if (maxd > 60) throw RuleError("rule nests too deeply (boolean stack > 60)");
+        if (maxd > 30) throw RuleError("rule nests too deeply (boolean stack > 30)");
         if (ranges) {
             bool ex = true;
             absorb(form, *ranges, ex);
