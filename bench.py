@@ -36,10 +36,10 @@ SEED = 0x6272696467656D63
 # Algorithmic integer work of one raw deal on the hot kernel for this workload ("W_int"):
 # thread-level integer instructions per raw deal, counted by ncu on the committed kernels
 # (sass__thread_inst_executed / raw deals of the launch):
-#   seat-first sampler  312  profiles/r01_prof_c2_sf1.txt   (per warp-iteration of 32 deals: stage A1 177,
-#                            A2 67, B 91, other 15 warp instructions)
+#   seat-first sampler  297  profiles/r01_prof_c2_seatfirst_2p28.txt  (7.96e10 thread instructions for a 2^28-deal
+#                            launch; per warp-iteration of 32 deals roughly: stage A1 160, A2 65, B 90, other 15)
 #   full-deal sampler   649  profiles/r01_c2_sample_kernel_v1.txt
-W_INT_BY_MODE = {1: 649, 2: 312}
+W_INT_BY_MODE = {1: 649, 2: 297}
 KERNEL_BY_MODE = {1: "sample_kernel<true,false>", 2: "sample_seatfirst_kernel"}
 W_INT_SURVEY = 1400                          # SURVEY 8d's budget for a naive per-card full deal
 INT_PEAK_NOMINAL = 148 * 128 * 1.965e9       # SMs x INT32 lanes x max SM clock
