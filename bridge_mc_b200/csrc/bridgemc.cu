@@ -290,8 +290,7 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
         const bool active = lane < count;
         Planes pl;
         const uint32_t xl = (P & 1u) ? 0xFFFFFFFFu : 0u, xh = (P & 2u) ? 0xFFFFFFFFu : 0u;
-        const bool voided = deal_fixed_core(a.key, STREAM_SEATFIRST_B, 39u, a.sf_q0, r.x & xl, r.y & xl, r.x & xh, r.y & xh,
-                                            ~r.x & 0x1FFF1FFFu, ~r.y & 0x1FFF1FFFu, c_thresh39, r.z, r.w, pl);
+        const bool voided = deal_rest39(a.key, a.sf_q0, r.x, r.y, xl, xh, r.z, r.w, pl);
         n_void += (active && voided) ? 1u : 0u;
         if (b2_mask == 0u) {
             stage_b(a, pl, active && !voided, hist, s_shape, lane, s_feat[warp]);

@@ -143,4 +143,116 @@ __host__ __device__ constexpr uint32_t thresh39(int w)
     return (uint32_t)((1ull << 32) % N);
 }
 
+// ---------------------------------------------------------------------------
+// Stage B, fast form: the other 39 cards are dealt to the three other seats on COMPACT positions
+// 0..38 with the static SWAR bookkeeping of deal52 (no per-lane indexing at all), and the two
+// compact owner planes are then deposited into the free positions of the primary seat's mask
+// (a software pdep, sheep-and-goats expand).  Same digits, same order, same owner rule as
+// deal_fixed_core with the primary hand fixed -- hence the same CPU mirror -- at a third of the
+// instructions.
+// ---------------------------------------------------------------------------
+struct RestState {
+    uint32_t w[4];
+    uint32_t x, Q, acc;
+    uint32_t lo[2], hi[2];      // compact planes: word 0 = cards 0..31, word 1 = cards 32..38
+    bool voided;
+};
+
+template <int V>
+__device__ __forceinline__ void rest_step(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, RestState &s)
+{
+    constexpr int n = 39 - V;
+    uint32_t u = 0;
+    if constexpr (n >= 2) {
+        if constexpr ((V & 3) == 0) {
+            if constexpr ((V & 15) == 0) philox4x32_10(key, idx_lo, idx_hi, (uint32_t)(V >> 4), STREAM_SEATFIRST_B, s.w);
+            s.x = s.w[(V >> 2) & 3];
+        }
+        mul_wide(s.x, (uint32_t)n, s.x, u);
+        if constexpr ((V & 3) == 3 || n == 2) {
+            constexpr uint32_t thresh = thresh39(V >> 2);
+            s.voided |= s.x < thresh;
+        }
+    }
+    const uint32_t E = u * 0x010101u + s.Q;
+    const uint32_t T7 = ~E & 0x808080u;
+    s.Q += T7 >> 7;
+    constexpr int i = V & 7;
+    s.acc += T7 >> (7 - i);
+    if constexpr (i == 7 || V == 38) {
+        constexpr uint32_t mask = V == 38 ? 0x7Fu : 0xFFu;
+        const uint32_t par = s.acc ^ (s.acc >> 8) ^ (s.acc >> 16);
+        const uint32_t lob = ~par & mask;
+        const uint32_t hib = ~(s.acc >> 8) & mask;
+        constexpr int word = V >> 5, sh = (V & 31) & ~7;
+        s.lo[word] |= lob << sh;
+        s.hi[word] |= hib << sh;
+        s.acc = 0;
+    }
+}
+
+template <int... V>
+__device__ __forceinline__ void rest_steps(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, RestState &s,
+                                           std::integer_sequence<int, V...>)
+{
+    (rest_step<V>(key, idx_lo, idx_hi, s), ...);
+}
+
+// sheep-and-goats masks of a 32-bit deposit (Hacker's Delight 7-5): computed once per mask word,
+// applied to both planes
+struct Deposit32 { uint32_t mv[5]; uint32_t m; };
+
+__device__ __forceinline__ Deposit32 deposit_prepare(uint32_t m)
+{
+    Deposit32 d;
+    d.m = m;
+    uint32_t mk = ~m << 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t mp = mk ^ (mk << 1);
+        mp ^= mp << 2;
+        mp ^= mp << 4;
+        mp ^= mp << 8;
+        mp ^= mp << 16;
+        const uint32_t mv = mp & m;
+        d.mv[i] = mv;
+        m = (m ^ mv) | (mv >> (1 << i));
+        mk &= ~mp;
+    }
+    return d;
+}
+
+__device__ __forceinline__ uint32_t deposit_apply(const Deposit32 &d, uint32_t x)
+{
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+        const uint32_t t = x << (1 << i);
+        x = (x & ~d.mv[i]) | (t & d.mv[i]);
+    }
+    return x & d.m;
+}
+
+// m0, m1: the primary seat's hand (lane layout); q0: initial Q with capacity 0 for that seat;
+// (xl, xh): all-ones where the primary seat's owner bit 0 / bit 1 is set.
+__device__ __forceinline__ bool deal_rest39(const PhiloxKey &key, uint32_t q0, uint32_t m0, uint32_t m1, uint32_t xl, uint32_t xh,
+                                            uint32_t idx_lo, uint32_t idx_hi, Planes &pl)
+{
+    RestState s;
+    s.x = 0; s.Q = q0; s.acc = 0; s.voided = false;
+    s.lo[0] = s.lo[1] = s.hi[0] = s.hi[1] = 0u;
+    rest_steps(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 39>{});
+    // split the 39 compact bits between the two words of the lane layout
+    const uint32_t f0 = ~m0 & 0x1FFF1FFFu, f1 = ~m1 & 0x1FFF1FFFu;
+    const uint32_t n0 = __popc(f0);                                   // 13..26 free cards in clubs + diamonds
+    const uint32_t keep = (1u << n0) - 1u;                            // n0 <= 26
+    const uint32_t lo_a = s.lo[0] & keep, hi_a = s.hi[0] & keep;
+    const uint32_t lo_b = __funnelshift_r(s.lo[0], s.lo[1], n0), hi_b = __funnelshift_r(s.hi[0], s.hi[1], n0);
+    const Deposit32 d0 = deposit_prepare(f0), d1 = deposit_prepare(f1);
+    pl.lo0 = deposit_apply(d0, lo_a) | (m0 & xl);
+    pl.hi0 = deposit_apply(d0, hi_a) | (m0 & xh);
+    pl.lo1 = deposit_apply(d1, lo_b) | (m1 & xl);
+    pl.hi1 = deposit_apply(d1, hi_b) | (m1 & xh);
+    return s.voided;
+}
+
 }  // namespace bmc
