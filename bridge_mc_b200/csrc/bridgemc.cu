@@ -23,6 +23,7 @@
 #include "deal.cuh"
 #include "features.cuh"
 #include "seatfirst.cuh"
+#include "reforder.cuh"
 #include "rules.hpp"
 
 using namespace bmc;
@@ -401,6 +402,80 @@ __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kerne
 }
 
 // ---------------------------------------------------------------------------
+// K1c: reference-order sampler (reforder.cuh): one thread = one deal, ranged seats sampled one
+// after the other exactly as `build` does (bridge.cl:1292-1319).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q)
+{
+    __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];
+    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
+    __shared__ uint8_t s_shape[14 * 14 * 14];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SF_HIST_COPIES * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
+    __syncthreads();
+    uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
+    uint32_t n_raw = 0, n_bad = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
+    unsigned long long off = (unsigned long long)blockIdx.x * THREADS + threadIdx.x;
+    for (uint32_t it = 0; it < a.iters; ++it, off += stride) {
+        const bool valid = off < a.n;
+        const unsigned long long idx = a.first + off;
+        const uint32_t il = (uint32_t)idx, ih = (uint32_t)(idx >> 32);
+        uint32_t lo0 = a.fix.lo0, lo1 = a.fix.lo1, hi0 = a.fix.hi0, hi1 = a.fix.hi1;
+        uint32_t f0 = a.fix.free0, f1 = a.fix.free1;
+        bool bad = false;
+        for (uint32_t j = 0; j < q.n_stages; ++j) {
+            const SeqStage &st = q.st[j];
+            if (j > 0u && st.m <= 13u) break;                     // a LATER seat is implied once 13 cards remain (bridge.cl:1303);
+                                                                  // the first def always goes through the root generator
+            const SeqRanges r = seq_infer(st, q.exhaust, f0, f1);
+            bad = bad || r.bad;
+            uint32_t h0 = 0, h1 = 0, att = 0;
+            bool need = valid && !bad;
+            while (need) {
+                const bool clean = seq_draw13(a.key, il, ih, STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, h0, h1);
+                if (clean && seq_hand_ok(r, h0, h1)) need = false;
+                else if (++att >= SEQ_MAX_ATTEMPTS) { bad = true; need = false; }
+            }
+            if (!valid || bad) { h0 = 0; h1 = 0; }
+            const uint32_t k = (uint32_t)st.seat;
+            if (k & 1u) { lo0 |= h0; lo1 |= h1; }
+            if (k & 2u) { hi0 |= h0; hi1 |= h1; }
+            f0 &= ~h0; f1 &= ~h1;
+        }
+        Planes pl = {lo0, lo1, hi0, hi1};
+        if (q.n_rest) {                                           // deal-all 13 for the remaining seats
+            uint32_t att = 0;
+            bool need = valid && !bad;
+            while (need) {
+                const bool voided = deal_fixed_core(a.key, STREAM_REFORDER_REST + (att << 8), q.n_rest, q.q_rest, lo0, lo1, hi0, hi1,
+                                                    f0, f1, q.thresh_rest, il, ih, pl);
+                if (!voided) need = false;
+                else if (++att >= 64u) { bad = true; need = false; }
+            }
+        }
+        n_raw += valid ? 1u : 0u;
+        n_bad += (valid && bad) ? 1u : 0u;
+        stage_b(a, pl, valid && !bad, hist, s_shape, lane, s_feat[warp], 0u);
+    }
+    {
+        unsigned long long r64 = n_raw, v64 = n_bad;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r64 += __shfl_xor_sync(0xFFFFFFFFu, r64, o);
+            v64 += __shfl_xor_sync(0xFFFFFFFFu, v64, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.tallies[0], r64);
+            if (v64) atomicAdd(&a.tallies[1], v64);
+        }
+    }
+    __syncthreads();
+    flush_hist(a, &s_hist[0][0], SF_HIST_COPIES);
+}
+
+// ---------------------------------------------------------------------------
 // K2: features / accept / choose-bid on given records
 // ---------------------------------------------------------------------------
 struct SchemeDev {
@@ -675,7 +750,11 @@ struct bmc_constraints {
     bool has_cons = false;
     bool has_fixed = false;
     FixDev fix{};
-    int mode = 0;                // requested: 0 auto, 1 full deal (deal52), 2 seat-first
+    bmc_seat_spec specs[4];      // as given (the reference-order sampler re-reads them)
+    bool has_rules = false;
+    int ref_defs = -1;           // reference-order mode: number of ranged seats after the fixed ones
+    SeqDev seq{};
+    int mode = 0;                // requested: 0 auto, 1 full deal (deal52), 2 seat-first, 3 reference order
     int resolved = 0;            // 0 = not calibrated yet
     double stage_a_pass = -1.0;  // measured pass rate of the primary seat's ranges
     std::mutex mu;
@@ -868,6 +947,13 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     int total_lo[F_COUNT] = {0};
     double selectivity[4] = {0, 0, 0, 0};
     for (int k = 0; k < 4; ++k) {
+        memset(&c->specs[k], 0xFF, sizeof(bmc_seat_spec));        // every bound -1 (nil)
+        c->specs[k].fixed = 0;
+        c->specs[k].fixed_mask = 0;
+        if (specs) c->specs[k] = specs[k];
+        if (rules && rules[k] && rules[k][0]) c->has_rules = true;
+    }
+    for (int k = 0; k < 4; ++k) {
         SeatC &sc = c->dev.seat[k];
         sc.prog = 0xFFFFFFFFu;
         sc.active = 0;
@@ -947,10 +1033,99 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
 
 int bmc_constraints_set_mode(bmc_constraints *c, int mode)
 {
-    if (!c || mode < 0 || mode > 2) return fail(BMC_E_INVALID, "bmc_constraints_set_mode: bad argument");
+    if (!c || mode < 0 || mode > 2) return fail(BMC_E_INVALID, "bmc_constraints_set_mode: bad argument (mode 3 is set by bmc_constraints_set_reference_order)");
     if (mode == 2 && (c->has_fixed || !c->has_cons)) return fail(BMC_E_INVALID, "seat-first mode needs a constrained seat and no fixed hands");
     c->mode = mode;
     c->resolved = 0;
+    return BMC_OK;
+}
+// Builds the per-stage constants of the reference-order sampler from the stored specs.
+static int build_seq(bmc_constraints *c, int n_defs)
+{
+    int n_fixed = 0;
+    while (n_fixed < 4 && c->specs[n_fixed].fixed) ++n_fixed;
+    for (int k = n_fixed; k < 4; ++k)
+        if (c->specs[k].fixed) return fail(BMC_E_INVALID, "reference order: fixed (:=) hands must occupy the first seats, as in `build`");
+    if (n_defs < 1 || n_fixed + n_defs > 4) return fail(BMC_E_INVALID, "reference order: bad number of ranged seats");
+    if (c->has_rules) return fail(BMC_E_INVALID, "reference order: the reference generator takes ranges only, not rule forms");
+    SeqDev &q = c->seq;
+    memset(&q, 0, sizeof q);
+    q.exhaust = (n_fixed + n_defs == 4) ? 1u : 0u;
+    auto has_hcp = [](const bmc_seat_spec &sp) { return sp.hcp[0] >= 0 || sp.hcp[1] >= 0; };
+    auto has_suit = [](const bmc_seat_spec &sp, int s) {
+        return sp.len[s][0] >= 0 || sp.len[s][1] >= 0 || sp.suit_hcp[s][0] >= 0 || sp.suit_hcp[s][1] >= 0;
+    };
+    auto has_third = [](const bmc_seat_spec &sp, int s) { return sp.suit_hcp[s][0] >= 0 || sp.suit_hcp[s][1] >= 0; };
+    uint32_t m = 52u - 13u * (uint32_t)n_fixed;
+    uint32_t cap[4] = {13, 13, 13, 13};
+    for (int k = 0; k < n_fixed; ++k) cap[k] = 0;
+    int sampled = 0;
+    for (int j = 0; j < n_defs; ++j, m -= 13u) {
+        SeqStage &st = q.st[j];
+        const bmc_seat_spec &own = c->specs[n_fixed + j];
+        st.seat = (int8_t)(n_fixed + j);
+        st.m = m;
+        st.has_hcp = has_hcp(own) ? 1 : 0;
+        st.hcp_lo = own.hcp[0]; st.hcp_hi = own.hcp[1];
+        st.has_others = j + 1 < n_defs ? 1 : 0;
+        int su = 0, sl = 0;
+        for (int o = j + 1; o < n_defs; ++o) {
+            const bmc_seat_spec &ot = c->specs[n_fixed + o];
+            if (!has_hcp(ot)) { st.others_missing_hcp = 1; continue; }
+            if (ot.hcp[1] >= 0) su += ot.hcp[1];
+            if (ot.hcp[0] >= 0) sl += ot.hcp[0];
+        }
+        st.sum_upper_hcp = (int16_t)su; st.sum_lower_hcp = (int16_t)sl;
+        for (int s = 0; s < 4; ++s) {
+            SeqSuit &qs = st.suit[s];
+            qs.has_spec = has_suit(own, s) ? 1 : 0;
+            qs.lo = own.len[s][0]; qs.hi = own.len[s][1];
+            qs.has_third = has_third(own, s) ? 1 : 0;
+            qs.third_lo = own.suit_hcp[s][0]; qs.third_hi = own.suit_hcp[s][1];
+            int u = 0, l = 0, lt = 0;
+            for (int o = j + 1; o < n_defs; ++o) {
+                const bmc_seat_spec &ot = c->specs[n_fixed + o];
+                if (!has_suit(ot, s)) { qs.others_missing = 1; continue; }
+                // (or (second val) (first val)) for the lower-bound fold, (first val) for the upper-bound fold
+                if (ot.len[s][1] >= 0) u += ot.len[s][1]; else if (ot.len[s][0] >= 0) u += ot.len[s][0];
+                if (ot.len[s][0] >= 0) l += ot.len[s][0];
+                if (has_third(ot, s) && ot.suit_hcp[s][0] >= 0) lt += ot.suit_hcp[s][0];
+            }
+            qs.sum_upper = (int16_t)u; qs.sum_lower = (int16_t)l; qs.sum_lower_third = (int16_t)lt;
+        }
+        for (int w = 0; w < 13; ++w) {
+            uint64_t N = 1;
+            for (int d = 0; d < 4; ++d) {
+                const int n = (int)m - 4 * w - d;
+                if (n >= 2) N *= (uint64_t)n;
+            }
+            st.thresh[w] = (uint32_t)((1ull << 32) % N);
+        }
+        if (j == 0 || m > 13u) { cap[n_fixed + j] = 0; ++sampled; }
+    }
+    q.n_stages = (uint32_t)n_defs;
+    q.n_rest = 52u - 13u * (uint32_t)(n_fixed + sampled);
+    const uint32_t p0 = cap[0], p1 = p0 + cap[1], p2 = p1 + cap[2];
+    q.q_rest = (128u - p0) | ((128u - p1) << 8) | ((128u - p2) << 16);
+    for (int w = 0; w < 10; ++w) {
+        uint64_t N = 1;
+        for (int d = 0; d < 4; ++d) {
+            const int n = (int)q.n_rest - 4 * w - d;
+            if (n >= 2) N *= (uint64_t)n;
+        }
+        q.thresh_rest[w] = (uint32_t)((1ull << 32) % N);
+    }
+    c->ref_defs = n_defs;
+    return BMC_OK;
+}
+
+int bmc_constraints_set_reference_order(bmc_constraints *c, int n_defs)
+{
+    if (!c) return fail(BMC_E_INVALID, "bmc_constraints_set_reference_order: NULL");
+    int rc = build_seq(c, n_defs);
+    if (rc) return rc;
+    c->mode = 3;
+    c->resolved = 3;
     return BMC_OK;
 }
 int bmc_constraints_mode(const bmc_constraints *c) { return c ? c->resolved : 0; }
@@ -1036,7 +1211,8 @@ static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
 
 // ---- sampling -------------------------------------------------------------------
 static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const FixDev *fix, bool seatfirst, uint64_t seed,
-                       uint64_t first, uint64_t n, uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev)
+                       uint64_t first, uint64_t n, uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev,
+                       const SeqDev *seq = nullptr)
 {
     SampleArgs a;
     a.cons = cons;
@@ -1057,13 +1233,15 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
         a.pad = 0;
     }
     int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
+    if (seq) blocks = ctx->sms * 4;
     const uint64_t per_thread = seatfirst ? SF_ILP : 1;           // raw deals per thread per iteration
     const uint64_t per_iter = (uint64_t)blocks * THREADS * per_thread;
     if (n < per_iter) blocks = (int)((n + THREADS * per_thread - 1) / (THREADS * per_thread));
     if (blocks < 1) blocks = 1;
     const uint64_t chunk = (uint64_t)blocks * THREADS * per_thread;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
-    if (seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a);
+    if (seq) sample_reforder_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a, *seq);
+    else if (seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a);
     else if (fix) {
         if (has_cons) sample_kernel<true, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
         else sample_kernel<false, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
@@ -1089,7 +1267,11 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
     const FixDev *fix = (cons && cons->has_fixed) ? &cons->fix : nullptr;
     bool seatfirst = false;
-    if (has_cons && !fix) {
+    const SeqDev *seq = nullptr;
+    if (cons && cons->resolved == 3) {                 // reference order: `build`'s own sequential semantics
+        seq = &cons->seq;
+        fix = &cons->fix;
+    } else if (has_cons && !fix) {
         bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
         // pass rate of `cal` over 2^16 raw deals of the full-deal kernel (a fixed calibration seed:
         // the outcome, hence the mode and the stream behind each index, is reproducible)
@@ -1172,7 +1354,7 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         uint64_t n = max_launch;
         if (n_raw && n_raw - done < n) n = n_raw - done;
         if (stepwise) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-        int rc = launch_wave(ctx, dev, has_cons, fix, seatfirst, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev);
+        int rc = launch_wave(ctx, dev, has_cons, fix, seatfirst, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev, seq);
         if (rc) return rc;
         done += n;
         ++waves;
@@ -1199,6 +1381,9 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
             }
         }
         if (n_accept_target && head[2] - start_acc >= n_accept_target) break;
+        // watchdog for open-ended jobs: a constraint nothing satisfies must not spin forever
+        if (n_raw == 0 && ((done >= (1ull << 36) && head[2] == start_acc) || done >= (1ull << 44))) break;
+        if (seq && head[2] == start_acc && head[1] >= done) break;      // reference order: every build signalled an error
     }
     if (!stepwise) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(read_head());

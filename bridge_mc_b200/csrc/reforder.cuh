@@ -1,0 +1,164 @@
+// reforder.cuh -- "reference order" sampler: the reference's own multi-seat semantics.
+//
+// `build` (bridge.cl:1292-1319) does NOT draw uniformly over the deals that satisfy every seat's
+// ranges.  It samples the ranged seats one after the other: seat j is uniform over the 13-card
+// hands of the REMAINING cards that satisfy ranges narrowed by infer-distgen-params
+// (bridge.cl:1126-1269) against the remaining supply and the later defs, with these quirks:
+//   * a suit whose narrowed spec has no explicit upper bound is capped at the number of LOW
+//     cards (2..10) left in that suit (bridge.cl:1000-1001 `(or max supply)`);
+//   * the last ranged seat is never sampled when only 13 cards remain (bridge.cl:1303);
+//   * a seat's own per-suit HCP range is dropped when no later def exists (the `,@(if suit-hcp ..)`
+//     splice of bridge.cl:1227-1229);
+//   * lower bounds are inferred only when the four seats are all fixed or ranged
+//     (hands-in-supply = others + 1, bridge.cl:1128,1194).
+// One thread produces one deal: per ranged seat a rejection loop over uniform 13-subsets of the
+// remaining cards (binary deal on compact positions + software deposit), then `deal-all` for the
+// unranged seats.  This path serves the REST-sized jobs of the reference (hundreds of deals);
+// joint rejection (the other kernels) is the throughput path.
+#pragma once
+#include <cstdint>
+#include "deal.cuh"
+#include "seatfirst.cuh"
+
+namespace bmc {
+
+constexpr uint32_t STREAM_REFORDER = 16u, STREAM_REFORDER_REST = 31u;
+constexpr uint32_t SEQ_MAX_ATTEMPTS = 1u << 14;     // candidates per seat before the deal is given up (counted in `voided`)
+
+struct SeqSuit {
+    int8_t has_spec, lo, hi, has_third, third_lo, third_hi;      // own spec; -1 = nil
+    int8_t others_missing;                                        // some later def lacks this suit
+    int8_t pad;
+    int16_t sum_upper, sum_lower, sum_lower_third;                // over the later defs
+    int16_t pad2;
+};
+struct SeqStage {
+    int8_t has_hcp, hcp_lo, hcp_hi, others_missing_hcp, has_others, seat, pad[2];
+    int16_t sum_upper_hcp, sum_lower_hcp;
+    uint32_t m;                   // cards remaining when this seat is sampled
+    SeqSuit suit[4];
+    uint32_t thresh[13];          // Lemire thresholds of the 4-digit words of the 13-of-m binary deal
+};
+struct SeqDev {
+    uint32_t n_stages, exhaust;   // exhaust: fixed + ranged seats = 4
+    uint32_t q_rest;              // initial Q of the final deal-all (capacity 13 for the unranged seats)
+    uint32_t n_rest;              // cards dealt by deal-all
+    uint32_t thresh_rest[10];
+    SeqStage st[4];
+};
+
+struct SeqRanges { int hcp_lo, hcp_hi; int len_lo[4], len_hi[4]; int sh_lo[4], sh_hi[4]; bool bad; };
+
+// infer-distgen-params for stage `s` on the remaining cards (f0, f1: lane-layout masks)
+__device__ __forceinline__ SeqRanges seq_infer(const SeqStage &s, uint32_t exhaust, uint32_t f0, uint32_t f1)
+{
+    SeqRanges r;
+    r.bad = false;
+    int slen[4], nlow[4], shcp[4], total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t lane = ((k < 2 ? f0 : f1) >> (16 * (k & 1))) & 0x1FFFu;
+        slen[k] = __popc(lane);
+        nlow[k] = __popc(lane & 0x1FFu);
+        shcp[k] = (int)((lane >> 9) & 1u) + 2 * (int)((lane >> 10) & 1u) + 3 * (int)((lane >> 11) & 1u) + 4 * (int)((lane >> 12) & 1u);
+        total += shcp[k];
+    }
+    // ---- infer-hcp-range (bridge.cl:1126-1153)
+    const int min_hcp = (exhaust && !s.others_missing_hcp) ? max(total - (int)s.sum_upper_hcp, 0) : 0;
+    const int up_limit = min(total - (int)s.sum_lower_hcp, total);
+    if (!s.has_hcp) {
+        if (up_limit < total || min_hcp > 0) { r.hcp_lo = min_hcp; r.hcp_hi = up_limit; }
+        else { r.hcp_lo = 0; r.hcp_hi = 64; }                      // no :hcp key: no filter
+    } else {
+        r.hcp_lo = max(s.hcp_lo >= 0 ? (int)s.hcp_lo : 0, min_hcp);
+        r.hcp_hi = s.hcp_hi >= 0 ? min((int)s.hcp_hi, up_limit) : up_limit;
+        if (r.hcp_lo > r.hcp_hi) r.bad = true;
+    }
+    // ---- infer-suit-ranges (bridge.cl:1192-1234)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const SeqSuit &q = s.suit[k];
+        const int min_len = (exhaust && !q.others_missing) ? max(slen[k] - (int)q.sum_upper, 0) : 0;
+        const int ul = min(slen[k] - (int)q.sum_lower, slen[k]);
+        r.sh_lo[k] = 0; r.sh_hi[k] = 64;
+        if (!q.has_spec) {
+            if (ul < slen[k]) { r.len_lo[k] = min_len; r.len_hi[k] = ul; }
+            else { r.len_lo[k] = 0; r.len_hi[k] = nlow[k]; }       // no key: the low-card cap
+        } else {
+            const int down = q.lo >= 0 ? max((int)q.lo, min_len) : min_len;
+            const int up = q.hi >= 0 ? min((int)q.hi, ul) : ul;
+            if (down > ul) r.bad = true;
+            r.len_lo[k] = down; r.len_hi[k] = up;
+            if (s.has_others) {                                      // suit-HCP narrowing only when later defs exist
+                const int ulh = min(shcp[k] - (int)q.sum_lower_third, shcp[k]);
+                if (!q.has_third) {
+                    if (ulh < shcp[k]) { r.sh_lo[k] = 0; r.sh_hi[k] = ulh; }
+                } else {
+                    r.sh_lo[k] = max(q.third_lo >= 0 ? (int)q.third_lo : 0, 0);
+                    r.sh_hi[k] = q.third_hi >= 0 ? min((int)q.third_hi, ulh) : ulh;
+                    if (r.sh_lo[k] > r.sh_hi[k]) r.bad = true;
+                }
+            }
+        }
+    }
+    // Necessary conditions for a non-empty admissible set; where they fail the reference's generator has
+    // total weight 0 and `(random 0)` signals an error (e.g. a 13-card single-suit remainder under the cap).
+    int sum_lo = 0, sum_hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int hi = min(r.len_hi[k], slen[k]), lo = max(r.len_lo[k], 0);
+        if (lo > hi) r.bad = true;
+        sum_lo += lo;
+        sum_hi += hi;
+    }
+    if (sum_lo > 13 || sum_hi < 13 || r.hcp_lo > total || r.hcp_hi < 0) r.bad = true;
+    return r;
+}
+
+__device__ __forceinline__ bool seq_hand_ok(const SeqRanges &r, uint32_t m0, uint32_t m1)
+{
+    const Feat f = hand_features(m0, m1);
+    const int hcp = (int)(f.f2 & 0xFFu);
+    bool ok = hcp >= r.hcp_lo && hcp <= r.hcp_hi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int len = (int)((f.f0 >> (8 * k)) & 0xFFu), sh = (int)((f.f1 >> (8 * k)) & 0xFFu);
+        ok = ok && len >= r.len_lo[k] && len <= r.len_hi[k] && sh >= r.sh_lo[k] && sh <= r.sh_hi[k];
+    }
+    return ok;
+}
+
+// Uniform 13-subset of the `m` free cards (f0, f1), attempt `att` of stage stream `stream`.
+// Returns false if a Lemire check failed (the caller simply tries again).
+__device__ __forceinline__ bool seq_draw13(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, uint32_t stream, uint32_t att,
+                                           uint32_t m, const uint32_t *__restrict__ thresh, uint32_t f0, uint32_t f1,
+                                           uint32_t &h0, uint32_t &h1)
+{
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    uint32_t x = 0, c0 = 0, c1 = 0;
+    int r = 13;
+    bool ok = true;
+    for (uint32_t v = 0, n = m; n >= 1u; ++v, --n) {
+        uint32_t u = 0;
+        if (n >= 2u) {
+            if ((v & 3u) == 0u) {
+                if ((v & 15u) == 0u) philox4x32_10(key, idx_lo, idx_hi, att * 4u + (v >> 4), stream, w);
+                const uint32_t sel = (v >> 2) & 3u;
+                x = sel == 0u ? w[0] : sel == 1u ? w[1] : sel == 2u ? w[2] : w[3];
+            }
+            mul_wide(x, n, x, u);
+            if ((v & 3u) == 3u || n == 2u) ok = ok && !(x < thresh[v >> 2]);
+        }
+        const uint32_t take = (int)u < r ? 1u : 0u;
+        r -= (int)take;
+        if (v < 32u) c0 |= take << v; else c1 |= take << (v - 32u);
+    }
+    const uint32_t n0 = __popc(f0);
+    const uint32_t a = n0 >= 32u ? c0 : (c0 & ((1u << n0) - 1u));
+    const uint32_t b = n0 >= 32u ? c1 : __funnelshift_r(c0, c1, n0);
+    h0 = deposit_apply(deposit_prepare(f0), a);
+    h1 = deposit_apply(deposit_prepare(f1), b);
+    return ok;
+}
+
+}  // namespace bmc

@@ -75,12 +75,20 @@ class Deal:
     BATCH = 2048
 
     def __init__(self, const_hands=None, defs=None, rules=None, engine: Engine | None = None, seed: int | None = None,
-                 max_raw: int = 1 << 34):
+                 max_raw: int = 1 << 34, semantics: str | None = None):
         self.const_hands = [self._hand(h) for h in (const_hands or [])]
         self.defs = [plist_to_def(sexp.read(d) if isinstance(d, str) else d) for d in (defs or [])]
         self.rules = list(rules or [])
         if len(self.const_hands) + len(self.defs) > 4:
             raise ValueError("more than four seats defined")
+        # "reference": `build`'s own sequential seat-by-seat sampling incl. its quirks (bmc_constraints_set_reference_order),
+        # the default for plain range defs; "uniform": uniform over the deals satisfying every seat (joint rejection),
+        # forced when rule forms are given (the reference generator cannot take them).
+        self.semantics = semantics or ("uniform" if any(self.rules) else "reference")
+        if self.semantics not in ("reference", "uniform"):
+            raise ValueError("semantics must be 'reference' or 'uniform'")
+        if self.semantics == "reference" and any(self.rules):
+            raise ValueError("rule forms need semantics='uniform'")
         self._engine = engine
         self.seed = DEFAULT_SEED ^ int.from_bytes(os.urandom(8), "little") if seed is None else seed
         self.max_raw = max_raw
@@ -116,6 +124,11 @@ class Deal:
             rules = [None] * len(self.const_hands) + list(self.rules)
             rules += [None] * (4 - len(rules))
             self._cons = Constraints(specs, rules if any(rules) else None)
+            if self.semantics == "reference":
+                # no def at all still samples one seat through the root generator (bridge.cl:1297-1313)
+                n_defs = max(1, len(self.defs))
+                if len(self.const_hands) + n_defs <= 4:
+                    self._cons.set_reference_order(n_defs)
         return self._cons
 
     def build_records(self, n: int) -> np.ndarray:
@@ -124,11 +137,14 @@ class Deal:
         out = []
         have = 0
         wave = 1 << 14
+        if self.semantics == "reference" and cons.mode in (0, 3):
+            wave = max(256, 1 << (max(n, 1) - 1).bit_length())      # every index yields a deal: no need to overdraw
         spent = 0
         while have < n:
-            rec, tal, st = self.engine.sample(cons, n_accept=n - have, seed=self.seed, first_index=self._next_index,
-                                              wave=wave, tally_mask=0, cap=(n - have) + wave)
-            used = st.waves * wave
+            budget = max(wave, min(self.max_raw - spent, wave * 256))          # bounded work per library call
+            rec, tal, st = self.engine.sample(cons, n_accept=n - have, n_raw=budget, seed=self.seed,
+                                              first_index=self._next_index, wave=wave, tally_mask=0, cap=(n - have) + wave)
+            used = int(st.raw)
             self._next_index += used
             spent += used
             if rec.shape[0]:
@@ -136,6 +152,9 @@ class Deal:
                 rec = rec[np.lexsort((rec[:, 0], rec[:, 1]))]
                 out.append(rec)
                 have += rec.shape[0]
+            elif cons.mode == 3 and st.voided == st.raw:
+                from .infer import BadRangeError
+                raise BadRangeError("Can't infer correct limit!", None, None)      # every build signals bad-range
             elif spent >= self.max_raw:
                 raise NoDealFound(f"no deal satisfies {self!r} within {spent} raw deals")
             if st.accepted * 64 < used and wave < (1 << 30):

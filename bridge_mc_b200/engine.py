@@ -70,11 +70,16 @@ class Constraints:
         self._h = C.c_void_p()
         check(L.bmc_constraints_create(arr, rarr, C.byref(self._h)))
 
-    MODE_AUTO, MODE_FULL, MODE_SEAT_FIRST = 0, 1, 2
+    MODE_AUTO, MODE_FULL, MODE_SEAT_FIRST, MODE_REFERENCE_ORDER = 0, 1, 2, 3
 
     def set_mode(self, mode: int):
         """bmc_constraints_set_mode: 0 auto, 1 full deal, 2 seat-first (see bridgemc.h)."""
         check(_lib.load().bmc_constraints_set_mode(self._h, mode))
+        return self
+
+    def set_reference_order(self, n_defs: int):
+        """bmc_constraints_set_reference_order: sample the `n_defs` ranged seats one after the other, as `build` does."""
+        check(_lib.load().bmc_constraints_set_reference_order(self._h, n_defs))
         return self
 
     @property

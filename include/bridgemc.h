@@ -146,6 +146,15 @@ void bmc_constraints_destroy(bmc_constraints *c);
  * bmc_constraints_mode returns the resolved mode (0 before the first call),
  * bmc_constraints_primary the seat tested first. */
 int  bmc_constraints_set_mode(bmc_constraints *c, int mode);
+/* Mode 3, "reference order": reproduce `build`'s OWN multi-seat semantics (bridge.cl:1292-1319)
+ * instead of the uniform distribution over valid deals: after the fixed hands (which must occupy
+ * the first seats) the next `n_defs` seats are sampled one after the other, each uniform over the
+ * hands of the remaining cards admitted by infer-distgen-params (bridge.cl:1126-1269) -- including
+ * the low-card cap on suits without an explicit upper bound, the never-sampled last seat and the
+ * dropped suit-HCP range of a lone def; the remaining seats are dealt by deal-all.  Ranges only (no
+ * rule forms).  Every index yields one deal (raw == accepted) unless the narrowed ranges are empty
+ * for it -- where the reference signals bad-range -- which is counted in `voided`. */
+int  bmc_constraints_set_reference_order(bmc_constraints *c, int n_defs);
 int  bmc_constraints_mode(const bmc_constraints *c);
 int  bmc_constraints_primary(const bmc_constraints *c);
 
@@ -164,7 +173,9 @@ void bmc_scheme_destroy(bmc_scheme *s);
  *   n_accept_target  > 0: whole waves of `wave` indices (0 = default 2^26)
  *       starting at first_index until accepted >= target or n_raw indices
  *       (0 = no limit) are used; the accepted SET depends only on
- *       (seed, first_index, wave, target).
+ *       (seed, first_index, wave, target).  Watchdog of the unlimited form: the
+ *       call returns (BMC_OK, fewer than target accepted) after 2^36 indices
+ *       without a single accepted deal, or 2^44 indices in all.
  * records may be NULL (tally only); at most `cap` records are stored.
  * Host-buffer form (what the Lisp shim calls): */
 int bmc_sample(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,

@@ -191,8 +191,14 @@ def test_deal_build_order_and_errors(engine):
     assert len(hands) == 4
     assert 15 <= sum(max(r - 8, 0) for s in hands[0].suits for r in s) <= 17 and len(hands[0].suits[3]) >= 5
     three = [str2hand("♣ AKQJ1098765432 ♦ ♥ ♠"), str2hand("♣ ♦ AKQJ1098765432 ♥ ♠"), str2hand("♣ ♦ ♥ AKQJ1098765432 ♠")]
-    only = Deal(three, [{"hcp": [10, 10]}], engine=engine, seed=2).build()
+    wide = {"hcp": [10, 10], "c": [0, 13], "d": [0, 13], "h": [0, 13], "s": [0, 13]}
+    only = Deal(three, [wide], engine=engine, seed=2).build()
     assert len(only) == 1 and only[0].suits[3] == list(range(13))      # bridge.cl:1316-1319: only the sampled hand
+    # kept quirk: a suit without an explicit upper bound is capped at its low cards (bridge.cl:1000-1001), so the
+    # reference cannot build this 13-spade remainder at all (total weight 0 -> error); uniform semantics can
+    with pytest.raises(BadRange):
+        Deal(three, [{"hcp": [10, 10]}], engine=engine, seed=2).build()
+    assert len(Deal(three, [{"hcp": [10, 10]}], engine=engine, seed=2, semantics="uniform").build()) == 1
     with pytest.raises(BadRange):
         Deal(defs=[{"hcp": [30, 37]}, {"hcp": [15, 17]}], engine=engine).build()
 
@@ -281,3 +287,14 @@ def test_empty_and_edge_inputs(engine):
     assert tal["raw"] == 1 and rec.shape[0] + tal["voided"] == 1
     rec, tal, st = engine.sample(None, n_raw=1000, seed=1, cap=10)           # cap smaller than the accepted count
     assert rec.shape[0] == 10 and tal["accepted"] > 10 and tal["stored"] == 10
+
+
+def test_open_ended_job_watchdog(engine):
+    """an accept-target job on a constraint (almost) nothing satisfies returns instead of spinning for ever"""
+    cons = Constraints([None, None, seat_spec(hcp=(37, 37)), None])           # 4 hands in 6.35e11
+    rec, tal, st = engine.sample(cons, n_accept=1000, wave=1 << 30, seed=1, cap=1000)
+    assert tal["accepted"] < 1000 and tal["raw"] >= 1 << 36
+    # and the host mirror reports it
+    from bridge_mc_b200.deal import NoDealFound
+    with pytest.raises(NoDealFound):
+        Deal(defs=[{"hcp": [37, 37]}], engine=engine, seed=1, semantics="uniform", max_raw=1 << 30).build()
