@@ -22,6 +22,7 @@
 (cffi:defcfun "bmc_last_error" :string)
 (cffi:defcfun "bmc_constraints_create" :int (specs :pointer) (rules :pointer) (out :pointer))
 (cffi:defcfun "bmc_constraints_destroy" :void (c :pointer))
+(cffi:defcfun "bmc_constraints_set_reference_order" :int (c :pointer) (n-defs :int))
 (cffi:defcfun "bmc_scheme_create" :int (table :string) (out :pointer))
 (cffi:defcfun "bmc_scheme_destroy" :void (s :pointer))
 (cffi:defcfun "bmc_sample" :int
@@ -102,7 +103,10 @@
                            do (fill-range p 'len i spec)
                               (fill-range p 'suit-hcp i (and (listp spec) (third spec))))))
           (bmc-check (bmc-constraints-create specs (cffi:null-pointer) out))
-          (setf handle (cffi:mem-ref out :pointer))))))
+          (setf handle (cffi:mem-ref out :pointer))
+          ;; keep `build`'s own seat-by-seat distribution (and quirks); no def still samples one seat
+          (bmc-check (bmc-constraints-set-reference-order handle (max 1 (length defs))))
+          handle))))
 
 (defmethod refill ((this gpu-deal) n)
   (with-slots (next-index seed) this

@@ -31,7 +31,7 @@ def main():
     for i, a in enumerate(sys.argv):
         if a == "--scale":
             scale = float(sys.argv[i + 1])
-    which = [a for a in args if a.startswith("c")] or ["c1", "c2", "c3", "c4", "c5"]
+    which = [a for a in args if a.startswith("c") or a == "ref"] or ["c1", "c2", "c3", "c4", "c5", "ref"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -98,6 +98,17 @@ def main():
         nt2 = bidding.nt_responses(2)
         cons = Constraints(None, [nt2.chooses((6, "NT")), None, bidding.openings.chooses((2, "NT")), None])
         run("C5", cons, int(1e11 * scale), "S chooses 2NT, N answers 6NT over (nt-responses 2)")
+    if "ref" in which:
+        # the REST shape (rest.cl:264-277): one fixed hand + three ranged seats, sampled in the reference's own
+        # seat-by-seat order (bmc_constraints_set_reference_order)
+        from bridge_mc_b200.cards import str2hand
+        from bridge_mc_b200.engine import seat_spec
+        south = str2hand("♠ AKJ5 ♥ K1064 ♦ Q87 ♣ A6")
+        specs = [seat_spec(fixed=south), seat_spec(hcp=(10, 12), s=(4, None)), seat_spec(), seat_spec()]
+        cons = Constraints(specs).set_reference_order(3)
+        run("REF-order", cons, int(2e8 * scale), "fixed hand + 3 ranged seats in `build`'s sequential order (mode 3)")
+        cons2 = Constraints([seat_spec(hcp=(15, 17), s=(5, None)), seat_spec(hcp=(10, 11), h=(4, None))]).set_reference_order(2)
+        run("REF-order-2", cons2, int(2e8 * scale), "two ranged seats (15-17 with 5+ spades, then 10-11 with 4+ hearts), mode 3")
     if "c4" in which and rank == 0:
         cs = [compscore.Contract(t).c_struct() for t in ("1NTS", "3NTS", "4HS", "4SS")] * 2
         vul = [0, 0, 0, 0, 1, 1, 1, 1]
