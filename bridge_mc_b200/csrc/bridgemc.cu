@@ -757,7 +757,7 @@ struct bmc_constraints {
     int mode = 0;                // requested: 0 auto, 1 full deal (deal52), 2 seat-first, 3 reference order
     int resolved = 0;            // 0 = not calibrated yet
     double stage_a_pass = -1.0;  // measured pass rate of the primary seat's ranges
-    std::mutex mu;
+    std::mutex mu, cal_mu;
 };
 
 struct bmc_scheme {
@@ -1273,6 +1273,7 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         fix = &cons->fix;
     } else if (has_cons && !fix) {
         bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
+        std::lock_guard<std::mutex> cal_lock(cc->cal_mu);      // one calibration per constraint, even across contexts
         // pass rate of `cal` over 2^16 raw deals of the full-deal kernel (a fixed calibration seed:
         // the outcome, hence the mode and the stream behind each index, is reproducible)
         auto pass_rate = [&](const ConsDev &cal, double &rate) -> int {
