@@ -474,3 +474,85 @@ class Bidding:
         else:
             self.bid_scheme = None             # the reference's cond has no live clause here ((nil ...), bidding.cl:479)
         return self.bids
+
+
+# ---- auctions as generator constraints (BASELINE config "full bidding-sequence constraints") ----
+def response_scheme(opening) -> RuleTable | None:
+    """The scheme class `bidding` switches to after `opening` (bidding.cl:476-479)."""
+    opening = _norm_bid(opening)
+    if opening == (2, "C"):
+        return two_c_responses
+    if opening[1] == "NT":
+        return nt_responses(opening[0])
+    if opening[0] == 1:
+        return basic_responses(opening)
+    return None
+
+
+def auction_rules(dealer: int, calls):
+    """Per-seat rule forms (seat order N E S W) for an auction that starts with `dealer` and goes `calls`:
+    each call is None / "P" (pass) or a bid like (1, "NT").  Calls before the first bid are judged over
+    `openings`; the opener's partner's first call over the response scheme of the opening
+    (`response_scheme`); the opponents' calls after the opening are not constrained beyond a pass being a pass
+    over `openings` (the reference has no overcall tables).  Returns a list of four forms (None = unconstrained)
+    ready for `Constraints(None, rules)`.
+
+    Example: auction_rules(0, ["P", "P", (1, "NT"), "P", (3, "NT")]) -- North deals and passes, East
+    passes, South opens 1NT, West passes, North answers 3NT."""
+    forms = [[] for _ in range(4)]
+    opener = opening = None
+    responded = False
+    for i, call in enumerate(calls):
+        seat = (dealer + i) % 4
+        is_pass = call is None or (isinstance(call, str) and call.upper() in ("P", "PASS"))
+        if opener is None:
+            if is_pass:
+                forms[seat].append(openings.passes())
+            else:
+                opener, opening = seat, _norm_bid(call)
+                forms[seat].append(openings.chooses(opening))
+        elif seat == (opener + 2) % 4 and not responded:
+            responded = True
+            scheme = response_scheme(opening)
+            if scheme is None:
+                raise ValueError(f"no response scheme after {opening}")
+            forms[seat].append(scheme.passes() if is_pass else scheme.chooses(call))
+        elif is_pass:
+            if seat != opener and not forms[seat]:
+                forms[seat].append(openings.passes())        # an opponent who has not spoken yet: no opening bid either
+        else:
+            raise ValueError("only the opening and the first response are modelled by the reference's tables")
+    return [None if not fs else fs[0] if len(fs) == 1 else _and(*fs) for fs in forms]
+
+
+def first_two_calls(records, engine: Engine | None = None):
+    """Batched class-`bidding` `next` (bidding.cl:463-480) over deal records, dealer = seat 0: for every deal the
+    first seat that has an opening bid, that bid, and partner's answer over the matching response scheme.
+    Returns (opener int8[n] (-1: passed out), opening list, response list); everything is evaluated on the GPU
+    (two bmc_filter passes per distinct opening)."""
+    eng = engine or Engine.default()
+    rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
+    _, feats = eng.filter(rec, None, openings.scheme())
+    bids = feats["bid"].astype(np.int64)                       # [n, 4]
+    if (bids == -2).any():
+        raise BidError("illegal function call while evaluating the openings")
+    has = bids >= 0
+    opener = np.where(has.any(axis=1), has.argmax(axis=1), -1).astype(np.int8)
+    n = rec.shape[0]
+    opening = [None] * n
+    response = [None] * n
+    open_idx = np.where(opener >= 0, bids[np.arange(n), np.maximum(opener, 0)], -1)
+    for k in np.unique(open_idx[open_idx >= 0]):
+        bid = openings.rows[int(k)][0]
+        sel = np.nonzero(open_idx == k)[0]
+        for i in sel:
+            opening[i] = bid
+        scheme = response_scheme(bid)
+        if scheme is None:
+            continue
+        _, f2 = eng.filter(rec[sel], None, scheme.scheme())
+        partner = (opener[sel].astype(np.int64) + 2) % 4
+        rb = f2["bid"][np.arange(sel.size), partner].astype(np.int64)
+        for i, r in zip(sel, rb):
+            response[i] = "error" if r == -2 else (None if r < 0 else scheme.rows[int(r)][0])
+    return opener, opening, response

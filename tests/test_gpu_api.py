@@ -298,3 +298,36 @@ def test_open_ended_job_watchdog(engine):
     from bridge_mc_b200.deal import NoDealFound
     with pytest.raises(NoDealFound):
         Deal(defs=[{"hcp": [37, 37]}], engine=engine, seed=1, semantics="uniform", max_raw=1 << 30).build()
+
+
+def test_auction_rules_and_first_two_calls(engine):
+    """auction constraints composed from the reference's tables (config C3) and the batched class-`bidding` next"""
+    rules = bidding.auction_rules(0, ["P", "P", (1, "NT"), "P", (3, "NT")])
+    cons = Constraints(None, rules)
+    rec, tal, _ = engine.sample(cons, n_raw=3_000_000, seed=41)
+    assert 3000 < rec.shape[0] < 4600                                   # p = 1.258e-3
+    opener, opening, response = bidding.first_two_calls(rec, engine)
+    assert (opener == 2).all() and set(opening) == {(1, "NT")} and set(response) == {(3, "NT")}
+    # on unconstrained deals: against the oracle's choose-bid, seat by seat
+    raw, _, _ = engine.sample(None, n_raw=20_000, seed=42)
+    opener, opening, response = bidding.first_two_calls(raw, engine)
+    m = seat_masks(raw)
+    op = O.choose_bid_batch(0, m.reshape(-1)).reshape(-1, 4)
+    names = bidding.openings.bids()
+    for i in range(0, raw.shape[0], 3):
+        seats = [k for k in range(4) if op[i, k] >= 0]
+        if not seats:
+            assert opener[i] == -1 and opening[i] is None
+            continue
+        k = seats[0]
+        assert opener[i] == k and opening[i] == names[op[i, k]]
+        partner = (k + 2) % 4
+        bid = opening[i]
+        if bid == (2, "C"):
+            sid, table = 3, bidding.two_c_responses
+        elif bid[1] == "NT":
+            sid, table = bid[0], bidding.nt_responses(bid[0])
+        else:
+            continue                                                    # basic-responses: checked against the Python evaluator elsewhere
+        r = int(O.choose_bid_batch(sid, m[i:i + 1, partner])[0])
+        assert response[i] == (None if r < 0 else table.rows[r][0])
