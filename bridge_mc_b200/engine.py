@@ -93,7 +93,10 @@ class Constraints:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            _lib.load().bmc_constraints_destroy(h)
+            try:
+                _lib.load().bmc_constraints_destroy(h)
+            except Exception:          # interpreter shutdown: module globals may already be gone
+                pass
             self._h = None
 
 
@@ -108,7 +111,10 @@ class Scheme:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            _lib.load().bmc_scheme_destroy(h)
+            try:
+                _lib.load().bmc_scheme_destroy(h)
+            except Exception:
+                pass
             self._h = None
 
 
