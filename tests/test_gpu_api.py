@@ -331,3 +331,29 @@ def test_auction_rules_and_first_two_calls(engine):
             continue                                                    # basic-responses: checked against the Python evaluator elsewhere
         r = int(O.choose_bid_batch(sid, m[i:i + 1, partner])[0])
         assert response[i] == (None if r < 0 else table.rows[r][0])
+
+
+def test_reentrancy_across_threads(engine):
+    """calls arrive concurrently from several threads in the reference (hunchentoot workers, dealgen/sim threads):
+    one ctx per thread, and a ctx shared by several threads, must both give the single-threaded results"""
+    import threading
+    from bridge_mc_b200.engine import Engine
+    cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    want = [sort_records(engine.sample(cons, n_raw=200_000, seed=50 + i)[0]) for i in range(6)]
+    got = [None] * 6
+    own = [Engine(0) for _ in range(3)]
+
+    def work(i):
+        eng = own[i] if i < 3 else engine                   # threads 3..5 share the session's ctx
+        for _ in range(3):
+            got[i] = sort_records(eng.sample(cons, n_raw=200_000, seed=50 + i)[0])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for i in range(6):
+        assert np.array_equal(got[i], want[i])
+    for e in own:
+        e.close()
