@@ -56,7 +56,7 @@ assert FEATURE_DTYPE.itemsize == 12
 
 EXPORTS = [
     "bmc_init", "bmc_shutdown", "bmc_last_error", "bmc_version", "bmc_host_alloc", "bmc_host_free",
-    "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_mode", "bmc_constraints_primary",
+    "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_set_jit", "bmc_constraints_jit_ms", "bmc_constraints_mode", "bmc_constraints_primary",
     "bmc_scheme_create",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
     "bmc_match_points", "bmc_score_tally", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
@@ -91,6 +91,9 @@ def load():
     L.bmc_constraints_destroy.restype = None
     L.bmc_constraints_set_mode.argtypes = [vp, C.c_int]
     L.bmc_constraints_set_reference_order.argtypes = [vp, C.c_int]
+    L.bmc_constraints_set_jit.argtypes = [vp, C.c_int]
+    L.bmc_constraints_jit_ms.argtypes = [vp]
+    L.bmc_constraints_jit_ms.restype = C.c_float
     L.bmc_constraints_mode.argtypes = [vp]
     L.bmc_constraints_primary.argtypes = [vp]
     L.bmc_scheme_create.argtypes = [C.c_char_p, C.POINTER(vp)]

@@ -25,6 +25,8 @@
 #include "seatfirst.cuh"
 #include "reforder.cuh"
 #include "rules.hpp"
+#include "jit.hpp"
+#include "embedded_src.inc"
 
 using namespace bmc;
 
@@ -44,362 +46,7 @@ static int fail(int code, const std::string &msg)
             return fail(BMC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
     } while (0)
 
-// ---------------------------------------------------------------------------
-// device-side constraint / tally layout
-// ---------------------------------------------------------------------------
-struct ConsDev {
-    SeatC seat[4];
-    uint32_t n_active;       // number of constrained seats
-    uint32_t primary;        // seat tested in stage A
-    uint32_t b1_mask;        // seat-first mode: seats fully tested right after the deal is completed (0xF: all of them);
-                             // the others are tested after one more compaction
-    uint32_t pad;
-    const uint32_t *code;    // device pointer, programs of all seats
-};
-
-// shared-memory histogram (per warp): hcp[4][40] | len[4][4][16] | shape[4][40]
-constexpr int SH_HCP = 0, SH_LEN = 160, SH_SHAPE = 160 + 256, SH_WORDS = 160 + 256 + 160;
-constexpr int WARPS_PER_BLOCK = 8, THREADS = WARPS_PER_BLOCK * 32;
-constexpr int QCAP = 64;     // per-warp queue of stage-A survivors
-
-__constant__ uint8_t c_shape_lut[14 * 14 * 14];   // (len_c, len_d, len_h) -> sorted-shape class
-
-struct SampleArgs {
-    ConsDev cons;
-    PhiloxKey key;
-    FixDev fix;
-    uint64_t first, n;
-    uint4 *records;          // may be null
-    uint64_t cap;
-    unsigned long long *tallies;   // bmc_tallies as u64 words
-    uint32_t tally_mask;
-    uint32_t iters;          // warp-iterations per warp
-    uint32_t sf_q0;          // seat-first mode: initial Q of stage B (capacity 0 for the primary seat)
-    uint32_t pad;
-};
-
-__device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0, uint32_t &m1)
-{
-    const uint32_t xl = (k & 1) ? 0u : 0xFFFFFFFFu, xh = (k & 2) ? 0u : 0xFFFFFFFFu;
-    m0 = (pl.lo0 ^ xl) & (pl.hi0 ^ xh) & 0x1FFF1FFFu;
-    m1 = (pl.lo1 ^ xl) & (pl.hi1 ^ xh) & 0x1FFF1FFFu;
-}
-
-// Full test (ranges + rule program) of the constrained seats selected by `mask`.
-__device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl, uint32_t mask, uint32_t *scratch, unsigned lane)
-{
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const SeatC &c = a.cons.seat[k];
-        if (c.active && ((mask >> k) & 1u)) {
-            uint32_t m0, m1;
-            seat_words(pl, k, m0, m1);
-            const Feat f = hand_features(m0, m1);
-            ok = ok && seat_ranges_ok(c, f);
-            if (c.prog != 0xFFFFFFFFu) {
-                bool err = false;
-                const bool v = run_program(a.cons.code + c.prog, feat_store(scratch, lane, f), err);
-                ok = ok && v && !err;
-            }
-        }
-    }
-    return ok;
-}
-
-// Stage B: full test of the seats in `mask`, then tallies and the compacted store.
-__device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
-                                        const uint8_t *shape_lut, unsigned lane, uint32_t *scratch, uint32_t mask = 0xFu)
-{
-    const bool ok = seats_pass(a, pl, mask, scratch, lane) && active;
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-    if (bal == 0u) return;
-    const unsigned cnt = __popc(bal);
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&a.tallies[2], (unsigned long long)cnt);      // accepted (also the slot cursor)
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (ok) {
-        const unsigned long long slot = base + __popc(bal & ((1u << lane) - 1u));
-        if (a.records != nullptr && slot < a.cap) a.records[slot] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
-        if (a.tally_mask) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t m0, m1;
-                seat_words(pl, k, m0, m1);
-                const Feat f = hand_features(m0, m1);
-                if (a.tally_mask & BMC_TALLY_HCP) atomicAdd(&hist[SH_HCP + k * 40 + (f.f2 & 0xFFu)], 1u);
-                if (a.tally_mask & BMC_TALLY_LEN) {
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) atomicAdd(&hist[SH_LEN + (k * 4 + s) * 16 + ((f.f0 >> (8 * s)) & 0xFFu)], 1u);
-                }
-                if (a.tally_mask & BMC_TALLY_SHAPE) {
-                    const uint32_t L = f.f0;
-                    const uint32_t cls = shape_lut[(L & 0xFFu) * 196u + ((L >> 8) & 0xFFu) * 14u + ((L >> 16) & 0xFFu)];
-                    atomicAdd(&hist[SH_SHAPE + k * 40 + cls], 1u);
-                }
-            }
-        }
-    }
-}
-
-// block-level flush of the per-warp shared histograms into bmc_tallies (u64 atomics)
-__device__ __forceinline__ void flush_hist(const SampleArgs &a, const uint32_t *s_hist, int copies = WARPS_PER_BLOCK)
-{
-    if (!a.tally_mask) return;
-    for (int i = threadIdx.x; i < SH_WORDS; i += THREADS) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int w = 0; w < copies; ++w) v += s_hist[w * SH_WORDS + i];
-        if (v == 0u) continue;
-        int word;                                                                    // padded shared layout -> bmc_tallies words
-        if (i < SH_LEN) word = 4 + i;                                                // hcp[4][40]
-        else if (i < SH_SHAPE) {
-            const int j = i - SH_LEN, bin = j & 15;
-            if (bin >= BMC_LEN_BINS) continue;
-            word = 4 + 160 + (j >> 4) * BMC_LEN_BINS + bin;                          // len[4][4][14]
-        } else word = 4 + 160 + 224 + (i - SH_SHAPE);                                // shape[4][40]
-        atomicAdd(&a.tallies[word], (unsigned long long)v);
-    }
-}
-
-template <bool HAS_CONS, bool FIXED>
-__global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__ SampleArgs a)
-{
-    __shared__ uint32_t s_hist[WARPS_PER_BLOCK][SH_WORDS];
-    __shared__ uint4 s_queue[HAS_CONS ? WARPS_PER_BLOCK : 1][QCAP];
-    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
-    __shared__ uint8_t s_shape[14 * 14 * 14];
-
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < WARPS_PER_BLOCK * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
-    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
-    __syncthreads();
-
-    uint32_t *hist = s_hist[warp];
-    const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
-    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    uint32_t n_raw = 0, n_void = 0;           // per thread: at most `iters` each
-    unsigned q_head = 0, q_tail = 0;          // warp-uniform
-
-    for (uint32_t it = 0; it < a.iters; ++it) {
-        const unsigned long long off = ((unsigned long long)it * total_warps + gwarp) * 32ull + lane;
-        const bool valid = off < a.n;
-        const unsigned long long idx = a.first + off;
-        Planes pl;
-        const bool voided = FIXED ? deal_fixed(a.key, a.fix, (uint32_t)idx, (uint32_t)(idx >> 32), pl)
-                                  : deal52(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
-        n_raw += valid ? 1u : 0u;
-        n_void += (valid && voided) ? 1u : 0u;
-        bool ok = valid && !voided;
-        if (HAS_CONS) {
-            // Stage A: cheap range test of the primary seat
-            const SeatC &c = a.cons.seat[a.cons.primary];
-            uint32_t m0, m1;
-            seat_words(pl, (int)a.cons.primary, m0, m1);
-            const Feat f = hand_features(m0, m1);
-            ok = ok && seat_ranges_ok(c, f);
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-            if (bal) {
-                if (ok) {
-                    const unsigned pos = (q_tail + __popc(bal & ((1u << lane) - 1u))) % QCAP;
-                    s_queue[warp][pos] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
-                }
-                q_tail += __popc(bal);
-                __syncwarp();
-                if (q_tail - q_head >= 32u) {
-                    const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
-                    q_head += 32u;
-                    __syncwarp();
-                    Planes p2 = {r.x, r.y, r.z, r.w};
-                    stage_b(a, p2, true, hist, s_shape, lane, s_feat[warp]);
-                }
-            }
-        } else {
-            stage_b(a, pl, ok, hist, s_shape, lane, s_feat[warp]);
-        }
-    }
-    if (HAS_CONS) {
-        const unsigned left = q_tail - q_head;       // < 32
-        if (left) {
-            const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
-            Planes p2 = {r.x, r.y, r.z, r.w};
-            stage_b(a, p2, lane < left, hist, s_shape, lane, s_feat[warp]);
-        }
-    }
-
-    // flush counters and histograms
-    {
-        unsigned long long r64 = n_raw, v64 = n_void;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            r64 += __shfl_xor_sync(0xFFFFFFFFu, r64, o);
-            v64 += __shfl_xor_sync(0xFFFFFFFFu, v64, o);
-        }
-        if (lane == 0) {
-            atomicAdd(&a.tallies[0], r64);
-            if (v64) atomicAdd(&a.tallies[1], v64);
-        }
-    }
-    __syncthreads();
-    flush_hist(a, &s_hist[0][0]);
-}
-
-// ---------------------------------------------------------------------------
-// K1b: seat-first sampler (seatfirst.cuh): stages A1 -> A2 -> B with two per-warp
-// compaction queues, so each stage runs on full warps.
-// ---------------------------------------------------------------------------
-#ifndef SF_MIN_BLOCKS
-#define SF_MIN_BLOCKS 6
-#endif
-constexpr int SF_HIST_COPIES = 2;
-#ifndef SF_ILP
-#define SF_ILP 1
-#endif
-__constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
-                                        thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
-
-__global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kernel(const __grid_constant__ SampleArgs a)
-{
-    __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];   // stage B is rare here: few copies suffice
-    __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (H | r << 16, idx_lo, idx_hi, -)
-    __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, idx_lo, idx_hi)
-    __shared__ uint4 s_q3[WARPS_PER_BLOCK][QCAP];     // B1 survivors: complete deals (planes)
-    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
-    __shared__ uint8_t s_shape[14 * 14 * 14];
-
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SF_HIST_COPIES * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
-    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
-    __syncthreads();
-
-    uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
-    uint4 *q1 = s_q1[warp], *q2 = s_q2[warp], *q3 = s_q3[warp];
-    unsigned h3 = 0, t3 = 0;
-    const uint32_t b1_mask = a.cons.b1_mask & 0xFu, b2_mask = ~b1_mask & 0xFu;
-    const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
-    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    uint32_t n_raw = 0, n_void = 0;                  // per thread: at most `iters` each
-    unsigned h1 = 0, t1 = 0, h2 = 0, t2 = 0;         // queue cursors, warp-uniform
-    const uint32_t P = a.cons.primary;
-    const SeatC &c = a.cons.seat[P];
-
-    // ---- stage B on up to 32 queued hands ------------------------------------------
-    auto run_b = [&](unsigned count) {
-        const uint4 r = q2[(h2 + lane) % QCAP];
-        h2 += count;
-        __syncwarp();
-        const bool active = lane < count;
-        Planes pl;
-        const uint32_t xl = (P & 1u) ? 0xFFFFFFFFu : 0u, xh = (P & 2u) ? 0xFFFFFFFFu : 0u;
-        const bool voided = deal_rest39(a.key, a.sf_q0, r.x, r.y, xl, xh, r.z, r.w, pl);
-        n_void += (active && voided) ? 1u : 0u;
-        if (b2_mask == 0u) {
-            stage_b(a, pl, active && !voided, hist, s_shape, lane, s_feat[warp]);
-            return;
-        }
-        // B1: the primary seat's program and the most selective other seat; survivors are compacted
-        // once more so that the remaining (expensive, rarely needed) programs run on full warps
-        const bool ok = seats_pass(a, pl, b1_mask, s_feat[warp], lane) && active && !voided;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-        if (bal) {
-            if (ok) q3[(t3 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
-            t3 += __popc(bal);
-            __syncwarp();
-            if (t3 - h3 >= 32u) {
-                const uint4 r3 = q3[(h3 + lane) % QCAP];
-                h3 += 32u;
-                __syncwarp();
-                const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-                stage_b(a, p3, true, hist, s_shape, lane, s_feat[warp], b2_mask);
-            }
-        }
-    };
-    // ---- stage A2 on up to 32 queued honour sets ---------------------------------------
-    auto run_a2 = [&](unsigned count) {
-        const uint4 r = q1[(h1 + lane) % QCAP];
-        h1 += count;
-        __syncwarp();
-        const bool active = lane < count;
-        bool voided = false;
-        uint32_t m0, m1;
-        sf_lows(a.key, r.y, r.z, r.x & 0xFFFFu, (int)(r.x >> 16), voided, m0, m1);
-        n_void += (active && voided) ? 1u : 0u;
-        const Feat f = hand_features(m0, m1);
-        const bool ok = active && !voided && seat_ranges_ok(c, f);
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-        if (bal) {
-            if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, r.y, r.z);
-            t2 += __popc(bal);
-            __syncwarp();
-            if (t2 - h2 >= 32u) run_b(32u);
-        }
-    };
-
-    // Each thread draws SF_ILP independent deals per iteration (two interleaved dependency chains keep
-    // both integer pipes fed).  Only the last iteration can hold indices past the end.
-    const unsigned long long stride = total_warps * (32ull * SF_ILP);
-    unsigned long long off = gwarp * (32ull * SF_ILP) + lane;
-    const uint32_t full_iters = (uint32_t)(a.n / stride);
-    const uint32_t hcp_lo = c.hcp_lo_span & 0xFFu, hcp_span = c.hcp_lo_span >> 8;
-    const bool need_power = (c.need & 2u) != 0u;
-    for (uint32_t it = 0; it < a.iters; ++it, off += stride) {
-        SeatFirstState s[SF_ILP];
-        uint32_t H[SF_ILP];
-        bool ok[SF_ILP];
-#pragma unroll
-        for (int j = 0; j < SF_ILP; ++j) {
-            const unsigned long long idx = a.first + off + 32ull * j;
-            H[j] = sf_honours(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), s[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < SF_ILP; ++j) {
-            const bool valid = it < full_iters || off + 32ull * j < a.n;
-            n_raw += (it >= full_iters && valid) ? 1u : 0u;
-            n_void += (valid && s[j].voided) ? 1u : 0u;
-            ok[j] = valid && !s[j].voided && (honour_hcp(H[j]) - hcp_lo) <= hcp_span;
-            if (need_power) {
-                uint32_t Pw, hcp;
-                honour_features(H[j], Pw, hcp);
-                ok[j] = ok[j] && in_ranges(Pw, c.A[1], c.B[1]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < SF_ILP; ++j) {
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok[j]);
-            if (bal) {
-                const unsigned long long idx = a.first + off + 32ull * j;
-                if (ok[j]) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] =
-                               make_uint4(H[j] | ((uint32_t)s[j].r << 16), (uint32_t)idx, (uint32_t)(idx >> 32), 0u);
-                t1 += __popc(bal);
-                __syncwarp();
-                if (t1 - h1 >= 32u) run_a2(32u);
-            }
-        }
-    }
-    if (t1 - h1) run_a2(t1 - h1);
-    if (t2 - h2) run_b(t2 - h2);
-    if (t3 - h3) {
-        const uint4 r3 = q3[(h3 + lane) % QCAP];
-        const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-        stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, s_feat[warp], b2_mask);
-    }
-    n_raw += full_iters * SF_ILP;
-
-    {
-        unsigned long long r64 = n_raw, v64 = n_void;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            r64 += __shfl_xor_sync(0xFFFFFFFFu, r64, o);
-            v64 += __shfl_xor_sync(0xFFFFFFFFu, v64, o);
-        }
-        if (lane == 0) {
-            atomicAdd(&a.tallies[0], r64);
-            if (v64) atomicAdd(&a.tallies[1], v64);
-        }
-    }
-    __syncthreads();
-    flush_hist(a, &s_hist[0][0], SF_HIST_COPIES);
-}
+#include "kernels.cuh"
 
 // ---------------------------------------------------------------------------
 // K1c: reference-order sampler (reforder.cuh): one thread = one deal, ranged seats sampled one
@@ -754,6 +401,10 @@ struct bmc_constraints {
     bool has_rules = false;
     int ref_defs = -1;           // reference-order mode: number of ranged seats after the fixed ones
     SeqDev seq{};
+    std::string rule_text[4];    // the rule forms as given (the NVRTC path re-reads them)
+    int jit = 0;                 // 0: interpret the rule bytecode; 1: compile the rule forms into the kernel (NVRTC)
+    JitKernel jit_kernel[2];     // [0] full-deal kernel, [1] seat-first kernel
+    std::string jit_log;
     int mode = 0;                // requested: 0 auto, 1 full deal (deal52), 2 seat-first, 3 reference order
     int resolved = 0;            // 0 = not calibrated yet
     double stage_a_pass = -1.0;  // measured pass rate of the primary seat's ranges
@@ -951,7 +602,7 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
         c->specs[k].fixed = 0;
         c->specs[k].fixed_mask = 0;
         if (specs) c->specs[k] = specs[k];
-        if (rules && rules[k] && rules[k][0]) c->has_rules = true;
+        if (rules && rules[k] && rules[k][0]) { c->has_rules = true; c->rule_text[k] = rules[k]; }
     }
     for (int k = 0; k < 4; ++k) {
         SeatC &sc = c->dev.seat[k];
@@ -1135,7 +786,94 @@ void bmc_constraints_destroy(bmc_constraints *c)
 {
     if (!c) return;
     if (c->d_code) { cudaSetDevice(c->d_device); cudaFree(c->d_code); }
+    for (JitKernel &jk : c->jit_kernel)
+        if (jk.module) { cudaSetDevice(jk.device); JitApi::get().ModuleUnload(jk.module); }
     delete c;
+}
+
+// ---- NVRTC specialisation of a constraint (jit.hpp) ------------------------------------------------
+static int jit_build(bmc_ctx *ctx, bmc_constraints *c, bool seatfirst)
+{
+    JitKernel &jk = c->jit_kernel[seatfirst ? 1 : 0];
+    if (jk.func && jk.device == ctx->device) return BMC_OK;
+    JitApi &api = JitApi::get();
+    if (!api.ok) return fail(BMC_E_CUDA, "NVRTC specialisation unavailable: " + api.why);
+    // 1. the rule forms as one C++ function
+    std::string fn =
+        "__device__ __forceinline__ bool bmc_jit_seat_rule(int seat, const bmc::Feat &f, bool &err)\n{\n"
+        "    const int vC = f.f0 & 0xFF, vD = (f.f0 >> 8) & 0xFF, vH = (f.f0 >> 16) & 0xFF, vS = (f.f0 >> 24) & 0xFF;\n"
+        "    const int vCP = f.f1 & 0xFF, vDP = (f.f1 >> 8) & 0xFF, vHP = (f.f1 >> 16) & 0xFF, vSP = (f.f1 >> 24) & 0xFF;\n"
+        "    const int vHCP = f.f2 & 0xFF, vLOS = (f.f2 >> 8) & 0xFF; const bool vBAL = ((f.f2 >> 16) & 0xFF) != 0;\n"
+        "    (void)vC; (void)vD; (void)vH; (void)vS; (void)vCP; (void)vDP; (void)vHP; (void)vSP; (void)vHCP; (void)vLOS; (void)vBAL;\n"
+        "    switch (seat) {\n";
+    try {
+        RuleEmitter em;
+        for (int k = 0; k < 4; ++k) {
+            if (c->dev.seat[k].prog == 0xFFFFFFFFu || c->rule_text[k].empty()) continue;
+            SxReader rd(c->rule_text[k]);
+            Sx form = rd.read();
+            if (form.is_list() && form.items.size() == 2 && form.items[0].is_sym("QUOTE")) form = form.items[1];
+            fn += "    case " + std::to_string(k) + ": return " + em.emit(form) + ";\n";
+        }
+    } catch (const RuleError &e) {
+        return fail(BMC_E_PARSE, std::string("jit: ") + e.what());
+    }
+    fn += "    default: return true;\n    }\n}\n";
+    const std::string prog = std::string(
+        "typedef unsigned char uint8_t; typedef signed char int8_t; typedef unsigned short uint16_t; typedef short int16_t;\n"
+        "typedef unsigned int uint32_t; typedef int int32_t; typedef unsigned long long uint64_t; typedef long long int64_t;\n"
+        "#define BMC_JIT 1\n") + (seatfirst ? "#define BMC_JIT_SEATFIRST 1\n" : "#define BMC_JIT_FULL 1\n") +
+        "#include \"features.cuh\"\n" + fn + "#include \"kernels.cuh\"\n";
+    // 2. compile for sm_100a
+    auto t0 = std::chrono::steady_clock::now();
+    nvrtcProgram p = nullptr;
+    if (api.CreateProgram(&p, prog.c_str(), "bmc_jit.cu", kJitSrcCount, kJitSrcTexts, kJitSrcNames) != NVRTC_SUCCESS)
+        return fail(BMC_E_CUDA, "nvrtcCreateProgram failed");
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    const nvrtcResult r = api.CompileProgram(p, 3, opts);
+    size_t ls = 0;
+    api.GetProgramLogSize(p, &ls);
+    c->jit_log.assign(ls, ' ');
+    if (ls) api.GetProgramLog(p, &c->jit_log[0]);
+    if (r != NVRTC_SUCCESS) {
+        api.DestroyProgram(&p);
+        return fail(BMC_E_CUDA, "NVRTC compilation failed: " + c->jit_log.substr(0, 2000));
+    }
+    size_t cs = 0;
+    api.GetCUBINSize(p, &cs);
+    std::vector<char> cubin(cs);
+    api.GetCUBIN(p, cubin.data());
+    api.DestroyProgram(&p);
+    // 3. load, bind, initialise the module's constant tables
+    if (jk.module) { api.ModuleUnload(jk.module); jk = JitKernel(); }
+    CUresult cr = api.ModuleLoadData(&jk.module, cubin.data());
+    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleLoadData failed: " + std::to_string((int)cr));
+    cr = api.ModuleGetFunction(&jk.func, jk.module, seatfirst ? "bmc_jit_sample_seatfirst" : "bmc_jit_sample_full");
+    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleGetFunction failed: " + std::to_string((int)cr));
+    CUdeviceptr lut = 0;
+    size_t lut_bytes = 0;
+    cr = api.ModuleGetGlobal(&lut, &lut_bytes, jk.module, "c_shape_lut");
+    if (cr != CUDA_SUCCESS || lut_bytes != sizeof g_shape_lut) return fail(BMC_E_CUDA, "jit: c_shape_lut not found");
+    cr = api.MemcpyHtoD(lut, g_shape_lut, sizeof g_shape_lut);
+    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "jit: shape LUT upload failed");
+    int occ = 0;
+    api.Occupancy(&occ, jk.func, THREADS, 0);
+    jk.blocks_per_sm = occ > 0 ? occ : 1;
+    jk.device = ctx->device;
+    jk.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return BMC_OK;
+}
+
+int bmc_constraints_set_jit(bmc_constraints *c, int on)
+{
+    if (!c || on < 0 || on > 1) return fail(BMC_E_INVALID, "bmc_constraints_set_jit: bad argument");
+    c->jit = on;
+    return BMC_OK;
+}
+float bmc_constraints_jit_ms(const bmc_constraints *c)
+{
+    if (!c) return 0.f;
+    return c->jit_kernel[0].compile_ms + c->jit_kernel[1].compile_ms;
 }
 
 static int cons_upload(bmc_ctx *ctx, const bmc_constraints *cc, ConsDev &dev)
@@ -1212,7 +950,7 @@ static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
 // ---- sampling -------------------------------------------------------------------
 static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const FixDev *fix, bool seatfirst, uint64_t seed,
                        uint64_t first, uint64_t n, uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev,
-                       const SeqDev *seq = nullptr)
+                       const SeqDev *seq = nullptr, const JitKernel *jit = nullptr)
 {
     SampleArgs a;
     a.cons = cons;
@@ -1234,13 +972,18 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     }
     int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
     if (seq) blocks = ctx->sms * 4;
+    if (jit) blocks = ctx->sms * jit->blocks_per_sm;
     const uint64_t per_thread = seatfirst ? SF_ILP : 1;           // raw deals per thread per iteration
     const uint64_t per_iter = (uint64_t)blocks * THREADS * per_thread;
     if (n < per_iter) blocks = (int)((n + THREADS * per_thread - 1) / (THREADS * per_thread));
     if (blocks < 1) blocks = 1;
     const uint64_t chunk = (uint64_t)blocks * THREADS * per_thread;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
-    if (seq) sample_reforder_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a, *seq);
+    if (jit) {
+        void *params[] = {&a};
+        const CUresult cr = JitApi::get().LaunchKernel(jit->func, (unsigned)blocks, 1, 1, THREADS, 1, 1, 0, (CUstream)ctx->stream, params, nullptr);
+        if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuLaunchKernel (jit) failed: " + std::to_string((int)cr));
+    } else if (seq) sample_reforder_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a, *seq);
     else if (seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a);
     else if (fix) {
         if (has_cons) sample_kernel<true, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
@@ -1323,6 +1066,14 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         dev.b1_mask = cc->dev.b1_mask;
         seatfirst = cc->resolved == 2;
     }
+    const JitKernel *jit = nullptr;
+    if (cons && cons->jit && has_cons && !fix && !seq && cons->has_rules) {
+        bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
+        std::lock_guard<std::mutex> jl(cc->cal_mu);
+        int rc = jit_build(ctx, cc, seatfirst);
+        if (rc) return rc;
+        jit = &cc->jit_kernel[seatfirst ? 1 : 0];
+    }
     const bool stream_copy = host_out && records_dev && cap;
     const bool stepwise = n_accept_target != 0 || stream_copy;
     if (wave == 0) wave = 1ull << 26;
@@ -1355,7 +1106,7 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         uint64_t n = max_launch;
         if (n_raw && n_raw - done < n) n = n_raw - done;
         if (stepwise) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-        int rc = launch_wave(ctx, dev, has_cons, fix, seatfirst, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev, seq);
+        int rc = launch_wave(ctx, dev, has_cons, fix, seatfirst, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev, seq, jit);
         if (rc) return rc;
         done += n;
         ++waves;

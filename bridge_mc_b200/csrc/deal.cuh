@@ -25,10 +25,17 @@
 //     u >= prefix_j; T7 = ~E & 0x808080 marks the prefixes that shrink.  Five
 //     instructions per card: IMAD.WIDE, IMAD, LOP3, 2 x LEA.HI.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
-#include <utility>
+#endif
 
 namespace bmc {
+
+// compile-time integer sequence (no <utility>: the same text is compiled by NVRTC)
+template <int... I> struct iseq {};
+template <int N, int... I> struct make_iseq_impl : make_iseq_impl<N - 1, N - 1, I...> {};
+template <int... I> struct make_iseq_impl<0, I...> { using type = iseq<I...>; };
+template <int N> using make_iseq = typename make_iseq_impl<N>::type;
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
@@ -140,7 +147,7 @@ __device__ __forceinline__ void deal_step(const PhiloxKey &key, uint32_t idx_lo,
 
 template <int... P>
 __device__ __forceinline__ void deal_all_steps(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, DealState &s,
-                                               std::integer_sequence<int, P...>)
+                                               iseq<P...>)
 {
     (deal_step<P>(key, idx_lo, idx_hi, s), ...);
 }
@@ -154,7 +161,7 @@ __device__ __forceinline__ bool deal52(const PhiloxKey &key, uint32_t idx_lo, ui
     s.acc = 0;
     s.lo[0] = s.lo[1] = s.hi[0] = s.hi[1] = 0u;
     s.voided = false;
-    deal_all_steps(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 52>{});
+    deal_all_steps(key, idx_lo, idx_hi, s, make_iseq<52>{});
     pl.lo0 = s.lo[0]; pl.lo1 = s.lo[1]; pl.hi0 = s.hi[0]; pl.hi1 = s.hi[1];
     return s.voided;
 }
@@ -174,6 +181,7 @@ struct FixDev {
     uint32_t thresh[10];          // Lemire threshold of every 4-digit word
 };
 
+#ifndef __CUDACC_RTC__
 __host__ inline void fixdev_init(FixDev &f, const uint64_t fixed_mask[4], const bool is_fixed[4])
 {
     uint64_t lo = 0, hi = 0, used = 0;
@@ -200,6 +208,7 @@ __host__ inline void fixdev_init(FixDev &f, const uint64_t fixed_mask[4], const 
         f.thresh[w] = (uint32_t)((1ull << 32) % N);
     }
 }
+#endif
 
 // Core loop.  All arguments but (idx, masks of the v2 path) are grid-uniform; the
 // seat-first sampler calls it with PER-LANE masks (the primary seat's hand).

@@ -8,8 +8,10 @@
 //     f0 = lens   (bytes c d h s)         f1 = power / suit HCP (bytes c d h s)
 //     f2 = hcp | losers<<8 | balanced<<16
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
-#include "rules.hpp"
+#endif
+#include "bytecode.h"
 
 namespace bmc {
 

@@ -9,27 +9,13 @@
 #pragma once
 #include <cstdint>
 #include <cstdlib>
+#include "bytecode.h"
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace bmc {
-
-// ---- feature vector --------------------------------------------------------
-enum Feature : int { F_C = 0, F_D, F_H, F_S, F_CP, F_DP, F_HP, F_SP, F_HCP, F_LOS, F_BAL, F_COUNT };
-
-// ---- bytecode ----------------------------------------------------------------
-// word: bits 0-3 op | 4-6 cmp | 8-11 feature a | 12-15 feature b | 16-23 const
-enum Op : uint32_t { OP_END = 0, OP_CMPC, OP_CMPF, OP_AND, OP_OR, OP_NOT, OP_TRUE, OP_FALSE,
-                     OP_ERRIF_T, OP_ERRIF_F };
-// cmp field = 3-bit truth table over (a<b, a==b, a>b)
-enum Cmp : uint32_t { CMP_LT = 1, CMP_LE = 3, CMP_GT = 4, CMP_GE = 6, CMP_EQ = 2, CMP_NE = 5 };
-
-inline uint32_t enc(Op op, Cmp c = CMP_LT, int a = 0, int b = 0, int k = 0)
-{
-    return (uint32_t)op | ((uint32_t)c << 4) | ((uint32_t)a << 8) | ((uint32_t)b << 12) | ((uint32_t)(k & 0xFF) << 16);
-}
 
 struct RuleError : std::runtime_error { using std::runtime_error::runtime_error; };
 

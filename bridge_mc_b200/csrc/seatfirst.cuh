@@ -18,8 +18,6 @@
 // Binary step (seat gets the card iff u < r, r = cards the seat still needs):
 //     d = u - r ; mask = (mask << 1) | sign(d) ; r += d >> 31        (4 instructions with the digit)
 #pragma once
-#include <cstdint>
-#include <utility>
 #include "deal.cuh"
 
 namespace bmc {
@@ -85,7 +83,7 @@ __device__ __forceinline__ void sf_step(const PhiloxKey &key, uint32_t idx_lo, u
 
 template <int Base, int... K>
 __device__ __forceinline__ void sf_steps(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s,
-                                         std::integer_sequence<int, K...>)
+                                         iseq<K...>)
 {
     (sf_step<Base + K>(key, idx_lo, idx_hi, s), ...);
 }
@@ -94,7 +92,7 @@ __device__ __forceinline__ void sf_steps(const PhiloxKey &key, uint32_t idx_lo, 
 __device__ __forceinline__ uint32_t sf_honours(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s)
 {
     s.x = 0; s.mask = 0; s.r = 13; s.voided = false;
-    sf_steps<0>(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 16>{});
+    sf_steps<0>(key, idx_lo, idx_hi, s, make_iseq<16>{});
     return s.mask & 0xFFFFu;
 }
 
@@ -122,10 +120,10 @@ __device__ __forceinline__ void sf_lows(const PhiloxKey &key, uint32_t idx_lo, u
     SeatFirstState s;
     s.x = 0; s.r = r; s.voided = voided;
     s.mask = 0;
-    sf_steps<16>(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 18>{});     // lows 35..18: hearts, spades
+    sf_steps<16>(key, idx_lo, idx_hi, s, make_iseq<18>{});     // lows 35..18: hearts, spades
     const uint32_t hs = s.mask & 0x3FFFFu;
     s.mask = 0;
-    sf_steps<34>(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 18>{});     // lows 17..0: clubs, diamonds
+    sf_steps<34>(key, idx_lo, idx_hi, s, make_iseq<18>{});     // lows 17..0: clubs, diamonds
     const uint32_t cd = s.mask & 0x3FFFFu;
     voided = s.voided;
     m0 = (cd & 0x1FFu) | ((cd & 0x3FE00u) << 7) | ((H & 0xFu) << 9) | ((H & 0xF0u) << 21);
@@ -193,7 +191,7 @@ __device__ __forceinline__ void rest_step(const PhiloxKey &key, uint32_t idx_lo,
 
 template <int... V>
 __device__ __forceinline__ void rest_steps(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, RestState &s,
-                                           std::integer_sequence<int, V...>)
+                                           iseq<V...>)
 {
     (rest_step<V>(key, idx_lo, idx_hi, s), ...);
 }
@@ -240,7 +238,7 @@ __device__ __forceinline__ bool deal_rest39(const PhiloxKey &key, uint32_t q0, u
     RestState s;
     s.x = 0; s.Q = q0; s.acc = 0; s.voided = false;
     s.lo[0] = s.lo[1] = s.hi[0] = s.hi[1] = 0u;
-    rest_steps(key, idx_lo, idx_hi, s, std::make_integer_sequence<int, 39>{});
+    rest_steps(key, idx_lo, idx_hi, s, make_iseq<39>{});
     // split the 39 compact bits between the two words of the lane layout
     const uint32_t f0 = ~m0 & 0x1FFF1FFFu, f1 = ~m1 & 0x1FFF1FFFu;
     const uint32_t n0 = __popc(f0);                                   // 13..26 free cards in clubs + diamonds

@@ -82,6 +82,15 @@ class Constraints:
         check(_lib.load().bmc_constraints_set_reference_order(self._h, n_defs))
         return self
 
+    def set_jit(self, on: bool = True):
+        """bmc_constraints_set_jit: compile the rule forms into the kernel with NVRTC instead of interpreting them."""
+        check(_lib.load().bmc_constraints_set_jit(self._h, 1 if on else 0))
+        return self
+
+    @property
+    def jit_ms(self) -> float:
+        return float(_lib.load().bmc_constraints_jit_ms(self._h))
+
     @property
     def mode(self) -> int:
         return _lib.load().bmc_constraints_mode(self._h)

@@ -155,6 +155,13 @@ int  bmc_constraints_set_mode(bmc_constraints *c, int mode);
  * rule forms).  Every index yields one deal (raw == accepted) unless the narrowed ranges are empty
  * for it -- where the reference signals bad-range -- which is counted in `voided`. */
 int  bmc_constraints_set_reference_order(bmc_constraints *c, int n_defs);
+/* Rule forms are interpreted from bytecode by default.  on = 1: at the next sampling call the forms
+ * are translated to C++, spliced into the same kernel source and compiled for sm_100a with NVRTC
+ * (about a second or two, once per constraint and dealing mode) -- the way the reference `eval`s its
+ * rule forms.  Results are bit-identical; worthwhile for long or repeated jobs on rule-heavy
+ * constraints.  BMC_E_CUDA if libnvrtc cannot be loaded.  bmc_constraints_jit_ms: compile time spent. */
+int  bmc_constraints_set_jit(bmc_constraints *c, int on);
+float bmc_constraints_jit_ms(const bmc_constraints *c);
 int  bmc_constraints_mode(const bmc_constraints *c);
 int  bmc_constraints_primary(const bmc_constraints *c);
 

@@ -28,6 +28,7 @@ SEED = 0x6272696467656D63
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     scale = 1.0
+    use_jit = "--jit" in sys.argv
     for i, a in enumerate(sys.argv):
         if a == "--scale":
             scale = float(sys.argv[i + 1])
@@ -47,6 +48,8 @@ def main():
     tallies = torch.zeros(_lib.TALLY_WORDS, dtype=torch.int64, device=dev)
 
     def run(name, cons, n_raw, note, tally_mask=7, records=False):
+        if use_jit and cons is not None:
+            cons.set_jit(True)
         first, per = bdist.rank_range(0, n_raw, rank, world)
         cap = 0
         rec = None
@@ -73,6 +76,7 @@ def main():
         if rank == 0:
             print(json.dumps({
                 "config": name, "note": note, "n_gpus": world, "mode": (cons.mode if cons else 1),
+                "jit_compile_ms": (cons.jit_ms if cons else 0.0),
                 "raw": t["raw"], "voided": t["voided"], "accepted": t["accepted"], "acceptance": t["accepted"] / max(1, t["raw"]),
                 "kernel_ms": float(ms[0]), "wall_ms_incl_allreduce": float(ms[1]),
                 "raw_deals_per_s": t["raw"] / (float(ms[0]) * 1e-3), "accepted_per_s": t["accepted"] / (float(ms[0]) * 1e-3),
