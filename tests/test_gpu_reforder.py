@@ -148,3 +148,14 @@ def test_reference_order_errors(engine):
     _, feats = engine.filter(rec)
     assert (feats["hcp"][:, 0] >= 20).all() and (feats["hcp"][:, 0] <= 22).all() and (feats["hcp"][:, 1] >= 19).all()
     assert (feats["hcp"][:, 0] + feats["hcp"][:, 1] <= 40).all()
+
+
+def test_three_ranged_seats_with_suit_hcp_ranges(engine):
+    """three defs with per-suit HCP ranges (third elements), open ends and a seat that lacks keys the others have:
+    exercises the suit-HCP narrowing against the later defs and the `others missing` cases of the folds"""
+    defs = [dict(hcp=(11, 14), s=(5, None, (4, None)), h=(0, 3)),
+            dict(hcp=(6, 9), s=(0, 3, (1, None)), d=(4, None)),
+            dict(c=(3, 6))]
+    tal, f = _compare(engine, [], defs, 5000, 3)
+    assert tal["hcp"][0][:11].sum() == 0 and tal["hcp"][0][15:].sum() == 0
+    assert tal["len"][2][0][:3].sum() == 0 and tal["len"][2][0][7:].sum() == 0      # third seat: 3..6 clubs
