@@ -46,6 +46,13 @@ class Stats(C.Structure):
                 ("waves", C.c_uint32), ("launches", C.c_uint32), ("kernel_ms", C.c_float), ("total_ms", C.c_float)]
 
 
+class Measure(C.Structure):
+    _fields_ = [("kind", C.c_uint8), ("seat", C.c_uint8), ("suit", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+M_HCP, M_LEN, M_SUIT_HCP, M_LOSERS, M_BALANCED, M_LINE_HCP, M_TRUMP_LEN, M_SHAPE, M_LONGEST = range(9)
+
+
 class Contract(C.Structure):
     _fields_ = [("level", C.c_int8), ("suit", C.c_int8), ("declarer", C.c_int8), ("dbl", C.c_int8)]
 
@@ -59,7 +66,7 @@ EXPORTS = [
     "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_set_jit", "bmc_constraints_jit_ms", "bmc_constraints_mode", "bmc_constraints_primary",
     "bmc_scheme_create",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
-    "bmc_match_points", "bmc_score_tally", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
+    "bmc_match_points", "bmc_score_tally", "bmc_hist_base", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
 ]
 
 _lib = None
@@ -106,6 +113,7 @@ def load():
     L.bmc_score.argtypes = [vp, C.POINTER(Contract), vp, u32, vp, u64, vp]
     L.bmc_match_points.argtypes = [vp, vp, vp, u64, vp, vp]
     L.bmc_score_tally.argtypes = [vp, C.POINTER(Contract), vp, u32, vp, u32, u64, u64, u64, vp, vp, vp]
+    L.bmc_hist_base.argtypes = [vp, vp, u64, C.POINTER(Measure), u32, vp, vp, u64, C.POINTER(u64)]
     L.bmc_int_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.bmc_launch_count.argtypes = [vp]
     L.bmc_launch_count.restype = u64

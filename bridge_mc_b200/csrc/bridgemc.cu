@@ -12,6 +12,7 @@
 // integer issue.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +25,7 @@
 #include "features.cuh"
 #include "seatfirst.cuh"
 #include "reforder.cuh"
+#include "hist.cuh"
 #include "rules.hpp"
 #include "jit.hpp"
 #include "embedded_src.inc"
@@ -1350,6 +1352,97 @@ int bmc_score_tally(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *
         for (int tr = 0; tr < 14; ++tr) tricks_hist[c * 14 + tr] = h[c * 14 + tr];
     for (uint32_t p = 0; p < n_pairs; ++p)
         for (int v = 0; v < 49; ++v) imp_hist[p * 49 + v] = h[8 * 14 + p * 49 + v];
+    return BMC_OK;
+}
+
+// ---- hist-base over measure tuples (bridge.cl:1325-1330) ---------------------------------------------
+__global__ void gather_first_kernel(const uint32_t *__restrict__ idx_sorted, const unsigned long long *__restrict__ offsets,
+                                    uint32_t runs, uint32_t *__restrict__ first)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < runs) first[i] = idx_sorted[offsets[i]];
+}
+
+int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc_measure *measures, uint32_t k,
+                  uint8_t *tuples, uint64_t *counts, uint64_t cap, uint64_t *n_unique)
+{
+    if (!ctx || !measures || k == 0 || k > 8 || !n_unique) return fail(BMC_E_INVALID, "bmc_hist_base: bad argument");
+    *n_unique = 0;
+    if (n == 0) return BMC_OK;
+    if (!records) return fail(BMC_E_INVALID, "bmc_hist_base: records is NULL");
+    if (n >= (1ull << 31)) return fail(BMC_E_CAPACITY, "bmc_hist_base: at most 2^31 - 1 deals per call");
+    MeasureDev md{};
+    md.k = k;
+    for (uint32_t j = 0; j < k; ++j) {
+        if (measures[j].kind > M_LONGEST || measures[j].seat > 3 || measures[j].suit > 3) return fail(BMC_E_INVALID, "bmc_hist_base: bad measure");
+        md.kind[j] = measures[j].kind; md.seat[j] = measures[j].seat; md.suit[j] = measures[j].suit;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    uint4 *d_rec = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr, *d_uniq = nullptr, *d_off = nullptr;
+    uint32_t *d_idx = nullptr, *d_idx2 = nullptr, *d_cnt = nullptr, *d_runs = nullptr, *d_first = nullptr;
+    uint8_t *d_lut = nullptr;
+    void *d_tmp = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    alloc((void **)&d_rec, n * sizeof(uint4));
+    alloc((void **)&d_keys, n * 8); alloc((void **)&d_keys2, n * 8); alloc((void **)&d_uniq, n * 8);
+    alloc((void **)&d_idx, n * 4); alloc((void **)&d_idx2, n * 4); alloc((void **)&d_cnt, n * 4); alloc((void **)&d_runs, 4);
+    alloc((void **)&d_lut, sizeof g_shape_lut);
+    std::vector<unsigned long long> h_uniq;
+    std::vector<uint32_t> h_cnt, h_first;
+    uint32_t runs = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rec, records, n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lut, g_shape_lut, sizeof g_shape_lut, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        measure_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(md, d_rec, n, d_lut, d_keys, d_idx);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    size_t tmp_bytes = 0, tmp2 = 0;
+    const int begin_bit = 8 * (8 - (int)k);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, (int)n, begin_bit, 64, ctx->stream);
+    if (e == cudaSuccess) e = cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, d_keys2, d_uniq, d_cnt, d_runs, (int)n, ctx->stream);
+    if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+    alloc(&d_tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, (int)n, begin_bit, 64, ctx->stream);
+    if (e == cudaSuccess) e = cub::DeviceRunLengthEncode::Encode(d_tmp, tmp_bytes, d_keys2, d_uniq, d_cnt, d_runs, (int)n, ctx->stream);
+    ctx->launches += 2;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&runs, d_runs, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && runs) {
+        h_uniq.resize(runs); h_cnt.resize(runs); h_first.resize(runs);
+        e = cudaMemcpy(h_uniq.data(), d_uniq, runs * 8ull, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(h_cnt.data(), d_cnt, runs * 4ull, cudaMemcpyDeviceToHost);
+        std::vector<unsigned long long> off(runs);
+        unsigned long long acc = 0;
+        for (uint32_t i = 0; i < runs; ++i) { off[i] = acc; acc += h_cnt[i]; }
+        alloc((void **)&d_off, runs * 8ull); alloc((void **)&d_first, runs * 4ull);
+        if (e == cudaSuccess) e = cudaMemcpy(d_off, off.data(), runs * 8ull, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            gather_first_kernel<<<(runs + 255) / 256, 256, 0, ctx->stream>>>(d_idx2, d_off, runs, d_first);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_first.data(), d_first, runs * 4ull, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d_rec); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_uniq); cudaFree(d_off); cudaFree(d_idx); cudaFree(d_idx2);
+    cudaFree(d_cnt); cudaFree(d_runs); cudaFree(d_first); cudaFree(d_lut); cudaFree(d_tmp);
+    if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("bmc_hist_base: ") + cudaGetErrorString(e));
+    *n_unique = runs;
+    if (runs > cap) return fail(BMC_E_CAPACITY, "bmc_hist_base: " + std::to_string(runs) + " distinct tuples, capacity " + std::to_string(cap));
+    if (runs && (!tuples || !counts)) return fail(BMC_E_INVALID, "bmc_hist_base: output buffers are NULL");
+    // first-seen order, like hist-base
+    std::vector<uint32_t> order(runs);
+    for (uint32_t i = 0; i < runs; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_first[a] < h_first[b]; });
+    for (uint32_t o = 0; o < runs; ++o) {
+        const uint32_t i = order[o];
+        for (uint32_t j = 0; j < k; ++j) tuples[(uint64_t)o * k + j] = (uint8_t)(h_uniq[i] >> (8 * (7 - j)));
+        counts[o] = h_cnt[i];
+    }
     return BMC_OK;
 }
 

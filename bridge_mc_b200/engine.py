@@ -246,6 +246,20 @@ class Engine:
                                       seed, first_index, n, th.ctypes.data, ih.ctypes.data, tab.ctypes.data))
         return th, ih[:npairs], tab
 
+    # ---- hist-base on the device -----------------------------------------------------
+    def hist_base(self, records: np.ndarray, measures, cap: int = 1 << 20):
+        """bmc_hist_base: `measures` = [(kind, seat, suit), ...] (kinds: _lib.M_*).  Returns hist-base rows
+        [[[m1, .., mk], count], ...] in first-seen order of `records` (bridge.cl:1325-1330)."""
+        rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
+        k = len(measures)
+        marr = (_lib.Measure * k)(*[_lib.Measure(int(m[0]), int(m[1]), int(m[2]) if len(m) > 2 else 0, 0) for m in measures])
+        tuples = np.empty((cap, k), dtype=np.uint8)
+        counts = np.empty(cap, dtype=np.uint64)
+        nu = C.c_uint64()
+        check(self._L.bmc_hist_base(self._h, rec.ctypes.data if rec.shape[0] else None, rec.shape[0], marr, k,
+                                    tuples.ctypes.data, counts.ctypes.data, cap, C.byref(nu)))
+        return [[[int(x) for x in tuples[i]], int(counts[i])] for i in range(nu.value)]
+
     # ---- measurement --------------------------------------------------------------
     def int_peak(self):
         ops = C.c_double()

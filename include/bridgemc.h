@@ -225,6 +225,18 @@ int bmc_score_tally(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *
                     uint64_t *tricks_hist /*[n_contracts][14]*/, uint64_t *imp_hist /*[n_pairs][49]*/,
                     int32_t *score_table /*[n_contracts][14]*/);
 
+/* ---- hist-base over measure tuples (bridge.cl:1325-1330; feeds hist-breakdown / hist-percent) ---- */
+/* A measure yields one byte per deal; seat 0..3 = N E S W ("seat and its partner" for the pair measures).
+ * kind: 0 HCP  1 suit length  2 suit HCP  3 losers  4 balanced?  5 line-hcp (bridge.cl:3238-3240)
+ *       6 trump-length (bridge.cl:3083-3086)  7 sorted-shape class (suit-distribution, bridge.cl:1438-1439;
+ *       see bmc_shape_table)  8 longest-suit of the pair, later suit wins ties (bridge.cl:3030-3036). */
+typedef struct { uint8_t kind, seat, suit, reserved; } bmc_measure;
+/* Evaluates the k (<= 8) measures on every deal, counts equal tuples and returns them in FIRST-SEEN order
+ * of `records` -- hist-base's output for the rows (m1 .. mk): tuples[i*k + j], counts[i], i < *n_unique.
+ * BMC_E_CAPACITY (with *n_unique set) if more than `cap` distinct tuples exist. */
+int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc_measure *measures, uint32_t k,
+                  uint8_t *tuples, uint64_t *counts, uint64_t cap, uint64_t *n_unique);
+
 /* ---- measurement helpers -------------------------------------------------- */
 /* INT32 issue-rate microbenchmark (IMAD + LOP3/IADD3 chains on every SM):
  * returns thread-level integer ops per second in *ops_per_s. */

@@ -357,3 +357,33 @@ def test_reentrancy_across_threads(engine):
         assert np.array_equal(got[i], want[i])
     for e in own:
         e.close()
+
+
+def test_device_hist_base_matches_the_host_mirror(engine):
+    """bmc_hist_base = hist-base (bridge.cl:1325-1330) over device-evaluated measure tuples: same rows, same
+    first-seen order, same counts as the host mirror on rows built from the oracle's features; then the tree"""
+    from bridge_mc_b200 import _lib as L
+    from bridge_mc_b200._lib import shape_table
+    rec, _, _ = engine.sample(None, n_raw=5_000, seed=61)          # the host mirror is O(n x distinct), like the reference
+    rec = rec[np.lexsort((rec[:, 0], rec[:, 1]))]
+    m = seat_masks(rec)
+    f = O.features_batch(m.reshape(-1)).reshape(-1, 4, 11)
+    shapes = [tuple(r) for r in shape_table().tolist()]
+    measures = [(L.M_HCP, 2), (L.M_LEN, 2, 3), (L.M_LINE_HCP, 0), (L.M_TRUMP_LEN, 0, 3), (L.M_BALANCED, 2), (L.M_LOSERS, 1),
+                (L.M_SHAPE, 3), (L.M_LONGEST, 0)]
+    rows = []
+    for i in range(rec.shape[0]):
+        comb = [int(f[i, 0, s] + f[i, 2, s]) for s in range(4)]
+        longest = max(range(4), key=lambda s: (comb[s], s))
+        rows.append([int(f[i, 2, 8]), int(f[i, 2, 3]), int(f[i, 0, 8] + f[i, 2, 8]), comb[3], int(f[i, 2, 10]), int(f[i, 1, 9]),
+                     shapes.index(tuple(sorted((int(x) for x in f[i, 3, 0:4]), reverse=True))), longest])
+    for k in (1, 2, 4, 8):
+        got = engine.hist_base(rec, measures[:k])
+        want = hist.hist_base([r[:k] for r in rows])
+        assert got == want, k
+    tree = hist.histogram([r[:2] for r in rows])
+    tree_dev = hist.hist_percent(hist.hist_breakdown(engine.hist_base(rec, measures[:2])))
+    assert tree == tree_dev
+    with pytest.raises(Exception):
+        engine.hist_base(rec, measures[:4], cap=10)
+    assert engine.hist_base(np.empty((0, 2), np.uint64), measures[:1]) == []
