@@ -63,7 +63,7 @@ assert FEATURE_DTYPE.itemsize == 12
 
 EXPORTS = [
     "bmc_init", "bmc_shutdown", "bmc_last_error", "bmc_version", "bmc_host_alloc", "bmc_host_free",
-    "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_set_jit", "bmc_constraints_jit_ms", "bmc_constraints_mode", "bmc_constraints_primary",
+    "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_set_jit", "bmc_constraints_jit_ms", "bmc_constraints_mode", "bmc_constraints_primary", "bmc_constraints_primary_hcp",
     "bmc_scheme_create",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
     "bmc_match_points", "bmc_score_tally", "bmc_hist_base", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
@@ -103,6 +103,7 @@ def load():
     L.bmc_constraints_jit_ms.restype = C.c_float
     L.bmc_constraints_mode.argtypes = [vp]
     L.bmc_constraints_primary.argtypes = [vp]
+    L.bmc_constraints_primary_hcp.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.bmc_scheme_create.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.bmc_scheme_size.argtypes = [vp]
     L.bmc_scheme_destroy.argtypes = [vp]

@@ -396,6 +396,8 @@ struct bmc_constraints {
     std::vector<uint32_t> code;
     uint32_t *d_code = nullptr;
     int d_device = -1;
+    uint32_t tab_off = 0;        // seat-first class table: word offset in `code`
+    int sf_hcp[2] = {0, 37};     // the HCP window the table was built for (primary seat)
     bool has_cons = false;
     bool has_fixed = false;
     FixDev fix{};
@@ -588,6 +590,55 @@ static void ranges_to_seatc(const SeatRanges &r, SeatC &c)
     }
 }
 
+// Class table of the seat-first stage A1 (seatfirst.cuh): the 625 honour-count classes (nJ nQ nK nA) of a
+// 13-card hand, those with hcp_lo <= HCP <= hcp_hi first, each with S * (weight before it), its counts,
+// I = product of C(4, n.) and floor(2^32 / I).  Appended to the code buffer (16-byte aligned).
+static void build_rank_table(bmc_constraints *c, int hcp_lo, int hcp_hi)
+{
+    static const uint64_t C4[5] = {1, 4, 6, 4, 1};
+    uint64_t C36[14];
+    C36[0] = 1;
+    for (int m = 1; m <= 13; ++m) C36[m] = C36[m - 1] * (uint64_t)(36 - m + 1) / (uint64_t)m;
+    const uint64_t N = 635013559600ull;                               // C(52,13)
+    const uint64_t S = (uint64_t)((((unsigned __int128)1) << 64) / N);
+    struct Cls { uint32_t info, magic; uint64_t w; };
+    std::vector<Cls> acc, rej;
+    for (int id = 0; id < 625; ++id) {
+        const int nJ = id % 5, nQ = (id / 5) % 5, nK = (id / 25) % 5, nA = id / 125, n = nJ + nQ + nK + nA;
+        if (n > 13) continue;
+        const uint64_t I = C4[nJ] * C4[nQ] * C4[nK] * C4[nA];
+        const int hcp = nJ + 2 * nQ + 3 * nK + 4 * nA;
+        Cls k;
+        k.info = (uint32_t)nJ | ((uint32_t)nQ << 3) | ((uint32_t)nK << 6) | ((uint32_t)nA << 9) | ((uint32_t)I << 12);
+        k.magic = I == 1 ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / I);
+        k.w = I * C36[13 - n];
+        (hcp >= hcp_lo && hcp <= hcp_hi ? acc : rej).push_back(k);
+    }
+    while (c->code.size() & 3u) c->code.push_back(enc(OP_END));
+    c->tab_off = (uint32_t)c->code.size();
+    uint64_t cum = 0;
+    int entries = 0;
+    auto emit = [&](const Cls &k) {
+        const uint64_t v = cum * S;
+        c->code.push_back((uint32_t)v); c->code.push_back((uint32_t)(v >> 32));
+        c->code.push_back(k.info); c->code.push_back(k.magic);
+        cum += k.w;
+        ++entries;
+    };
+    for (const Cls &k : acc) emit(k);
+    const uint64_t w_acc = cum;
+    for (const Cls &k : rej) emit(k);
+    for (; entries < RANK_TAB_ENTRIES; ++entries) {
+        c->code.push_back(0xFFFFFFFFu); c->code.push_back(0xFFFFFFFFu); c->code.push_back(1u << 12); c->code.push_back(0xFFFFFFFFu);
+    }
+    uint32_t top = 0;
+    if (acc.size() > 1) { top = 1; while (2u * top <= (uint32_t)acc.size() - 1u) top *= 2u; }
+    c->dev.sf_top = top;
+    c->dev.sf_theta = w_acc * S;
+    c->dev.sf_void_lo = (uint32_t)(N * S);            // the high word of N * S is 0xFFFFFFFF (N < 2^40)
+    c->sf_hcp[0] = hcp_lo; c->sf_hcp[1] = hcp_hi;
+}
+
 int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules[4], bmc_constraints **out)
 {
     if (!out) return fail(BMC_E_INVALID, "out is NULL");
@@ -677,6 +728,10 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     for (int k = 0; k < 4; ++k)
         if (c->dev.seat[k].active && selectivity[k] < best) { best = selectivity[k]; c->dev.primary = (uint32_t)k; }
     c->code.push_back(enc(OP_END));
+    if (c->has_cons) {
+        const uint32_t ls = c->dev.seat[c->dev.primary].hcp_lo_span;
+        build_rank_table(c.get(), (int)(ls & 0xFFu), (int)((ls & 0xFFu) + (ls >> 8)));
+    }
     if (c->has_fixed && is_fixed[0] && is_fixed[1] && is_fixed[2] && is_fixed[3])
         return fail(BMC_E_INVALID, "all four hands are fixed: nothing to deal");
     fixdev_init(c->fix, fixed_mask, is_fixed);
@@ -783,6 +838,13 @@ int bmc_constraints_set_reference_order(bmc_constraints *c, int n_defs)
 }
 int bmc_constraints_mode(const bmc_constraints *c) { return c ? c->resolved : 0; }
 int bmc_constraints_primary(const bmc_constraints *c) { return c ? (int)c->dev.primary : -1; }
+int bmc_constraints_primary_hcp(const bmc_constraints *c, int32_t *lo, int32_t *hi)
+{
+    if (!c || !lo || !hi) return fail(BMC_E_INVALID, "bmc_constraints_primary_hcp: NULL argument");
+    *lo = c->sf_hcp[0];
+    *hi = c->sf_hcp[1];
+    return BMC_OK;
+}
 
 void bmc_constraints_destroy(bmc_constraints *c)
 {
@@ -895,6 +957,7 @@ static int cons_upload(bmc_ctx *ctx, const bmc_constraints *cc, ConsDev &dev)
     }
     dev = c->dev;
     dev.code = c->d_code;
+    dev.sf_tab = reinterpret_cast<const uint4 *>(c->d_code + c->tab_off);
     return BMC_OK;
 }
 
@@ -975,12 +1038,18 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
     if (seq) blocks = ctx->sms * 4;
     if (jit) blocks = ctx->sms * jit->blocks_per_sm;
-    const uint64_t per_thread = seatfirst ? SF_ILP : 1;           // raw deals per thread per iteration
+    const uint64_t per_thread = seatfirst ? 2 : 1;                // raw deals per thread per iteration
     const uint64_t per_iter = (uint64_t)blocks * THREADS * per_thread;
     if (n < per_iter) blocks = (int)((n + THREADS * per_thread - 1) / (THREADS * per_thread));
     if (blocks < 1) blocks = 1;
     const uint64_t chunk = (uint64_t)blocks * THREADS * per_thread;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
+    if (seatfirst) {
+        // a lane owns the index PAIRS (2p, 2p + 1): an odd first index or an odd end adds one pair
+        const uint64_t pairs = ((first + n + 1) >> 1) - (first >> 1);
+        const uint64_t per = (uint64_t)blocks * THREADS;
+        a.iters = (uint32_t)((pairs + per - 1) / per);
+    }
     if (jit) {
         void *params[] = {&a};
         const CUresult cr = JitApi::get().LaunchKernel(jit->func, (unsigned)blocks, 1, 1, THREADS, 1, 1, 0, (CUstream)ctx->stream, params, nullptr);

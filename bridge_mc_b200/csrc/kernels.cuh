@@ -27,8 +27,12 @@ struct ConsDev {
     uint32_t primary;        // seat tested in stage A
     uint32_t b1_mask;        // seat-first mode: seats fully tested right after the deal is completed (0xF: all of them);
                              // the others are tested after one more compaction
-    uint32_t pad;
+    uint32_t sf_top;         // seat-first stage A1: first step of the class search (a power of two, 0: one class)
     const uint32_t *code;    // device pointer, programs of all seats
+    const uint4 *sf_tab;     // seat-first stage A1: class table of the primary seat (seatfirst.cuh), in the code buffer
+    unsigned long long sf_theta;   // u < sf_theta: the honour holding has an admissible HCP
+    uint32_t sf_void_lo;     // u >= 0xFFFFFFFF:sf_void_lo voids the index (u beyond S * C(52,13))
+    uint32_t pad;
 };
 
 // shared-memory histogram (per warp): hcp[4][40] | len[4][4][16] | shape[4][40]
@@ -47,7 +51,7 @@ struct SampleArgs {
     uint64_t cap;
     unsigned long long *tallies;   // bmc_tallies as u64 words
     uint32_t tally_mask;
-    uint32_t iters;          // warp-iterations per warp
+    uint32_t iters;          // warp-iterations per warp (seat-first: each covers one pair of indices per lane)
     uint32_t sf_q0;          // seat-first mode: initial Q of stage B (capacity 0 for the primary seat)
     uint32_t pad;
 };
@@ -223,23 +227,20 @@ __device__ __forceinline__ void sample_body(const SampleArgs &a)
 }
 
 // ---------------------------------------------------------------------------
-// K1b: seat-first sampler (seatfirst.cuh): stages A1 -> A2 -> B with two per-warp
-// compaction queues, so each stage runs on full warps.
+// K1b: seat-first sampler (seatfirst.cuh): stages A1 -> A2 -> B1 -> B2 with per-warp
+// compaction queues between them, so each stage runs on full warps.
 // ---------------------------------------------------------------------------
 #ifndef SF_MIN_BLOCKS
 #define SF_MIN_BLOCKS 6
 #endif
 constexpr int SF_HIST_COPIES = 2;
-#ifndef SF_ILP
-#define SF_ILP 1
-#endif
 __constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
                                         thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
 
 __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
 {
     __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];   // stage B is rare here: few copies suffice
-    __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (H | r << 16, idx_lo, idx_hi, -)
+    __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (u_lo, u_hi, idx_lo, idx_hi)
     __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, idx_lo, idx_hi)
     __shared__ uint4 s_q3[WARPS_PER_BLOCK][QCAP];     // B1 survivors: complete deals (planes)
     __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
@@ -256,7 +257,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     const uint32_t b1_mask = a.cons.b1_mask & 0xFu, b2_mask = ~b1_mask & 0xFu;
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    uint32_t n_raw = 0, n_void = 0;                  // per thread: at most `iters` each
+    uint32_t n_void = 0;                             // per thread
     unsigned h1 = 0, t1 = 0, h2 = 0, t2 = 0;         // queue cursors, warp-uniform
     const uint32_t P = a.cons.primary;
     const SeatC &c = a.cons.seat[P];
@@ -292,88 +293,78 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
             }
         }
     };
-    // ---- stage A2 on up to 32 queued honour sets ---------------------------------------
+    // ---- stage A2 on up to 32 queued survivors of the HCP test ----------------------------
     auto run_a2 = [&](unsigned count) {
-        const uint4 r = q1[(h1 + lane) % QCAP];
+        const uint4 r = q1[(h1 + lane) % QCAP];       // (u_lo, u_hi, idx_lo, idx_hi)
         h1 += count;
         __syncwarp();
         const bool active = lane < count;
+        const uint32_t H = sf_unrank_honours(a.cons.sf_tab, a.cons.sf_top, r.x, r.y);
         bool voided = false;
         uint32_t m0, m1;
-        sf_lows(a.key, r.y, r.z, r.x & 0xFFFFu, (int)(r.x >> 16), voided, m0, m1);
+        sf_lows(a.key, r.z, r.w, H, 13 - (int)__popc(H), voided, m0, m1);
         n_void += (active && voided) ? 1u : 0u;
         const Feat f = hand_features(m0, m1);
         const bool ok = active && !voided && seat_ranges_ok(c, f);
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
-            if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, r.y, r.z);
+            if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, r.z, r.w);
             t2 += __popc(bal);
             __syncwarp();
-            if (t2 - h2 >= 32u) run_b(32u);
         }
     };
 
-    // Each thread draws SF_ILP independent deals per iteration (two interleaved dependency chains keep
-    // both integer pipes fed).  Only the last iteration can hold indices past the end.
-    const unsigned long long stride = total_warps * (32ull * SF_ILP);
-    unsigned long long off = gwarp * (32ull * SF_ILP) + lane;
-    const uint32_t full_iters = (uint32_t)(a.n / stride);
-    const uint32_t hcp_lo = c.hcp_lo_span & 0xFFu, hcp_span = c.hcp_lo_span >> 8;
-    const bool need_power = (c.need & 2u) != 0u;
-    for (uint32_t it = 0; it < a.iters; ++it, off += stride) {
-        SeatFirstState s[SF_ILP];
-        uint32_t H[SF_ILP];
-        bool ok[SF_ILP];
-#pragma unroll
-        for (int j = 0; j < SF_ILP; ++j) {
-            const unsigned long long idx = a.first + off + 32ull * j;
-            H[j] = sf_honours(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), s[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < SF_ILP; ++j) {
-            const bool valid = it < full_iters || off + 32ull * j < a.n;
-            n_raw += (it >= full_iters && valid) ? 1u : 0u;
-            n_void += (valid && s[j].voided) ? 1u : 0u;
-            ok[j] = valid && !s[j].voided && (honour_hcp(H[j]) - hcp_lo) <= hcp_span;
-            if (need_power) {
-                uint32_t Pw, hcp;
-                honour_features(H[j], Pw, hcp);
-                ok[j] = ok[j] && in_ranges(Pw, c.A[1], c.B[1]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < SF_ILP; ++j) {
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok[j]);
+    // Stage A1.  One Philox call yields the 64-bit uniforms of the two indices of a pair (2p, 2p + 1);
+    // a lane owns one pair per iteration and handles its two indices in consecutive sub-steps, so the
+    // survivor queue never receives more than 32 entries between two drains.
+    const unsigned long long stride = total_warps * 32ull;                     // pairs per iteration of the grid
+    unsigned long long pair = (a.first >> 1) + gwarp * 32ull + lane;            // absolute pair number
+    unsigned long long off = 2ull * (gwarp * 32ull + lane) - (a.first & 1ull);  // index - a.first (wraps below 0)
+    const uint32_t steps = 2u * a.iters;
+    const unsigned long long theta = a.cons.sf_theta;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t st = 0;; ++st) {
+        const bool fin = st >= steps;
+        if (!fin) {
+            const uint32_t j = st & 1u;
+            if (j == 0u) philox4x32_10(a.key, (uint32_t)pair, (uint32_t)(pair >> 32), 0u, STREAM_SEATFIRST_RANK, w);
+            const uint32_t u_lo = j ? w[2] : w[0], u_hi = j ? w[3] : w[1];
+            const bool valid = off + j < a.n;
+            const bool ok = valid && ((((unsigned long long)u_hi) << 32) | u_lo) < theta;
+            if (u_hi == 0xFFFFFFFFu && valid && u_lo >= a.cons.sf_void_lo) ++n_void;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
             if (bal) {
-                const unsigned long long idx = a.first + off + 32ull * j;
-                if (ok[j]) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] =
-                               make_uint4(H[j] | ((uint32_t)s[j].r << 16), (uint32_t)idx, (uint32_t)(idx >> 32), 0u);
+                const unsigned long long idx = 2ull * pair + j;
+                if (ok) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(u_lo, u_hi, (uint32_t)idx, (uint32_t)(idx >> 32));
                 t1 += __popc(bal);
                 __syncwarp();
-                if (t1 - h1 >= 32u) run_a2(32u);
             }
+            if (j) { pair += stride; off += 2ull * stride; }
         }
+        // drain the queues: full warps while the stream lasts, whatever is left at the end
+        for (;;) {
+            const unsigned n1 = t1 - h1;
+            const bool do_a2 = n1 >= 32u || (fin && n1 != 0u);
+            if (do_a2) run_a2(n1 < 32u ? n1 : 32u);
+            const unsigned n2 = t2 - h2;
+            const bool do_b = n2 >= 32u || (fin && n2 != 0u && t1 == h1);
+            if (do_b) run_b(n2 < 32u ? n2 : 32u);
+            if (!do_a2 && !do_b) break;
+        }
+        if (fin) break;
     }
-    if (t1 - h1) run_a2(t1 - h1);
-    if (t2 - h2) run_b(t2 - h2);
     if (t3 - h3) {
         const uint4 r3 = q3[(h3 + lane) % QCAP];
         const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
         stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, s_feat[warp], b2_mask);
     }
-    n_raw += full_iters * SF_ILP;
 
     {
-        unsigned long long r64 = n_raw, v64 = n_void;
+        unsigned long long v64 = n_void;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            r64 += __shfl_xor_sync(0xFFFFFFFFu, r64, o);
-            v64 += __shfl_xor_sync(0xFFFFFFFFu, v64, o);
-        }
-        if (lane == 0) {
-            atomicAdd(&a.tallies[0], r64);
-            if (v64) atomicAdd(&a.tallies[1], v64);
-        }
+        for (int o = 16; o > 0; o >>= 1) v64 += __shfl_xor_sync(0xFFFFFFFFu, v64, o);
+        if (lane == 0 && v64) atomicAdd(&a.tallies[1], v64);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.tallies[0], a.n);   // the grid covers exactly [first, first + n)
     }
     __syncthreads();
     flush_hist(a, &s_hist[0][0], SF_HIST_COPIES);

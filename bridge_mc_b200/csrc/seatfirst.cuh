@@ -5,8 +5,10 @@
 // and a constraint that rejects most deals on the primary seat alone never needs
 // the later factors.  The sampler therefore runs three stages with a warp-level
 // compaction queue between them, so every stage executes on full warps:
-//   A1  16 honour cards, primary seat vs the rest (1 Philox call)  -> HCP / suit-HCP ranges
-//   A2  36 low cards, primary seat vs the rest (2 Philox calls)     -> all ranges of the seat
+//   A1  the RANK of the primary seat's honour holding in an order that puts the holdings with an
+//       admissible HCP first (half a Philox call, one 64-bit compare)   -> HCP range
+//   A2  unrank the honours, then 36 low cards, primary seat vs the rest (2 Philox calls)
+//                                                                   -> all ranges of the seat
 //   B   the other 39 cards to the other three seats (deal_fixed with the primary
 //       hand as a per-lane fixed hand, 3 Philox calls)            -> every seat's full test
 // Each factor is sampled exactly (mixed-radix digits + Lemire rejection, see
@@ -14,6 +16,16 @@
 // constraint -- the same distribution as dealing all 52 cards and rejecting.
 // Mirrored bit for bit by orc_gpu_seatfirst_hand / orc_gpu_deal_fixed in
 // oracle/bmc_oracle.c.
+//
+// Stage A1 in detail.  A 13-card hand holds nJ jacks, nQ queens, nK kings and nA aces with
+// probability w / C(52,13), w = C(4,nJ) C(4,nQ) C(4,nK) C(4,nA) C(36, 13 - nJ - nQ - nK - nA), and its
+// HCP is nJ + 2 nQ + 3 nK + 4 nA: the 625 count classes are laid out on [0, C(52,13)) with the
+// classes whose HCP lies in the seat's range FIRST.  One 64-bit uniform u then decides the HCP
+// test by a single compare (u < theta = S * weight of the admitted classes, S = floor(2^64 /
+// C(52,13))); only the survivors look their class up (binary search over the scaled cumulative
+// weights), take the identity of the honours from the exactly uniform residual (u - S cum) mod
+// I, I = C(4,nJ) C(4,nQ) C(4,nK) C(4,nA), and go on to deal the low cards.  u >= S C(52,13)
+// (probability 3e-8) voids the index, so every class keeps its exact probability.
 //
 // Binary step (seat gets the card iff u < r, r = cards the seat still needs):
 //     d = u - r ; mask = (mask << 1) | sign(d) ; r += d >> 31        (4 instructions with the digit)
@@ -88,32 +100,49 @@ __device__ __forceinline__ void sf_steps(const PhiloxKey &key, uint32_t idx_lo, 
     (sf_step<Base + K>(key, idx_lo, idx_hi, s), ...);
 }
 
-// Stage A1: returns H (bit h = honour h = 4*suit + (rank-9)), leaves the RNG state for A2.
-__device__ __forceinline__ uint32_t sf_honours(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s)
+// ---- stage A1, rank form -----------------------------------------------------------
+constexpr uint32_t STREAM_SEATFIRST_RANK = 4u;
+constexpr int RANK_TAB_ENTRIES = 1024;      // 625 classes at most, padded for the branch-free search
+
+// Table entry (uint4): x,y = S * (weight of the classes before this one) as lo,hi;
+// z = nJ | nQ<<3 | nK<<6 | nA<<9 | I<<12;  w = floor(2^32 / I) (2^32 - 1 for I = 1).
+// Returns H: bit 4*suit + level (J Q K A = 0..3) set where the seat holds that honour.
+__device__ __forceinline__ uint32_t sf_unrank_honours(const uint4 *__restrict__ tab, uint32_t top, uint32_t u_lo, uint32_t u_hi)
 {
-    s.x = 0; s.mask = 0; s.r = 13; s.voided = false;
-    sf_steps<0>(key, idx_lo, idx_hi, s, make_iseq<16>{});
-    return s.mask & 0xFFFFu;
+    const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
+    uint32_t pos = 0;
+    for (uint32_t s = top; s != 0u; s >>= 1) {           // warp-uniform trip count
+        const uint2 c = __ldg(reinterpret_cast<const uint2 *>(tab + pos + s));
+        if ((((unsigned long long)c.y << 32) | c.x) <= u) pos += s;
+    }
+    const uint4 e = __ldg(tab + pos);
+    const unsigned long long d = u - ((((unsigned long long)e.y) << 32) | e.x);   // uniform on [0, S * I * C(36, m))
+    const uint32_t info = e.z, magic = e.w, I = (info >> 12) & 0x7FFu;
+    auto mod_i = [&](uint32_t x) {                        // x mod I, I <= 1296
+        const uint32_t r = x - __umulhi(x, magic) * I;
+        return r >= I ? r - I : r;
+    };
+    const uint32_t c32 = 0u - magic * I;                  // 2^32 mod I (1 instead of 0 for I = 1: harmless)
+    uint32_t i = mod_i(mod_i((uint32_t)(d >> 32)) * c32 + mod_i((uint32_t)d));
+    uint32_t H = 0;
+#pragma unroll
+    for (int lev = 0; lev < 4; ++lev) {
+        const uint32_t c = (info >> (3 * lev)) & 7u;                  // honours of this level in the hand
+        const uint32_t r = (0x14641u >> (4u * c)) & 15u;              // C(4, c)
+        const uint32_t M = r == 1u ? 65536u : (r == 4u ? 16384u : 10923u);
+        const uint32_t q = (i * M) >> 16;                             // i / r, exact for i < 1296
+        const uint32_t dg = i - q * r;
+        i = q;
+        const uint32_t off = (0xFB510u >> (4u * c)) & 15u;            // first subset of size c in the nibble list
+        const uint32_t m4 = (uint32_t)(0xFEDB7CA965384210ull >> (4u * (off + dg))) & 15u;   // which suits
+        const uint32_t sp = (((m4 * 0x41u) & 0x303u) * 9u) & 0x1111u; // spread: suit s -> bit 4 s (no carries)
+        H |= sp << lev;
+    }
+    return H;
 }
 
-// HCP alone from the honour mask: J1 Q2 K3 A4 over the four suit nibbles (XU pipe is idle here).
-__device__ __forceinline__ uint32_t honour_hcp(uint32_t H)
-{
-    return __popc(H & 0x1111u) + 2u * __popc(H & 0x2222u) + 3u * __popc(H & 0x4444u) + 4u * __popc(H & 0x8888u);
-}
-
-// Features available after A1: power bytes (c d h s) and HCP.
-__device__ __forceinline__ void honour_features(uint32_t H, uint32_t &P, uint32_t &hcp)
-{
-    const uint32_t M = 0x01010101u;
-    const uint32_t X = (H & 0xFu) | ((H & 0xF0u) << 4) | ((H & 0xF00u) << 8) | ((H & 0xF000u) << 12);
-    const uint32_t J = X & M, Qn = (X >> 1) & M, K = (X >> 2) & M, A = (X >> 3) & M;
-    P = J + 2u * Qn + 3u * K + 4u * A;
-    hcp = (P * M) >> 24;
-}
-
-// Stage A2: continues from the A1 state (H, r, voided restored by the caller); returns the
-// seat's hand as lane-layout words.
+// Stage A2: 36 low cards given the honours H (r = 13 - popc(H) cards still needed), Philox stream 2
+// blocks 1 and 2; returns the seat's hand as lane-layout words.
 __device__ __forceinline__ void sf_lows(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, uint32_t H, int r, bool &voided,
                                         uint32_t &m0, uint32_t &m1)
 {

@@ -99,6 +99,13 @@ class Constraints:
     def primary(self) -> int:
         return _lib.load().bmc_constraints_primary(self._h)
 
+    @property
+    def primary_hcp(self):
+        """(lo, hi): the HCP window of the primary seat that mode 2 orders the honour holdings by"""
+        lo, hi = C.c_int32(), C.c_int32()
+        check(_lib.load().bmc_constraints_primary_hcp(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:

@@ -139,12 +139,15 @@ void bmc_constraints_destroy(bmc_constraints *c);
 /* How raw deals are drawn (both are exactly uniform; they consume the Philox stream
  * differently, so the deal behind a given index depends on the mode):
  *   1 full deal   all 52 cards, then test (best when most deals pass the primary seat)
- *   2 seat-first  the primary (most selective) seat's honours, then its low cards, then
+ *   2 seat-first  the primary (most selective) seat's honour holding (drawn by rank, holdings with
+ *                 an admissible HCP first: one compare per raw index), then its low cards, then
  *                 the other three hands -- each stage only for survivors of the previous one
  *   0 auto        (default) calibrates the primary seat's pass rate on 2^16 deals at the
  *                 first sampling call and picks 2 when it is below 0.30.
  * bmc_constraints_mode returns the resolved mode (0 before the first call),
- * bmc_constraints_primary the seat tested first. */
+ * bmc_constraints_primary the seat tested first, bmc_constraints_primary_hcp the HCP window of
+ * that seat (its range after the rule form's ranges were absorbed) that stage A1 of mode 2 orders
+ * the honour holdings by -- together with the seed they determine the deal behind an index. */
 int  bmc_constraints_set_mode(bmc_constraints *c, int mode);
 /* Mode 3, "reference order": reproduce `build`'s OWN multi-seat semantics (bridge.cl:1292-1319)
  * instead of the uniform distribution over valid deals: after the fixed hands (which must occupy
@@ -164,6 +167,7 @@ int  bmc_constraints_set_jit(bmc_constraints *c, int on);
 float bmc_constraints_jit_ms(const bmc_constraints *c);
 int  bmc_constraints_mode(const bmc_constraints *c);
 int  bmc_constraints_primary(const bmc_constraints *c);
+int  bmc_constraints_primary_hcp(const bmc_constraints *c, int32_t *lo, int32_t *hi);
 
 /* A rule table as printed by Lisp: "(((2 C) . FORM) ((2 NT) . FORM) ...)" --
  * `openings`, (nt-responses n), 2C-responses, (basic-responses bid) ...

@@ -718,64 +718,115 @@ ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fix
     return gpu_deal_fixed_stream(seed, index, fixed, 0, lo_plane, hi_plane);
 }
 
-/* CPU mirror of the seat-first sampler (csrc/seatfirst.cuh).  Stage A: the
- * primary seat's hand, 52 binary steps (16 honours spade-A-first, then 36 low
- * cards spade-10-first), Philox stream 2.  Returns the hand as a lane mask and
- * sets *voided: bit 0 = a Lemire check failed in A1 (honours), bit 1 = in A2 (low cards). */
+/* CPU mirror of the seat-first sampler (csrc/seatfirst.cuh).
+ * Stage A1: the honour holding of the primary seat is drawn BY RANK.  The 625 count classes
+ * (nJ nQ nK nA), weight C(4,nJ) C(4,nQ) C(4,nK) C(4,nA) C(36, 13 - n), are laid out on
+ * [0, C(52,13)) with the classes whose HCP lies in [hcp_lo, hcp_hi] first (ascending class id
+ * nJ + 5 nQ + 25 nK + 125 nA within each group); u = 64 bits of Philox stream 4 (counter =
+ * index >> 1, words 2 (index & 1) and 2 (index & 1) + 1), rank = u / S with S = floor(2^64 /
+ * C(52,13)); u >= S C(52,13) voids the index.  The identity of the honours comes from
+ * (u - S cum) mod I, I = product of the C(4, n.), as mixed-radix digits J first.
+ * Stage A2: 36 low cards (spade 10 first ... club 2 last), binary steps on Philox stream 2
+ * blocks 1 and 2.  Returns the hand as a lane mask; *voided: bit 0 = void in A1, bit 1 = in A2;
+ * *a1_pass = 1 when the class has an admissible HCP (the index survives stage A1). */
 static const int SF_HI[11] = {52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9};
 static const int SF_LO[11] = {49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2};
-ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int *voided)
+static const uint8_t SUBSETS4[5][6] = { {0}, {1, 2, 4, 8}, {3, 5, 6, 9, 10, 12}, {7, 11, 13, 14}, {15} };
+ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int hcp_lo, int hcp_hi, int *voided, int *a1_pass)
 {
+    static const uint64_t C4[5] = {1, 4, 6, 4, 1};
+    const uint64_t N = 635013559600ull;
+    const uint64_t S = (uint64_t)((((unsigned __int128)1) << 64) / N);
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-    uint32_t w[4] = {0, 0, 0, 0}, x = 0;
-    int r = 13, vd = 0;
-    uint64_t hand = 0;
-    for (int i = 0; i < 52; ++i) {
-        int n = 52 - i, u = 0;
+    uint32_t w[4];
+    uint64_t pair = index >> 1;
+    uint32_t ctr[4] = { (uint32_t)pair, (uint32_t)(pair >> 32), 0, 4 };
+    orc_philox4x32_10(ctr, key, w);
+    const int j = (int)(index & 1);
+    const uint64_t u = ((uint64_t)w[2 * j + 1] << 32) | w[2 * j];
+    int vd = 0;
+    *a1_pass = 0;
+    if (u >= N * S) { *voided = 1; return 0; }
+    const uint64_t R = u / S;
+    /* walk the classes in table order: admitted ones first */
+    uint64_t cum = 0, hand = 0;
+    int found = 0;
+    for (int group = 0; group < 2 && !found; ++group)
+        for (int id = 0; id < 625 && !found; ++id) {
+            int c[4] = { id % 5, (id / 5) % 5, (id / 25) % 5, id / 125 };
+            int n = c[0] + c[1] + c[2] + c[3];
+            if (n > 13) continue;
+            int hcp = c[0] + 2 * c[1] + 3 * c[2] + 4 * c[3];
+            int admitted = hcp >= hcp_lo && hcp <= hcp_hi;
+            if (admitted != (group == 0)) continue;
+            uint64_t I = C4[c[0]] * C4[c[1]] * C4[c[2]] * C4[c[3]];
+            uint64_t lows = 1;                                   /* C(36, 13 - n) */
+            for (int t = 1; t <= 13 - n; ++t) lows = lows * (uint64_t)(36 - t + 1) / (uint64_t)t;
+            uint64_t wgt = I * lows;
+            if (R < cum + wgt) {
+                uint64_t i = (u - cum * S) % I;
+                for (int lev = 0; lev < 4; ++lev) {
+                    uint64_t r = C4[c[lev]];
+                    int m4 = SUBSETS4[c[lev]][i % r];
+                    i /= r;
+                    for (int su = 0; su < 4; ++su)
+                        if ((m4 >> su) & 1) hand |= 1ull << (16 * su + 9 + lev);
+                }
+                *a1_pass = admitted;
+                found = 1;
+            }
+            cum += wgt;
+        }
+    int r = 13 - __builtin_popcountll(hand);
+    uint32_t x = 0;
+    for (int i = 16; i < 52; ++i) {
+        int n = 52 - i, d = 0;
         if (n >= 2) {
             int g = 0;
             while (!(n <= SF_HI[g] && n >= SF_LO[g])) ++g;
             if (n == SF_HI[g]) {
                 if ((g & 3) == 0) {
-                    uint32_t ctr[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(g >> 2), 2 };
-                    orc_philox4x32_10(ctr, key, w);
+                    uint32_t c2[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(g >> 2), 2 };
+                    orc_philox4x32_10(c2, key, w);
                 }
                 x = w[g & 3];
             }
             uint64_t p = (uint64_t)x * (uint32_t)n;
-            u = (int)(p >> 32);
+            d = (int)(p >> 32);
             x = (uint32_t)p;
             if (n == SF_LO[g]) {
-                uint64_t N = 1;
-                for (int m = SF_LO[g]; m <= SF_HI[g]; ++m) N *= (uint64_t)m;
-                if (x < (uint32_t)((((uint64_t)1) << 32) % N)) vd |= g < 4 ? 1 : 2;   /* stage A1 : A2 */
+                uint64_t Ng = 1;
+                for (int m = SF_LO[g]; m <= SF_HI[g]; ++m) Ng *= (uint64_t)m;
+                if (x < (uint32_t)((((uint64_t)1) << 32) % Ng)) vd |= 2;
             }
         }
-        if (u < r) {
+        if (d < r) {
             --r;
-            int suit, rank;
-            if (i < 16) { int h = 15 - i; suit = h / 4; rank = 9 + h % 4; }
-            else { int l = 35 - (i - 16); suit = l / 9; rank = l % 9; }
+            int l = 35 - (i - 16), suit = l / 9, rank = l % 9;
             hand |= 1ull << (16 * suit + rank);
         }
     }
     *voided = vd;
     return hand;
 }
-/* Full seat-first deal: primary seat P from stage A, the other 39 cards by the
- * fixed-hand dealer on Philox stream 3.  Return: bit 0 = void in A1, bit 1 = void in A2, bit 2 = void in B. */
-ORC_API int orc_gpu_deal_seatfirst(uint64_t seed, uint64_t index, int primary, uint64_t *lo_plane, uint64_t *hi_plane)
+/* Full seat-first deal: primary seat P from stage A, the other 39 cards by the fixed-hand dealer on
+ * Philox stream 3.  Return: bit 0 = void in A1, bit 1 = void in A2, bit 2 = void in B, bit 3 = the
+ * index passes stage A1 (HCP window). */
+ORC_API int orc_gpu_deal_seatfirst(uint64_t seed, uint64_t index, int primary, int hcp_lo, int hcp_hi,
+                                   uint64_t *lo_plane, uint64_t *hi_plane)
 {
-    int va = 0;
+    int va = 0, pass = 0;
     uint64_t fixed[4] = {0, 0, 0, 0};
-    fixed[primary] = orc_gpu_seatfirst_hand(seed, index, &va);
+    fixed[primary] = orc_gpu_seatfirst_hand(seed, index, hcp_lo, hcp_hi, &va, &pass);
+    if (va & 1) { *lo_plane = 0; *hi_plane = 0; return 1; }
     int vb = gpu_deal_fixed_stream(seed, index, fixed, 3, lo_plane, hi_plane);
-    return va | (vb << 2);
+    return va | (vb << 2) | (pass << 3);
 }
-ORC_API void orc_gpu_deal_seatfirst_batch(uint64_t seed, uint64_t first, uint64_t n, int primary, uint64_t *rec, uint8_t *flags)
+ORC_API void orc_gpu_deal_seatfirst_batch(uint64_t seed, uint64_t first, uint64_t n, int primary, int hcp_lo, int hcp_hi,
+                                          uint64_t *rec, uint8_t *flags)
 {
     for (uint64_t i = 0; i < n; ++i)
-        flags[i] = (uint8_t)orc_gpu_deal_seatfirst(seed, first + i, primary, &rec[2 * i], &rec[2 * i + 1]);
+        flags[i] = (uint8_t)orc_gpu_deal_seatfirst(seed, first + i, primary, hcp_lo, hcp_hi, &rec[2 * i], &rec[2 * i + 1]);
 }
 
 ORC_API void orc_gpu_deal_fixed_batch(uint64_t seed, uint64_t first, uint64_t n, const uint64_t fixed[4],

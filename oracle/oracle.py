@@ -113,7 +113,7 @@ def lib():
     L.orc_gpu_deal_batch.restype = None
     L.orc_gpu_deal_fixed_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64 * 4, C.c_void_p, C.c_void_p]
     L.orc_gpu_deal_fixed_batch.restype = None
-    L.orc_gpu_deal_seatfirst_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_gpu_deal_seatfirst_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_gpu_deal_seatfirst_batch.restype = None
     L.orc_ref_run.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.orc_ref_run.restype = C.c_uint64
@@ -225,12 +225,12 @@ def gpu_deal_fixed_batch(seed: int, first: int, n: int, fixed):
     return rec, void
 
 
-def gpu_deal_seatfirst_batch(seed: int, first: int, n: int, primary: int):
-    """CPU mirror of the seat-first sampler: (records, flags); flags bit0 / bit1 / bit2 = a Lemire check failed in
-    stage A1 / A2 / B."""
+def gpu_deal_seatfirst_batch(seed: int, first: int, n: int, primary: int, hcp=(0, 37)):
+    """CPU mirror of the seat-first sampler for a primary seat with HCP window `hcp`: (records, flags);
+    flags bit0 / bit1 / bit2 = a Lemire check failed in stage A1 / A2 / B, bit 3 = the index passes stage A1."""
     rec = np.empty((n, 2), dtype=np.uint64)
     flags = np.empty(n, dtype=np.uint8)
-    lib().orc_gpu_deal_seatfirst_batch(seed, first, n, primary, rec.ctypes.data, flags.ctypes.data)
+    lib().orc_gpu_deal_seatfirst_batch(seed, first, n, primary, int(hcp[0]), int(hcp[1]), rec.ctypes.data, flags.ctypes.data)
     return rec, flags
 
 

@@ -83,7 +83,7 @@ def mirror_stream(cons, seed, first, n):
     """CPU mirror of the raw stream the sampler draws for `cons` (after its first sampling call):
     (records, void_a, void_b)"""
     if cons is not None and cons.mode == 2:
-        rec, fl = O.gpu_deal_seatfirst_batch(seed, first, n, cons.primary)
+        rec, fl = O.gpu_deal_seatfirst_batch(seed, first, n, cons.primary, cons.primary_hcp)
         return rec, (fl & 3) != 0, (fl & 4) != 0
     rec, void = O.gpu_deal_batch(seed, first, n)
     return rec, void.astype(bool), np.zeros(n, dtype=bool)
@@ -107,10 +107,12 @@ def test_constrained_sampler_equals_filtered_stream(engine, mode):
     if mode == 1:
         assert tal["voided"] == int(va.sum())
     else:
-        _, fl = O.gpu_deal_seatfirst_batch(SEED, 1000, n, 2)
+        assert cons.primary_hcp == (15, 17)
+        _, fl = O.gpu_deal_seatfirst_batch(SEED, 1000, n, 2, (15, 17))
         f = O.features_batch(seat_masks(ref)[:, 2])
-        pass_a1 = (f[:, 8] >= 15) & (f[:, 8] <= 17)                 # stage A1 tests HCP (and suit HCP) only
         v1, v2, v3 = (fl & 1) != 0, (fl & 2) != 0, (fl & 4) != 0
+        pass_a1 = (f[:, 8] >= 15) & (f[:, 8] <= 17) & ~v1            # stage A1 tests the HCP window only
+        assert np.array_equal(pass_a1, (fl & 8) != 0)
         expect = v1.sum() + (~v1 & pass_a1 & v2).sum() + (~v1 & ~v2 & (acc == 1) & v3).sum()
         assert tal["voided"] == int(expect)      # this rule is exactly its ranges: passing stage A2 == accepted
 
@@ -258,9 +260,11 @@ def test_c2_acceptance_rate_exact_seat_first(engine):
     cons = Constraints(None, [None, None, rule, None]).set_mode(2)
     n = 50_000_000
     _, tal, _ = engine.sample(cons, n_raw=n, seed=123, cap=0)
-    hi = [52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9]
-    lo = [49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2]
+    hi = [36, 32, 28, 24, 20, 15, 9]                                 # stage A2: the 36 low cards
+    lo = [33, 29, 25, 21, 16, 10, 2]
+    n_hands = 635013559600
     surv_a = prod(1 - ((1 << 32) % prod(range(l, h + 1))) / 2 ** 32 for h, l in zip(hi, lo))
+    surv_a *= (2 ** 64 // n_hands) * n_hands / 2 ** 64                # stage A1: u beyond S * C(52,13)
     surv_b = prod(1 - ((1 << 32) % prod(m for m in range(39 - 4 * w - 3, 39 - 4 * w + 1) if m >= 2)) / 2 ** 32
                   for w in range(10))
     p = 24235203726 / 635013559600 * surv_a * surv_b
