@@ -1038,7 +1038,7 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
     if (seq) blocks = ctx->sms * 4;
     if (jit) blocks = ctx->sms * jit->blocks_per_sm;
-    const uint64_t per_thread = seatfirst ? 2 : 1;                // raw deals per thread per iteration
+    const uint64_t per_thread = seatfirst ? 2 * SF_PAIRS : 1;     // raw deals per thread per iteration
     const uint64_t per_iter = (uint64_t)blocks * THREADS * per_thread;
     if (n < per_iter) blocks = (int)((n + THREADS * per_thread - 1) / (THREADS * per_thread));
     if (blocks < 1) blocks = 1;
@@ -1047,7 +1047,7 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     if (seatfirst) {
         // a lane owns the index PAIRS (2p, 2p + 1): an odd first index or an odd end adds one pair
         const uint64_t pairs = ((first + n + 1) >> 1) - (first >> 1);
-        const uint64_t per = (uint64_t)blocks * THREADS;
+        const uint64_t per = (uint64_t)blocks * THREADS * SF_PAIRS;
         a.iters = (uint32_t)((pairs + per - 1) / per);
     }
     if (jit) {
@@ -1148,7 +1148,10 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     const bool stream_copy = host_out && records_dev && cap;
     const bool stepwise = n_accept_target != 0 || stream_copy;
     if (wave == 0) wave = 1ull << 26;
-    const uint64_t max_launch = stepwise ? wave : (1ull << 36);   // 2^36: keeps a warp's iteration counter in 32 bits
+    // 2^36 keeps a warp's iteration counter in 32 bits; the seat-first kernel carries 32-bit offsets from the
+    // launch's first index in its queues: 2^31 indices per launch
+    uint64_t max_launch = stepwise ? wave : (1ull << 36);
+    if (seatfirst && max_launch > (1ull << 31)) max_launch = 1ull << 31;
     uint32_t waves = 0;
     const uint64_t launches0 = ctx->launches;
     // The counters are read back through host-mapped memory written by a tiny kernel: a memcpy on

@@ -234,14 +234,18 @@ __device__ __forceinline__ void sample_body(const SampleArgs &a)
 #define SF_MIN_BLOCKS 6
 #endif
 constexpr int SF_HIST_COPIES = 2;
+#ifndef SF_PAIRS
+#define SF_PAIRS 4            /* index pairs (Philox calls) per lane and iteration of stage A1 */
+#endif
+constexpr int SF_QCAP1 = 256; // stage A1 -> A2 queue (32-bit entries): survivors of one iteration fit at any pass rate below 7/8
 __constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
                                         thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
 
 __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
 {
     __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];   // stage B is rare here: few copies suffice
-    __shared__ uint4 s_q1[WARPS_PER_BLOCK][QCAP];     // A1 survivors: (u_lo, u_hi, idx_lo, idx_hi)
-    __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, idx_lo, idx_hi)
+    __shared__ uint32_t s_q1[WARPS_PER_BLOCK][SF_QCAP1];   // A1 survivors: index - a.first
+    __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, index - a.first, -)
     __shared__ uint4 s_q3[WARPS_PER_BLOCK][QCAP];     // B1 survivors: complete deals (planes)
     __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
     __shared__ uint8_t s_shape[14 * 14 * 14];
@@ -252,7 +256,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     __syncthreads();
 
     uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
-    uint4 *q1 = s_q1[warp], *q2 = s_q2[warp], *q3 = s_q3[warp];
+    uint4 *q2 = s_q2[warp], *q3 = s_q3[warp];
     unsigned h3 = 0, t3 = 0;
     const uint32_t b1_mask = a.cons.b1_mask & 0xFu, b2_mask = ~b1_mask & 0xFu;
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
@@ -264,13 +268,14 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
 
     // ---- stage B on up to 32 queued hands ------------------------------------------
     auto run_b = [&](unsigned count) {
-        const uint4 r = q2[(h2 + lane) % QCAP];
+        const uint4 r = q2[(h2 + lane) % QCAP];       // (m0, m1, index - a.first, -)
         h2 += count;
         __syncwarp();
         const bool active = lane < count;
         Planes pl;
         const uint32_t xl = (P & 1u) ? 0xFFFFFFFFu : 0u, xh = (P & 2u) ? 0xFFFFFFFFu : 0u;
-        const bool voided = deal_rest39(a.key, a.sf_q0, r.x, r.y, xl, xh, r.z, r.w, pl);
+        const unsigned long long idx = a.first + r.z;
+        const bool voided = deal_rest39(a.key, a.sf_q0, r.x, r.y, xl, xh, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
         n_void += (active && voided) ? 1u : 0u;
         if (b2_mask == 0u) {
             stage_b(a, pl, active && !voided, hist, s_shape, lane, s_feat[warp]);
@@ -295,52 +300,89 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     };
     // ---- stage A2 on up to 32 queued survivors of the HCP test ----------------------------
     auto run_a2 = [&](unsigned count) {
-        const uint4 r = q1[(h1 + lane) % QCAP];       // (u_lo, u_hi, idx_lo, idx_hi)
+        const uint32_t off = s_q1[warp][(h1 + lane) % SF_QCAP1];      // index - a.first
         h1 += count;
         __syncwarp();
         const bool active = lane < count;
-        const uint32_t H = sf_unrank_honours(a.cons.sf_tab, a.cons.sf_top, r.x, r.y);
+        const unsigned long long idx = a.first + off;
+        uint32_t w[4];
+        philox4x32_10(a.key, (uint32_t)(idx >> 1), (uint32_t)(idx >> 33), 0u, STREAM_SEATFIRST_RANK, w);
+        const bool second = (idx & 1ull) != 0ull;
+        const uint32_t H = sf_unrank_honours(a.cons.sf_tab, a.cons.sf_top, second ? w[2] : w[0], second ? w[3] : w[1]);
         bool voided = false;
         uint32_t m0, m1;
-        sf_lows(a.key, r.z, r.w, H, 13 - (int)__popc(H), voided, m0, m1);
+        sf_lows(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), H, 13 - (int)__popc(H), voided, m0, m1);
         n_void += (active && voided) ? 1u : 0u;
         const Feat f = hand_features(m0, m1);
         const bool ok = active && !voided && seat_ranges_ok(c, f);
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
-            if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, r.z, r.w);
+            if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, off, 0u);
             t2 += __popc(bal);
             __syncwarp();
         }
     };
 
-    // Stage A1.  One Philox call yields the 64-bit uniforms of the two indices of a pair (2p, 2p + 1);
-    // a lane owns one pair per iteration and handles its two indices in consecutive sub-steps, so the
-    // survivor queue never receives more than 32 entries between two drains.
-    const unsigned long long stride = total_warps * 32ull;                     // pairs per iteration of the grid
-    unsigned long long pair = (a.first >> 1) + gwarp * 32ull + lane;            // absolute pair number
-    unsigned long long off = 2ull * (gwarp * 32ull + lane) - (a.first & 1ull);  // index - a.first (wraps below 0)
-    const uint32_t steps = 2u * a.iters;
+    // Stage A1.  One Philox call yields the 64-bit uniforms of the two indices of a pair (2p, 2p + 1).
+    // Per iteration a lane tests SF_PAIRS pairs and keeps one survivor bit per index; the survivors are
+    // then queued as 32-bit offsets from a.first (a launch covers at most 2^31 indices, host), one per
+    // lane and round, and stage A2 recomputes their uniforms.  Rounds that do not fit wait for a drain.
+    const uint32_t tid_g = (uint32_t)gwarp * 32u + lane;
+    const uint32_t stride = (uint32_t)total_warps * 32u;                       // pairs per pass of the grid
+    const unsigned long long base_pair = a.first >> 1;
+    const uint32_t odd = (uint32_t)a.first & 1u, n32 = (uint32_t)a.n;
+    const uint32_t full_iters = n32 / (2u * SF_PAIRS * stride);                // iterations before it: every index valid
     const unsigned long long theta = a.cons.sf_theta;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    for (uint32_t st = 0;; ++st) {
-        const bool fin = st >= steps;
-        if (!fin) {
-            const uint32_t j = st & 1u;
-            if (j == 0u) philox4x32_10(a.key, (uint32_t)pair, (uint32_t)(pair >> 32), 0u, STREAM_SEATFIRST_RANK, w);
-            const uint32_t u_lo = j ? w[2] : w[0], u_hi = j ? w[3] : w[1];
-            const bool valid = off + j < a.n;
-            const bool ok = valid && ((((unsigned long long)u_hi) << 32) | u_lo) < theta;
-            if (u_hi == 0xFFFFFFFFu && valid && u_lo >= a.cons.sf_void_lo) ++n_void;
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-            if (bal) {
-                const unsigned long long idx = 2ull * pair + j;
-                if (ok) q1[(t1 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(u_lo, u_hi, (uint32_t)idx, (uint32_t)(idx >> 32));
-                t1 += __popc(bal);
-                __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t it = 0, mask = 0, po0 = 0;
+    bool pending = false;
+    for (;;) {
+        if (!pending && it < a.iters) {
+            po0 = it * (SF_PAIRS * stride) + tid_g;                            // pair offset of bit pair 0; bit pair k: + k * stride
+            mask = 0;
+            uint32_t rare = 1u;
+#pragma unroll
+            for (int k = 0; k < SF_PAIRS; ++k) {
+                uint32_t w[4];
+                const unsigned long long pair = base_pair + (po0 + (uint32_t)k * stride);
+                philox4x32_10(a.key, (uint32_t)pair, (uint32_t)(pair >> 32), 0u, STREAM_SEATFIRST_RANK, w);
+                if (((((unsigned long long)w[1]) << 32) | w[0]) < theta) mask |= 1u << (2 * k);
+                if (((((unsigned long long)w[3]) << 32) | w[2]) < theta) mask |= 2u << (2 * k);
+                rare *= (w[1] + 1u) * (w[3] + 1u);                             // 0 when a high word is all ones (or by chance)
             }
-            if (j) { pair += stride; off += 2ull * stride; }
+            if (__any_sync(0xFFFFFFFFu, rare == 0u) || it == 0u || it >= full_iters) {
+                // edge iterations: drop the indices outside [first, first + n); 2^-32 per index: the void check
+#pragma unroll 1
+                for (int k = 0; k < SF_PAIRS; ++k) {
+                    uint32_t w[4];
+                    const uint32_t po = po0 + (uint32_t)k * stride;
+                    const unsigned long long pair = base_pair + po;
+                    philox4x32_10(a.key, (uint32_t)pair, (uint32_t)(pair >> 32), 0u, STREAM_SEATFIRST_RANK, w);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const bool valid = 2u * po + (uint32_t)j - odd < n32;      // wraps for the index before a.first
+                        if (!valid) mask &= ~(1u << (2 * k + j));
+                        if (valid && w[2 * j + 1] == 0xFFFFFFFFu && w[2 * j] >= a.cons.sf_void_lo) ++n_void;
+                    }
+                }
+            }
+            ++it;
         }
+        for (;;) {                                                             // queue one survivor per lane and round
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, mask != 0u);
+            pending = false;
+            if (bal == 0u) break;
+            pending = true;
+            if (t1 - h1 + __popc(bal) > (unsigned)SF_QCAP1) break;
+            if (mask != 0u) {
+                const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                s_q1[warp][(t1 + __popc(bal & lt)) % SF_QCAP1] = 2u * (po0 + (b >> 1) * stride) + (b & 1u) - odd;
+            }
+            t1 += __popc(bal);
+        }
+        __syncwarp();
+        const bool fin = !pending && it >= a.iters;
         // drain the queues: full warps while the stream lasts, whatever is left at the end
         for (;;) {
             const unsigned n1 = t1 - h1;
