@@ -635,7 +635,7 @@ static void build_rank_table(bmc_constraints *c, int hcp_lo, int hcp_hi)
     if (acc.size() > 1) { top = 1; while (2u * top <= (uint32_t)acc.size() - 1u) top *= 2u; }
     c->dev.sf_top = top;
     c->dev.sf_theta = w_acc * S;
-    c->dev.sf_void_lo = (uint32_t)(N * S);            // the high word of N * S is 0xFFFFFFFF (N < 2^40)
+    c->dev.sf_void = N * S;
     c->sf_hcp[0] = hcp_lo; c->sf_hcp[1] = hcp_hi;
 }
 

@@ -31,8 +31,7 @@ struct ConsDev {
     const uint32_t *code;    // device pointer, programs of all seats
     const uint4 *sf_tab;     // seat-first stage A1: class table of the primary seat (seatfirst.cuh), in the code buffer
     unsigned long long sf_theta;   // u < sf_theta: the honour holding has an admissible HCP
-    uint32_t sf_void_lo;     // u >= 0xFFFFFFFF:sf_void_lo voids the index (u beyond S * C(52,13))
-    uint32_t pad;
+    unsigned long long sf_void;    // u >= sf_void = S * C(52,13) voids the index (probability 1.2e-8)
 };
 
 // shared-memory histogram (per warp): hcp[4][40] | len[4][4][16] | shape[4][40]
@@ -237,7 +236,8 @@ constexpr int SF_HIST_COPIES = 2;
 #ifndef SF_PAIRS
 #define SF_PAIRS 4            /* index pairs (Philox calls) per lane and iteration of stage A1 */
 #endif
-constexpr int SF_QCAP1 = 256; // stage A1 -> A2 queue (32-bit entries): survivors of one iteration fit at any pass rate below 7/8
+constexpr int SF_QCAP1 = 128; // stage A1 -> A2 queue (32-bit entries); rounds that do not fit wait for a drain
+__constant__ LowTabs c_lowtabs = make_lowtabs();
 __constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
                                         thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
 
@@ -249,10 +249,13 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     __shared__ uint4 s_q3[WARPS_PER_BLOCK][QCAP];     // B1 survivors: complete deals (planes)
     __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
     __shared__ uint8_t s_shape[14 * 14 * 14];
+    __shared__ __align__(16) LowTabs s_low;
 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < SF_HIST_COPIES * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
     for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(LowTabs) / 4); i += THREADS)
+        reinterpret_cast<uint32_t *>(&s_low)[i] = reinterpret_cast<const uint32_t *>(&c_lowtabs)[i];
     __syncthreads();
 
     uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
@@ -308,13 +311,16 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         uint32_t w[4];
         philox4x32_10(a.key, (uint32_t)(idx >> 1), (uint32_t)(idx >> 33), 0u, STREAM_SEATFIRST_RANK, w);
         const bool second = (idx & 1ull) != 0ull;
-        const uint32_t H = sf_unrank_honours(a.cons.sf_tab, a.cons.sf_top, second ? w[2] : w[0], second ? w[3] : w[1]);
-        bool voided = false;
-        uint32_t m0, m1;
-        sf_lows(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), H, 13 - (int)__popc(H), voided, m0, m1);
-        n_void += (active && voided) ? 1u : 0u;
+        unsigned long long d;
+        uint32_t magic, i, ell, m0, m1;
+        const uint32_t info = sf_find_class(a.cons.sf_tab, a.cons.sf_top, second ? w[2] : w[0], second ? w[3] : w[1], d, magic);
+        sf_split(d, (info >> 12) & 0x7FFu, magic, i, ell);
+        const uint32_t H = sf_honours_of(info, i);
+        sf_unrank_lows(s_low, ell, 13u - (uint32_t)__popc(H), m0, m1);
+        m0 |= ((H & 0xFu) << 9) | ((H & 0xF0u) << 21);
+        m1 |= ((H & 0xF00u) << 1) | ((H & 0xF000u) << 13);
         const Feat f = hand_features(m0, m1);
-        const bool ok = active && !voided && seat_ranges_ok(c, f);
+        const bool ok = active && seat_ranges_ok(c, f);
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
             if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, off, 0u);
@@ -340,7 +346,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         if (!pending && it < a.iters) {
             po0 = it * (SF_PAIRS * stride) + tid_g;                            // pair offset of bit pair 0; bit pair k: + k * stride
             mask = 0;
-            uint32_t rare = 1u;
+            uint32_t top = 0u;
 #pragma unroll
             for (int k = 0; k < SF_PAIRS; ++k) {
                 uint32_t w[4];
@@ -348,10 +354,10 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
                 philox4x32_10(a.key, (uint32_t)pair, (uint32_t)(pair >> 32), 0u, STREAM_SEATFIRST_RANK, w);
                 if (((((unsigned long long)w[1]) << 32) | w[0]) < theta) mask |= 1u << (2 * k);
                 if (((((unsigned long long)w[3]) << 32) | w[2]) < theta) mask |= 2u << (2 * k);
-                rare *= (w[1] + 1u) * (w[3] + 1u);                             // 0 when a high word is all ones (or by chance)
+                top = max(top, max(w[1], w[3]));
             }
-            if (__any_sync(0xFFFFFFFFu, rare == 0u) || it == 0u || it >= full_iters) {
-                // edge iterations: drop the indices outside [first, first + n); 2^-32 per index: the void check
+            if (__any_sync(0xFFFFFFFFu, top >= (uint32_t)(a.cons.sf_void >> 32)) || it == 0u || it >= full_iters) {
+                // edge iterations: drop the indices outside [first, first + n); 1.2e-8 per index: the void check
 #pragma unroll 1
                 for (int k = 0; k < SF_PAIRS; ++k) {
                     uint32_t w[4];
@@ -362,7 +368,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
                     for (int j = 0; j < 2; ++j) {
                         const bool valid = 2u * po + (uint32_t)j - odd < n32;      // wraps for the index before a.first
                         if (!valid) mask &= ~(1u << (2 * k + j));
-                        if (valid && w[2 * j + 1] == 0xFFFFFFFFu && w[2 * j] >= a.cons.sf_void_lo) ++n_void;
+                        if (valid && ((((unsigned long long)w[2 * j + 1]) << 32) | w[2 * j]) >= a.cons.sf_void) ++n_void;
                     }
                 }
             }

@@ -104,10 +104,64 @@ __device__ __forceinline__ void sf_steps(const PhiloxKey &key, uint32_t idx_lo, 
 constexpr uint32_t STREAM_SEATFIRST_RANK = 4u;
 constexpr int RANK_TAB_ENTRIES = 1024;      // 625 classes at most, padded for the branch-free search
 
+constexpr unsigned long long SF_HANDS = 635013559600ull;          // C(52,13)
+constexpr unsigned long long SF_S = 29049370ull;                  // floor(2^64 / C(52,13))
+constexpr unsigned long long SF_S_RECIP = 635013567375ull;        // floor(2^64 / SF_S)
+static_assert(SF_S * SF_HANDS == 0xFFFFFFCB68F946E0ull, "S C(52,13) is the void threshold");
+static_assert(SF_HANDS * (SF_S + 1ull) < SF_HANDS * SF_S, "S = floor(2^64 / C(52,13)): the next multiple wraps");
+
+// Low-card tables (compile-time constants): a hand holds k of the 36 low cards (2..10, nine per suit)
+// as l_c, l_d, l_h, l_s of each suit with weight C(9,l_c) C(9,l_d) C(9,l_h) C(9,l_s).
+//   prefix[st][k][l] = sum_{j<l} C(9,j) C(R,k-j), R = 27, 18, 9 for st = 0, 1, 2: the number of ways with
+//                      fewer than l cards in suit st when k low cards go to suits st..3 (0xFFFFFFFF past the end);
+//   c9[l] = { C(9,l), floor(2^32 / C(9,l)), index of the first l-subset in subset9, 0 };
+//   subset9 = the 512 subsets of nine cards ordered by size, then by value.
+struct LowTabs {
+    uint32_t prefix[3][14][16];
+    uint32_t c9[10][4];
+    uint16_t subset9[512];
+};
+__host__ __device__ constexpr unsigned long long sf_binom(int n, int k)
+{
+    if (k < 0 || k > n) return 0ull;
+    unsigned long long r = 1ull;
+    for (int i = 1; i <= k; ++i) r = r * (unsigned long long)(n - k + i) / (unsigned long long)i;
+    return r;
+}
+__host__ __device__ constexpr LowTabs make_lowtabs()
+{
+    LowTabs t{};
+    for (int st = 0; st < 3; ++st)
+        for (int k = 0; k < 14; ++k) {
+            const int R = 27 - 9 * st;
+            // the running total reaches C(R+9,k) > ell at l = 10 at the latest; entries after it are 0xFFFFFFFF
+            unsigned long long run = 0ull;
+            for (int l = 0; l < 16; ++l) {
+                t.prefix[st][k][l] = l <= 10 ? (uint32_t)(run > 0xFFFFFFFFull ? 0xFFFFFFFFull : run) : 0xFFFFFFFFu;
+                if (l <= 9) run += sf_binom(9, l) * sf_binom(R, k - l);
+            }
+        }
+    int pos = 0;
+    for (int l = 0; l <= 9; ++l) {
+        const unsigned long long c = sf_binom(9, l);
+        t.c9[l][0] = (uint32_t)c;
+        t.c9[l][1] = c == 1ull ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / c);
+        t.c9[l][2] = (uint32_t)pos;
+        t.c9[l][3] = 0u;
+        for (int v = 0; v < 512; ++v) {
+            int pc = 0;
+            for (int b = 0; b < 9; ++b) pc += (v >> b) & 1;
+            if (pc == l) t.subset9[pos++] = (uint16_t)v;
+        }
+    }
+    return t;
+}
+
 // Table entry (uint4): x,y = S * (weight of the classes before this one) as lo,hi;
 // z = nJ | nQ<<3 | nK<<6 | nA<<9 | I<<12;  w = floor(2^32 / I) (2^32 - 1 for I = 1).
-// Returns H: bit 4*suit + level (J Q K A = 0..3) set where the seat holds that honour.
-__device__ __forceinline__ uint32_t sf_unrank_honours(const uint4 *__restrict__ tab, uint32_t top, uint32_t u_lo, uint32_t u_hi)
+// Finds the class of u; returns its info word, sets d = u - S cum (uniform on [0, S I C(36,m))).
+__device__ __forceinline__ uint32_t sf_find_class(const uint4 *__restrict__ tab, uint32_t top, uint32_t u_lo, uint32_t u_hi,
+                                                  unsigned long long &d, uint32_t &magic)
 {
     const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
     uint32_t pos = 0;
@@ -116,14 +170,33 @@ __device__ __forceinline__ uint32_t sf_unrank_honours(const uint4 *__restrict__ 
         if ((((unsigned long long)c.y << 32) | c.x) <= u) pos += s;
     }
     const uint4 e = __ldg(tab + pos);
-    const unsigned long long d = u - ((((unsigned long long)e.y) << 32) | e.x);   // uniform on [0, S * I * C(36, m))
-    const uint32_t info = e.z, magic = e.w, I = (info >> 12) & 0x7FFu;
-    auto mod_i = [&](uint32_t x) {                        // x mod I, I <= 1296
-        const uint32_t r = x - __umulhi(x, magic) * I;
-        return r >= I ? r - I : r;
-    };
-    const uint32_t c32 = 0u - magic * I;                  // 2^32 mod I (1 instead of 0 for I = 1: harmless)
-    uint32_t i = mod_i(mod_i((uint32_t)(d >> 32)) * c32 + mod_i((uint32_t)d));
+    d = u - ((((unsigned long long)e.y) << 32) | e.x);
+    magic = e.w;
+    return e.z;
+}
+
+// d uniform on [0, S I L): q = d / S is uniform on [0, I L); i = q mod I picks the identity of the
+// honours, ell = q / I the low cards -- exactly uniform and independent.  q < 2^42, I <= 1296.
+__device__ __forceinline__ void sf_split(unsigned long long d, uint32_t I, uint32_t magic, uint32_t &i, uint32_t &ell)
+{
+    unsigned long long q = __umul64hi(d, SF_S_RECIP);     // q or q - 1 (- 2 never: d < 2^64, see the mirror's test)
+    unsigned long long r = d - q * SF_S;
+    if (r >= SF_S) { r -= SF_S; ++q; }
+    if (r >= SF_S) { r -= SF_S; ++q; }
+    const uint32_t qh = (uint32_t)(q >> 21), ql = (uint32_t)q & 0x1FFFFFu;     // long division in base 2^21
+    uint32_t a = __umulhi(qh, magic), ra = qh - a * I;
+    if (ra >= I) { ra -= I; ++a; }
+    const uint32_t t = (ra << 21) | ql;                   // < 1296 * 2^21 < 2^32
+    uint32_t b = __umulhi(t, magic);
+    i = t - b * I;
+    if (i >= I) { i -= I; ++b; }
+    ell = (a << 21) + b;
+}
+
+// Identity of the honours: i in [0, I) as mixed-radix digits (J first) over the C(4, n.) subsets of suits.
+// Returns H: bit 4*suit + level (J Q K A = 0..3) set where the seat holds that honour.
+__device__ __forceinline__ uint32_t sf_honours_of(uint32_t info, uint32_t i)
+{
     uint32_t H = 0;
 #pragma unroll
     for (int lev = 0; lev < 4; ++lev) {
@@ -139,6 +212,34 @@ __device__ __forceinline__ uint32_t sf_unrank_honours(const uint4 *__restrict__ 
         H |= sp << lev;
     }
     return H;
+}
+
+// The k low cards of the hand from their rank ell in [0, C(36,k)): suit by suit (c d h s), the length
+// by a search over prefix[st][k], the cards by the subset table.  Returns the two lane-layout words
+// (low nine bits of each 16-bit lane).
+__device__ __forceinline__ void sf_unrank_lows(const LowTabs &T, uint32_t ell, uint32_t k, uint32_t &m0, uint32_t &m1)
+{
+    uint32_t sub[4];
+    k = min(k, 13u);
+#pragma unroll
+    for (int st = 0; st < 3; ++st) {
+        const uint32_t *row = T.prefix[st][k];
+        uint32_t l = 0;
+#pragma unroll
+        for (int s = 8; s != 0; s >>= 1) if (row[l + s] <= ell) l += s;
+        l = min(l, 9u);
+        ell -= row[l];
+        const uint4 e = *reinterpret_cast<const uint4 *>(T.c9[l]);
+        uint32_t q = __umulhi(ell, e.y), r = ell - q * e.x;            // ell = q C(9,l) + r
+        if (r >= e.x) { r -= e.x; ++q; }
+        sub[st] = T.subset9[(e.z + r) & 511u];
+        ell = q;
+        k = min(k - l, 13u);
+    }
+    const uint32_t l3 = min(k, 9u);
+    sub[3] = T.subset9[(T.c9[l3][2] + ell) & 511u];
+    m0 = sub[0] | (sub[1] << 16);
+    m1 = sub[2] | (sub[3] << 16);
 }
 
 // Stage A2: 36 low cards given the honours H (r = 13 - popc(H) cards still needed), Philox stream 2

@@ -726,11 +726,17 @@ ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fix
  * index >> 1, words 2 (index & 1) and 2 (index & 1) + 1), rank = u / S with S = floor(2^64 /
  * C(52,13)); u >= S C(52,13) voids the index.  The identity of the honours comes from
  * (u - S cum) mod I, I = product of the C(4, n.), as mixed-radix digits J first.
- * Stage A2: 36 low cards (spade 10 first ... club 2 last), binary steps on Philox stream 2
- * blocks 1 and 2.  Returns the hand as a lane mask; *voided: bit 0 = void in A1, bit 1 = in A2;
+ * Stage A2: with q = (u - S cum) / S, i = q mod I picks the honours and ell = q / I, uniform on
+ * [0, C(36, 13 - n)), is the rank of the low cards (no further random numbers).
+ * Returns the hand as a lane mask; *voided: bit 0 = void in A1 (bit 1 is no longer used);
  * *a1_pass = 1 when the class has an admissible HCP (the index survives stage A1). */
-static const int SF_HI[11] = {52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9};
-static const int SF_LO[11] = {49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2};
+static uint64_t binom_small(int n, int k)
+{
+    if (k < 0 || k > n) return 0;
+    uint64_t r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (uint64_t)(n - k + i) / (uint64_t)i;
+    return r;
+}
 static const uint8_t SUBSETS4[5][6] = { {0}, {1, 2, 4, 8}, {3, 5, 6, 9, 10, 12}, {7, 11, 13, 14}, {15} };
 ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int hcp_lo, int hcp_hi, int *voided, int *a1_pass)
 {
@@ -749,7 +755,7 @@ ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int hcp_l
     if (u >= N * S) { *voided = 1; return 0; }
     const uint64_t R = u / S;
     /* walk the classes in table order: admitted ones first */
-    uint64_t cum = 0, hand = 0;
+    uint64_t cum = 0, hand = 0, ell = 0;
     int found = 0;
     for (int group = 0; group < 2 && !found; ++group)
         for (int id = 0; id < 625 && !found; ++id) {
@@ -764,7 +770,9 @@ ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int hcp_l
             for (int t = 1; t <= 13 - n; ++t) lows = lows * (uint64_t)(36 - t + 1) / (uint64_t)t;
             uint64_t wgt = I * lows;
             if (R < cum + wgt) {
-                uint64_t i = (u - cum * S) % I;
+                uint64_t q = (u - cum * S) / S;                      /* uniform on [0, I C(36, 13 - n)) */
+                uint64_t i = q % I;
+                ell = q / I;
                 for (int lev = 0; lev < 4; ++lev) {
                     uint64_t r = C4[c[lev]];
                     int m4 = SUBSETS4[c[lev]][i % r];
@@ -777,34 +785,30 @@ ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int hcp_l
             }
             cum += wgt;
         }
-    int r = 13 - __builtin_popcountll(hand);
-    uint32_t x = 0;
-    for (int i = 16; i < 52; ++i) {
-        int n = 52 - i, d = 0;
-        if (n >= 2) {
-            int g = 0;
-            while (!(n <= SF_HI[g] && n >= SF_LO[g])) ++g;
-            if (n == SF_HI[g]) {
-                if ((g & 3) == 0) {
-                    uint32_t c2[4] = { (uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(g >> 2), 2 };
-                    orc_philox4x32_10(c2, key, w);
-                }
-                x = w[g & 3];
+    /* Stage A2: the low cards from ell, suit by suit (c d h s): the number of cards l of the suit is the
+     * largest l with sum_{j<l} C(9,j) C(R,k-j) <= ell (R = low cards of the later suits, k = low cards
+     * still to place), the cards are the (ell' mod C(9,l))-th l-subset of the nine in numeric order. */
+    int k = 13 - __builtin_popcountll(hand);
+    for (int su = 0; su < 4; ++su) {
+        int R = 27 - 9 * su, l = 0;
+        uint64_t rank;
+        if (su < 3) {
+            uint64_t before = 0, acc = 0;
+            for (int j = 0; j <= 9; ++j) {
+                if (acc <= ell) { l = j; before = acc; }
+                acc += binom_small(9, j) * binom_small(R, k - j);
             }
-            uint64_t p = (uint64_t)x * (uint32_t)n;
-            d = (int)(p >> 32);
-            x = (uint32_t)p;
-            if (n == SF_LO[g]) {
-                uint64_t Ng = 1;
-                for (int m = SF_LO[g]; m <= SF_HI[g]; ++m) Ng *= (uint64_t)m;
-                if (x < (uint32_t)((((uint64_t)1) << 32) % Ng)) vd |= 2;
-            }
+            ell -= before;
+            rank = ell % binom_small(9, l);
+            ell /= binom_small(9, l);
+        } else {
+            l = k;
+            rank = ell;
         }
-        if (d < r) {
-            --r;
-            int l = 35 - (i - 16), suit = l / 9, rank = l % 9;
-            hand |= 1ull << (16 * suit + rank);
-        }
+        uint64_t seen = 0;
+        for (unsigned v = 0; v < 512; ++v)
+            if (__builtin_popcount(v) == l && seen++ == rank) { hand |= (uint64_t)v << (16 * su); break; }
+        k -= l;
     }
     *voided = vd;
     return hand;

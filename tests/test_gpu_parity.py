@@ -117,6 +117,18 @@ def test_constrained_sampler_equals_filtered_stream(engine, mode):
         assert tal["voided"] == int(expect)      # this rule is exactly its ranges: passing stage A2 == accepted
 
 
+def test_seat_first_void_count_of_stage_a1(engine):
+    """stage A1 voids u >= S * C(52,13) (S = floor(2^64 / C(52,13))): 1.22e-8 per index.  With a window no
+    hand reaches before stage A2 matters (37 HCP: 4 hands in 6.35e11) every void counted is an A1 void."""
+    cons = Constraints([None, None, seat_spec(hcp=(37, 37)), None]).set_mode(2)
+    n = 1 << 34
+    _, tal, _ = engine.sample(cons, n_raw=n, seed=77, cap=0)
+    n_hands = 635013559600
+    p = 1 - (2 ** 64 // n_hands) * n_hands / 2 ** 64
+    assert tal["raw"] == n and tal["accepted"] <= 2
+    assert abs(tal["voided"] - n * p) < 5 * (n * p) ** 0.5, (tal["voided"], n * p)
+
+
 def test_auto_mode_picks_by_pass_rate(engine):
     tight = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
     loose = Constraints([None, seat_spec(hcp=(0, 20)), None, None])
@@ -260,11 +272,8 @@ def test_c2_acceptance_rate_exact_seat_first(engine):
     cons = Constraints(None, [None, None, rule, None]).set_mode(2)
     n = 50_000_000
     _, tal, _ = engine.sample(cons, n_raw=n, seed=123, cap=0)
-    hi = [36, 32, 28, 24, 20, 15, 9]                                 # stage A2: the 36 low cards
-    lo = [33, 29, 25, 21, 16, 10, 2]
     n_hands = 635013559600
-    surv_a = prod(1 - ((1 << 32) % prod(range(l, h + 1))) / 2 ** 32 for h, l in zip(hi, lo))
-    surv_a *= (2 ** 64 // n_hands) * n_hands / 2 ** 64                # stage A1: u beyond S * C(52,13)
+    surv_a = (2 ** 64 // n_hands) * n_hands / 2 ** 64                 # stage A1: u beyond S * C(52,13); A2 draws nothing
     surv_b = prod(1 - ((1 << 32) % prod(m for m in range(39 - 4 * w - 3, 39 - 4 * w + 1) if m >= 2)) / 2 ** 32
                   for w in range(10))
     p = 24235203726 / 635013559600 * surv_a * surv_b

@@ -12,6 +12,8 @@ if cfg == "c1":
 elif cfg == "c3":
     p = bidding.openings.passes()
     cons = Constraints(None, [f"(and {p} T)", p, bidding.openings.chooses((1, "NT")), p])
+elif cfg == "c5":
+    cons = Constraints(None, [bidding.nt_responses(2).chooses((6, "NT")), None, bidding.openings.chooses((2, "NT")), None])
 else:
     cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
 if len(sys.argv) > 3 and cons is not None:
