@@ -631,9 +631,30 @@ static void build_rank_table(bmc_constraints *c, int hcp_lo, int hcp_hi)
     for (; entries < RANK_TAB_ENTRIES; ++entries) {
         c->code.push_back(0xFFFFFFFFu); c->code.push_back(0xFFFFFFFFu); c->code.push_back(1u << 12); c->code.push_back(0xFFFFFFFFu);
     }
-    uint32_t top = 0;
-    if (acc.size() > 1) { top = 1; while (2u * top <= (uint32_t)acc.size() - 1u) top *= 2u; }
-    c->dev.sf_top = top;
+    // bucket index of the class search (seatfirst.cuh sf_find_class)
+    const uint64_t theta = w_acc * S;
+    const uint64_t bm = ((uint64_t)SF_BUCKETS << 32) / ((theta >> 32) + 1);
+    const uint32_t bmul = bm > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bm;
+    const size_t tab_words = (size_t)c->tab_off;
+    auto cum_of = [&](int k) {
+        return (uint64_t)c->code[tab_words + 4 * (size_t)k] | ((uint64_t)c->code[tab_words + 4 * (size_t)k + 1] << 32);
+    };
+    auto f = [&](uint64_t u_hi) { return (uint32_t)((u_hi * (uint64_t)bmul) >> 32); };
+    int pos = 0;
+    for (uint32_t j = 0; j < (uint32_t)SF_BUCKETS; j += 2) {
+        uint32_t pair16[2];
+        for (uint32_t h = 0; h < 2; ++h) {
+            // smallest u_hi with f(u_hi) >= j + h
+            uint64_t lo = (((uint64_t)(j + h) << 32) + bmul - 1) / bmul;
+            while (lo > 0 && f(lo - 1) >= j + h) --lo;
+            while (lo <= 0xFFFFFFFFull && f(lo) < j + h) ++lo;
+            const uint64_t u_min = lo > 0xFFFFFFFFull ? ~0ull : lo << 32;
+            while (pos + 1 < RANK_TAB_ENTRIES - 1 && cum_of(pos + 1) <= u_min) ++pos;
+            pair16[h] = (uint32_t)pos;
+        }
+        c->code.push_back(pair16[0] | (pair16[1] << 16));
+    }
+    c->dev.sf_bmul = bmul;
     c->dev.sf_theta = w_acc * S;
     c->dev.sf_void = N * S;
     c->sf_hcp[0] = hcp_lo; c->sf_hcp[1] = hcp_hi;

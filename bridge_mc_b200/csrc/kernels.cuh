@@ -27,7 +27,7 @@ struct ConsDev {
     uint32_t primary;        // seat tested in stage A
     uint32_t b1_mask;        // seat-first mode: seats fully tested right after the deal is completed (0xF: all of them);
                              // the others are tested after one more compaction
-    uint32_t sf_top;         // seat-first stage A1: first step of the class search (a power of two, 0: one class)
+    uint32_t sf_bmul;        // seat-first stage A2: bucket of a survivor = umulhi(u_hi, sf_bmul) (seatfirst.cuh)
     const uint32_t *code;    // device pointer, programs of all seats
     const uint4 *sf_tab;     // seat-first stage A1: class table of the primary seat (seatfirst.cuh), in the code buffer
     unsigned long long sf_theta;   // u < sf_theta: the honour holding has an admissible HCP
@@ -313,7 +313,9 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         const bool second = (idx & 1ull) != 0ull;
         unsigned long long d;
         uint32_t magic, i, ell, m0, m1;
-        const uint32_t info = sf_find_class(a.cons.sf_tab, a.cons.sf_top, second ? w[2] : w[0], second ? w[3] : w[1], d, magic);
+        // lanes past the end of the queue look up u = 0: class 0, nothing to scan
+        const uint32_t info = sf_find_class(a.cons.sf_tab, a.cons.sf_bmul, active ? (second ? w[2] : w[0]) : 0u,
+                                            active ? (second ? w[3] : w[1]) : 0u, d, magic);
         sf_split(d, (info >> 12) & 0x7FFu, magic, i, ell);
         const uint32_t H = sf_honours_of(info, i);
         sf_unrank_lows(s_low, ell, 13u - (uint32_t)__popc(H), m0, m1);

@@ -102,7 +102,8 @@ __device__ __forceinline__ void sf_steps(const PhiloxKey &key, uint32_t idx_lo, 
 
 // ---- stage A1, rank form -----------------------------------------------------------
 constexpr uint32_t STREAM_SEATFIRST_RANK = 4u;
-constexpr int RANK_TAB_ENTRIES = 1024;      // 625 classes at most, padded for the branch-free search
+constexpr int RANK_TAB_ENTRIES = 640;       // 625 classes at most, then entries no u reaches
+constexpr int SF_BUCKETS = 256;
 
 constexpr unsigned long long SF_HANDS = 635013559600ull;          // C(52,13)
 constexpr unsigned long long SF_S = 29049370ull;                  // floor(2^64 / C(52,13))
@@ -159,15 +160,20 @@ __host__ __device__ constexpr LowTabs make_lowtabs()
 
 // Table entry (uint4): x,y = S * (weight of the classes before this one) as lo,hi;
 // z = nJ | nQ<<3 | nK<<6 | nA<<9 | I<<12;  w = floor(2^32 / I) (2^32 - 1 for I = 1).
+// The table is followed by SF_BUCKETS 16-bit entries: bucket[j] = the class holding the smallest u with
+// umulhi(u_hi, bmul) = j (bmul ~ SF_BUCKETS 2^32 / (theta_hi + 1)), so a lookup is one indexed load and a
+// short forward scan instead of a binary search.
 // Finds the class of u; returns its info word, sets d = u - S cum (uniform on [0, S I C(36,m))).
-__device__ __forceinline__ uint32_t sf_find_class(const uint4 *__restrict__ tab, uint32_t top, uint32_t u_lo, uint32_t u_hi,
+__device__ __forceinline__ uint32_t sf_find_class(const uint4 *__restrict__ tab, uint32_t bmul, uint32_t u_lo, uint32_t u_hi,
                                                   unsigned long long &d, uint32_t &magic)
 {
     const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
-    uint32_t pos = 0;
-    for (uint32_t s = top; s != 0u; s >>= 1) {           // warp-uniform trip count
-        const uint2 c = __ldg(reinterpret_cast<const uint2 *>(tab + pos + s));
-        if ((((unsigned long long)c.y << 32) | c.x) <= u) pos += s;
+    const uint16_t *bucket = reinterpret_cast<const uint16_t *>(tab + RANK_TAB_ENTRIES);
+    uint32_t pos = __ldg(bucket + min(__umulhi(u_hi, bmul), (uint32_t)SF_BUCKETS - 1u));
+    for (;;) {
+        const uint2 c = __ldg(reinterpret_cast<const uint2 *>(tab + pos + 1u));
+        if ((((unsigned long long)c.y << 32) | c.x) > u || pos >= (uint32_t)RANK_TAB_ENTRIES - 2u) break;
+        ++pos;
     }
     const uint4 e = __ldg(tab + pos);
     d = u - ((((unsigned long long)e.y) << 32) | e.x);
