@@ -1,104 +1,35 @@
 // seatfirst.cuh -- lazy, seat-first dealing for rejection sampling (device).
 //
 // A uniformly random deal factorises as
-//     P(primary seat's honours) x P(its low cards | honours) x P(other three hands | primary hand)
-// and a constraint that rejects most deals on the primary seat alone never needs
-// the later factors.  The sampler therefore runs three stages with a warp-level
-// compaction queue between them, so every stage executes on full warps:
-//   A1  the RANK of the primary seat's honour holding in an order that puts the holdings with an
-//       admissible HCP first (half a Philox call, one 64-bit compare)   -> HCP range
-//   A2  unrank the honours, then 36 low cards, primary seat vs the rest (2 Philox calls)
-//                                                                   -> all ranges of the seat
-//   B   the other 39 cards to the other three seats (deal_fixed with the primary
-//       hand as a per-lane fixed hand, 3 Philox calls)            -> every seat's full test
-// Each factor is sampled exactly (mixed-radix digits + Lemire rejection, see
-// deal.cuh), so accepted deals are exactly uniform over the deals that satisfy the
-// constraint -- the same distribution as dealing all 52 cards and rejecting.
-// Mirrored bit for bit by orc_gpu_seatfirst_hand / orc_gpu_deal_fixed in
-// oracle/bmc_oracle.c.
+//     P(primary seat's honour counts) x P(its cards | counts) x P(other three hands | primary hand)
+// and a constraint that rejects most deals on the primary seat alone never needs the later
+// factors.  The sampler therefore runs in stages with a warp-level compaction queue between them, so
+// every stage executes on full warps:
+//   A1  the RANK of the primary seat's hand in an order that puts the honour holdings with an
+//       admissible HCP first (half a Philox call, one 64-bit compare)          -> HCP range
+//   A2  unrank the hand from the same uniform: honour counts, their suits, the low cards suit by
+//       suit (no further random numbers)                                       -> all ranges of the seat
+//   B   the other 39 cards to the other three seats (3 Philox calls, digits + Lemire rejection as in
+//       deal.cuh)                                                              -> every seat's full test
+// Every factor is sampled exactly, so accepted deals are exactly uniform over the deals that satisfy
+// the constraint -- the same distribution as dealing all 52 cards and rejecting.  Mirrored bit for
+// bit by orc_gpu_seatfirst_hand / gpu_deal_fixed_stream in oracle/bmc_oracle.c.
 //
-// Stage A1 in detail.  A 13-card hand holds nJ jacks, nQ queens, nK kings and nA aces with
-// probability w / C(52,13), w = C(4,nJ) C(4,nQ) C(4,nK) C(4,nA) C(36, 13 - nJ - nQ - nK - nA), and its
-// HCP is nJ + 2 nQ + 3 nK + 4 nA: the 625 count classes are laid out on [0, C(52,13)) with the
-// classes whose HCP lies in the seat's range FIRST.  One 64-bit uniform u then decides the HCP
+// Stage A in detail.  A 13-card hand holds nJ jacks, nQ queens, nK kings and nA aces with
+// probability w / C(52,13), w = I C(36, m), I = C(4,nJ) C(4,nQ) C(4,nK) C(4,nA), m = 13 - nJ - nQ - nK -
+// nA, and its HCP is nJ + 2 nQ + 3 nK + 4 nA: the 625 count classes are laid out on [0, C(52,13)) with
+// the classes whose HCP lies in the seat's range FIRST.  One 64-bit uniform u then decides the HCP
 // test by a single compare (u < theta = S * weight of the admitted classes, S = floor(2^64 /
-// C(52,13))); only the survivors look their class up (binary search over the scaled cumulative
-// weights), take the identity of the honours from the exactly uniform residual (u - S cum) mod
-// I, I = C(4,nJ) C(4,nQ) C(4,nK) C(4,nA), and go on to deal the low cards.  u >= S C(52,13)
-// (probability 3e-8) voids the index, so every class keeps its exact probability.
-//
-// Binary step (seat gets the card iff u < r, r = cards the seat still needs):
-//     d = u - r ; mask = (mask << 1) | sign(d) ; r += d >> 31        (4 instructions with the digit)
+// C(52,13))); u >= S C(52,13) (probability 1.2e-8) voids the index, so every hand keeps its exact
+// probability.  Only the survivors look their class up; q = (u - S cum) / S is uniform on [0, I C(36,m)):
+// q mod I picks the suits of the honours, q / I is the rank of the m low cards among the C(36,m)
+// possibilities, unranked suit by suit with binomial prefix sums.
 #pragma once
 #include "deal.cuh"
 
 namespace bmc {
 
-constexpr uint32_t STREAM_SEATFIRST_A = 2u, STREAM_SEATFIRST_B = 3u;
-
-// ---- digit schedule of stage A: 52 cards, n = 52 - i cards left at step i ----------
-// words 0..3 (Philox block 0): n = 52..37 in fours; words 4..7 (block 1): 36..21 in fours;
-// words 8..10 (block 2): 20..16, 15..10, 9..2.
-__host__ __device__ constexpr int sf_grp_hi(int g)
-{
-    constexpr int t[11] = {52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9};
-    return t[g];
-}
-__host__ __device__ constexpr int sf_grp_lo(int g)
-{
-    constexpr int t[11] = {49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2};
-    return t[g];
-}
-__host__ __device__ constexpr int sf_grp_of(int n)
-{
-    for (int g = 0; g < 11; ++g) if (n <= sf_grp_hi(g) && n >= sf_grp_lo(g)) return g;
-    return -1;
-}
-__host__ __device__ constexpr uint32_t sf_grp_thresh(int g)
-{
-    uint64_t N = 1;
-    for (int n = sf_grp_lo(g); n <= sf_grp_hi(g); ++n) N *= (uint64_t)n;
-    return (uint32_t)((1ull << 32) % N);
-}
-
-struct SeatFirstState {
-    uint32_t w[4];
-    uint32_t x;
-    uint32_t mask;      // ownership bits of the cards dealt so far (first card = highest bit)
-    int r;              // cards the primary seat still needs
-    bool voided;
-};
-
-// step I of 52: I = 0..15 honours (spade A first ... club J last), I = 16..51 low cards
-// (spade 10 first ... club 2 last)
-template <int I>
-__device__ __forceinline__ void sf_step(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s)
-{
-    constexpr int n = 52 - I;
-    uint32_t u = 0;
-    if constexpr (n >= 2) {
-        constexpr int g = sf_grp_of(n);
-        if constexpr (n == sf_grp_hi(g)) {
-            if constexpr ((g & 3) == 0) philox4x32_10(key, idx_lo, idx_hi, (uint32_t)(g >> 2), STREAM_SEATFIRST_A, s.w);
-            s.x = s.w[g & 3];
-        }
-        mul_wide(s.x, (uint32_t)n, s.x, u);
-        if constexpr (n == sf_grp_lo(g)) {
-            constexpr uint32_t thresh = sf_grp_thresh(g);
-            s.voided |= s.x < thresh;
-        }
-    }
-    const int d = (int)u - s.r;                         // < 0: the seat takes the card
-    s.mask = __funnelshift_l((uint32_t)d, s.mask, 1);   // (mask << 1) | sign bit
-    s.r += d >> 31;
-}
-
-template <int Base, int... K>
-__device__ __forceinline__ void sf_steps(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, SeatFirstState &s,
-                                         iseq<K...>)
-{
-    (sf_step<Base + K>(key, idx_lo, idx_hi, s), ...);
-}
+constexpr uint32_t STREAM_SEATFIRST_B = 3u;       // (stream 2 belonged to the card-by-card stage A of earlier builds)
 
 // ---- stage A1, rank form -----------------------------------------------------------
 constexpr uint32_t STREAM_SEATFIRST_RANK = 4u;
@@ -246,24 +177,6 @@ __device__ __forceinline__ void sf_unrank_lows(const LowTabs &T, uint32_t ell, u
     sub[3] = T.subset9[(T.c9[l3][2] + ell) & 511u];
     m0 = sub[0] | (sub[1] << 16);
     m1 = sub[2] | (sub[3] << 16);
-}
-
-// Stage A2: 36 low cards given the honours H (r = 13 - popc(H) cards still needed), Philox stream 2
-// blocks 1 and 2; returns the seat's hand as lane-layout words.
-__device__ __forceinline__ void sf_lows(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, uint32_t H, int r, bool &voided,
-                                        uint32_t &m0, uint32_t &m1)
-{
-    SeatFirstState s;
-    s.x = 0; s.r = r; s.voided = voided;
-    s.mask = 0;
-    sf_steps<16>(key, idx_lo, idx_hi, s, make_iseq<18>{});     // lows 35..18: hearts, spades
-    const uint32_t hs = s.mask & 0x3FFFFu;
-    s.mask = 0;
-    sf_steps<34>(key, idx_lo, idx_hi, s, make_iseq<18>{});     // lows 17..0: clubs, diamonds
-    const uint32_t cd = s.mask & 0x3FFFFu;
-    voided = s.voided;
-    m0 = (cd & 0x1FFu) | ((cd & 0x3FE00u) << 7) | ((H & 0xFu) << 9) | ((H & 0xF0u) << 21);
-    m1 = (hs & 0x1FFu) | ((hs & 0x3FE00u) << 7) | ((H & 0xF00u) << 1) | ((H & 0xF000u) << 13);
 }
 
 // Lemire thresholds of deal_fixed's words for 39 free cards (4 digits per word)
