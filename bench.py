@@ -36,13 +36,13 @@ SEED = 0x6272696467656D63
 # Algorithmic integer work of one raw deal on the hot kernel for this workload ("W_int"):
 # thread-level integer instructions per raw deal, counted by ncu on the committed kernels
 # (sass__thread_inst_executed / raw deals of the launch):
-#   seat-first sampler  248  profiles/r01_prof_c2_seatfirst_final_2p28.txt  (6.66e10 thread instructions for a
-#                            2^28-deal launch)
+#   seat-first sampler  128  profiles/r01_prof_c2_rankfirst_2p28.txt  (3.42e10 thread instructions for a
+#                            2^28-deal launch; 248 before stage A became a rank draw)
 #   full-deal sampler   649  profiles/r01_c2_sample_kernel_v1.txt
-W_INT_BY_MODE = {1: 649, 2: 248}
+W_INT_BY_MODE = {1: 649, 2: 128}
 # DRAM bytes of one 2^28-deal seat-first launch that stores its 10.2 M records (163 MB algorithmic): ncu
-# dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_bench_launch_traffic.csv (the rest is still in L2 at kernel end)
-TRAFFIC_BYTES_BY_MODE = {1: None, 2: 100_900_000}
+# dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_launches_bench_rankfirst.csv (the rest is still in L2 at kernel end)
+TRAFFIC_BYTES_BY_MODE = {1: None, 2: 101_600_000}
 KERNEL_BY_MODE = {1: "sample_kernel<true,false>", 2: "sample_seatfirst_kernel"}
 W_INT_SURVEY = 1400                          # SURVEY 8d's budget for a naive per-card full deal
 INT_PEAK_NOMINAL = 148 * 128 * 1.965e9       # SMs x INT32 lanes x max SM clock
