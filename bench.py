@@ -214,6 +214,8 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: libbridgemc has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
     bdist.init_process_group("nccl", dev)
 
     eng = Engine(local)
