@@ -129,6 +129,57 @@ def test_seat_first_void_count_of_stage_a1(engine):
     assert abs(tal["voided"] - n * p) < 5 * (n * p) ** 0.5, (tal["voided"], n * p)
 
 
+@pytest.mark.parametrize("seat,spec", [
+    (0, dict(hcp=(0, 37))),                        # every class admitted: theta = S * C(52,13)
+    (1, dict(hcp=(20, 21))),
+    (3, dict(hcp=(0, 7), s=(5, 13))),
+    (2, dict(hcp=(11, 14), h=(4, 6), d=(0, 3))),
+    (0, dict(hcp=(28, 37))),                       # a handful of tiny classes
+    (1, dict(c=(6, 13))),                          # no HCP range at all
+])
+def test_seat_first_windows_and_seats_vs_mirror(engine, seat, spec):
+    """rank draw + unranking for other HCP windows and primary seats: the accepted set equals the CPU
+    mirror's stream filtered by the same constraint"""
+    specs = [None] * 4
+    specs[seat] = seat_spec(**spec)
+    cons = Constraints(specs).set_mode(2)
+    n = 150_000
+    got, tal, _ = engine.sample(cons, n_raw=n, seed=SEED + seat, first_index=3)      # odd first index: a split pair
+    assert (cons.mode, cons.primary) == (2, seat)
+    lo, hi = cons.primary_hcp
+    assert (lo, hi) == (spec.get("hcp", (0, 37))[0], min(spec.get("hcp", (0, 37))[1], 37))
+    ref, va, vb = mirror_stream(cons, SEED + seat, 3, n)
+    acc, _ = engine.filter(ref, cons, None, want_features=False)
+    keep = (acc == 1) & ~va & ~vb
+    assert tal["raw"] == n and tal["accepted"] == int(keep.sum()) == got.shape[0]
+    assert np.array_equal(sort_records(got), sort_records(ref[keep]))
+
+
+def test_chi_square_seat_first_full_distribution(engine):
+    """the whole rank / unrank path at acceptance 1: with an all-admitting window on South the seat-first
+    kernel must reproduce the exact HCP and sorted-shape pmfs of every seat (parity rejected if p < 1e-3)"""
+    from math import comb
+    from itertools import permutations
+    from bridge_mc_b200._lib import shape_table
+    cons = Constraints([None, None, seat_spec(hcp=(0, 37)), None]).set_mode(2)
+    n = 20_000_000
+    _, tal, _ = engine.sample(cons, n_raw=n, seed=606, cap=0)
+    acc = tal["accepted"]
+    assert cons.mode == 2 and 0.99 * n < acc <= n
+    hcp_num, _ = O.Distgen(c=(0, 13), d=(0, 13), h=(0, 13), s=(0, 13)).pmf()
+    total = comb(52, 13)
+    exp_hcp = np.array(hcp_num, float) / total * acc
+    shape_w = [sum(comb(13, p[0]) * comb(13, p[1]) * comb(13, p[2]) * comb(13, p[3]) for p in set(permutations(r)))
+               for r in shape_table().tolist()]
+    exp_shape = np.array(shape_w, float) / total * acc
+    exp_len = np.array([comb(13, l) * comb(39, 13 - l) for l in range(14)], float) / total * acc
+    for k in range(4):
+        assert _chi2_p(tal["hcp"][k], exp_hcp) > 1e-3
+        assert _chi2_p(tal["shape"][k], exp_shape) > 1e-3
+        for su in range(4):
+            assert _chi2_p(tal["len"][k][su], exp_len) > 1e-3
+
+
 def test_auto_mode_picks_by_pass_rate(engine):
     tight = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
     loose = Constraints([None, seat_spec(hcp=(0, 20)), None, None])

@@ -3,7 +3,8 @@ against exact combinatorial pmfs at 1e11 raw deals.
 
   full-deal kernel  : unconstrained, every seat's HCP (38 bins) and sorted shape (39 bins)
   seat-first kernel : South test-bid (1 NT); acceptance against the exact probability (times the exact
-                      Lemire survival factors) and South's 15/16/17 split; the other seats' HCP given South
+                      survival factors of the void checks) and South's 15/16/17 split; then, with an all-admitting
+                      window, every seat's HCP / shape and South's suit lengths through the rank / unrank path
 """
 import json, os, sys
 from math import comb, prod
@@ -51,9 +52,7 @@ out["full_deal"] = {"accepted": acc, "voided": t["voided"], "kernel_ms": st.kern
 
 cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None]).set_mode(2)
 _, t, st = eng.sample(cons, n_raw=N, seed=20261021, cap=0)
-hi = [52, 48, 44, 40, 36, 32, 28, 24, 20, 15, 9]
-lo = [49, 45, 41, 37, 33, 29, 25, 21, 16, 10, 2]
-surv = prod(1 - ((1 << 32) % prod(range(l, h + 1))) / 2 ** 32 for h, l in zip(hi, lo))
+surv = (2 ** 64 // total) * total / 2 ** 64            # stage A1: u beyond S * C(52,13); stage A2 draws no random numbers
 surv *= prod(1 - ((1 << 32) % prod(m for m in range(39 - 4 * w - 3, 39 - 4 * w + 1) if m >= 2)) / 2 ** 32 for w in range(10))
 p = 24235203726 / total * surv
 z = (t["accepted"] - N * p) / (N * p * (1 - p)) ** 0.5
@@ -61,4 +60,14 @@ split = np.array([9820068156, 8126568540, 6288567030], float)
 out["seat_first_1nt"] = {"accepted": t["accepted"], "expected": N * p, "z": z, "p_two_sided": float(2 * norm.sf(abs(z))),
                          "kernel_ms": st.kernel_ms,
                          "south_hcp_split": chi2_p(t["hcp"][2][15:18], split / split.sum() * t["accepted"])}
+# the whole rank / unrank path at acceptance 1 (an all-admitting window on South), N / 10 raw deals
+from bridge_mc_b200.engine import seat_spec
+cons = Constraints([None, None, seat_spec(hcp=(0, 37)), None]).set_mode(2)
+_, t, st = eng.sample(cons, n_raw=N // 10, seed=20261022, cap=0)
+acc = t["accepted"]
+len_num = np.array([comb(13, l) * comb(39, 13 - l) for l in range(14)], float)
+out["seat_first_all_hands"] = {"raw": N // 10, "accepted": acc, "voided": t["voided"], "kernel_ms": st.kernel_ms,
+                               "hcp": [chi2_p(t["hcp"][k], hcp_num / total * acc) for k in range(4)],
+                               "shape": [chi2_p(t["shape"][k], shape_num / total * acc) for k in range(4)],
+                               "south_len": [chi2_p(t["len"][2][su], len_num / total * acc) for su in range(4)]}
 print(json.dumps(out, indent=1))
