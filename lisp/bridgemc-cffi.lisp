@@ -23,6 +23,15 @@
 (cffi:defcfun "bmc_constraints_create" :int (specs :pointer) (rules :pointer) (out :pointer))
 (cffi:defcfun "bmc_constraints_destroy" :void (c :pointer))
 (cffi:defcfun "bmc_constraints_set_reference_order" :int (c :pointer) (n-defs :int))
+(cffi:defcfun "bmc_constraints_set_mode" :int (c :pointer) (mode :int))
+(cffi:defcfun "bmc_constraints_set_jit" :int (c :pointer) (on :int))
+;; what determines the deal behind a Philox index besides the seed (log them with a reproducible job)
+(cffi:defcfun "bmc_constraints_mode" :int (c :pointer))
+(cffi:defcfun "bmc_constraints_primary" :int (c :pointer))
+(cffi:defcfun "bmc_constraints_primary_hcp" :int (c :pointer) (lo :pointer) (hi :pointer))
+(cffi:defcfun "bmc_hist_base" :int
+  (ctx :pointer) (records :pointer) (n :uint64) (measures :pointer) (k :uint32)
+  (tuples :pointer) (counts :pointer) (cap :uint64) (n-unique :pointer))
 (cffi:defcfun "bmc_scheme_create" :int (table :string) (out :pointer))
 (cffi:defcfun "bmc_scheme_destroy" :void (s :pointer))
 (cffi:defcfun "bmc_sample" :int
