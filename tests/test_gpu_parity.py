@@ -144,11 +144,12 @@ def test_seat_first_windows_and_seats_vs_mirror(engine, seat, spec):
     specs[seat] = seat_spec(**spec)
     cons = Constraints(specs).set_mode(2)
     n = 150_000
-    got, tal, _ = engine.sample(cons, n_raw=n, seed=SEED + seat, first_index=3)      # odd first index: a split pair
+    first = 3 if seat % 2 == 0 else (1 << 45) + 7                                    # odd first index: a split pair
+    got, tal, _ = engine.sample(cons, n_raw=n, seed=SEED + seat, first_index=first)
     assert (cons.mode, cons.primary) == (2, seat)
     lo, hi = cons.primary_hcp
     assert (lo, hi) == (spec.get("hcp", (0, 37))[0], min(spec.get("hcp", (0, 37))[1], 37))
-    ref, va, vb = mirror_stream(cons, SEED + seat, 3, n)
+    ref, va, vb = mirror_stream(cons, SEED + seat, first, n)
     acc, _ = engine.filter(ref, cons, None, want_features=False)
     keep = (acc == 1) & ~va & ~vb
     assert tal["raw"] == n and tal["accepted"] == int(keep.sum()) == got.shape[0]
