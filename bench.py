@@ -92,6 +92,28 @@ def cpu_reference_rate(n_per_thread: int, threads: int, seed0: int = 1):
     return n_per_thread * threads / dt, sum(passed) / dt, dt
 
 
+def cpu_best_effort_rate(n_per_thread: int, threads: int):
+    """SURVEY 8d's second comparator: a careful scalar host implementation of the same job (Philox, partial
+    Fisher-Yates for South, popcount features, test-bid (1 NT); accepted deals completed) on all host threads.
+    Not the reference algorithm.  Returns (raw deals/s, accepted/s, seconds)."""
+    from oracle import oracle as O
+    L = O.lib()
+    acc = [0] * threads
+
+    def work(i):
+        cs = C.c_uint64()
+        acc[i] = L.orc_cpu_best_run(SEED, i << 40, n_per_thread, C.byref(cs))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return n_per_thread * threads / dt, sum(acc) / dt, dt
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -361,6 +383,13 @@ def run_gpu(args):
                 "accepted_per_s": p,
                 "sample": f"{n} builds/thread on {threads} threads ({dt:.1f} s) of the reference's distgen sampler "
                           f"(box ranges, per-deal rescan) + test-bid (1 NT); value = accepted/s / {P_1NT:.6f}"}
+            rb, ab, dtb = cpu_best_effort_rate(200_000, threads)
+            nb = max(200_000, int(200_000 * 3.0 / max(dtb, 1e-3)))
+            rb, ab, dtb = cpu_best_effort_rate(nb, threads)
+            line["cpu_baseline"]["best_effort"] = {
+                "value": rb, "unit": UNIT, "cores": threads, "accepted_per_s": ab,
+                "sample": f"{nb} raw deals/thread on {threads} threads ({dtb:.1f} s): scalar C, Philox + partial Fisher-Yates + "
+                          "popcount features + test-bid (1 NT) -- the honest CPU ceiling, not the reference algorithm"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -833,6 +833,63 @@ ORC_API void orc_gpu_deal_seatfirst_batch(uint64_t seed, uint64_t first, uint64_
         flags[i] = (uint8_t)orc_gpu_deal_seatfirst(seed, first + i, primary, hcp_lo, hcp_hi, &rec[2 * i], &rec[2 * i + 1]);
 }
 
+/* Best-effort CPU comparator (SURVEY 8d "ii"; NOT the reference algorithm and not a mirror of the GPU
+ * stream): what a careful scalar host implementation of the same job costs.  Per index: Philox4x32-10
+ * words, a partial Fisher-Yates shuffle of 13 cards for South by multiply-shift draws with Lemire
+ * rejection, popcount features, the test-bid (1 NT) test (balanced?, 15-17 HCP); accepted deals get the
+ * remaining 38 draws (a full deal).  Returns the number accepted; *checksum folds the accepted deals. */
+static inline uint32_t best_bounded(uint32_t *w, int *have, uint32_t ctr[4], const uint32_t key[2], uint32_t n)
+{
+    for (;;) {
+        if (*have == 0) { orc_philox4x32_10(ctr, key, w); ++ctr[2]; *have = 4; }
+        uint64_t p = (uint64_t)w[4 - (*have)--] * n;
+        if ((uint32_t)p >= (uint32_t)(-n) % n) return (uint32_t)(p >> 32);
+    }
+}
+ORC_API uint64_t orc_cpu_best_run(uint64_t seed, uint64_t first, uint64_t n, uint64_t *checksum)
+{
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint64_t accepted = 0, sum = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t idx = first + i;
+        uint32_t ctr[4] = { (uint32_t)idx, (uint32_t)(idx >> 32), 0, 7 }, w[4];
+        int have = 0;
+        uint8_t cards[52];
+        for (int c = 0; c < 52; ++c) cards[c] = (uint8_t)c;
+        uint64_t south = 0;
+        for (int k = 0; k < 13; ++k) {
+            const uint32_t j = (uint32_t)k + best_bounded(w, &have, ctr, key, 52u - (uint32_t)k);
+            const uint8_t t = cards[k]; cards[k] = cards[j]; cards[j] = t;
+            south |= 1ull << (16 * (cards[k] / 13) + cards[k] % 13);
+        }
+        /* features: lengths, suit power (J1 Q2 K3 A4), HCP, balanced? (bidding.cl:40-46) */
+        int len[4], pw[4], hcp = 0, weak = 0, ok = 1;
+        for (int su = 0; su < 4; ++su) {
+            const uint32_t lane = (uint32_t)(south >> (16 * su)) & 0x1FFFu;
+            len[su] = __builtin_popcount(lane);
+            pw[su] = (int)((lane >> 9) & 1) + 2 * (int)((lane >> 10) & 1) + 3 * (int)((lane >> 11) & 1) + 4 * (int)((lane >> 12) & 1);
+            hcp += pw[su];
+            weak += pw[su] < 3;
+            if (len[su] < 2 || len[su] > (su < 2 ? 5 : 4)) ok = 0;
+        }
+        if (!ok || hcp < 15 || hcp > 17 || weak >= 2) continue;
+        for (int k = 13; k < 51; ++k) {
+            const uint32_t j = (uint32_t)k + best_bounded(w, &have, ctr, key, 52u - (uint32_t)k);
+            const uint8_t t = cards[k]; cards[k] = cards[j]; cards[j] = t;
+        }
+        uint64_t lo = 0, hi = 0;
+        for (int k = 0; k < 52; ++k) {
+            const int owner = k < 13 ? 2 : (k < 26 ? 0 : (k < 39 ? 1 : 3)), bit = 16 * (cards[k] / 13) + cards[k] % 13;
+            lo |= (uint64_t)(owner & 1) << bit;
+            hi |= (uint64_t)(owner >> 1) << bit;
+        }
+        sum += lo ^ (hi << 1);
+        ++accepted;
+    }
+    if (checksum) *checksum = sum;
+    return accepted;
+}
+
 ORC_API void orc_gpu_deal_fixed_batch(uint64_t seed, uint64_t first, uint64_t n, const uint64_t fixed[4],
                                       uint64_t *rec, uint8_t *voided)
 {

@@ -115,6 +115,8 @@ def lib():
     L.orc_gpu_deal_fixed_batch.restype = None
     L.orc_gpu_deal_seatfirst_batch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_gpu_deal_seatfirst_batch.restype = None
+    L.orc_cpu_best_run.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.orc_cpu_best_run.restype = C.c_uint64
     L.orc_ref_run.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.orc_ref_run.restype = C.c_uint64
     L.orc_build_batch.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p]

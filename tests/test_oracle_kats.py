@@ -237,3 +237,17 @@ def test_gpu_deal_mirror_is_a_deal_and_void_rate():
     for k in range(4):
         assert all(bin(int(x)).count("1") == 13 for x in m[:500, k])
     assert 0.0005 < void.mean() < 0.004
+
+
+def test_best_effort_cpu_comparator_is_a_valid_sampler():
+    """bench.py's second CPU comparator (not the reference algorithm): its acceptance of test-bid (1 NT) must
+    agree with the exact probability 24 235 203 726 / C(52,13), and it is deterministic in (seed, index)."""
+    import ctypes as C
+    L = O.lib()
+    n = 1_000_000
+    c1, c2 = C.c_uint64(), C.c_uint64()
+    a1 = L.orc_cpu_best_run(5, 1 << 33, n, C.byref(c1))
+    a2 = L.orc_cpu_best_run(5, 1 << 33, n, C.byref(c2))
+    assert (a1, c1.value) == (a2, c2.value)
+    p = 24235203726 / 635013559600
+    assert abs(a1 - n * p) < 4 * (n * p * (1 - p)) ** 0.5

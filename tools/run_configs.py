@@ -113,20 +113,34 @@ def main():
         run("REF-order", cons, int(2e8 * scale), "fixed hand + 3 ranged seats in `build`'s sequential order (mode 3)")
         cons2 = Constraints([seat_spec(hcp=(15, 17), s=(5, None)), seat_spec(hcp=(10, 11), h=(4, None))]).set_reference_order(2)
         run("REF-order-2", cons2, int(2e8 * scale), "two ranged seats (15-17 with 5+ spades, then 10-11 with 4+ hearts), mode 3")
-    if "c4" in which and rank == 0:
+    if "c4" in which:
+        # score / IMP tallies over n deals, the index range split over the ranks, histograms all-reduced
         cs = [compscore.Contract(t).c_struct() for t in ("1NTS", "3NTS", "4HS", "4SS")] * 2
         vul = [0, 0, 0, 0, 1, 1, 1, 1]
         pairs = [0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6, 7]
-        n = int(1e8 * scale)
+        n = int(1e8 * scale) * world                       # weak scaling: 1e8 deals per GPU
+        first, per = bdist.rank_range(0, n, rank, world)
         eng.score_tally(cs, vul, pairs, n=1 << 20, seed=SEED)
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        th, ih, tab = eng.score_tally(cs, vul, pairs, n=n, seed=SEED)
-        dt = time.perf_counter() - t0
-        print(json.dumps({"config": "C4", "note": "base-score / match-points tallies, 8 contract x vulnerability rows, 6 IMP pairs, "
-                          "tricks = Philox stream 1 (the reference's trick source is out of scope)", "n_gpus": 1,
-                          "deals": n, "wall_ms": dt * 1e3, "deals_per_s": n / dt, "contract_evals_per_s": 8 * n / dt,
-                          "tricks_hist_row0": [int(x) for x in th[0]], "score_table_3NTS_vul": [int(x) for x in tab[5]]}))
+        th, ih, tab = eng.score_tally(cs, vul, pairs, n=per, seed=SEED, first_index=first)
+        hist = torch.from_numpy(np.concatenate([th.reshape(-1), ih.reshape(-1)]).astype(np.int64)).to(dev)
+        if world > 1:
+            dist.all_reduce(hist)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt[0])
+        hist = hist.cpu().numpy()
+        if rank == 0:
+            print(json.dumps({"config": "C4", "note": "base-score / match-points tallies, 8 contract x vulnerability rows, 6 IMP pairs, "
+                              "tricks = Philox stream 1 (the reference's trick source is out of scope); wall clock incl. the all-reduce",
+                              "n_gpus": world, "deals": n, "wall_ms": dt * 1e3, "deals_per_s": n / dt, "contract_evals_per_s": 8 * n / dt,
+                              "tricks_hist_row0": [int(x) for x in hist[:14]], "hist_checksum": int((hist * np.arange(1, hist.size + 1)).sum() % (1 << 61)),
+                              "score_table_3NTS_vul": [int(x) for x in tab[5]]}))
     if world > 1:
         dist.destroy_process_group()
 
