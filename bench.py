@@ -114,6 +114,41 @@ def cpu_best_effort_rate(n_per_thread: int, threads: int):
     return n_per_thread * threads / dt, sum(acc) / dt, dt
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the pinned record buffer
+    of the e2e leg is allocated next to the GPU's PCIe root.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        want = getattr(torch.cuda.get_device_properties(index), "pci_bus_id", None)
+        if want is not None:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(hi).bus == want:
+                    h = hi
+                    break
+        bus_id = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus_id = (bus_id.decode() if isinstance(bus_id, bytes) else bus_id).lower()
+        if len(bus_id.split(":")[0]) == 8:                 # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus_id = bus_id[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus_id}/numa_node").read())
+        if node < 0:
+            return "no NUMA node reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"node {node}: none of its CPUs is available to this process"
+        os.sched_setaffinity(0, allowed)
+        return f"node {node}, {len(allowed)} CPUs"
+    except Exception as e:                                  # pragma: no cover
+        return "unbound: " + repr(e)[:80]
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -240,6 +275,8 @@ def run_gpu(args):
         os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
     bdist.init_process_group("nccl", dev)
 
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     eng = Engine(local)
     stream = torch.cuda.Stream(dev)               # events must be recorded on the stream the kernels run on
     torch.cuda.set_stream(stream)
@@ -351,7 +388,8 @@ def run_gpu(args):
                        "l2": "no input buffers (counter-based RNG); 1.6 GB of records written per step >> 126 MB L2",
                        "e2e_note": "e2e copies all 1.6 GB of accepted records to pinned host memory every step (overlapped "
                                    "with the next wave); it is PCIe-bound, the device number is integer-issue bound",
-                       "parallelism": f"dp{world}: disjoint Philox index ranges + NCCL all-reduce of the {_lib.TALLY_WORDS * 8} B tally buffer"},
+                       "parallelism": f"dp{world}: disjoint Philox index ranges + NCCL all-reduce of the {_lib.TALLY_WORDS * 8} B tally buffer",
+                       "host_binding_rank0": numa},
             "accepted_per_s": acc_all / (ms * 1e-3),
             "acceptance": acc_all / max(1.0, raw_all),
             "sampler_mode": {1: "full-deal", 2: "seat-first"}[cons.mode],
