@@ -9,6 +9,8 @@ rec, _, _ = eng.sample(None, n_raw=1 << 22, seed=1)
 cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
 for _ in range(2):
     acc, feats = eng.filter(rec, cons, bidding.openings.scheme())
+for _ in range(2):
+    eng.filter(rec, None, None)                      # features only: the HBM-bound form of K2
 cs = [compscore.Contract(t).c_struct() for t in ("1NTS", "3NTS", "4HS", "4SS")]
 tr = np.random.default_rng(1).integers(0, 14, size=(1 << 22, 4)).astype(np.uint8)
 for _ in range(2):
