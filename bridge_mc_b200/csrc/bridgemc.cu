@@ -1059,17 +1059,17 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
     if (seq) blocks = ctx->sms * 4;
     if (jit) blocks = ctx->sms * jit->blocks_per_sm;
-    const uint64_t per_thread = seatfirst ? 2 * SF_PAIRS : 1;     // raw deals per thread per iteration
+    const uint64_t per_thread = seatfirst ? 4 * SF_CALLS : 1;     // raw deals per thread per iteration
     const uint64_t per_iter = (uint64_t)blocks * THREADS * per_thread;
     if (n < per_iter) blocks = (int)((n + THREADS * per_thread - 1) / (THREADS * per_thread));
     if (blocks < 1) blocks = 1;
     const uint64_t chunk = (uint64_t)blocks * THREADS * per_thread;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
     if (seatfirst) {
-        // a lane owns the index PAIRS (2p, 2p + 1): an odd first index or an odd end adds one pair
-        const uint64_t pairs = ((first + n + 1) >> 1) - (first >> 1);
-        const uint64_t per = (uint64_t)blocks * THREADS * SF_PAIRS;
-        a.iters = (uint32_t)((pairs + per - 1) / per);
+        // a lane owns index QUADS (4c .. 4c + 3, one Philox call): a misaligned first index or end adds one
+        const uint64_t calls = ((first + n + 3) >> 2) - (first >> 2);
+        const uint64_t per = (uint64_t)blocks * THREADS * SF_CALLS;
+        a.iters = (uint32_t)((calls + per - 1) / per);
     }
     if (jit) {
         void *params[] = {&a};

@@ -50,7 +50,7 @@ struct SampleArgs {
     uint64_t cap;
     unsigned long long *tallies;   // bmc_tallies as u64 words
     uint32_t tally_mask;
-    uint32_t iters;          // warp-iterations per warp (seat-first: each covers one pair of indices per lane)
+    uint32_t iters;          // warp-iterations per warp (seat-first: each covers 4 SF_CALLS indices per lane)
     uint32_t sf_q0;          // seat-first mode: initial Q of stage B (capacity 0 for the primary seat)
     uint32_t pad;
 };
@@ -233,8 +233,8 @@ __device__ __forceinline__ void sample_body(const SampleArgs &a)
 #define SF_MIN_BLOCKS 6
 #endif
 constexpr int SF_HIST_COPIES = 2;
-#ifndef SF_PAIRS
-#define SF_PAIRS 4            /* index pairs (Philox calls) per lane and iteration of stage A1 */
+#ifndef SF_CALLS
+#define SF_CALLS 4            /* Philox calls (four indices each) per lane and iteration of stage A1 */
 #endif
 constexpr int SF_QCAP1 = 128; // stage A1 -> A2 queue (32-bit entries); rounds that do not fit wait for a drain
 __constant__ LowTabs c_lowtabs = make_lowtabs();
@@ -308,14 +308,16 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         __syncwarp();
         const bool active = lane < count;
         const unsigned long long idx = a.first + off;
-        uint32_t w[4];
-        philox4x32_10(a.key, (uint32_t)(idx >> 1), (uint32_t)(idx >> 33), 0u, STREAM_SEATFIRST_RANK, w);
-        const bool second = (idx & 1ull) != 0ull;
+        uint32_t wh[4], wl[4];
+        philox4x32_10(a.key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK, wh);
+        philox4x32_10(a.key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK_LO, wl);
+        const uint32_t j = (uint32_t)idx & 3u;
+        const uint32_t u_hi = j < 2u ? (j == 0u ? wh[0] : wh[1]) : (j == 2u ? wh[2] : wh[3]);
+        const uint32_t u_lo = j < 2u ? (j == 0u ? wl[0] : wl[1]) : (j == 2u ? wl[2] : wl[3]);
         unsigned long long d;
         uint32_t magic, i, ell, m0, m1;
         // lanes past the end of the queue look up u = 0: class 0, nothing to scan
-        const uint32_t info = sf_find_class(a.cons.sf_tab, a.cons.sf_bmul, active ? (second ? w[2] : w[0]) : 0u,
-                                            active ? (second ? w[3] : w[1]) : 0u, d, magic);
+        const uint32_t info = sf_find_class(a.cons.sf_tab, a.cons.sf_bmul, active ? u_lo : 0u, active ? u_hi : 0u, d, magic);
         sf_split(d, (info >> 12) & 0x7FFu, magic, i, ell);
         const uint32_t H = sf_honours_of(info, i);
         sf_unrank_lows(s_low, ell, 13u - (uint32_t)__popc(H), m0, m1);
@@ -331,46 +333,56 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         }
     };
 
-    // Stage A1.  One Philox call yields the 64-bit uniforms of the two indices of a pair (2p, 2p + 1).
-    // Per iteration a lane tests SF_PAIRS pairs and keeps one survivor bit per index; the survivors are
-    // then queued as 32-bit offsets from a.first (a launch covers at most 2^31 indices, host), one per
-    // lane and round, and stage A2 recomputes their uniforms.  Rounds that do not fit wait for a drain.
+    // Stage A1.  The uniform of index i is u = (hi word << 32) | lo word, the words (i & 3) of the Philox
+    // calls with counter i >> 2 on streams 4 (hi) and 5 (lo).  u < theta is decided by the hi word alone
+    // unless it EQUALS theta's hi word (2^-32 per index), so one Philox call tests four indices; the lo
+    // call is made for ties, for the void check (u >= S C(52,13), hi word >= 0xFFFFFFCB) and by stage A2.
+    // Per iteration a lane tests SF_CALLS calls = 4 SF_CALLS indices and keeps one survivor bit per index;
+    // the survivors are queued as 32-bit offsets from a.first (a launch covers at most 2^31 indices,
+    // host), one per lane and round.  Rounds that do not fit wait for a drain.
     const uint32_t tid_g = (uint32_t)gwarp * 32u + lane;
-    const uint32_t stride = (uint32_t)total_warps * 32u;                       // pairs per pass of the grid
-    const unsigned long long base_pair = a.first >> 1;
-    const uint32_t odd = (uint32_t)a.first & 1u, n32 = (uint32_t)a.n;
-    const uint32_t full_iters = n32 / (2u * SF_PAIRS * stride);                // iterations before it: every index valid
-    const unsigned long long theta = a.cons.sf_theta;
+    const uint32_t stride = (uint32_t)total_warps * 32u;                       // calls per pass of the grid
+    const unsigned long long base_call = a.first >> 2;
+    const uint32_t mis = (uint32_t)a.first & 3u, n32 = (uint32_t)a.n;
+    const uint32_t full_iters = n32 / (4u * SF_CALLS * stride);                // iterations before it: every index valid
+    const uint32_t theta_hi = (uint32_t)(a.cons.sf_theta >> 32), void_hi = (uint32_t)(a.cons.sf_void >> 32);
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t it = 0, mask = 0, po0 = 0;
+    uint32_t it = 0, mask = 0, co0 = 0;
     bool pending = false;
     for (;;) {
         if (!pending && it < a.iters) {
-            po0 = it * (SF_PAIRS * stride) + tid_g;                            // pair offset of bit pair 0; bit pair k: + k * stride
+            co0 = it * (SF_CALLS * stride) + tid_g;                            // call offset of bits 0..3; bits 4k..4k+3: + k * stride
             mask = 0;
             uint32_t top = 0u;
+            bool tie = false;
 #pragma unroll
-            for (int k = 0; k < SF_PAIRS; ++k) {
+            for (int k = 0; k < SF_CALLS; ++k) {
                 uint32_t w[4];
-                const unsigned long long pair = base_pair + (po0 + (uint32_t)k * stride);
-                philox4x32_10(a.key, (uint32_t)pair, (uint32_t)(pair >> 32), 0u, STREAM_SEATFIRST_RANK, w);
-                if (((((unsigned long long)w[1]) << 32) | w[0]) < theta) mask |= 1u << (2 * k);
-                if (((((unsigned long long)w[3]) << 32) | w[2]) < theta) mask |= 2u << (2 * k);
-                top = max(top, max(w[1], w[3]));
-            }
-            if (__any_sync(0xFFFFFFFFu, top >= (uint32_t)(a.cons.sf_void >> 32)) || it == 0u || it >= full_iters) {
-                // edge iterations: drop the indices outside [first, first + n); 1.2e-8 per index: the void check
-#pragma unroll 1
-                for (int k = 0; k < SF_PAIRS; ++k) {
-                    uint32_t w[4];
-                    const uint32_t po = po0 + (uint32_t)k * stride;
-                    const unsigned long long pair = base_pair + po;
-                    philox4x32_10(a.key, (uint32_t)pair, (uint32_t)(pair >> 32), 0u, STREAM_SEATFIRST_RANK, w);
+                const unsigned long long call = base_call + (co0 + (uint32_t)k * stride);
+                philox4x32_10(a.key, (uint32_t)call, (uint32_t)(call >> 32), 0u, STREAM_SEATFIRST_RANK, w);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const bool valid = 2u * po + (uint32_t)j - odd < n32;      // wraps for the index before a.first
-                        if (!valid) mask &= ~(1u << (2 * k + j));
-                        if (valid && ((((unsigned long long)w[2 * j + 1]) << 32) | w[2 * j]) >= a.cons.sf_void) ++n_void;
+                for (int j = 0; j < 4; ++j) {
+                    if (w[j] < theta_hi) mask |= 1u << (4 * k + j);
+                    tie = tie || w[j] == theta_hi;
+                    top = max(top, w[j]);
+                }
+            }
+            if (__any_sync(0xFFFFFFFFu, tie || top >= void_hi) || it == 0u || it >= full_iters) {
+                // edge iterations: drop the indices outside [first, first + n); rare: ties and the void check
+#pragma unroll 1
+                for (int k = 0; k < SF_CALLS; ++k) {
+                    uint32_t wh[4], wl[4];
+                    const uint32_t co = co0 + (uint32_t)k * stride;
+                    const unsigned long long call = base_call + co;
+                    philox4x32_10(a.key, (uint32_t)call, (uint32_t)(call >> 32), 0u, STREAM_SEATFIRST_RANK, wh);
+                    philox4x32_10(a.key, (uint32_t)call, (uint32_t)(call >> 32), 0u, STREAM_SEATFIRST_RANK_LO, wl);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool valid = 4u * co + (uint32_t)j - mis < n32;      // wraps for the indices before a.first
+                        const unsigned long long u = (((unsigned long long)wh[j]) << 32) | wl[j];
+                        const uint32_t bit = 1u << (4 * k + j);
+                        mask = (valid && u < a.cons.sf_theta) ? (mask | bit) : (mask & ~bit);
+                        if (valid && u >= a.cons.sf_void) ++n_void;
                     }
                 }
             }
@@ -385,7 +397,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
             if (mask != 0u) {
                 const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
                 mask &= mask - 1u;
-                s_q1[warp][(t1 + __popc(bal & lt)) % SF_QCAP1] = 2u * (po0 + (b >> 1) * stride) + (b & 1u) - odd;
+                s_q1[warp][(t1 + __popc(bal & lt)) % SF_QCAP1] = 4u * (co0 + (b >> 2) * stride) + (b & 3u) - mis;
             }
             t1 += __popc(bal);
         }

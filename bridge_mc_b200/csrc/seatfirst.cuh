@@ -6,7 +6,8 @@
 // factors.  The sampler therefore runs in stages with a warp-level compaction queue between them, so
 // every stage executes on full warps:
 //   A1  the RANK of the primary seat's hand in an order that puts the honour holdings with an
-//       admissible HCP first (half a Philox call, one 64-bit compare)          -> HCP range
+//       admissible HCP first (a quarter of a Philox call, one 32-bit compare; the low word of the
+//       rank is drawn only for ties, 2^-32 per index)                          -> HCP range
 //   A2  unrank the hand from the same uniform: honour counts, their suits, the low cards suit by
 //       suit (no further random numbers)                                       -> all ranges of the seat
 //   B   the other 39 cards to the other three seats (3 Philox calls, digits + Lemire rejection as in
@@ -32,7 +33,7 @@ namespace bmc {
 constexpr uint32_t STREAM_SEATFIRST_B = 3u;       // (stream 2 belonged to the card-by-card stage A of earlier builds)
 
 // ---- stage A1, rank form -----------------------------------------------------------
-constexpr uint32_t STREAM_SEATFIRST_RANK = 4u;
+constexpr uint32_t STREAM_SEATFIRST_RANK = 4u, STREAM_SEATFIRST_RANK_LO = 5u;   // hi and lo word of u
 constexpr int RANK_TAB_ENTRIES = 640;       // 625 classes at most, then entries no u reaches
 constexpr int SF_BUCKETS = 256;
 

@@ -722,8 +722,8 @@ ORC_API int orc_gpu_deal_fixed(uint64_t seed, uint64_t index, const uint64_t fix
  * Stage A1: the honour holding of the primary seat is drawn BY RANK.  The 625 count classes
  * (nJ nQ nK nA), weight C(4,nJ) C(4,nQ) C(4,nK) C(4,nA) C(36, 13 - n), are laid out on
  * [0, C(52,13)) with the classes whose HCP lies in [hcp_lo, hcp_hi] first (ascending class id
- * nJ + 5 nQ + 25 nK + 125 nA within each group); u = 64 bits of Philox stream 4 (counter =
- * index >> 1, words 2 (index & 1) and 2 (index & 1) + 1), rank = u / S with S = floor(2^64 /
+ * nJ + 5 nQ + 25 nK + 125 nA within each group); u = (hi << 32) | lo, the words (index & 3) of the
+ * Philox calls with counter index >> 2 on streams 4 (hi) and 5 (lo); rank = u / S with S = floor(2^64 /
  * C(52,13)); u >= S C(52,13) voids the index.  The identity of the honours comes from
  * (u - S cum) mod I, I = product of the C(4, n.), as mixed-radix digits J first.
  * Stage A2: with q = (u - S cum) / S, i = q mod I picks the honours and ell = q / I, uniform on
@@ -744,12 +744,13 @@ ORC_API uint64_t orc_gpu_seatfirst_hand(uint64_t seed, uint64_t index, int hcp_l
     const uint64_t N = 635013559600ull;
     const uint64_t S = (uint64_t)((((unsigned __int128)1) << 64) / N);
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-    uint32_t w[4];
-    uint64_t pair = index >> 1;
-    uint32_t ctr[4] = { (uint32_t)pair, (uint32_t)(pair >> 32), 0, 4 };
-    orc_philox4x32_10(ctr, key, w);
-    const int j = (int)(index & 1);
-    const uint64_t u = ((uint64_t)w[2 * j + 1] << 32) | w[2 * j];
+    uint32_t wh[4], wl[4];
+    uint64_t call = index >> 2;
+    uint32_t ch[4] = { (uint32_t)call, (uint32_t)(call >> 32), 0, 4 }, cl[4] = { (uint32_t)call, (uint32_t)(call >> 32), 0, 5 };
+    orc_philox4x32_10(ch, key, wh);
+    orc_philox4x32_10(cl, key, wl);
+    const int j = (int)(index & 3);
+    const uint64_t u = ((uint64_t)wh[j] << 32) | wl[j];
     int vd = 0;
     *a1_pass = 0;
     if (u >= N * S) { *voided = 1; return 0; }
