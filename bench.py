@@ -36,10 +36,10 @@ SEED = 0x6272696467656D63
 # Algorithmic integer work of one raw deal on the hot kernel for this workload ("W_int"):
 # thread-level integer instructions per raw deal, counted by ncu on the committed kernels
 # (sass__thread_inst_executed / raw deals of the launch):
-#   seat-first sampler  128  profiles/r01_prof_c2_rankfirst_2p28.txt  (3.42e10 thread instructions for a
+#   seat-first sampler  116  profiles/r01_prof_c2_rankfirst_2p28.txt  (3.10e10 thread instructions for a
 #                            2^28-deal launch; 248 before stage A became a rank draw)
 #   full-deal sampler   649  profiles/r01_c2_sample_kernel_v1.txt
-W_INT_BY_MODE = {1: 649, 2: 128}
+W_INT_BY_MODE = {1: 649, 2: 116}
 # DRAM bytes of one 2^28-deal seat-first launch that stores its 10.2 M records (163 MB algorithmic): ncu
 # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_launches_bench_rankfirst.csv (the rest is still in L2 at kernel end)
 TRAFFIC_BYTES_BY_MODE = {1: None, 2: 101_600_000}
