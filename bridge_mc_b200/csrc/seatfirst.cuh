@@ -49,7 +49,7 @@ static_assert(SF_HANDS * (SF_S + 1ull) < SF_HANDS * SF_S, "S = floor(2^64 / C(52
 //                      fewer than l cards in suit st when k low cards go to suits st..3 (0xFFFFFFFF past the end);
 //   c9[l] = { C(9,l), floor(2^32 / C(9,l)), index of the first l-subset in subset9, 0 };
 //   subset9 = the 512 subsets of nine cards ordered by size, then by value.
-struct LowTabs {
+struct alignas(16) LowTabs {
     uint32_t prefix[3][14][16];
     uint32_t c9[10][4];
     uint16_t subset9[512];
@@ -90,6 +90,25 @@ __host__ __device__ constexpr LowTabs make_lowtabs()
     return t;
 }
 
+// High halves of products; host versions so that the unranking arithmetic can be checked exhaustively on
+// the CPU (tests/unrank_selftest.cu).
+__host__ __device__ __forceinline__ uint32_t sf_mulhi32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((unsigned long long)a * b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ unsigned long long sf_mulhi64(unsigned long long a, unsigned long long b)
+{
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
 // Table entry (uint4): x,y = S * (weight of the classes before this one) as lo,hi;
 // z = nJ | nQ<<3 | nK<<6 | nA<<9 | I<<12;  w = floor(2^32 / I) (2^32 - 1 for I = 1).
 // The table is followed by SF_BUCKETS 16-bit entries: bucket[j] = the class holding the smallest u with
@@ -101,7 +120,7 @@ __device__ __forceinline__ uint32_t sf_find_class(const uint4 *__restrict__ tab,
 {
     const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
     const uint16_t *bucket = reinterpret_cast<const uint16_t *>(tab + RANK_TAB_ENTRIES);
-    uint32_t pos = __ldg(bucket + min(__umulhi(u_hi, bmul), (uint32_t)SF_BUCKETS - 1u));
+    uint32_t pos = __ldg(bucket + min(sf_mulhi32(u_hi, bmul), (uint32_t)SF_BUCKETS - 1u));
     for (;;) {
         const uint2 c = __ldg(reinterpret_cast<const uint2 *>(tab + pos + 1u));
         if ((((unsigned long long)c.y << 32) | c.x) > u || pos >= (uint32_t)RANK_TAB_ENTRIES - 2u) break;
@@ -115,17 +134,17 @@ __device__ __forceinline__ uint32_t sf_find_class(const uint4 *__restrict__ tab,
 
 // d uniform on [0, S I L): q = d / S is uniform on [0, I L); i = q mod I picks the identity of the
 // honours, ell = q / I the low cards -- exactly uniform and independent.  q < 2^42, I <= 1296.
-__device__ __forceinline__ void sf_split(unsigned long long d, uint32_t I, uint32_t magic, uint32_t &i, uint32_t &ell)
+__host__ __device__ __forceinline__ void sf_split(unsigned long long d, uint32_t I, uint32_t magic, uint32_t &i, uint32_t &ell)
 {
-    unsigned long long q = __umul64hi(d, SF_S_RECIP);     // q or q - 1 (- 2 never: d < 2^64, see the mirror's test)
+    unsigned long long q = sf_mulhi64(d, SF_S_RECIP);     // floor(d / S) or one less (tests/unrank_selftest.cu)
     unsigned long long r = d - q * SF_S;
     if (r >= SF_S) { r -= SF_S; ++q; }
     if (r >= SF_S) { r -= SF_S; ++q; }
     const uint32_t qh = (uint32_t)(q >> 21), ql = (uint32_t)q & 0x1FFFFFu;     // long division in base 2^21
-    uint32_t a = __umulhi(qh, magic), ra = qh - a * I;
+    uint32_t a = sf_mulhi32(qh, magic), ra = qh - a * I;
     if (ra >= I) { ra -= I; ++a; }
     const uint32_t t = (ra << 21) | ql;                   // < 1296 * 2^21 < 2^32
-    uint32_t b = __umulhi(t, magic);
+    uint32_t b = sf_mulhi32(t, magic);
     i = t - b * I;
     if (i >= I) { i -= I; ++b; }
     ell = (a << 21) + b;
@@ -133,7 +152,7 @@ __device__ __forceinline__ void sf_split(unsigned long long d, uint32_t I, uint3
 
 // Identity of the honours: i in [0, I) as mixed-radix digits (J first) over the C(4, n.) subsets of suits.
 // Returns H: bit 4*suit + level (J Q K A = 0..3) set where the seat holds that honour.
-__device__ __forceinline__ uint32_t sf_honours_of(uint32_t info, uint32_t i)
+__host__ __device__ __forceinline__ uint32_t sf_honours_of(uint32_t info, uint32_t i)
 {
     uint32_t H = 0;
 #pragma unroll
@@ -155,26 +174,26 @@ __device__ __forceinline__ uint32_t sf_honours_of(uint32_t info, uint32_t i)
 // The k low cards of the hand from their rank ell in [0, C(36,k)): suit by suit (c d h s), the length
 // by a search over prefix[st][k], the cards by the subset table.  Returns the two lane-layout words
 // (low nine bits of each 16-bit lane).
-__device__ __forceinline__ void sf_unrank_lows(const LowTabs &T, uint32_t ell, uint32_t k, uint32_t &m0, uint32_t &m1)
+__host__ __device__ __forceinline__ void sf_unrank_lows(const LowTabs &T, uint32_t ell, uint32_t k, uint32_t &m0, uint32_t &m1)
 {
     uint32_t sub[4];
-    k = min(k, 13u);
+    k = k < 13u ? k : 13u;
 #pragma unroll
     for (int st = 0; st < 3; ++st) {
         const uint32_t *row = T.prefix[st][k];
         uint32_t l = 0;
 #pragma unroll
         for (int s = 8; s != 0; s >>= 1) if (row[l + s] <= ell) l += s;
-        l = min(l, 9u);
+        l = l < 9u ? l : 9u;
         ell -= row[l];
         const uint4 e = *reinterpret_cast<const uint4 *>(T.c9[l]);
-        uint32_t q = __umulhi(ell, e.y), r = ell - q * e.x;            // ell = q C(9,l) + r
+        uint32_t q = sf_mulhi32(ell, e.y), r = ell - q * e.x;          // ell = q C(9,l) + r
         if (r >= e.x) { r -= e.x; ++q; }
         sub[st] = T.subset9[(e.z + r) & 511u];
         ell = q;
-        k = min(k - l, 13u);
+        k = k - l < 13u ? k - l : 13u;
     }
-    const uint32_t l3 = min(k, 9u);
+    const uint32_t l3 = k < 9u ? k : 9u;
     sub[3] = T.subset9[(T.c9[l3][2] + ell) & 511u];
     m0 = sub[0] | (sub[1] << 16);
     m1 = sub[2] | (sub[3] << 16);

@@ -265,3 +265,19 @@ def test_further_bid_table_shape():
     t2 = bidding.further_bid("(and (>= hcp 6) (>= S 4))", "(and (>= hcp 12) (<= hcp 22) (>= D 5) (>= S 4))", (2, "S"))
     assert t2.bids() == [(5, "D"), None, (4, "D"), (5, "D"), (3, "D"), (4, "S"), None, (3, "S"), (5, "S")]
     assert t2.scheme().size == len(t2.rows)
+
+
+def test_unranking_arithmetic_selftest(tmp_path):
+    """tests/unrank_selftest.cu: the seat-first sampler's unranking helpers (seatfirst.cuh) compiled for the HOST --
+    exact division by S and by the class multiplicities, bijectivity of the honour and low-card maps, the
+    compile-time binomial tables"""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "unrank_selftest")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "unrank_selftest.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "unrank_selftest: ok" in out.stdout, out.stdout[-2000:]
