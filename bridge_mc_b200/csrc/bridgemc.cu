@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_c
         }
         n_raw += valid ? 1u : 0u;
         n_bad += (valid && bad) ? 1u : 0u;
-        stage_b(a, pl, valid && !bad, hist, s_shape, lane, s_feat[warp], 0u);
+        stage_b(a, pl, valid && !bad, hist, s_shape, lane, s_feat[warp], 0u);     // nothing left to test
     }
     {
         unsigned long long r64 = n_raw, v64 = n_bad;
@@ -744,7 +744,11 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     for (int s = 0; s < 4; ++s)
         if (total_lo[F_C + s] > 13) return fail(BMC_E_BAD_RANGE, "Can't infer correct limit!: minimum suit lengths exceed 13");
     c->dev.primary = 0;
+    c->dev.n_prog = 0;
     c->dev.b1_mask = 0xFu;
+    c->dev.pad = 0;
+    for (int k = 0; k < 4; ++k)
+        if (c->dev.seat[k].active && c->dev.seat[k].prog != 0xFFFFFFFFu) c->dev.n_prog++;
     double best = 2.0;
     for (int k = 0; k < 4; ++k)
         if (c->dev.seat[k].active && selectivity[k] < best) { best = selectivity[k]; c->dev.primary = (uint32_t)k; }
@@ -1139,7 +1143,7 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
             }
             cc->dev.b1_mask = 0xFu;
             if (cc->resolved == 2 && dev.n_active >= 3) {
-                // choose the most selective other seat to be tested together with the primary seat
+                // the most selective other seat: tested together with the primary seat by the compiled-rule kernel
                 double best = 2.0;
                 int second = -1;
                 for (int k = 0; k < 4; ++k) {

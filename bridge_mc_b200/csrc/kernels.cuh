@@ -25,8 +25,9 @@ struct ConsDev {
     SeatC seat[4];
     uint32_t n_active;       // number of constrained seats
     uint32_t primary;        // seat tested in stage A
-    uint32_t b1_mask;        // seat-first mode: seats fully tested right after the deal is completed (0xF: all of them);
-                             // the others are tested after one more compaction
+    uint32_t n_prog;         // constrained seats with a rule program (seat-first mode: 0 = no second stage B)
+    uint32_t b1_mask;        // compiled-rule (NVRTC) build of the seat-first kernel: seats fully tested in stage B1 (the
+    uint32_t pad;            // primary and the most selective other seat, chosen by calibration); the rest follow in B2
     uint32_t sf_bmul;        // seat-first stage A2: bucket of a survivor = umulhi(u_hi, sf_bmul) (seatfirst.cuh)
     const uint32_t *code;    // device pointer, programs of all seats
     const uint4 *sf_tab;     // seat-first stage A1: class table of the primary seat (seatfirst.cuh), in the code buffer
@@ -62,19 +63,22 @@ __device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0
     m1 = (pl.lo1 ^ xl) & (pl.hi1 ^ xh) & 0x1FFF1FFFu;
 }
 
-// Full test (ranges + rule program) of the constrained seats selected by `mask`.
-__device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl, uint32_t mask, uint32_t *scratch, unsigned lane)
+// Test of the constrained seats: their ranges (what & TEST_RANGES), their rule programs (what & TEST_PROGS).
+// `what` carries the seats to look at in bits 4..7 (TEST_SEATS(mask)); TEST_ALL = everything of every seat.
+constexpr uint32_t TEST_RANGES = 1u, TEST_PROGS = 2u, TEST_ALL = 0xF3u;
+__host__ __device__ constexpr uint32_t TEST_SEATS(uint32_t mask) { return (mask & 0xFu) << 4; }
+__device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl, uint32_t what, uint32_t *scratch, unsigned lane)
 {
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const SeatC &c = a.cons.seat[k];
-        if (c.active && ((mask >> k) & 1u)) {
+        if (c.active && ((what >> (4 + k)) & 1u) && ((what & TEST_RANGES) || c.prog != 0xFFFFFFFFu)) {
             uint32_t m0, m1;
             seat_words(pl, k, m0, m1);
             const Feat f = hand_features(m0, m1);
-            ok = ok && seat_ranges_ok(c, f);
-            if (c.prog != 0xFFFFFFFFu) {
+            if (what & TEST_RANGES) ok = ok && seat_ranges_ok(c, f);
+            if ((what & TEST_PROGS) && c.prog != 0xFFFFFFFFu) {
                 bool err = false;
 #ifdef BMC_JIT
                 const bool v = bmc_jit_seat_rule(k, f, err);        // the seat's rule form, compiled to native code
@@ -88,11 +92,11 @@ __device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl
     return ok;
 }
 
-// Stage B: full test of the seats in `mask`, then tallies and the compacted store.
+// Stage B: test of the constrained seats (`what`: ranges, programs or both), then tallies and the compacted store.
 __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
-                                        const uint8_t *shape_lut, unsigned lane, uint32_t *scratch, uint32_t mask = 0xFu)
+                                        const uint8_t *shape_lut, unsigned lane, uint32_t *scratch, uint32_t what = TEST_ALL)
 {
-    const bool ok = seats_pass(a, pl, mask, scratch, lane) && active;
+    const bool ok = seats_pass(a, pl, what, scratch, lane) && active;
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
     if (bal == 0u) return;
     const unsigned cnt = __popc(bal);
@@ -261,7 +265,19 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
     uint4 *q2 = s_q2[warp], *q3 = s_q3[warp];
     unsigned h3 = 0, t3 = 0;
-    const uint32_t b1_mask = a.cons.b1_mask & 0xFu, b2_mask = ~b1_mask & 0xFu;
+    // Stage B in two steps with a compaction between them, when there is something to gain:
+    //   interpreted rule programs: B1 = the cheap range tests of every seat, B2 = the programs, on full warps of
+    //                              deals that can still be accepted;
+    //   compiled rule forms (NVRTC build): B1 = ranges and rules of the primary and the most selective other
+    //                              seat (b1_mask, calibrated), B2 = the remaining seats.
+#ifdef BMC_JIT
+    const uint32_t rest = ~a.cons.b1_mask & 0xFu;
+    const bool two_stage = rest != 0u;
+    const uint32_t what1 = TEST_SEATS(a.cons.b1_mask) | TEST_RANGES | TEST_PROGS, what2 = TEST_SEATS(rest) | TEST_RANGES | TEST_PROGS;
+#else
+    const bool two_stage = a.cons.n_prog != 0u;
+    const uint32_t what1 = TEST_SEATS(0xFu) | TEST_RANGES, what2 = TEST_SEATS(0xFu) | TEST_PROGS;
+#endif
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
     uint32_t n_void = 0;                             // per thread
@@ -280,13 +296,11 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         const unsigned long long idx = a.first + r.z;
         const bool voided = deal_rest39(a.key, a.sf_q0, r.x, r.y, xl, xh, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
         n_void += (active && voided) ? 1u : 0u;
-        if (b2_mask == 0u) {
-            stage_b(a, pl, active && !voided, hist, s_shape, lane, s_feat[warp]);
+        if (!two_stage) {
+            stage_b(a, pl, active && !voided, hist, s_shape, lane, s_feat[warp], TEST_ALL);
             return;
         }
-        // B1: the primary seat's program and the most selective other seat; survivors are compacted
-        // once more so that the remaining (expensive, rarely needed) programs run on full warps
-        const bool ok = seats_pass(a, pl, b1_mask, s_feat[warp], lane) && active && !voided;
+        const bool ok = seats_pass(a, pl, what1, s_feat[warp], lane) && active && !voided;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
             if (ok) q3[(t3 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
@@ -297,7 +311,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
                 h3 += 32u;
                 __syncwarp();
                 const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-                stage_b(a, p3, true, hist, s_shape, lane, s_feat[warp], b2_mask);
+                stage_b(a, p3, true, hist, s_shape, lane, s_feat[warp], what2);
             }
         }
     };
@@ -418,7 +432,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     if (t3 - h3) {
         const uint4 r3 = q3[(h3 + lane) % QCAP];
         const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-        stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, s_feat[warp], b2_mask);
+        stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, s_feat[warp], what2);
     }
 
     {
