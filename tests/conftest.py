@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no binaries (they are git-ignored): build them once, as __graft_entry__.build() does."""
+    need = [os.path.join(ROOT, "bridge_mc_b200", "libbridgemc.so"), os.path.join(ROOT, "oracle", "libbmc_oracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def _have_gpu():
     try:
         import torch
