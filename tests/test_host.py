@@ -281,3 +281,17 @@ def test_unranking_arithmetic_selftest(tmp_path):
     subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "unrank_selftest: ok" in out.stdout, out.stdout[-2000:]
+
+
+def test_primary_seat_and_its_hcp_window_without_a_gpu():
+    """bmc_constraints_create is host code: the seat the seat-first sampler draws by rank, and the HCP window its
+    class table is ordered by (ranges of the spec, tightened by what the rule form implies)"""
+    from bridge_mc_b200.engine import Constraints, seat_spec
+    c = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    assert (c.primary, c.primary_hcp, c.mode) == (2, (15, 17), 0)
+    c = Constraints([None, seat_spec(hcp=(20, 21)), None, seat_spec(hcp=(0, 30))])
+    assert (c.primary, c.primary_hcp) == (1, (20, 21))
+    c = Constraints([seat_spec(s=(6, 13)), None, None, None])
+    assert (c.primary, c.primary_hcp) == (0, (0, 37))
+    c = Constraints([None, None, None, seat_spec(hcp=(12, None))], [None, None, None, "(< hcp 15)"])
+    assert (c.primary, c.primary_hcp) == (3, (12, 14))
