@@ -295,3 +295,40 @@ def test_primary_seat_and_its_hcp_window_without_a_gpu():
     assert (c.primary, c.primary_hcp) == (0, (0, 37))
     c = Constraints([None, None, None, seat_spec(hcp=(12, None))], [None, None, None, "(< hcp 15)"])
     assert (c.primary, c.primary_hcp) == (3, (12, 14))
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "sample_1nt")
+    libdir = os.path.join(root, "bridge_mc_b200")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "sample_1nt.c"), "-L" + libdir, "-lbridgemc", "-Wl,-rpath," + libdir,
+                    "-o", exe], check=True)
+    return exe
+
+
+def test_c_abi_from_plain_c_without_a_gpu(tmp_path):
+    """include/bridgemc.h is C99 and examples/sample_1nt.c links against the library; without a device the
+    program reports BMC_E_CUDA (exit 3) -- no CPU fallback"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by the gpu-marked variant")
+    out = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 3 and "needs a CUDA device" in out.stdout, out.stdout
+
+
+@pytest.mark.gpu
+def test_c_abi_from_plain_c(tmp_path):
+    import subprocess
+    out = subprocess.run([_build_c_example(tmp_path), "50000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mode 2, primary seat 2, HCP window 15-17" in out.stdout
+    m = re.search(r"accepted (\d+)\s+stored (\d+)", out.stdout)
+    assert m and int(m.group(1)) >= 50000 and int(m.group(2)) == 50000
+    assert out.stdout.count("\n") >= 7 and "S:" in out.stdout
