@@ -17,7 +17,10 @@
  *    returns BMC_E_CUDA;
  *  - re-entrant: a bmc_ctx owns one CUDA stream; use one ctx per calling
  *    thread (hunchentoot workers, dealgen<..>/sim{..} threads -- rest.cl:403,
- *    bridge.cl:3100,3115) or serialise calls on a shared one.
+ *    bridge.cl:3100,3115) or serialise calls on a shared one.  A
+ *    bmc_constraints / bmc_scheme may be shared by the contexts of ONE device
+ *    (its device-side tables are uploaded once, under a lock); with several
+ *    devices in one process create one per device.
  *
  * Encoding (bridge.cl:519-547): suit c=0 d=1 h=2 s=3, rank 0..12 = 2..A.
  * Seats 0..3 = N E S W.  A 64-bit "lane mask" holds one 16-bit lane per suit,
