@@ -286,3 +286,44 @@ def mc_deal(defs, measures, runs: int = 500, engine: Engine | None = None, seed:
     mc.sim(runs)
     rows = [list(itertools.chain.from_iterable(v if isinstance(v, list) else [v] for v in r)) for r in mc.select()]
     return mc, _hist.histogram(rows)
+
+
+def hand_or_def_parser(defs):
+    """rest.cl:279-285 hand-or-def-parser: the request's `defs`, a list of (type, text) pairs; type "hand" gives a
+    fixed hand (str2hand), anything else is the printed range def, e.g. "(:hcp (15 17) :s (5 nil))", read as Lisp
+    reads it.  The result is what mc_deal takes."""
+    out = []
+    for kind, val in defs:
+        if str(kind).lstrip(":").strip("|").lower() == "hand":
+            out.append(str2hand(val))
+        else:
+            out.append(plist_to_def(sexp.read(val)))
+    return out
+
+
+def measure_parser(names, best_tricks=None, engine: Engine | None = None):
+    """rest.cl:287-303 measure-parser: contract names ("3NTS", "4HSx") -> measures `msr-<name>` returning
+    [tricks, base-score of the contract with that many tricks].  The reference takes the tricks from
+    `best-tricks`, i.e. its `play-deal` estimator, which is outside this library: the caller
+    supplies it as `best_tricks(suit_sym, declarer_hand, left, dummy, right) -> int`.  [""] selects the
+    reference's default measure `best-outcomes`, which needs the same estimator."""
+    from . import compscore
+    if best_tricks is None:
+        raise NotImplementedError("msr-<contract> / best-outcomes need the reference's play-deal trick estimator, "
+                                  "which this library does not contain; pass best_tricks=")
+    if list(names) == [""]:
+        raise NotImplementedError("best-outcomes is defined by play-deal alone; name the contracts to score")
+    measures = []
+    for name in names:
+        contract = compscore.Contract(name)
+        shift = "NESW".index(contract.declarer)
+
+        def msr(_trump, *hands, _c=contract, _shift=shift, _name=name):
+            tricks = int(best_tricks(_c.suit_sym(), *roll(-_shift, list(hands))))
+            scored = compscore.Contract(_name).with_score(tricks)
+            return [tricks, compscore.base_score(scored, engine=engine)]
+
+        msr.__name__ = f"msr-{name}"
+        measures.append(msr)
+    return measures
+

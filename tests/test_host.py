@@ -332,3 +332,37 @@ def test_c_abi_from_plain_c(tmp_path):
     m = re.search(r"accepted (\d+)\s+stored (\d+)", out.stdout)
     assert m and int(m.group(1)) >= 50000 and int(m.group(2)) == 50000
     assert out.stdout.count("\n") >= 7 and "S:" in out.stdout
+
+
+def test_rest_parsers():
+    """rest.cl:279-303: hand-or-def-parser and the shape of measure-parser's result (the trick estimator behind
+    msr-<contract> is an explicit input: play-deal is outside the library)"""
+    from bridge_mc_b200.deal import hand_or_def_parser, measure_parser
+    south = "S: ♠ AKJ5 ♥ K1064 ♦ Q87 ♣ A6"
+    defs = hand_or_def_parser([(":|hand|", south), ("def", "(:hcp (10 12) :s (4 nil))"), ("def", "NIL"), ("def", "(:hcp 12)")])
+    assert defs[0] == cards.str2hand(south)
+    assert defs[1:] == [{"hcp": [10, 12], "s": [4, None]}, {}, {"hcp": 12}]
+    with pytest.raises(NotImplementedError):
+        measure_parser(["3NTS"])
+    ms = measure_parser(["3NTS", "4HNx"], best_tricks=lambda suit, a, b, c, d: 9)
+    assert [m.__name__ for m in ms] == ["msr-3NTS", "msr-4HNx"]
+
+
+@pytest.mark.gpu
+def test_measure_parser_scores_through_the_library():
+    from bridge_mc_b200.deal import Deal, McCase, measure_parser
+    from bridge_mc_b200.engine import Engine
+    eng = Engine.default()
+    seen = []
+
+    def best_tricks(suit, declarer, left, dummy, right):
+        seen.append((suit, declarer))
+        return 10 if suit == "H" else 9
+
+    ms = measure_parser(["3NTS", "4HNx"], best_tricks=best_tricks, engine=eng)
+    mc = McCase(Deal(engine=eng, seed=11), ms)
+    rows = mc.sim(3)
+    for hands, a, b in rows:
+        assert a == [9, 400] and b == [10, 590]            # 3NT= and 4Hx= not vulnerable (compscore.cl KAT values)
+    # the declarer's hand comes first: South for 3NTS, North for 4HNx
+    assert seen[0] == (None, rows[0][0][2]) and seen[1] == ("H", rows[0][0][0])
