@@ -20,6 +20,7 @@ from . import sexp
 from .cards import Hand, str2hand, unpack_deal, seat_masks
 from .engine import Constraints, DEFAULT_SEED, Engine, seat_spec
 from .infer import infer_distgen_params, plist_to_def, supply
+from .lists import roll  # noqa: F401  (bridge.cl:420-425; re-exported)
 
 
 class NoDealFound(RuntimeError):
@@ -54,14 +55,6 @@ def close_list(lst, base):
 def reorder(lst, indexes):
     """bridge.cl:202-204"""
     return [lst[i] if i < len(lst) else None for i in indexes]
-
-
-def roll(amount, lst):
-    """bridge.cl:420-425"""
-    if not lst:
-        return lst
-    a = (-amount) % len(lst)
-    return list(lst) if a == 0 else list(lst[a:]) + list(lst[:a])
 
 
 class Deal:

@@ -34,7 +34,11 @@ KEEP = {
     "HC-PERMUTS", "POSSIBLE-LC-LENS", "PERMUT-WEIGHT", "COMBINATIONS", "TAKE", "REMOVE-CARDS",
     "SUITS", "HANDID", "MAPCAR", "LENGTH", "SCANSTR", "FORMAT", "INVERT-ID", "BID-JUMP",
     "COMBINE-SHAPES", "CARD", "UNHAND", "REORDER",
+    # the small list utilities the deal path is written with (bridge_mc_b200/lists.py)
+    "CARDS-BY", "VALID-HCP-SUMS", "PUSH-POS", "ROLL", "ZIP-DEALS", "EVEN-SUBLISTS",
 }
+# comparisons of a tested call against a constant: (< (suit<> 'c 'd) 0)
+KEEP_NESTED = {"SUIT<>", "CARD<>"}
 
 
 def head_of(form):
@@ -49,7 +53,8 @@ def main():
             if head_of(form) != "TEST" or len(form) != 4:
                 continue
             tested = form[1]
-            if head_of(tested) not in KEEP:
+            nested = head_of(tested[1]) if isinstance(tested, list) and len(tested) > 1 else None
+            if head_of(tested) not in KEEP and not (head_of(tested) in ("<", ">", "=") and nested in KEEP_NESTED):
                 continue
             kats.append({
                 "file": fname, "line": line,

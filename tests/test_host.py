@@ -366,3 +366,73 @@ def test_measure_parser_scores_through_the_library():
         assert a == [9, 400] and b == [10, 590]            # 3NT= and 4Hx= not vulnerable (compscore.cl KAT values)
     # the declarer's hand comes first: South for 3NTS, North for 4HNx
     assert seen[0] == (None, rows[0][0][2]) and seen[1] == ("H", rows[0][0][0])
+
+
+def test_deal_path_list_utilities_kats():
+    """the reference's inline tests of the small list utilities its deal path is written with
+    (bridge_mc_b200/lists.py): take, remove-cards, cards-by, valid-hcp-sums, push-pos, roll, zip-deals,
+    even-sublists, suit<>, card<>; mod-or-push by hand (its test forms hold lambdas)"""
+    import operator
+    from bridge_mc_b200 import lists
+    fns = {"CARD-HCP": lists.card_hcp, "CARD-SUITNO": lists.card_suitno, "<": operator.lt, ">": operator.gt,
+           "=": operator.eq, "<=": operator.le, ">=": operator.ge}
+
+    def ev(x):
+        if isinstance(x, list) and x and x[0] == "QUOTE":
+            return x[1]
+        if isinstance(x, list) and x and x[0] == "FUNCTION":
+            return fns[str(x[1])]
+        if x == ["ALL-CARDS"]:
+            return lists.all_cards()
+        return x
+
+    def kwargs(rest):
+        out = {}
+        for i in range(0, len(rest), 2):
+            out[str(rest[i]).lstrip(":").lower()] = ev(rest[i + 1])
+        return out
+
+    def nil(x):                       # NIL and () are the same object in Lisp
+        if x is None:
+            return []
+        return [nil(y) for y in x] if isinstance(x, list) else x
+
+    seen = 0
+    for where, form, exp in load_kats("TAKE"):
+        assert lists.take(form[1], ev(form[2])) == exp, where
+        seen += 1
+    for where, form, exp in load_kats("REMOVE-CARDS"):
+        assert lists.remove_cards(ev(form[1]), ev(form[2])) == exp, where
+        seen += 1
+    for where, form, exp in load_kats("CARDS-BY"):
+        assert nil(lists.cards_by(ev(form[1]), ev(form[2]))) == nil(exp), where
+        seen += 1
+    for where, form, exp in load_kats("VALID-HCP-SUMS"):
+        assert lists.valid_hcp_sums(form[1], **kwargs(form[2:])) == exp, where
+        seen += 1
+    for where, form, exp in load_kats("PUSH-POS"):
+        assert nil(lists.push_pos(ev(form[1]), form[2], ev(form[3]))) == nil(exp), where
+        seen += 1
+    for where, form, exp in load_kats("ROLL"):
+        assert lists.roll(form[1], ev(form[2])) == exp and roll(form[1], ev(form[2])) == exp, where
+        seen += 1
+    for where, form, exp in load_kats("ZIP-DEALS"):
+        assert lists.zip_deals(ev(form[1])) == exp, where
+        seen += 1
+    for where, form, exp in load_kats("EVEN-SUBLISTS"):
+        assert lists.even_sublists(form[1], ev(form[2])) == exp, where
+        seen += 1
+    for head in ("<", ">", "="):
+        for where, form, exp in load_kats(head):
+            call = form[1]
+            f = lists.suit_cmp if call[0] == "SUIT<>" else lists.card_cmp
+            assert fns[head](f(ev(call[1]), ev(call[2])), form[2]) is truth(exp), where
+            seen += 1
+    assert seen == 3 + 1 + 3 + 7 + 4 + 4 + 1 + 1 + 7
+    # bridge.cl:466-484
+    dbl = lambda ref, x: x * 2 if ref == x else None
+    assert lists.mod_or_push(dbl, lambda x: x, [1, 4, 5, 6, 10], 1) == [2, 4, 5, 6, 10]
+    assert lists.mod_or_push(dbl, lambda x: x, [1, 4, 5, 6, 10], 7) == [1, 4, 5, 6, 10, 7]
+    assert lists.mod_or_push(dbl, lambda x: [x, 1], [], 1) == [[1, 1]]
+    with pytest.raises(lists.BadIndex):
+        lists.take(3, [1, 2, 3])
