@@ -474,6 +474,23 @@ static void deal_from(orc_rng *r, int *pile, int *npile, int amount, int *out, i
     }
 }
 
+/* bridge.cl:289-296 randcar-weights: index of the element chosen with probability weight / total
+ * (walk with `<`, subtracting); -1 when the total weight is 0 (the reference returns nil). */
+ORC_API int orc_randcar_weights(const uint64_t *weights, int n, uint64_t *rng_state)
+{
+    uint64_t total = 0;
+    for (int i = 0; i < n; ++i) total += weights[i];
+    if (total == 0) return -1;
+    orc_rng r = { *rng_state };
+    uint64_t w = rng_below(&r, total);
+    *rng_state = r.s;
+    for (int i = 0; i < n; ++i) {
+        if (w < weights[i]) return i;
+        w -= weights[i];
+    }
+    return n - 1;
+}
+
 /* bridge.cl:1075-1083 rand-hand: re-walks the pattern list recomputing every
  * weight (the per-deal rescan), with the reference's `>` comparison; then
  * rand-dist (1061-1063) / dist-from-hc (1053-1059) / randcar-weights (289-296)

@@ -251,3 +251,27 @@ def test_best_effort_cpu_comparator_is_a_valid_sampler():
     assert (a1, c1.value) == (a2, c2.value)
     p = 24235203726 / 635013559600
     assert abs(a1 - n * p) < 4 * (n * p * (1 - p)) ** 0.5
+
+
+def test_randcar_weights_statistical():
+    """bridge.cl:298-303: 1001 repetitions of 161 weighted draws from ((1 1) (5 2) (10 3)): every value <= 3 and
+    every sum in (380, 440) -- a 3.5-sigma window on the upper side, so the reference's own run fails about one
+    time in five; here the generator is seeded, the outcome is fixed"""
+    import ctypes as C
+    L = O.lib()
+    L.orc_randcar_weights.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_uint64)]
+    w = (C.c_uint64 * 3)(1, 5, 10)
+    st = C.c_uint64(20261020)
+    counts = [0, 0, 0]
+    for _ in range(1001):
+        total = 0
+        for _ in range(161):
+            k = L.orc_randcar_weights(w, 3, C.byref(st))
+            assert 0 <= k <= 2
+            counts[k] += 1
+            total += k + 1
+        assert 380 < total < 440
+    n = sum(counts)
+    for k, p in enumerate((1 / 16, 5 / 16, 10 / 16)):
+        assert abs(counts[k] - n * p) < 4.5 * (n * p * (1 - p)) ** 0.5
+    assert L.orc_randcar_weights((C.c_uint64 * 2)(0, 0), 2, C.byref(st)) == -1
