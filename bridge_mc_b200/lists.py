@@ -147,3 +147,29 @@ def even_sublists(size, lst):
     """bridge.cl:909-914"""
     lst = list(lst)
     return [lst[i:i + size] for i in range(0, len(lst), size)]
+
+
+def divlist(sectests, lst, map=None):
+    """bridge.cl:239-248: split `lst` into len(sectests) + 1 sections -- the first test an element passes, the
+    last section for none; each section in REVERSE order of arrival"""
+    acc = [None] * (len(sectests) + 1)
+    for x in lst:
+        sec = next((i for i, t in enumerate(sectests) if t(x)), len(sectests))
+        acc = push_pos(acc, sec, map(x) if map else x)
+    return acc
+
+
+def suit_breakdown(cards):
+    """bridge.cl:866-869: cards by suit, c d h and the rest (spades)"""
+    return divlist([lambda c, s=s: str(c[0]).upper() == s for s in ("C", "D", "H")], cards)
+
+
+def hcp_breakdown(cards):
+    """bridge.cl:871-874: cards by HCP value 0 1 2 3 and the rest (aces)"""
+    return divlist([lambda c, v=v: card_hcp(c) == v for v in range(4)], cards)
+
+
+def supply(cards):
+    """bridge.cl:876-878: per suit (n_low nJ nQ nK nA) of `cards`"""
+    return [[len(x or []) for x in hcp_breakdown(suit or [])] for suit in suit_breakdown(cards)]
+

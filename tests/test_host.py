@@ -436,3 +436,10 @@ def test_deal_path_list_utilities_kats():
     assert lists.mod_or_push(dbl, lambda x: [x, 1], [], 1) == [[1, 1]]
     with pytest.raises(lists.BadIndex):
         lists.take(3, [1, 2, 3])
+    # bridge.cl:250-258 divlist, and supply (876-878) against the bit-plane version the library's callers use
+    lt10, gt5 = (lambda x: 10 < x), (lambda x: 5 > x)
+    assert lists.divlist([lt10, gt5], [5, 10, 15, 20, 11, 1, 0, 3, 17, 20]) == [[20, 17, 11, 20, 15], [3, 0, 1], [10, 5]]
+    assert lists.divlist([lt10, gt5], [5, 10, 15, 20, 11, 1, 0, 3, 17, 20], map=lambda x: 2 * x) == [[40, 34, 22, 40, 30], [6, 0, 2], [20, 10]]
+    some = [c for i, c in enumerate(lists.all_cards()) if i % 3 != 1]
+    assert lists.supply(some) == infer.supply([13 * lists.suitno(s) + r for s, r in some])
+    assert lists.supply(lists.all_cards()) == [[9, 1, 1, 1, 1]] * 4
