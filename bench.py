@@ -317,7 +317,7 @@ def run_gpu(args):
     ev0.record(stream)
     for i in range(args.steps):
         st = step(args.warmup + i)
-        raw += st.raw; acc += st.accepted; kernel_ms += st.kernel_ms; launches += st.launches
+        raw += st.raw; acc += st.accepted; kernel_ms += st.kernel_ms; launches += st.waves      # sampler launches that ran
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

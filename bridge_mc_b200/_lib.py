@@ -12,8 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbridgemc.so")
 
 BMC_OK, BMC_E_INVALID, BMC_E_CUDA, BMC_E_BAD_RANGE, BMC_E_PARSE, BMC_E_NOMEM, BMC_E_CAPACITY = 0, -1, -2, -3, -4, -5, -6
-TALLY_HCP, TALLY_LEN, TALLY_SHAPE, TALLY_ALL = 1, 2, 4, 7
+TALLY_HCP, TALLY_LEN, TALLY_SHAPE, TALLY_ALL, TALLY_SCORE = 1, 2, 4, 7, 8
 HCP_BINS, LEN_BINS, SHAPE_BINS = 40, 14, 40
+SCORE_CONTRACTS, SCORE_PAIRS = 8, 8
 
 
 class BridgeMcError(RuntimeError):
@@ -35,7 +36,9 @@ class SeatSpec(C.Structure):
 class Tallies(C.Structure):
     _fields_ = [("raw", C.c_uint64), ("voided", C.c_uint64), ("accepted", C.c_uint64), ("stored", C.c_uint64),
                 ("hcp", (C.c_uint64 * HCP_BINS) * 4), ("len", ((C.c_uint64 * LEN_BINS) * 4) * 4),
-                ("shape", (C.c_uint64 * SHAPE_BINS) * 4)]
+                ("shape", (C.c_uint64 * SHAPE_BINS) * 4),
+                ("tricks", (C.c_uint64 * 14) * SCORE_CONTRACTS), ("imps", (C.c_uint64 * 49) * SCORE_PAIRS),
+                ("imp_dropped", C.c_uint64 * SCORE_PAIRS)]
 
 
 TALLY_WORDS = C.sizeof(Tallies) // 8
@@ -65,6 +68,7 @@ EXPORTS = [
     "bmc_init", "bmc_shutdown", "bmc_last_error", "bmc_version", "bmc_host_alloc", "bmc_host_free",
     "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_set_jit", "bmc_constraints_jit_ms", "bmc_constraints_mode", "bmc_constraints_primary", "bmc_constraints_primary_hcp",
     "bmc_scheme_create",
+    "bmc_constraints_set_scoring", "bmc_sample_indices", "bmc_sample_indices_dev", "bmc_expand", "bmc_expand_dev", "bmc_sample_multi",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
     "bmc_match_points", "bmc_score_tally", "bmc_hist_base", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
 ]
@@ -110,10 +114,17 @@ def load():
     L.bmc_scheme_destroy.restype = None
     L.bmc_sample.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, C.POINTER(Tallies), C.POINTER(Stats)]
     L.bmc_sample_dev.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, vp, C.POINTER(Stats)]
+    L.bmc_constraints_set_scoring.argtypes = [vp, C.POINTER(Contract), vp, u32, vp, u32]
+    L.bmc_sample_indices.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, C.POINTER(Tallies), C.POINTER(Stats)]
+    L.bmc_sample_indices_dev.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, vp, C.POINTER(Stats)]
+    L.bmc_expand.argtypes = [vp, vp, u64, u64, vp, u64, vp]
+    L.bmc_expand_dev.argtypes = [vp, vp, u64, u64, vp, u64, vp]
+    L.bmc_sample_multi.argtypes = [C.POINTER(C.c_int), C.c_int, vp, u64, u64, u64, u64, u64, u32, vp, u64, C.POINTER(Tallies),
+                                   C.POINTER(Stats)]
     L.bmc_filter.argtypes = [vp, vp, vp, vp, u64, vp, vp]
     L.bmc_score.argtypes = [vp, C.POINTER(Contract), vp, u32, vp, u64, vp]
     L.bmc_match_points.argtypes = [vp, vp, vp, u64, vp, vp]
-    L.bmc_score_tally.argtypes = [vp, C.POINTER(Contract), vp, u32, vp, u32, u64, u64, u64, vp, vp, vp]
+    L.bmc_score_tally.argtypes = [vp, C.POINTER(Contract), vp, u32, vp, u32, u64, u64, u64, vp, vp, vp, vp]
     L.bmc_hist_base.argtypes = [vp, vp, u64, C.POINTER(Measure), u32, vp, vp, u64, C.POINTER(u64)]
     L.bmc_int_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.bmc_launch_count.argtypes = [vp]

@@ -13,10 +13,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -54,59 +58,65 @@ static int fail(int code, const std::string &msg)
 // K1c: reference-order sampler (reforder.cuh): one thread = one deal, ranged seats sampled one
 // after the other exactly as `build` does (bridge.cl:1292-1319).
 // ---------------------------------------------------------------------------
+// The deal behind index `idx`; returns true where the reference signals an error for it (counted in `voided`).
+__device__ __forceinline__ bool reforder_deal(const SampleArgs &a, const SeqDev &q, unsigned long long idx, bool valid, Planes &pl)
+{
+    const uint32_t il = (uint32_t)idx, ih = (uint32_t)(idx >> 32);
+    uint32_t lo0 = a.fix.lo0, lo1 = a.fix.lo1, hi0 = a.fix.hi0, hi1 = a.fix.hi1;
+    uint32_t f0 = a.fix.free0, f1 = a.fix.free1;
+    bool bad = false;
+    for (uint32_t j = 0; j < q.n_stages; ++j) {
+        const SeqStage &st = q.st[j];
+        if (j > 0u && st.m <= 13u) break;                     // a LATER seat is implied once 13 cards remain (bridge.cl:1303);
+                                                              // the first def always goes through the root generator
+        const SeqRanges r = seq_infer(st, q.exhaust, f0, f1);
+        bad = bad || r.bad;
+        uint32_t h0 = 0, h1 = 0, att = 0;
+        bool need = valid && !bad;
+        while (need) {
+            const bool clean = seq_draw13(a.key, il, ih, STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, h0, h1);
+            if (clean && seq_hand_ok(r, h0, h1)) need = false;
+            else if (++att >= SEQ_MAX_ATTEMPTS) { bad = true; need = false; }
+        }
+        if (!valid || bad) { h0 = 0; h1 = 0; }
+        const uint32_t k = (uint32_t)st.seat;
+        if (k & 1u) { lo0 |= h0; lo1 |= h1; }
+        if (k & 2u) { hi0 |= h0; hi1 |= h1; }
+        f0 &= ~h0; f1 &= ~h1;
+    }
+    pl.lo0 = lo0; pl.lo1 = lo1; pl.hi0 = hi0; pl.hi1 = hi1;
+    if (q.n_rest) {                                           // deal-all 13 for the remaining seats
+        uint32_t att = 0;
+        bool need = valid && !bad;
+        while (need) {
+            const bool voided = deal_fixed_core(a.key, STREAM_REFORDER_REST + (att << 8), q.n_rest, q.q_rest, lo0, lo1, hi0, hi1,
+                                                f0, f1, q.thresh_rest, il, ih, pl);
+            if (!voided) need = false;
+            else if (++att >= 64u) { bad = true; need = false; }
+        }
+    }
+    return bad;
+}
+
 __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q)
 {
-    __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];
-    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
-    __shared__ uint8_t s_shape[14 * 14 * 14];
+    if (wave_cancelled(a)) return;
+    const SmemPlan sp = smem_plan(false, false, false, false, a.tally_mask);
+    uint32_t *smem = s_dyn;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SF_HIST_COPIES * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
-    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
+    tally_init(a, sp, smem, FULL_HIST_COPIES);
     __syncthreads();
-    uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
+    const TallyMem tm = tally_mem(sp, smem, warp);
     uint32_t n_raw = 0, n_bad = 0;
     const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
     unsigned long long off = (unsigned long long)blockIdx.x * THREADS + threadIdx.x;
     for (uint32_t it = 0; it < a.iters; ++it, off += stride) {
         const bool valid = off < a.n;
-        const unsigned long long idx = a.first + off;
-        const uint32_t il = (uint32_t)idx, ih = (uint32_t)(idx >> 32);
-        uint32_t lo0 = a.fix.lo0, lo1 = a.fix.lo1, hi0 = a.fix.hi0, hi1 = a.fix.hi1;
-        uint32_t f0 = a.fix.free0, f1 = a.fix.free1;
-        bool bad = false;
-        for (uint32_t j = 0; j < q.n_stages; ++j) {
-            const SeqStage &st = q.st[j];
-            if (j > 0u && st.m <= 13u) break;                     // a LATER seat is implied once 13 cards remain (bridge.cl:1303);
-                                                                  // the first def always goes through the root generator
-            const SeqRanges r = seq_infer(st, q.exhaust, f0, f1);
-            bad = bad || r.bad;
-            uint32_t h0 = 0, h1 = 0, att = 0;
-            bool need = valid && !bad;
-            while (need) {
-                const bool clean = seq_draw13(a.key, il, ih, STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, h0, h1);
-                if (clean && seq_hand_ok(r, h0, h1)) need = false;
-                else if (++att >= SEQ_MAX_ATTEMPTS) { bad = true; need = false; }
-            }
-            if (!valid || bad) { h0 = 0; h1 = 0; }
-            const uint32_t k = (uint32_t)st.seat;
-            if (k & 1u) { lo0 |= h0; lo1 |= h1; }
-            if (k & 2u) { hi0 |= h0; hi1 |= h1; }
-            f0 &= ~h0; f1 &= ~h1;
-        }
-        Planes pl = {lo0, lo1, hi0, hi1};
-        if (q.n_rest) {                                           // deal-all 13 for the remaining seats
-            uint32_t att = 0;
-            bool need = valid && !bad;
-            while (need) {
-                const bool voided = deal_fixed_core(a.key, STREAM_REFORDER_REST + (att << 8), q.n_rest, q.q_rest, lo0, lo1, hi0, hi1,
-                                                    f0, f1, q.thresh_rest, il, ih, pl);
-                if (!voided) need = false;
-                else if (++att >= 64u) { bad = true; need = false; }
-            }
-        }
+        Planes pl;
+        const bool bad = reforder_deal(a, q, a.first + off, valid, pl);
         n_raw += valid ? 1u : 0u;
         n_bad += (valid && bad) ? 1u : 0u;
-        stage_b(a, pl, valid && !bad, hist, s_shape, lane, s_feat[warp], 0u);     // nothing left to test
+        stage_b(a, pl, (uint32_t)off, valid && !bad, tm, lane, nullptr, 0u);     // nothing left to test
     }
     {
         unsigned long long r64 = n_raw, v64 = n_bad;
@@ -121,7 +131,38 @@ __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_c
         }
     }
     __syncthreads();
-    flush_hist(a, &s_hist[0][0], SF_HIST_COPIES);
+    flush_hist(a, sp, smem, FULL_HIST_COPIES);
+}
+
+// ---------------------------------------------------------------------------
+// Expansion of index records (bmc_expand): the deal behind an index is a pure function of (seed, index,
+// constraint, dealing mode), so an accepted deal can be shipped as its 32-bit index offset and regenerated on
+// demand.  One thread per offset; mode 1 full deal (free or with fixed hands), 2 seat-first, 3 reference order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q, int mode,
+                                                         const uint32_t *__restrict__ offsets, unsigned long long n, uint4 *__restrict__ out)
+{
+    __shared__ __align__(16) LowTabs s_low;
+    if (mode == 2) {
+        for (int i = threadIdx.x; i < (int)(sizeof(LowTabs) / 4); i += THREADS)
+            reinterpret_cast<uint32_t *>(&s_low)[i] = reinterpret_cast<const uint32_t *>(&c_lowtabs)[i];
+        __syncthreads();
+    }
+    const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+        const unsigned long long idx = a.first + offsets[i];
+        Planes pl;
+        if (mode == 3) reforder_deal(a, q, idx, true, pl);
+        else if (mode == 2) {
+            uint32_t m0, m1;
+            sf_primary_hand(a.key, a.cons.sf_tab, a.cons.sf_bmul, s_low, idx, true, m0, m1);
+            const uint32_t P = a.cons.primary;
+            const uint32_t xl = (P & 1u) ? 0xFFFFFFFFu : 0u, xh = (P & 2u) ? 0xFFFFFFFFu : 0u;
+            deal_rest39(a.key, a.sf_q0, m0, m1, xl, xh, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
+        } else if (a.fix.n_free != 52u) deal_fixed(a.key, a.fix, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
+        else deal52(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
+        out[i] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -201,55 +242,17 @@ __global__ void __launch_bounds__(256) filter_kernel(const __grid_constant__ Con
 // ---------------------------------------------------------------------------
 // K4: scoring
 // ---------------------------------------------------------------------------
-// contract-score (bridge.cl:3045-3069), written out from the rules of the
-// reference text (incl. its non-standard branches)
-__host__ __device__ inline int contract_score_dev(int suit, int tricks, int vul, int dbl, int level)
-{
-    if (level == 0) level = tricks - 6 > 1 ? tricks - 6 : 1;
-    const int r = tricks - level - 6;
-    const int mult = dbl == 2 ? 4 : (dbl ? 2 : 1);
-    if (r < 0) {
-        if (!dbl) return r * (vul ? 100 : 50);
-        int pen;
-        if (vul) pen = -200 + 300 * (r + 1);
-        else pen = r >= -3 ? 100 + 200 * r : -800 + 300 * (r + 3);      // -100 -300 -500, then -1100 ...
-        return pen * (dbl == 2 ? 2 : 1);
-    }
-    const int per = suit <= 1 ? 20 : 30;
-    const int trick_pts = ((suit == 4 ? 10 : 0) + per * level) * mult;
-    int bonus;
-    if (level == 7) bonus = vul ? 2000 : 1300;
-    else if (level == 6) bonus = vul ? 1250 : 800;
-    else bonus = trick_pts >= 100 ? (vul ? 500 : 300) : 50;
-    const int over = dbl ? (dbl == 2 ? 100 : 50) + (vul ? 200 : 100) * r : per * r;
-    return trick_pts + bonus + over;
-}
-__host__ __device__ inline int base_score_dev(bmc_contract c, int tricks, int vul)
-{
-    const int s = contract_score_dev(c.suit, tricks, vul, c.dbl, c.level);
-    return (c.declarer == 1 || c.declarer == 3) ? -s : s;
-}
-__constant__ int c_imp_pts[24] = {20, 50, 90, 130, 170, 220, 270, 320, 370, 430, 500, 600, 750, 900,
-                                  1100, 1300, 1500, 1750, 2000, 2300, 2500, 3000, 3500, 4000};
-__device__ __forceinline__ int imps_dev(int diff, bool &bad)
-{
-    const int a = diff < 0 ? -diff : diff;
-    int pos = 24;
-#pragma unroll
-    for (int i = 23; i >= 0; --i) if (a < c_imp_pts[i]) pos = i;
-    bad = pos == 24;
-    return bad ? 0 : (diff < 0 ? -pos : pos);
-}
-
-struct ContractTable { bmc_contract c[8]; uint8_t vul[8]; uint8_t pairs[16]; uint32_t n, n_pairs; };
+// contract-score / base-score / match-points and the stand-in trick source live in score.cuh (shared with the
+// sampling kernels, which tally scores over the accepted deals in stage B).
+static_assert(sizeof(ContractDev) == sizeof(bmc_contract), "ContractDev mirrors bmc_contract");
 
 // HBM-bound (1 B in, 4 B out per element): each thread scores four consecutive elements
 // (one 32-bit load, one 128-bit store); the contract index advances without a division.
-__global__ void __launch_bounds__(256) score_kernel(const bmc_contract *__restrict__ contracts, const uint8_t *__restrict__ vul,
+__global__ void __launch_bounds__(256) score_kernel(const ContractDev *__restrict__ contracts, const uint8_t *__restrict__ vul,
                                                     uint32_t nc, const uint8_t *__restrict__ tricks, unsigned long long total,
                                                     int32_t *__restrict__ scores)
 {
-    __shared__ bmc_contract s_c[64];
+    __shared__ ContractDev s_c[64];
     __shared__ uint8_t s_v[64];
     const bool cached = nc <= 64u;
     if (cached)
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(256) score_kernel(const bmc_contract *__restri
         int *o = &out.x;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const bmc_contract ct = cached ? s_c[c] : contracts[c];
+            const ContractDev ct = cached ? s_c[c] : contracts[c];
             const int v = cached ? s_v[c] : (vul ? vul[c] : 0);
             o[k] = base_score_dev(ct, (int)((t4 >> (8 * k)) & 0xFFu), v);
             c = c + 1u == nc ? 0u : c + 1u;
@@ -289,58 +292,30 @@ __global__ void __launch_bounds__(256) imps_kernel(const int32_t *__restrict__ a
     }
 }
 
-// tricks for deal `idx`, contract c: 16-bit lane c of Philox(stream 1), mapped to
-// 0..13 by multiply-shift; lanes whose low product part is < 65536 mod 14 (=2)
-// are biased and take the next lane (8..15) instead.
+// Index-keyed drill tally: tricks of deal `idx` = tricks_of(Philox(seed; idx_lo, idx_hi, block, stream 1)) (score.cuh):
+// eight exactly uniform values 0..13.  hist = tricks[8][14] | imps[8][49] | dropped[8] (u64 words).
 __global__ void __launch_bounds__(256) score_tally_kernel(const __grid_constant__ ContractTable t, const __grid_constant__ PhiloxKey key,
                                                           unsigned long long first, unsigned long long n,
-                                                          unsigned long long *__restrict__ tricks_hist,
-                                                          unsigned long long *__restrict__ imp_hist)
+                                                          unsigned long long *__restrict__ hist)
 {
-    __shared__ uint32_t s_tr[8 * 14];
-    __shared__ uint32_t s_imp[8 * 49];
-    __shared__ int s_score[8 * 14];
-    for (int i = threadIdx.x; i < 8 * 14; i += blockDim.x) {
-        s_tr[i] = 0;
+    __shared__ uint32_t s_h[SCORE_WORDS];
+    __shared__ int s_score[SCORE_TR_WORDS];
+    for (int i = threadIdx.x; i < SCORE_TR_WORDS; i += blockDim.x) {
         const int c = i / 14;
         s_score[i] = c < (int)t.n ? base_score_dev(t.c[c], i % 14, t.vul[c]) : 0;
     }
-    for (int i = threadIdx.x; i < 8 * 49; i += blockDim.x) s_imp[i] = 0;
+    for (int i = threadIdx.x; i < SCORE_WORDS; i += blockDim.x) s_h[i] = 0;
     __syncthreads();
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const unsigned long long idx = first + i;
-        uint32_t w[4];
-        philox4x32_10(key, (uint32_t)idx, (uint32_t)(idx >> 32), 0u, 1u, w);
-        int tr[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t lane16 = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-            uint32_t prod = lane16 * 14u;
-            if ((prod & 0xFFFFu) < 2u) {       // biased lane: deterministic redraw from a second block
-                uint32_t w2[4];
-                philox4x32_10(key, (uint32_t)idx, (uint32_t)(idx >> 32), 1u + c, 1u, w2);
-                prod = (w2[0] >> 16) * 14u;    // residual bias 2^-16 * 2/65536 -- below any observable level
-            }
-            tr[c] = (int)(prod >> 16);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (c < (int)t.n) atomicAdd(&s_tr[c * 14 + tr[c]], 1u);
-#pragma unroll
-        for (int p = 0; p < 8; ++p)
-            if (p < (int)t.n_pairs) {
-                const int ca = t.pairs[2 * p], cb = t.pairs[2 * p + 1];
-                bool bad;
-                const int v = imps_dev(s_score[ca * 14 + tr[ca]] - s_score[cb * 14 + tr[cb]], bad);
-                if (!bad) atomicAdd(&s_imp[p * 49 + 24 + v], 1u);
-            }
+        uint32_t tr[8];
+        tricks_of(key, (uint32_t)idx, (uint32_t)(idx >> 32), 0u, 1u, tr);
+        score_tally_update(t, s_score, tr, s_h);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 8 * 14; i += blockDim.x)
-        if (s_tr[i]) atomicAdd(&tricks_hist[i], (unsigned long long)s_tr[i]);
-    for (int i = threadIdx.x; i < 8 * 49; i += blockDim.x)
-        if (s_imp[i]) atomicAdd(&imp_hist[i], (unsigned long long)s_imp[i]);
+    for (int i = threadIdx.x; i < SCORE_WORDS; i += blockDim.x)
+        if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
 }
 
 // ---------------------------------------------------------------------------
@@ -365,12 +340,30 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t seed, uint32_t *
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
 }
 
-// Publishes the four leading counters into host-mapped pinned memory, so the per-wave
-// read-back does not occupy the device->host copy engine (which streams the records).
-__global__ void publish_counters_kernel(const unsigned long long *__restrict__ tallies, volatile unsigned long long *mapped)
+// Runs after every wave.  Publishes the four leading counters and a wave sequence number into host-mapped
+// pinned memory -- so the host follows the job without a device->host copy (the copy engine streams the
+// records) and without synchronising the stream -- and snapshots the accepted counter for the next wave's
+// cancellation test (wave_cancelled, kernels.cuh).
+__global__ void publish_counters_kernel(const unsigned long long *__restrict__ tallies, volatile unsigned long long *mapped,
+                                        unsigned long long *snap, unsigned long long seq)
 {
     if (threadIdx.x < 4) mapped[threadIdx.x] = tallies[threadIdx.x];
+    if (threadIdx.x == 0) *snap = tallies[2];
     __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) mapped[4] = seq;
+    __threadfence_system();
+}
+
+// Sums the tally buffers of peer devices into this device's buffer over NVLink (bmc_sample_multi): P2P loads.
+struct PeerTallies { const unsigned long long *p[16]; int n; };
+__global__ void reduce_peer_tallies_kernel(unsigned long long *dst, const __grid_constant__ PeerTallies peers, int words)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) {
+        unsigned long long v = dst[i];
+        for (int g = 0; g < peers.n; ++g) v += peers.p[g][i];
+        dst[i] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -380,22 +373,26 @@ struct bmc_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    unsigned long long *h_head = nullptr;        // pinned + mapped: per-wave read-back of the four counters
+    unsigned long long *h_head = nullptr;        // pinned + mapped: {raw, voided, accepted, stored, wave sequence number}
     unsigned long long *h_head_dev = nullptr;    // its device alias
-    bmc_record *d_rec = nullptr;                 // grow-only record scratch of the host-buffer API
-    uint64_t rec_cap = 0;
+    unsigned long long *d_snap = nullptr;        // accepted counter at the end of the previous wave
+    void *d_rec = nullptr;                       // grow-only record scratch of the host-buffer API
+    uint64_t rec_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long *d_tallies = nullptr;     // scratch tallies for the host-buffer API
     uint64_t launches = 0;
-    int blocks_cons = 0, blocks_free = 0, blocks_sf = 0;
     std::mutex mu;
 };
 
-struct bmc_constraints {
-    ConsDev dev{};               // dev.code filled lazily per device
-    std::vector<uint32_t> code;
+struct ConsTables {              // per-device copies of a constraint's tables
     uint32_t *d_code = nullptr;
-    int d_device = -1;
+    JitKernel jit[2];            // [0] full-deal kernel, [1] seat-first kernel
+};
+
+struct bmc_constraints {
+    ConsDev dev{};               // dev.code filled per device
+    std::vector<uint32_t> code;
+    std::map<int, ConsTables> tabs;      // device -> tables (guarded by mu)
     uint32_t tab_off = 0;        // seat-first class table: word offset in `code`
     int sf_hcp[2] = {0, 37};     // the HCP window the table was built for (primary seat)
     bool has_cons = false;
@@ -406,62 +403,75 @@ struct bmc_constraints {
     int ref_defs = -1;           // reference-order mode: number of ranged seats after the fixed ones
     SeqDev seq{};
     std::string rule_text[4];    // the rule forms as given (the NVRTC path re-reads them)
-    int jit = 0;                 // 0: interpret the rule bytecode; 1: compile the rule forms into the kernel (NVRTC)
-    JitKernel jit_kernel[2];     // [0] full-deal kernel, [1] seat-first kernel
+    int jit = 0;                 // 0: interpret the rule bytecode; 1: compile the rule forms into the kernel (NVRTC); 2: auto
+    float jit_ms = 0.f;
+    double interp_ms = 0.0;      // kernel time spent so far with interpreted rules (auto-JIT trigger)
     std::string jit_log;
     int mode = 0;                // requested: 0 auto, 1 full deal (deal52), 2 seat-first, 3 reference order
     int resolved = 0;            // 0 = not calibrated yet
     double stage_a_pass = -1.0;  // measured pass rate of the primary seat's ranges
+    ContractTable score{};       // bmc_constraints_set_scoring
     std::mutex mu, cal_mu;
 };
 
+struct SchemeTables { uint32_t *d_code = nullptr, *d_off = nullptr; };
 struct bmc_scheme {
     std::vector<uint32_t> code, row_off;
     std::vector<std::string> bids;
-    uint32_t *d_code = nullptr, *d_off = nullptr;
-    int d_device = -1;
+    std::map<int, SchemeTables> tabs;
     std::mutex mu;
 };
 
-static std::once_flag g_lut_once[16];
-static uint8_t g_shapes[39][4];
-static uint8_t g_shape_lut[14 * 14 * 14];
-static std::once_flag g_shape_once;
-
-static void init_shapes()
+static int check_contracts(const bmc_contract *c, uint32_t n)
 {
-    int n = 0;
-    for (int a = 4; a <= 13; ++a)
-        for (int b = 0; b <= a; ++b)
-            for (int c = 0; c <= b; ++c) {
-                const int d = 13 - a - b - c;
-                if (d < 0 || d > c) continue;
-                g_shapes[n][0] = (uint8_t)a; g_shapes[n][1] = (uint8_t)b; g_shapes[n][2] = (uint8_t)c; g_shapes[n][3] = (uint8_t)d;
-                ++n;
-            }
-    memset(g_shape_lut, 0xFF, sizeof g_shape_lut);
-    for (int x = 0; x <= 13; ++x)
-        for (int y = 0; x + y <= 13; ++y)
-            for (int z = 0; x + y + z <= 13; ++z) {
-                int v[4] = {x, y, z, 13 - x - y - z};
-                for (int i = 0; i < 4; ++i)
-                    for (int j = i + 1; j < 4; ++j)
-                        if (v[j] > v[i]) { int t = v[i]; v[i] = v[j]; v[j] = t; }
-                for (int k = 0; k < 39; ++k)
-                    if (g_shapes[k][0] == v[0] && g_shapes[k][1] == v[1] && g_shapes[k][2] == v[2] && g_shapes[k][3] == v[3])
-                        g_shape_lut[x * 196 + y * 14 + z] = (uint8_t)k;
-            }
+    for (uint32_t i = 0; i < n; ++i)
+        if (c[i].level < 0 || c[i].level > 7 || c[i].suit < 0 || c[i].suit > 4 || c[i].dbl < 0 || c[i].dbl > 2 || c[i].declarer < -1 || c[i].declarer > 3)
+            return fail(BMC_E_INVALID, "contract " + std::to_string(i) + " out of range");
+    return BMC_OK;
 }
+
+static int fill_contract_table(ContractTable &t, const bmc_contract *contracts, const uint8_t *vulnerable, uint32_t nc,
+                               const uint8_t *pairs, uint32_t n_pairs)
+{
+    { int rc = check_contracts(contracts, nc); if (rc) return rc; }
+    t.n = nc; t.n_pairs = n_pairs;
+    for (uint32_t i = 0; i < nc; ++i) {
+        t.c[i].level = contracts[i].level; t.c[i].suit = contracts[i].suit;
+        t.c[i].declarer = contracts[i].declarer; t.c[i].dbl = contracts[i].dbl;
+        t.vul[i] = vulnerable ? (vulnerable[i] ? 1 : 0) : 0;
+    }
+    for (uint32_t i = 0; i < 2 * n_pairs; ++i) {
+        if (pairs[i] >= nc) return fail(BMC_E_INVALID, "pair index out of range");
+        t.pairs[i] = pairs[i];
+    }
+    return BMC_OK;
+}
+
+static const ShapeList g_shapes = make_shape_list();
 
 extern "C" {
 
 const char *bmc_last_error(void) { return g_err.c_str(); }
-const char *bmc_version(void) { return "bridgemc 0.1 (sm_100a)"; }
+const char *bmc_version(void) { return "bridgemc 0.2 (sm_100a)"; }
 
-void bmc_shape_table(uint8_t out[39][4])
+void bmc_shape_table(uint8_t out[39][4]) { memcpy(out, g_shapes.s, sizeof g_shapes.s); }
+
+static int ctx_setup(bmc_ctx *c)
 {
-    std::call_once(g_shape_once, init_shapes);
-    memcpy(out, g_shapes, sizeof g_shapes);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    c->sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaMalloc(&c->d_tallies, sizeof(bmc_tallies)));
+    CUDA_TRY(cudaMalloc(&c->d_snap, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_snap, 0, sizeof(unsigned long long)));
+    CUDA_TRY(cudaHostAlloc(&c->h_head, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void **)&c->h_head_dev, c->h_head, 0));
+    return BMC_OK;
 }
 
 int bmc_init(int device, bmc_ctx **out)
@@ -474,41 +484,13 @@ int bmc_init(int device, bmc_ctx **out)
         return fail(BMC_E_CUDA, std::string("no CUDA device (") + cudaGetErrorString(e) + "); libbridgemc has no CPU fallback");
     if (device < 0 || device >= count) return fail(BMC_E_INVALID, "bmc_init: device index out of range");
     CUDA_TRY(cudaSetDevice(device));
-    std::call_once(g_shape_once, init_shapes);
     bmc_ctx *c = new bmc_ctx();
     c->device = device;
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    c->sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->stream = c->own_stream;
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&c->ev0));
-    CUDA_TRY(cudaEventCreate(&c->ev1));
-    CUDA_TRY(cudaMalloc(&c->d_tallies, sizeof(bmc_tallies)));
-    CUDA_TRY(cudaHostAlloc(&c->h_head, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
-    CUDA_TRY(cudaHostGetDevicePointer((void **)&c->h_head_dev, c->h_head, 0));
-    if (device < 16) {
-        cudaError_t le = cudaSuccess;
-        std::call_once(g_lut_once[device], [&] { le = cudaMemcpyToSymbol(c_shape_lut, g_shape_lut, sizeof g_shape_lut); });
-        if (le != cudaSuccess) return fail(BMC_E_CUDA, std::string("shape LUT upload: ") + cudaGetErrorString(le));
-    } else {
-        CUDA_TRY(cudaMemcpyToSymbol(c_shape_lut, g_shape_lut, sizeof g_shape_lut));
-    }
-    int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<true, false>, THREADS, 0));
-    c->blocks_cons = c->sms * (occ > 0 ? occ : 1);
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_kernel<false, false>, THREADS, 0));
-    c->blocks_free = c->sms * (occ > 0 ? occ : 1);
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_seatfirst_kernel, THREADS, 0));
-    c->blocks_sf = c->sms * (occ > 0 ? occ : 1);
-    if (const char *e = getenv("BMC_BLOCKS_PER_SM")) {        // tuning knob: cap the resident blocks per SM
-        const int cap = atoi(e);
-        if (cap > 0) {
-            if (c->blocks_sf > c->sms * cap) c->blocks_sf = c->sms * cap;
-            if (c->blocks_cons > c->sms * cap) c->blocks_cons = c->sms * cap;
-            if (c->blocks_free > c->sms * cap) c->blocks_free = c->sms * cap;
-        }
+    const int rc = ctx_setup(c);
+    if (rc != BMC_OK) {                     // a failed init releases whatever it had created (g_err keeps the cause)
+        const std::string why = g_err;
+        bmc_shutdown(c);
+        return fail(rc, why);
     }
     *out = c;
     return BMC_OK;
@@ -518,14 +500,15 @@ void bmc_shutdown(bmc_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_tallies);
-    cudaFreeHost(c->h_head);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->d_tallies) cudaFree(c->d_tallies);
+    if (c->d_snap) cudaFree(c->d_snap);
+    if (c->h_head) cudaFreeHost(c->h_head);
     if (c->d_rec) cudaFree(c->d_rec);
-    cudaStreamDestroy(c->copy_stream);
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -874,17 +857,33 @@ int bmc_constraints_primary_hcp(const bmc_constraints *c, int32_t *lo, int32_t *
 void bmc_constraints_destroy(bmc_constraints *c)
 {
     if (!c) return;
-    if (c->d_code) { cudaSetDevice(c->d_device); cudaFree(c->d_code); }
-    for (JitKernel &jk : c->jit_kernel)
-        if (jk.module) { cudaSetDevice(jk.device); JitApi::get().ModuleUnload(jk.module); }
+    for (auto &kv : c->tabs) {
+        cudaSetDevice(kv.first);
+        if (kv.second.d_code) cudaFree(kv.second.d_code);
+        for (JitKernel &jk : kv.second.jit)
+            if (jk.module) JitApi::get().ModuleUnload(jk.module);
+    }
     delete c;
 }
 
-// ---- NVRTC specialisation of a constraint (jit.hpp) ------------------------------------------------
-static int jit_build(bmc_ctx *ctx, bmc_constraints *c, bool seatfirst)
+// The contracts / IMP pairs tallied over the accepted deals when tally_mask has BMC_TALLY_SCORE.
+int bmc_constraints_set_scoring(bmc_constraints *c, const bmc_contract *contracts, const uint8_t *vulnerable, uint32_t nc,
+                                const uint8_t *pairs, uint32_t n_pairs)
 {
-    JitKernel &jk = c->jit_kernel[seatfirst ? 1 : 0];
-    if (jk.func && jk.device == ctx->device) return BMC_OK;
+    if (!c || (nc && !contracts) || nc > (uint32_t)SCORE_MAX_CONTRACTS || n_pairs > (uint32_t)SCORE_MAX_PAIRS || (n_pairs && !pairs))
+        return fail(BMC_E_INVALID, "bmc_constraints_set_scoring: bad argument");
+    ContractTable t{};
+    int rc = fill_contract_table(t, contracts, vulnerable, nc, pairs, n_pairs);
+    if (rc) return rc;
+    c->score = t;
+    return BMC_OK;
+}
+
+// ---- NVRTC specialisation of a constraint (jit.hpp) ------------------------------------------------
+static int jit_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *tabs, bool seatfirst)
+{
+    JitKernel &jk = tabs->jit[seatfirst ? 1 : 0];      // caller holds c->cal_mu; the ctx's device is current
+    if (jk.func) return BMC_OK;
     JitApi &api = JitApi::get();
     if (!api.ok) return fail(BMC_E_CUDA, "NVRTC specialisation unavailable: " + api.why);
     // 1. the rule forms as one C++ function
@@ -934,55 +933,42 @@ static int jit_build(bmc_ctx *ctx, bmc_constraints *c, bool seatfirst)
     api.GetCUBIN(p, cubin.data());
     api.DestroyProgram(&p);
     // 3. load, bind, initialise the module's constant tables
-    if (jk.module) { api.ModuleUnload(jk.module); jk = JitKernel(); }
     CUresult cr = api.ModuleLoadData(&jk.module, cubin.data());
     if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleLoadData failed: " + std::to_string((int)cr));
     cr = api.ModuleGetFunction(&jk.func, jk.module, seatfirst ? "bmc_jit_sample_seatfirst" : "bmc_jit_sample_full");
     if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleGetFunction failed: " + std::to_string((int)cr));
-    CUdeviceptr lut = 0;
-    size_t lut_bytes = 0;
-    cr = api.ModuleGetGlobal(&lut, &lut_bytes, jk.module, "c_shape_lut");
-    if (cr != CUDA_SUCCESS || lut_bytes != sizeof g_shape_lut) return fail(BMC_E_CUDA, "jit: c_shape_lut not found");
-    cr = api.MemcpyHtoD(lut, g_shape_lut, sizeof g_shape_lut);
-    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "jit: shape LUT upload failed");
-    int occ = 0;
-    api.Occupancy(&occ, jk.func, THREADS, 0);
-    jk.blocks_per_sm = occ > 0 ? occ : 1;
     jk.device = ctx->device;
     jk.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->jit_ms += jk.compile_ms;
     return BMC_OK;
 }
 
 int bmc_constraints_set_jit(bmc_constraints *c, int on)
 {
-    if (!c || on < 0 || on > 1) return fail(BMC_E_INVALID, "bmc_constraints_set_jit: bad argument");
+    if (!c || on < 0 || on > 2) return fail(BMC_E_INVALID, "bmc_constraints_set_jit: bad argument");
     c->jit = on;
     return BMC_OK;
 }
 float bmc_constraints_jit_ms(const bmc_constraints *c)
 {
-    if (!c) return 0.f;
-    return c->jit_kernel[0].compile_ms + c->jit_kernel[1].compile_ms;
+    return c ? c->jit_ms : 0.f;
 }
 
-static int cons_upload(bmc_ctx *ctx, const bmc_constraints *cc, ConsDev &dev)
+// Device-side tables of a constraint, one copy per device (a handle may be shared by contexts of several devices).
+static int cons_upload(bmc_ctx *ctx, const bmc_constraints *cc, ConsDev &dev, ConsTables **tabs = nullptr)
 {
     bmc_constraints *c = const_cast<bmc_constraints *>(cc);
     std::lock_guard<std::mutex> lk(c->mu);
-    if (c->d_code && c->d_device != ctx->device) {
-        cudaSetDevice(c->d_device);
-        cudaFree(c->d_code);
-        c->d_code = nullptr;
-        cudaSetDevice(ctx->device);
-    }
-    if (!c->d_code) {
-        CUDA_TRY(cudaMalloc(&c->d_code, c->code.size() * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemcpy(c->d_code, c->code.data(), c->code.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        c->d_device = ctx->device;
+    ConsTables &t = c->tabs[ctx->device];               // std::map: the element's address is stable
+    if (tabs) *tabs = &t;
+    if (!t.d_code) {
+        CUDA_TRY(cudaMalloc(&t.d_code, c->code.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpyAsync(t.d_code, c->code.data(), c->code.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     dev = c->dev;
-    dev.code = c->d_code;
-    dev.sf_tab = reinterpret_cast<const uint4 *>(c->d_code + c->tab_off);
+    dev.code = t.d_code;
+    dev.sf_tab = reinterpret_cast<const uint4 *>(t.d_code + c->tab_off);
     return BMC_OK;
 }
 
@@ -1011,7 +997,11 @@ int bmc_scheme_size(const bmc_scheme *s) { return s ? (int)s->row_off.size() : 0
 void bmc_scheme_destroy(bmc_scheme *s)
 {
     if (!s) return;
-    if (s->d_code) { cudaSetDevice(s->d_device); cudaFree(s->d_code); cudaFree(s->d_off); }
+    for (auto &kv : s->tabs) {
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second.d_code);
+        cudaFree(kv.second.d_off);
+    }
     delete s;
 }
 static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
@@ -1020,56 +1010,92 @@ static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
     if (!ss || ss->row_off.empty()) return BMC_OK;
     bmc_scheme *s = const_cast<bmc_scheme *>(ss);
     std::lock_guard<std::mutex> lk(s->mu);
-    if (s->d_code && s->d_device != ctx->device) {
-        cudaSetDevice(s->d_device);
-        cudaFree(s->d_code); cudaFree(s->d_off);
-        s->d_code = s->d_off = nullptr;
-        cudaSetDevice(ctx->device);
+    SchemeTables &t = s->tabs[ctx->device];
+    if (!t.d_code) {
+        CUDA_TRY(cudaMalloc(&t.d_code, s->code.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&t.d_off, s->row_off.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpyAsync(t.d_code, s->code.data(), s->code.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(t.d_off, s->row_off.data(), s->row_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
-    if (!s->d_code) {
-        CUDA_TRY(cudaMalloc(&s->d_code, s->code.size() * sizeof(uint32_t)));
-        CUDA_TRY(cudaMalloc(&s->d_off, s->row_off.size() * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemcpy(s->d_code, s->code.data(), s->code.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(s->d_off, s->row_off.data(), s->row_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        s->d_device = ctx->device;
-    }
-    dev.code = s->d_code; dev.row_off = s->d_off; dev.n_rows = (uint32_t)s->row_off.size();
+    dev.code = t.d_code; dev.row_off = t.d_off; dev.n_rows = (uint32_t)s->row_off.size();
     return BMC_OK;
 }
 
 // ---- sampling -------------------------------------------------------------------
-static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const FixDev *fix, bool seatfirst, uint64_t seed,
-                       uint64_t first, uint64_t n, uint32_t tally_mask, void *records_dev, uint64_t cap, void *tallies_dev,
-                       const SeqDev *seq = nullptr, const JitKernel *jit = nullptr)
+struct WaveCfg {                 // what is constant over the waves of one call
+    ConsDev cons{};
+    bool has_cons = false, seatfirst = false, interp = false;
+    const FixDev *fix = nullptr;
+    const SeqDev *seq = nullptr;
+    const JitKernel *jit = nullptr;
+    ConsTables *tabs = nullptr;
+    uint64_t seed = 0, call_first = 0, target = 0, start_acc = 0;
+    uint32_t tally_mask = 0, rec_mode = 0;
+    void *records = nullptr;
+    uint64_t cap = 0;
+    void *tallies = nullptr;
+    ContractTable score{};
+};
+
+static int blocks_per_sm(const void *kernel, size_t smem)
+{
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    static const int cap = [] { const char *e = getenv("BMC_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();      // tuning knob
+    return cap > 0 && occ > cap ? cap : occ;
+}
+
+static int launch_wave(bmc_ctx *ctx, const WaveCfg &w, uint64_t first, uint64_t n)
 {
     SampleArgs a;
-    a.cons = cons;
-    if (fix) a.fix = *fix;
-    else { memset(&a.fix, 0, sizeof a.fix); a.fix.n_free = 52; }
-    a.key = philox_key(seed);
+    memset(&a, 0, sizeof a);
+    a.cons = w.cons;
+    if (w.fix) a.fix = *w.fix;
+    else a.fix.n_free = 52;
+    a.key = philox_key(w.seed);
+    a.tkey = philox_key(w.seed ^ SCORE_KEY_XOR);
     a.first = first;
     a.n = n;
-    a.records = (uint4 *)records_dev;
-    a.cap = records_dev ? cap : 0;
-    a.tallies = (unsigned long long *)tallies_dev;
-    a.tally_mask = tally_mask;
+    a.records = w.records;
+    a.cap = w.records ? w.cap : 0;
+    a.tallies = (unsigned long long *)w.tallies;
+    a.tally_mask = w.tally_mask;
+    a.rec_mode = w.rec_mode;
+    a.idx_base = (uint32_t)(first - w.call_first);
+    a.flags = w.interp ? ARGS_INTERP : 0u;
+    a.target = w.target;
+    a.start_acc = w.start_acc;
+    a.snap = ctx->d_snap;
+    a.score = w.score;
     {   // stage B of the seat-first sampler: the primary seat has no capacity left
         uint32_t cap4[4] = {13, 13, 13, 13};
-        cap4[cons.primary & 3u] = 0;
+        cap4[w.cons.primary & 3u] = 0;
         const uint32_t p0 = cap4[0], p1 = p0 + cap4[1], p2 = p1 + cap4[2];
         a.sf_q0 = (128u - p0) | ((128u - p1) << 8) | ((128u - p2) << 16);
-        a.pad = 0;
     }
-    int blocks = seatfirst ? ctx->blocks_sf : has_cons ? ctx->blocks_cons : ctx->blocks_free;
-    if (seq) blocks = ctx->sms * 4;
-    if (jit) blocks = ctx->sms * jit->blocks_per_sm;
-    const uint64_t per_thread = seatfirst ? 4 * SF_CALLS : 1;     // raw deals per thread per iteration
+    const bool jit = w.jit != nullptr;
+    const SmemPlan plan = w.seq ? smem_plan(false, false, false, false, w.tally_mask)
+                                : smem_plan(w.seatfirst, w.seatfirst || w.has_cons, w.seatfirst && sf_two_stage(w.cons, jit), w.interp, w.tally_mask);
+    const size_t smem = (size_t)plan.words * 4u;
+    const void *kernel = w.seq ? (const void *)sample_reforder_kernel
+                       : w.seatfirst ? (const void *)sample_seatfirst_kernel
+                       : w.fix ? (w.has_cons ? (const void *)sample_kernel<true, true> : (const void *)sample_kernel<false, true>)
+                               : (w.has_cons ? (const void *)sample_kernel<true, false> : (const void *)sample_kernel<false, false>);
+    int per_sm;
+    if (jit) {
+        int occ = 0;
+        JitApi::get().Occupancy(&occ, w.jit->func, THREADS, smem);
+        per_sm = occ > 0 ? occ : 1;
+    } else per_sm = blocks_per_sm(kernel, smem);
+    int blocks = ctx->sms * per_sm;
+    const uint64_t per_thread = w.seatfirst ? 4 * SF_CALLS : 1;     // raw deals per thread per iteration
     const uint64_t per_iter = (uint64_t)blocks * THREADS * per_thread;
     if (n < per_iter) blocks = (int)((n + THREADS * per_thread - 1) / (THREADS * per_thread));
     if (blocks < 1) blocks = 1;
     const uint64_t chunk = (uint64_t)blocks * THREADS * per_thread;
     a.iters = (uint32_t)((n + chunk - 1) / chunk);
-    if (seatfirst) {
+    if (w.seatfirst) {
         // a lane owns index QUADS (4c .. 4c + 3, one Philox call): a misaligned first index or end adds one
         const uint64_t calls = ((first + n + 3) >> 2) - (first >> 2);
         const uint64_t per = (uint64_t)blocks * THREADS * SF_CALLS;
@@ -1077,49 +1103,44 @@ static int launch_wave(bmc_ctx *ctx, const ConsDev &cons, bool has_cons, const F
     }
     if (jit) {
         void *params[] = {&a};
-        const CUresult cr = JitApi::get().LaunchKernel(jit->func, (unsigned)blocks, 1, 1, THREADS, 1, 1, 0, (CUstream)ctx->stream, params, nullptr);
+        const CUresult cr = JitApi::get().LaunchKernel(w.jit->func, (unsigned)blocks, 1, 1, THREADS, 1, 1, (unsigned)smem, (CUstream)ctx->stream, params, nullptr);
         if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuLaunchKernel (jit) failed: " + std::to_string((int)cr));
-    } else if (seq) sample_reforder_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a, *seq);
-    else if (seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a);
-    else if (fix) {
-        if (has_cons) sample_kernel<true, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
-        else sample_kernel<false, true><<<blocks, THREADS, 0, ctx->stream>>>(a);
+    } else if (w.seq) sample_reforder_kernel<<<blocks, THREADS, smem, ctx->stream>>>(a, *w.seq);
+    else if (w.seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, smem, ctx->stream>>>(a);
+    else if (w.fix) {
+        if (w.has_cons) sample_kernel<true, true><<<blocks, THREADS, smem, ctx->stream>>>(a);
+        else sample_kernel<false, true><<<blocks, THREADS, smem, ctx->stream>>>(a);
     } else {
-        if (has_cons) sample_kernel<true, false><<<blocks, THREADS, 0, ctx->stream>>>(a);
-        else sample_kernel<false, false><<<blocks, THREADS, 0, ctx->stream>>>(a);
+        if (w.has_cons) sample_kernel<true, false><<<blocks, THREADS, smem, ctx->stream>>>(a);
+        else sample_kernel<false, false><<<blocks, THREADS, smem, ctx->stream>>>(a);
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return BMC_OK;
 }
 
-// Common driver.  host_out != NULL: records are streamed to the caller's buffer on a
-// second stream while the next wave computes (the copy of wave k overlaps wave k+1).
-static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
-                       uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records_dev, uint64_t cap,
-                       void *tallies_dev, bmc_stats *stats, bmc_record *host_out)
+// Resolves how `cons` is sampled on this context's device: uploads its tables, calibrates the dealing mode once per
+// constraint (reproducibly: fixed calibration seed), builds the NVRTC kernel when asked.  Fills the constant part of `w`.
+static int resolve_cfg(bmc_ctx *ctx, const bmc_constraints *cons, WaveCfg &w)
 {
-    if (n_accept_target == 0 && n_raw == 0) return fail(BMC_E_INVALID, "nothing to do: n_raw == 0 and no accept target");
-    auto t0 = std::chrono::steady_clock::now();
-    ConsDev dev{};
-    const bool has_cons = cons && cons->has_cons;
-    if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
-    const FixDev *fix = (cons && cons->has_fixed) ? &cons->fix : nullptr;
-    bool seatfirst = false;
-    const SeqDev *seq = nullptr;
+    w.has_cons = cons && cons->has_cons;
+    if (w.has_cons) { int rc = cons_upload(ctx, cons, w.cons, &w.tabs); if (rc) return rc; }
+    w.fix = (cons && cons->has_fixed) ? &cons->fix : nullptr;
+    if (cons) w.score = cons->score;
     if (cons && cons->resolved == 3) {                 // reference order: `build`'s own sequential semantics
-        seq = &cons->seq;
-        fix = &cons->fix;
-    } else if (has_cons && !fix) {
+        w.seq = &cons->seq;
+        w.fix = &cons->fix;
+    } else if (w.has_cons && !w.fix) {
         bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
         std::lock_guard<std::mutex> cal_lock(cc->cal_mu);      // one calibration per constraint, even across contexts
-        // pass rate of `cal` over 2^16 raw deals of the full-deal kernel (a fixed calibration seed:
-        // the outcome, hence the mode and the stream behind each index, is reproducible)
+        // pass rate of `cal` over 2^16 raw deals of the full-deal kernel
         auto pass_rate = [&](const ConsDev &cal, double &rate) -> int {
             unsigned long long *d_cal = nullptr, h4[4] = {0, 0, 0, 0};
             CUDA_TRY(cudaMalloc(&d_cal, sizeof(bmc_tallies)));
             cudaMemsetAsync(d_cal, 0, sizeof(bmc_tallies), ctx->stream);
-            int rc = launch_wave(ctx, cal, true, nullptr, false, 0x63616C6962726174ull, 0, 1u << 16, 0, nullptr, 0, d_cal);
+            WaveCfg wc;
+            wc.cons = cal; wc.has_cons = true; wc.seed = 0x63616C6962726174ull; wc.tallies = d_cal;
+            int rc = launch_wave(ctx, wc, 0, 1u << 16);
             cudaError_t e = cudaMemcpyAsync(h4, d_cal, sizeof h4, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             cudaFree(d_cal);
@@ -1132,125 +1153,243 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
             if (cc->mode != 0) cc->resolved = cc->mode;
             else {
                 // the primary seat's RANGES alone: seat-first pays off when most deals die on them
-                ConsDev cal = dev;
+                ConsDev cal = w.cons;
                 for (int k = 0; k < 4; ++k) {
                     cal.seat[k].prog = 0xFFFFFFFFu;
-                    if ((uint32_t)k != dev.primary) cal.seat[k].active = 0;
+                    if ((uint32_t)k != w.cons.primary) cal.seat[k].active = 0;
                 }
                 int rc = pass_rate(cal, cc->stage_a_pass);
                 if (rc) return rc;
                 cc->resolved = cc->stage_a_pass < 0.30 ? 2 : 1;
             }
             cc->dev.b1_mask = 0xFu;
-            if (cc->resolved == 2 && dev.n_active >= 3) {
+            if (cc->resolved == 2 && w.cons.n_active >= 3) {
                 // the most selective other seat: tested together with the primary seat by the compiled-rule kernel
                 double best = 2.0;
                 int second = -1;
                 for (int k = 0; k < 4; ++k) {
-                    if ((uint32_t)k == dev.primary || !dev.seat[k].active) continue;
-                    ConsDev cal = dev;
+                    if ((uint32_t)k == w.cons.primary || !w.cons.seat[k].active) continue;
+                    ConsDev cal = w.cons;
                     for (int j = 0; j < 4; ++j) if (j != k) cal.seat[j].active = 0;
                     cal.primary = (uint32_t)k;
+                    cal.n_prog = cal.seat[k].prog != 0xFFFFFFFFu ? 1u : 0u;
                     double r = 1.0;
                     int rc = pass_rate(cal, r);
                     if (rc) return rc;
                     if (r < best) { best = r; second = k; }
                 }
-                if (second >= 0) cc->dev.b1_mask = (1u << dev.primary) | (1u << second);
+                if (second >= 0) cc->dev.b1_mask = (1u << w.cons.primary) | (1u << second);
             }
         }
-        dev.b1_mask = cc->dev.b1_mask;
-        seatfirst = cc->resolved == 2;
+        w.cons.b1_mask = cc->dev.b1_mask;
+        w.seatfirst = cc->resolved == 2;
     }
-    const JitKernel *jit = nullptr;
-    if (cons && cons->jit && has_cons && !fix && !seq && cons->has_rules) {
+    w.interp = w.has_cons && w.cons.n_prog != 0u;
+    if (cons && cons->has_rules && w.has_cons && !w.fix && !w.seq) {
         bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
         std::lock_guard<std::mutex> jl(cc->cal_mu);
-        int rc = jit_build(ctx, cc, seatfirst);
-        if (rc) return rc;
-        jit = &cc->jit_kernel[seatfirst ? 1 : 0];
+        // jit 1: always; jit 2 (default): once the constraint has spent more than a second of kernel time interpreting
+        // its rule programs -- about what the NVRTC build costs.  Results are bit-identical either way.
+        const bool want = cc->jit == 1 || (cc->jit == 2 && cc->interp_ms > 1000.0 && w.cons.n_prog != 0u && JitApi::get().ok);
+        if (want) {
+            int rc = jit_build(ctx, cc, w.tabs, w.seatfirst);
+            if (rc) {
+                if (cc->jit == 1) return rc;
+                cc->jit = 0;                           // auto: the build failed once -- keep interpreting
+            } else {
+                w.jit = &w.tabs->jit[w.seatfirst ? 1 : 0];
+                w.interp = false;
+            }
+        }
+    }
+    return BMC_OK;
+}
+
+static int publish(bmc_ctx *ctx, const void *tallies_dev, unsigned long long seq)
+{
+    publish_counters_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)tallies_dev, ctx->h_head_dev, ctx->d_snap, seq);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BMC_OK;
+}
+
+// Common driver.  An accept-target job enqueues its waves back to back in batches sized from the acceptance seen so
+// far: a wave that starts after the target was met cancels itself on the device (wave_cancelled), so the accepted
+// set is still "whole waves from first_index until the target is met" while the host synchronises once per batch
+// instead of once per wave.  host_out != NULL: records are streamed to the caller's buffer on a second stream while
+// later waves compute; the host follows the waves through the counters each one publishes in mapped memory.
+static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                       uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records_dev, uint64_t cap,
+                       void *tallies_dev, bmc_stats *stats, void *host_out, uint32_t rec_mode)
+{
+    if (n_accept_target == 0 && n_raw == 0) return fail(BMC_E_INVALID, "nothing to do: n_raw == 0 and no accept target");
+    if ((tally_mask & BMC_TALLY_SCORE) && (!cons || cons->score.n == 0))
+        return fail(BMC_E_INVALID, "BMC_TALLY_SCORE needs contracts: bmc_constraints_set_scoring");
+    auto t0 = std::chrono::steady_clock::now();
+    WaveCfg w;
+    { int rc = resolve_cfg(ctx, cons, w); if (rc) return rc; }
+    w.seed = seed; w.call_first = first_index; w.tally_mask = tally_mask; w.rec_mode = rec_mode;
+    w.records = records_dev; w.cap = cap; w.tallies = tallies_dev;
+    const uint64_t elem = rec_mode ? sizeof(uint32_t) : sizeof(bmc_record);
+    if (rec_mode) {
+        // index records are 32-bit offsets from first_index: a call spans at most 2^32 indices
+        if (n_raw > (1ull << 32)) return fail(BMC_E_INVALID, "index records: at most 2^32 indices per call");
+        if (n_raw == 0) n_raw = 1ull << 32;
     }
     const bool stream_copy = host_out && records_dev && cap;
     const bool stepwise = n_accept_target != 0 || stream_copy;
     if (wave == 0) wave = 1ull << 26;
-    // 2^36 keeps a warp's iteration counter in 32 bits; the seat-first kernel carries 32-bit offsets from the
-    // launch's first index in its queues: 2^31 indices per launch
-    uint64_t max_launch = stepwise ? wave : (1ull << 36);
-    if (seatfirst && max_launch > (1ull << 31)) max_launch = 1ull << 31;
-    uint32_t waves = 0;
+    // 32-bit offsets from the launch's first index travel through the kernels' queues: 2^32 indices per launch
+    // (2^31 for the seat-first kernel, whose offsets are computed in quads)
+    uint64_t max_launch = stepwise ? wave : (1ull << 32);
+    if (max_launch > (1ull << 32)) max_launch = 1ull << 32;
+    if (w.seatfirst && max_launch > (1ull << 31)) max_launch = 1ull << 31;
     const uint64_t launches0 = ctx->launches;
-    // The counters are read back through host-mapped memory written by a tiny kernel: a memcpy on
-    // the compute stream would queue on the same device->host copy engine as the record copies of
-    // copy_stream and was measured to serialise the waves behind them.
     volatile unsigned long long *head = ctx->h_head;
-    unsigned long long start_acc = 0;
-    head[0] = head[1] = head[2] = head[3] = 0;
-    auto read_head = [&]() -> cudaError_t {
-        publish_counters_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)tallies_dev, ctx->h_head_dev);
-        ctx->launches++;
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        return cudaStreamSynchronize(ctx->stream);
-    };
-    if (stepwise) {
-        CUDA_TRY(read_head());
-        start_acc = head[2];
-    }
-    uint64_t copied = start_acc < cap ? start_acc : cap;
-    float kernel_ms = 0.f;
-    if (!stepwise) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    uint64_t done = 0;
-    for (;;) {
-        if (n_raw && done >= n_raw) break;
-        uint64_t n = max_launch;
-        if (n_raw && n_raw - done < n) n = n_raw - done;
-        if (stepwise) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-        int rc = launch_wave(ctx, dev, has_cons, fix, seatfirst, seed, first_index + done, n, tally_mask, records_dev, cap, tallies_dev, seq, jit);
+    for (int i = 0; i < 5; ++i) head[i] = 0;
+    unsigned long long seq = 0;
+    auto sync_head = [&]() -> int {                      // publish, wait for the stream, the counters are in `head`
+        int rc = publish(ctx, tallies_dev, ++seq);
         if (rc) return rc;
-        done += n;
-        ++waves;
-        if (!stepwise) continue;
-        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-        CUDA_TRY(read_head());
-        {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);       // device time of this wave's kernel only
-            kernel_ms += ms;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return BMC_OK;
+    };
+    { int rc = sync_head(); if (rc) return rc; }         // counters already in the caller's tally buffer
+    const unsigned long long start_raw = head[0], start_acc = head[2];
+    w.target = n_accept_target;
+    w.start_acc = start_acc;
+    uint64_t copied = start_acc < cap ? start_acc : cap;
+    auto copy_upto = [&](unsigned long long accepted) -> int {
+        const uint64_t upto = accepted < cap ? accepted : cap;
+        if (stream_copy && upto > copied) {
+            CUDA_TRY(cudaMemcpyAsync((char *)host_out + copied * elem, (const char *)records_dev + copied * elem,
+                                     (upto - copied) * elem, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            copied = upto;
         }
-        if (stream_copy) {
-            const uint64_t upto = head[2] < cap ? head[2] : cap;
-            if (upto > copied) {
-                auto tc0 = std::chrono::steady_clock::now();
-                CUDA_TRY(cudaMemcpyAsync(host_out + copied, (const bmc_record *)records_dev + copied,
-                                         (upto - copied) * sizeof(bmc_record), cudaMemcpyDeviceToHost, ctx->copy_stream));
-                if (getenv("BMC_DEBUG"))
-                    fprintf(stderr, "[bmc] wave %u: copy of %.1f MB enqueued in %.3f ms at t=%.2f ms (kernel_ms so far %.2f)\n", waves,
-                            (upto - copied) * 16e-6,
-                            std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - tc0).count(),
-                            std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(), kernel_ms);
-                copied = upto;
+        return BMC_OK;
+    };
+    float kernel_ms = 0.f;
+    uint64_t done = 0;                                    // indices enqueued (cancelled waves included)
+    bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
+    if (!stepwise) {
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        while (done < n_raw) {
+            const uint64_t n = n_raw - done < max_launch ? n_raw - done : max_launch;
+            int rc = launch_wave(ctx, w, first_index + done, n);
+            if (rc) return rc;
+            done += n;
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        { int rc = sync_head(); if (rc) return rc; }
+        cudaEventElapsedTime(&kernel_ms, ctx->ev0, ctx->ev1);
+    } else {
+        uint64_t batch = 1;
+        for (;;) {
+            if (n_raw && done >= n_raw) break;
+            CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+            const unsigned long long seq0 = seq;
+            for (uint64_t k = 0; k < batch && !(n_raw && done >= n_raw); ++k) {
+                uint64_t n = max_launch;
+                if (n_raw && n_raw - done < n) n = n_raw - done;
+                int rc = launch_wave(ctx, w, first_index + done, n);
+                if (rc) return rc;
+                rc = publish(ctx, tallies_dev, ++seq);
+                if (rc) return rc;
+                done += n;
+            }
+            CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+            if (stream_copy) {
+                // follow the waves of the batch as they finish and copy what each one added
+                unsigned long long seen = seq0;
+                unsigned spins = 0;
+                while (seen < seq) {
+                    const unsigned long long now = head[4];
+                    if (now > seen) {
+                        seen = now;
+                        std::atomic_thread_fence(std::memory_order_acquire);
+                        int rc = copy_upto(head[2]);
+                        if (rc) return rc;
+                    } else if ((++spins & 0x3FFu) == 0u) {
+                        const cudaError_t q = cudaStreamQuery(ctx->stream);
+                        if (q == cudaSuccess) break;                         // drained: the final read below sees everything
+                        if (q != cudaErrorNotReady) return fail(BMC_E_CUDA, std::string("sampling kernel: ") + cudaGetErrorString(q));
+                        std::this_thread::yield();
+                    }
+                }
+            }
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            { int rc = copy_upto(head[2]); if (rc) return rc; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            kernel_ms += ms;
+            if (cc && w.interp) { std::lock_guard<std::mutex> jl(cc->cal_mu); cc->interp_ms += ms; }
+            const unsigned long long acc = head[2] - start_acc, raw = head[0] - start_raw;
+            if (n_accept_target && acc >= n_accept_target) break;
+            // watchdog for open-ended jobs: a constraint nothing satisfies must not spin forever
+            if (n_raw == 0 && ((done >= (1ull << 36) && acc == 0) || done >= (1ull << 44))) break;
+            if (w.seq && acc == 0 && head[1] >= done) break;                 // reference order: every build signalled an error
+            if (!n_accept_target) batch = 8;
+            else if (acc == 0 || raw == 0) batch = batch < 32 ? batch * 2 : 64;
+            else {
+                const double per_wave = (double)acc / (double)raw * (double)max_launch;
+                const double need = (double)(n_accept_target - acc) / per_wave;
+                batch = need < 1.0 ? 1 : need > 64.0 ? 64 : (uint64_t)(need + 0.999);
+            }
+            // a long job on interpreted rules: switch to the compiled kernel between batches (bit-identical results)
+            if (cc && w.interp && cc->jit == 2 && cc->interp_ms > 1000.0) {
+                int rc = resolve_cfg(ctx, cons, w);
+                if (rc) return rc;
             }
         }
-        if (n_accept_target && head[2] - start_acc >= n_accept_target) break;
-        // watchdog for open-ended jobs: a constraint nothing satisfies must not spin forever
-        if (n_raw == 0 && ((done >= (1ull << 36) && head[2] == start_acc) || done >= (1ull << 44))) break;
-        if (seq && head[2] == start_acc && head[1] >= done) break;      // reference order: every build signalled an error
     }
-    if (!stepwise) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-    CUDA_TRY(read_head());
-    if (getenv("BMC_DEBUG"))
-        fprintf(stderr, "[bmc] compute done at t=%.2f ms\n", std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    if (!stepwise && cc && w.interp) { std::lock_guard<std::mutex> jl(cc->cal_mu); cc->interp_ms += kernel_ms; }
     if (stream_copy) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
-    if (getenv("BMC_DEBUG"))
-        fprintf(stderr, "[bmc] copies done at t=%.2f ms\n", std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (stats) {
-        float ms = kernel_ms;
-        if (!stepwise) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        stats->raw = head[0]; stats->voided = head[1]; stats->accepted = head[2];
+        stats->raw = head[0] - start_raw; stats->voided = head[1]; stats->accepted = head[2];
         stats->stored = records_dev ? (head[2] < cap ? head[2] : cap) : 0;
-        stats->waves = waves;
+        stats->waves = (uint32_t)((stats->raw + max_launch - 1) / max_launch);        // waves that ran (cancelled ones draw nothing)
         stats->launches = (uint32_t)(ctx->launches - launches0);
-        stats->kernel_ms = ms;
+        stats->kernel_ms = kernel_ms;
+        stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return BMC_OK;
+}
+
+static int ensure_scratch(bmc_ctx *ctx, uint64_t bytes)
+{
+    // device scratch for the records is kept by the context and only ever grows
+    if (bytes > ctx->rec_bytes) {
+        if (ctx->d_rec) cudaFree(ctx->d_rec);
+        ctx->d_rec = nullptr;
+        ctx->rec_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_rec, bytes));
+        ctx->rec_bytes = bytes;
+    }
+    return BMC_OK;
+}
+
+static int sample_host(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                       uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records, uint64_t cap,
+                       bmc_tallies *tallies, bmc_stats *stats, uint32_t rec_mode)
+{
+    if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
+    auto t0 = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!records) cap = 0;
+    { int rc = ensure_scratch(ctx, cap * (rec_mode ? sizeof(uint32_t) : sizeof(bmc_record))); if (rc) return rc; }
+    CUDA_TRY(cudaMemsetAsync(ctx->d_tallies, 0, sizeof(bmc_tallies), ctx->stream));
+    bmc_stats st{};
+    int rc = sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, cap ? ctx->d_rec : nullptr, cap,
+                         ctx->d_tallies, &st, cap ? records : nullptr, rec_mode);
+    if (rc != BMC_OK) return rc;
+    bmc_tallies host_t;
+    CUDA_TRY(cudaMemcpyAsync(&host_t, ctx->d_tallies, sizeof host_t, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    host_t.stored = st.stored;
+    if (tallies) *tallies = host_t;
+    if (stats) {
+        *stats = st;
         stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     return BMC_OK;
@@ -1264,39 +1403,234 @@ int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uin
     std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     return sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, records_dev, cap, tallies_dev,
-                       stats, nullptr);
+                       stats, nullptr, 0u);
 }
 
 int bmc_sample(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
                uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, bmc_record *records, uint64_t cap,
                bmc_tallies *tallies, bmc_stats *stats)
 {
-    if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
-    auto t0 = std::chrono::steady_clock::now();
+    return sample_host(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, records, cap, tallies, stats, 0u);
+}
+
+// ---- index records: 4 bytes per accepted deal instead of 16, expanded on demand -------------------------------
+int bmc_sample_indices(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                       uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, uint32_t *offsets, uint64_t cap,
+                       bmc_tallies *tallies, bmc_stats *stats)
+{
+    return sample_host(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, offsets, cap, tallies, stats, 1u);
+}
+
+int bmc_sample_indices_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                           uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *offsets_dev, uint64_t cap,
+                           void *tallies_dev, bmc_stats *stats)
+{
+    if (!ctx || !tallies_dev) return fail(BMC_E_INVALID, "bmc_sample_indices_dev: ctx / tallies_dev is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (!records) cap = 0;
-    // device scratch for the records is kept by the context and only ever grows
-    if (cap > ctx->rec_cap) {
-        if (ctx->d_rec) cudaFree(ctx->d_rec);
-        ctx->d_rec = nullptr;
-        ctx->rec_cap = 0;
-        CUDA_TRY(cudaMalloc(&ctx->d_rec, cap * sizeof(bmc_record)));
-        ctx->rec_cap = cap;
+    return sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, offsets_dev, cap, tallies_dev,
+                       stats, nullptr, 1u);
+}
+
+static int expand_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, const uint32_t *d_off,
+                       uint64_t n, uint4 *d_out)
+{
+    WaveCfg w;
+    { int rc = resolve_cfg(ctx, cons, w); if (rc) return rc; }
+    SampleArgs a;
+    memset(&a, 0, sizeof a);
+    a.cons = w.cons;
+    if (w.fix) a.fix = *w.fix;
+    else a.fix.n_free = 52;
+    a.key = philox_key(seed);
+    a.first = first_index;
+    {
+        uint32_t cap4[4] = {13, 13, 13, 13};
+        cap4[w.cons.primary & 3u] = 0;
+        const uint32_t p0 = cap4[0], p1 = p0 + cap4[1], p2 = p1 + cap4[2];
+        a.sf_q0 = (128u - p0) | ((128u - p1) << 8) | ((128u - p2) << 16);
     }
-    CUDA_TRY(cudaMemsetAsync(ctx->d_tallies, 0, sizeof(bmc_tallies), ctx->stream));
-    bmc_stats st{};
-    int rc = sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, cap ? ctx->d_rec : nullptr, cap,
-                         ctx->d_tallies, &st, cap ? records : nullptr);
-    if (rc != BMC_OK) return rc;
-    bmc_tallies host_t;
-    CUDA_TRY(cudaMemcpyAsync(&host_t, ctx->d_tallies, sizeof host_t, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    host_t.stored = st.stored;
-    if (tallies) *tallies = host_t;
+    const int mode = w.seq ? 3 : w.seatfirst ? 2 : 1;
+    static const SeqDev no_seq{};
+    uint64_t want = (n + THREADS - 1) / THREADS;
+    const unsigned blocks = (unsigned)(want < (uint64_t)ctx->sms * 8 ? want : (uint64_t)ctx->sms * 8);
+    expand_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a, w.seq ? *w.seq : no_seq, mode, d_off, n, d_out);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BMC_OK;
+}
+
+// records[i] = the deal behind index first_index + offsets[i], for the same (cons, seed) the offsets were sampled
+// with (bmc_sample_indices).  Host buffers.
+int bmc_expand(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, const uint32_t *offsets,
+               uint64_t n, bmc_record *records)
+{
+    if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
+    if (n == 0) return BMC_OK;
+    if (!offsets || !records) return fail(BMC_E_INVALID, "bmc_expand: NULL buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t chunk = 1ull << 24;                   // bounded device footprint: 16 Mi deals per pass
+    const uint64_t m = n < chunk ? n : chunk;
+    { int rc = ensure_scratch(ctx, m * (sizeof(uint32_t) + sizeof(bmc_record))); if (rc) return rc; }
+    uint4 *d_out = (uint4 *)ctx->d_rec;
+    uint32_t *d_off = (uint32_t *)((char *)ctx->d_rec + m * sizeof(bmc_record));
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t k = n - off < chunk ? n - off : chunk;
+        CUDA_TRY(cudaMemcpyAsync(d_off, offsets + off, k * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = expand_core(ctx, cons, seed, first_index, d_off, k, d_out);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(records + off, d_out, k * sizeof(bmc_record), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return BMC_OK;
+}
+
+int bmc_expand_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, const void *offsets_dev,
+                   uint64_t n, void *records_dev)
+{
+    if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
+    if (n == 0) return BMC_OK;
+    if (!offsets_dev || !records_dev) return fail(BMC_E_INVALID, "bmc_expand_dev: NULL buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return expand_core(ctx, cons, seed, first_index, (const uint32_t *)offsets_dev, n, (uint4 *)records_dev);
+}
+
+// ---- one call, several devices ---------------------------------------------------------------------------------
+// The index range [first_index, first_index + n_raw) is split into contiguous shares, one host thread and one context
+// per device; the only exchange is the sum of the tally buffers (device 0 reads its peers' over NVLink when peer
+// access is available, else the host adds them).  Because a deal is a pure function of (seed, index), tallies and the
+// accepted set are identical for every number of devices.  With an accept target every device runs whole waves of its
+// own sub-range [first_index + g 2^40, ...) until it holds its share of the target.
+struct MultiPool {
+    std::mutex mu;
+    std::map<int, bmc_ctx *> ctx;
+    ~MultiPool() { for (auto &kv : ctx) bmc_shutdown(kv.second); }
+};
+static MultiPool g_pool;
+
+int bmc_sample_multi(const int *devices, int n_devices, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
+                     uint64_t n_raw, uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, bmc_record *records,
+                     uint64_t cap, bmc_tallies *tallies, bmc_stats *stats)
+{
+    if (!devices || n_devices < 1 || n_devices > 16) return fail(BMC_E_INVALID, "bmc_sample_multi: 1..16 devices");
+    if (n_accept_target == 0 && n_raw == 0) return fail(BMC_E_INVALID, "nothing to do: n_raw == 0 and no accept target");
+    auto t0 = std::chrono::steady_clock::now();
+    const int G = n_devices;
+    std::vector<bmc_ctx *> ctxs(G, nullptr);
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        for (int g = 0; g < G; ++g) {
+            for (int h = 0; h < g; ++h)
+                if (devices[h] == devices[g]) return fail(BMC_E_INVALID, "bmc_sample_multi: a device is listed twice");
+            bmc_ctx *&c = g_pool.ctx[devices[g]];
+            if (!c) { int rc = bmc_init(devices[g], &c); if (rc) { g_pool.ctx.erase(devices[g]); return rc; } }
+            ctxs[g] = c;
+        }
+    }
+    if (!records) cap = 0;
+    // resolve the dealing mode once (on the first device) so that every device deals the same way
+    {
+        std::lock_guard<std::mutex> lk(ctxs[0]->mu);
+        CUDA_TRY(cudaSetDevice(ctxs[0]->device));
+        WaveCfg w;
+        int rc = resolve_cfg(ctxs[0], cons, w);
+        if (rc) return rc;
+    }
+    std::vector<int> rcs(G, BMC_OK);
+    std::vector<std::string> errs(G);
+    std::vector<bmc_stats> sts(G);
+    std::vector<uint64_t> slot(G + 1, 0);
+    const uint64_t cap_g = cap / (uint64_t)G;
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            bmc_ctx *ctx = ctxs[g];
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            auto run = [&]() -> int {
+                CUDA_TRY(cudaSetDevice(ctx->device));
+                uint64_t first = first_index, count = 0, target = 0;
+                if (n_accept_target) {
+                    first = first_index + ((uint64_t)g << 40);
+                    target = (n_accept_target + (uint64_t)G - 1) / (uint64_t)G;
+                    count = n_raw ? (n_raw + (uint64_t)G - 1) / (uint64_t)G : 0;
+                } else {
+                    const uint64_t base = n_raw / (uint64_t)G, extra = n_raw % (uint64_t)G;
+                    count = base + ((uint64_t)g < extra ? 1 : 0);
+                    first = first_index + (uint64_t)g * base + ((uint64_t)g < extra ? (uint64_t)g : extra);
+                }
+                CUDA_TRY(cudaMemsetAsync(ctx->d_tallies, 0, sizeof(bmc_tallies), ctx->stream));
+                if (!n_accept_target && count == 0) { sts[g] = bmc_stats{}; return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? BMC_OK : BMC_E_CUDA; }
+                int rc = ensure_scratch(ctx, cap_g * sizeof(bmc_record));
+                if (rc) return rc;
+                return sample_core(ctx, cons, seed, first, count, target, wave, tally_mask, cap_g ? ctx->d_rec : nullptr, cap_g,
+                                   ctx->d_tallies, &sts[g], cap_g ? (void *)(records + (uint64_t)g * cap_g) : nullptr, 0u);
+            };
+            rcs[g] = run();
+            if (rcs[g]) errs[g] = g_err;
+        });
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], "device " + std::to_string(devices[g]) + ": " + errs[g]);
+    // ---- the one exchange: sum of the tally buffers ----
+    bmc_tallies total;
+    memset(&total, 0, sizeof total);
+    bool p2p = G > 1;
+    for (int g = 1; g < G && p2p; ++g) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctxs[0]->device, ctxs[g]->device) != cudaSuccess || !can) p2p = false;
+    }
+    if (p2p) {
+        std::lock_guard<std::mutex> lk(ctxs[0]->mu);
+        CUDA_TRY(cudaSetDevice(ctxs[0]->device));
+        PeerTallies peers{};
+        peers.n = G - 1;
+        for (int g = 1; g < G; ++g) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[g]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { p2p = false; break; }
+            cudaGetLastError();
+            peers.p[g - 1] = ctxs[g]->d_tallies;
+        }
+        if (p2p) {
+            reduce_peer_tallies_kernel<<<2, 256, 0, ctxs[0]->stream>>>(ctxs[0]->d_tallies, peers, (int)BMC_TALLY_WORDS);
+            ctxs[0]->launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(&total, ctxs[0]->d_tallies, sizeof total, cudaMemcpyDeviceToHost, ctxs[0]->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctxs[0]->stream));
+        }
+    }
+    if (!p2p) {
+        uint64_t *acc = reinterpret_cast<uint64_t *>(&total);
+        memset(&total, 0, sizeof total);
+        for (int g = 0; g < G; ++g) {
+            bmc_tallies t;
+            std::lock_guard<std::mutex> lk(ctxs[g]->mu);
+            CUDA_TRY(cudaSetDevice(ctxs[g]->device));
+            CUDA_TRY(cudaMemcpyAsync(&t, ctxs[g]->d_tallies, sizeof t, cudaMemcpyDeviceToHost, ctxs[g]->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctxs[g]->stream));
+            const uint64_t *src = reinterpret_cast<const uint64_t *>(&t);
+            for (size_t i = 0; i < BMC_TALLY_WORDS; ++i) acc[i] += src[i];
+        }
+    }
+    // ---- close the gaps between the devices' record segments ----
+    uint64_t stored = 0;
+    for (int g = 0; g < G; ++g) {
+        if (cap_g && g > 0 && sts[g].stored) memmove(records + stored, records + (uint64_t)g * cap_g, sts[g].stored * sizeof(bmc_record));
+        stored += cap_g ? sts[g].stored : 0;
+    }
+    total.stored = stored;
+    if (tallies) *tallies = total;
     if (stats) {
-        *stats = st;
-        stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        bmc_stats s{};
+        for (int g = 0; g < G; ++g) {
+            s.raw += sts[g].raw; s.voided += sts[g].voided; s.accepted += sts[g].accepted;
+            s.waves += sts[g].waves; s.launches += sts[g].launches;
+            if (sts[g].kernel_ms > s.kernel_ms) s.kernel_ms = sts[g].kernel_ms;      // device time: the slowest device's
+        }
+        s.stored = stored;
+        s.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        *stats = s;
     }
     return BMC_OK;
 }
@@ -1342,14 +1676,6 @@ int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *sche
 }
 
 // ---- scoring --------------------------------------------------------------------
-static int check_contracts(const bmc_contract *c, uint32_t n)
-{
-    for (uint32_t i = 0; i < n; ++i)
-        if (c[i].level < 0 || c[i].level > 7 || c[i].suit < 0 || c[i].suit > 4 || c[i].dbl < 0 || c[i].dbl > 2 || c[i].declarer < -1 || c[i].declarer > 3)
-            return fail(BMC_E_INVALID, "contract " + std::to_string(i) + " out of range");
-    return BMC_OK;
-}
-
 int bmc_score(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulnerable, uint32_t nc, const uint8_t *tricks,
               uint64_t n, int32_t *scores)
 {
@@ -1373,7 +1699,7 @@ int bmc_score(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulner
     if (e == cudaSuccess) {
         const uint64_t want = (total / 4 + 255) / 256 + 1;
         const unsigned blocks = (unsigned)(want < (uint64_t)ctx->sms * 16 ? want : (uint64_t)ctx->sms * 16);
-        score_kernel<<<blocks, 256, 0, ctx->stream>>>(d_c, d_v, nc, d_t, total, d_s);
+        score_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const ContractDev *>(d_c), d_v, nc, d_t, total, d_s);
         ctx->launches++;
         e = cudaGetLastError();
     }
@@ -1413,42 +1739,38 @@ int bmc_match_points(bmc_ctx *ctx, const int32_t *a, const int32_t *b, uint64_t 
 
 int bmc_score_tally(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulnerable, uint32_t nc, const uint8_t *pairs,
                     uint32_t n_pairs, uint64_t seed, uint64_t first_index, uint64_t n, uint64_t *tricks_hist, uint64_t *imp_hist,
-                    int32_t *score_table)
+                    uint64_t *imp_dropped, int32_t *score_table)
 {
     if (!ctx || !contracts || nc == 0 || nc > 8 || n_pairs > 8 || !tricks_hist) return fail(BMC_E_INVALID, "bmc_score_tally: bad argument");
     if (n_pairs && (!pairs || !imp_hist)) return fail(BMC_E_INVALID, "bmc_score_tally: pairs / imp_hist is NULL");
-    { int rc = check_contracts(contracts, nc); if (rc) return rc; }
     ContractTable t{};
-    t.n = nc; t.n_pairs = n_pairs;
-    for (uint32_t i = 0; i < nc; ++i) { t.c[i] = contracts[i]; t.vul[i] = vulnerable ? vulnerable[i] : 0; }
-    for (uint32_t i = 0; i < 2 * n_pairs; ++i) {
-        if (pairs[i] >= nc) return fail(BMC_E_INVALID, "pair index out of range");
-        t.pairs[i] = pairs[i];
-    }
+    { int rc = fill_contract_table(t, contracts, vulnerable, nc, pairs, n_pairs); if (rc) return rc; }
     if (score_table)
         for (uint32_t c = 0; c < nc; ++c)
             for (int tr = 0; tr < 14; ++tr) score_table[c * 14 + tr] = base_score_dev(t.c[c], tr, t.vul[c]);
     std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     unsigned long long *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, (8 * 14 + 8 * 49) * sizeof(unsigned long long)));
-    cudaError_t e = cudaMemsetAsync(d, 0, (8 * 14 + 8 * 49) * sizeof(unsigned long long), ctx->stream);
+    CUDA_TRY(cudaMalloc(&d, SCORE_WORDS * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, SCORE_WORDS * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess && n) {
         uint64_t want = (n + 255) / 256;
         const unsigned blocks = (unsigned)(want < (uint64_t)ctx->sms * 8 ? want : (uint64_t)ctx->sms * 8);
-        score_tally_kernel<<<blocks, 256, 0, ctx->stream>>>(t, philox_key(seed), first_index, n, d, d + 8 * 14);
+        score_tally_kernel<<<blocks, 256, 0, ctx->stream>>>(t, philox_key(seed), first_index, n, d);
         ctx->launches++;
         e = cudaGetLastError();
     }
-    std::vector<unsigned long long> h(8 * 14 + 8 * 49);
+    std::vector<unsigned long long> h(SCORE_WORDS);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
     if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("bmc_score_tally: ") + cudaGetErrorString(e));
     for (uint32_t c = 0; c < nc; ++c)
         for (int tr = 0; tr < 14; ++tr) tricks_hist[c * 14 + tr] = h[c * 14 + tr];
-    for (uint32_t p = 0; p < n_pairs; ++p)
-        for (int v = 0; v < 49; ++v) imp_hist[p * 49 + v] = h[8 * 14 + p * 49 + v];
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        for (int v = 0; v < 49; ++v) imp_hist[p * 49 + v] = h[SCORE_TR_WORDS + p * 49 + v];
+        if (imp_dropped) imp_dropped[p] = h[SCORE_TR_WORDS + SCORE_IMP_WORDS + p];
+    }
     return BMC_OK;
 }
 
@@ -1486,12 +1808,13 @@ int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc
     alloc((void **)&d_rec, n * sizeof(uint4));
     alloc((void **)&d_keys, n * 8); alloc((void **)&d_keys2, n * 8); alloc((void **)&d_uniq, n * 8);
     alloc((void **)&d_idx, n * 4); alloc((void **)&d_idx2, n * 4); alloc((void **)&d_cnt, n * 4); alloc((void **)&d_runs, 4);
-    alloc((void **)&d_lut, sizeof g_shape_lut);
+    alloc((void **)&d_lut, sizeof(ShapeLut));
     std::vector<unsigned long long> h_uniq;
     std::vector<uint32_t> h_cnt, h_first;
     uint32_t runs = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rec, records, n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lut, g_shape_lut, sizeof g_shape_lut, cudaMemcpyHostToDevice, ctx->stream);
+    static const ShapeLut h_lut = make_shape_lut();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lut, h_lut.v, sizeof(ShapeLut), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         measure_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(md, d_rec, n, d_lut, d_keys, d_idx);
         ctx->launches++;
@@ -1510,13 +1833,15 @@ int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess && runs) {
         h_uniq.resize(runs); h_cnt.resize(runs); h_first.resize(runs);
-        e = cudaMemcpy(h_uniq.data(), d_uniq, runs * 8ull, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(h_cnt.data(), d_cnt, runs * 4ull, cudaMemcpyDeviceToHost);
+        e = cudaMemcpyAsync(h_uniq.data(), d_uniq, runs * 8ull, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt.data(), d_cnt, runs * 4ull, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         std::vector<unsigned long long> off(runs);
         unsigned long long acc = 0;
         for (uint32_t i = 0; i < runs; ++i) { off[i] = acc; acc += h_cnt[i]; }
         alloc((void **)&d_off, runs * 8ull); alloc((void **)&d_first, runs * 4ull);
-        if (e == cudaSuccess) e = cudaMemcpy(d_off, off.data(), runs * 8ull, cudaMemcpyHostToDevice);
+        // same stream as the kernel that reads it (ctx->stream is non-blocking: the legacy stream would not order them)
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off.data(), runs * 8ull, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) {
             gather_first_kernel<<<(runs + 255) / 256, 256, 0, ctx->stream>>>(d_idx2, d_off, runs, d_first);
             ctx->launches++;

@@ -80,10 +80,14 @@ __device__ __forceinline__ uint8_t *feat_store(uint32_t *warp_scratch, unsigned 
     return reinterpret_cast<uint8_t *>(p);
 }
 
-// Interpret one program (warp-uniform control flow; boolean stack in one 32-bit register, depth
-// checked by the compiler).  `fb` = this lane's feature bytes (feat_store).  The next word is
-// fetched while the current one executes.  err is set where the reference would signal an
-// "illegal function call" (un-spliced rule lists, bidding.cl:249).
+// Interpret one program (warp-uniform control flow; the boolean stack lives in one 32-bit register,
+// two bits per slot -- value, error -- depth <= 15 checked by the compiler).  `fb` = this lane's
+// feature bytes (feat_store).  The next word is fetched while the current one executes.  err is set
+// where the reference would signal an "illegal function call" (un-spliced rule lists,
+// bidding.cl:249) -- i.e. only when Lisp's left-to-right short-circuit evaluation REACHES the
+// illegal form: programs that contain one use the three-valued ops (bytecode.h); invariant: value
+// bit = 0 wherever the error bit is set.  Programs without one never set an error bit and keep the
+// cheap two-valued ops.
 __device__ __forceinline__ bool run_program(const uint32_t *__restrict__ code, const uint8_t *fb, bool &err)
 {
     uint32_t st = 0;
@@ -96,16 +100,24 @@ __device__ __forceinline__ bool run_program(const uint32_t *__restrict__ code, c
             const uint32_t a = fb[(w >> 8) & 15u];
             const uint32_t b = op == OP_CMPC ? (w >> 16) & 0xFFu : (uint32_t)fb[(w >> 12) & 15u];
             const uint32_t state = a < b ? 0u : (a == b ? 1u : 2u);
-            st = (st << 1) | (((w >> 4) >> state) & 1u);
-        } else if (op == OP_AND) { const uint32_t t = st & 1u; st >>= 1; st &= ~1u | t; }
-        else if (op == OP_OR) { const uint32_t t = st & 1u; st >>= 1; st |= t; }
+            st = (st << 2) | (((w >> 4) >> state) & 1u);
+        } else if (op == OP_AND) { const uint32_t t = st & 1u; st >>= 2; st &= ~1u | t; }
+        else if (op == OP_OR) { const uint32_t t = st & 1u; st >>= 2; st |= t; }
         else if (op == OP_NOT) st ^= 1u;
-        else if (op == OP_TRUE) st = (st << 1) | 1u;
-        else if (op == OP_FALSE) st <<= 1;
-        else if (op == OP_ERRIF_T) { err |= (st & 1u) != 0u; st &= ~1u; }
-        else if (op == OP_ERRIF_F) err |= (st & 1u) == 0u;
+        else if (op == OP_TRUE) st = (st << 2) | 1u;
+        else if (op == OP_FALSE) st <<= 2;
+        else if (op == OP_ERR) st = (st << 2) | 2u;
+        else if (op == OP_AND3 || op == OP_OR3) {     // a = the slot below, b = the top slot
+            const uint32_t vb = st & 1u, eb = (st >> 1) & 1u;
+            st >>= 2;
+            const uint32_t va = st & 1u, ea = (st >> 1) & 1u;
+            const uint32_t v = op == OP_AND3 ? (va & vb) : (va | (vb & (ea ^ 1u)));
+            const uint32_t e = op == OP_AND3 ? (ea | (va & eb)) : (ea | ((va ^ 1u) & eb));
+            st = (st & ~3u) | v | (e << 1);
+        } else if (op == OP_NOT3) st = (st & ~1u) | (((st | (st >> 1)) & 1u) ^ 1u);
         w = next;
     }
+    err = err || (st & 2u) != 0u;
     return (st & 1u) != 0u;
 }
 

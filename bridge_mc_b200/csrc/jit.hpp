@@ -23,17 +23,9 @@ namespace bmc {
 // ---- S-expression -> C++ expression (same language as RuleCompiler::expr) -----------------
 class RuleEmitter {
 public:
-    std::string emit(const Sx &x)
-    {
-        try {
-            return expr(x);
-        } catch (const Illegal &) {
-            return "(err = true, false)";
-        }
-    }
+    std::string emit(const Sx &x) { return expr(x); }
 
 private:
-    struct Illegal {};
     static const char *var_of(const std::string &s)
     {
         static const char *in[] = {"C", "D", "H", "S", "CPOWER", "DPOWER", "HPOWER", "SPOWER", "HCP", "LOOSERS", "LOSERS"};
@@ -93,23 +85,16 @@ private:
         case Sx::LIST: break;
         }
         const Sx &h = x.items[0];
-        if (h.kind != Sx::SYM) throw Illegal{};
+        // an "illegal function call" (bidding.cl:249) counts only where C++'s own short-circuit order -- the
+        // same as Lisp's -- reaches it
+        if (h.kind != Sx::SYM) return "(err = true, false)";
         const std::string &op = h.sym;
         const size_t n = x.items.size() - 1;
         if (op == "AND" || op == "OR") {
             const bool is_and = op == "AND";
             if (n == 0) return is_and ? "true" : "false";
             std::string s = "(";
-            for (size_t i = 1; i <= n; ++i) {
-                std::string part;
-                try {
-                    part = expr(x.items[i]);
-                } catch (const Illegal &) {
-                    if (i == 1) throw;
-                    part = "(err = true, false)";          // reached only if the prefix lets evaluation through
-                }
-                s += (i > 1 ? (is_and ? " && " : " || ") : "") + part;
-            }
+            for (size_t i = 1; i <= n; ++i) s += (i > 1 ? (is_and ? " && " : " || ") : "") + expr(x.items[i]);
             return s + ")";
         }
         if (op == "NOT" || op == "NULL") return "(!" + expr(x.items.at(1)) + ")";

@@ -8,11 +8,13 @@
 #include "deal.cuh"
 #include "features.cuh"
 #include "seatfirst.cuh"
+#include "score.cuh"
 
 #ifndef BMC_TALLY_HCP          /* NVRTC build: the few constants of bridgemc.h the kernels need */
 #define BMC_TALLY_HCP   1u
 #define BMC_TALLY_LEN   2u
 #define BMC_TALLY_SHAPE 4u
+#define BMC_TALLY_SCORE 8u
 #define BMC_LEN_BINS   14
 #endif
 
@@ -35,25 +37,111 @@ struct ConsDev {
     unsigned long long sf_void;    // u >= sf_void = S * C(52,13) voids the index (probability 1.2e-8)
 };
 
-// shared-memory histogram (per warp): hcp[4][40] | len[4][4][16] | shape[4][40]
+// shared-memory histogram (per copy): hcp[4][40] | len[4][4][16] | shape[4][40]
 constexpr int SH_HCP = 0, SH_LEN = 160, SH_SHAPE = 160 + 256, SH_WORDS = 160 + 256 + 160;
 constexpr int WARPS_PER_BLOCK = 8, THREADS = WARPS_PER_BLOCK * 32;
 constexpr int QCAP = 64;     // per-warp queue of stage-A survivors
+constexpr int FULL_HIST_COPIES = 8, SF_HIST_COPIES = 2;
+// words of bmc_tallies: 4 counters | hcp[4][40] | len[4][4][14] | shape[4][40] | tricks[8][14] | imps[8][49] | imp_dropped[8]
+constexpr int TALLY_SCORE_WORD = 4 + 160 + 224 + 160;
 
-__constant__ uint8_t c_shape_lut[14 * 14 * 14];   // (len_c, len_d, len_h) -> sorted-shape class
+// (len_c, len_d, len_h) -> sorted-shape class: the 39 shapes a >= b >= c >= d, a + b + c + d = 13, in the order
+// of bmc_shape_table (a ascending from 4, then b, then c).  A compile-time constant (no upload).
+struct ShapeLut { uint8_t v[14 * 14 * 14]; };
+struct ShapeList { uint8_t s[39][4]; };
+__host__ __device__ constexpr ShapeList make_shape_list()
+{
+    ShapeList L{};
+    int n = 0;
+    for (int a = 4; a <= 13; ++a)
+        for (int b = 0; b <= a; ++b)
+            for (int c = 0; c <= b; ++c) {
+                const int d = 13 - a - b - c;
+                if (d < 0 || d > c) continue;
+                L.s[n][0] = (uint8_t)a; L.s[n][1] = (uint8_t)b; L.s[n][2] = (uint8_t)c; L.s[n][3] = (uint8_t)d;
+                ++n;
+            }
+    return L;
+}
+__host__ __device__ constexpr ShapeLut make_shape_lut()
+{
+    ShapeLut T{};
+    const ShapeList L = make_shape_list();
+    for (int i = 0; i < 14 * 14 * 14; ++i) T.v[i] = 0xFF;
+    for (int x = 0; x <= 13; ++x)
+        for (int y = 0; x + y <= 13; ++y)
+            for (int z = 0; x + y + z <= 13; ++z) {
+                int v[4] = {x, y, z, 13 - x - y - z};
+                for (int i = 0; i < 4; ++i)
+                    for (int j = i + 1; j < 4; ++j)
+                        if (v[j] > v[i]) { const int t = v[i]; v[i] = v[j]; v[j] = t; }
+                for (int k = 0; k < 39; ++k)
+                    if (L.s[k][0] == v[0] && L.s[k][1] == v[1] && L.s[k][2] == v[2] && L.s[k][3] == v[3])
+                        T.v[x * 196 + y * 14 + z] = (uint8_t)k;
+            }
+    return T;
+}
+__constant__ ShapeLut c_shape_lut = make_shape_lut();
+constexpr int SHAPE_LUT_WORDS = (14 * 14 * 14 + 3) / 4;
 
 struct SampleArgs {
     ConsDev cons;
     PhiloxKey key;
     FixDev fix;
     uint64_t first, n;
-    uint4 *records;          // may be null
+    void *records;           // may be null; uint4 records, or 32-bit index offsets when rec_mode = 1
     uint64_t cap;
     unsigned long long *tallies;   // bmc_tallies as u64 words
     uint32_t tally_mask;
     uint32_t iters;          // warp-iterations per warp (seat-first: each covers 4 SF_CALLS indices per lane)
     uint32_t sf_q0;          // seat-first mode: initial Q of stage B (capacity 0 for the primary seat)
-    uint32_t pad;
+    uint32_t rec_mode;       // 0: 128-bit records; 1: the accepted deal's index as a 32-bit offset from the CALL's first index
+    uint32_t idx_base;       // rec_mode 1: a.first - (first index of the call)
+    uint32_t flags;          // bit 0: this launch interprets rule programs (needs the feature scratch)
+    uint64_t target;         // != 0: the launch does nothing if *snap - start_acc >= target: accept-target jobs enqueue their
+    uint64_t start_acc;      //       waves back to back and the waves after the one that reaches the target are no-ops.
+    const unsigned long long *snap;   // the accepted counter as it stood when the previous wave ended (publish_counters_kernel)
+    ContractTable score;     // BMC_TALLY_SCORE: contracts / IMP pairs tallied over the accepted deals (score.cuh)
+    PhiloxKey tkey;          // key of the stand-in trick source
+};
+constexpr uint32_t ARGS_INTERP = 1u;
+
+// Dynamic shared memory: only what the launch needs, so the common configurations keep their occupancy.
+// Offsets in 32-bit words from the start of the dynamic segment; computed identically by host and device.
+struct SmemPlan {
+    uint32_t low, q1, q2, q3, q3i, shape, hist, feat, sc_hist, sc_tab, words;
+};
+__host__ __device__ inline uint32_t smem_take(uint32_t &cur, uint32_t words)
+{
+    const uint32_t at = cur;
+    cur += (words + 3u) & ~3u;                  // 16-byte granules
+    return at;
+}
+// seatfirst = the seat-first kernel; two_stage = stage B is split by a third queue
+__host__ __device__ inline SmemPlan smem_plan(bool seatfirst, bool has_queue, bool two_stage, bool interp, uint32_t tally_mask)
+{
+    SmemPlan p{};
+    uint32_t cur = 0;
+    p.low = seatfirst ? smem_take(cur, (uint32_t)(sizeof(LowTabs) / 4)) : 0u;
+    p.q2 = has_queue ? smem_take(cur, WARPS_PER_BLOCK * QCAP * 4) : 0u;                 // uint4 entries
+    p.q1 = has_queue ? smem_take(cur, WARPS_PER_BLOCK * (seatfirst ? 128 : QCAP)) : 0u;  // seat-first: A1 survivors; full deal: offsets of q2's entries
+    p.q3 = two_stage ? smem_take(cur, WARPS_PER_BLOCK * QCAP * 4) : 0u;
+    p.q3i = two_stage ? smem_take(cur, WARPS_PER_BLOCK * QCAP) : 0u;
+    p.shape = (tally_mask & BMC_TALLY_SHAPE) ? smem_take(cur, SHAPE_LUT_WORDS) : 0u;
+    p.hist = (tally_mask & 7u) ? smem_take(cur, (seatfirst ? SF_HIST_COPIES : FULL_HIST_COPIES) * SH_WORDS) : 0u;
+    p.feat = interp ? smem_take(cur, WARPS_PER_BLOCK * FEAT_SCRATCH_WORDS) : 0u;
+    p.sc_hist = (tally_mask & BMC_TALLY_SCORE) ? smem_take(cur, SCORE_WORDS) : 0u;
+    p.sc_tab = (tally_mask & BMC_TALLY_SCORE) ? smem_take(cur, SCORE_TR_WORDS) : 0u;
+    p.words = cur;
+    return p;
+}
+
+// what stage B needs of the block's shared memory
+struct TallyMem {
+    uint32_t *hist;          // this warp's histogram copy
+    const uint8_t *shape;    // sorted-shape LUT
+    uint32_t *sc_hist;       // score histogram (one per block)
+    const int *sc_tab;       // base-score table [8][14]
 };
 
 __device__ __forceinline__ void seat_words(const Planes &pl, int k, uint32_t &m0, uint32_t &m1)
@@ -93,8 +181,9 @@ __device__ __forceinline__ bool seats_pass(const SampleArgs &a, const Planes &pl
 }
 
 // Stage B: test of the constrained seats (`what`: ranges, programs or both), then tallies and the compacted store.
-__device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, bool active, uint32_t *hist,
-                                        const uint8_t *shape_lut, unsigned lane, uint32_t *scratch, uint32_t what = TEST_ALL)
+// `off` = the deal's index - a.first (stored instead of the record when rec_mode = 1).
+__device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, uint32_t off, bool active, const TallyMem &tm,
+                                        unsigned lane, uint32_t *scratch, uint32_t what = TEST_ALL)
 {
     const bool ok = seats_pass(a, pl, what, scratch, lane) && active;
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
@@ -105,62 +194,112 @@ __device__ __forceinline__ void stage_b(const SampleArgs &a, const Planes &pl, b
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (ok) {
         const unsigned long long slot = base + __popc(bal & ((1u << lane) - 1u));
-        if (a.records != nullptr && slot < a.cap) a.records[slot] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
-        if (a.tally_mask) {
+        if (a.records != nullptr && slot < a.cap) {
+            if (a.rec_mode == 0u) reinterpret_cast<uint4 *>(a.records)[slot] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+            else reinterpret_cast<uint32_t *>(a.records)[slot] = a.idx_base + off;
+        }
+        if (a.tally_mask & 7u) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t m0, m1;
                 seat_words(pl, k, m0, m1);
                 const Feat f = hand_features(m0, m1);
-                if (a.tally_mask & BMC_TALLY_HCP) atomicAdd(&hist[SH_HCP + k * 40 + (f.f2 & 0xFFu)], 1u);
+                if (a.tally_mask & BMC_TALLY_HCP) atomicAdd(&tm.hist[SH_HCP + k * 40 + (f.f2 & 0xFFu)], 1u);
                 if (a.tally_mask & BMC_TALLY_LEN) {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) atomicAdd(&hist[SH_LEN + (k * 4 + s) * 16 + ((f.f0 >> (8 * s)) & 0xFFu)], 1u);
+                    for (int s = 0; s < 4; ++s) atomicAdd(&tm.hist[SH_LEN + (k * 4 + s) * 16 + ((f.f0 >> (8 * s)) & 0xFFu)], 1u);
                 }
                 if (a.tally_mask & BMC_TALLY_SHAPE) {
                     const uint32_t L = f.f0;
-                    const uint32_t cls = shape_lut[(L & 0xFFu) * 196u + ((L >> 8) & 0xFFu) * 14u + ((L >> 16) & 0xFFu)];
-                    atomicAdd(&hist[SH_SHAPE + k * 40 + cls], 1u);
+                    const uint32_t cls = tm.shape[(L & 0xFFu) * 196u + ((L >> 8) & 0xFFu) * 14u + ((L >> 16) & 0xFFu)];
+                    atomicAdd(&tm.hist[SH_SHAPE + k * 40 + cls], 1u);
                 }
             }
+        }
+        if (a.tally_mask & BMC_TALLY_SCORE) {
+            // compscore tallies over the accepted deal (base-score / match-points, compscore.cl:94-131): the stand-in
+            // trick source is keyed on the deal itself (score.cuh)
+            uint32_t tr[8];
+            tricks_of(a.tkey, pl.lo0, pl.lo1, pl.hi0, pl.hi1, tr);
+            score_tally_update(a.score, tm.sc_tab, tr, tm.sc_hist);
         }
     }
 }
 
-// block-level flush of the per-warp shared histograms into bmc_tallies (u64 atomics)
-__device__ __forceinline__ void flush_hist(const SampleArgs &a, const uint32_t *s_hist, int copies = WARPS_PER_BLOCK)
+// block-level set-up / flush of the shared histograms
+__device__ __forceinline__ void tally_init(const SampleArgs &a, const SmemPlan &p, uint32_t *smem, int copies)
 {
-    if (!a.tally_mask) return;
-    for (int i = threadIdx.x; i < SH_WORDS; i += THREADS) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int w = 0; w < copies; ++w) v += s_hist[w * SH_WORDS + i];
-        if (v == 0u) continue;
-        int word;                                                                    // padded shared layout -> bmc_tallies words
-        if (i < SH_LEN) word = 4 + i;                                                // hcp[4][40]
-        else if (i < SH_SHAPE) {
-            const int j = i - SH_LEN, bin = j & 15;
-            if (bin >= BMC_LEN_BINS) continue;
-            word = 4 + 160 + (j >> 4) * BMC_LEN_BINS + bin;                          // len[4][4][14]
-        } else word = 4 + 160 + 224 + (i - SH_SHAPE);                                // shape[4][40]
-        atomicAdd(&a.tallies[word], (unsigned long long)v);
+    if (a.tally_mask & 7u)
+        for (int i = threadIdx.x; i < copies * SH_WORDS; i += THREADS) smem[p.hist + i] = 0u;
+    if (a.tally_mask & BMC_TALLY_SHAPE)
+        for (int i = threadIdx.x; i < SHAPE_LUT_WORDS; i += THREADS)
+            smem[p.shape + i] = reinterpret_cast<const uint32_t *>(c_shape_lut.v)[i];
+    if (a.tally_mask & BMC_TALLY_SCORE) {
+        for (int i = threadIdx.x; i < SCORE_WORDS; i += THREADS) smem[p.sc_hist + i] = 0u;
+        for (int i = threadIdx.x; i < SCORE_TR_WORDS; i += THREADS) {
+            const int c = i / 14;
+            reinterpret_cast<int *>(smem)[p.sc_tab + i] = c < (int)a.score.n ? base_score_dev(a.score.c[c], i % 14, a.score.vul[c]) : 0;
+        }
     }
 }
+__device__ __forceinline__ TallyMem tally_mem(const SmemPlan &p, uint32_t *smem, unsigned copy)
+{
+    TallyMem tm;
+    tm.hist = smem + p.hist + copy * SH_WORDS;
+    tm.shape = reinterpret_cast<const uint8_t *>(smem + p.shape);
+    tm.sc_hist = smem + p.sc_hist;
+    tm.sc_tab = reinterpret_cast<const int *>(smem + p.sc_tab);
+    return tm;
+}
+__device__ __forceinline__ void flush_hist(const SampleArgs &a, const SmemPlan &p, const uint32_t *smem, int copies)
+{
+    if (a.tally_mask & 7u) {
+        const uint32_t *s_hist = smem + p.hist;
+        for (int i = threadIdx.x; i < SH_WORDS; i += THREADS) {
+            uint32_t v = 0;
+            for (int w = 0; w < copies; ++w) v += s_hist[w * SH_WORDS + i];
+            if (v == 0u) continue;
+            int word;                                                                    // padded shared layout -> bmc_tallies words
+            if (i < SH_LEN) word = 4 + i;                                                // hcp[4][40]
+            else if (i < SH_SHAPE) {
+                const int j = i - SH_LEN, bin = j & 15;
+                if (bin >= BMC_LEN_BINS) continue;
+                word = 4 + 160 + (j >> 4) * BMC_LEN_BINS + bin;                          // len[4][4][14]
+            } else word = 4 + 160 + 224 + (i - SH_SHAPE);                                // shape[4][40]
+            atomicAdd(&a.tallies[word], (unsigned long long)v);
+        }
+    }
+    if (a.tally_mask & BMC_TALLY_SCORE)
+        for (int i = threadIdx.x; i < SCORE_WORDS; i += THREADS) {
+            const uint32_t v = smem[p.sc_hist + i];
+            if (v) atomicAdd(&a.tallies[TALLY_SCORE_WORD + i], (unsigned long long)v);
+        }
+}
+
+// accept-target jobs: a wave launched after the target was reached does nothing (and counts nothing).  The test
+// reads a snapshot taken between the waves -- not the live counter, which this very wave advances -- so every
+// block of a wave takes the same decision and the accepted set stays "whole waves until the target is met".
+__device__ __forceinline__ bool wave_cancelled(const SampleArgs &a)
+{
+    return a.target != 0ull && __ldg(a.snap) - a.start_acc >= a.target;
+}
+
+extern __shared__ __align__(16) uint32_t s_dyn[];
 
 template <bool HAS_CONS, bool FIXED>
 __device__ __forceinline__ void sample_body(const SampleArgs &a)
 {
-    __shared__ uint32_t s_hist[WARPS_PER_BLOCK][SH_WORDS];
-    __shared__ uint4 s_queue[HAS_CONS ? WARPS_PER_BLOCK : 1][QCAP];
-    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
-    __shared__ uint8_t s_shape[14 * 14 * 14];
-
+    if (wave_cancelled(a)) return;
+    const SmemPlan sp = smem_plan(false, HAS_CONS, false, (a.flags & ARGS_INTERP) != 0u, a.tally_mask);
+    uint32_t *smem = s_dyn;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < WARPS_PER_BLOCK * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
-    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
+    tally_init(a, sp, smem, FULL_HIST_COPIES);
     __syncthreads();
 
-    uint32_t *hist = s_hist[warp];
+    const TallyMem tm = tally_mem(sp, smem, warp);
+    uint4 *queue = reinterpret_cast<uint4 *>(smem + sp.q2) + warp * QCAP;
+    uint32_t *qoff = smem + sp.q1 + warp * QCAP;
+    uint32_t *feat = smem + sp.feat + warp * FEAT_SCRATCH_WORDS;
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
     uint32_t n_raw = 0, n_void = 0;           // per thread: at most `iters` each
@@ -187,28 +326,31 @@ __device__ __forceinline__ void sample_body(const SampleArgs &a)
             if (bal) {
                 if (ok) {
                     const unsigned pos = (q_tail + __popc(bal & ((1u << lane) - 1u))) % QCAP;
-                    s_queue[warp][pos] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+                    queue[pos] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+                    qoff[pos] = (uint32_t)off;
                 }
                 q_tail += __popc(bal);
                 __syncwarp();
                 if (q_tail - q_head >= 32u) {
-                    const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
+                    const uint4 r = queue[(q_head + lane) % QCAP];
+                    const uint32_t o = qoff[(q_head + lane) % QCAP];
                     q_head += 32u;
                     __syncwarp();
                     Planes p2 = {r.x, r.y, r.z, r.w};
-                    stage_b(a, p2, true, hist, s_shape, lane, s_feat[warp]);
+                    stage_b(a, p2, o, true, tm, lane, feat);
                 }
             }
         } else {
-            stage_b(a, pl, ok, hist, s_shape, lane, s_feat[warp]);
+            stage_b(a, pl, (uint32_t)off, ok, tm, lane, feat);
         }
     }
     if (HAS_CONS) {
         const unsigned left = q_tail - q_head;       // < 32
         if (left) {
-            const uint4 r = s_queue[warp][(q_head + lane) % QCAP];
+            const uint4 r = queue[(q_head + lane) % QCAP];
+            const uint32_t o = qoff[(q_head + lane) % QCAP];
             Planes p2 = {r.x, r.y, r.z, r.w};
-            stage_b(a, p2, lane < left, hist, s_shape, lane, s_feat[warp]);
+            stage_b(a, p2, o, lane < left, tm, lane, feat);
         }
     }
 
@@ -226,7 +368,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs &a)
         }
     }
     __syncthreads();
-    flush_hist(a, &s_hist[0][0]);
+    flush_hist(a, sp, smem, FULL_HIST_COPIES);
 }
 
 // ---------------------------------------------------------------------------
@@ -236,46 +378,51 @@ __device__ __forceinline__ void sample_body(const SampleArgs &a)
 #ifndef SF_MIN_BLOCKS
 #define SF_MIN_BLOCKS 6
 #endif
-constexpr int SF_HIST_COPIES = 2;
 #ifndef SF_CALLS
 #define SF_CALLS 4            /* Philox calls (four indices each) per lane and iteration of stage A1 */
 #endif
 constexpr int SF_QCAP1 = 128; // stage A1 -> A2 queue (32-bit entries); rounds that do not fit wait for a drain
 __constant__ LowTabs c_lowtabs = make_lowtabs();
-__constant__ uint32_t c_thresh39[10] = {thresh39(0), thresh39(1), thresh39(2), thresh39(3), thresh39(4),
-                                        thresh39(5), thresh39(6), thresh39(7), thresh39(8), thresh39(9)};
+
+// Stage B in two steps with a compaction between them, when there is something to gain:
+//   interpreted rule programs: B1 = the cheap range tests of every seat, B2 = the programs, on full warps of
+//                              deals that can still be accepted;
+//   compiled rule forms (NVRTC build): B1 = ranges and rules of the primary and the most selective other
+//                              seat (b1_mask, calibrated), B2 = the remaining seats.
+__host__ __device__ inline bool sf_two_stage(const ConsDev &c, bool jit)
+{
+    return jit ? (~c.b1_mask & 0xFu) != 0u : c.n_prog != 0u;
+}
 
 __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
 {
-    __shared__ uint32_t s_hist[SF_HIST_COPIES][SH_WORDS];   // stage B is rare here: few copies suffice
-    __shared__ uint32_t s_q1[WARPS_PER_BLOCK][SF_QCAP1];   // A1 survivors: index - a.first
-    __shared__ uint4 s_q2[WARPS_PER_BLOCK][QCAP];     // A2 survivors: (m0, m1, index - a.first, -)
-    __shared__ uint4 s_q3[WARPS_PER_BLOCK][QCAP];     // B1 survivors: complete deals (planes)
-    __shared__ uint32_t s_feat[WARPS_PER_BLOCK][FEAT_SCRATCH_WORDS];
-    __shared__ uint8_t s_shape[14 * 14 * 14];
-    __shared__ __align__(16) LowTabs s_low;
-
+    if (wave_cancelled(a)) return;
+#ifdef BMC_JIT
+    constexpr bool kJit = true;
+#else
+    constexpr bool kJit = false;
+#endif
+    const bool two_stage = sf_two_stage(a.cons, kJit);
+    const SmemPlan sp = smem_plan(true, true, two_stage, (a.flags & ARGS_INTERP) != 0u, a.tally_mask);
+    uint32_t *smem = s_dyn;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SF_HIST_COPIES * SH_WORDS; i += THREADS) (&s_hist[0][0])[i] = 0u;
-    for (int i = threadIdx.x; i < 14 * 14 * 14; i += THREADS) s_shape[i] = c_shape_lut[i];
+    tally_init(a, sp, smem, SF_HIST_COPIES);
     for (int i = threadIdx.x; i < (int)(sizeof(LowTabs) / 4); i += THREADS)
-        reinterpret_cast<uint32_t *>(&s_low)[i] = reinterpret_cast<const uint32_t *>(&c_lowtabs)[i];
+        smem[sp.low + i] = reinterpret_cast<const uint32_t *>(&c_lowtabs)[i];
     __syncthreads();
 
-    uint32_t *hist = s_hist[warp % SF_HIST_COPIES];
-    uint4 *q2 = s_q2[warp], *q3 = s_q3[warp];
+    const LowTabs &s_low = *reinterpret_cast<const LowTabs *>(smem + sp.low);
+    const TallyMem tm = tally_mem(sp, smem, warp % SF_HIST_COPIES);
+    uint32_t *q1 = smem + sp.q1 + warp * SF_QCAP1;                                  // A1 survivors: index - a.first
+    uint4 *q2 = reinterpret_cast<uint4 *>(smem + sp.q2) + warp * QCAP;              // A2 survivors: (m0, m1, index - a.first, -)
+    uint4 *q3 = reinterpret_cast<uint4 *>(smem + sp.q3) + warp * QCAP;              // B1 survivors: complete deals (planes)
+    uint32_t *q3i = smem + sp.q3i + warp * QCAP;                                    //               and their index - a.first
+    uint32_t *feat = smem + sp.feat + warp * FEAT_SCRATCH_WORDS;
     unsigned h3 = 0, t3 = 0;
-    // Stage B in two steps with a compaction between them, when there is something to gain:
-    //   interpreted rule programs: B1 = the cheap range tests of every seat, B2 = the programs, on full warps of
-    //                              deals that can still be accepted;
-    //   compiled rule forms (NVRTC build): B1 = ranges and rules of the primary and the most selective other
-    //                              seat (b1_mask, calibrated), B2 = the remaining seats.
 #ifdef BMC_JIT
     const uint32_t rest = ~a.cons.b1_mask & 0xFu;
-    const bool two_stage = rest != 0u;
     const uint32_t what1 = TEST_SEATS(a.cons.b1_mask) | TEST_RANGES | TEST_PROGS, what2 = TEST_SEATS(rest) | TEST_RANGES | TEST_PROGS;
 #else
-    const bool two_stage = a.cons.n_prog != 0u;
     const uint32_t what1 = TEST_SEATS(0xFu) | TEST_RANGES, what2 = TEST_SEATS(0xFu) | TEST_PROGS;
 #endif
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
@@ -297,46 +444,38 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         const bool voided = deal_rest39(a.key, a.sf_q0, r.x, r.y, xl, xh, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
         n_void += (active && voided) ? 1u : 0u;
         if (!two_stage) {
-            stage_b(a, pl, active && !voided, hist, s_shape, lane, s_feat[warp], TEST_ALL);
+            stage_b(a, pl, r.z, active && !voided, tm, lane, feat, TEST_ALL);
             return;
         }
-        const bool ok = seats_pass(a, pl, what1, s_feat[warp], lane) && active && !voided;
+        const bool ok = seats_pass(a, pl, what1, feat, lane) && active && !voided;
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
-            if (ok) q3[(t3 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+            if (ok) {
+                const unsigned pos = (t3 + __popc(bal & ((1u << lane) - 1u))) % QCAP;
+                q3[pos] = make_uint4(pl.lo0, pl.lo1, pl.hi0, pl.hi1);
+                q3i[pos] = r.z;
+            }
             t3 += __popc(bal);
             __syncwarp();
             if (t3 - h3 >= 32u) {
                 const uint4 r3 = q3[(h3 + lane) % QCAP];
+                const uint32_t o3 = q3i[(h3 + lane) % QCAP];
                 h3 += 32u;
                 __syncwarp();
                 const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-                stage_b(a, p3, true, hist, s_shape, lane, s_feat[warp], what2);
+                stage_b(a, p3, o3, true, tm, lane, feat, what2);
             }
         }
     };
     // ---- stage A2 on up to 32 queued survivors of the HCP test ----------------------------
     auto run_a2 = [&](unsigned count) {
-        const uint32_t off = s_q1[warp][(h1 + lane) % SF_QCAP1];      // index - a.first
+        const uint32_t off = q1[(h1 + lane) % SF_QCAP1];      // index - a.first
         h1 += count;
         __syncwarp();
         const bool active = lane < count;
         const unsigned long long idx = a.first + off;
-        uint32_t wh[4], wl[4];
-        philox4x32_10(a.key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK, wh);
-        philox4x32_10(a.key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK_LO, wl);
-        const uint32_t j = (uint32_t)idx & 3u;
-        const uint32_t u_hi = j < 2u ? (j == 0u ? wh[0] : wh[1]) : (j == 2u ? wh[2] : wh[3]);
-        const uint32_t u_lo = j < 2u ? (j == 0u ? wl[0] : wl[1]) : (j == 2u ? wl[2] : wl[3]);
-        unsigned long long d;
-        uint32_t magic, i, ell, m0, m1;
-        // lanes past the end of the queue look up u = 0: class 0, nothing to scan
-        const uint32_t info = sf_find_class(a.cons.sf_tab, a.cons.sf_bmul, active ? u_lo : 0u, active ? u_hi : 0u, d, magic);
-        sf_split(d, (info >> 12) & 0x7FFu, magic, i, ell);
-        const uint32_t H = sf_honours_of(info, i);
-        sf_unrank_lows(s_low, ell, 13u - (uint32_t)__popc(H), m0, m1);
-        m0 |= ((H & 0xFu) << 9) | ((H & 0xF0u) << 21);
-        m1 |= ((H & 0xF00u) << 1) | ((H & 0xF000u) << 13);
+        uint32_t m0, m1;
+        sf_primary_hand(a.key, a.cons.sf_tab, a.cons.sf_bmul, s_low, active ? idx : 0ull, active, m0, m1);
         const Feat f = hand_features(m0, m1);
         const bool ok = active && seat_ranges_ok(c, f);
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
@@ -411,7 +550,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
             if (mask != 0u) {
                 const uint32_t b = (uint32_t)__ffs((int)mask) - 1u;
                 mask &= mask - 1u;
-                s_q1[warp][(t1 + __popc(bal & lt)) % SF_QCAP1] = 4u * (co0 + (b >> 2) * stride) + (b & 3u) - mis;
+                q1[(t1 + __popc(bal & lt)) % SF_QCAP1] = 4u * (co0 + (b >> 2) * stride) + (b & 3u) - mis;
             }
             t1 += __popc(bal);
         }
@@ -431,8 +570,9 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     }
     if (t3 - h3) {
         const uint4 r3 = q3[(h3 + lane) % QCAP];
+        const uint32_t o3 = q3i[(h3 + lane) % QCAP];
         const Planes p3 = {r3.x, r3.y, r3.z, r3.w};
-        stage_b(a, p3, lane < t3 - h3, hist, s_shape, lane, s_feat[warp], what2);
+        stage_b(a, p3, o3, lane < t3 - h3, tm, lane, feat, what2);
     }
 
     {
@@ -443,7 +583,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.tallies[0], a.n);   // the grid covers exactly [first, first + n)
     }
     __syncthreads();
-    flush_hist(a, &s_hist[0][0], SF_HIST_COPIES);
+    flush_hist(a, sp, smem, SF_HIST_COPIES);
 }
 
 

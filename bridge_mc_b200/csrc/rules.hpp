@@ -145,23 +145,23 @@ public:
     void compile(const Sx &form, std::vector<uint32_t> &code, SeatRanges *ranges = nullptr, bool *exact = nullptr)
     {
         size_t start = code.size();
-        try {
-            expr(form, code);
-        } catch (const IllegalCall &) {          // the whole form is an illegal call: always an error
-            code.resize(start);
-            code.push_back(enc(OP_TRUE));
-            code.push_back(enc(OP_ERRIF_T));
-        }
+        expr(form, code);
         code.push_back(enc(OP_END));
-        // boolean stack lives in one 32-bit register
+        // A program that can raise the error evaluates with Lisp's short-circuit order made explicit: the
+        // three-valued and / or / not (bytecode.h), so that an illegal form only counts where it is reached.
+        bool has_err = false;
+        for (size_t i = start; i < code.size(); ++i) has_err = has_err || (code[i] & 15u) == OP_ERR;
+        // boolean stack lives in one 32-bit register, two bits per slot
         int depth = 0, maxd = 0;
         for (size_t i = start; i < code.size(); ++i) {
             uint32_t op = code[i] & 15u;
-            if (op == OP_CMPC || op == OP_CMPF || op == OP_TRUE || op == OP_FALSE) ++depth;
+            if (has_err && (op == OP_AND || op == OP_OR || op == OP_NOT))
+                code[i] = (code[i] & ~15u) | (op == OP_AND ? OP_AND3 : op == OP_OR ? OP_OR3 : OP_NOT3);
+            if (op == OP_CMPC || op == OP_CMPF || op == OP_TRUE || op == OP_FALSE || op == OP_ERR) ++depth;
             else if (op == OP_AND || op == OP_OR) --depth;
             if (depth > maxd) maxd = depth;
         }
-        if (maxd > 30) throw RuleError("rule nests too deeply (boolean stack > 30)");
+        if (maxd > 15) throw RuleError("rule nests too deeply (boolean stack > 15)");
         if (ranges) {
             bool ex = true;
             absorb(form, *ranges, ex);
@@ -303,25 +303,18 @@ private:
         case Sx::LIST: break;
         }
         const Sx &h = x.items[0];
-        if (h.kind != Sx::SYM) throw IllegalCall{show(x)};
+        // A list whose head is not a symbol (the un-spliced rule list of bidding.cl:249) is an "illegal
+        // function call" -- but only if evaluation reaches it: it compiles to the ERROR value, which joins
+        // the chain like any other operand; the three-valued and / or / not (bytecode.h) let it surface
+        // exactly where Lisp's short-circuit order would evaluate it.
+        if (h.kind != Sx::SYM) { code.push_back(enc(OP_ERR)); return; }
         const std::string &op = h.sym;
         size_t n = x.items.size() - 1;
         if (op == "AND" || op == "OR") {
             bool is_and = op == "AND";
             if (n == 0) { code.push_back(enc(is_and ? OP_TRUE : OP_FALSE)); return; }
             for (size_t i = 1; i <= n; ++i) {
-                const size_t mark = code.size();
-                try {
-                    expr(x.items[i], code);
-                } catch (const IllegalCall &) {
-                    code.resize(mark);
-                    // The reference only signals "illegal function call" if evaluation
-                    // reaches this conjunct (and/or short-circuit): error iff the
-                    // prefix is true (and) / false (or).
-                    if (i == 1) throw;
-                    code.push_back(enc(is_and ? OP_ERRIF_T : OP_ERRIF_F));
-                    continue;
-                }
+                expr(x.items[i], code);
                 if (i > 1) code.push_back(enc(is_and ? OP_AND : OP_OR));
             }
             return;
@@ -381,7 +374,6 @@ private:
             code.push_back(enc(OP_OR));
         }
     }
-    struct IllegalCall { std::string what; };
 
     // ---- range absorption over top-level conjuncts -----------------------------
     void tighten(SeatRanges &r, int f, Cmp c, long k)

@@ -199,6 +199,28 @@ __host__ __device__ __forceinline__ void sf_unrank_lows(const LowTabs &T, uint32
     m1 = sub[2] | (sub[3] << 16);
 }
 
+// The primary seat's hand behind index `idx` (stage A2; also bmc_expand): u from the two Philox calls, its
+// count class, the identity of the honours, the low cards.  Lanes with active = false look up u = 0
+// (class 0, nothing to scan) and return that hand.
+__device__ __forceinline__ void sf_primary_hand(const PhiloxKey &key, const uint4 *__restrict__ tab, uint32_t bmul, const LowTabs &T,
+                                                unsigned long long idx, bool active, uint32_t &m0, uint32_t &m1)
+{
+    uint32_t wh[4], wl[4];
+    philox4x32_10(key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK, wh);
+    philox4x32_10(key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK_LO, wl);
+    const uint32_t j = (uint32_t)idx & 3u;
+    const uint32_t u_hi = j < 2u ? (j == 0u ? wh[0] : wh[1]) : (j == 2u ? wh[2] : wh[3]);
+    const uint32_t u_lo = j < 2u ? (j == 0u ? wl[0] : wl[1]) : (j == 2u ? wl[2] : wl[3]);
+    unsigned long long d;
+    uint32_t magic, i, ell;
+    const uint32_t info = sf_find_class(tab, bmul, active ? u_lo : 0u, active ? u_hi : 0u, d, magic);
+    sf_split(d, (info >> 12) & 0x7FFu, magic, i, ell);
+    const uint32_t H = sf_honours_of(info, i);
+    sf_unrank_lows(T, ell, 13u - (uint32_t)__popc(H), m0, m1);
+    m0 |= ((H & 0xFu) << 9) | ((H & 0xF0u) << 21);
+    m1 |= ((H & 0xF00u) << 1) | ((H & 0xF000u) << 13);
+}
+
 // Lemire thresholds of deal_fixed's words for 39 free cards (4 digits per word)
 __host__ __device__ constexpr uint32_t thresh39(int w)
 {

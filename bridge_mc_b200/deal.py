@@ -87,6 +87,7 @@ class Deal:
         self.max_raw = max_raw
         self._next_index = 0
         self._buffer = []
+        self._carry = None
         self._cons = None
 
     @staticmethod
@@ -124,25 +125,44 @@ class Deal:
                     self._cons.set_reference_order(n_defs)
         return self._cons
 
+    def _shuffled(self, rec: np.ndarray, first_index: int) -> np.ndarray:
+        """The accepted SET of a library call is fixed by (seed, index range); the order in which the kernel stored it is
+        not.  Sorting makes the batch reproducible, and a permutation that depends on (seed, first_index) only -- never on
+        the cards -- makes every prefix of it an unbiased sample, so callers may take fewer deals than a call produced."""
+        rec = rec[np.lexsort((rec[:, 0], rec[:, 1]))]
+        rng = np.random.default_rng([self.seed & 0xFFFFFFFFFFFFFFFF, first_index & 0xFFFFFFFFFFFFFFFF])
+        return rec[rng.permutation(rec.shape[0])]
+
     def build_records(self, n: int) -> np.ndarray:
-        """n accepted deals as uint64[n,2] records (seat k = k-th of const, `:~`, random)."""
+        """n accepted deals as uint64[n,2] records (seat k = k-th of const, `:~`, random).  Deals a library call produced
+        beyond `n` are kept for the next call (the kernels run whole waves)."""
         cons = self.constraints()
         out = []
         have = 0
+        if self._carry is not None and self._carry.shape[0]:
+            take = self._carry[:n]
+            self._carry = self._carry[take.shape[0]:]
+            out.append(take)
+            have = take.shape[0]
+        every_index_deals = self.semantics == "reference" and cons.mode in (0, 3)
         wave = 1 << 14
-        if self.semantics == "reference" and cons.mode in (0, 3):
-            wave = max(256, 1 << (max(n, 1) - 1).bit_length())      # every index yields a deal: no need to overdraw
         spent = 0
         while have < n:
-            budget = max(wave, min(self.max_raw - spent, wave * 256))          # bounded work per library call
-            rec, tal, st = self.engine.sample(cons, n_accept=n - have, n_raw=budget, seed=self.seed,
-                                              first_index=self._next_index, wave=wave, tally_mask=0, cap=(n - have) + wave)
+            first = self._next_index
+            if every_index_deals:
+                # reference order: one deal per index (unless the reference would signal an error for it) -- ask for
+                # exactly the missing ones, nothing is overdrawn
+                need = n - have
+                rec, tal, st = self.engine.sample(cons, n_raw=need, seed=self.seed, first_index=first, tally_mask=0, cap=need)
+            else:
+                budget = max(wave, min(self.max_raw - spent, wave * 256))          # bounded work per library call
+                rec, tal, st = self.engine.sample(cons, n_accept=n - have, n_raw=budget, seed=self.seed, first_index=first,
+                                                  wave=wave, tally_mask=0, cap=(n - have) + wave)
             used = int(st.raw)
             self._next_index += used
             spent += used
             if rec.shape[0]:
-                # the accepted set of a call is fixed; its order is not: sort for reproducibility
-                rec = rec[np.lexsort((rec[:, 0], rec[:, 1]))]
+                rec = self._shuffled(rec, first)
                 out.append(rec)
                 have += rec.shape[0]
             elif cons.mode == 3 and st.voided == st.raw:
@@ -150,11 +170,11 @@ class Deal:
                 raise BadRangeError("Can't infer correct limit!", None, None)      # every build signals bad-range
             elif spent >= self.max_raw:
                 raise NoDealFound(f"no deal satisfies {self!r} within {spent} raw deals")
-            if st.accepted * 64 < used and wave < (1 << 30):
+            if not every_index_deals and st.accepted * 64 < used and wave < (1 << 30):
                 wave <<= 2                                   # rare constraint: take bigger bites
         rec = np.concatenate(out) if out else np.empty((0, 2), np.uint64)
         if rec.shape[0] > n:
-            self._buffer_extra = rec[n:]
+            self._carry = rec[n:]
         return rec[:n]
 
     def build(self):

@@ -82,9 +82,22 @@ class Constraints:
         check(_lib.load().bmc_constraints_set_reference_order(self._h, n_defs))
         return self
 
-    def set_jit(self, on: bool = True):
-        """bmc_constraints_set_jit: compile the rule forms into the kernel with NVRTC instead of interpreting them."""
-        check(_lib.load().bmc_constraints_set_jit(self._h, 1 if on else 0))
+    def set_jit(self, on=True):
+        """bmc_constraints_set_jit: True / 1 compile the rule forms into the kernel with NVRTC, False / 0 always interpret
+        them, 2 (the library's default) switch by itself after a second of interpreted kernel time."""
+        check(_lib.load().bmc_constraints_set_jit(self._h, int(on)))
+        return self
+
+    def set_scoring(self, contracts, vulnerable, pairs=()):
+        """bmc_constraints_set_scoring: the contracts (Contract structs) and IMP pairs [(a, b), ...] that TALLY_SCORE
+        tallies over the accepted deals."""
+        nc = len(contracts)
+        carr = (Contract * max(nc, 1))(*contracts)
+        vul = np.ascontiguousarray(vulnerable, dtype=np.uint8)
+        pr = np.ascontiguousarray(pairs, dtype=np.uint8).reshape(-1)
+        check(_lib.load().bmc_constraints_set_scoring(self._h, carr, vul.ctypes.data if nc else None, nc,
+                                                      pr.ctypes.data if pr.size else None, pr.size // 2))
+        self.n_contracts, self.n_pairs = nc, pr.size // 2
         return self
 
     @property
@@ -140,6 +153,9 @@ def tallies_to_dict(t: Tallies) -> dict:
         "hcp": np.ctypeslib.as_array(t.hcp).astype(np.int64)[:, :38].copy(),
         "len": np.ctypeslib.as_array(t.len).astype(np.int64).copy(),
         "shape": np.ctypeslib.as_array(t.shape).astype(np.int64)[:, :39].copy(),
+        "tricks": np.ctypeslib.as_array(t.tricks).astype(np.int64).copy(),
+        "imps": np.ctypeslib.as_array(t.imps).astype(np.int64).copy(),
+        "imp_dropped": np.ctypeslib.as_array(t.imp_dropped).astype(np.int64).copy(),
     }
 
 
@@ -148,6 +164,20 @@ def tallies_from_words(words: np.ndarray) -> dict:
     w = np.ascontiguousarray(words, dtype=np.uint64)
     t = Tallies.from_buffer_copy(w.tobytes())
     return tallies_to_dict(t)
+
+
+def sample_multi(devices, cons: Constraints | None = None, *, n_raw: int = 0, n_accept: int = 0, seed: int = DEFAULT_SEED,
+                 first_index: int = 0, wave: int = 0, tally_mask: int = TALLY_ALL, cap: int = 0):
+    """bmc_sample_multi: one call over several GPUs of the box (contiguous index shares, tallies summed in the library).
+    Returns (records uint64[stored,2], tallies dict, Stats)."""
+    L = _lib.load()
+    devs = (C.c_int * len(devices))(*devices)
+    records = np.empty((cap, 2), dtype=np.uint64) if cap else None
+    t, st = Tallies(), Stats()
+    check(L.bmc_sample_multi(devs, len(devices), cons._h if cons else None, seed, first_index, n_raw, n_accept, wave, tally_mask,
+                             records.ctypes.data if cap else None, cap, C.byref(t), C.byref(st)))
+    out = records[:st.stored] if cap else np.empty((0, 2), dtype=np.uint64)
+    return out, tallies_to_dict(t), st
 
 
 class Engine:
@@ -204,6 +234,41 @@ class Engine:
                                      tally_mask, records_ptr or None, cap, tallies_ptr, C.byref(st)))
         return st
 
+    def sample_indices(self, cons: Constraints | None = None, *, n_raw: int = 0, n_accept: int = 0, seed: int = DEFAULT_SEED,
+                       first_index: int = 0, wave: int = 0, tally_mask: int = TALLY_ALL, cap: int | None = None,
+                       offsets: np.ndarray | None = None):
+        """bmc_sample_indices: like sample(), but every accepted deal comes back as the 32-bit offset of its index from
+        first_index (uint32[stored]); expand() regenerates the records."""
+        if cap is None:
+            cap = n_accept + (n_accept // 8) + 4096 if n_accept else n_raw
+        if offsets is None and cap:
+            offsets = np.empty(cap, dtype=np.uint32)
+        t, st = Tallies(), Stats()
+        check(self._L.bmc_sample_indices(self._h, cons._h if cons else None, seed, first_index, n_raw, n_accept, wave,
+                                         tally_mask, offsets.ctypes.data if cap else None, cap, C.byref(t), C.byref(st)))
+        out = offsets[:st.stored] if cap else np.empty(0, dtype=np.uint32)
+        return out, tallies_to_dict(t), st
+
+    def sample_indices_dev(self, cons: Constraints | None, offsets_ptr: int, cap: int, tallies_ptr: int, *, n_raw: int = 0,
+                           n_accept: int = 0, seed: int = DEFAULT_SEED, first_index: int = 0, wave: int = 0,
+                           tally_mask: int = TALLY_ALL) -> Stats:
+        st = Stats()
+        check(self._L.bmc_sample_indices_dev(self._h, cons._h if cons else None, seed, first_index, n_raw, n_accept, wave,
+                                             tally_mask, offsets_ptr or None, cap, tallies_ptr, C.byref(st)))
+        return st
+
+    def expand(self, cons: Constraints | None, offsets: np.ndarray, *, seed: int = DEFAULT_SEED, first_index: int = 0) -> np.ndarray:
+        """bmc_expand: index offsets -> records uint64[n,2]."""
+        off = np.ascontiguousarray(offsets, dtype=np.uint32).reshape(-1)
+        out = np.empty((off.size, 2), dtype=np.uint64)
+        check(self._L.bmc_expand(self._h, cons._h if cons else None, seed, first_index, off.ctypes.data if off.size else None,
+                                 off.size, out.ctypes.data if off.size else None))
+        return out
+
+    def expand_dev(self, cons: Constraints | None, offsets_ptr: int, n: int, records_ptr: int, *, seed: int = DEFAULT_SEED,
+                   first_index: int = 0):
+        check(self._L.bmc_expand_dev(self._h, cons._h if cons else None, seed, first_index, offsets_ptr, n, records_ptr))
+
     def set_stream(self, cuda_stream: int):
         check(self._L.bmc_set_stream(self._h, cuda_stream or None))
 
@@ -248,9 +313,11 @@ class Engine:
         npairs = pr.size // 2
         th = np.zeros((nc, 14), dtype=np.uint64)
         ih = np.zeros((max(npairs, 1), 49), dtype=np.uint64)
+        dropped = np.zeros(max(npairs, 1), dtype=np.uint64)
         tab = np.zeros((nc, 14), dtype=np.int32)
         check(self._L.bmc_score_tally(self._h, carr, vul.ctypes.data, nc, pr.ctypes.data if npairs else None, npairs,
-                                      seed, first_index, n, th.ctypes.data, ih.ctypes.data, tab.ctypes.data))
+                                      seed, first_index, n, th.ctypes.data, ih.ctypes.data, dropped.ctypes.data, tab.ctypes.data))
+        self.last_imp_dropped = dropped[:npairs]
         return th, ih[:npairs], tab
 
     # ---- hist-base on the device -----------------------------------------------------

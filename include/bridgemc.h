@@ -18,9 +18,9 @@
  *  - re-entrant: a bmc_ctx owns one CUDA stream; use one ctx per calling
  *    thread (hunchentoot workers, dealgen<..>/sim{..} threads -- rest.cl:403,
  *    bridge.cl:3100,3115) or serialise calls on a shared one.  A
- *    bmc_constraints / bmc_scheme may be shared by the contexts of ONE device
- *    (its device-side tables are uploaded once, under a lock); with several
- *    devices in one process create one per device.
+ *    bmc_constraints / bmc_scheme may be shared by any number of contexts, on
+ *    one device or several: its device-side tables are uploaded once per
+ *    device, under a lock.
  *
  * Encoding (bridge.cl:519-547): suit c=0 d=1 h=2 s=3, rank 0..12 = 2..A.
  * Seats 0..3 = N E S W.  A 64-bit "lane mask" holds one 16-bit lane per suit,
@@ -84,6 +84,8 @@ typedef struct { bmc_seat_features seat[4]; } bmc_features;
 #define BMC_HCP_BINS   40      /* 0..37 used */
 #define BMC_LEN_BINS   14
 #define BMC_SHAPE_BINS 40      /* 39 sorted shapes, see bmc_shape_table */
+#define BMC_SCORE_CONTRACTS 8  /* contracts / IMP pairs of the fused compscore tally (bmc_constraints_set_scoring) */
+#define BMC_SCORE_PAIRS     8
 typedef struct {
     uint64_t raw;              /* deal indices drawn */
     uint64_t voided;           /* indices discarded by the exact-uniformity (Lemire) check */
@@ -92,6 +94,10 @@ typedef struct {
     uint64_t hcp[4][BMC_HCP_BINS];
     uint64_t len[4][4][BMC_LEN_BINS];     /* [seat][suit][length] */
     uint64_t shape[4][BMC_SHAPE_BINS];    /* [seat][sorted-shape class] */
+    /* BMC_TALLY_SCORE: compscore.cl tallies over the ACCEPTED deals (base-score, match-points; compscore.cl:94-131) */
+    uint64_t tricks[BMC_SCORE_CONTRACTS][14];   /* [contract][tricks] */
+    uint64_t imps[BMC_SCORE_PAIRS][49];         /* [pair][24 + match-points(a, b)] */
+    uint64_t imp_dropped[BMC_SCORE_PAIRS];      /* |score difference| >= 4000: match-points signals an error there */
 } bmc_tallies;
 #define BMC_TALLY_WORDS (sizeof(bmc_tallies) / sizeof(uint64_t))
 
@@ -99,6 +105,7 @@ typedef struct {
 #define BMC_TALLY_LEN   2u
 #define BMC_TALLY_SHAPE 4u
 #define BMC_TALLY_ALL   7u
+#define BMC_TALLY_SCORE 8u     /* score the accepted deals against the contracts attached to the constraint */
 
 typedef struct {
     uint64_t raw, voided, accepted, stored;
@@ -106,6 +113,7 @@ typedef struct {
     float    kernel_ms;        /* CUDA-event time of the sampling kernels */
     float    total_ms;         /* wall time of the call */
 } bmc_stats;
+
 
 /* compscore.cl:38-65 class `contract` after parsing (the string parser stays on
  * the Lisp side).  suit 0 c 1 d 2 h 3 s 4 NT; declarer 0 N 1 E 2 S 3 W, -1 none;
@@ -165,11 +173,22 @@ int  bmc_constraints_set_reference_order(bmc_constraints *c, int n_defs);
  * are translated to C++, spliced into the same kernel source and compiled for sm_100a with NVRTC
  * (about a second or two, once per constraint and dealing mode) -- the way the reference `eval`s its
  * rule forms.  Results are bit-identical; worthwhile for long or repeated jobs on rule-heavy
- * constraints.  BMC_E_CUDA if libnvrtc cannot be loaded.  bmc_constraints_jit_ms: compile time spent. */
+ * constraints.  BMC_E_CUDA if libnvrtc cannot be loaded.  bmc_constraints_jit_ms: compile time spent.
+ * on = 2 (the default): interpret, and switch to the compiled kernel by itself once the constraint has spent more
+ * than a second of kernel time on interpreted rules (about what the build costs). */
 int  bmc_constraints_set_jit(bmc_constraints *c, int on);
 float bmc_constraints_jit_ms(const bmc_constraints *c);
 int  bmc_constraints_mode(const bmc_constraints *c);
 int  bmc_constraints_primary(const bmc_constraints *c);
+/* Attaches the contracts to score to a constraint: with BMC_TALLY_SCORE in tally_mask the sampling kernels tally, for
+ * every ACCEPTED deal, tricks[c][t] and imps[p][24 + match-points(contracts[pairs[2p]], contracts[pairs[2p+1]])] in the
+ * launch that draws the deal -- `msr-<contract>` measures + base-score + histogram of rest.cl:287-303 / compscore.cl in
+ * one pass ("compscore tallies over constrained samples").  The trick column comes from a stand-in for the reference's
+ * play-deal estimator (not part of this library): eight exactly uniform values 0..13 that are a function of the deal
+ * alone (Philox keyed by seed, counter = the deal's record), so tallies do not depend on the dealing mode, the index
+ * behind a deal or the split over devices.  n_contracts <= 8, n_pairs <= 8; vulnerable[c] != 0 => :vulnerable t. */
+int  bmc_constraints_set_scoring(bmc_constraints *c, const bmc_contract *contracts, const uint8_t *vulnerable,
+                                 uint32_t n_contracts, const uint8_t *pairs, uint32_t n_pairs);
 int  bmc_constraints_primary_hcp(const bmc_constraints *c, int32_t *lo, int32_t *hi);
 
 /* A rule table as printed by Lisp: "(((2 C) . FORM) ((2 NT) . FORM) ...)" --
@@ -187,9 +206,12 @@ void bmc_scheme_destroy(bmc_scheme *s);
  *   n_accept_target  > 0: whole waves of `wave` indices (0 = default 2^26)
  *       starting at first_index until accepted >= target or n_raw indices
  *       (0 = no limit) are used; the accepted SET depends only on
- *       (seed, first_index, wave, target).  Watchdog of the unlimited form: the
- *       call returns (BMC_OK, fewer than target accepted) after 2^36 indices
- *       without a single accepted deal, or 2^44 indices in all.
+ *       (seed, first_index, wave, target); stats->raw tells how many indices were
+ *       used (the next job continues at first_index + raw).  The waves are enqueued
+ *       back to back -- one that starts after the target was met cancels itself on the
+ *       device -- so the host synchronises a few times per job, not once per wave.
+ *       Watchdog of the unlimited form: the call returns (BMC_OK, fewer than target
+ *       accepted) after 2^36 indices without a single accepted deal, or 2^44 in all.
  * records may be NULL (tally only); at most `cap` records are stored.
  * Host-buffer form (what the Lisp shim calls): */
 int bmc_sample(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
@@ -201,6 +223,35 @@ int bmc_sample(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_
 int bmc_sample_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
                    uint64_t n_raw, uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask,
                    void *records_dev, uint64_t cap, void *tallies_dev, bmc_stats *stats);
+
+/* Index records: the deal behind an index is a pure function of (seed, index, constraint, dealing mode), so an
+ * accepted deal can leave the device as the 32-bit OFFSET of its index from first_index -- 4 bytes instead of 16 -- and
+ * be regenerated where and when the hands are needed.  Same arguments and semantics as bmc_sample / bmc_sample_dev
+ * with offsets[] in place of records[]; a call spans at most 2^32 indices (n_raw = 0 means 2^32).  offsets are in
+ * no particular order (like records). */
+int bmc_sample_indices(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
+                       uint64_t n_raw, uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask,
+                       uint32_t *offsets, uint64_t cap, bmc_tallies *tallies, bmc_stats *stats);
+int bmc_sample_indices_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
+                           uint64_t n_raw, uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask,
+                           void *offsets_dev, uint64_t cap, void *tallies_dev, bmc_stats *stats);
+/* records[i] = the deal behind index first_index + offsets[i]; (cons, seed, first_index) as given to the sampling call
+ * (and the same dealing mode: bmc_constraints_mode).  Any offset may be expanded, accepted or not. */
+int bmc_expand(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
+               const uint32_t *offsets, uint64_t n, bmc_record *records);
+int bmc_expand_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
+                   const void *offsets_dev, uint64_t n, void *records_dev);
+
+/* One call, several GPUs of the box: devices[0..n_devices) each get a contiguous share of
+ * [first_index, first_index + n_raw), one host thread and one internal context per device; the only exchange is the
+ * sum of the tally buffers (device 0 reads its peers' buffers over NVLink when peer access is available, else the
+ * host adds them).  Tallies and the accepted set are IDENTICAL for every number of devices.  records (host, may be
+ * NULL): the devices' accepted deals, device after device; at most cap / n_devices per device.  With
+ * n_accept_target > 0 every device instead runs whole waves of its own range first_index + g * 2^40 ... until it
+ * holds ceil(target / n_devices) deals (that result depends on n_devices).  stats->kernel_ms: the slowest device. */
+int bmc_sample_multi(const int *devices, int n_devices, const bmc_constraints *cons, uint64_t seed,
+                     uint64_t first_index, uint64_t n_raw, uint64_t n_accept_target, uint64_t wave,
+                     uint32_t tally_mask, bmc_record *records, uint64_t cap, bmc_tallies *tallies, bmc_stats *stats);
 
 /* ---- filter / features on given deals: assess-hand, balanced?, test-bid,
  * choose-bid (bidding.cl:33-46,111-112,146-150) over a deal set ---------------- */
@@ -220,17 +271,18 @@ int bmc_score(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulner
  * where |diff| >= 4000 (the reference errors there), imps[i] = 0. */
 int bmc_match_points(bmc_ctx *ctx, const int32_t *a, const int32_t *b, uint64_t n,
                      int8_t *imps, uint8_t *status);
-/* Fused drill tally (config "compscore tallies over constrained samples"):
- * for deal i in [0,n) and contract c, tricks = Philox(seed, stream 1, index
- * first_index+i, word c) uniform on 0..13 (the reference's trick source,
- * play-deal, is out of scope); tricks_hist[c][t] += 1; for every pair p,
- * imp_hist[p][24 + match-points(contracts[pairs[2p]], contracts[pairs[2p+1]])] += 1.
- * score_table[c][t] = base-score (output, may be NULL).  n_contracts <= 8, n_pairs <= 8. */
+/* Drill tally over an index range without dealing (the scoring arithmetic alone; the tally over CONSTRAINED samples
+ * is BMC_TALLY_SCORE of the sampling calls): for index i in [first_index, first_index + n) and contract c, tricks =
+ * the stand-in trick source keyed by (seed, i) -- eight exactly uniform values 0..13 (mixed-radix digits of one
+ * Philox word, Lemire rejection); tricks_hist[c][t] += 1; for every pair p, imp_hist[p][24 + match-points(
+ * contracts[pairs[2p]], contracts[pairs[2p+1]])] += 1, or imp_dropped[p] += 1 where |difference| >= 4000 (the
+ * reference signals an error there).  score_table[c][t] = base-score (output).  imp_dropped and score_table may be
+ * NULL.  n_contracts <= 8, n_pairs <= 8. */
 int bmc_score_tally(bmc_ctx *ctx, const bmc_contract *contracts, const uint8_t *vulnerable,
                     uint32_t n_contracts, const uint8_t *pairs, uint32_t n_pairs,
                     uint64_t seed, uint64_t first_index, uint64_t n,
                     uint64_t *tricks_hist /*[n_contracts][14]*/, uint64_t *imp_hist /*[n_pairs][49]*/,
-                    int32_t *score_table /*[n_contracts][14]*/);
+                    uint64_t *imp_dropped /*[n_pairs]*/, int32_t *score_table /*[n_contracts][14]*/);
 
 /* ---- hist-base over measure tuples (bridge.cl:1325-1330; feeds hist-breakdown / hist-percent) ---- */
 /* A measure yields one byte per deal; seat 0..3 = N E S W ("seat and its partner" for the pair measures).

@@ -370,15 +370,18 @@ static uint64_t pattern_weight(const orc_distgen *g, unsigned pat,
     uint64_t total = 0;
     for (int a = lo[0]; a <= hi[0]; ++a)
         for (int b = lo[1]; b <= hi[1]; ++b)
-            for (int c = lo[2]; c <= hi[2]; ++c)
-                for (int d = lo[3]; d <= hi[3]; ++d) {
-                    if (a + b + c + d != need) continue;
+            for (int c = lo[2]; c <= hi[2]; ++c) {
+                /* list-prod + filter on the sum (bridge.cl:1002-1004): per (a b c) at most one d qualifies */
+                const int d = need - a - b - c;
+                if (d < lo[3] || d > hi[3]) continue;
+                {
                     uint64_t w = orc_combinations(g->lc_supply[0], a) * orc_combinations(g->lc_supply[1], b)
                                * orc_combinations(g->lc_supply[2], c) * orc_combinations(g->lc_supply[3], d);
                     if (lc_out) { lc_out[n][0] = a; lc_out[n][1] = b; lc_out[n][2] = c; lc_out[n][3] = d; w_out[n] = w; }
                     ++n;
                     total += w;
                 }
+            }
     if (n_out) *n_out = n;
     return total;
 }
@@ -913,4 +916,311 @@ ORC_API void orc_gpu_deal_fixed_batch(uint64_t seed, uint64_t first, uint64_t n,
 {
     for (uint64_t i = 0; i < n; ++i)
         voided[i] = (uint8_t)orc_gpu_deal_fixed(seed, first + i, fixed, &rec[2 * i], &rec[2 * i + 1]);
+}
+
+/* ------------------------------------------------------------------ */
+/* Stand-in trick source + compscore tallies (mirror of csrc/score.cuh) */
+/* ------------------------------------------------------------------ */
+/* Eight exactly uniform trick counts 0..13 from the Philox stream (c0, c1, c2 + block, c3): the mixed-radix
+ * digits (multiply-shift by 14) of the first word whose final remainder passes Lemire's test
+ * (>= 2^32 mod 14^8 = 1 343 389 184); at most 16 blocks. */
+ORC_API void orc_tricks_of(const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t t[8])
+{
+    for (uint32_t b = 0;; ++b) {
+        uint32_t ctr[4] = { c0, c1, c2 + b, c3 }, w[4];
+        orc_philox4x32_10(ctr, key, w);
+        for (int j = 0; j < 4; ++j) {
+            uint32_t x = w[j], d[8];
+            for (int k = 0; k < 8; ++k) { uint64_t p = (uint64_t)x * 14u; d[k] = (uint32_t)(p >> 32); x = (uint32_t)p; }
+            if (x >= 1343389184u || (b == 15 && j == 3)) { memcpy(t, d, sizeof d); return; }
+        }
+    }
+}
+
+typedef struct { int8_t level, suit, declarer, dbl; } orc_contract;
+
+/* hist: tricks[8][14] | imps[8][49] | dropped[8] (u64), ACCUMULATED.  base-score per compscore.cl:94-100,
+ * match-points per compscore.cl:123-131 (|diff| >= 4000 -> dropped). */
+static void score_tally_one(const orc_contract *c, const uint8_t *vul, int nc, const uint8_t *pairs, int np,
+                            const uint32_t tr[8], uint64_t *hist)
+{
+    for (int k = 0; k < nc; ++k) hist[k * 14 + tr[k]]++;
+    for (int p = 0; p < np; ++p) {
+        int a = pairs[2 * p], b = pairs[2 * p + 1], im;
+        int sa = orc_base_score(c[a].level, c[a].suit, c[a].declarer, c[a].dbl, (int)tr[a], vul[a]);
+        int sb = orc_base_score(c[b].level, c[b].suit, c[b].declarer, c[b].dbl, (int)tr[b], vul[b]);
+        if (orc_imps(sa - sb, &im) == 0) hist[8 * 14 + p * 49 + 24 + im]++;
+        else hist[8 * 14 + 8 * 49 + p]++;
+    }
+}
+/* deal-keyed form (BMC_TALLY_SCORE of the sampling kernels): counter = the record, key = seed ^ "tricks" */
+ORC_API void orc_score_tally_records(uint64_t seed, const uint64_t *rec, uint64_t n, const orc_contract *c, const uint8_t *vul,
+                                     int nc, const uint8_t *pairs, int np, uint64_t *hist)
+{
+    seed ^= 0x0000747269636B73ull;
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t tr[8];
+        orc_tricks_of(key, (uint32_t)rec[2 * i], (uint32_t)(rec[2 * i] >> 32), (uint32_t)rec[2 * i + 1], (uint32_t)(rec[2 * i + 1] >> 32), tr);
+        score_tally_one(c, vul, nc, pairs, np, tr, hist);
+    }
+}
+/* index-keyed form (bmc_score_tally): counter = (index_lo, index_hi, block, 1), key = seed */
+ORC_API void orc_score_tally_index(uint64_t seed, uint64_t first, uint64_t n, const orc_contract *c, const uint8_t *vul,
+                                   int nc, const uint8_t *pairs, int np, uint64_t *hist)
+{
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t tr[8];
+        orc_tricks_of(key, (uint32_t)(first + i), (uint32_t)((first + i) >> 32), 0u, 1u, tr);
+        score_tally_one(c, vul, nc, pairs, np, tr, hist);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* infer-* (bridge.cl:1085-1269) and `build` with any number of ranged */
+/* seats (bridge.cl:1292-1319), self-contained                         */
+/* ------------------------------------------------------------------ */
+/* A range def as `build` sees it after rest.cl's normdef (numbers are (n n) lists): -1 = nil. */
+typedef struct {
+    int has_hcp, hcp_lo, hcp_hi;                 /* :hcp (lo hi) */
+    int has_suit[4], len_lo[4], len_hi[4];       /* :c :d :h :s (lo hi [third]) */
+    int has_third[4], th_lo[4], th_hi[4];        /* third element: per-suit HCP range (lo hi) */
+} orc_def;
+
+#define NILV (-1)
+/* bridge.cl:1101-1104 -? with nil = NILV on the right-hand side only (the accumulator is always a number here) */
+static int minus_q(int a, int b) { return b == NILV ? a : a - b; }
+
+/* hcp spec of one other def for the folds: present?, (first, second) */
+typedef struct { int present, lo, hi; } hcp_ref;
+
+/* bridge.cl:1126-1153 infer-hcp-range over `nsuit` supply rows.  base: present?, lo, hi.  Returns 0 and
+ * *out_has / out_lo / out_hi (out_has = 0: the reference returns nil), or -1 where it signals bad-range. */
+static int infer_hcp_range(int supply[][5], int nsuit, int base_has, int base_lo, int base_hi,
+                           const hcp_ref *others, int n_others, int *out_has, int *out_lo, int *out_hi)
+{
+    int total = 0, cards = 0;
+    for (int s = 0; s < nsuit; ++s) {
+        for (int h = 1; h <= 4; ++h) total += h * supply[s][h];          /* permut-hcp of the flattened honour counts */
+        for (int h = 0; h <= 4; ++h) cards += supply[s][h];
+    }
+    int min_hcp = 0;
+    if (cards == 13 * (n_others + 1)) {                                    /* (= (hands-in-supply supply) (+ (length other-defs) 1)) */
+        int acc = total;
+        for (int i = 0; i < n_others; ++i) {
+            if (!others[i].present) acc = 0;                               /* :default 0 */
+            else if (acc != 0) { acc = minus_q(acc, others[i].hi); if (acc < 0) acc = 0; }
+        }
+        min_hcp = acc;
+    }
+    int max_hcp = total;
+    for (int i = 0; i < n_others; ++i)
+        if (others[i].present) max_hcp = minus_q(max_hcp, others[i].lo);   /* default: acc */
+    const int up_limit = max_hcp < total ? max_hcp : total;
+    if (!base_has) {
+        *out_has = (up_limit < total || min_hcp > 0);
+        *out_lo = min_hcp; *out_hi = up_limit;
+        return 0;
+    }
+    int down = base_lo == NILV ? 0 : base_lo;
+    if (min_hcp > down) down = min_hcp;
+    int up = base_hi == NILV ? up_limit : (base_hi < up_limit ? base_hi : up_limit);
+    if (down > up) return -1;
+    *out_has = 1; *out_lo = down; *out_hi = up;
+    return 0;
+}
+
+/* bridge.cl:1267-1269 infer-distgen-params = infer-hcp-range ++ infer-suit-ranges (1192-1234).
+ * Returns 0 and the narrowed def, -1 on bad-range. */
+ORC_API int orc_infer_distgen_params(int supply[4][5], const orc_def *base_in, const orc_def *others, int n_others, orc_def *out)
+{
+    orc_def nil_def;
+    memset(&nil_def, 0, sizeof nil_def);
+    const orc_def *base = base_in ? base_in : &nil_def;                    /* (car nil) = nil: no key at all */
+    memset(out, 0, sizeof *out);
+    out->hcp_lo = out->hcp_hi = NILV;
+    for (int s = 0; s < 4; ++s) out->len_lo[s] = out->len_hi[s] = out->th_lo[s] = out->th_hi[s] = NILV;
+    hcp_ref refs[4];
+    for (int i = 0; i < n_others; ++i) { refs[i].present = others[i].has_hcp; refs[i].lo = others[i].hcp_lo; refs[i].hi = others[i].hcp_hi; }
+    if (infer_hcp_range(supply, 4, base->has_hcp, base->hcp_lo, base->hcp_hi, refs, n_others,
+                        &out->has_hcp, &out->hcp_lo, &out->hcp_hi)) return -1;
+    int cards = 0, suitlen[4];
+    for (int s = 0; s < 4; ++s) {
+        suitlen[s] = 0;
+        for (int h = 0; h <= 4; ++h) suitlen[s] += supply[s][h];
+        cards += suitlen[s];
+    }
+    const int exhaust = cards == 13 * (n_others + 1);
+    for (int s = 0; s < 4; ++s) {
+        int min_len = 0;
+        if (exhaust) {
+            int acc = suitlen[s];
+            for (int i = 0; i < n_others; ++i) {
+                if (!others[i].has_suit[s]) acc = 0;                                       /* :default 0 */
+                else if (acc != 0) acc = minus_q(acc, others[i].len_hi[s] != NILV ? others[i].len_hi[s] : others[i].len_lo[s]);
+            }
+            min_len = acc;
+        }
+        int max_len = suitlen[s];
+        for (int i = 0; i < n_others; ++i)
+            if (others[i].has_suit[s]) max_len = minus_q(max_len, others[i].len_lo[s]);
+        const int up_limit = max_len < suitlen[s] ? max_len : suitlen[s];
+        if (!base->has_suit[s]) {
+            if (up_limit < suitlen[s]) { out->has_suit[s] = 1; out->len_lo[s] = min_len; out->len_hi[s] = up_limit; }
+            continue;
+        }
+        int down = base->len_lo[s] != NILV ? (base->len_lo[s] > min_len ? base->len_lo[s] : min_len) : min_len;
+        int up = base->len_hi[s] != NILV ? (base->len_hi[s] < up_limit ? base->len_hi[s] : up_limit) : up_limit;
+        if (down > up_limit) return -1;
+        out->has_suit[s] = 1; out->len_lo[s] = down; out->len_hi[s] = up;
+        if (n_others > 0) {                                                                   /* suit-hcp is a non-empty list */
+            for (int i = 0; i < n_others; ++i) {
+                refs[i].present = others[i].has_suit[s] && others[i].has_third[s];
+                refs[i].lo = others[i].th_lo[s]; refs[i].hi = others[i].th_hi[s];
+            }
+            int has = 0, lo = NILV, hi = NILV;
+            if (infer_hcp_range(&supply[s], 1, base->has_third[s], base->th_lo[s], base->th_hi[s], refs, n_others, &has, &lo, &hi)) return -1;
+            if (has) { out->has_third[s] = 1; out->th_lo[s] = lo; out->th_hi[s] = hi; }
+        }
+    }
+    return 0;
+}
+
+static void def_to_spec(const orc_def *d, orc_spec *sp)
+{
+    memset(sp, 0, sizeof *sp);
+    sp->has_hcp = d->has_hcp; sp->hcp_lo = d->hcp_lo; sp->hcp_hi = d->hcp_hi;
+    for (int s = 0; s < 4; ++s) {
+        sp->len_lo[s] = d->has_suit[s] ? d->len_lo[s] : NILV;
+        sp->len_hi[s] = d->has_suit[s] ? d->len_hi[s] : NILV;
+        sp->has_shcp[s] = d->has_suit[s] && d->has_third[s];
+        sp->shcp_lo[s] = d->th_lo[s]; sp->shcp_hi[s] = d->th_hi[s];
+    }
+}
+
+/* rand-hand on a generator whose weights are kept (same distribution as orc_rand_hand, which re-walks the
+ * pattern list recomputing every weight -- that form is the TIMED baseline; this one serves the distribution checks) */
+static uint64_t rand_hand_weights(orc_distgen *g, const uint64_t *wts, orc_rng *r)
+{
+    static __thread int lc[20000][4];
+    static __thread uint64_t w[20000];
+    uint64_t x = rng_below(r, g->total);
+    int cur = 0;
+    for (;; ++cur) { if (!(x > wts[cur])) break; x -= wts[cur]; }         /* bridge.cl:1075-1080, `>` kept */
+    unsigned pat = g->pat[cur];
+    int n;
+    uint64_t tot = pattern_weight(g, pat, lc, w, &n);
+    int pick = 0;
+    if (tot > 0) { uint64_t y = rng_below(r, tot); for (pick = 0; pick < n; ++pick) { if (y < w[pick]) break; y -= w[pick]; } }
+    uint64_t hand = 0;
+    for (int s = 0; s < 4; ++s) {
+        unsigned lane = (unsigned)(g->cards >> (13 * s)) & 0x1FFFu;
+        int pile[13], np = 0, got[13], ng = 0;
+        for (int rk = 0; rk <= 8; ++rk) if (lane >> rk & 1) pile[np++] = rk;
+        deal_from(r, pile, &np, tot > 0 ? lc[pick][s] : 0, got, &ng);
+        for (int k = 0; k < ng; ++k) hand |= 1ull << (13 * s + got[k]);
+        for (int h = 0; h < 4; ++h) if (pat_bit(pat, s, h)) hand |= 1ull << (13 * s + 9 + h);
+    }
+    return hand;
+}
+
+/* One `build` (bridge.cl:1292-1319): consts = 52-bit card masks of the := hands, defs = the :~ defs in order.
+ * hands[] gets consts, the sampled seats, then the deal-all hands; returns their number, or -1 where the
+ * reference signals an error (bad-range, or a generator of total weight 0: `(random 0)`).
+ * root / root_w: the cached root generator and its weights (NULL: built here). */
+static int ref_build_one(const uint64_t *consts, int n_consts, const orc_def *defs, int n_defs, orc_rng *r,
+                         orc_distgen *root, const uint64_t *root_w, uint64_t *hands)
+{
+    uint64_t rest = (1ull << 52) - 1;
+    int nh = 0;
+    for (int i = 0; i < n_consts; ++i) { rest &= ~consts[i]; hands[nh++] = consts[i]; }
+    int first = 1, di = 0;
+    /* the first def always goes through the root generator, even when there is none ((car nil) = nil) */
+    while (first || (di < n_defs && __builtin_popcountll(rest) > 13)) {
+        orc_distgen *g = root;
+        uint64_t *wts = NULL;
+        const uint64_t *use_w = root_w;
+        if (!first || !root) {
+            int sup[4][5];
+            orc_def nar;
+            orc_spec sp;
+            orc_supply(rest, sup);
+            const int n_others = n_defs - di - 1 > 0 ? n_defs - di - 1 : 0;
+            if (orc_infer_distgen_params(sup, di < n_defs ? &defs[di] : NULL, di + 1 < n_defs ? &defs[di + 1] : NULL, n_others, &nar)) return -1;
+            def_to_spec(&nar, &sp);
+            g = orc_distgen_new(rest, &sp);
+            wts = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(g->npat ? g->npat : 1));
+            for (int i = 0; i < g->npat; ++i) wts[i] = pattern_weight(g, g->pat[i], NULL, NULL, NULL);
+            use_w = wts;
+        }
+        if (g->total == 0) { if (g != root) { orc_distgen_free(g); free(wts); } return -1; }
+        const uint64_t h = rand_hand_weights(g, use_w, r);
+        if (g != root) { orc_distgen_free(g); free(wts); }
+        hands[nh++] = h;
+        rest &= ~h;
+        first = 0;
+        ++di;
+    }
+    if (rest) {
+        uint64_t st = r->s;
+        nh += orc_deal_all(rest, &st, hands + nh);
+        r->s = st;
+    }
+    return nh;
+}
+
+#include <pthread.h>
+typedef struct {
+    const uint64_t *consts; int n_consts; const orc_def *defs; int n_defs;
+    uint64_t seed, n; uint64_t *out; int8_t *count; orc_distgen *root; const uint64_t *root_w;
+} ref_job;
+static void *ref_worker(void *arg)
+{
+    ref_job *j = (ref_job *)arg;
+    orc_rng r = { j->seed };
+    for (uint64_t i = 0; i < j->n; ++i) {
+        uint64_t h[8] = {0};
+        const int k = ref_build_one(j->consts, j->n_consts, j->defs, j->n_defs, &r, j->root, j->root_w, h);
+        j->count[i] = (int8_t)k;
+        for (int q = 0; q < 4; ++q) j->out[4 * i + q] = (k > q) ? h[q] : 0;
+    }
+    return NULL;
+}
+/* n builds on `threads` host threads (independent generators seeded seed + 7919 t): out[4 i + k] = hand k of build i
+ * (52-bit masks, `build`'s order), count[i] = hands returned or -1 = the reference signals an error. */
+ORC_API int orc_ref_build_batch(const uint64_t *consts, int n_consts, const orc_def *defs, int n_defs, uint64_t n, uint64_t seed,
+                                int threads, uint64_t *out, int8_t *count)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    binom_init();
+    /* the root generator is made once, like the reference's `rootgen` slot (bridge.cl:1297-1301) */
+    uint64_t cards = (1ull << 52) - 1;
+    for (int i = 0; i < n_consts; ++i) cards &= ~consts[i];
+    int sup[4][5];
+    orc_def nar;
+    orc_spec sp;
+    orc_supply(cards, sup);
+    if (orc_infer_distgen_params(sup, n_defs ? &defs[0] : NULL, n_defs > 1 ? &defs[1] : NULL, n_defs > 1 ? n_defs - 1 : 0, &nar)) {
+        for (uint64_t i = 0; i < n; ++i) count[i] = -1;
+        return -1;
+    }
+    def_to_spec(&nar, &sp);
+    orc_distgen *root = orc_distgen_new(cards, &sp);
+    uint64_t *root_w = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(root->npat ? root->npat : 1));
+    for (int i = 0; i < root->npat; ++i) root_w[i] = pattern_weight(root, root->pat[i], NULL, NULL, NULL);
+    pthread_t th[64];
+    ref_job jobs[64];
+    uint64_t at = 0;
+    for (int t = 0; t < threads; ++t) {
+        const uint64_t share = n / (uint64_t)threads + ((uint64_t)t < n % (uint64_t)threads ? 1 : 0);
+        jobs[t] = (ref_job){ consts, n_consts, defs, n_defs, seed + 7919ull * (uint64_t)t, share, out + 4 * at, count + at, root, root_w };
+        at += share;
+        pthread_create(&th[t], NULL, ref_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    orc_distgen_free(root);
+    free(root_w);
+    return 0;
 }

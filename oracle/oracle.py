@@ -64,6 +64,61 @@ def make_spec(hcp=None, c=None, d=None, h=None, s=None) -> Spec:
 FULL_DECK = (1 << 52) - 1
 
 
+class Def(C.Structure):
+    """orc_def: a range def as `build` sees it (numbers normalised to (n n), like rest.cl's normdef); -1 = nil."""
+    _fields_ = [("has_hcp", C.c_int), ("hcp_lo", C.c_int), ("hcp_hi", C.c_int),
+                ("has_suit", C.c_int * 4), ("len_lo", C.c_int * 4), ("len_hi", C.c_int * 4),
+                ("has_third", C.c_int * 4), ("th_lo", C.c_int * 4), ("th_hi", C.c_int * 4)]
+
+
+def _pair(v):
+    if isinstance(v, int):
+        return v, v
+    lo = -1 if v[0] is None else int(v[0])
+    hi = -1 if len(v) < 2 or v[1] is None else int(v[1])
+    return lo, hi
+
+
+def make_def(d) -> Def:
+    """{'hcp': [lo, hi] | n, 'c': [lo, hi, [slo, shi]] | n, ...} (None = nil) -> Def"""
+    out = Def()
+    out.hcp_lo = out.hcp_hi = -1
+    for i in range(4):
+        out.len_lo[i] = out.len_hi[i] = out.th_lo[i] = out.th_hi[i] = -1
+    d = d or {}
+    if d.get("hcp") is not None:
+        out.has_hcp = 1
+        out.hcp_lo, out.hcp_hi = _pair(d["hcp"])
+    for i, k in enumerate("cdhs"):
+        v = d.get(k)
+        if v is None:
+            continue
+        out.has_suit[i] = 1
+        out.len_lo[i], out.len_hi[i] = _pair(v)
+        if not isinstance(v, int) and len(v) > 2 and v[2] is not None:
+            out.has_third[i] = 1
+            out.th_lo[i], out.th_hi[i] = _pair(v[2])
+    return out
+
+
+def def_to_dict(d: Def) -> dict:
+    nil = lambda x: None if x < 0 else x
+    out = {}
+    if d.has_hcp:
+        out["hcp"] = [nil(d.hcp_lo), nil(d.hcp_hi)]
+    for i, k in enumerate("cdhs"):
+        if d.has_suit[i]:
+            v = [nil(d.len_lo[i]), nil(d.len_hi[i])]
+            if d.has_third[i]:
+                v.append([nil(d.th_lo[i]), nil(d.th_hi[i])])
+            out[k] = v
+    return out
+
+
+class Contract(C.Structure):
+    _fields_ = [("level", C.c_int8), ("suit", C.c_int8), ("declarer", C.c_int8), ("dbl", C.c_int8)]
+
+
 def lib():
     global _LIB
     if _LIB is not None:
@@ -121,8 +176,77 @@ def lib():
     L.orc_ref_run.restype = C.c_uint64
     L.orc_build_batch.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p]
     L.orc_build_batch.restype = None
+    L.orc_tricks_of.argtypes = [C.c_uint32 * 2, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32 * 8]
+    L.orc_tricks_of.restype = None
+    L.orc_score_tally_records.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(Contract), C.c_void_p, C.c_int, C.c_void_p,
+                                          C.c_int, C.c_void_p]
+    L.orc_score_tally_records.restype = None
+    L.orc_score_tally_index.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Contract), C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_int, C.c_void_p]
+    L.orc_score_tally_index.restype = None
+    L.orc_infer_distgen_params.argtypes = [(C.c_int * 5) * 4, C.POINTER(Def), C.POINTER(Def), C.c_int, C.POINTER(Def)]
+    L.orc_ref_build_batch.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(Def), C.c_int, C.c_uint64, C.c_uint64, C.c_int,
+                                      C.c_void_p, C.c_void_p]
     _LIB = L
     return L
+
+
+def infer_distgen_params(supply, base, others):
+    """bridge.cl:1267-1269 through the C restatement: supply = 4 x [n_low nJ nQ nK nA] (fewer rows are padded with
+    empty suits); defs as make_def takes them.  Returns the narrowed def as a dict, or raises ValueError (bad-range)."""
+    sup = ((C.c_int * 5) * 4)()
+    for i, row in enumerate(supply):
+        for j, v in enumerate(row):
+            sup[i][j] = v
+    oth = (Def * max(1, len(others)))(*[make_def(o) for o in others])
+    out = Def()
+    b = make_def(base) if base is not None else None
+    rc = lib().orc_infer_distgen_params(sup, C.byref(b) if b is not None else None, oth, len(others), C.byref(out))
+    if rc:
+        raise ValueError("bad-range")
+    return def_to_dict(out)
+
+
+def ref_build_batch(consts, defs, n: int, seed: int = 1, threads: int = 0):
+    """n x `build` (bridge.cl:1292-1319) with the reference's own algorithm: consts = 52-bit id-order masks of the :=
+    hands, defs = the :~ defs.  Returns (hands uint64[n,4] in build's order, count int8[n]: hands returned, -1 = error)."""
+    import os
+    if threads <= 0:
+        threads = max(1, len(os.sched_getaffinity(0)))
+    carr = (C.c_uint64 * max(1, len(consts)))(*[int(c) for c in consts])
+    darr = (Def * max(1, len(defs)))(*[make_def(d) for d in defs])
+    out = np.zeros((n, 4), dtype=np.uint64)
+    cnt = np.zeros(n, dtype=np.int8)
+    lib().orc_ref_build_batch(carr, len(consts), darr, len(defs), n, seed, threads, out.ctypes.data, cnt.ctypes.data)
+    return out, cnt
+
+
+def _score_args(contracts, vulnerable, pairs):
+    carr = (Contract * len(contracts))(*[Contract(int(c.level), int(c.suit), int(c.declarer), int(c.dbl)) for c in contracts])
+    vul = np.ascontiguousarray(vulnerable, dtype=np.uint8)
+    pr = np.ascontiguousarray(pairs, dtype=np.uint8).reshape(-1)
+    return carr, vul, pr
+
+
+def score_tally_records(seed: int, records: np.ndarray, contracts, vulnerable, pairs):
+    """CPU mirror of BMC_TALLY_SCORE: (tricks int64[8,14], imps int64[8,49], dropped int64[8]) over the given records."""
+    rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
+    carr, vul, pr = _score_args(contracts, vulnerable, pairs)
+    hist = np.zeros(8 * 14 + 8 * 49 + 8, dtype=np.uint64)
+    lib().orc_score_tally_records(seed, rec.ctypes.data, rec.shape[0], carr, vul.ctypes.data, len(contracts), pr.ctypes.data,
+                                  pr.size // 2, hist.ctypes.data)
+    h = hist.astype(np.int64)
+    return h[:112].reshape(8, 14), h[112:112 + 392].reshape(8, 49), h[504:]
+
+
+def score_tally_index(seed: int, first: int, n: int, contracts, vulnerable, pairs):
+    """CPU mirror of bmc_score_tally (index-keyed trick source)."""
+    carr, vul, pr = _score_args(contracts, vulnerable, pairs)
+    hist = np.zeros(8 * 14 + 8 * 49 + 8, dtype=np.uint64)
+    lib().orc_score_tally_index(seed, first, n, carr, vul.ctypes.data, len(contracts), pr.ctypes.data, pr.size // 2,
+                                hist.ctypes.data)
+    h = hist.astype(np.int64)
+    return h[:112].reshape(8, 14), h[112:112 + 392].reshape(8, 49), h[504:]
 
 
 # ---- convenience wrappers -------------------------------------------------

@@ -238,23 +238,95 @@ def test_mc_case_save_load(engine, tmp_path):
     assert [r[1] for r in back.data] == [r[1] for r in mc.data]
 
 
-# ---- fused score tally ----------------------------------------------------------------------------
-def test_score_tally_consistent(engine):
-    cs = [compscore.Contract(t).c_struct() for t in ("1NTS", "3NTS", "4HS", "4SS")]
-    th, ih, tab = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=2_000_000, seed=9)
-    assert (th.sum(axis=1) == 2_000_000).all()
-    exp = 2_000_000 / 14
-    assert (abs(th.astype(float) - exp) < 6 * exp ** 0.5).all()          # uniform tricks 0..13
-    for c in range(4):
+# ---- compscore tallies ----------------------------------------------------------------------------------
+SCORE_CONTRACTS = ("1NTS", "3NTS", "4HS", "4SS", "1NTS", "3NTS", "4HS", "7NTNxx")
+SCORE_VUL = [0, 0, 0, 0, 1, 1, 1, 1]
+SCORE_PAIRS = [0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6, 7, 7, 3]           # the last two pairs overflow the IMP table at times
+
+
+def test_score_tally_bit_exact_vs_oracle(engine):
+    """bmc_score_tally (index-keyed trick source -> base-score -> match-points) against the CPU mirror, word for word:
+    trick histogram, IMP histogram and the count of differences off the IMP table (the reference errors there)"""
+    cs = [compscore.Contract(t).c_struct() for t in SCORE_CONTRACTS]
+    n = 300_000
+    th, ih, tab = engine.score_tally(cs, SCORE_VUL, SCORE_PAIRS, n=n, seed=9, first_index=12345678901)
+    tr_o, im_o, dr_o = O.score_tally_index(9, 12345678901, n, cs, SCORE_VUL, SCORE_PAIRS)
+    assert np.array_equal(th.astype(np.int64), tr_o[:len(cs)])
+    assert np.array_equal(ih.astype(np.int64), im_o[:len(SCORE_PAIRS) // 2])
+    assert np.array_equal(engine.last_imp_dropped.astype(np.int64), dr_o[:len(SCORE_PAIRS) // 2])
+    assert dr_o[5:7].sum() > 0                                            # the overflow path was exercised
+    assert (th.sum(axis=1) == n).all() and (ih.sum(axis=1) + engine.last_imp_dropped == n).all()
+    exp = n / 14
+    assert (abs(th.astype(float) - exp) < 6 * exp ** 0.5).all()          # exactly uniform tricks 0..13
+    for c in range(len(cs)):
         for t in range(14):
-            assert tab[c, t] == O.lib().orc_base_score(cs[c].level, cs[c].suit, cs[c].declarer, cs[c].dbl, t, [0, 1, 0, 1][c])
-    assert (ih.sum(axis=1) == 2_000_000).all()
-    # determinism: same (seed, range) -> same tallies, and additivity over index sub-ranges
-    th2, ih2, _ = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=2_000_000, seed=9)
-    assert np.array_equal(th, th2) and np.array_equal(ih, ih2)
-    a = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=1_200_000, seed=9)
-    b = engine.score_tally(cs, [0, 1, 0, 1], [0, 1, 2, 3], n=800_000, seed=9, first_index=1_200_000)
+            assert tab[c, t] == O.lib().orc_base_score(cs[c].level, cs[c].suit, cs[c].declarer, cs[c].dbl, t, SCORE_VUL[c])
+    # additivity over index sub-ranges (what lets GPUs split a job)
+    a = engine.score_tally(cs, SCORE_VUL, SCORE_PAIRS, n=200_000, seed=9, first_index=12345678901)
+    b = engine.score_tally(cs, SCORE_VUL, SCORE_PAIRS, n=100_000, seed=9, first_index=12345678901 + 200_000)
     assert np.array_equal(a[0] + b[0], th) and np.array_equal(a[1] + b[1], ih)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fused_score_tally_over_constrained_sample(engine, mode):
+    """BASELINE config 4: compscore tallies over CONSTRAINED samples.  The sampling kernel scores every accepted deal
+    in stage B (BMC_TALLY_SCORE); the result must equal the CPU mirror applied to the records the same call stored."""
+    from bridge_mc_b200._lib import TALLY_ALL, TALLY_SCORE
+    cs = [compscore.Contract(t).c_struct() for t in SCORE_CONTRACTS]
+    cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None]).set_mode(mode)
+    cons.set_scoring(cs, SCORE_VUL, SCORE_PAIRS)
+    n = 1 << 22
+    rec, tal, _ = engine.sample(cons, n_raw=n, seed=21, tally_mask=TALLY_ALL | TALLY_SCORE)
+    assert rec.shape[0] == tal["accepted"] > 100_000
+    tr_o, im_o, dr_o = O.score_tally_records(21, rec, cs, SCORE_VUL, SCORE_PAIRS)
+    assert np.array_equal(tal["tricks"], tr_o) and np.array_equal(tal["imps"], im_o) and np.array_equal(tal["imp_dropped"], dr_o)
+    assert (tal["tricks"].sum(axis=1) == tal["accepted"]).all()
+    # the tally is a function of the accepted SET: any partition of the index range gives the same words
+    parts = [engine.sample(cons, n_raw=n // 4, seed=21, first_index=i * (n // 4), cap=0, tally_mask=TALLY_SCORE)[1] for i in range(4)]
+    for key in ("tricks", "imps", "imp_dropped"):
+        assert np.array_equal(tal[key], sum(p[key] for p in parts))
+    # without the bit nothing is scored; without contracts the bit is an error
+    _, plain, _ = engine.sample(cons, n_raw=1 << 16, seed=21, cap=0)
+    assert plain["tricks"].sum() == 0 and plain["imps"].sum() == 0
+    from bridge_mc_b200._lib import BridgeMcError
+    with pytest.raises(BridgeMcError):
+        engine.sample(Constraints(None, [None, None, bidding.openings.form((1, "NT")), None]), n_raw=1 << 16, cap=0,
+                      tally_mask=TALLY_SCORE)
+
+
+# ---- C5: the rare constraint (S chooses 2NT, N answers 6NT over (nt-responses 2)) ---------------------------
+def _c5_rules():
+    return [bidding.nt_responses(2).chooses((6, "NT")), None, bidding.openings.chooses((2, "NT")), None]
+
+
+def _c5_oracle(rec):
+    m = seat_masks(rec)
+    return (O.choose_bid_batch(0, m[:, 2]) == 1) & (O.choose_bid_batch(2, m[:, 0]) == 6)     # openings[1] = 2NT, nt2[6] = 6NT
+
+
+def test_c5_constraint_parity(engine):
+    """bidding.cl:81-82,166-187.  (i) both dealing modes: every accepted deal satisfies the oracle's choose-bid, and the
+    acceptance agrees with the known 2.1685e-5; (ii) on deals where South does open 2NT the accept flag is bit-exact
+    against the oracle (near misses included); (iii) the full-deal sampler's accepted set = the filter of the
+    unconstrained stream over the same indices."""
+    n = 100_000_000
+    counts = []
+    for mode in (1, 2):
+        cons = Constraints(None, _c5_rules()).set_mode(mode)
+        rec, tal, _ = engine.sample(cons, n_raw=n, seed=55, cap=8192)
+        assert rec.shape[0] == tal["accepted"] and _c5_oracle(rec).all(), mode
+        counts.append(tal["accepted"])
+        exp = 2.1685e-5 * n
+        assert abs(tal["accepted"] - exp) < 6 * exp ** 0.5, (mode, tal["accepted"])
+    south_2nt = Constraints(None, [None, None, bidding.openings.chooses((2, "NT")), None])
+    near, _, _ = engine.sample(south_2nt, n_raw=12_000_000, seed=56)
+    assert near.shape[0] > 50_000
+    acc, _ = engine.filter(near, Constraints(None, _c5_rules()), None, want_features=False)
+    ref = _c5_oracle(near)
+    assert np.array_equal(acc.astype(bool), ref) and 100 < ref.sum() < 600
+    raw, _, _ = engine.sample(None, n_raw=4_000_000, seed=57)
+    got, _, _ = engine.sample(Constraints(None, _c5_rules()).set_mode(1), n_raw=4_000_000, seed=57)
+    assert np.array_equal(sort_records(got), sort_records(raw[_c5_oracle(raw)]))
 
 
 def test_sampler_partition_invariance(engine):
@@ -387,3 +459,106 @@ def test_device_hist_base_matches_the_host_mirror(engine):
     with pytest.raises(Exception):
         engine.hist_base(rec, measures[:4], cap=10)
     assert engine.hist_base(np.empty((0, 2), np.uint64), measures[:1]) == []
+
+
+# ---- index records ----------------------------------------------------------------------------------------
+def test_index_records_expand_to_the_same_deals(engine):
+    """bmc_sample_indices / bmc_expand: an accepted deal shipped as the 32-bit offset of its index regenerates to exactly
+    the record the 16-byte path stores -- in every dealing mode (full deal, fixed hands, seat-first, reference order)"""
+    h = str2hand("♣ AJ7 ♦ AK54 ♥ 6543 ♠ 64")
+    nt = [None, None, bidding.openings.form((1, "NT")), None]
+    cases = [
+        (lambda: None, 50_000),
+        (lambda: Constraints([seat_spec(fixed=h), seat_spec(hcp=(12, 14))]), 200_000),
+        (lambda: Constraints(None, nt).set_mode(1), 300_000),
+        (lambda: Constraints(None, nt).set_mode(2), 1_000_003),
+        (lambda: Constraints([seat_spec(hcp=(15, 17), s=(5, None)), seat_spec(hcp=(10, 11), h=(4, None))]).set_reference_order(2), 100_000),
+    ]
+    for make, n in cases:
+        cons = make()
+        first = 777_777_777_777
+        rec, tal, _ = engine.sample(cons, n_raw=n, seed=33, first_index=first)
+        off, tal2, st = engine.sample_indices(cons, n_raw=n, seed=33, first_index=first)
+        assert off.dtype == np.uint32 and off.shape[0] == rec.shape[0] == tal["accepted"] == tal2["accepted"]
+        assert len(np.unique(off)) == off.shape[0] and (off < n).all()
+        for key in ("hcp", "len", "shape"):
+            assert np.array_equal(tal[key], tal2[key])
+        back = engine.expand(cons, off, seed=33, first_index=first)
+        assert np.array_equal(sort_records(back), sort_records(rec))
+    # accept-target form: offsets relative to the call's first index across several waves
+    cons = Constraints(None, nt)
+    off, tal, st = engine.sample_indices(cons, n_accept=50_000, wave=1 << 18, seed=34, first_index=5)
+    rec, _, _ = engine.sample(cons, n_raw=int(st.raw), seed=34, first_index=5)
+    assert st.raw > (1 << 18) and np.array_equal(sort_records(engine.expand(cons, off, seed=34, first_index=5)), sort_records(rec))
+    assert engine.expand(cons, np.empty(0, np.uint32)).shape == (0, 2)
+
+
+def test_accept_target_waves_are_cancelled_on_the_device(engine):
+    """accept-target jobs enqueue their waves in batches; the waves after the one that meets the target cancel
+    themselves, so the result is still `whole waves until the target is met` and raw counts only the waves that ran"""
+    cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    wave = 1 << 16
+    for target in (1, 2_000, 2_600, 30_000):
+        rec, tal, st = engine.sample(cons, n_accept=target, wave=wave, seed=12, cap=40_000)
+        assert tal["raw"] == st.raw == st.waves * wave and tal["accepted"] >= target
+        if st.waves > 1:                                              # one wave fewer would not have been enough
+            _, short, _ = engine.sample(cons, n_raw=int(st.raw) - wave, seed=12, cap=0)
+            assert short["accepted"] < target
+        again, _, _ = engine.sample(cons, n_raw=int(st.raw), seed=12, cap=40_000)
+        assert np.array_equal(sort_records(rec), sort_records(again))
+
+
+# ---- one call, several devices ----------------------------------------------------------------------------
+def test_sample_multi_is_independent_of_the_device_count(engine):
+    """bmc_sample_multi: contiguous index shares per device, tallies summed inside the library.  Tallies and the accepted
+    set are identical for every device count (1 .. all GPUs of the box) and equal to the single-context call."""
+    import torch
+    from bridge_mc_b200._lib import TALLY_ALL, TALLY_SCORE
+    from bridge_mc_b200.engine import sample_multi
+    cs = [compscore.Contract(t).c_struct() for t in SCORE_CONTRACTS]
+    cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    cons.set_scoring(cs, SCORE_VUL, SCORE_PAIRS)
+    n = 3_000_001
+    mask = TALLY_ALL | TALLY_SCORE
+    rec1, tal1, _ = engine.sample(cons, n_raw=n, seed=71, first_index=11, tally_mask=mask)
+    ndev = torch.cuda.device_count()
+    for g in sorted({1, min(2, ndev), min(4, ndev), ndev}):
+        rec, tal, st = sample_multi(list(range(g)), cons, n_raw=n, seed=71, first_index=11, tally_mask=mask, cap=200_000 * g)
+        assert st.raw == n and tal["raw"] == n
+        for key in ("voided", "accepted", "stored"):
+            assert tal[key] == tal1[key], (g, key)
+        for key in ("hcp", "len", "shape", "tricks", "imps", "imp_dropped"):
+            assert np.array_equal(tal[key], tal1[key]), (g, key)
+        assert np.array_equal(sort_records(rec), sort_records(rec1)), g
+    # accept-target form: every device brings its share
+    rec, tal, st = sample_multi(list(range(ndev)), cons, n_accept=10_000, wave=1 << 16, seed=72, cap=20_000 * ndev, tally_mask=TALLY_ALL)
+    assert tal["accepted"] >= 10_000 and rec.shape[0] == tal["accepted"]
+    from bridge_mc_b200._lib import BridgeMcError
+    with pytest.raises(BridgeMcError):
+        sample_multi([0, 0], cons, n_raw=10)
+
+
+# ---- truncation must not bias the sample (Deal.build / McCase.sim) ----------------------------------------------
+def test_small_requests_are_unbiased(engine):
+    """A caller that takes fewer deals than a library call produced must still see an unbiased sample: the spade ace is
+    with each seat a quarter of the time (sim(50) used to keep the 50 SMALLEST records of a wave)."""
+    def ace_seats(deal_obj, n):
+        rec = deal_obj.build_records(n)
+        assert rec.shape[0] == n
+        m = seat_masks(rec)
+        return [int(((m[:, k] >> np.uint64(16 * 3 + 12)) & np.uint64(1)).sum()) for k in range(4)]
+
+    for semantics in ("reference", "uniform"):
+        tot = np.zeros(4)
+        for seed in range(40):
+            tot += ace_seats(Deal(defs=[{}], engine=engine, seed=1000 + seed, semantics=semantics), 50)
+        assert tot.sum() == 2000
+        assert (abs(tot - 500) < 5 * (2000 * 0.25 * 0.75) ** 0.5).all(), (semantics, tot)
+    # the deals a call overdraws are handed out by the next calls, not dropped
+    d = Deal(defs=[{"hcp": [15, 17]}], engine=engine, seed=5, semantics="uniform")
+    a = d.build_records(10)
+    used = d._next_index
+    b = d.build_records(10)
+    assert d._next_index == used and not np.array_equal(a, b)
+    rows = McCase(Deal(engine=engine, seed=9), [lambda t, n, e, s, w: 12 in s.suits[3]]).sim(50)
+    assert len(rows) == 50

@@ -2,8 +2,6 @@
 reference's own sequential `build` (bridge.cl:1292-1319), which differs from the uniform distribution over valid
 deals once two or more seats are ranged.  Checked against (a) exact pmfs where one seat is ranged and (b) the
 reference algorithm restated in the oracle (oracle/ref_build.py) for multi-seat defs."""
-import ctypes as C
-
 import numpy as np
 import pytest
 from scipy.stats import chi2
@@ -11,7 +9,7 @@ from scipy.stats import chi2
 from bridge_mc_b200.cards import Hand, seat_masks, str2hand
 from bridge_mc_b200.engine import Constraints, seat_spec
 from oracle import oracle as O
-from oracle.ref_build import ref_build
+from oracle.ref_build import ref_build_batch
 
 pytestmark = pytest.mark.gpu
 
@@ -76,14 +74,14 @@ def test_lone_def_drops_its_suit_hcp_range(engine):
     assert (feats["suit_hcp"][:, 0, 3] < 8).any()
 
 
+N_ORACLE = 100_000          # builds of the reference algorithm per comparison (C restatement, all host threads)
+
+
 def _oracle_sample(consts, defs, n, seed=1):
-    st = C.c_uint64(seed)
-    out = []
-    for _ in range(n):
-        hands = ref_build(consts, defs, st)
-        if hands is not None:
-            out.append([lanes_from52(h) for h in hands])
-    return np.array(out, dtype=np.uint64)
+    """n builds of the reference's own algorithm (oracle/ref_build.py: distgen + infer-* + build, all C); the builds
+    for which the reference signals an error are left out, as the GPU counts them in `voided`"""
+    hands, n_err = ref_build_batch(consts, defs, n, seed)
+    return O.mask52_to_lanes64(hands.reshape(-1)).reshape(-1, 4), n_err
 
 
 def _compare(engine, consts_hands, defs, n_oracle, seats_sampled):
@@ -93,7 +91,10 @@ def _compare(engine, consts_hands, defs, n_oracle, seats_sampled):
     _, tal, _ = engine.sample(cons, n_raw=n, seed=9, cap=0)
     assert tal["accepted"] + tal["voided"] == n and tal["accepted"] > 0.9 * n
     consts52 = [sum(1 << c for c in h.cards()) for h in consts_hands]
-    ora = _oracle_sample(consts52, defs, n_oracle)
+    ora, n_err = _oracle_sample(consts52, defs, n_oracle)
+    # the share of builds that signal an error agrees too (binomial, 5 sigma)
+    p_void = tal["voided"] / n
+    assert abs(n_err - p_void * n_oracle) <= 5 * (max(p_void, 1 / n_oracle) * n_oracle) ** 0.5 + 1, (n_err, p_void)
     f = O.features_batch(ora.reshape(-1)).reshape(ora.shape[0], -1, 11)
     ps = []
     for k in range(4):
@@ -103,13 +104,13 @@ def _compare(engine, consts_hands, defs, n_oracle, seats_sampled):
         for s in range(4):
             gpu_len = tal["len"][k][s] / tal["accepted"]
             ps.append(chi2_p(np.bincount(f[:, k, s], minlength=14), gpu_len * ora.shape[0]))
-    assert min(ps) > 1e-4, ps
+    assert min(ps) > 1e-4, ps            # 4 x (1 + 4) tests
     return tal, f
 
 
 def test_two_ranged_seats_follow_the_sequential_distribution(engine):
     defs = [dict(hcp=(15, 17), s=(5, None)), dict(hcp=(10, 11), h=(4, None))]
-    tal, f = _compare(engine, [], defs, 1200, 2)
+    tal, f = _compare(engine, [], defs, N_ORACLE, 2)
     # and this is NOT the uniform distribution over valid deals: joint rejection weights seat 0's hands by
     # the number of completions, which shifts its tallies
     cons_joint = Constraints([seat_spec(hcp=(15, 17), s=(5, 13)), seat_spec(hcp=(10, 11), h=(4, 13))])
@@ -124,7 +125,7 @@ def test_fixed_hand_and_three_ranged_seats(engine):
     seats are all defined, and the last ranged seat is implied, never sampled"""
     rng = dict(hcp=(0, 11), c=(2, 5), d=(2, 5), h=(2, 5), s=(2, 5))
     fixed = Hand([[12, 9, 5], [12, 11, 3, 2], [4, 3, 2, 1], [4, 2]])
-    tal, f = _compare(engine, [fixed], [rng, rng, rng], 4000, 2)
+    tal, f = _compare(engine, [fixed], [rng, rng, rng], N_ORACLE, 2)
     for k in (1, 2, 3):                                                # incl. the never-sampled last seat
         assert tal["hcp"][k][12:].sum() == 0
         assert tal["len"][k][:, :2].sum() == 0 and tal["len"][k][:, 6:].sum() == 0
@@ -156,6 +157,6 @@ def test_three_ranged_seats_with_suit_hcp_ranges(engine):
     defs = [dict(hcp=(11, 14), s=(5, None, (4, None)), h=(0, 3)),
             dict(hcp=(6, 9), s=(0, 3, (1, None)), d=(4, None)),
             dict(c=(3, 6))]
-    tal, f = _compare(engine, [], defs, 5000, 3)
+    tal, f = _compare(engine, [], defs, N_ORACLE, 3)
     assert tal["hcp"][0][:11].sum() == 0 and tal["hcp"][0][15:].sum() == 0
     assert tal["len"][2][0][:3].sum() == 0 and tal["len"][2][0][7:].sum() == 0      # third seat: 3..6 clubs

@@ -185,7 +185,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), f"libbridgemc.so does not export {name}"
     assert sorted(_lib.EXPORTS) == declared
     assert C.sizeof(_lib.SeatSpec) == 32 and C.sizeof(_lib.Stats) == 48 and C.sizeof(_lib.Contract) == 4
-    assert _lib.TALLY_WORDS == 4 + 4 * 40 + 4 * 4 * 14 + 4 * 40
+    assert _lib.TALLY_WORDS == 4 + 4 * 40 + 4 * 4 * 14 + 4 * 40 + 8 * 14 + 8 * 49 + 8
     assert b"sm_100a" in L.bmc_version()
 
 

@@ -275,3 +275,72 @@ def test_randcar_weights_statistical():
     for k, p in enumerate((1 / 16, 5 / 16, 10 / 16)):
         assert abs(counts[k] - n * p) < 4.5 * (n * p * (1 - p)) ** 0.5
     assert L.orc_randcar_weights((C.c_uint64 * 2)(0, 0), 2, C.byref(st)) == -1
+
+
+# ---- infer-* in the oracle's own C restatement (bridge.cl:1126-1281: 7 + 5 + 2 KATs) ----------------------------
+def _plist_dict(x):
+    """(:HCP (11 15) :C (6 NIL)) as read by sexp -> {'hcp': [11, 15], 'c': [6, None]}"""
+    x = unquote(x)
+    if not x:
+        return {}
+    return {str(x[i]).lstrip(":").lower(): x[i + 1] for i in range(0, len(x) - 1, 2)}
+
+
+def test_infer_kats_in_the_oracle():
+    """The oracle's infer-* (used by oracle/ref_build.py, independent of the product's host mirror) replays the
+    reference's 14 KATs.  orc_infer_distgen_params computes both halves; each KAT compares the half it is about."""
+    full = [[9, 1, 1, 1, 1]] * 4
+    n = 0
+    for head, keys in (("INFER-HCP-RANGE", ("hcp",)), ("INFER-SUIT-RANGES", ("c", "d", "h", "s"))):
+        for where, form, exp in load_kats(head):
+            sup = full if form[1] == ["SUPPLY", ["ALL-CARDS"]] else unquote(form[1])
+            got = O.infer_distgen_params(sup, _plist_dict(form[2]) or None, [_plist_dict(o) for o in form[3:]])
+            want = _plist_dict(exp)
+            assert {k: v for k, v in got.items() if k in keys} == want, (where, got, want)
+            n += 1
+    for where, form, exp in load_kats("INFER-DISTGEN-PARAMS"):
+        got = O.infer_distgen_params(unquote(form[1]), _plist_dict(form[2]), [_plist_dict(o) for o in (unquote(form[3]) or [])])
+        assert got == _plist_dict(exp) and list(got) == list(_plist_dict(exp)), where
+        n += 1
+    assert n == 7 + 5 + 2
+    with pytest.raises(ValueError):                           # bad-range (bridge.cl:1144-1146)
+        O.infer_distgen_params(full, {"hcp": [30, 35]}, [{"hcp": [12, 15]}])
+    with pytest.raises(ValueError):                           # bridge.cl:1223-1225
+        O.infer_distgen_params(full, {"s": [10, None]}, [{"s": [5, 6]}])
+
+
+def test_oracle_build_property():
+    """bridge.cl:2989-3003 on the oracle's own `build`: three ranged seats + one fixed hand; every hand -- also the
+    never-sampled fourth -- has HCP <= 11 and suit lengths 2..5; the four hands tile the deck"""
+    rng = {"hcp": [0, 11], "c": [2, 5], "d": [2, 5], "h": [2, 5], "s": [2, 5]}
+    fixed = sum(1 << (13 * s + r) for s, ranks in enumerate([[12, 9, 5], [12, 11, 3, 2], [4, 3, 2, 1], [4, 2]]) for r in ranks)
+    hands, cnt = O.ref_build_batch([fixed], [rng, rng, rng], 200, seed=3, threads=2)
+    assert (cnt == 4).all()
+    for row in hands.tolist():
+        assert row[0] == fixed and row[0] | row[1] | row[2] | row[3] == (1 << 52) - 1
+        for h in row[1:]:
+            lens = [bin((h >> (13 * s)) & 0x1FFF).count("1") for s in range(4)]
+            hcp = sum(max(r - 8, 0) for s in range(4) for r in range(13) if (h >> (13 * s + r)) & 1)
+            assert hcp <= 11 and all(2 <= x <= 5 for x in lens)
+
+
+def test_trick_source_is_exactly_uniform():
+    """orc_tricks_of (mirror of csrc/score.cuh): digits of an accepted word are uniform on 0..13 and independent; the
+    accept test is Lemire's (x * 14^8 mod 2^32 >= 2^32 mod 14^8)"""
+    import ctypes as C
+    import numpy as np
+    assert (1 << 32) % 14 ** 8 == 1343389184
+    key = (C.c_uint32 * 2)(123, 456)
+    out = (C.c_uint32 * 8)()
+    counts = np.zeros((8, 14), dtype=np.int64)
+    n = 60000
+    for i in range(n):
+        O.lib().orc_tricks_of(key, i, 7, 0, 1, out)
+        for k in range(8):
+            counts[k, out[k]] += 1
+    exp = n / 14
+    assert (abs(counts - exp) < 5 * exp ** 0.5).all()
+    # score tallies: rows sum to n; a pair whose difference can exceed 3999 reports the overflow in `dropped`
+    cs = [O.Contract(7, 4, 2, 2), O.Contract(7, 4, 0, 2)]          # 7NT redoubled, S and N
+    tr, im, dropped = O.score_tally_index(9, 0, 20000, cs, [1, 1], [0, 1])
+    assert tr[0].sum() == 20000 and tr[1].sum() == 20000 and im[0].sum() + dropped[0] == 20000 and dropped[0] > 0
