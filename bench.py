@@ -39,11 +39,11 @@ SEED = 0x6272696467656D63
 #   seat-first sampler  116  profiles/r01_prof_c2_rankfirst_2p28.txt  (3.10e10 thread instructions for a
 #                            2^28-deal launch; 248 before stage A became a rank draw)
 #   full-deal sampler   649  profiles/r01_c2_sample_kernel_v1.txt
-W_INT_BY_MODE = {1: 649, 2: 116}
+W_INT_BY_MODE = {1: 649, 2: 116, 4: 116}
 # DRAM bytes of one 2^28-deal seat-first launch that stores its 10.2 M records (163 MB algorithmic): ncu
 # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_launches_bench_rankfirst.csv (the rest is still in L2 at kernel end)
-TRAFFIC_BYTES_BY_MODE = {1: None, 2: 101_600_000}
-KERNEL_BY_MODE = {1: "sample_kernel<true,false>", 2: "sample_seatfirst_kernel"}
+TRAFFIC_BYTES_BY_MODE = {1: None, 2: 101_600_000, 4: None}
+KERNEL_BY_MODE = {1: "sample_kernel<true,false>", 2: "sample_seatfirst_kernel<false>", 4: "sample_seatfirst_kernel<true>"}
 W_INT_SURVEY = 1400                          # SURVEY 8d's budget for a naive per-card full deal
 INT_PEAK_NOMINAL = 148 * 128 * 1.965e9       # SMs x INT32 lanes x max SM clock
 
@@ -392,7 +392,7 @@ def run_gpu(args):
                        "host_binding_rank0": numa},
             "accepted_per_s": acc_all / (ms * 1e-3),
             "acceptance": acc_all / max(1.0, raw_all),
-            "sampler_mode": {1: "full-deal", 2: "seat-first"}[cons.mode],
+            "sampler_mode": {1: "full-deal", 2: "seat-first", 4: "seat-first, exact class table"}[cons.mode],
             "roofline": {"bound": "int32-issue", "kernel": KERNEL_BY_MODE[cons.mode], "achieved": achieved, "peak": peak,
                          "unit": "Tint-op/s", "frac": achieved / peak if peak else None,
                          "traffic": TRAFFIC_BYTES_BY_MODE[cons.mode] if args.wave == 1 << 28 else None,

@@ -15,6 +15,7 @@ BMC_OK, BMC_E_INVALID, BMC_E_CUDA, BMC_E_BAD_RANGE, BMC_E_PARSE, BMC_E_NOMEM, BM
 TALLY_HCP, TALLY_LEN, TALLY_SHAPE, TALLY_ALL, TALLY_SCORE = 1, 2, 4, 7, 8
 HCP_BINS, LEN_BINS, SHAPE_BINS = 40, 14, 40
 SCORE_CONTRACTS, SCORE_PAIRS = 8, 8
+LANE_MASK = 0x1FFF1FFF1FFF1FFF
 
 
 class BridgeMcError(RuntimeError):
@@ -68,7 +69,7 @@ EXPORTS = [
     "bmc_init", "bmc_shutdown", "bmc_last_error", "bmc_version", "bmc_host_alloc", "bmc_host_free",
     "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_set_jit", "bmc_constraints_jit_ms", "bmc_constraints_mode", "bmc_constraints_primary", "bmc_constraints_primary_hcp",
     "bmc_scheme_create",
-    "bmc_constraints_set_scoring", "bmc_sample_indices", "bmc_sample_indices_dev", "bmc_expand", "bmc_expand_dev", "bmc_sample_multi",
+    "bmc_constraints_set_scoring", "bmc_constraints_primary_acceptance", "bmc_distgen", "bmc_sample_indices", "bmc_sample_indices_dev", "bmc_expand", "bmc_expand_dev", "bmc_sample_multi",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
     "bmc_match_points", "bmc_score_tally", "bmc_hist_base", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
 ]
@@ -114,6 +115,8 @@ def load():
     L.bmc_scheme_destroy.restype = None
     L.bmc_sample.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, C.POINTER(Tallies), C.POINTER(Stats)]
     L.bmc_sample_dev.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, vp, C.POINTER(Stats)]
+    L.bmc_constraints_primary_acceptance.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.bmc_distgen.argtypes = [vp, u64, C.POINTER(SeatSpec), vp, vp, u32, C.POINTER(u32), C.POINTER(u64), vp, vp]
     L.bmc_constraints_set_scoring.argtypes = [vp, C.POINTER(Contract), vp, u32, vp, u32]
     L.bmc_sample_indices.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, C.POINTER(Tallies), C.POINTER(Stats)]
     L.bmc_sample_indices_dev.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, vp, C.POINTER(Stats)]

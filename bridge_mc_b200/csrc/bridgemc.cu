@@ -30,6 +30,7 @@
 #include "seatfirst.cuh"
 #include "reforder.cuh"
 #include "hist.cuh"
+#include "distgen.cuh"
 #include "rules.hpp"
 #include "jit.hpp"
 #include "embedded_src.inc"
@@ -137,13 +138,14 @@ __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_c
 // ---------------------------------------------------------------------------
 // Expansion of index records (bmc_expand): the deal behind an index is a pure function of (seed, index,
 // constraint, dealing mode), so an accepted deal can be shipped as its 32-bit index offset and regenerated on
-// demand.  One thread per offset; mode 1 full deal (free or with fixed hands), 2 seat-first, 3 reference order.
+// demand.  One thread per offset; mode 1 full deal (free or with fixed hands), 2 / 4 seat-first (count classes / exact
+// class table), 3 reference order.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q, int mode,
                                                          const uint32_t *__restrict__ offsets, unsigned long long n, uint4 *__restrict__ out)
 {
     __shared__ __align__(16) LowTabs s_low;
-    if (mode == 2) {
+    if (mode == 2 || mode == 4) {
         for (int i = threadIdx.x; i < (int)(sizeof(LowTabs) / 4); i += THREADS)
             reinterpret_cast<uint32_t *>(&s_low)[i] = reinterpret_cast<const uint32_t *>(&c_lowtabs)[i];
         __syncthreads();
@@ -153,9 +155,10 @@ __global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__
         const unsigned long long idx = a.first + offsets[i];
         Planes pl;
         if (mode == 3) reforder_deal(a, q, idx, true, pl);
-        else if (mode == 2) {
+        else if (mode == 2 || mode == 4) {
             uint32_t m0, m1;
-            sf_primary_hand(a.key, a.cons.sf_tab, a.cons.sf_bmul, s_low, idx, true, m0, m1);
+            if (mode == 4) sf_exact_hand(a.key, a.cons.x, s_low, idx, true, m0, m1);
+            else sf_primary_hand(a.key, a.cons.sf_tab, a.cons.sf_bmul, s_low, idx, true, m0, m1);
             const uint32_t P = a.cons.primary;
             const uint32_t xl = (P & 1u) ? 0xFFFFFFFFu : 0u, xh = (P & 2u) ? 0xFFFFFFFFu : 0u;
             deal_rest39(a.key, a.sf_q0, m0, m1, xl, xh, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
@@ -386,7 +389,12 @@ struct bmc_ctx {
 
 struct ConsTables {              // per-device copies of a constraint's tables
     uint32_t *d_code = nullptr;
-    JitKernel jit[2];            // [0] full-deal kernel, [1] seat-first kernel
+    JitKernel jit[3];            // [0] full-deal kernel, [1] seat-first kernel, [2] seat-first kernel, exact class table
+    // exact class table of the primary seat (mode 4; distgen.cuh)
+    unsigned long long *x_cum = nullptr;
+    uint32_t *x_keys = nullptr, *x_bkt = nullptr;
+    uint32_t x_bmul = 0, x_nbkt = 0;
+    bool x_built = false;
 };
 
 struct bmc_constraints {
@@ -409,7 +417,10 @@ struct bmc_constraints {
     std::string jit_log;
     int mode = 0;                // requested: 0 auto, 1 full deal (deal52), 2 seat-first, 3 reference order
     int resolved = 0;            // 0 = not calibrated yet
-    double stage_a_pass = -1.0;  // measured pass rate of the primary seat's ranges
+    double stage_a_pass = -1.0;  // pass rate of the primary seat (exact: x_weight / C(52,13))
+    uint64_t x_weight = 0;       // hands the primary seat's constraint admits (exact, from the device enumeration)
+    uint64_t x_classes = 0;      // classes (honours x low-card counts) among them
+    bool x_known = false;
     ContractTable score{};       // bmc_constraints_set_scoring
     std::mutex mu, cal_mu;
 };
@@ -749,8 +760,8 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
 
 int bmc_constraints_set_mode(bmc_constraints *c, int mode)
 {
-    if (!c || mode < 0 || mode > 2) return fail(BMC_E_INVALID, "bmc_constraints_set_mode: bad argument (mode 3 is set by bmc_constraints_set_reference_order)");
-    if (mode == 2 && (c->has_fixed || !c->has_cons)) return fail(BMC_E_INVALID, "seat-first mode needs a constrained seat and no fixed hands");
+    if (!c || mode < 0 || mode > 4 || mode == 3) return fail(BMC_E_INVALID, "bmc_constraints_set_mode: bad argument (mode 3 is set by bmc_constraints_set_reference_order)");
+    if ((mode == 2 || mode == 4) && (c->has_fixed || !c->has_cons)) return fail(BMC_E_INVALID, "seat-first modes need a constrained seat and no fixed hands");
     c->mode = mode;
     c->resolved = 0;
     return BMC_OK;
@@ -860,6 +871,9 @@ void bmc_constraints_destroy(bmc_constraints *c)
     for (auto &kv : c->tabs) {
         cudaSetDevice(kv.first);
         if (kv.second.d_code) cudaFree(kv.second.d_code);
+        if (kv.second.x_cum) cudaFree(kv.second.x_cum);
+        if (kv.second.x_keys) cudaFree(kv.second.x_keys);
+        if (kv.second.x_bkt) cudaFree(kv.second.x_bkt);
         for (JitKernel &jk : kv.second.jit)
             if (jk.module) JitApi::get().ModuleUnload(jk.module);
     }
@@ -880,9 +894,9 @@ int bmc_constraints_set_scoring(bmc_constraints *c, const bmc_contract *contract
 }
 
 // ---- NVRTC specialisation of a constraint (jit.hpp) ------------------------------------------------
-static int jit_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *tabs, bool seatfirst)
+static int jit_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *tabs, bool seatfirst, bool exact)
 {
-    JitKernel &jk = tabs->jit[seatfirst ? 1 : 0];      // caller holds c->cal_mu; the ctx's device is current
+    JitKernel &jk = tabs->jit[seatfirst ? (exact ? 2 : 1) : 0];      // caller holds c->cal_mu; the ctx's device is current
     if (jk.func) return BMC_OK;
     JitApi &api = JitApi::get();
     if (!api.ok) return fail(BMC_E_CUDA, "NVRTC specialisation unavailable: " + api.why);
@@ -911,6 +925,7 @@ static int jit_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *tabs, bool se
         "typedef unsigned char uint8_t; typedef signed char int8_t; typedef unsigned short uint16_t; typedef short int16_t;\n"
         "typedef unsigned int uint32_t; typedef int int32_t; typedef unsigned long long uint64_t; typedef long long int64_t;\n"
         "#define BMC_JIT 1\n") + (seatfirst ? "#define BMC_JIT_SEATFIRST 1\n" : "#define BMC_JIT_FULL 1\n") +
+        (exact ? "#define BMC_JIT_EXACT 1\n" : "") +
         "#include \"features.cuh\"\n" + fn + "#include \"kernels.cuh\"\n";
     // 2. compile for sm_100a
     auto t0 = std::chrono::steady_clock::now();
@@ -1025,7 +1040,7 @@ static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
 // ---- sampling -------------------------------------------------------------------
 struct WaveCfg {                 // what is constant over the waves of one call
     ConsDev cons{};
-    bool has_cons = false, seatfirst = false, interp = false;
+    bool has_cons = false, seatfirst = false, exact = false, interp = false;
     const FixDev *fix = nullptr;
     const SeqDev *seq = nullptr;
     const JitKernel *jit = nullptr;
@@ -1079,7 +1094,7 @@ static int launch_wave(bmc_ctx *ctx, const WaveCfg &w, uint64_t first, uint64_t 
                                 : smem_plan(w.seatfirst, w.seatfirst || w.has_cons, w.seatfirst && sf_two_stage(w.cons, jit), w.interp, w.tally_mask);
     const size_t smem = (size_t)plan.words * 4u;
     const void *kernel = w.seq ? (const void *)sample_reforder_kernel
-                       : w.seatfirst ? (const void *)sample_seatfirst_kernel
+                       : w.seatfirst ? (w.exact ? (const void *)sample_seatfirst_kernel<true> : (const void *)sample_seatfirst_kernel<false>)
                        : w.fix ? (w.has_cons ? (const void *)sample_kernel<true, true> : (const void *)sample_kernel<false, true>)
                                : (w.has_cons ? (const void *)sample_kernel<true, false> : (const void *)sample_kernel<false, false>);
     int per_sm;
@@ -1106,7 +1121,8 @@ static int launch_wave(bmc_ctx *ctx, const WaveCfg &w, uint64_t first, uint64_t 
         const CUresult cr = JitApi::get().LaunchKernel(w.jit->func, (unsigned)blocks, 1, 1, THREADS, 1, 1, (unsigned)smem, (CUstream)ctx->stream, params, nullptr);
         if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuLaunchKernel (jit) failed: " + std::to_string((int)cr));
     } else if (w.seq) sample_reforder_kernel<<<blocks, THREADS, smem, ctx->stream>>>(a, *w.seq);
-    else if (w.seatfirst) sample_seatfirst_kernel<<<blocks, THREADS, smem, ctx->stream>>>(a);
+    else if (w.seatfirst && w.exact) sample_seatfirst_kernel<true><<<blocks, THREADS, smem, ctx->stream>>>(a);
+    else if (w.seatfirst) sample_seatfirst_kernel<false><<<blocks, THREADS, smem, ctx->stream>>>(a);
     else if (w.fix) {
         if (w.has_cons) sample_kernel<true, true><<<blocks, THREADS, smem, ctx->stream>>>(a);
         else sample_kernel<false, true><<<blocks, THREADS, smem, ctx->stream>>>(a);
@@ -1116,6 +1132,107 @@ static int launch_wave(bmc_ctx *ctx, const WaveCfg &w, uint64_t first, uint64_t 
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
+    return BMC_OK;
+}
+
+// ---- device distgen: class enumeration (distgen.cuh) -------------------------------------------------------
+struct PatternScan {                     // host copy of pass 1
+    std::vector<unsigned long long> w;   // weight per pattern
+    std::vector<uint32_t> cnt;           // admitted classes per pattern
+    std::vector<uint8_t> flag;           // pattern passes the honour-level tests
+    unsigned long long hcp_pmf[40];
+    unsigned long long len_pmf[4 * 14];
+};
+static int distgen_count(bmc_ctx *ctx, const ClassSpec &cs, PatternScan &ps, bool want_pmf, unsigned long long **keep_w = nullptr,
+                         uint32_t **keep_cnt = nullptr)
+{
+    unsigned long long *d_w = nullptr, *d_pmf = nullptr;
+    uint32_t *d_c = nullptr;
+    uint8_t *d_f = nullptr;
+    cudaError_t e = cudaMalloc(&d_w, DG_PATTERNS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, DG_PATTERNS * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_f, DG_PATTERNS);
+    if (e == cudaSuccess && want_pmf) e = cudaMalloc(&d_pmf, (40 + 56) * sizeof(unsigned long long));
+    if (e == cudaSuccess && want_pmf) e = cudaMemsetAsync(d_pmf, 0, (40 + 56) * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) {
+        distgen_count_kernel<<<DG_PATTERNS, DG_THREADS, 0, ctx->stream>>>(cs, d_w, d_c, d_f, d_pmf, d_pmf ? d_pmf + 40 : nullptr);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    ps.w.resize(DG_PATTERNS); ps.cnt.resize(DG_PATTERNS); ps.flag.resize(DG_PATTERNS);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ps.w.data(), d_w, DG_PATTERNS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ps.cnt.data(), d_c, DG_PATTERNS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ps.flag.data(), d_f, DG_PATTERNS, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && want_pmf) {
+        e = cudaMemcpyAsync(ps.hcp_pmf, d_pmf, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ps.len_pmf, d_pmf + 40, 56 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_f); cudaFree(d_pmf);
+    if (keep_w && e == cudaSuccess) *keep_w = d_w; else cudaFree(d_w);
+    if (keep_cnt && e == cudaSuccess) *keep_cnt = d_c; else cudaFree(d_c);
+    if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("distgen: ") + cudaGetErrorString(e));
+    return BMC_OK;
+}
+
+constexpr uint64_t EXACT_MAX_CLASSES = 1ull << 23;     // all 4 582 640 classes of a 13-card hand fit (55 MB of tables)
+
+// The exact class table of the primary seat on this device.  Always leaves the exact acceptance of the seat in the
+// constraint (x_weight / C(52,13)); *built = false when the table would be too large (or nothing is admitted).
+static int exact_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *t, bool *built)
+{
+    *built = false;
+    if (t->x_built) { *built = true; return BMC_OK; }
+    const uint32_t P = c->dev.primary;
+    ClassSpec cs{};
+    cs.seat = c->dev.seat[P];
+    cs.prog = cs.seat.prog != 0xFFFFFFFFu ? t->d_code + cs.seat.prog : nullptr;
+    for (int s = 0; s < 4; ++s) cs.n_low[s] = 9;
+    cs.hon_avail = 0xFFFFu;
+    cs.hand_size = 13;
+    PatternScan ps;
+    unsigned long long *d_w = nullptr;
+    uint32_t *d_c = nullptr;
+    { int rc = distgen_count(ctx, cs, ps, false, &d_w, &d_c); if (rc) return rc; }
+    // exclusive scans over the 65 536 patterns (host: a control-plane step, once per constraint and device)
+    std::vector<unsigned long long> pcum(DG_PATTERNS);
+    std::vector<uint32_t> poff(DG_PATTERNS);
+    unsigned long long W = 0, K = 0;
+    for (int p = 0; p < DG_PATTERNS; ++p) { pcum[p] = W; poff[p] = (uint32_t)K; W += ps.w[p]; K += ps.cnt[p]; }
+    c->x_weight = W; c->x_classes = K; c->x_known = true;
+    c->stage_a_pass = (double)W / (double)SF_HANDS;
+    if (K == 0 || K > EXACT_MAX_CLASSES) { cudaFree(d_w); cudaFree(d_c); return BMC_OK; }
+    unsigned long long *d_pcum = nullptr;
+    uint32_t *d_poff = nullptr;
+    cudaError_t e = cudaMalloc(&d_pcum, DG_PATTERNS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d_poff, DG_PATTERNS * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&t->x_cum, (K + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&t->x_keys, K * sizeof(uint32_t));
+    // buckets: about two per class, a power of two in [2^8, 2^23]
+    uint32_t nb = 256;
+    while (nb < 2 * K && nb < (1u << 23)) nb <<= 1;
+    const unsigned long long theta = W * SF_S;
+    unsigned long long bm = ((unsigned long long)nb << 32) / ((theta >> 32) + 1ull);
+    const uint32_t bmul = bm > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bm;
+    if (e == cudaSuccess) e = cudaMalloc(&t->x_bkt, ((size_t)nb + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pcum, pcum.data(), DG_PATTERNS * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_poff, poff.data(), DG_PATTERNS * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->x_cum + K, &W, sizeof W, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        distgen_emit_kernel<<<DG_PATTERNS, DG_THREADS, 0, ctx->stream>>>(cs, d_pcum, d_poff, d_c, t->x_keys, t->x_cum);
+        distgen_bucket_kernel<<<(nb + 256) / 256, 256, 0, ctx->stream>>>(t->x_cum, (uint32_t)K, bmul, nb, SF_S, t->x_bkt);
+        ctx->launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_w); cudaFree(d_c); cudaFree(d_pcum); cudaFree(d_poff);
+    if (e != cudaSuccess) {
+        cudaFree(t->x_cum); cudaFree(t->x_keys); cudaFree(t->x_bkt);
+        t->x_cum = nullptr; t->x_keys = nullptr; t->x_bkt = nullptr;
+        return fail(BMC_E_CUDA, std::string("exact class table: ") + cudaGetErrorString(e));
+    }
+    t->x_bmul = bmul; t->x_nbkt = nb; t->x_built = true;
+    *built = true;
     return BMC_OK;
 }
 
@@ -1150,20 +1267,18 @@ static int resolve_cfg(bmc_ctx *ctx, const bmc_constraints *cons, WaveCfg &w)
             return BMC_OK;
         };
         if (cc->resolved == 0) {
+            // The device enumeration (distgen.cuh) gives the primary seat's EXACT acceptance -- no sampling
+            // calibration -- and, when it is small enough, the class table of mode 4.
+            bool built = false;
+            if (cc->mode == 0 || cc->mode == 4) { int rc = exact_build(ctx, cc, w.tabs, &built); if (rc) return rc; }
+            if ((cc->mode == 0 || cc->mode == 4) && cc->x_weight == 0)
+                return fail(BMC_E_BAD_RANGE, "seat " + std::to_string(w.cons.primary) + ": no 13-card hand satisfies its constraint (total weight 0)");
+            if (cc->mode == 4 && !built)
+                return fail(BMC_E_CAPACITY, "mode 4: the primary seat admits " + std::to_string(cc->x_classes) + " classes of hands, more than the table holds");
             if (cc->mode != 0) cc->resolved = cc->mode;
-            else {
-                // the primary seat's RANGES alone: seat-first pays off when most deals die on them
-                ConsDev cal = w.cons;
-                for (int k = 0; k < 4; ++k) {
-                    cal.seat[k].prog = 0xFFFFFFFFu;
-                    if ((uint32_t)k != w.cons.primary) cal.seat[k].active = 0;
-                }
-                int rc = pass_rate(cal, cc->stage_a_pass);
-                if (rc) return rc;
-                cc->resolved = cc->stage_a_pass < 0.30 ? 2 : 1;
-            }
+            else cc->resolved = cc->stage_a_pass >= 0.30 ? 1 : built ? 4 : 2;      // seat-first pays off when most deals die on the primary seat
             cc->dev.b1_mask = 0xFu;
-            if (cc->resolved == 2 && w.cons.n_active >= 3) {
+            if ((cc->resolved == 2 || cc->resolved == 4) && w.cons.n_active >= 3) {
                 // the most selective other seat: tested together with the primary seat by the compiled-rule kernel
                 double best = 2.0;
                 int second = -1;
@@ -1182,7 +1297,19 @@ static int resolve_cfg(bmc_ctx *ctx, const bmc_constraints *cons, WaveCfg &w)
             }
         }
         w.cons.b1_mask = cc->dev.b1_mask;
-        w.seatfirst = cc->resolved == 2;
+        w.seatfirst = cc->resolved == 2 || cc->resolved == 4;
+        w.exact = cc->resolved == 4;
+        if (w.exact) {
+            bool built = false;
+            int rc = exact_build(ctx, cc, w.tabs, &built);             // per device; a no-op once built
+            if (rc) return rc;
+            if (!built) return fail(BMC_E_CAPACITY, "mode 4: class table unavailable");
+            w.cons.x.cum = w.tabs->x_cum; w.cons.x.keys = w.tabs->x_keys; w.cons.x.bkt = w.tabs->x_bkt;
+            w.cons.x.bmul = w.tabs->x_bmul; w.cons.x.n_bkt = w.tabs->x_nbkt;
+            w.cons.sf_theta = cc->x_weight * SF_S;
+            // the primary seat is admitted by construction: its program never runs in the sampling kernel
+            if (w.cons.seat[w.cons.primary].prog != 0xFFFFFFFFu && w.cons.n_prog) w.cons.n_prog--;
+        }
     }
     w.interp = w.has_cons && w.cons.n_prog != 0u;
     if (cons && cons->has_rules && w.has_cons && !w.fix && !w.seq) {
@@ -1192,12 +1319,12 @@ static int resolve_cfg(bmc_ctx *ctx, const bmc_constraints *cons, WaveCfg &w)
         // its rule programs -- about what the NVRTC build costs.  Results are bit-identical either way.
         const bool want = cc->jit == 1 || (cc->jit == 2 && cc->interp_ms > 1000.0 && w.cons.n_prog != 0u && JitApi::get().ok);
         if (want) {
-            int rc = jit_build(ctx, cc, w.tabs, w.seatfirst);
+            int rc = jit_build(ctx, cc, w.tabs, w.seatfirst, w.exact);
             if (rc) {
                 if (cc->jit == 1) return rc;
                 cc->jit = 0;                           // auto: the build failed once -- keep interpreting
             } else {
-                w.jit = &w.tabs->jit[w.seatfirst ? 1 : 0];
+                w.jit = &w.tabs->jit[w.seatfirst ? (w.exact ? 2 : 1) : 0];
                 w.interp = false;
             }
         }
@@ -1450,7 +1577,7 @@ static int expand_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         const uint32_t p0 = cap4[0], p1 = p0 + cap4[1], p2 = p1 + cap4[2];
         a.sf_q0 = (128u - p0) | ((128u - p1) << 8) | ((128u - p2) << 16);
     }
-    const int mode = w.seq ? 3 : w.seatfirst ? 2 : 1;
+    const int mode = w.seq ? 3 : w.seatfirst ? (w.exact ? 4 : 2) : 1;
     static const SeqDev no_seq{};
     uint64_t want = (n + THREADS - 1) / THREADS;
     const unsigned blocks = (unsigned)(want < (uint64_t)ctx->sms * 8 ? want : (uint64_t)ctx->sms * 8);
@@ -1632,6 +1759,76 @@ int bmc_sample_multi(const int *devices, int n_devices, const bmc_constraints *c
         s.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         *stats = s;
     }
+    return BMC_OK;
+}
+
+// ---- device distgen (bridge.cl:1018-1045) --------------------------------------------------------------------
+int bmc_distgen(bmc_ctx *ctx, uint64_t cards, const bmc_seat_spec *spec, uint16_t *patterns, uint64_t *weights, uint32_t cap,
+                uint32_t *n_patterns, uint64_t *total_weight, uint64_t *hcp_pmf, uint64_t *len_pmf)
+{
+    if (!ctx || !n_patterns) return fail(BMC_E_INVALID, "bmc_distgen: NULL argument");
+    *n_patterns = 0;
+    if (cards & ~BMC_LANE_MASK) return fail(BMC_E_INVALID, "bmc_distgen: cards is not a lane mask");
+    // the range spec as distgen reads it: :hcp (lo hi); suit (lo hi (shcp-lo shcp-hi)); an open upper length
+    // bound is the number of LOW cards left in the suit (bridge.cl:1000-1001 `(or max supply)`)
+    SeatRanges r;
+    ClassSpec cs{};
+    cs.hon_avail = 0;
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t lane = (uint32_t)(cards >> (16 * s)) & 0x1FFFu;
+        cs.n_low[s] = (uint32_t)__builtin_popcount(lane & 0x1FFu);
+        for (int h = 0; h < 4; ++h)
+            if ((lane >> (9 + h)) & 1u) cs.hon_avail |= 1u << (15 - (4 * s + h));
+    }
+    cs.hand_size = 13;
+    if (spec) {
+        if (spec->hcp[0] >= 0) r.lo[F_HCP] = spec->hcp[0];
+        if (spec->hcp[1] >= 0) r.hi[F_HCP] = spec->hcp[1];
+        for (int s = 0; s < 4; ++s) {
+            if (spec->len[s][0] >= 0) r.lo[F_C + s] = spec->len[s][0];
+            r.hi[F_C + s] = spec->len[s][1] >= 0 ? spec->len[s][1] : (int)cs.n_low[s];
+            if (spec->suit_hcp[s][0] >= 0) r.lo[F_CP + s] = spec->suit_hcp[s][0];
+            if (spec->suit_hcp[s][1] >= 0) r.hi[F_CP + s] = spec->suit_hcp[s][1];
+        }
+    } else
+        for (int s = 0; s < 4; ++s) r.hi[F_C + s] = (int)cs.n_low[s];
+    for (int s = 0; s < 4; ++s) { if (r.hi[F_C + s] > 13) r.hi[F_C + s] = 13; if (r.hi[F_CP + s] > 10) r.hi[F_CP + s] = 10; }
+    if (r.hi[F_HCP] > 40) r.hi[F_HCP] = 40;
+    SeatC sc{};
+    const bool empty = r.empty();                       // an empty range admits no pattern at all
+    if (!empty) ranges_to_seatc(r, sc);
+    sc.prog = 0xFFFFFFFFu; sc.active = 1;
+    cs.seat = sc;
+    cs.prog = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    PatternScan ps;
+    if (empty) { ps.w.assign(DG_PATTERNS, 0); ps.cnt.assign(DG_PATTERNS, 0); ps.flag.assign(DG_PATTERNS, 0); memset(ps.hcp_pmf, 0, sizeof ps.hcp_pmf); memset(ps.len_pmf, 0, sizeof ps.len_pmf); }
+    else { int rc = distgen_count(ctx, cs, ps, hcp_pmf || len_pmf); if (rc) return rc; }
+    uint32_t n = 0;
+    uint64_t total = 0;
+    // rows in the generator's order: binary counting, club jack most significant = ascending pattern value.
+    // bridge.cl:955-957: a deck without any honour has no pattern at all (hc-permuts returns nil).
+    for (uint32_t p = 0; p < DG_PATTERNS && cs.hon_avail; ++p) {
+        if (!ps.flag[p]) continue;
+        if (n < cap) { if (patterns) patterns[n] = (uint16_t)p; if (weights) weights[n] = ps.w[p]; }
+        total += ps.w[p];
+        ++n;
+    }
+    *n_patterns = n;
+    if (total_weight) *total_weight = total;
+    if (hcp_pmf) for (int i = 0; i < 38; ++i) hcp_pmf[i] = empty ? 0 : ps.hcp_pmf[i];
+    if (len_pmf) for (int i = 0; i < 56; ++i) len_pmf[i] = empty ? 0 : ps.len_pmf[i];
+    if (n > cap && (patterns || weights)) return fail(BMC_E_CAPACITY, "bmc_distgen: " + std::to_string(n) + " patterns, capacity " + std::to_string(cap));
+    return BMC_OK;
+}
+
+int bmc_constraints_primary_acceptance(const bmc_constraints *c, uint64_t *hands, uint64_t *classes)
+{
+    if (!c || !hands) return fail(BMC_E_INVALID, "bmc_constraints_primary_acceptance: NULL argument");
+    if (!c->x_known) return fail(BMC_E_INVALID, "bmc_constraints_primary_acceptance: not enumerated yet (first sampling call in mode 0 or 4)");
+    *hands = c->x_weight;
+    if (classes) *classes = c->x_classes;
     return BMC_OK;
 }
 

@@ -33,8 +33,9 @@ struct ConsDev {
     uint32_t sf_bmul;        // seat-first stage A2: bucket of a survivor = umulhi(u_hi, sf_bmul) (seatfirst.cuh)
     const uint32_t *code;    // device pointer, programs of all seats
     const uint4 *sf_tab;     // seat-first stage A1: class table of the primary seat (seatfirst.cuh), in the code buffer
-    unsigned long long sf_theta;   // u < sf_theta: the honour holding has an admissible HCP
+    unsigned long long sf_theta;   // u < sf_theta: the honour holding has an admissible HCP (mode 4: the hand satisfies the seat)
     unsigned long long sf_void;    // u >= sf_void = S * C(52,13) voids the index (probability 1.2e-8)
+    ExactTab x;                    // mode 4: exact class table of the primary seat (distgen.cuh)
 };
 
 // shared-memory histogram (per copy): hcp[4][40] | len[4][4][16] | shape[4][40]
@@ -394,6 +395,9 @@ __host__ __device__ inline bool sf_two_stage(const ConsDev &c, bool jit)
     return jit ? (~c.b1_mask & 0xFu) != 0u : c.n_prog != 0u;
 }
 
+// EXACT = mode 4: stage A1 accepts exactly the primary seat's admissible hands (class table), stage A2 unranks
+// without testing and stage B leaves the primary seat alone.
+template <bool EXACT>
 __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
 {
     if (wave_cancelled(a)) return;
@@ -419,11 +423,12 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
     uint32_t *q3i = smem + sp.q3i + warp * QCAP;                                    //               and their index - a.first
     uint32_t *feat = smem + sp.feat + warp * FEAT_SCRATCH_WORDS;
     unsigned h3 = 0, t3 = 0;
+    const uint32_t seats = EXACT ? 0xFu & ~(1u << a.cons.primary) : 0xFu;      // mode 4: the primary seat is admitted by construction
 #ifdef BMC_JIT
     const uint32_t rest = ~a.cons.b1_mask & 0xFu;
-    const uint32_t what1 = TEST_SEATS(a.cons.b1_mask) | TEST_RANGES | TEST_PROGS, what2 = TEST_SEATS(rest) | TEST_RANGES | TEST_PROGS;
+    const uint32_t what1 = TEST_SEATS(a.cons.b1_mask & seats) | TEST_RANGES | TEST_PROGS, what2 = TEST_SEATS(rest & seats) | TEST_RANGES | TEST_PROGS;
 #else
-    const uint32_t what1 = TEST_SEATS(0xFu) | TEST_RANGES, what2 = TEST_SEATS(0xFu) | TEST_PROGS;
+    const uint32_t what1 = TEST_SEATS(seats) | TEST_RANGES, what2 = TEST_SEATS(seats) | TEST_PROGS;
 #endif
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -444,7 +449,7 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         const bool voided = deal_rest39(a.key, a.sf_q0, r.x, r.y, xl, xh, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
         n_void += (active && voided) ? 1u : 0u;
         if (!two_stage) {
-            stage_b(a, pl, r.z, active && !voided, tm, lane, feat, TEST_ALL);
+            stage_b(a, pl, r.z, active && !voided, tm, lane, feat, TEST_SEATS(seats) | TEST_RANGES | TEST_PROGS);
             return;
         }
         const bool ok = seats_pass(a, pl, what1, feat, lane) && active && !voided;
@@ -475,9 +480,12 @@ __device__ __forceinline__ void sample_seatfirst_body(const SampleArgs &a)
         const bool active = lane < count;
         const unsigned long long idx = a.first + off;
         uint32_t m0, m1;
-        sf_primary_hand(a.key, a.cons.sf_tab, a.cons.sf_bmul, s_low, active ? idx : 0ull, active, m0, m1);
-        const Feat f = hand_features(m0, m1);
-        const bool ok = active && seat_ranges_ok(c, f);
+        bool ok = active;
+        if (EXACT) sf_exact_hand(a.key, a.cons.x, s_low, active ? idx : 0ull, active, m0, m1);
+        else {
+            sf_primary_hand(a.key, a.cons.sf_tab, a.cons.sf_bmul, s_low, active ? idx : 0ull, active, m0, m1);
+            ok = ok && seat_ranges_ok(c, hand_features(m0, m1));
+        }
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
         if (bal) {
             if (ok) q2[(t2 + __popc(bal & ((1u << lane) - 1u))) % QCAP] = make_uint4(m0, m1, off, 0u);
@@ -593,9 +601,10 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const __grid_constant__
 {
     sample_body<HAS_CONS, FIXED>(a);
 }
+template <bool EXACT>
 __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) sample_seatfirst_kernel(const __grid_constant__ SampleArgs a)
 {
-    sample_seatfirst_body(a);
+    sample_seatfirst_body<EXACT>(a);
 }
 #else
 #ifdef BMC_JIT_FULL
@@ -607,7 +616,11 @@ extern "C" __global__ void __launch_bounds__(THREADS) bmc_jit_sample_full(const 
 #ifdef BMC_JIT_SEATFIRST
 extern "C" __global__ void __launch_bounds__(THREADS, SF_MIN_BLOCKS) bmc_jit_sample_seatfirst(const __grid_constant__ SampleArgs a)
 {
-    sample_seatfirst_body(a);
+#ifdef BMC_JIT_EXACT
+    sample_seatfirst_body<true>(a);
+#else
+    sample_seatfirst_body<false>(a);
+#endif
 }
 #endif
 #endif

@@ -221,6 +221,57 @@ __device__ __forceinline__ void sf_primary_hand(const PhiloxKey &key, const uint
     m1 |= ((H & 0xF00u) << 1) | ((H & 0xF000u) << 13);
 }
 
+// ---- stage A, exact form (mode 4) --------------------------------------------------------------------
+// The class table built by distgen.cuh lists every class of hands the primary seat's constraint admits --
+// (honours exactly, low-card counts per suit) -- with the number of hands before it.  The admitted hands
+// occupy the ranks [0, W) of the 64-bit uniform's scale, so stage A1's one compare (u < W S) accepts exactly
+// the indices whose primary hand satisfies the seat, and stage A2 only unranks: rank R = u / S, class by a
+// bucket index + short binary search on the cumulative counts, then r = R - cum is split into one subset
+// index per suit (mixed radix over C(9, l_s)).  Every hand keeps its S preimages in u: exactly uniform.
+struct ExactTab {
+    const unsigned long long *cum;    // [n_cls + 1] hands before class i
+    const uint32_t *keys;             // [n_cls] honours (bit 4 s + level) | l_c << 16 | l_d << 20 | l_h << 24 | l_s << 28
+    const uint32_t *bkt;              // [n_bkt + 1] class of the smallest u of bucket j = umulhi(u_hi, bmul)
+    uint32_t bmul, n_bkt;
+};
+
+__device__ __forceinline__ void sf_exact_hand(const PhiloxKey &key, const ExactTab &x, const LowTabs &T, unsigned long long idx,
+                                              bool active, uint32_t &m0, uint32_t &m1)
+{
+    uint32_t wh[4], wl[4];
+    philox4x32_10(key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK, wh);
+    philox4x32_10(key, (uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, STREAM_SEATFIRST_RANK_LO, wl);
+    const uint32_t j = (uint32_t)idx & 3u;
+    uint32_t u_hi = j < 2u ? (j == 0u ? wh[0] : wh[1]) : (j == 2u ? wh[2] : wh[3]);
+    uint32_t u_lo = j < 2u ? (j == 0u ? wl[0] : wl[1]) : (j == 2u ? wl[2] : wl[3]);
+    if (!active) { u_hi = 0u; u_lo = 0u; }
+    const unsigned long long u = ((unsigned long long)u_hi << 32) | u_lo;
+    unsigned long long R = sf_mulhi64(u, SF_S_RECIP);          // floor(u / S) or one less (tests/unrank_selftest.cu)
+    unsigned long long rem = u - R * SF_S;
+    if (rem >= SF_S) { rem -= SF_S; ++R; }
+    if (rem >= SF_S) { rem -= SF_S; ++R; }
+    const uint32_t b = min(sf_mulhi32(u_hi, x.bmul), x.n_bkt - 1u);
+    uint32_t lo = __ldg(x.bkt + b), hi = __ldg(x.bkt + b + 1u);
+    while (lo < hi) {                                           // largest class with cum <= R
+        const uint32_t mid = (lo + hi + 1u) >> 1;
+        if (__ldg(x.cum + mid) <= R) lo = mid; else hi = mid - 1u;
+    }
+    const uint32_t k = __ldg(x.keys + lo);
+    uint32_t r = (uint32_t)(R - __ldg(x.cum + lo));             // < prod C(9, l_s) <= 126^4 < 2^32
+    uint32_t sub[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t l = min((k >> (16 + 4 * s)) & 15u, 9u);
+        const uint4 e = *reinterpret_cast<const uint4 *>(T.c9[l]);
+        uint32_t q = sf_mulhi32(r, e.y), t = r - q * e.x;       // r = q C(9,l) + t
+        if (t >= e.x) { t -= e.x; ++q; }
+        sub[s] = T.subset9[(e.z + t) & 511u];
+        r = q;
+    }
+    m0 = sub[0] | (sub[1] << 16) | ((k & 0xFu) << 9) | ((k & 0xF0u) << 21);
+    m1 = sub[2] | (sub[3] << 16) | ((k & 0xF00u) << 1) | ((k & 0xF000u) << 13);
+}
+
 // Lemire thresholds of deal_fixed's words for 39 free cards (4 digits per word)
 __host__ __device__ constexpr uint32_t thresh39(int w)
 {

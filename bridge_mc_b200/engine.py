@@ -70,7 +70,7 @@ class Constraints:
         self._h = C.c_void_p()
         check(L.bmc_constraints_create(arr, rarr, C.byref(self._h)))
 
-    MODE_AUTO, MODE_FULL, MODE_SEAT_FIRST, MODE_REFERENCE_ORDER = 0, 1, 2, 3
+    MODE_AUTO, MODE_FULL, MODE_SEAT_FIRST, MODE_REFERENCE_ORDER, MODE_SEAT_FIRST_EXACT = 0, 1, 2, 3, 4
 
     def set_mode(self, mode: int):
         """bmc_constraints_set_mode: 0 auto, 1 full deal, 2 seat-first (see bridgemc.h)."""
@@ -118,6 +118,14 @@ class Constraints:
         lo, hi = C.c_int32(), C.c_int32()
         check(_lib.load().bmc_constraints_primary_hcp(self._h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    @property
+    def primary_acceptance(self):
+        """(hands, classes): the exact number of 13-card hands (of C(52,13)) the primary seat's constraint admits and the
+        classes they fall into -- known after the first sampling call in mode 0 / 4 (device enumeration)."""
+        hands, classes = C.c_uint64(), C.c_uint64()
+        check(_lib.load().bmc_constraints_primary_acceptance(self._h, C.byref(hands), C.byref(classes)))
+        return hands.value, classes.value
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -333,6 +341,22 @@ class Engine:
         check(self._L.bmc_hist_base(self._h, rec.ctypes.data if rec.shape[0] else None, rec.shape[0], marr, k,
                                     tuples.ctypes.data, counts.ctypes.data, cap, C.byref(nu)))
         return [[[int(x) for x in tuples[i]], int(counts[i])] for i in range(nu.value)]
+
+    # ---- distgen on the device --------------------------------------------------------
+    def distgen(self, spec=None, cards: int = _lib.LANE_MASK, cap: int = 65536):
+        """bmc_distgen: the reference's exact enumerator (bridge.cl:921-1045) for one range spec (seat_spec / dict / None)
+        over the deck `cards` (lane mask).  Returns dict(patterns uint16[n], weights uint64[n], total, hcp_pmf[38],
+        len_pmf[4,14]); pattern bit 15 = club J ... bit 0 = spade A."""
+        if isinstance(spec, dict):
+            spec = seat_spec(**{kk.lower().lstrip(":"): vv for kk, vv in spec.items()})
+        pats = np.zeros(cap, dtype=np.uint16)
+        wts = np.zeros(cap, dtype=np.uint64)
+        hcp = np.zeros(38, dtype=np.uint64)
+        lens = np.zeros((4, 14), dtype=np.uint64)
+        n, total = C.c_uint32(), C.c_uint64()
+        check(self._L.bmc_distgen(self._h, cards, C.byref(spec) if spec is not None else None, pats.ctypes.data, wts.ctypes.data,
+                                  cap, C.byref(n), C.byref(total), hcp.ctypes.data, lens.ctypes.data))
+        return {"patterns": pats[:n.value], "weights": wts[:n.value], "total": total.value, "hcp_pmf": hcp, "len_pmf": lens}
 
     # ---- measurement --------------------------------------------------------------
     def int_peak(self):

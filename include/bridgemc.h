@@ -153,8 +153,13 @@ void bmc_constraints_destroy(bmc_constraints *c);
  *   2 seat-first  the primary (most selective) seat's honour holding (drawn by rank, holdings with
  *                 an admissible HCP first: one compare per raw index), then its low cards, then
  *                 the other three hands -- each stage only for survivors of the previous one
- *   0 auto        (default) calibrates the primary seat's pass rate on 2^16 deals at the
- *                 first sampling call and picks 2 when it is below 0.30.
+ *   4 seat-first, exact: the device enumerates every CLASS of hands (honours exactly, low-card counts per
+ *                 suit -- the reference's distgen enumeration, bridge.cl:921-1045) the primary seat's ranges
+ *                 AND rule form admit; the admitted hands come first in the rank order, so the one compare
+ *                 per raw index accepts exactly the indices whose primary hand satisfies the seat, and the
+ *                 survivors are unranked without any further test (a 13-card hand has 4 582 640 classes at most).
+ *   0 auto        (default) at the first sampling call the enumeration gives the primary seat's EXACT
+ *                 acceptance: 1 when it is 0.30 or more, else 4.
  * bmc_constraints_mode returns the resolved mode (0 before the first call),
  * bmc_constraints_primary the seat tested first, bmc_constraints_primary_hcp the HCP window of
  * that seat (its range after the rule form's ranges were absorbed) that stage A1 of mode 2 orders
@@ -190,6 +195,9 @@ int  bmc_constraints_primary(const bmc_constraints *c);
 int  bmc_constraints_set_scoring(bmc_constraints *c, const bmc_contract *contracts, const uint8_t *vulnerable,
                                  uint32_t n_contracts, const uint8_t *pairs, uint32_t n_pairs);
 int  bmc_constraints_primary_hcp(const bmc_constraints *c, int32_t *lo, int32_t *hi);
+/* After the first sampling call in mode 0 / 4: the exact number of 13-card hands (of C(52,13) = 635 013 559 600) that
+ * satisfy the primary seat's ranges and rule form, and the number of classes they fall into. */
+int  bmc_constraints_primary_acceptance(const bmc_constraints *c, uint64_t *hands, uint64_t *classes);
 
 /* A rule table as printed by Lisp: "(((2 C) . FORM) ((2 NT) . FORM) ...)" --
  * `openings`, (nt-responses n), 2C-responses, (basic-responses bid) ...
@@ -252,6 +260,18 @@ int bmc_expand_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uin
 int bmc_sample_multi(const int *devices, int n_devices, const bmc_constraints *cons, uint64_t seed,
                      uint64_t first_index, uint64_t n_raw, uint64_t n_accept_target, uint64_t wave,
                      uint32_t tally_mask, bmc_record *records, uint64_t cap, bmc_tallies *tallies, bmc_stats *stats);
+
+/* ---- distgen: the reference's exact enumerator on the device (bridge.cl:921-1045) -----------------------------
+ * (make-instance 'distgen :cards CARDS :hcp .. :c .. :d .. :h .. :s ..) followed by `next` until exhausted: the
+ * (weight pattern) rows in the generator's order.  cards = lane mask of the deck dealt from (BMC_LANE_MASK = all 52);
+ * spec: hcp / len / suit_hcp ranges as distgen reads them (-1 = nil; fixed, losers ignored; an open upper length
+ * bound means the number of LOW cards left in the suit, bridge.cl:1000-1001).  patterns[i]: bit 15 = club J, 14 =
+ * club Q ... bit 0 = spade A (the reference's 16-element 0/1 list read as a binary number); weights[i] = number of
+ * hands with exactly those honours.  Every pattern that passes the honour-level tests is a row, also with weight 0.
+ * total_weight = the generator's total-weight; hcp_pmf[38] / len_pmf[4][14] (may be NULL) = hands by HCP / by suit
+ * length: the exact distribution of one constrained hand.  patterns / weights may be NULL (count only). */
+int bmc_distgen(bmc_ctx *ctx, uint64_t cards, const bmc_seat_spec *spec, uint16_t *patterns, uint64_t *weights,
+                uint32_t cap, uint32_t *n_patterns, uint64_t *total_weight, uint64_t *hcp_pmf, uint64_t *len_pmf);
 
 /* ---- filter / features on given deals: assess-hand, balanced?, test-bid,
  * choose-bid (bidding.cl:33-46,111-112,146-150) over a deal set ---------------- */

@@ -1224,3 +1224,107 @@ ORC_API int orc_ref_build_batch(const uint64_t *consts, int n_consts, const orc_
     free(root_w);
     return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* CPU mirror of the seat-first sampler's EXACT form (mode 4)          */
+/* ------------------------------------------------------------------ */
+/* The primary seat's hands are grouped into CLASSES -- the honours exactly (pattern p: bit 15 = club J, 14 = club Q
+ * ... bit 0 = spade A, the order of hc-permuts, bridge.cl:926-957) and the number of low cards (2..10) per suit
+ * (l_c l_d l_h l_s) -- like distgen's enumeration (bridge.cl:990-1045) over the full deck.  Classes run in ascending
+ * (p, l_c, l_d, l_h); a class has prod C(9, l_s) hands.  The classes whose features satisfy the seat are the table;
+ * the uniform u of an index (as in orc_gpu_seatfirst_hand) has rank R = u / S; the index passes stage A1 iff
+ * R < W = hands in the table; then class = the one with cum <= R < cum + weight, r = R - cum, and suit by suit
+ * (clubs first) t = r mod C(9, l), r = r / C(9, l): the low cards are the t-th l-subset of the nine in numeric order. */
+typedef struct { uint64_t *cum; uint32_t *pat; uint8_t (*l)[4]; uint32_t n; uint64_t W; } orc_xtab;
+
+/* pred: kind 0 = ranges only; 1 = ranges AND test-rule(scheme, k); 2 = ranges AND choose-bid(scheme) == k.
+ * lo / hi: inclusive ranges over the 11 features (lens, power, hcp, losers, balanced). */
+ORC_API orc_xtab *orc_xtab_build(int kind, int scheme, int k, const int lo[11], const int hi[11])
+{
+    orc_xtab *t = (orc_xtab *)calloc(1, sizeof *t);
+    size_t capn = 1 << 16;
+    t->cum = (uint64_t *)malloc(capn * sizeof(uint64_t));
+    t->pat = (uint32_t *)malloc(capn * sizeof(uint32_t));
+    t->l = (uint8_t (*)[4])malloc(capn * 4);
+    for (uint32_t p = 0; p < 65536; ++p) {
+        uint16_t hon[4];
+        int b = 0, hcp = 0;
+        for (int s = 0; s < 4; ++s) {
+            hon[s] = 0;
+            for (int h = 0; h < 4; ++h) if (p >> (15 - (4 * s + h)) & 1) { hon[s] |= (uint16_t)(1u << (9 + h)); ++b; hcp += h + 1; }
+        }
+        if (hcp < lo[8] || hcp > hi[8]) continue;                       /* every class of the pattern fails the HCP range */
+        for (int l0 = 0; l0 <= 9; ++l0) for (int l1 = 0; l1 <= 9; ++l1) for (int l2 = 0; l2 <= 9; ++l2) {
+            const int l3 = 13 - b - l0 - l1 - l2;
+            if (l3 < 0 || l3 > 9) continue;
+            const int lv[4] = { l0, l1, l2, l3 };
+            uint16_t suits[4];
+            int f[11], ok = 1;
+            for (int s = 0; s < 4; ++s) suits[s] = (uint16_t)(hon[s] | ((1u << lv[s]) - 1u));
+            orc_assess(suits, f);
+            for (int i = 0; i < 11 && ok; ++i) ok = f[i] >= lo[i] && f[i] <= hi[i];
+            if (ok && kind == 1) ok = orc_test_rule(scheme, k, f);
+            if (ok && kind == 2) {
+                int first = -1, n = orc_scheme_size(scheme);
+                for (int j = 0; j < n && first < 0; ++j) if (orc_test_rule(scheme, j, f)) first = j;
+                ok = first == k;
+            }
+            if (!ok) continue;
+            if (t->n == capn) {
+                capn *= 2;
+                t->cum = (uint64_t *)realloc(t->cum, capn * sizeof(uint64_t));
+                t->pat = (uint32_t *)realloc(t->pat, capn * sizeof(uint32_t));
+                t->l = (uint8_t (*)[4])realloc(t->l, capn * 4);
+            }
+            t->cum[t->n] = t->W;
+            t->pat[t->n] = p;
+            for (int s = 0; s < 4; ++s) t->l[t->n][s] = (uint8_t)lv[s];
+            t->W += binom_small(9, l0) * binom_small(9, l1) * binom_small(9, l2) * binom_small(9, l3);
+            ++t->n;
+        }
+    }
+    return t;
+}
+ORC_API void orc_xtab_free(orc_xtab *t) { if (t) { free(t->cum); free(t->pat); free(t->l); free(t); } }
+ORC_API uint64_t orc_xtab_weight(const orc_xtab *t) { return t->W; }
+ORC_API uint32_t orc_xtab_classes(const orc_xtab *t) { return t->n; }
+
+/* bit 0 = void (u >= S C(52,13)), bit 2 = void in stage B, bit 3 = the index passes stage A1 (R < W) */
+ORC_API int orc_gpu_deal_exact(const orc_xtab *t, uint64_t seed, uint64_t index, int primary, uint64_t *lo_plane, uint64_t *hi_plane)
+{
+    const uint64_t N = 635013559600ull;
+    const uint64_t S = (uint64_t)((((unsigned __int128)1) << 64) / N);
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t wh[4], wl[4];
+    uint64_t call = index >> 2;
+    uint32_t ch[4] = { (uint32_t)call, (uint32_t)(call >> 32), 0, 4 }, cl[4] = { (uint32_t)call, (uint32_t)(call >> 32), 0, 5 };
+    orc_philox4x32_10(ch, key, wh);
+    orc_philox4x32_10(cl, key, wl);
+    const int j = (int)(index & 3);
+    const uint64_t u = ((uint64_t)wh[j] << 32) | wl[j];
+    *lo_plane = 0; *hi_plane = 0;
+    if (u >= N * S) return 1;
+    const uint64_t R = u / S;
+    if (R >= t->W) return 0;
+    uint32_t a = 0, b = t->n - 1;
+    while (a < b) { uint32_t mid = (a + b + 1) / 2; if (t->cum[mid] <= R) a = mid; else b = mid - 1; }
+    uint64_t r = R - t->cum[a], hand = 0;
+    for (int s = 0; s < 4; ++s) {
+        const int l = t->l[a][s];
+        const uint64_t c = binom_small(9, l), tt = r % c;
+        r /= c;
+        uint64_t seen = 0;
+        for (unsigned v = 0; v < 512; ++v)
+            if (__builtin_popcount(v) == l && seen++ == tt) { hand |= (uint64_t)v << (16 * s); break; }
+        for (int h = 0; h < 4; ++h) if (t->pat[a] >> (15 - (4 * s + h)) & 1) hand |= 1ull << (16 * s + 9 + h);
+    }
+    uint64_t fixed[4] = {0, 0, 0, 0};
+    fixed[primary] = hand;
+    const int vb = gpu_deal_fixed_stream(seed, index, fixed, 3, lo_plane, hi_plane);
+    return (vb << 2) | 8;
+}
+ORC_API void orc_gpu_deal_exact_batch(const orc_xtab *t, uint64_t seed, uint64_t first, uint64_t n, int primary, uint64_t *rec, uint8_t *flags)
+{
+    for (uint64_t i = 0; i < n; ++i)
+        flags[i] = (uint8_t)orc_gpu_deal_exact(t, seed, first + i, primary, &rec[2 * i], &rec[2 * i + 1]);
+}

@@ -187,6 +187,16 @@ def lib():
     L.orc_infer_distgen_params.argtypes = [(C.c_int * 5) * 4, C.POINTER(Def), C.POINTER(Def), C.c_int, C.POINTER(Def)]
     L.orc_ref_build_batch.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(Def), C.c_int, C.c_uint64, C.c_uint64, C.c_int,
                                       C.c_void_p, C.c_void_p]
+    L.orc_xtab_build.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int * 11, C.c_int * 11]
+    L.orc_xtab_build.restype = C.c_void_p
+    L.orc_xtab_free.argtypes = [C.c_void_p]
+    L.orc_xtab_free.restype = None
+    L.orc_xtab_weight.argtypes = [C.c_void_p]
+    L.orc_xtab_weight.restype = C.c_uint64
+    L.orc_xtab_classes.argtypes = [C.c_void_p]
+    L.orc_xtab_classes.restype = C.c_uint32
+    L.orc_gpu_deal_exact_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_gpu_deal_exact_batch.restype = None
     _LIB = L
     return L
 
@@ -367,3 +377,41 @@ def mask52_to_lanes64(m52: np.ndarray) -> np.ndarray:
     for s in range(4):
         out |= ((m >> np.uint64(13 * s)) & np.uint64(0x1FFF)) << np.uint64(16 * s)
     return out
+
+
+class ExactTable:
+    """CPU mirror of the sampler's exact class table (mode 4) for a primary seat whose constraint is: inclusive ranges
+    over the 11 features (dict: lens / power as 4-lists of (lo, hi), hcp, losers, balanced as (lo, hi)), optionally AND
+    test-rule (kind 1) or choose-bid == k (kind 2) over one of the oracle's schemes."""
+
+    def __init__(self, ranges=None, kind=0, scheme=0, k=0):
+        lo, hi = [0] * 11, [13, 13, 13, 13, 10, 10, 10, 10, 37, 12, 1]
+        ranges = ranges or {}
+        for i, key in enumerate(("lens", "power")):
+            for s, r in enumerate(ranges.get(key, [None] * 4)):
+                if r is not None:
+                    lo[4 * i + s], hi[4 * i + s] = r
+        for i, key in ((8, "hcp"), (9, "losers"), (10, "balanced")):
+            if ranges.get(key) is not None:
+                lo[i], hi[i] = ranges[key]
+        self._t = lib().orc_xtab_build(kind, scheme, k, (C.c_int * 11)(*lo), (C.c_int * 11)(*hi))
+
+    def __del__(self):
+        if getattr(self, "_t", None):
+            lib().orc_xtab_free(self._t)
+            self._t = None
+
+    @property
+    def weight(self):
+        return lib().orc_xtab_weight(self._t)
+
+    @property
+    def classes(self):
+        return lib().orc_xtab_classes(self._t)
+
+    def deal_batch(self, seed: int, first: int, n: int, primary: int):
+        """(records, flags): flags bit 0 = void in A1, bit 2 = void in B, bit 3 = the index passes stage A1"""
+        rec = np.empty((n, 2), dtype=np.uint64)
+        flags = np.empty(n, dtype=np.uint8)
+        lib().orc_gpu_deal_exact_batch(self._t, seed, first, n, primary, rec.ctypes.data, flags.ctypes.data)
+        return rec, flags

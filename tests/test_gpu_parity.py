@@ -186,8 +186,14 @@ def test_auto_mode_picks_by_pass_rate(engine):
     loose = Constraints([None, seat_spec(hcp=(0, 20)), None, None])
     engine.sample(tight, n_raw=1000, cap=0)
     engine.sample(loose, n_raw=1000, cap=0)
-    assert (tight.mode, tight.primary) == (2, 2)
+    assert (tight.mode, tight.primary) == (4, 2)             # exact acceptance 0.0382 < 0.30: seat-first with the class table
     assert (loose.mode, loose.primary) == (1, 1)
+    assert tight.primary_acceptance[0] == 24235203726 and loose.primary_acceptance[0] > 0.9 * 635013559600
+    # a shapeless, wide window: still under 0.30, a few hundred thousand classes
+    wide = Constraints([None, None, seat_spec(hcp=(0, 7)), None])
+    engine.sample(wide, n_raw=1000, cap=0)
+    hands, classes = wide.primary_acceptance
+    assert wide.mode == 4 and hands / 635013559600 < 0.30 and classes > 100_000
 
 
 def test_seat_first_multi_seat_and_programs(engine):
