@@ -165,6 +165,10 @@ def test_exact_mode_distribution_and_jit(engine):
 
 def test_a_seat_nothing_satisfies_is_reported(engine):
     from bridge_mc_b200._lib import BadRange
-    cons = Constraints(None, [None, None, "(and (> hcp 30) balanced (> S 9))", None])
+    # 37 HCP needs A K Q in every suit and a jack: 4-3-3-3, never five clubs -- but no single range says so
+    cons = Constraints(None, [None, None, "(and (> hcp 36) (> C 4))", None])
     with pytest.raises(BadRange):
         engine.sample(cons, n_raw=1000)
+    # mode 1 does not enumerate: it simply accepts nothing
+    _, tal, _ = engine.sample(Constraints(None, [None, None, "(and (> hcp 36) (> C 4))", None]).set_mode(1), n_raw=100_000, cap=0)
+    assert tal["accepted"] == 0
