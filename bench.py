@@ -33,17 +33,8 @@ UNIT = "deals/s"
 P_BOX = 29286389970 / 635013559600          # exact acceptance of the range ("box") form the reference can generate
 P_1NT = 24235203726 / 635013559600          # exact acceptance of test-bid (1 NT)
 SEED = 0x6272696467656D63
-# Algorithmic integer work of one raw deal on the hot kernel for this workload ("W_int"):
-# thread-level integer instructions per raw deal, counted by ncu on the committed kernels
-# (sass__thread_inst_executed / raw deals of the launch):
-#   seat-first sampler  116  profiles/r01_prof_c2_rankfirst_2p28.txt  (3.10e10 thread instructions for a
-#                            2^28-deal launch; 248 before stage A became a rank draw)
-#   full-deal sampler   649  profiles/r01_c2_sample_kernel_v1.txt
-W_INT_BY_MODE = {1: 649, 2: 116, 4: 116}
-# DRAM bytes of one 2^28-deal seat-first launch that stores its 10.2 M records (163 MB algorithmic): ncu
-# dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_launches_bench_rankfirst.csv (the rest is still in L2 at kernel end)
-TRAFFIC_BYTES_BY_MODE = {1: None, 2: 101_600_000, 4: None}
-KERNEL_BY_MODE = {1: "sample_kernel<true,false>", 2: "sample_seatfirst_kernel<false>", 4: "sample_seatfirst_kernel<true>"}
+# Algorithmic integer work of one raw deal on the hot kernel ("W_int") = thread-level integer instructions per
+# raw deal, counted by ncu on the committed kernels: read from profiles/roofline_inputs.json (see roofline_inputs()).
 W_INT_SURVEY = 1400                          # SURVEY 8d's budget for a naive per-card full deal
 INT_PEAK_NOMINAL = 148 * 128 * 1.965e9       # SMs x INT32 lanes x max SM clock
 
@@ -258,6 +249,38 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def source_hash():
+    """sha256 over the library's sources: profiles/roofline_inputs.json records it with every ncu-derived figure, so a
+    figure measured on an older kernel is reported as stale instead of being silently reused."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "bridge_mc_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".hpp", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def roofline_inputs(kernel_key):
+    """W_int (thread-level integer instructions per raw deal, ncu sass__thread_inst_executed / raw deals of the launch) and
+    the DRAM bytes of one launch for the dominant kernel, from profiles/roofline_inputs.json (tools/roofline_inputs.py
+    writes it from an .ncu-rep).  Returns (entry, stale)."""
+    path = os.path.join(ROOT, "profiles", "roofline_inputs.json")
+    try:
+        table = json.load(open(path))
+    except Exception as e:
+        raise SystemExit(f"bench.py: {path} is missing or unreadable ({e}); run tools/roofline_inputs.py on a fresh ncu capture")
+    if kernel_key not in table:
+        raise SystemExit(f"bench.py: no roofline inputs for {kernel_key} in {path}")
+    ent = table[kernel_key]
+    stale = ent.get("src_hash") != source_hash()
+    if stale:
+        print(f"bench.py: WARNING roofline inputs for {kernel_key} were measured on sources {ent.get('src_hash')}, "
+              f"current {source_hash()}: re-profile (tools/roofline_inputs.py)", file=sys.stderr)
+    return ent, stale
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -275,7 +298,6 @@ def run_gpu(args):
         os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
     bdist.init_process_group("nccl", dev)
 
-    full_affinity = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     eng = Engine(local)
     stream = torch.cuda.Stream(dev)               # events must be recorded on the stream the kernels run on
@@ -294,7 +316,7 @@ def run_gpu(args):
         first = bdist.step_first_index(i, rank, world)      # disjoint Philox counter ranges per (step, rank)
         st = eng.sample_dev(cons, records.data_ptr(), cap, tallies.data_ptr(), n_accept=target, wave=args.wave,
                             first_index=first, seed=SEED)
-        bdist.allreduce_tallies(tallies)                    # the only exchange: a 4.4 KB histogram buffer over NVLink
+        bdist.allreduce_tallies(tallies)                    # the only exchange: an 8.5 KB histogram buffer over NVLink
         return st
 
     def barrier():
@@ -313,18 +335,18 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     raw = acc = 0
     kernel_ms = 0.0
-    launches = 0
+    waves = 0
     ev0.record(stream)
     for i in range(args.steps):
         st = step(args.warmup + i)
-        raw += st.raw; acc += st.accepted; kernel_ms += st.kernel_ms; launches += st.waves      # sampler launches that ran
+        raw += st.raw; acc += st.accepted; kernel_ms += st.kernel_ms; waves += st.waves      # sampler launches that ran
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     gpu_launches = eng.launch_count() - l0
     final = tallies_from_words(tallies.cpu().numpy().view(np.uint64))
-    tot = torch.tensor([float(raw), float(acc), ms, kernel_ms, float(launches)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(raw), float(acc), ms, kernel_ms, float(waves)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tot.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -335,37 +357,55 @@ def run_gpu(args):
         raw_all, acc_all = float(raw), float(acc)
     value = raw_all / (ms * 1e-3)
 
-    # ---- end-to-end through the host-buffer C ABI (what the Lisp shim calls) ----
-    e2e = None
+    # ---- end to end through the host-buffer C ABI (what the Lisp shim calls), host<->device copies inside the timed
+    # region.  Three result forms: index records (bmc_sample_indices: 4 B per accepted deal, the headline), full
+    # 16-byte records (bmc_sample), tallies only (records = NULL: the histogram job of /api/mc).
+    e2e = {}
     if not args.no_e2e:
         L = _lib.load()
-        nbytes = cap * 16
-        hp = L.bmc_host_alloc(nbytes)
-        if hp:
-            host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint64)), shape=(cap, 2))
-            k = max(1, min(args.steps, 2))
-            eng.sample(cons, n_accept=target, wave=args.wave, first_index=bdist.step_first_index(99, rank, world), seed=SEED,
-                       cap=cap, records=host)        # warm the path once
+        hp = L.bmc_host_alloc(cap * 16)
+        if not hp:
+            raise SystemExit("bench.py: bmc_host_alloc failed")
+        host_rec = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint64)), shape=(cap, 2))
+        host_off = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(cap,))
+
+        def e2e_leg(kind, k, base):
+            def one(i):
+                first = bdist.step_first_index(base + i, rank, world)
+                if kind == "indices":
+                    return eng.sample_indices(cons, n_accept=target, wave=args.wave, first_index=first, seed=SEED, cap=cap, offsets=host_off)
+                if kind == "records":
+                    return eng.sample(cons, n_accept=target, wave=args.wave, first_index=first, seed=SEED, cap=cap, records=host_rec)
+                return eng.sample(cons, n_accept=target, wave=args.wave, first_index=first, seed=SEED, cap=0)
+            one(-1)                                  # warm the path once
             barrier()
             t0 = time.perf_counter()
-            e_raw = e_stored = 0
+            e_raw = e_acc = e_stored = 0
             for i in range(k):
-                _, t_h, st = eng.sample(cons, n_accept=target, wave=args.wave,
-                                        first_index=bdist.step_first_index(100 + i, rank, world), seed=SEED, cap=cap,
-                                        records=host)
-                e_raw += st.raw; e_stored += st.stored
+                _, t_h, st = one(i)
+                e_raw += st.raw; e_acc += t_h["accepted"]; e_stored += st.stored
             barrier()
             dt = time.perf_counter() - t0
-            et = torch.tensor([float(e_raw), dt], dtype=torch.float64, device=dev)
+            et = torch.tensor([float(e_raw), float(e_acc), dt], dtype=torch.float64, device=dev)
             if world > 1:
                 emx = et.clone()
                 dist.all_reduce(emx, op=dist.ReduceOp.MAX)
                 dist.all_reduce(et, op=dist.ReduceOp.SUM)
-                dt = float(emx[1])
-            e2e = {"value": float(et[0]) / dt, "unit": UNIT, "h2d_bytes_per_step": 4096,
-                   "d2h_bytes_per_step": int(e_stored // k * 16 + _lib.TALLY_WORDS * 8), "steps": k,
-                   "api": "bmc_sample (host buffers: pinned record buffer from bmc_host_alloc)"}
-            L.bmc_host_free(hp)
+                dt = float(emx[2])
+            per = {"indices": 4, "records": 16, "tallies": 0}[kind]
+            d2h = int(e_stored // k * per + _lib.TALLY_WORDS * 8)
+            return {"value": float(et[0]) / dt, "unit": UNIT, "accepted_per_s": float(et[1]) / dt,
+                    "h2d_bytes_per_step": 4096, "d2h_bytes_per_step": d2h, "steps": k, "ms_per_step": 1e3 * dt / k,
+                    "d2h_gb_per_s_all_ranks": d2h * world * k / dt / 1e9,
+                    "api": {"indices": "bmc_sample_indices (host buffer of 32-bit index offsets, pinned; bmc_expand regenerates records on demand)",
+                            "records": "bmc_sample (host buffer of 16-byte records, pinned)",
+                            "tallies": "bmc_sample with records = NULL (tally buffer only)"}[kind]}
+
+        k = max(10, args.steps)
+        e2e["indices"] = e2e_leg("indices", k, 1000)
+        e2e["records"] = e2e_leg("records", max(3, min(args.steps, 5)), 2000)
+        e2e["tallies"] = e2e_leg("tallies", k, 3000)
+        L.bmc_host_free(hp)
 
     if rank == 0:
         peaks = {}
@@ -374,11 +414,14 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        avg_launch_ms = kernel_ms / max(1, launches)
-        deals_per_launch = raw / max(1, launches)
-        W_INT = W_INT_BY_MODE[cons.mode]
+        avg_launch_ms = kernel_ms / max(1, waves)
+        deals_per_launch = raw / max(1, waves)
+        kernel_key = {1: "sample_kernel<true,false>", 2: "sample_seatfirst_kernel<false>", 4: "sample_seatfirst_kernel<true>"}[cons.mode]
+        ent, stale = roofline_inputs(kernel_key + "/c2")
+        W_INT = ent["w_int_per_deal"]
         achieved = deals_per_launch * W_INT / (avg_launch_ms * 1e-3) / 1e12
         peak = int_peak / 1e12
+        hbm_ach = (acc / max(1, waves)) * 16 / (avg_launch_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -386,31 +429,35 @@ def run_gpu(args):
             "config": {"workload": f"C2: South test-bid (1 NT) rejection sampling, {target:.0e} accepted deals per GPU per step "
                                    f"(waves of {args.wave} Philox indices)",
                        "l2": "no input buffers (counter-based RNG); 1.6 GB of records written per step >> 126 MB L2",
-                       "e2e_note": "e2e copies all 1.6 GB of accepted records to pinned host memory every step (overlapped "
-                                   "with the next wave); it is PCIe-bound, the device number is integer-issue bound",
+                       "e2e_note": "e2e = bmc_sample_indices with a pinned host buffer: every accepted deal leaves the device as the 32-bit "
+                                   "offset of its Philox index (the deal is a pure function of seed and index; bmc_expand regenerates "
+                                   "records); e2e_full_records ships the 16-byte records, e2e_tallies_only the tally buffer alone",
                        "parallelism": f"dp{world}: disjoint Philox index ranges + NCCL all-reduce of the {_lib.TALLY_WORDS * 8} B tally buffer",
                        "host_binding_rank0": numa},
             "accepted_per_s": acc_all / (ms * 1e-3),
             "acceptance": acc_all / max(1.0, raw_all),
-            "sampler_mode": {1: "full-deal", 2: "seat-first", 4: "seat-first, exact class table"}[cons.mode],
-            "roofline": {"bound": "int32-issue", "kernel": KERNEL_BY_MODE[cons.mode], "achieved": achieved, "peak": peak,
+            "sampler_mode": {1: "full-deal", 2: "seat-first (count classes)", 4: "seat-first (exact class table)"}[cons.mode],
+            "primary_seat_exact_acceptance": (cons.primary_acceptance[0] / 635013559600) if cons.mode == 4 else None,
+            "roofline": {"bound": "int32-issue", "kernel": kernel_key, "achieved": achieved, "peak": peak,
                          "unit": "Tint-op/s", "frac": achieved / peak if peak else None,
-                         "traffic": TRAFFIC_BYTES_BY_MODE[cons.mode] if args.wave == 1 << 28 else None,
+                         "traffic": ent.get("dram_bytes_per_launch") if deals_per_launch == ent.get("deals_per_launch") else None,
                          "w_int_per_deal": W_INT, "avg_launch_ms": avg_launch_ms, "deals_per_launch": deals_per_launch,
+                         "sampler_launches": waves,
+                         "inputs": {"file": "profiles/roofline_inputs.json", "source": ent.get("source"), "stale": stale,
+                                    "src_hash": ent.get("src_hash"), "issue_active_pct_ncu": ent.get("issue_active_pct")},
                          "peak_source": "bmc_int_peak microbenchmark on this GPU (IMAD+LOP3 chains, burst); "
                                         "MEASURED_PEAKS.json has no integer figure",
                          "peak_nominal": INT_PEAK_NOMINAL / 1e12, "frac_of_nominal": achieved * 1e12 / INT_PEAK_NOMINAL,
-                         "w_int_source": "ncu sass__thread_inst_executed / raw deals, profiles/ (see bench.py W_INT_BY_MODE)",
                          "full_deal_equivalent_at_survey_w_int_1400": deals_per_launch * W_INT_SURVEY / (avg_launch_ms * 1e-3) / int_peak,
-                         "hbm": {"achieved": (acc / max(1, launches)) * 16 / (avg_launch_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                                 "unit": "GB/s", "peak_source": hbm_src,
-                                 "frac": (acc / max(1, launches)) * 16 / (avg_launch_ms * 1e-3) / 1e9 / hbm_peak}},
+                         "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "frac": hbm_ach / hbm_peak}},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "tally_check": {"accepted": final["accepted"], "south_hcp_15_16_17": [int(x) for x in final["hcp"][2][15:18]]},
         }
         if e2e:
-            line["e2e"] = e2e
+            line["e2e"] = e2e["indices"]
+            line["e2e_full_records"] = e2e["records"]
+            line["e2e_tallies_only"] = e2e["tallies"]
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             _, _, dt0 = cpu_reference_rate(200, threads)                 # size the bounded sample for ~12 s of CPU work

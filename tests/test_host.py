@@ -328,7 +328,7 @@ def test_c_abi_from_plain_c(tmp_path):
     import subprocess
     out = subprocess.run([_build_c_example(tmp_path), "50000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "mode 2, primary seat 2, HCP window 15-17" in out.stdout
+    assert "mode 4, primary seat 2, HCP window 15-17" in out.stdout      # auto: exact seat-first
     m = re.search(r"accepted (\d+)\s+stored (\d+)", out.stdout)
     assert m and int(m.group(1)) >= 50000 and int(m.group(2)) == 50000
     assert out.stdout.count("\n") >= 7 and "S:" in out.stdout
