@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from bridge_mc_b200 import _lib, bidding, compscore
+from bridge_mc_b200 import _lib, bidding, compscore  # noqa: F401
 from bridge_mc_b200 import dist as bdist
 from bridge_mc_b200.engine import Constraints, Engine, tallies_from_words
 
@@ -81,7 +81,8 @@ def main():
                 "kernel_ms": float(ms[0]), "wall_ms_incl_allreduce": float(ms[1]),
                 "raw_deals_per_s": t["raw"] / (float(ms[0]) * 1e-3), "accepted_per_s": t["accepted"] / (float(ms[0]) * 1e-3),
                 "hcp_seat2_15_17": [int(x) for x in t["hcp"][2][15:18]],
-                "tally_checksum": int(t["hcp"].sum() + 3 * t["len"].sum() + 7 * t["shape"].sum()) % (1 << 61),
+                "primary_seat_exact_acceptance": (cons.primary_acceptance[0] / 635013559600) if (cons is not None and cons.mode == 4) else None,
+                "tally_checksum": int((t["hcp"] * np.arange(1, 153).reshape(4, 38)).sum() + 3 * t["len"].sum() + 7 * t["shape"].sum()) % (1 << 61),
             }))
         return t
 
@@ -114,33 +115,21 @@ def main():
         cons2 = Constraints([seat_spec(hcp=(15, 17), s=(5, None)), seat_spec(hcp=(10, 11), h=(4, None))]).set_reference_order(2)
         run("REF-order-2", cons2, int(2e8 * scale), "two ranged seats (15-17 with 5+ spades, then 10-11 with 4+ hearts), mode 3")
     if "c4" in which:
-        # score / IMP tallies over n deals, the index range split over the ranks, histograms all-reduced
+        # compscore tallies over CONSTRAINED samples: C2's sampler scores every accepted deal in the launch that draws it
+        # (BMC_TALLY_SCORE): 8 contract x vulnerability rows + 6 IMP pairs; the index range is fixed (8 x 10 x 2^28 raw,
+        # ~8.2e8 accepted) and split over the ranks, so every tally is identical for every number of GPUs
+        from bridge_mc_b200._lib import TALLY_ALL, TALLY_SCORE
         cs = [compscore.Contract(t).c_struct() for t in ("1NTS", "3NTS", "4HS", "4SS")] * 2
-        vul = [0, 0, 0, 0, 1, 1, 1, 1]
-        pairs = [0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6, 7]
-        n = int(1e8 * scale) * world                       # weak scaling: 1e8 deals per GPU
-        first, per = bdist.rank_range(0, n, rank, world)
-        eng.score_tally(cs, vul, pairs, n=1 << 20, seed=SEED)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        th, ih, tab = eng.score_tally(cs, vul, pairs, n=per, seed=SEED, first_index=first)
-        hist = torch.from_numpy(np.concatenate([th.reshape(-1), ih.reshape(-1)]).astype(np.int64)).to(dev)
-        if world > 1:
-            dist.all_reduce(hist)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = float(dt[0])
-        hist = hist.cpu().numpy()
+        cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+        cons.set_scoring(cs, [0, 0, 0, 0, 1, 1, 1, 1], [0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6, 7])
+        t = run("C4", cons, int(8 * 10 * (1 << 28) * scale), "South test-bid (1 NT) sample scored in stage B: tricks x base-score per "
+                "contract, match-points per pair (stand-in trick source keyed on the deal; play-deal is out of scope)",
+                tally_mask=TALLY_ALL | TALLY_SCORE)
         if rank == 0:
-            print(json.dumps({"config": "C4", "note": "base-score / match-points tallies, 8 contract x vulnerability rows, 6 IMP pairs, "
-                              "tricks = Philox stream 1 (the reference's trick source is out of scope); wall clock incl. the all-reduce",
-                              "n_gpus": world, "deals": n, "wall_ms": dt * 1e3, "deals_per_s": n / dt, "contract_evals_per_s": 8 * n / dt,
-                              "tricks_hist_row0": [int(x) for x in hist[:14]], "hist_checksum": int((hist * np.arange(1, hist.size + 1)).sum() % (1 << 61)),
-                              "score_table_3NTS_vul": [int(x) for x in tab[5]]}))
+            print(json.dumps({"config": "C4-tallies", "n_gpus": world, "accepted": t["accepted"],
+                              "tricks_row0": [int(x) for x in t["tricks"][0]], "imps_pair0_nonzero": int((t["imps"][0] > 0).sum()),
+                              "imp_dropped": [int(x) for x in t["imp_dropped"]],
+                              "score_checksum": int((t["tricks"] * np.arange(1, 113).reshape(8, 14)).sum() + 3 * (t["imps"] * np.arange(1, 393).reshape(8, 49)).sum()) % (1 << 61)}))
     if world > 1:
         dist.destroy_process_group()
 
