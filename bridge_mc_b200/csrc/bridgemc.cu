@@ -168,79 +168,10 @@ __global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__
     }
 }
 
-// ---------------------------------------------------------------------------
-// K2: features / accept / choose-bid on given records
-// ---------------------------------------------------------------------------
-struct SchemeDev {
-    const uint32_t *code;
-    const uint32_t *row_off;     // offsets into code, n_rows entries
-    uint32_t n_rows;
-};
-
-__global__ void __launch_bounds__(256) filter_kernel(const __grid_constant__ ConsDev cons, int has_cons,
-                                                     const __grid_constant__ SchemeDev sch, const uint4 *__restrict__ rec,
-                                                     unsigned long long n, uint8_t *__restrict__ accept,
-                                                     bmc_features *__restrict__ feats)
-{
-    __shared__ uint32_t s_feat[8][FEAT_SCRATCH_WORDS];
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    uint4 r = make_uint4(0, 0, 0, 0);
-    if (live) r = rec[i];
-    const Planes pl = {r.x, r.y, r.z, r.w};
-    bool ok = true;
-    bmc_features out;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        uint32_t m0, m1;
-        seat_words(pl, k, m0, m1);
-        const Feat f = hand_features(m0, m1);
-        const uint8_t *fb = feat_store(s_feat[threadIdx.x >> 5], threadIdx.x & 31u, f);
-        if (has_cons) {
-            const SeatC &c = cons.seat[k];
-            if (c.active) {
-                ok = ok && seat_ranges_ok(c, f);
-                if (c.prog != 0xFFFFFFFFu) {
-                    bool err = false;
-                    const bool v = run_program(cons.code + c.prog, fb, err);
-                    ok = ok && v && !err;
-                }
-            }
-        }
-        int bid = -1;
-        if (sch.n_rows) {
-            // choose-bid: first row whose form is true; -2 where the reference would
-            // signal an error before finding one
-            bool done = false;
-            for (uint32_t row = 0; row < sch.n_rows; ++row) {
-                bool err = false;
-                const bool v = run_program(sch.code + __ldg(sch.row_off + row), fb, err);
-                if (!done) {
-                    if (err) { bid = -2; done = true; }
-                    else if (v) { bid = (int)row; done = true; }
-                }
-                if (__all_sync(0xFFFFFFFFu, done)) break;
-            }
-        }
-        bmc_seat_features &o = out.seat[k];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            o.len[s] = (uint8_t)((f.f0 >> (8 * s)) & 0xFFu);
-            o.suit_hcp[s] = (uint8_t)((f.f1 >> (8 * s)) & 0xFFu);
-        }
-        o.hcp = (uint8_t)(f.f2 & 0xFFu);
-        o.losers = (uint8_t)((f.f2 >> 8) & 0xFFu);
-        o.balanced = (uint8_t)((f.f2 >> 16) & 0xFFu);
-        o.bid = (int8_t)bid;
-    }
-    if (!live) return;
-    if (accept) accept[i] = ok ? 1 : 0;
-    if (feats) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&out);
-        uint4 *dst = reinterpret_cast<uint4 *>(feats + i);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-    }
-}
+// K2 (features / accept / choose-bid on given records) lives in filter.cuh: it is also compiled at run time with the
+// rows of a rule table translated to C++ (NVRTC), like the sampling kernels.
+#include "filter.cuh"
+static_assert(sizeof(FeatOut) == sizeof(bmc_features), "FeatOut mirrors bmc_features");
 
 // ---------------------------------------------------------------------------
 // K4: scoring
@@ -425,11 +356,15 @@ struct bmc_constraints {
     std::mutex mu, cal_mu;
 };
 
-struct SchemeTables { uint32_t *d_code = nullptr, *d_off = nullptr; };
+struct SchemeTables { uint32_t *d_code = nullptr, *d_off = nullptr; JitKernel jit; };
 struct bmc_scheme {
     std::vector<uint32_t> code, row_off;
     std::vector<std::string> bids;
+    std::vector<Sx> forms;       // the rows' rule forms (the NVRTC path re-reads them)
     std::map<int, SchemeTables> tabs;
+    int jit = 2;                 // 0 interpret, 1 compile (NVRTC), 2 auto: compile for large or repeated jobs
+    double interp_ms = 0.0;      // kernel time spent interpreting this table
+    float jit_ms = 0.f;
     std::mutex mu;
 };
 
@@ -894,20 +829,56 @@ int bmc_constraints_set_scoring(bmc_constraints *c, const bmc_contract *contract
 }
 
 // ---- NVRTC specialisation of a constraint (jit.hpp) ------------------------------------------------
+static const char kJitPrelude[] =
+    "typedef unsigned char uint8_t; typedef signed char int8_t; typedef unsigned short uint16_t; typedef short int16_t;\n"
+    "typedef unsigned int uint32_t; typedef int int32_t; typedef unsigned long long uint64_t; typedef long long int64_t;\n"
+    "#define BMC_JIT 1\n";
+static const char kJitVars[] =
+    "    const int vC = f.f0 & 0xFF, vD = (f.f0 >> 8) & 0xFF, vH = (f.f0 >> 16) & 0xFF, vS = (f.f0 >> 24) & 0xFF;\n"
+    "    const int vCP = f.f1 & 0xFF, vDP = (f.f1 >> 8) & 0xFF, vHP = (f.f1 >> 16) & 0xFF, vSP = (f.f1 >> 24) & 0xFF;\n"
+    "    const int vHCP = f.f2 & 0xFF, vLOS = (f.f2 >> 8) & 0xFF; const bool vBAL = ((f.f2 >> 16) & 0xFF) != 0;\n"
+    "    (void)vC; (void)vD; (void)vH; (void)vS; (void)vCP; (void)vDP; (void)vHP; (void)vSP; (void)vHCP; (void)vLOS; (void)vBAL;\n";
+
+// Compiles `prog` (which #includes the embedded device sources) for sm_100a and loads entry point `entry`.
+static int jit_compile(bmc_ctx *ctx, const std::string &prog, const char *entry, JitKernel &jk, std::string &log)
+{
+    JitApi &api = JitApi::get();
+    if (!api.ok) return fail(BMC_E_CUDA, "NVRTC specialisation unavailable: " + api.why);
+    auto t0 = std::chrono::steady_clock::now();
+    nvrtcProgram p = nullptr;
+    if (api.CreateProgram(&p, prog.c_str(), "bmc_jit.cu", kJitSrcCount, kJitSrcTexts, kJitSrcNames) != NVRTC_SUCCESS)
+        return fail(BMC_E_CUDA, "nvrtcCreateProgram failed");
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    const nvrtcResult r = api.CompileProgram(p, 3, opts);
+    size_t ls = 0;
+    api.GetProgramLogSize(p, &ls);
+    log.assign(ls, ' ');
+    if (ls) api.GetProgramLog(p, &log[0]);
+    if (r != NVRTC_SUCCESS) {
+        api.DestroyProgram(&p);
+        return fail(BMC_E_CUDA, "NVRTC compilation failed: " + log.substr(0, 2000));
+    }
+    size_t cs = 0;
+    api.GetCUBINSize(p, &cs);
+    std::vector<char> cubin(cs);
+    api.GetCUBIN(p, cubin.data());
+    api.DestroyProgram(&p);
+    CUresult cr = api.ModuleLoadData(&jk.module, cubin.data());
+    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleLoadData failed: " + std::to_string((int)cr));
+    cr = api.ModuleGetFunction(&jk.func, jk.module, entry);
+    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleGetFunction failed: " + std::to_string((int)cr));
+    jk.device = ctx->device;
+    jk.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return BMC_OK;
+}
+
 static int jit_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *tabs, bool seatfirst, bool exact)
 {
     JitKernel &jk = tabs->jit[seatfirst ? (exact ? 2 : 1) : 0];      // caller holds c->cal_mu; the ctx's device is current
     if (jk.func) return BMC_OK;
-    JitApi &api = JitApi::get();
-    if (!api.ok) return fail(BMC_E_CUDA, "NVRTC specialisation unavailable: " + api.why);
-    // 1. the rule forms as one C++ function
-    std::string fn =
-        "__device__ __forceinline__ bool bmc_jit_seat_rule(int seat, const bmc::Feat &f, bool &err)\n{\n"
-        "    const int vC = f.f0 & 0xFF, vD = (f.f0 >> 8) & 0xFF, vH = (f.f0 >> 16) & 0xFF, vS = (f.f0 >> 24) & 0xFF;\n"
-        "    const int vCP = f.f1 & 0xFF, vDP = (f.f1 >> 8) & 0xFF, vHP = (f.f1 >> 16) & 0xFF, vSP = (f.f1 >> 24) & 0xFF;\n"
-        "    const int vHCP = f.f2 & 0xFF, vLOS = (f.f2 >> 8) & 0xFF; const bool vBAL = ((f.f2 >> 16) & 0xFF) != 0;\n"
-        "    (void)vC; (void)vD; (void)vH; (void)vS; (void)vCP; (void)vDP; (void)vHP; (void)vSP; (void)vHCP; (void)vLOS; (void)vBAL;\n"
-        "    switch (seat) {\n";
+    // the rule forms as one C++ function
+    std::string fn = "__device__ __forceinline__ bool bmc_jit_seat_rule(int seat, const bmc::Feat &f, bool &err)\n{\n" +
+                     std::string(kJitVars) + "    switch (seat) {\n";
     try {
         RuleEmitter em;
         for (int k = 0; k < 4; ++k) {
@@ -921,40 +892,36 @@ static int jit_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *tabs, bool se
         return fail(BMC_E_PARSE, std::string("jit: ") + e.what());
     }
     fn += "    default: return true;\n    }\n}\n";
-    const std::string prog = std::string(
-        "typedef unsigned char uint8_t; typedef signed char int8_t; typedef unsigned short uint16_t; typedef short int16_t;\n"
-        "typedef unsigned int uint32_t; typedef int int32_t; typedef unsigned long long uint64_t; typedef long long int64_t;\n"
-        "#define BMC_JIT 1\n") + (seatfirst ? "#define BMC_JIT_SEATFIRST 1\n" : "#define BMC_JIT_FULL 1\n") +
-        (exact ? "#define BMC_JIT_EXACT 1\n" : "") +
-        "#include \"features.cuh\"\n" + fn + "#include \"kernels.cuh\"\n";
-    // 2. compile for sm_100a
-    auto t0 = std::chrono::steady_clock::now();
-    nvrtcProgram p = nullptr;
-    if (api.CreateProgram(&p, prog.c_str(), "bmc_jit.cu", kJitSrcCount, kJitSrcTexts, kJitSrcNames) != NVRTC_SUCCESS)
-        return fail(BMC_E_CUDA, "nvrtcCreateProgram failed");
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-    const nvrtcResult r = api.CompileProgram(p, 3, opts);
-    size_t ls = 0;
-    api.GetProgramLogSize(p, &ls);
-    c->jit_log.assign(ls, ' ');
-    if (ls) api.GetProgramLog(p, &c->jit_log[0]);
-    if (r != NVRTC_SUCCESS) {
-        api.DestroyProgram(&p);
-        return fail(BMC_E_CUDA, "NVRTC compilation failed: " + c->jit_log.substr(0, 2000));
-    }
-    size_t cs = 0;
-    api.GetCUBINSize(p, &cs);
-    std::vector<char> cubin(cs);
-    api.GetCUBIN(p, cubin.data());
-    api.DestroyProgram(&p);
-    // 3. load, bind, initialise the module's constant tables
-    CUresult cr = api.ModuleLoadData(&jk.module, cubin.data());
-    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleLoadData failed: " + std::to_string((int)cr));
-    cr = api.ModuleGetFunction(&jk.func, jk.module, seatfirst ? "bmc_jit_sample_seatfirst" : "bmc_jit_sample_full");
-    if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuModuleGetFunction failed: " + std::to_string((int)cr));
-    jk.device = ctx->device;
-    jk.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const std::string prog = std::string(kJitPrelude) + (seatfirst ? "#define BMC_JIT_SEATFIRST 1\n" : "#define BMC_JIT_FULL 1\n") +
+                             (exact ? "#define BMC_JIT_EXACT 1\n" : "") + "#include \"features.cuh\"\n" + fn + "#include \"kernels.cuh\"\n";
+    int rc = jit_compile(ctx, prog, seatfirst ? "bmc_jit_sample_seatfirst" : "bmc_jit_sample_full", jk, c->jit_log);
+    if (rc) return rc;
     c->jit_ms += jk.compile_ms;
+    return BMC_OK;
+}
+
+// choose-bid over a rule table as one straight-line function: rows in order, first whose form holds; -2 where
+// evaluation reaches an illegal form first; -1 = nil.
+static int scheme_jit_build(bmc_ctx *ctx, bmc_scheme *s, SchemeTables *tabs)
+{
+    JitKernel &jk = tabs->jit;                        // caller holds s->mu
+    if (jk.func) return BMC_OK;
+    std::string fn = "__device__ __forceinline__ bool bmc_jit_seat_rule(int, const bmc::Feat &, bool &) { return true; }\n"
+                     "__device__ __forceinline__ int bmc_jit_choose_bid(const bmc::Feat &f)\n{\n" + std::string(kJitVars);
+    try {
+        RuleEmitter em;
+        for (size_t r = 0; r < s->forms.size(); ++r)
+            fn += "    { bool err = false; const bool v = " + em.emit(s->forms[r]) + "; if (err) return -2; if (v) return " +
+                  std::to_string(r) + "; }\n";
+    } catch (const RuleError &e) {
+        return fail(BMC_E_PARSE, std::string("jit: ") + e.what());
+    }
+    fn += "    return -1;\n}\n";
+    const std::string prog = std::string(kJitPrelude) + "#define BMC_JIT_FILTER 1\n#include \"features.cuh\"\n" + fn + "#include \"filter.cuh\"\n";
+    std::string log;
+    int rc = jit_compile(ctx, prog, "bmc_jit_filter", jk, log);
+    if (rc) return rc;
+    s->jit_ms += jk.compile_ms;
     return BMC_OK;
 }
 
@@ -1000,6 +967,7 @@ int bmc_scheme_create(const char *table, bmc_scheme **out)
             s->code.insert(s->code.end(), rows.progs[i].begin(), rows.progs[i].end());
         }
         s->bids = rows.bids;
+        s->forms = rows.forms;
         s->code.push_back(enc(OP_END));          // spare word: the interpreter prefetches one word ahead
         if (s->row_off.size() > 120) return fail(BMC_E_CAPACITY, "rule table has more than 120 rows");
         *out = s.release();
@@ -1016,16 +984,26 @@ void bmc_scheme_destroy(bmc_scheme *s)
         cudaSetDevice(kv.first);
         cudaFree(kv.second.d_code);
         cudaFree(kv.second.d_off);
+        if (kv.second.jit.module) JitApi::get().ModuleUnload(kv.second.jit.module);
     }
     delete s;
 }
-static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev)
+int bmc_scheme_set_jit(bmc_scheme *s, int on)
+{
+    if (!s || on < 0 || on > 2) return fail(BMC_E_INVALID, "bmc_scheme_set_jit: bad argument");
+    s->jit = on;
+    return BMC_OK;
+}
+float bmc_scheme_jit_ms(const bmc_scheme *s) { return s ? s->jit_ms : 0.f; }
+static int scheme_upload(bmc_ctx *ctx, const bmc_scheme *ss, SchemeDev &dev, SchemeTables **tabs = nullptr)
 {
     dev.code = nullptr; dev.row_off = nullptr; dev.n_rows = 0;
+    if (tabs) *tabs = nullptr;
     if (!ss || ss->row_off.empty()) return BMC_OK;
     bmc_scheme *s = const_cast<bmc_scheme *>(ss);
     std::lock_guard<std::mutex> lk(s->mu);
     SchemeTables &t = s->tabs[ctx->device];
+    if (tabs) *tabs = &t;
     if (!t.d_code) {
         CUDA_TRY(cudaMalloc(&t.d_code, s->code.size() * sizeof(uint32_t)));
         CUDA_TRY(cudaMalloc(&t.d_off, s->row_off.size() * sizeof(uint32_t)));
@@ -1833,6 +1811,54 @@ int bmc_constraints_primary_acceptance(const bmc_constraints *c, uint64_t *hands
 }
 
 // ---- filter ---------------------------------------------------------------------
+// One pass of K2 over device buffers.  A rule table (scheme) is interpreted row by row, or -- scheme->jit 1, or 2
+// (default) for large (>= 2^21 deals) or repeated jobs -- evaluated by the NVRTC-compiled form of its rows.
+static int filter_core(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme, const uint4 *d_rec, uint64_t k,
+                       uint8_t *d_acc, bmc_features *d_feat)
+{
+    ConsDev dev{};
+    const bool has_cons = cons && cons->has_cons;
+    if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
+    SchemeDev sd;
+    SchemeTables *st = nullptr;
+    { int rc = scheme_upload(ctx, scheme, sd, &st); if (rc) return rc; }
+    const JitKernel *jit = nullptr;
+    bmc_scheme *sch = const_cast<bmc_scheme *>(scheme);
+    if (st && sd.n_rows) {
+        std::lock_guard<std::mutex> lk(sch->mu);
+        const bool want = sch->jit == 1 || (sch->jit == 2 && (k >= (1ull << 21) || sch->interp_ms > 500.0) && JitApi::get().ok);
+        if (want) {
+            int rc = scheme_jit_build(ctx, sch, st);
+            if (rc) {
+                if (sch->jit == 1) return rc;
+                sch->jit = 0;                        // auto: the build failed once -- keep interpreting
+            } else jit = &st->jit;
+        }
+    }
+    const unsigned blocks = (unsigned)((k + 255) / 256);
+    int hc = has_cons ? 1 : 0;
+    unsigned long long kk = k;
+    FeatOut *fo = reinterpret_cast<FeatOut *>(d_feat);
+    const bool timed = st && sd.n_rows && !jit;
+    if (timed) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (jit) {
+        void *params[] = {&dev, &hc, &sd, (void *)&d_rec, &kk, &d_acc, &fo};
+        const CUresult cr = JitApi::get().LaunchKernel(jit->func, blocks, 1, 1, 256, 1, 1, 0, (CUstream)ctx->stream, params, nullptr);
+        if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuLaunchKernel (jit filter) failed: " + std::to_string((int)cr));
+    } else filter_kernel<<<blocks, 256, 0, ctx->stream>>>(dev, hc, sd, d_rec, kk, d_acc, fo);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (timed) {
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        std::lock_guard<std::mutex> lk(sch->mu);
+        sch->interp_ms += ms;
+    }
+    return BMC_OK;
+}
+
 int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme, const bmc_record *records, uint64_t n,
                uint8_t *accept, bmc_features *feats)
 {
@@ -1841,11 +1867,6 @@ int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *sche
     if (!records) return fail(BMC_E_INVALID, "records is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    ConsDev dev{};
-    const bool has_cons = cons && cons->has_cons;
-    if (has_cons) { int rc = cons_upload(ctx, cons, dev); if (rc) return rc; }
-    SchemeDev sd;
-    { int rc = scheme_upload(ctx, scheme, sd); if (rc) return rc; }
     const uint64_t chunk = 1ull << 22;       // bounded device footprint: 4 Mi deals per pass
     uint4 *d_rec = nullptr;
     uint8_t *d_acc = nullptr;
@@ -1856,20 +1877,32 @@ int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *sche
     if (accept) e = cudaMalloc(&d_acc, m);
     if (e == cudaSuccess && feats) e = cudaMalloc(&d_feat, m * sizeof(bmc_features));
     int rc = BMC_OK;
-    for (uint64_t off = 0; off < n && e == cudaSuccess; off += chunk) {
+    for (uint64_t off = 0; off < n && e == cudaSuccess && rc == BMC_OK; off += chunk) {
         const uint64_t k = n - off < chunk ? n - off : chunk;
         e = cudaMemcpyAsync(d_rec, records + off, k * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) break;
-        filter_kernel<<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(dev, has_cons ? 1 : 0, sd, d_rec, k, d_acc, d_feat);
-        ctx->launches++;
-        e = cudaGetLastError();
-        if (e == cudaSuccess && accept) e = cudaMemcpyAsync(accept + off, d_acc, k, cudaMemcpyDeviceToHost, ctx->stream);
+        rc = filter_core(ctx, cons, scheme, d_rec, k, d_acc, d_feat);
+        if (rc) break;
+        if (accept) e = cudaMemcpyAsync(accept + off, d_acc, k, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess && feats) e = cudaMemcpyAsync(feats + off, d_feat, k * sizeof(bmc_features), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
-    if (e != cudaSuccess) rc = fail(BMC_E_CUDA, std::string("bmc_filter: ") + cudaGetErrorString(e));
+    if (rc == BMC_OK && e != cudaSuccess) rc = fail(BMC_E_CUDA, std::string("bmc_filter: ") + cudaGetErrorString(e));
     cudaFree(d_rec); cudaFree(d_acc); cudaFree(d_feat);
     return rc;
+}
+
+// device-buffer form: records_dev / accept_dev / feats_dev are device pointers (either output may be NULL); asynchronous
+// on the context's stream like bmc_sample_dev's outputs
+int bmc_filter_dev(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme, const void *records_dev, uint64_t n,
+                   void *accept_dev, void *feats_dev)
+{
+    if (!ctx) return fail(BMC_E_INVALID, "ctx is NULL");
+    if (n == 0) return BMC_OK;
+    if (!records_dev) return fail(BMC_E_INVALID, "records_dev is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return filter_core(ctx, cons, scheme, (const uint4 *)records_dev, n, (uint8_t *)accept_dev, (bmc_features *)feats_dev);
 }
 
 // ---- scoring --------------------------------------------------------------------

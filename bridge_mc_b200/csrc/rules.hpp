@@ -430,6 +430,7 @@ private:
 struct SchemeRows {
     std::vector<std::string> bids;
     std::vector<std::vector<uint32_t>> progs;
+    std::vector<Sx> forms;             // the rows' rule forms (NIL for a NIL row): the NVRTC path re-reads them
 };
 
 inline std::string sx_to_string(const Sx &x)
@@ -460,6 +461,7 @@ inline SchemeRows compile_scheme(const std::string &text)
         if (row.kind == Sx::NIL) {               // a NIL row (further-bid emits them): never matches
             out.bids.push_back("NIL");
             out.progs.push_back({enc(OP_FALSE), enc(OP_END)});
+            out.forms.push_back(Sx{});
             continue;
         }
         if (!row.is_list() || row.items.empty()) throw RuleError("bad rule row: " + sx_to_string(row));
@@ -476,6 +478,7 @@ inline SchemeRows compile_scheme(const std::string &text)
         rc.compile(form, code);
         out.bids.push_back(sx_to_string(row.items[0]));
         out.progs.push_back(std::move(code));
+        out.forms.push_back(form);
     }
     return out;
 }

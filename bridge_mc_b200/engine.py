@@ -145,6 +145,15 @@ class Scheme:
         check(_lib.load().bmc_scheme_create(table_sexpr.encode("utf-8"), C.byref(self._h)))
         self.size = _lib.load().bmc_scheme_size(self._h)
 
+    def set_jit(self, on):
+        """bmc_scheme_set_jit: 0 interpret the rows, 1 compile them into the filter kernel (NVRTC), 2 auto (default)"""
+        check(_lib.load().bmc_scheme_set_jit(self._h, int(on)))
+        return self
+
+    @property
+    def jit_ms(self) -> float:
+        return float(_lib.load().bmc_scheme_jit_ms(self._h))
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -292,6 +301,12 @@ class Engine:
                                  rec.ctypes.data if n else None, n, acc.ctypes.data,
                                  feats.ctypes.data if want_features else None))
         return acc, feats
+
+    def filter_dev(self, records_ptr: int, n: int, cons: Constraints | None = None, scheme: Scheme | None = None,
+                   accept_ptr: int = 0, feats_ptr: int = 0):
+        """bmc_filter_dev: device pointers, asynchronous on the context's stream"""
+        check(self._L.bmc_filter_dev(self._h, cons._h if cons else None, scheme._h if scheme else None, records_ptr, n,
+                                     accept_ptr or None, feats_ptr or None))
 
     # ---- scoring ----------------------------------------------------------------
     def score(self, contracts, vulnerable, tricks: np.ndarray) -> np.ndarray:

@@ -205,6 +205,11 @@ int  bmc_constraints_primary_acceptance(const bmc_constraints *c, uint64_t *hand
  * choose-bid (first row whose form is true, bidding.cl:146-150). */
 int  bmc_scheme_create(const char *table_sexpr, bmc_scheme **out);
 int  bmc_scheme_size(const bmc_scheme *s);
+/* How bmc_filter evaluates the table: 0 interpret its rows from bytecode; 1 translate the rows to C++ and compile them
+ * into the filter kernel with NVRTC (about a second, once per table and device; bit-identical results); 2 (default)
+ * interpret small jobs, compile for large (>= 2^21 deals) or repeated ones. */
+int  bmc_scheme_set_jit(bmc_scheme *s, int on);
+float bmc_scheme_jit_ms(const bmc_scheme *s);
 void bmc_scheme_destroy(bmc_scheme *s);
 
 /* ---- sampling: replaces `build` in a loop / `sim` (bridge.cl:1292-1319, 3144-3162) */
@@ -280,6 +285,9 @@ int bmc_distgen(bmc_ctx *ctx, uint64_t cards, const bmc_seat_spec *spec, uint16_
  * feats may each be NULL. */
 int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme,
                const bmc_record *records, uint64_t n, uint8_t *accept, bmc_features *feats);
+/* device-buffer form (e.g. the records bmc_sample_dev just wrote): no host copies, asynchronous on the ctx's stream */
+int bmc_filter_dev(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme,
+                   const void *records_dev, uint64_t n, void *accept_dev, void *feats_dev);
 
 /* ---- scoring: contract-score (bridge.cl:3045-3069), base-score
  * (compscore.cl:94-100), match-points (compscore.cl:127-131) ------------------ */
