@@ -59,8 +59,11 @@ static int fail(int code, const std::string &msg)
 // K1c: reference-order sampler (reforder.cuh): one thread = one deal, ranged seats sampled one
 // after the other exactly as `build` does (bridge.cl:1292-1319).
 // ---------------------------------------------------------------------------
-// The deal behind index `idx`; returns true where the reference signals an error for it (counted in `voided`).
-__device__ __forceinline__ bool reforder_deal(const SampleArgs &a, const SeqDev &q, unsigned long long idx, bool valid, Planes &pl)
+// One thread, one index, start to end (bmc_expand; the sampling kernel below pipelines the same steps and draws the
+// same numbers): stage 1 by rank, every later ranged seat by rejection over uniform 13-subsets of the remaining
+// cards, deal-all for the rest.  Returns true where the reference signals an error for the index (`voided`).
+__device__ __forceinline__ bool reforder_deal(const SampleArgs &a, const SeqDev &q, const SeqRoot &root, const LowTabs &T,
+                                              unsigned long long idx, bool valid, Planes &pl)
 {
     const uint32_t il = (uint32_t)idx, ih = (uint32_t)(idx >> 32);
     uint32_t lo0 = a.fix.lo0, lo1 = a.fix.lo1, hi0 = a.fix.hi0, hi1 = a.fix.hi1;
@@ -70,14 +73,20 @@ __device__ __forceinline__ bool reforder_deal(const SampleArgs &a, const SeqDev 
         const SeqStage &st = q.st[j];
         if (j > 0u && st.m <= 13u) break;                     // a LATER seat is implied once 13 cards remain (bridge.cl:1303);
                                                               // the first def always goes through the root generator
-        const SeqRanges r = seq_infer(st, q.exhaust, f0, f1);
-        bad = bad || r.bad;
-        uint32_t h0 = 0, h1 = 0, att = 0;
-        bool need = valid && !bad;
-        while (need) {
-            const bool clean = seq_draw13(a.key, il, ih, STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, h0, h1);
-            if (clean && seq_hand_ok(r, h0, h1)) need = false;
-            else if (++att >= SEQ_MAX_ATTEMPTS) { bad = true; need = false; }
+        uint32_t h0 = 0, h1 = 0;
+        if (j == 0u) {
+            if (valid && !seq_stage1(a.key, root, T, il, ih, h0, h1)) bad = true;
+        } else {
+            const SeqRanges r = seq_infer(st, q.exhaust, f0, f1);
+            const SeqPacked pk = seq_pack(r);
+            bad = bad || r.bad;
+            uint32_t att = 0;
+            bool need = valid && !bad;
+            while (need) {
+                const bool clean = seq_draw13(a.key, il, ih, STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, h0, h1);
+                if (clean && seq_packed_ok(pk, h0, h1)) need = false;
+                else if (++att >= SEQ_MAX_ATTEMPTS) { bad = true; need = false; }
+            }
         }
         if (!valid || bad) { h0 = 0; h1 = 0; }
         const uint32_t k = (uint32_t)st.seat;
@@ -99,26 +108,143 @@ __device__ __forceinline__ bool reforder_deal(const SampleArgs &a, const SeqDev 
     return bad;
 }
 
-__global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q)
+// Sampling kernel: a warp is a small dataflow machine.  Stage 1 runs on full warps of new indices and feeds a queue;
+// each lane then carries ONE deal through the later ranged seats -- one rejection attempt per iteration, the narrowed
+// ranges recomputed when it moves to the next seat -- and takes a new deal from the queue the moment its own is
+// complete, so no lane waits for the slowest one of its warp; complete deals collect in a second queue and go through
+// deal-all, tallies and the store 32 at a time.
+constexpr int RQ_CAP = 64;
+__global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q,
+                                                                  const __grid_constant__ SeqRoot root)
 {
     if (wave_cancelled(a)) return;
+    __shared__ __align__(16) LowTabs s_low;
+    __shared__ uint4 s_q1[WARPS_PER_BLOCK][RQ_CAP];           // stage-1 results: (hand m0, m1, index - a.first, -)
+    __shared__ uint4 s_qd[WARPS_PER_BLOCK][RQ_CAP];           // complete deals: planes ...
+    __shared__ uint4 s_qe[WARPS_PER_BLOCK][RQ_CAP];           // ... and (free f0, f1, index - a.first, -)
     const SmemPlan sp = smem_plan(false, false, false, false, a.tally_mask);
     uint32_t *smem = s_dyn;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     tally_init(a, sp, smem, FULL_HIST_COPIES);
+    for (int i = threadIdx.x; i < (int)(sizeof(LowTabs) / 4); i += THREADS)
+        reinterpret_cast<uint32_t *>(&s_low)[i] = reinterpret_cast<const uint32_t *>(&c_lowtabs)[i];
     __syncthreads();
     const TallyMem tm = tally_mem(sp, smem, warp);
+    uint4 *q1 = s_q1[warp], *qd = s_qd[warp], *qe = s_qe[warp];
+    unsigned h1 = 0, t1 = 0, hd = 0, td = 0;                  // queue cursors, warp-uniform
+    const uint32_t lt = (1u << lane) - 1u;
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS_PER_BLOCK;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + warp;
     uint32_t n_raw = 0, n_bad = 0;
-    const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
-    unsigned long long off = (unsigned long long)blockIdx.x * THREADS + threadIdx.x;
-    for (uint32_t it = 0; it < a.iters; ++it, off += stride) {
-        const bool valid = off < a.n;
-        Planes pl;
-        const bool bad = reforder_deal(a, q, a.first + off, valid, pl);
-        n_raw += valid ? 1u : 0u;
-        n_bad += (valid && bad) ? 1u : 0u;
-        stage_b(a, pl, (uint32_t)off, valid && !bad, tm, lane, nullptr, 0u);     // nothing left to test
+    // the deal this lane carries
+    bool busy = false, fresh = false;
+    uint32_t off = 0, lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0, f0 = 0, f1 = 0, j = 0, att = 0;
+    SeqPacked pk = {0, 0, 0, 0, 0, 0};
+    uint32_t batch = 0;
+
+    auto run_done = [&](unsigned count) {                     // deal-all + tallies + store for up to 32 complete deals
+        const uint4 d = qd[(hd + lane) % RQ_CAP], e = qe[(hd + lane) % RQ_CAP];
+        hd += count;
+        __syncwarp();
+        const bool active = lane < count;
+        const unsigned long long idx = a.first + e.z;
+        Planes pl = {d.x, d.y, d.z, d.w};
+        bool bad = false;
+        if (q.n_rest) {
+            uint32_t at = 0;
+            bool need = active;
+            while (need) {
+                const bool voided = deal_fixed_core(a.key, STREAM_REFORDER_REST + (at << 8), q.n_rest, q.q_rest, d.x, d.y, d.z, d.w,
+                                                    e.x, e.y, q.thresh_rest, (uint32_t)idx, (uint32_t)(idx >> 32), pl);
+                if (!voided) need = false;
+                else if (++at >= 64u) { bad = true; need = false; }
+            }
+        }
+        n_bad += (active && bad) ? 1u : 0u;
+        stage_b(a, pl, e.z, active && !bad, tm, lane, nullptr, 0u);      // nothing left to test
+    };
+
+    for (;;) {
+        // 1. keep the stage-1 queue stocked: full warps of new indices
+        while (t1 - h1 < 32u && batch < a.iters) {
+            const unsigned long long o = ((unsigned long long)batch * total_warps + gwarp) * 32ull + lane;
+            ++batch;
+            const bool valid = o < a.n;
+            const unsigned long long idx = a.first + o;
+            uint32_t m0, m1;
+            const bool ok = seq_stage1(a.key, root, s_low, (uint32_t)idx, (uint32_t)(idx >> 32), m0, m1) && valid;
+            n_raw += valid ? 1u : 0u;
+            n_bad += (valid && !ok) ? 1u : 0u;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+            if (ok) q1[(t1 + __popc(bal & lt)) % RQ_CAP] = make_uint4(m0, m1, (uint32_t)o, 0u);
+            t1 += __popc(bal);
+            __syncwarp();
+        }
+        // 2. idle lanes take a deal from the queue
+        {
+            const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+            const unsigned avail = t1 - h1, want = __popc(idle);
+            const unsigned take = want < avail ? want : avail;
+            const unsigned my = __popc(idle & lt);
+            if (!busy && my < take) {
+                const uint4 e = q1[(h1 + my) % RQ_CAP];
+                const uint32_t k = (uint32_t)q.st[0].seat;
+                lo0 = a.fix.lo0 | ((k & 1u) ? e.x : 0u); lo1 = a.fix.lo1 | ((k & 1u) ? e.y : 0u);
+                hi0 = a.fix.hi0 | ((k & 2u) ? e.x : 0u); hi1 = a.fix.hi1 | ((k & 2u) ? e.y : 0u);
+                f0 = a.fix.free0 & ~e.x; f1 = a.fix.free1 & ~e.y;
+                off = e.z; j = 1u; busy = true; fresh = true;
+            }
+            h1 += take;
+            __syncwarp();
+        }
+        if (!__any_sync(0xFFFFFFFFu, busy)) {
+            if (batch >= a.iters && t1 == h1) break;            // nothing in flight, nothing left to draw
+            continue;
+        }
+        // 3. lanes that just received a deal or just finished a seat: done, or the next seat's narrowed ranges
+        if (__any_sync(0xFFFFFFFFu, fresh)) {
+            bool done = false;
+            if (fresh) {
+                if (j >= q.n_stages || q.st[j < 4u ? j : 3u].m <= 13u) done = true;      // a later seat is implied once 13 cards remain
+                else {
+                    const SeqRanges r = seq_infer(q.st[j], q.exhaust, f0, f1);
+                    if (r.bad) { busy = false; ++n_bad; }      // the reference signals bad-range for this build
+                    else { pk = seq_pack(r); att = 0u; }
+                }
+                fresh = false;
+            }
+            // complete deals queue up for deal-all (fewer than 32 wait there, at most 32 join: the queue holds 64)
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, done);
+            if (bal) {
+                if (done) {
+                    const unsigned pos = (td + __popc(bal & lt)) % RQ_CAP;
+                    qd[pos] = make_uint4(lo0, lo1, hi0, hi1);
+                    qe[pos] = make_uint4(f0, f1, off, 0u);
+                    busy = false;
+                }
+                td += __popc(bal);
+                __syncwarp();
+                while (td - hd >= 32u) run_done(32u);
+            }
+        }
+        // 4. one rejection attempt per busy lane
+        if (busy) {
+            const SeqStage &st = q.st[j < 4u ? j : 3u];
+            const unsigned long long idx = a.first + off;
+            uint32_t x0, x1;
+            const bool clean = seq_draw13(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, x0, x1);
+            if (clean && seq_packed_ok(pk, x0, x1)) {
+                const uint32_t k = (uint32_t)st.seat;
+                if (k & 1u) { lo0 |= x0; lo1 |= x1; }
+                if (k & 2u) { hi0 |= x0; hi1 |= x1; }
+                f0 &= ~x0; f1 &= ~x1;
+                ++j;
+                fresh = true;
+            } else if (++att >= SEQ_MAX_ATTEMPTS) { busy = false; ++n_bad; }
+        }
     }
+    if (td - hd) run_done(td - hd);
+
     {
         unsigned long long r64 = n_raw, v64 = n_bad;
 #pragma unroll
@@ -141,11 +267,12 @@ __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_c
 // demand.  One thread per offset; mode 1 full deal (free or with fixed hands), 2 / 4 seat-first (count classes / exact
 // class table), 3 reference order.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q, int mode,
+__global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__ SampleArgs a, const __grid_constant__ SeqDev q,
+                                                         const __grid_constant__ SeqRoot root, int mode,
                                                          const uint32_t *__restrict__ offsets, unsigned long long n, uint4 *__restrict__ out)
 {
     __shared__ __align__(16) LowTabs s_low;
-    if (mode == 2 || mode == 4) {
+    if (mode >= 2) {
         for (int i = threadIdx.x; i < (int)(sizeof(LowTabs) / 4); i += THREADS)
             reinterpret_cast<uint32_t *>(&s_low)[i] = reinterpret_cast<const uint32_t *>(&c_lowtabs)[i];
         __syncthreads();
@@ -154,7 +281,7 @@ __global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__
     for (unsigned long long i = (unsigned long long)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
         const unsigned long long idx = a.first + offsets[i];
         Planes pl;
-        if (mode == 3) reforder_deal(a, q, idx, true, pl);
+        if (mode == 3) reforder_deal(a, q, root, s_low, idx, true, pl);
         else if (mode == 2 || mode == 4) {
             uint32_t m0, m1;
             if (mode == 4) sf_exact_hand(a.key, a.cons.x, s_low, idx, true, m0, m1);
@@ -326,6 +453,7 @@ struct ConsTables {              // per-device copies of a constraint's tables
     uint32_t *x_keys = nullptr, *x_bkt = nullptr;
     uint32_t x_bmul = 0, x_nbkt = 0;
     bool x_built = false;
+    SeqRoot root{};              // mode 3: the root generator's class table (uses the x_* arrays) and its scale
 };
 
 struct bmc_constraints {
@@ -693,10 +821,27 @@ int bmc_constraints_create(const bmc_seat_spec specs[4], const char *const rules
     return BMC_OK;
 }
 
+// A change of dealing mode invalidates the per-device class tables (mode 4's and mode 3's share the arrays).
+static void drop_class_tables(bmc_constraints *c)
+{
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto &kv : c->tabs) {
+        ConsTables &t = kv.second;
+        if (t.x_cum || t.x_keys || t.x_bkt) {
+            cudaSetDevice(kv.first);
+            cudaFree(t.x_cum); cudaFree(t.x_keys); cudaFree(t.x_bkt);
+        }
+        t.x_cum = nullptr; t.x_keys = nullptr; t.x_bkt = nullptr;
+        t.x_built = false;
+        t.root = SeqRoot{};
+    }
+}
+
 int bmc_constraints_set_mode(bmc_constraints *c, int mode)
 {
     if (!c || mode < 0 || mode > 4 || mode == 3) return fail(BMC_E_INVALID, "bmc_constraints_set_mode: bad argument (mode 3 is set by bmc_constraints_set_reference_order)");
     if ((mode == 2 || mode == 4) && (c->has_fixed || !c->has_cons)) return fail(BMC_E_INVALID, "seat-first modes need a constrained seat and no fixed hands");
+    drop_class_tables(c);
     c->mode = mode;
     c->resolved = 0;
     return BMC_OK;
@@ -786,6 +931,7 @@ int bmc_constraints_set_reference_order(bmc_constraints *c, int n_defs)
     if (!c) return fail(BMC_E_INVALID, "bmc_constraints_set_reference_order: NULL");
     int rc = build_seq(c, n_defs);
     if (rc) return rc;
+    drop_class_tables(c);
     c->mode = 3;
     c->resolved = 3;
     return BMC_OK;
@@ -1098,7 +1244,7 @@ static int launch_wave(bmc_ctx *ctx, const WaveCfg &w, uint64_t first, uint64_t 
         void *params[] = {&a};
         const CUresult cr = JitApi::get().LaunchKernel(w.jit->func, (unsigned)blocks, 1, 1, THREADS, 1, 1, (unsigned)smem, (CUstream)ctx->stream, params, nullptr);
         if (cr != CUDA_SUCCESS) return fail(BMC_E_CUDA, "cuLaunchKernel (jit) failed: " + std::to_string((int)cr));
-    } else if (w.seq) sample_reforder_kernel<<<blocks, THREADS, smem, ctx->stream>>>(a, *w.seq);
+    } else if (w.seq) sample_reforder_kernel<<<blocks, THREADS, smem, ctx->stream>>>(a, *w.seq, w.tabs->root);
     else if (w.seatfirst && w.exact) sample_seatfirst_kernel<true><<<blocks, THREADS, smem, ctx->stream>>>(a);
     else if (w.seatfirst) sample_seatfirst_kernel<false><<<blocks, THREADS, smem, ctx->stream>>>(a);
     else if (w.fix) {
@@ -1155,8 +1301,61 @@ static int distgen_count(bmc_ctx *ctx, const ClassSpec &cs, PatternScan &ps, boo
 
 constexpr uint64_t EXACT_MAX_CLASSES = 1ull << 23;     // all 4 582 640 classes of a 13-card hand fit (55 MB of tables)
 
-// The exact class table of the primary seat on this device.  Always leaves the exact acceptance of the seat in the
-// constraint (x_weight / C(52,13)); *built = false when the table would be too large (or nothing is admitted).
+// Enumerates the classes `cs` admits and, when there are between 1 and EXACT_MAX_CLASSES of them, leaves their table on
+// the device in t->x_*.  scale = 0: the rank of u is u / floor(2^64 / W) (a generator of its own: mode 3's root);
+// otherwise u / scale (mode 4: scale = floor(2^64 / C(52,13)), the admitted hands come first).
+static int class_table_build(bmc_ctx *ctx, const ClassSpec &cs, unsigned long long scale, ConsTables *t, unsigned long long *W_out,
+                             unsigned long long *K_out, bool *built)
+{
+    *built = false;
+    PatternScan ps;
+    unsigned long long *d_w = nullptr;
+    uint32_t *d_c = nullptr;
+    { int rc = distgen_count(ctx, cs, ps, false, &d_w, &d_c); if (rc) return rc; }
+    // exclusive scans over the 65 536 patterns (host: a control-plane step, once per constraint and device)
+    std::vector<unsigned long long> pcum(DG_PATTERNS);
+    std::vector<uint32_t> poff(DG_PATTERNS);
+    unsigned long long W = 0, K = 0;
+    for (int p = 0; p < DG_PATTERNS; ++p) { pcum[p] = W; poff[p] = (uint32_t)K; W += ps.w[p]; K += ps.cnt[p]; }
+    *W_out = W; *K_out = K;
+    if (K == 0 || K > EXACT_MAX_CLASSES) { cudaFree(d_w); cudaFree(d_c); return BMC_OK; }
+    const unsigned long long S = scale ? scale : (unsigned long long)((((unsigned __int128)1) << 64) / W);
+    unsigned long long *d_pcum = nullptr;
+    uint32_t *d_poff = nullptr;
+    cudaError_t e = cudaMalloc(&d_pcum, DG_PATTERNS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d_poff, DG_PATTERNS * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&t->x_cum, (K + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&t->x_keys, K * sizeof(uint32_t));
+    // buckets: about two per class, a power of two in [2^8, 2^23]
+    uint32_t nb = 256;
+    while (nb < 2 * K && nb < (1u << 23)) nb <<= 1;
+    const unsigned long long theta = W * S;                  // <= 2^64 - 1
+    unsigned long long bm = ((unsigned long long)nb << 32) / ((theta >> 32) + 1ull);
+    const uint32_t bmul = bm > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bm;
+    if (e == cudaSuccess) e = cudaMalloc(&t->x_bkt, ((size_t)nb + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pcum, pcum.data(), DG_PATTERNS * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_poff, poff.data(), DG_PATTERNS * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->x_cum + K, &W, sizeof W, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        distgen_emit_kernel<<<DG_PATTERNS, DG_THREADS, 0, ctx->stream>>>(cs, d_pcum, d_poff, d_c, t->x_keys, t->x_cum);
+        distgen_bucket_kernel<<<(nb + 256) / 256, 256, 0, ctx->stream>>>(t->x_cum, (uint32_t)K, bmul, nb, S, t->x_bkt);
+        ctx->launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_w); cudaFree(d_c); cudaFree(d_pcum); cudaFree(d_poff);
+    if (e != cudaSuccess) {
+        cudaFree(t->x_cum); cudaFree(t->x_keys); cudaFree(t->x_bkt);
+        t->x_cum = nullptr; t->x_keys = nullptr; t->x_bkt = nullptr;
+        return fail(BMC_E_CUDA, std::string("class table: ") + cudaGetErrorString(e));
+    }
+    t->x_bmul = bmul; t->x_nbkt = nb; t->x_built = true;
+    *built = true;
+    return BMC_OK;
+}
+
+// The exact class table of the primary seat on this device (mode 4).  Always leaves the exact acceptance of the seat in
+// the constraint (x_weight / C(52,13)); *built = false when nothing is admitted.
 static int exact_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *t, bool *built)
 {
     *built = false;
@@ -1168,49 +1367,64 @@ static int exact_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *t, bool *bu
     for (int s = 0; s < 4; ++s) cs.n_low[s] = 9;
     cs.hon_avail = 0xFFFFu;
     cs.hand_size = 13;
-    PatternScan ps;
-    unsigned long long *d_w = nullptr;
-    uint32_t *d_c = nullptr;
-    { int rc = distgen_count(ctx, cs, ps, false, &d_w, &d_c); if (rc) return rc; }
-    // exclusive scans over the 65 536 patterns (host: a control-plane step, once per constraint and device)
-    std::vector<unsigned long long> pcum(DG_PATTERNS);
-    std::vector<uint32_t> poff(DG_PATTERNS);
     unsigned long long W = 0, K = 0;
-    for (int p = 0; p < DG_PATTERNS; ++p) { pcum[p] = W; poff[p] = (uint32_t)K; W += ps.w[p]; K += ps.cnt[p]; }
+    int rc = class_table_build(ctx, cs, SF_S, t, &W, &K, built);
+    if (rc) return rc;
     c->x_weight = W; c->x_classes = K; c->x_known = true;
     c->stage_a_pass = (double)W / (double)SF_HANDS;
-    if (K == 0 || K > EXACT_MAX_CLASSES) { cudaFree(d_w); cudaFree(d_c); return BMC_OK; }
-    unsigned long long *d_pcum = nullptr;
-    uint32_t *d_poff = nullptr;
-    cudaError_t e = cudaMalloc(&d_pcum, DG_PATTERNS * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&d_poff, DG_PATTERNS * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&t->x_cum, (K + 1) * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&t->x_keys, K * sizeof(uint32_t));
-    // buckets: about two per class, a power of two in [2^8, 2^23]
-    uint32_t nb = 256;
-    while (nb < 2 * K && nb < (1u << 23)) nb <<= 1;
-    const unsigned long long theta = W * SF_S;
-    unsigned long long bm = ((unsigned long long)nb << 32) / ((theta >> 32) + 1ull);
-    const uint32_t bmul = bm > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bm;
-    if (e == cudaSuccess) e = cudaMalloc(&t->x_bkt, ((size_t)nb + 1) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pcum, pcum.data(), DG_PATTERNS * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_poff, poff.data(), DG_PATTERNS * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t->x_cum + K, &W, sizeof W, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
-        distgen_emit_kernel<<<DG_PATTERNS, DG_THREADS, 0, ctx->stream>>>(cs, d_pcum, d_poff, d_c, t->x_keys, t->x_cum);
-        distgen_bucket_kernel<<<(nb + 256) / 256, 256, 0, ctx->stream>>>(t->x_cum, (uint32_t)K, bmul, nb, SF_S, t->x_bkt);
-        ctx->launches += 2;
-        e = cudaGetLastError();
+    return BMC_OK;
+}
+
+static void ranges_to_seatc(const SeatRanges &r, SeatC &c);
+
+// Mode 3: the root generator (first ranged seat over the deck the fixed hands leave) as a class table on this device.
+static int root_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *t)
+{
+    if (t->x_built || t->root.limit) return BMC_OK;          // built, or known to be empty (limit = 1 marks it)
+    const SeqDev &q = c->seq;
+    const SeqRanges r = seq_infer(q.st[0], q.exhaust, c->fix.free0, c->fix.free1);
+    SeqRoot root{};
+    root.low0 = c->fix.free0 & 0x01FF01FFu;
+    root.low1 = c->fix.free1 & 0x01FF01FFu;
+    root.full = (root.low0 == 0x01FF01FFu && root.low1 == 0x01FF01FFu) ? 1u : 0u;
+    ClassSpec cs{};
+    cs.hand_size = 13;
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t lane = ((s < 2 ? c->fix.free0 : c->fix.free1) >> (16 * (s & 1))) & 0x1FFFu;
+        cs.n_low[s] = (uint32_t)__builtin_popcount(lane & 0x1FFu);
+        for (int h = 0; h < 4; ++h)
+            if ((lane >> (9 + h)) & 1u) cs.hon_avail |= 1u << (15 - (4 * s + h));
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_w); cudaFree(d_c); cudaFree(d_pcum); cudaFree(d_poff);
-    if (e != cudaSuccess) {
-        cudaFree(t->x_cum); cudaFree(t->x_keys); cudaFree(t->x_bkt);
-        t->x_cum = nullptr; t->x_keys = nullptr; t->x_bkt = nullptr;
-        return fail(BMC_E_CUDA, std::string("exact class table: ") + cudaGetErrorString(e));
+    SeatRanges sr;
+    bool empty = r.bad;
+    sr.lo[F_HCP] = r.hcp_lo < 0 ? 0 : r.hcp_lo; sr.hi[F_HCP] = r.hcp_hi > 40 ? 40 : r.hcp_hi;
+    for (int s = 0; s < 4; ++s) {
+        sr.lo[F_C + s] = r.len_lo[s] < 0 ? 0 : r.len_lo[s]; sr.hi[F_C + s] = r.len_hi[s] > 13 ? 13 : r.len_hi[s];
+        sr.lo[F_CP + s] = r.sh_lo[s] < 0 ? 0 : r.sh_lo[s]; sr.hi[F_CP + s] = r.sh_hi[s] > 10 ? 10 : r.sh_hi[s];
     }
-    t->x_bmul = bmul; t->x_nbkt = nb; t->x_built = true;
-    *built = true;
+    empty = empty || sr.empty();
+    unsigned long long W = 0, K = 0;
+    bool built = false;
+    if (!empty) {
+        SeatC sc{};
+        ranges_to_seatc(sr, sc);
+        sc.prog = 0xFFFFFFFFu; sc.active = 1;
+        cs.seat = sc;
+        cs.prog = nullptr;
+        int rc = class_table_build(ctx, cs, 0ull, t, &W, &K, &built);
+        if (rc) return rc;
+    }
+    if (built) {
+        root.W = W;
+        root.S = (unsigned long long)((((unsigned __int128)1) << 64) / W);
+        root.S_recip = (unsigned long long)((((unsigned __int128)1) << 64) / root.S);
+        root.limit = W * root.S;
+        root.x.cum = t->x_cum; root.x.keys = t->x_keys; root.x.bkt = t->x_bkt; root.x.bmul = t->x_bmul; root.x.n_bkt = t->x_nbkt;
+    } else {
+        root.W = 0;                                          // the root generator has total weight 0: every build signals an error
+        root.limit = 1;
+    }
+    t->root = root;
     return BMC_OK;
 }
 
@@ -1219,10 +1433,15 @@ static int exact_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *t, bool *bu
 static int resolve_cfg(bmc_ctx *ctx, const bmc_constraints *cons, WaveCfg &w)
 {
     w.has_cons = cons && cons->has_cons;
-    if (w.has_cons) { int rc = cons_upload(ctx, cons, w.cons, &w.tabs); if (rc) return rc; }
+    if (cons) { int rc = cons_upload(ctx, cons, w.cons, &w.tabs); if (rc) return rc; }
+    if (!w.has_cons) w.cons = ConsDev{};
     w.fix = (cons && cons->has_fixed) ? &cons->fix : nullptr;
     if (cons) w.score = cons->score;
     if (cons && cons->resolved == 3) {                 // reference order: `build`'s own sequential semantics
+        bmc_constraints *cc = const_cast<bmc_constraints *>(cons);
+        std::lock_guard<std::mutex> cal_lock(cc->cal_mu);
+        int rc = root_build(ctx, cc, w.tabs);
+        if (rc) return rc;
         w.seq = &cons->seq;
         w.fix = &cons->fix;
     } else if (w.has_cons && !w.fix) {
@@ -1557,9 +1776,10 @@ static int expand_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     }
     const int mode = w.seq ? 3 : w.seatfirst ? (w.exact ? 4 : 2) : 1;
     static const SeqDev no_seq{};
+    static const SeqRoot no_root{};
     uint64_t want = (n + THREADS - 1) / THREADS;
     const unsigned blocks = (unsigned)(want < (uint64_t)ctx->sms * 8 ? want : (uint64_t)ctx->sms * 8);
-    expand_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a, w.seq ? *w.seq : no_seq, mode, d_off, n, d_out);
+    expand_kernel<<<blocks, THREADS, 0, ctx->stream>>>(a, w.seq ? *w.seq : no_seq, w.seq ? w.tabs->root : no_root, mode, d_off, n, d_out);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return BMC_OK;

@@ -19,6 +19,7 @@
 #include <cstdint>
 #include "deal.cuh"
 #include "seatfirst.cuh"
+#include "distgen.cuh"
 
 namespace bmc {
 
@@ -49,8 +50,19 @@ struct SeqDev {
 
 struct SeqRanges { int hcp_lo, hcp_hi; int len_lo[4], len_hi[4]; int sh_lo[4], sh_hi[4]; bool bad; };
 
+__host__ __device__ __forceinline__ int seq_popc(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+__host__ __device__ __forceinline__ int seq_min(int a, int b) { return a < b ? a : b; }
+__host__ __device__ __forceinline__ int seq_max(int a, int b) { return a > b ? a : b; }
+
 // infer-distgen-params for stage `s` on the remaining cards (f0, f1: lane-layout masks)
-__device__ __forceinline__ SeqRanges seq_infer(const SeqStage &s, uint32_t exhaust, uint32_t f0, uint32_t f1)
+__host__ __device__ __forceinline__ SeqRanges seq_infer(const SeqStage &s, uint32_t exhaust, uint32_t f0, uint32_t f1)
 {
     SeqRanges r;
     r.bad = false;
@@ -58,44 +70,44 @@ __device__ __forceinline__ SeqRanges seq_infer(const SeqStage &s, uint32_t exhau
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t lane = ((k < 2 ? f0 : f1) >> (16 * (k & 1))) & 0x1FFFu;
-        slen[k] = __popc(lane);
-        nlow[k] = __popc(lane & 0x1FFu);
+        slen[k] = seq_popc(lane);
+        nlow[k] = seq_popc(lane & 0x1FFu);
         shcp[k] = (int)((lane >> 9) & 1u) + 2 * (int)((lane >> 10) & 1u) + 3 * (int)((lane >> 11) & 1u) + 4 * (int)((lane >> 12) & 1u);
         total += shcp[k];
     }
     // ---- infer-hcp-range (bridge.cl:1126-1153)
-    const int min_hcp = (exhaust && !s.others_missing_hcp) ? max(total - (int)s.sum_upper_hcp, 0) : 0;
-    const int up_limit = min(total - (int)s.sum_lower_hcp, total);
+    const int min_hcp = (exhaust && !s.others_missing_hcp) ? seq_max(total - (int)s.sum_upper_hcp, 0) : 0;
+    const int up_limit = seq_min(total - (int)s.sum_lower_hcp, total);
     if (!s.has_hcp) {
         if (up_limit < total || min_hcp > 0) { r.hcp_lo = min_hcp; r.hcp_hi = up_limit; }
         else { r.hcp_lo = 0; r.hcp_hi = 64; }                      // no :hcp key: no filter
     } else {
-        r.hcp_lo = max(s.hcp_lo >= 0 ? (int)s.hcp_lo : 0, min_hcp);
-        r.hcp_hi = s.hcp_hi >= 0 ? min((int)s.hcp_hi, up_limit) : up_limit;
+        r.hcp_lo = seq_max(s.hcp_lo >= 0 ? (int)s.hcp_lo : 0, min_hcp);
+        r.hcp_hi = s.hcp_hi >= 0 ? seq_min((int)s.hcp_hi, up_limit) : up_limit;
         if (r.hcp_lo > r.hcp_hi) r.bad = true;
     }
     // ---- infer-suit-ranges (bridge.cl:1192-1234)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const SeqSuit &q = s.suit[k];
-        const int min_len = (exhaust && !q.others_missing) ? max(slen[k] - (int)q.sum_upper, 0) : 0;
-        const int ul = min(slen[k] - (int)q.sum_lower, slen[k]);
+        const int min_len = (exhaust && !q.others_missing) ? seq_max(slen[k] - (int)q.sum_upper, 0) : 0;
+        const int ul = seq_min(slen[k] - (int)q.sum_lower, slen[k]);
         r.sh_lo[k] = 0; r.sh_hi[k] = 64;
         if (!q.has_spec) {
             if (ul < slen[k]) { r.len_lo[k] = min_len; r.len_hi[k] = ul; }
             else { r.len_lo[k] = 0; r.len_hi[k] = nlow[k]; }       // no key: the low-card cap
         } else {
-            const int down = q.lo >= 0 ? max((int)q.lo, min_len) : min_len;
-            const int up = q.hi >= 0 ? min((int)q.hi, ul) : ul;
+            const int down = q.lo >= 0 ? seq_max((int)q.lo, min_len) : min_len;
+            const int up = q.hi >= 0 ? seq_min((int)q.hi, ul) : ul;
             if (down > ul) r.bad = true;
             r.len_lo[k] = down; r.len_hi[k] = up;
             if (s.has_others) {                                      // suit-HCP narrowing only when later defs exist
-                const int ulh = min(shcp[k] - (int)q.sum_lower_third, shcp[k]);
+                const int ulh = seq_min(shcp[k] - (int)q.sum_lower_third, shcp[k]);
                 if (!q.has_third) {
                     if (ulh < shcp[k]) { r.sh_lo[k] = 0; r.sh_hi[k] = ulh; }
                 } else {
-                    r.sh_lo[k] = max(q.third_lo >= 0 ? (int)q.third_lo : 0, 0);
-                    r.sh_hi[k] = q.third_hi >= 0 ? min((int)q.third_hi, ulh) : ulh;
+                    r.sh_lo[k] = seq_max(q.third_lo >= 0 ? (int)q.third_lo : 0, 0);
+                    r.sh_hi[k] = q.third_hi >= 0 ? seq_min((int)q.third_hi, ulh) : ulh;
                     if (r.sh_lo[k] > r.sh_hi[k]) r.bad = true;
                 }
             }
@@ -106,7 +118,7 @@ __device__ __forceinline__ SeqRanges seq_infer(const SeqStage &s, uint32_t exhau
     int sum_lo = 0, sum_hi = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int hi = min(r.len_hi[k], slen[k]), lo = max(r.len_lo[k], 0);
+        const int hi = seq_min(r.len_hi[k], slen[k]), lo = seq_max(r.len_lo[k], 0);
         if (lo > hi) r.bad = true;
         sum_lo += lo;
         sum_hi += hi;
@@ -126,6 +138,92 @@ __device__ __forceinline__ bool seq_hand_ok(const SeqRanges &r, uint32_t m0, uin
         ok = ok && len >= r.len_lo[k] && len <= r.len_hi[k] && sh >= r.sh_lo[k] && sh <= r.sh_hi[k];
     }
     return ok;
+}
+
+// The narrowed ranges as the packed byte test of features.cuh (A = 0x80 - lo, B = 0x7F - hi per byte).
+struct SeqPacked { uint32_t A0, B0, A1, B1, A2, B2; };
+__host__ __device__ __forceinline__ SeqPacked seq_pack(const SeqRanges &r)
+{
+    SeqPacked p;
+    p.A0 = p.B0 = p.A1 = p.B1 = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int llo = seq_max(r.len_lo[k], 0), lhi = seq_min(r.len_hi[k], 13);
+        const int slo = seq_max(r.sh_lo[k], 0), shi = seq_min(r.sh_hi[k], 10);
+        p.A0 |= (uint32_t)(0x80 - llo) << (8 * k); p.B0 |= (uint32_t)(0x7F - seq_max(lhi, 0)) << (8 * k);
+        p.A1 |= (uint32_t)(0x80 - slo) << (8 * k); p.B1 |= (uint32_t)(0x7F - seq_max(shi, 0)) << (8 * k);
+    }
+    const int hlo = seq_max(r.hcp_lo, 0), hhi = seq_max(seq_min(r.hcp_hi, 37), 0);
+    p.A2 = (uint32_t)(0x80 - hlo) | 0x80808000u;               // losers, balanced?, spare byte: unconstrained
+    p.B2 = (uint32_t)(0x7F - hhi) | 0x7F7E0000u;
+    return p;
+}
+__device__ __forceinline__ bool seq_packed_ok(const SeqPacked &p, uint32_t m0, uint32_t m1)
+{
+    const Feat f = hand_features(m0, m1);
+    return in_ranges(f.f0, p.A0, p.B0) && in_ranges(f.f1, p.A1, p.B1) && in_ranges(f.f2, p.A2, p.B2);
+}
+
+// Stage 1 BY RANK: the first ranged seat goes through the root generator, whose narrowed ranges depend on the
+// fixed hands only (bridge.cl:1297-1301 caches it for that reason).  Its admissible hands are enumerated once on
+// the device (distgen.cuh: classes over the remaining deck, weights prod C(n_low_s, l_s)) and a hand is drawn by
+// unranking a uniform R in [0, W) -- what `rand-hand` does with its weighted walk, without the walk.
+struct SeqRoot {
+    ExactTab x;
+    unsigned long long W, S, S_recip, limit;     // hands; floor(2^64 / W); floor(2^64 / S); W S (u >= limit is redrawn)
+    uint32_t low0, low1;                          // available low cards (lane layout, bits 0..8 of each lane)
+    uint32_t full;                                // 1: every low card is available (no deposit needed)
+};
+
+// t-th l-subset of the first n of nine positions = the t-th entry of subset9's size-l list (numeric order puts the
+// subsets that avoid the high positions first).
+__device__ __forceinline__ bool seq_stage1(const PhiloxKey &key, const SeqRoot &root, const LowTabs &T, uint32_t idx_lo, uint32_t idx_hi,
+                                           uint32_t &m0, uint32_t &m1)
+{
+    m0 = m1 = 0u;
+    if (root.W == 0ull) return false;
+    unsigned long long u = 0ull;
+    bool got = false;
+    for (uint32_t att = 0; att < 8u && !got; ++att) {           // u >= W S has probability < W / 2^64
+        uint32_t w[4];
+        philox4x32_10(key, idx_lo, idx_hi, att, STREAM_REFORDER, w);
+        u = ((unsigned long long)w[0] << 32) | w[1];
+        got = u < root.limit;
+    }
+    if (!got) return false;
+    unsigned long long R = sf_mulhi64(u, root.S_recip);
+    unsigned long long rem = u - R * root.S;
+    while (rem >= root.S) { rem -= root.S; ++R; }
+    const ExactTab &x = root.x;
+    const uint32_t b = min(sf_mulhi32((uint32_t)(u >> 32), x.bmul), x.n_bkt - 1u);
+    uint32_t lo = __ldg(x.bkt + b), hi = __ldg(x.bkt + b + 1u);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1u) >> 1;
+        if (__ldg(x.cum + mid) <= R) lo = mid; else hi = mid - 1u;
+    }
+    const uint32_t k = __ldg(x.keys + lo);
+    uint32_t r = (uint32_t)(R - __ldg(x.cum + lo));
+    uint32_t sub[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t l = min((k >> (16 + 4 * s)) & 15u, 9u);
+        const uint32_t n = (uint32_t)__popc((((s < 2) ? root.low0 : root.low1) >> (16 * (s & 1))) & 0x1FFu);
+        const uint32_t c = c_binom.c[n][l];                    // l-subsets of the n available low cards
+        const uint32_t q = c ? r / c : 0u;
+        sub[s] = T.subset9[(T.c9[l][2] + (r - q * c)) & 511u];
+        r = q;
+    }
+    uint32_t l0 = sub[0] | (sub[1] << 16), l1 = sub[2] | (sub[3] << 16);
+    if (!root.full) {
+        // compact subsets -> the available positions: one deposit per word (the diamonds' / spades' bits follow the
+        // clubs' / hearts' in the compact word)
+        const uint32_t nc = (uint32_t)__popc(root.low0 & 0x1FFu), nh = (uint32_t)__popc(root.low1 & 0x1FFu);
+        l0 = deposit_apply(deposit_prepare(root.low0), sub[0] | (sub[1] << nc));
+        l1 = deposit_apply(deposit_prepare(root.low1), sub[2] | (sub[3] << nh));
+    }
+    m0 = l0 | ((k & 0xFu) << 9) | ((k & 0xF0u) << 21);
+    m1 = l1 | ((k & 0xF00u) << 1) | ((k & 0xF000u) << 13);
+    return true;
 }
 
 // Uniform 13-subset of the `m` free cards (f0, f1), attempt `att` of stage stream `stream`.

@@ -199,7 +199,7 @@ def test_tallies_as_hist_base_and_device_hist_base(ctx):
     tallies = (C.c_uint64 * _lib.TALLY_WORDS)()
     st = Stats()
     n = 20000
-    assert L.bmc_sample(h, handle, 7, 0, n, 0, 0, 7, NULL, 0, C.cast(tallies, C.c_void_p), C.byref(st)) == 0     # sample-tallies
+    assert L.bmc_sample(h, handle, 7, 0, n, 0, 0, 7, NULL, 0, C.cast(tallies, C.POINTER(_lib.Tallies)), C.byref(st)) == 0     # sample-tallies
     words = np.ctypeslib.as_array(tallies)
     base = [[v, int(words[4 + 40 * 0 + v])] for v in range(38) if words[4 + 40 * 0 + v]]      # (tallies->base t :hcp 0)
     assert sum(c for _, c in base) == n and {v for v, _ in base} == {15, 16, 17}
@@ -234,7 +234,7 @@ def test_score_tallies_and_multi_device_as_the_shim_calls_them(ctx):
     assert L.bmc_constraints_set_scoring(handle, cs, vul, 4, pr, 2) == 0
     tallies = (C.c_uint64 * _lib.TALLY_WORDS)()
     st = Stats()
-    assert L.bmc_sample(h, handle, 9, 0, 0, 30000, 16384, 8, NULL, 0, C.cast(tallies, C.c_void_p), C.byref(st)) == 0
+    assert L.bmc_sample(h, handle, 9, 0, 0, 30000, 16384, 8, NULL, 0, C.cast(tallies, C.POINTER(_lib.Tallies)), C.byref(st)) == 0
     words = np.ctypeslib.as_array(tallies).astype(np.int64)
     tricks = words[548:548 + 112].reshape(8, 14)
     imps = words[548 + 112:548 + 112 + 392].reshape(8, 49)
