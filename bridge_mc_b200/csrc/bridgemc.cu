@@ -1179,6 +1179,8 @@ struct WaveCfg {                 // what is constant over the waves of one call
 
 static int blocks_per_sm(const void *kernel, size_t smem)
 {
+    // static + dynamic shared memory may exceed the 48 KB a launch gets without asking (the reference-order kernel)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     static const int cap = [] { const char *e = getenv("BMC_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();      // tuning knob
@@ -1319,7 +1321,7 @@ static int class_table_build(bmc_ctx *ctx, const ClassSpec &cs, unsigned long lo
     for (int p = 0; p < DG_PATTERNS; ++p) { pcum[p] = W; poff[p] = (uint32_t)K; W += ps.w[p]; K += ps.cnt[p]; }
     *W_out = W; *K_out = K;
     if (K == 0 || K > EXACT_MAX_CLASSES) { cudaFree(d_w); cudaFree(d_c); return BMC_OK; }
-    const unsigned long long S = scale ? scale : (unsigned long long)((((unsigned __int128)1) << 64) / W);
+    const unsigned long long S = scale ? scale : ~0ull / W;                 // floor((2^64 - 1) / W): fits 64 bits even for W = 1
     unsigned long long *d_pcum = nullptr;
     uint32_t *d_poff = nullptr;
     cudaError_t e = cudaMalloc(&d_pcum, DG_PATTERNS * sizeof(unsigned long long));
@@ -1416,7 +1418,7 @@ static int root_build(bmc_ctx *ctx, bmc_constraints *c, ConsTables *t)
     }
     if (built) {
         root.W = W;
-        root.S = (unsigned long long)((((unsigned __int128)1) << 64) / W);
+        root.S = ~0ull / W;                                  // every hand has exactly S preimages among the u < W S
         root.S_recip = (unsigned long long)((((unsigned __int128)1) << 64) / root.S);
         root.limit = W * root.S;
         root.x.cum = t->x_cum; root.x.keys = t->x_keys; root.x.bkt = t->x_bkt; root.x.bmul = t->x_bmul; root.x.n_bkt = t->x_nbkt;
