@@ -295,7 +295,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner and warnings: not on stdout (one JSON line only)
     bdist.init_process_group("nccl", dev)
 
     numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
