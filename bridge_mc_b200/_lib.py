@@ -64,11 +64,12 @@ class Contract(C.Structure):
 FEATURE_DTYPE = np.dtype([("len", np.uint8, (4,)), ("suit_hcp", np.uint8, (4,)), ("hcp", np.uint8),
                           ("losers", np.uint8), ("balanced", np.uint8), ("bid", np.int8)])
 assert FEATURE_DTYPE.itemsize == 12
+AUCTION_DTYPE = np.dtype([("opener", np.int8), ("opening", np.int8), ("response", np.int8), ("status", np.int8)])
 
 EXPORTS = [
     "bmc_init", "bmc_shutdown", "bmc_last_error", "bmc_version", "bmc_host_alloc", "bmc_host_free",
     "bmc_shape_table", "bmc_constraints_create", "bmc_constraints_destroy", "bmc_constraints_set_mode", "bmc_constraints_set_reference_order", "bmc_constraints_set_jit", "bmc_constraints_jit_ms", "bmc_constraints_mode", "bmc_constraints_primary", "bmc_constraints_primary_hcp",
-    "bmc_scheme_create", "bmc_scheme_set_jit", "bmc_scheme_jit_ms", "bmc_filter_dev",
+    "bmc_auction", "bmc_auction_dev", "bmc_scheme_create", "bmc_scheme_set_jit", "bmc_scheme_jit_ms", "bmc_filter_dev",
     "bmc_constraints_set_scoring", "bmc_constraints_primary_acceptance", "bmc_distgen", "bmc_sample_indices", "bmc_sample_indices_dev", "bmc_expand", "bmc_expand_dev", "bmc_sample_multi",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
     "bmc_match_points", "bmc_score_tally", "bmc_hist_base", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
@@ -126,6 +127,8 @@ def load():
                                    C.POINTER(Stats)]
     L.bmc_filter.argtypes = [vp, vp, vp, vp, u64, vp, vp]
     L.bmc_filter_dev.argtypes = [vp, vp, vp, vp, u64, vp, vp]
+    L.bmc_auction.argtypes = [vp, vp, C.POINTER(vp), C.c_int, vp, u64, vp]
+    L.bmc_auction_dev.argtypes = [vp, vp, C.POINTER(vp), C.c_int, vp, u64, vp]
     L.bmc_scheme_set_jit.argtypes = [vp, C.c_int]
     L.bmc_scheme_jit_ms.argtypes = [vp]
     L.bmc_scheme_jit_ms.restype = C.c_float

@@ -525,34 +525,24 @@ def auction_rules(dealer: int, calls):
     return [None if not fs else fs[0] if len(fs) == 1 else _and(*fs) for fs in forms]
 
 
-def first_two_calls(records, engine: Engine | None = None):
-    """Batched class-`bidding` `next` (bidding.cl:463-480) over deal records, dealer = seat 0: for every deal the
-    first seat that has an opening bid, that bid, and partner's answer over the matching response scheme.
-    Returns (opener int8[n] (-1: passed out), opening list, response list); everything is evaluated on the GPU
-    (two bmc_filter passes per distinct opening)."""
+def first_two_calls(records, engine: Engine | None = None, dealer: int = 0):
+    """Batched class-`bidding` `next` (bidding.cl:463-480) over deal records: for every deal the first seat, from the
+    dealer on, that has an opening bid, that bid, and partner's answer over the response scheme the opening selects.
+    One library call (bmc_auction: the whole driver runs in one kernel).
+    Returns (opener int8[n] (-1: passed out), opening list, response list)."""
     eng = engine or Engine.default()
-    rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
-    _, feats = eng.filter(rec, None, openings.scheme())
-    bids = feats["bid"].astype(np.int64)                       # [n, 4]
-    if (bids == -2).any():
+    tables = [response_scheme(b) for b in openings.bids()]
+    out = eng.auction(records, openings.scheme(), [t.scheme() if t is not None else None for t in tables], dealer)
+    if (out["status"] == 1).any():
         raise BidError("illegal function call while evaluating the openings")
-    has = bids >= 0
-    opener = np.where(has.any(axis=1), has.argmax(axis=1), -1).astype(np.int8)
-    n = rec.shape[0]
-    opening = [None] * n
-    response = [None] * n
-    open_idx = np.where(opener >= 0, bids[np.arange(n), np.maximum(opener, 0)], -1)
-    for k in np.unique(open_idx[open_idx >= 0]):
-        bid = openings.rows[int(k)][0]
-        sel = np.nonzero(open_idx == k)[0]
-        for i in sel:
-            opening[i] = bid
-        scheme = response_scheme(bid)
-        if scheme is None:
-            continue
-        _, f2 = eng.filter(rec[sel], None, scheme.scheme())
-        partner = (opener[sel].astype(np.int64) + 2) % 4
-        rb = f2["bid"][np.arange(sel.size), partner].astype(np.int64)
-        for i, r in zip(sel, rb):
-            response[i] = "error" if r == -2 else (None if r < 0 else scheme.rows[int(r)][0])
-    return opener, opening, response
+    names = openings.bids()
+    opening = [None if k < 0 else names[k] for k in out["opening"].tolist()]
+    response = []
+    for k, r, st in zip(out["opening"].tolist(), out["response"].tolist(), out["status"].tolist()):
+        if st == 2:
+            response.append("error")
+        elif k < 0 or r < 0 or tables[k] is None:
+            response.append(None)
+        else:
+            response.append(tables[k].rows[r][0])
+    return out["opener"].copy(), opening, response

@@ -301,6 +301,60 @@ __global__ void __launch_bounds__(THREADS) expand_kernel(const __grid_constant__
 static_assert(sizeof(FeatOut) == sizeof(bmc_features), "FeatOut mirrors bmc_features");
 
 // ---------------------------------------------------------------------------
+// K2b: the auction driver of class `bidding` (`next`, bidding.cl:463-480) over a deal set: the first seat, from
+// the dealer on, that has a bid over the opening scheme; the deal is "rolled" so that the opener sits first; the
+// response scheme is the one the opening selects ((2 c) -> 2c-responses, NT -> (nt-responses level), a one-level
+// suit -> (basic-responses bid), otherwise none) and the opener's partner chooses over it.
+// ---------------------------------------------------------------------------
+constexpr int AUCTION_MAX_OPENINGS = 32;
+struct AuctionDev { SchemeDev open; SchemeDev resp[AUCTION_MAX_OPENINGS]; int dealer; };
+struct AuctionOut { int8_t opener, opening, response, status; };        // same layout as bmc_auction_row
+static_assert(sizeof(AuctionOut) == sizeof(bmc_auction_row), "AuctionOut mirrors bmc_auction_row");
+
+// choose-bid over one table: first row whose form holds; -2 = an illegal form was reached first; -1 = nil
+__device__ __forceinline__ int choose_row(const SchemeDev &sch, const uint8_t *fb)
+{
+    for (uint32_t row = 0; row < sch.n_rows; ++row) {
+        bool err = false;
+        const bool v = run_program(sch.code + __ldg(sch.row_off + row), fb, err);
+        if (err) return -2;
+        if (v) return (int)row;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) auction_kernel(const __grid_constant__ AuctionDev a, const uint4 *__restrict__ rec,
+                                                      unsigned long long n, AuctionOut *__restrict__ out)
+{
+    __shared__ uint32_t s_feat[8 * FEAT_SCRATCH_WORDS];
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;                                   // the interpreter keeps per-lane state: lanes may diverge freely
+    const uint4 r = rec[i];
+    const Planes pl = {r.x, r.y, r.z, r.w};
+    uint32_t *scratch = s_feat + (threadIdx.x >> 5) * FEAT_SCRATCH_WORDS;
+    AuctionOut o = {-1, -1, -1, 0};
+    for (int p = 0; p < 4 && o.opener < 0 && o.status == 0; ++p) {
+        const int seat = (a.dealer + p) & 3;
+        uint32_t m0, m1;
+        seat_words(pl, seat, m0, m1);
+        const int bid = choose_row(a.open, feat_store(scratch, threadIdx.x & 31u, hand_features(m0, m1)));
+        if (bid == -2) o.status = 1;
+        else if (bid >= 0) { o.opener = (int8_t)seat; o.opening = (int8_t)bid; }
+    }
+    if (o.opener >= 0) {
+        const SchemeDev &rs = a.resp[o.opening];
+        if (rs.n_rows) {
+            uint32_t m0, m1;
+            seat_words(pl, (o.opener + 2) & 3, m0, m1);
+            const int bid = choose_row(rs, feat_store(scratch, threadIdx.x & 31u, hand_features(m0, m1)));
+            if (bid == -2) o.status = 2;
+            else o.response = (int8_t)bid;
+        }
+    }
+    out[i] = o;
+}
+
+// ---------------------------------------------------------------------------
 // K4: scoring
 // ---------------------------------------------------------------------------
 // contract-score / base-score / match-points and the stand-in trick source live in score.cuh (shared with the
@@ -2125,6 +2179,62 @@ int bmc_filter_dev(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *
     std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     return filter_core(ctx, cons, scheme, (const uint4 *)records_dev, n, (uint8_t *)accept_dev, (bmc_features *)feats_dev);
+}
+
+// ---- auction driver (bidding.cl:457-480) -------------------------------------------------------------------------
+static int auction_core(bmc_ctx *ctx, const bmc_scheme *openings, const bmc_scheme *const *responses, int dealer, const uint4 *d_rec,
+                        uint64_t k, bmc_auction_row *d_out)
+{
+    AuctionDev a{};
+    a.dealer = dealer & 3;
+    { int rc = scheme_upload(ctx, openings, a.open); if (rc) return rc; }
+    for (uint32_t r = 0; r < a.open.n_rows; ++r) {
+        int rc = scheme_upload(ctx, responses ? responses[r] : nullptr, a.resp[r]);
+        if (rc) return rc;
+    }
+    auction_kernel<<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(a, d_rec, k, reinterpret_cast<AuctionOut *>(d_out));
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BMC_OK;
+}
+
+int bmc_auction(bmc_ctx *ctx, const bmc_scheme *openings, const bmc_scheme *const *responses, int dealer, const bmc_record *records,
+                uint64_t n, bmc_auction_row *out)
+{
+    if (!ctx || !openings || !out) return fail(BMC_E_INVALID, "bmc_auction: NULL argument");
+    if (openings->row_off.size() > (size_t)AUCTION_MAX_OPENINGS) return fail(BMC_E_CAPACITY, "bmc_auction: at most 32 opening rows");
+    if (dealer < 0 || dealer > 3) return fail(BMC_E_INVALID, "bmc_auction: dealer is a seat 0..3");
+    if (n == 0) return BMC_OK;
+    if (!records) return fail(BMC_E_INVALID, "records is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t chunk = 1ull << 22;
+    const uint64_t m = n < chunk ? n : chunk;
+    { int rc = ensure_scratch(ctx, m * (sizeof(bmc_record) + sizeof(bmc_auction_row))); if (rc) return rc; }
+    uint4 *d_rec = (uint4 *)ctx->d_rec;
+    bmc_auction_row *d_out = (bmc_auction_row *)((char *)ctx->d_rec + m * sizeof(bmc_record));
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t k = n - off < chunk ? n - off : chunk;
+        CUDA_TRY(cudaMemcpyAsync(d_rec, records + off, k * sizeof(bmc_record), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = auction_core(ctx, openings, responses, dealer, d_rec, k, d_out);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + off, d_out, k * sizeof(bmc_auction_row), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return BMC_OK;
+}
+
+int bmc_auction_dev(bmc_ctx *ctx, const bmc_scheme *openings, const bmc_scheme *const *responses, int dealer, const void *records_dev,
+                    uint64_t n, void *out_dev)
+{
+    if (!ctx || !openings || !out_dev) return fail(BMC_E_INVALID, "bmc_auction_dev: NULL argument");
+    if (openings->row_off.size() > (size_t)AUCTION_MAX_OPENINGS) return fail(BMC_E_CAPACITY, "bmc_auction_dev: at most 32 opening rows");
+    if (dealer < 0 || dealer > 3) return fail(BMC_E_INVALID, "bmc_auction_dev: dealer is a seat 0..3");
+    if (n == 0) return BMC_OK;
+    if (!records_dev) return fail(BMC_E_INVALID, "records_dev is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return auction_core(ctx, openings, responses, dealer, (const uint4 *)records_dev, n, (bmc_auction_row *)out_dev);
 }
 
 // ---- scoring --------------------------------------------------------------------

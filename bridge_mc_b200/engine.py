@@ -308,6 +308,16 @@ class Engine:
         check(self._L.bmc_filter_dev(self._h, cons._h if cons else None, scheme._h if scheme else None, records_ptr, n,
                                      accept_ptr or None, feats_ptr or None))
 
+    def auction(self, records: np.ndarray, openings: Scheme, responses, dealer: int = 0) -> np.ndarray:
+        """bmc_auction: class `bidding` / `next` (bidding.cl:457-480) over a deal set.  `responses` = one Scheme (or None)
+        per row of `openings`.  Returns a structured array (opener, opening, response, status)."""
+        rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
+        n = rec.shape[0]
+        arr = (C.c_void_p * max(1, len(responses)))(*[(r._h if r is not None else None) for r in responses])
+        out = np.empty(n, dtype=_lib.AUCTION_DTYPE)
+        check(self._L.bmc_auction(self._h, openings._h, arr, dealer, rec.ctypes.data if n else None, n, out.ctypes.data))
+        return out
+
     # ---- scoring ----------------------------------------------------------------
     def score(self, contracts, vulnerable, tricks: np.ndarray) -> np.ndarray:
         """bmc_score: tricks uint8[n, n_contracts] -> base scores int32[n, n_contracts]."""

@@ -289,6 +289,19 @@ int bmc_filter(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *sche
 int bmc_filter_dev(bmc_ctx *ctx, const bmc_constraints *cons, const bmc_scheme *scheme,
                    const void *records_dev, uint64_t n, void *accept_dev, void *feats_dev);
 
+/* ---- the auction driver: class `bidding` / `next` (bidding.cl:457-480) over a deal set --------------------------
+ * For every deal: the first seat, from `dealer` on (N E S W order), that has a bid over `openings` (choose-bid,
+ * first matching row) opens; its partner -- the deal "rolled" so that the opener sits first -- answers over the
+ * scheme that opening selects: responses[row] for opening row `row` (what `next` installs as bid-scheme: 2c-responses
+ * after (2 c), (nt-responses level) after NT, (basic-responses bid) after a one-level suit; NULL = none).
+ * opener -1 = passed out; opening / response = row of the scheme (-1 = nil); status 1 / 2 = evaluation reached an
+ * illegal form in the openings / the responses (the reference signals an error there). */
+typedef struct { int8_t opener, opening, response, status; } bmc_auction_row;
+int bmc_auction(bmc_ctx *ctx, const bmc_scheme *openings, const bmc_scheme *const *responses, int dealer,
+                const bmc_record *records, uint64_t n, bmc_auction_row *out);
+int bmc_auction_dev(bmc_ctx *ctx, const bmc_scheme *openings, const bmc_scheme *const *responses, int dealer,
+                    const void *records_dev, uint64_t n, void *out_dev);
+
 /* ---- scoring: contract-score (bridge.cl:3045-3069), base-score
  * (compscore.cl:94-100), match-points (compscore.cl:127-131) ------------------ */
 /* scores[i*n_contracts + c] = base-score of contracts[c] making tricks[i*n_contracts + c]

@@ -562,3 +562,50 @@ def test_small_requests_are_unbiased(engine):
     assert d._next_index == used and not np.array_equal(a, b)
     rows = McCase(Deal(engine=engine, seed=9), [lambda t, n, e, s, w: 12 in s.suits[3]]).sim(50)
     assert len(rows) == 50
+
+
+# ---- the auction driver on the device (class bidding / next, bidding.cl:457-480) ---------------------------------------
+def test_auction_driver_kernel(engine):
+    """bmc_auction: one kernel finds the opener from any dealer, the opening, the response scheme that opening selects
+    and partner's answer.  Against the oracle's choose-bid per seat (openings, nt-responses, 2C-responses), the Python
+    restatement of good-opening? for basic-responses, and the reference's own example deal (bidding.cl:482-487)."""
+    from oracle import rule_eval as R
+    from bridge_mc_b200 import sexp
+    rec, _, _ = engine.sample(None, n_raw=30_000, seed=43)
+    m = seat_masks(rec)
+    op = O.choose_bid_batch(0, m.reshape(-1)).reshape(-1, 4)
+    f = O.features_batch(m.reshape(-1)).reshape(-1, 4, 11)
+    names = bidding.openings.bids()
+    tables = [bidding.response_scheme(b) for b in names]
+    schemes = [t.scheme() if t is not None else None for t in tables]
+    parsed = {k: [(b, sexp.read(frm)) for b, frm in t.rows] for k, t in enumerate(tables) if t is not None}
+    for dealer in range(4):
+        out = engine.auction(rec, bidding.openings.scheme(), schemes, dealer)
+        order = [(dealer + p) % 4 for p in range(4)]
+        for i in range(0, rec.shape[0], 5 if dealer else 1):
+            seats = [k for k in order if op[i, k] >= 0]
+            if not seats:
+                assert tuple(out[i]) == (-1, -1, -1, 0)
+                continue
+            k = seats[0]
+            row = int(op[i, k])
+            assert (out["opener"][i], out["opening"][i]) == (k, row), (dealer, i)
+            partner = (k + 2) % 4
+            if tables[row] is None:
+                assert out["response"][i] == -1 and out["status"][i] == 0
+                continue
+            d = {"lens": f[i, partner, 0:4].tolist(), "power": f[i, partner, 4:8].tolist(), "hcp": int(f[i, partner, 8]),
+                 "losers": int(f[i, partner, 9]), "balanced": bool(f[i, partner, 10])}
+            try:
+                want = next((j for j, (_, frm) in enumerate(parsed[row]) if R._truth(R.evaluate(frm, d))), -1)
+                assert (out["response"][i], out["status"][i]) == (want, 0), (dealer, i, names[row])
+            except R.IllegalCall:
+                assert out["status"][i] == 2, (dealer, i, names[row])
+    assert (out["status"] == 2).any()                   # the un-spliced list of bidding.cl:249 is reached by some deals
+    deal = [str2hand("N: ♠ Q1097 ♥ 3 ♦ KJ1063 ♣ K102"), str2hand("E: ♠ 62 ♥ AJ75 ♦ A942 ♣ 987"),
+            str2hand("S: ♠ AKJ5 ♥ K1064 ♦ Q87 ♣ A6"), str2hand("W: ♠ 843 ♥ Q982 ♦ 5 ♣ QJ543")]
+    one = engine.auction(cards.pack_deals([deal]), bidding.openings.scheme(), schemes, 0)[0]
+    ref = [O.choose_bid(0, h) for h in deal]
+    first = next(i for i, k in enumerate(ref) if k >= 0)
+    assert (one["opener"], one["opening"]) == (first, ref[first])
+    assert engine.auction(np.empty((0, 2), np.uint64), bidding.openings.scheme(), schemes).shape == (0,)
