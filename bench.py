@@ -250,15 +250,14 @@ class ClockSampler:
 # GPU arm
 # ---------------------------------------------------------------------------
 def source_hash():
-    """sha256 over the library's sources: profiles/roofline_inputs.json records it with every ncu-derived figure, so a
-    figure measured on an older kernel is reported as stale instead of being silently reused."""
+    """sha256 over the sources of the sampling kernels: profiles/roofline_inputs.json records it with every ncu-derived
+    figure, so a figure measured on an older kernel is reported as stale instead of being silently reused."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "bridge_mc_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".hpp", ".h")):
-            h.update(name.encode())
-            h.update(open(os.path.join(d, name), "rb").read())
+    for name in ("bytecode.h", "deal.cuh", "features.cuh", "seatfirst.cuh", "score.cuh", "kernels.cuh", "reforder.cuh", "distgen.cuh"):
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
 
 

@@ -609,3 +609,28 @@ def test_auction_driver_kernel(engine):
     first = next(i for i, k in enumerate(ref) if k >= 0)
     assert (one["opener"], one["opening"]) == (first, ref[first])
     assert engine.auction(np.empty((0, 2), np.uint64), bidding.openings.scheme(), schemes).shape == (0,)
+
+
+def test_play_training_setup(engine):
+    """training.cl:58-79 (a22): build + longest-suit x 2 + four estimator calls + better-score; the estimator is passed
+    in (play-deal is not part of the library) -- here a stand-in that counts the declaring line's HCP"""
+    from types import SimpleNamespace
+    from bridge_mc_b200 import training
+    calls = []
+
+    def fake_play_deal(trump, declarer, left, dummy, right):
+        hcp = sum(max(r - 8, 0) for h in (declarer, dummy) for s in h.suits for r in s)
+        calls.append(trump)
+        return SimpleNamespace(tricks=hcp // 3 + (1 if trump else 0), first_lead=(0, 0))
+
+    drill = training.play_training(fake_play_deal, training.full_random(engine, seed=77))
+    deal = drill["deal"]
+    assert len(deal) == 4 and sorted(c for h in deal for c in h.cards()) == list(range(52))
+    ns, we = training.longest_suit(*deal), training.longest_suit(*deal[1:], deal[0])
+    assert calls == [ns, None, we, None]                                  # the four candidates, in play-training's order
+    best = max(range(4), key=lambda i: ([sum(max(r - 8, 0) for h in (c[0][0], c[0][2]) for s in h.suits for r in s) // 3
+                                         + (1 if c[1] else 0) for c in training.drill_candidates(deal)][i], -i))
+    assert (drill["hands"], drill["trump"]) == training.drill_candidates(deal)[best]
+    # longest-suit: later suits win ties (bridge.cl:3032 `>=`)
+    h = [str2hand("♣ AKQ2 ♦ 432 ♥ 432 ♠ 432"), None, str2hand("♣ 43 ♦ 765 ♥ 8765 ♠ 8765"), None]
+    assert training.longest_suit(*h) == "S"

@@ -37,7 +37,7 @@ cap = n if cfg in ("c1", "ref") else n // 16
 if cfg in ("c1", "ref"):
     cap = min(cap, 1 << 24)
 for i in range(3):
-    rec, tal, st = eng.sample(cons, n_raw=n, first_index=i << 40, cap=cap, tally_mask=mask)
+    rec, tal, st = eng.sample(cons, n_raw=n, first_index=i << 40, cap=cap, tally_mask=mask, wave=n)      # one launch per call
     print(cfg, "raw", tal["raw"], "acc", tal["accepted"], "ms", round(st.kernel_ms, 3),
           "deals/s %.3e" % (tal["raw"] / st.kernel_ms * 1e3), "acc/s %.3e" % (tal["accepted"] / st.kernel_ms * 1e3),
           "mode", cons.mode if cons else 1)
