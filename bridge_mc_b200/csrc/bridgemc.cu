@@ -80,11 +80,12 @@ __device__ __forceinline__ bool reforder_deal(const SampleArgs &a, const SeqDev 
             const SeqRanges r = seq_infer(st, q.exhaust, f0, f1);
             const SeqPacked pk = seq_pack(r);
             bad = bad || r.bad;
+            unsigned long long M1, M2, M4;
+            seq_hcp_planes(f0, f1, M1, M2, M4);
             uint32_t att = 0;
             bool need = valid && !bad;
             while (need) {
-                const bool clean = seq_draw13(a.key, il, ih, STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, h0, h1);
-                if (clean && seq_packed_ok(pk, h0, h1)) need = false;
+                if (seq_attempt(a.key, il, ih, STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, pk, r.hcp_lo, r.hcp_hi, M1, M2, M4, h0, h1)) need = false;
                 else if (++att >= SEQ_MAX_ATTEMPTS) { bad = true; need = false; }
             }
         }
@@ -140,6 +141,8 @@ __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_c
     bool busy = false, fresh = false;
     uint32_t off = 0, lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0, f0 = 0, f1 = 0, j = 0, att = 0;
     SeqPacked pk = {0, 0, 0, 0, 0, 0};
+    unsigned long long M1 = 0, M2 = 0, M4 = 0;                // honour weight planes of the remaining deck, compact coordinates
+    int hcp_lo = 0, hcp_hi = 64;
     uint32_t batch = 0;
 
     auto run_done = [&](unsigned count) {                     // deal-all + tallies + store for up to 32 complete deals
@@ -209,7 +212,10 @@ __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_c
                 else {
                     const SeqRanges r = seq_infer(q.st[j], q.exhaust, f0, f1);
                     if (r.bad) { busy = false; ++n_bad; }      // the reference signals bad-range for this build
-                    else { pk = seq_pack(r); att = 0u; }
+                    else {
+                        pk = seq_pack(r); hcp_lo = r.hcp_lo; hcp_hi = r.hcp_hi; att = 0u;
+                        seq_hcp_planes(f0, f1, M1, M2, M4);
+                    }
                 }
                 fresh = false;
             }
@@ -227,20 +233,44 @@ __global__ void __launch_bounds__(THREADS) sample_reforder_kernel(const __grid_c
                 while (td - hd >= 32u) run_done(32u);
             }
         }
-        // 4. one rejection attempt per busy lane
-        if (busy) {
+        // 4. rejection: every busy lane draws SEQ_DRAWS candidates (cheap: one Philox call, Floyd's thirteen draws, HCP in
+        //    compact coordinates) and keeps the first whose HCP fits; that one is deposited and fully tested.  Attempts
+        //    are consumed strictly in order, so the accepted hand is the first admissible one of the index's stream --
+        //    exactly what the one-thread form (reforder_deal) finds.
+        if (__any_sync(0xFFFFFFFFu, busy)) {
             const SeqStage &st = q.st[j < 4u ? j : 3u];
             const unsigned long long idx = a.first + off;
-            uint32_t x0, x1;
-            const bool clean = seq_draw13(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), STREAM_REFORDER + j, att, st.m, st.thresh, f0, f1, x0, x1);
-            if (clean && seq_packed_ok(pk, x0, x1)) {
-                const uint32_t k = (uint32_t)st.seat;
-                if (k & 1u) { lo0 |= x0; lo1 |= x1; }
-                if (k & 2u) { hi0 |= x0; hi1 |= x1; }
-                f0 &= ~x0; f1 &= ~x1;
-                ++j;
-                fresh = true;
-            } else if (++att >= SEQ_MAX_ATTEMPTS) { busy = false; ++n_bad; }
+            unsigned long long cand = 0ull;
+            uint32_t cand_att = 0u;
+            bool have = false;
+            if (busy) {
+#pragma unroll 1
+                for (uint32_t d = 0; d < SEQ_DRAWS; ++d) {
+                    unsigned long long c;
+                    const bool clean = seq_draw_floyd(a.key, (uint32_t)idx, (uint32_t)(idx >> 32), STREAM_REFORDER + j, att + d, st.m, st.thresh, c);
+                    const int hcp = seq_compact_hcp(c, M1, M2, M4);
+                    if (!have && clean && hcp >= hcp_lo && hcp <= hcp_hi) { have = true; cand = c; cand_att = att + d; }
+                }
+            }
+            bool ok = false;
+            uint32_t x0 = 0, x1 = 0;
+            if (have) {
+                seq_expand(cand, f0, f1, x0, x1);
+                ok = seq_packed_ok(pk, x0, x1);
+            }
+            if (busy) {
+                if (ok) {
+                    const uint32_t k = (uint32_t)st.seat;
+                    if (k & 1u) { lo0 |= x0; lo1 |= x1; }
+                    if (k & 2u) { hi0 |= x0; hi1 |= x1; }
+                    f0 &= ~x0; f1 &= ~x1;
+                    ++j;
+                    fresh = true;
+                } else {
+                    att = have ? cand_att + 1u : att + SEQ_DRAWS;
+                    if (att >= SEQ_MAX_ATTEMPTS) { busy = false; ++n_bad; }
+                }
+            }
         }
     }
     if (td - hd) run_done(td - hd);
@@ -954,14 +984,13 @@ static int build_seq(bmc_constraints *c, int n_defs)
             }
             qs.sum_upper = (int16_t)u; qs.sum_lower = (int16_t)l; qs.sum_lower_third = (int16_t)lt;
         }
-        for (int w = 0; w < 13; ++w) {
+        // Floyd's 13 bounded draws (ranges m-12 .. m), four per Philox word, the last one alone (reforder.cuh seq_draw_floyd)
+        for (int g = 0; g < 4; ++g) {
             uint64_t N = 1;
-            for (int d = 0; d < 4; ++d) {
-                const int n = (int)m - 4 * w - d;
-                if (n >= 2) N *= (uint64_t)n;
-            }
-            st.thresh[w] = (uint32_t)((1ull << 32) % N);
+            for (int d = 0; d < (g < 3 ? 4 : 1); ++d) N *= (uint64_t)((int)m - 12 + 4 * g + d);
+            st.thresh[g] = (uint32_t)((1ull << 32) % N);
         }
+        for (int g = 4; g < 13; ++g) st.thresh[g] = 0;
         if (j == 0 || m > 13u) { cap[n_fixed + j] = 0; ++sampled; }
     }
     q.n_stages = (uint32_t)n_defs;

@@ -25,6 +25,7 @@ namespace bmc {
 
 constexpr uint32_t STREAM_REFORDER = 16u, STREAM_REFORDER_REST = 31u;
 constexpr uint32_t SEQ_MAX_ATTEMPTS = 1u << 14;     // candidates per seat before the deal is given up (counted in `voided`)
+constexpr uint32_t SEQ_DRAWS = 4u;                  // candidates a lane draws per pass of the pipeline
 
 struct SeqSuit {
     int8_t has_spec, lo, hi, has_third, third_lo, third_hi;      // own spec; -1 = nil
@@ -226,37 +227,83 @@ __device__ __forceinline__ bool seq_stage1(const PhiloxKey &key, const SeqRoot &
     return true;
 }
 
-// Uniform 13-subset of the `m` free cards (f0, f1), attempt `att` of stage stream `stream`.
-// Returns false if a Lemire check failed (the caller simply tries again).
-__device__ __forceinline__ bool seq_draw13(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, uint32_t stream, uint32_t att,
-                                           uint32_t m, const uint32_t *__restrict__ thresh, uint32_t f0, uint32_t f1,
-                                           uint32_t &h0, uint32_t &h1)
+// Uniform 13-subset of the m <= 39 remaining cards as a mask over COMPACT positions (the free cards in card order),
+// attempt `att` of stage stream `stream`: Floyd's algorithm -- for j = m-13 .. m-1 draw t uniform on [0, j] and take
+// t, or j if t is taken already -- thirteen bounded draws, the mixed-radix digits (4 + 4 + 4 + 1) of the four words of
+// ONE Philox call, each word with Lemire's remainder test (thresh[0..3] = 2^32 mod the product of its ranges).
+// Returns false if a test failed (the caller simply moves on to the next attempt).
+__device__ __forceinline__ bool seq_draw_floyd(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, uint32_t stream, uint32_t att,
+                                               uint32_t m, const uint32_t *__restrict__ thresh, unsigned long long &c)
 {
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    uint32_t x = 0, c0 = 0, c1 = 0;
-    int r = 13;
+    uint32_t w[4];
+    philox4x32_10(key, idx_lo, idx_hi, att, stream, w);
     bool ok = true;
-    for (uint32_t v = 0, n = m; n >= 1u; ++v, --n) {
-        uint32_t u = 0;
-        if (n >= 2u) {
-            if ((v & 3u) == 0u) {
-                if ((v & 15u) == 0u) philox4x32_10(key, idx_lo, idx_hi, att * 4u + (v >> 4), stream, w);
-                const uint32_t sel = (v >> 2) & 3u;
-                x = sel == 0u ? w[0] : sel == 1u ? w[1] : sel == 2u ? w[2] : w[3];
-            }
-            mul_wide(x, n, x, u);
-            if ((v & 3u) == 3u || n == 2u) ok = ok && !(x < thresh[v >> 2]);
+    c = 0ull;
+    uint32_t j = m - 13u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t x = w[g];
+#pragma unroll
+        for (int d = 0; d < (g < 3 ? 4 : 1); ++d, ++j) {
+            uint32_t t;
+            mul_wide(x, j + 1u, x, t);
+            const unsigned long long taken = (c >> t) & 1ull;
+            c |= 1ull << (taken ? j : t);
         }
-        const uint32_t take = (int)u < r ? 1u : 0u;
-        r -= (int)take;
-        if (v < 32u) c0 |= take << v; else c1 |= take << (v - 32u);
+        ok = ok && !(x < thresh[g]);
     }
+    return ok;
+}
+
+// Honour cards of the remaining deck in compact coordinates, as three weight planes: HCP of a compact subset c =
+// popc(c & M1) + 2 popc(c & M2) + 4 popc(c & M4) (J = 1: M1; Q = 2: M2; K = 3: M1 and M2; A = 4: M4).
+__device__ __forceinline__ void seq_hcp_planes(uint32_t f0, uint32_t f1, unsigned long long &M1, unsigned long long &M2, unsigned long long &M4)
+{
+    M1 = M2 = M4 = 0ull;
+    const uint32_t base1 = (uint32_t)__popc(f0);
+#pragma unroll
+    for (int wd = 0; wd < 2; ++wd) {
+        const uint32_t f = wd ? f1 : f0, base = wd ? base1 : 0u;
+#pragma unroll
+        for (int ln = 0; ln < 2; ++ln)
+#pragma unroll
+            for (int lev = 0; lev < 4; ++lev) {
+                const uint32_t b = 16u * ln + 9u + lev;
+                if ((f >> b) & 1u) {
+                    const unsigned long long bit = 1ull << (base + (uint32_t)__popc(f & ((1u << b) - 1u)));
+                    if (lev == 0 || lev == 2) M1 |= bit;
+                    if (lev == 1 || lev == 2) M2 |= bit;
+                    if (lev == 3) M4 |= bit;
+                }
+            }
+    }
+}
+__device__ __forceinline__ int seq_compact_hcp(unsigned long long c, unsigned long long M1, unsigned long long M2, unsigned long long M4)
+{
+    return __popcll(c & M1) + 2 * __popcll(c & M2) + 4 * __popcll(c & M4);
+}
+
+// compact subset -> the hand in lane layout (software deposit into the free positions)
+__device__ __forceinline__ void seq_expand(unsigned long long c, uint32_t f0, uint32_t f1, uint32_t &h0, uint32_t &h1)
+{
     const uint32_t n0 = __popc(f0);
-    const uint32_t a = n0 >= 32u ? c0 : (c0 & ((1u << n0) - 1u));
-    const uint32_t b = n0 >= 32u ? c1 : __funnelshift_r(c0, c1, n0);
+    const uint32_t a = n0 >= 32u ? (uint32_t)c : ((uint32_t)c & ((1u << n0) - 1u));
+    const uint32_t b = (uint32_t)(c >> n0);
     h0 = deposit_apply(deposit_prepare(f0), a);
     h1 = deposit_apply(deposit_prepare(f1), b);
-    return ok;
+}
+
+// One rejection attempt in full: draw, HCP in compact space (most candidates die here, cheaply), deposit, packed test.
+__device__ __forceinline__ bool seq_attempt(const PhiloxKey &key, uint32_t idx_lo, uint32_t idx_hi, uint32_t stream, uint32_t att, uint32_t m,
+                                            const uint32_t *__restrict__ thresh, uint32_t f0, uint32_t f1, const SeqPacked &pk, int hcp_lo,
+                                            int hcp_hi, unsigned long long M1, unsigned long long M2, unsigned long long M4, uint32_t &h0, uint32_t &h1)
+{
+    unsigned long long c;
+    if (!seq_draw_floyd(key, idx_lo, idx_hi, stream, att, m, thresh, c)) return false;
+    const int hcp = seq_compact_hcp(c, M1, M2, M4);
+    if (hcp < hcp_lo || hcp > hcp_hi) return false;
+    seq_expand(c, f0, f1, h0, h1);
+    return seq_packed_ok(pk, h0, h1);
 }
 
 }  // namespace bmc
