@@ -249,13 +249,16 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
-def source_hash():
-    """sha256 over the sources of the sampling kernels: profiles/roofline_inputs.json records it with every ncu-derived
-    figure, so a figure measured on an older kernel is reported as stale instead of being silently reused."""
+SAMPLER_SOURCES = ("bytecode.h", "deal.cuh", "features.cuh", "seatfirst.cuh", "score.cuh", "kernels.cuh")
+
+
+def source_hash(files=SAMPLER_SOURCES):
+    """sha256 over the sources a kernel is built from: profiles/roofline_inputs.json records it (and the file list) with
+    every ncu-derived figure, so a figure measured on an older kernel is reported as stale instead of being silently reused."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "bridge_mc_b200", "csrc")
-    for name in ("bytecode.h", "deal.cuh", "features.cuh", "seatfirst.cuh", "score.cuh", "kernels.cuh", "reforder.cuh", "distgen.cuh"):
+    for name in files:
         h.update(name.encode())
         h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
@@ -273,10 +276,11 @@ def roofline_inputs(kernel_key):
     if kernel_key not in table:
         raise SystemExit(f"bench.py: no roofline inputs for {kernel_key} in {path}")
     ent = table[kernel_key]
-    stale = ent.get("src_hash") != source_hash()
+    now = source_hash(tuple(ent.get("src_files") or SAMPLER_SOURCES))
+    stale = ent.get("src_hash") != now
     if stale:
         print(f"bench.py: WARNING roofline inputs for {kernel_key} were measured on sources {ent.get('src_hash')}, "
-              f"current {source_hash()}: re-profile (tools/roofline_inputs.py)", file=sys.stderr)
+              f"current {now}: re-profile (tools/roofline_inputs.py)", file=sys.stderr)
     return ent, stale
 
 

@@ -1,5 +1,5 @@
 """Extracts the roofline inputs of one kernel from an .ncu-rep (ncu --set full) into profiles/roofline_inputs.json:
-    python tools/roofline_inputs.py <x.ncu-rep> <key> <units_per_launch> [summary.txt]
+    python tools/roofline_inputs.py <x.ncu-rep> <key> <units_per_launch> [summary.txt] [src,files]
 key = "<kernel>/<config>", e.g. "sample_seatfirst_kernel<true>/c2"; units = raw deals (or records) the captured launch
 processed.  Records W_int = sass__thread_inst_executed_true / units, DRAM bytes, issue utilisation and the hash of the
 library sources the capture belongs to (bench.py flags a mismatch as stale)."""
@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import source_hash  # noqa: E402
+from bench import SAMPLER_SOURCES, source_hash  # noqa: E402
 
 rep, key, units = sys.argv[1], sys.argv[2], float(sys.argv[3])
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -45,8 +45,15 @@ ent = {
     "issue_active_pct": num("sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
     "registers": num("launch__registers_per_thread"),
     "source": sys.argv[4] if len(sys.argv) > 4 else os.path.basename(rep),
-    "src_hash": source_hash(),
 }
+files = tuple(sys.argv[5].split(",")) if len(sys.argv) > 5 else SAMPLER_SOURCES
+ent["src_files"] = list(files)
+ent["src_hash"] = source_hash(files)
+for extra in ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+              "sm__warps_active.avg.pct_of_peak_sustained_active"):
+    if extra in d:
+        ent[extra.split(".")[0]] = num(extra)
 path = os.path.join(ROOT, "profiles", "roofline_inputs.json")
 table = json.load(open(path)) if os.path.exists(path) else {}
 table[key] = ent
