@@ -64,6 +64,9 @@ class Contract(C.Structure):
 FEATURE_DTYPE = np.dtype([("len", np.uint8, (4,)), ("suit_hcp", np.uint8, (4,)), ("hcp", np.uint8),
                           ("losers", np.uint8), ("balanced", np.uint8), ("bid", np.int8)])
 assert FEATURE_DTYPE.itemsize == 12
+PLAY_DTYPE = np.dtype([("status", np.uint8), ("n_tricks", np.uint8), ("score", np.uint8, (2,)), ("cards", np.uint8, (13, 4)),
+                       ("winner", np.uint8, (13,)), ("reserved", np.uint8, (3,))])
+assert PLAY_DTYPE.itemsize == 72
 AUCTION_DTYPE = np.dtype([("opener", np.int8), ("opening", np.int8), ("response", np.int8), ("status", np.int8)])
 
 EXPORTS = [
@@ -73,6 +76,7 @@ EXPORTS = [
     "bmc_constraints_set_scoring", "bmc_constraints_primary_acceptance", "bmc_distgen", "bmc_sample_indices", "bmc_sample_indices_dev", "bmc_expand", "bmc_expand_dev", "bmc_sample_multi",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
     "bmc_match_points", "bmc_score_tally", "bmc_hist_base", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
+    "bmc_play_deal", "bmc_play_deal_dev", "bmc_play_hands", "bmc_best_tricks",
 ]
 
 _lib = None
@@ -140,6 +144,10 @@ def load():
     L.bmc_launch_count.argtypes = [vp]
     L.bmc_launch_count.restype = u64
     L.bmc_set_stream.argtypes = [vp, vp]
+    L.bmc_play_deal.argtypes = [vp, vp, u64, vp, vp, C.c_int, u32, vp]
+    L.bmc_play_deal_dev.argtypes = [vp, vp, u64, vp, vp, C.c_int, u32, vp]
+    L.bmc_best_tricks.argtypes = [vp, vp, u64, vp, vp, C.c_int, u32, vp]
+    L.bmc_play_hands.argtypes = [vp, vp, u64, vp, C.c_int, u32, vp]
     _lib = L
     return L
 

@@ -31,6 +31,7 @@
 #include "reforder.cuh"
 #include "hist.cuh"
 #include "distgen.cuh"
+#include "playdeal.cuh"
 #include "rules.hpp"
 #include "jit.hpp"
 #include "embedded_src.inc"
@@ -525,6 +526,8 @@ struct bmc_ctx {
     uint64_t rec_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long *d_tallies = nullptr;     // scratch tallies for the host-buffer API
+    uint8_t *d_arena = nullptr;                  // grow-only per-deal arenas of the trick estimator (bmc_play_deal)
+    uint64_t arena_bytes = 0;
     uint64_t launches = 0;
     std::mutex mu;
 };
@@ -660,6 +663,7 @@ void bmc_shutdown(bmc_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->d_tallies) cudaFree(c->d_tallies);
+    if (c->d_arena) cudaFree(c->d_arena);
     if (c->d_snap) cudaFree(c->d_snap);
     if (c->h_head) cudaFreeHost(c->h_head);
     if (c->d_rec) cudaFree(c->d_rec);
@@ -2460,6 +2464,150 @@ int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc
 }
 
 // ---- measurement ------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// play-deal (bridge.cl:2961): one thread per deal (playdeal.cuh)
+// ---------------------------------------------------------------------------
+constexpr int PD_THREADS = 64;
+__global__ void __launch_bounds__(PD_THREADS) play_deal_kernel(const uint4 *records, const unsigned long long *hands4, unsigned long long n,
+                                                                 const int8_t *trump, const uint8_t *declarer, int per_deal, uint8_t *arenas,
+                                                                 uint32_t arena_bytes, bmc_play_result *out)
+{
+    pd::Scratch S;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * PD_THREADS + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * PD_THREADS;
+    uint8_t *arena = arenas + tid * (unsigned long long)arena_bytes;
+    for (unsigned long long i = tid; i < n; i += stride) {
+        const int tr = trump[per_deal ? i : 0];
+        pd::Hand h[4];
+        if (records) {
+            const uint4 r = records[i];                              // lo plane (x, y), hi plane (z, w)
+            const int dec = declarer[per_deal ? i : 0] & 3;
+            for (int k = 0; k < 4; ++k) {
+                const int seat = (dec + k) & 3;
+                const uint32_t xl = (seat & 1) ? 0u : 0xFFFFFFFFu, xh = (seat & 2) ? 0u : 0xFFFFFFFFu;
+                const uint32_t m0 = (r.x ^ xl) & (r.z ^ xh) & 0x1FFF1FFFu, m1 = (r.y ^ xl) & (r.w ^ xh) & 0x1FFF1FFFu;
+                h[k].s[0] = (uint16_t)(m0 & 0xFFFFu); h[k].s[1] = (uint16_t)(m0 >> 16);
+                h[k].s[2] = (uint16_t)(m1 & 0xFFFFu); h[k].s[3] = (uint16_t)(m1 >> 16);
+                h[k].id = (uint8_t)k;
+            }
+        } else {
+            for (int k = 0; k < 4; ++k) {                            // four lane masks: declarer, left, dummy, right
+                const unsigned long long m = hands4[4 * i + k];
+                for (int s = 0; s < 4; ++s) h[k].s[s] = (uint16_t)((m >> (16 * s)) & 0x1FFFu);
+                h[k].id = (uint8_t)k;
+            }
+        }
+        pd::Result res;
+        pd::play_deal(arena, arena_bytes, tr < 0 || tr > 3 ? -1 : tr, h, S, res);
+        bmc_play_result o;
+        o.status = (uint8_t)res.status; o.n_tricks = res.n; o.score[0] = res.score[0]; o.score[1] = res.score[1];
+        for (int t = 0; t < 13; ++t) {
+            for (int c = 0; c < 4; ++c) o.cards[t][c] = t < res.n ? res.tricks[t][c] : 0xFF;
+            o.winner[t] = t < res.n ? res.wno[t] : 0xFF;
+        }
+        o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
+        out[i] = o;
+    }
+}
+
+static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_hands4, uint64_t n, const int8_t *d_trump,
+                            const uint8_t *d_declarer, int per_deal, uint32_t arena_kb, void *d_out)
+{
+    const uint64_t arena = (uint64_t)(arena_kb ? arena_kb : 1024u) * 1024u;
+    if (arena > (1ull << 31)) return fail(BMC_E_INVALID, "bmc_play_deal: arena_kb too large");
+    uint64_t threads = (n + PD_THREADS - 1) / PD_THREADS * PD_THREADS;
+    const uint64_t max_threads = (uint64_t)ctx->sms * PD_THREADS * 2;
+    if (threads > max_threads) threads = max_threads;
+    const uint64_t need = threads * arena;
+    if (need > ctx->arena_bytes) {
+        if (ctx->d_arena) cudaFree(ctx->d_arena);
+        ctx->d_arena = nullptr; ctx->arena_bytes = 0;
+        if (cudaMalloc(&ctx->d_arena, need) != cudaSuccess) { cudaGetLastError(); return fail(BMC_E_NOMEM, "bmc_play_deal: cannot allocate the per-deal arenas"); }
+        ctx->arena_bytes = need;
+    }
+    play_deal_kernel<<<(unsigned)(threads / PD_THREADS), PD_THREADS, 0, ctx->stream>>>(
+        reinterpret_cast<const uint4 *>(d_records), reinterpret_cast<const unsigned long long *>(d_hands4), n, d_trump, d_declarer,
+        per_deal, ctx->d_arena, (uint32_t)arena,
+        reinterpret_cast<bmc_play_result *>(d_out));
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("bmc_play_deal: ") + cudaGetErrorString(e));
+    return BMC_OK;
+}
+
+int bmc_play_deal_dev(bmc_ctx *ctx, const void *d_records, uint64_t n, const int8_t *d_trump, const uint8_t *d_declarer,
+                      int per_deal, uint32_t arena_kb, void *d_out)
+{
+    if (!ctx || !d_records || !d_trump || !d_declarer || !d_out) return fail(BMC_E_INVALID, "bmc_play_deal_dev: NULL argument");
+    if (n == 0) return BMC_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return play_deal_launch(ctx, d_records, nullptr, n, d_trump, d_declarer, per_deal, arena_kb, d_out);
+}
+
+static int play_deal_host(bmc_ctx *ctx, const void *records, const void *hands4, uint64_t n, const int8_t *trump,
+                          const uint8_t *declarer, int per_deal, uint32_t arena_kb, bmc_play_result *out)
+{
+    const uint64_t np = per_deal ? n : 1;
+    for (uint64_t i = 0; i < np; ++i)
+        if (trump[i] < -1 || trump[i] > 3 || (declarer && declarer[i] > 3)) return fail(BMC_E_INVALID, "play-deal: trump in -1..3, declarer in 0..3");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t in_bytes = records ? n * sizeof(bmc_record) : n * 4 * sizeof(uint64_t);
+    void *d_in = nullptr, *d_o = nullptr; int8_t *d_t = nullptr; uint8_t *d_d = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, in_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, n * sizeof(bmc_play_result));
+    if (e == cudaSuccess) e = cudaMalloc(&d_t, np);
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, np);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, records ? records : hands4, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_t, trump, np, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && declarer) e = cudaMemcpyAsync(d_d, declarer, np, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = BMC_OK;
+    if (e == cudaSuccess) rc = play_deal_launch(ctx, records ? d_in : nullptr, records ? nullptr : d_in, n, d_t, d_d, per_deal, arena_kb, d_o);
+    if (e == cudaSuccess && rc == BMC_OK) e = cudaMemcpyAsync(out, d_o, n * sizeof(bmc_play_result), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rc == BMC_OK) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_o); cudaFree(d_t); cudaFree(d_d);
+    if (rc != BMC_OK) return rc;
+    if (e != cudaSuccess) return fail(BMC_E_CUDA, std::string("play-deal: ") + cudaGetErrorString(e));
+    return BMC_OK;
+}
+
+int bmc_play_deal(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const int8_t *trump, const uint8_t *declarer,
+                  int per_deal, uint32_t arena_kb, bmc_play_result *out)
+{
+    if (!ctx || !records || !trump || !declarer || !out) return fail(BMC_E_INVALID, "bmc_play_deal: NULL argument");
+    if (n == 0) return BMC_OK;
+    return play_deal_host(ctx, records, nullptr, n, trump, declarer, per_deal, arena_kb, out);
+}
+
+int bmc_play_hands(bmc_ctx *ctx, const uint64_t *hands, uint64_t n, const int8_t *trump, int per_deal, uint32_t arena_kb,
+                   bmc_play_result *out)
+{
+    if (!ctx || !hands || !trump || !out) return fail(BMC_E_INVALID, "bmc_play_hands: NULL argument");
+    if (n == 0) return BMC_OK;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t seen = 0;
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t m = hands[4 * i + k];
+            if ((m & ~BMC_LANE_MASK) || (m & seen)) return fail(BMC_E_INVALID, "bmc_play_hands: hands overlap or use bits outside the lane mask");
+            seen |= m;
+        }
+    }
+    return play_deal_host(ctx, nullptr, hands, n, trump, nullptr, per_deal, arena_kb, out);
+}
+
+int bmc_best_tricks(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const int8_t *trump, const uint8_t *declarer,
+                    int per_deal, uint32_t arena_kb, uint8_t *tricks)
+{
+    if (!tricks) return fail(BMC_E_INVALID, "bmc_best_tricks: NULL argument");
+    std::vector<bmc_play_result> res(n);
+    const int rc = bmc_play_deal(ctx, records, n, trump, declarer, per_deal, arena_kb, res.data());
+    if (rc != BMC_OK) return rc;
+    for (uint64_t i = 0; i < n; ++i) tricks[i] = res[i].status == 0 ? res[i].score[1] : 255;
+    return BMC_OK;
+}
+
 int bmc_int_peak(bmc_ctx *ctx, double *ops_per_s, float *ms_out)
 {
     if (!ctx || !ops_per_s) return fail(BMC_E_INVALID, "bmc_int_peak: NULL argument");

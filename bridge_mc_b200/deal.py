@@ -316,16 +316,18 @@ def hand_or_def_parser(defs):
 
 def measure_parser(names, best_tricks=None, engine: Engine | None = None):
     """rest.cl:287-303 measure-parser: contract names ("3NTS", "4HSx") -> measures `msr-<name>` returning
-    [tricks, base-score of the contract with that many tricks].  The reference takes the tricks from
-    `best-tricks`, i.e. its `play-deal` estimator, which is outside this library: the caller
-    supplies it as `best_tricks(suit_sym, declarer_hand, left, dummy, right) -> int`.  [""] selects the
-    reference's default measure `best-outcomes`, which needs the same estimator."""
-    from . import compscore
+    [tricks, base-score of the contract with that many tricks].  The tricks come from `best-tricks`, i.e. the
+    `play-deal` estimator (bridge.cl:2961), which runs on the GPU (bridge_mc_b200/playdeal.py, bmc_play_hands);
+    `best_tricks(suit_sym, declarer_hand, left, dummy, right) -> int` replaces it if given.  [""] selects the
+    reference's default measure `best-outcomes` (bridge.cl:3071)."""
+    from . import compscore, playdeal
     if best_tricks is None:
-        raise NotImplementedError("msr-<contract> / best-outcomes need the reference's play-deal trick estimator, "
-                                  "which this library does not contain; pass best_tricks=")
+        def best_tricks(suit, *hands):
+            return playdeal.best_tricks(suit, *hands, engine=engine)
     if list(names) == [""]:
-        raise NotImplementedError("best-outcomes is defined by play-deal alone; name the contracts to score")
+        def best_outcomes(_trump, *hands):
+            return playdeal.best_outcomes(None, *hands, engine=engine)
+        return [best_outcomes]
     measures = []
     for name in names:
         contract = compscore.Contract(name)

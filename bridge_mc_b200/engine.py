@@ -353,6 +353,48 @@ class Engine:
         self.last_imp_dropped = dropped[:npairs]
         return th, ih[:npairs], tab
 
+    # ---- play-deal: the trick estimator -------------------------------------------------
+    def play_deal(self, records: np.ndarray, trump, declarer, arena_kb: int = 0) -> np.ndarray:
+        """bmc_play_deal: the reference's `play-deal` (bridge.cl:2961) on every record, one GPU thread per deal.
+        `trump` (-1 = no trump, 0..3 = c d h s) and `declarer` (seat 0..3) are scalars or per-deal arrays.
+        Returns a structured array (_lib.PLAY_DTYPE): status, n_tricks, score (defence, declarer), cards, winner."""
+        rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
+        n = rec.shape[0]
+        per = int(np.ndim(trump) > 0 or np.ndim(declarer) > 0)
+        tr = np.ascontiguousarray(np.broadcast_to(np.asarray(trump, dtype=np.int8), (n,) if per else (1,)))
+        de = np.ascontiguousarray(np.broadcast_to(np.asarray(declarer, dtype=np.uint8), (n,) if per else (1,)))
+        out = np.empty(n, dtype=_lib.PLAY_DTYPE)
+        if n:
+            check(self._L.bmc_play_deal(self._h, rec.ctypes.data, n, tr.ctypes.data, de.ctypes.data, per, arena_kb, out.ctypes.data))
+        return out
+
+    def play_hands(self, hands: np.ndarray, trump, arena_kb: int = 0) -> np.ndarray:
+        """bmc_play_hands: `hands` uint64[n, 4] lane masks (declarer, left, dummy, right), possibly partial deals."""
+        hm = np.ascontiguousarray(hands, dtype=np.uint64).reshape(-1, 4)
+        n = hm.shape[0]
+        per = int(np.ndim(trump) > 0)
+        tr = np.ascontiguousarray(np.broadcast_to(np.asarray(trump, dtype=np.int8), (n,) if per else (1,)))
+        out = np.empty(n, dtype=_lib.PLAY_DTYPE)
+        if n:
+            check(self._L.bmc_play_hands(self._h, hm.ctypes.data, n, tr.ctypes.data, per, arena_kb, out.ctypes.data))
+        return out
+
+    def play_deal_dev(self, records_ptr: int, n: int, trump_ptr: int, declarer_ptr: int, per_deal: bool, out_ptr: int, arena_kb: int = 0):
+        """bmc_play_deal_dev: device pointers in, device pointer out (72-byte results)."""
+        check(self._L.bmc_play_deal_dev(self._h, records_ptr, n, trump_ptr, declarer_ptr, int(per_deal), arena_kb, out_ptr))
+
+    def best_tricks(self, records: np.ndarray, trump, declarer, arena_kb: int = 0) -> np.ndarray:
+        """bmc_best_tricks: `best-tricks` (bridge.cl:3027-3028) per record; 255 where play-deal gave no outcome."""
+        rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 2)
+        n = rec.shape[0]
+        per = int(np.ndim(trump) > 0 or np.ndim(declarer) > 0)
+        tr = np.ascontiguousarray(np.broadcast_to(np.asarray(trump, dtype=np.int8), (n,) if per else (1,)))
+        de = np.ascontiguousarray(np.broadcast_to(np.asarray(declarer, dtype=np.uint8), (n,) if per else (1,)))
+        out = np.empty(n, dtype=np.uint8)
+        if n:
+            check(self._L.bmc_best_tricks(self._h, rec.ctypes.data, n, tr.ctypes.data, de.ctypes.data, per, arena_kb, out.ctypes.data))
+        return out
+
     # ---- hist-base on the device -----------------------------------------------------
     def hist_base(self, records: np.ndarray, measures, cap: int = 1 << 20):
         """bmc_hist_base: `measures` = [(kind, seat, suit), ...] (kinds: _lib.M_*).  Returns hist-base rows

@@ -337,6 +337,37 @@ typedef struct { uint8_t kind, seat, suit, reserved; } bmc_measure;
 int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc_measure *measures, uint32_t k,
                   uint8_t *tuples, uint64_t *counts, uint64_t cap, uint64_t *n_unique);
 
+/* ---- play-deal: the trick estimator (bridge.cl:2961-2963; best-tricks 3027-3028) ------------------ */
+/* Result of `play-deal trump declarer left dummy right` for one deal.  `score` is the reference outcome's
+ * (score ...) pair: score[0] = tricks of the side that leads first (the defence), score[1] = tricks of the
+ * declaring side, i.e. what `best-tricks` returns (bridge.cl:3028).  cards[t][i] = i-th card played to trick t,
+ * suit << 4 | rank (0xFF = nothing played), winner[t] = position in the trick of the winning card
+ * (`winner-nos`).  status: 0 ok; 1 the deal's route lists outgrew the per-deal arena (re-run with a larger
+ * arena_kb); 2 the reference would signal a Lisp error on this deal; 3 an internal table overflowed;
+ * 4 the reference returns nil. */
+typedef struct {
+    uint8_t status, n_tricks;
+    uint8_t score[2];
+    uint8_t cards[13][4];
+    uint8_t winner[13];
+    uint8_t reserved[3];
+} bmc_play_result;   /* 72 bytes */
+/* One GPU thread plays one deal.  trump[i] in {-1 (no trump), 0..3 = c d h s}; declarer[i] = seat 0..3 (N E S W);
+ * the left-hand opponent (seat + 1) leads.  per_deal = 0: trump[0] / declarer[0] apply to every deal.
+ * arena_kb: per-deal scratch for the route lists (0 = default 1024).  `bmc_play_deal` takes host buffers,
+ * `bmc_play_deal_dev` device pointers (no copies; runs on the context's stream and synchronises it). */
+int bmc_play_deal(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const int8_t *trump, const uint8_t *declarer,
+                  int per_deal, uint32_t arena_kb, bmc_play_result *out);
+int bmc_play_deal_dev(bmc_ctx *ctx, const void *d_records, uint64_t n, const int8_t *d_trump, const uint8_t *d_declarer,
+                      int per_deal, uint32_t arena_kb, void *d_out);
+/* The same for four explicit hands per deal -- hands[4*i + k] = lane mask of declarer, left, dummy, right -- which
+ * need not cover the deck: the reference's own tests call play-deal's parts on endings of a few cards. */
+int bmc_play_hands(bmc_ctx *ctx, const uint64_t *hands, uint64_t n, const int8_t *trump, int per_deal, uint32_t arena_kb,
+                   bmc_play_result *out);
+/* best-tricks (bridge.cl:3027-3028) for every deal: tricks[i] = score[1] of play-deal, 255 where status != 0 */
+int bmc_best_tricks(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const int8_t *trump, const uint8_t *declarer,
+                    int per_deal, uint32_t arena_kb, uint8_t *tricks);
+
 /* ---- measurement helpers -------------------------------------------------- */
 /* INT32 issue-rate microbenchmark (IMAD + LOP3/IADD3 chains on every SM):
  * returns thread-level integer ops per second in *ops_per_s. */

@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE -- run the reference's own Lisp sources (read in place from /root/reference, build container
+only) under oracle/minilisp.py and write what they compute into committed fixtures:
+
+    python oracle/run_reference.py tests            # tests/golden/reference_inline_tests.json
+    python oracle/run_reference.py playdeal [N]     # tests/golden/playdeal_ref.json
+
+`tests` evaluates every inline `(test FORM EXPECTED PRED)` form of bridge.cl (lines 23-3086) with the reference's own
+definitions and records pass / fail and, for failures, the value the reference code really produces.  At this
+snapshot eight tests of the trick estimator fail IN THE REFERENCE ITSELF (their expected values are stale: e.g.
+bridge.cl:2694 expects a trick led with a card that was played two tricks earlier, and the TODO above it shows the
+value was pasted from another deal); the oracle's restatement (oracle/playdeal.py) is held to the value the code
+computes, not to the stale literal.
+
+`playdeal` draws seeded random deals (full 13-card deals and k-card endings), calls the reference's `play-deal`
+(bridge.cl:2961) on each with no trump and with a trump suit, and stores deal, trump, tricks, winners and score.
+These are outputs of the reference itself: tests/test_playdeal_oracle.py holds the restatement to them, and
+tests/test_gpu_playdeal.py the CUDA path.
+"""
+import json
+import multiprocessing as mp
+import os
+import random
+import sys
+import threading
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != HERE]   # `oracle` must be the package, not oracle/oracle.py
+sys.path.insert(0, os.path.join(HERE, ".."))
+from oracle import minilisp as M  # noqa: E402
+
+REF = "/root/reference/backend/bridge.cl"
+GOLDEN = os.path.join(HERE, "..", "tests", "golden")
+
+
+def big_stack(fn, *args):
+    out = {}
+
+    def run():
+        out["v"] = fn(*args)
+    threading.stack_size(2040 * 1024 * 1024)
+    th = threading.Thread(target=run)
+    th.start()
+    th.join()
+    return out.get("v")
+
+
+def load(on_test=None, last_line=3086):
+    it = M.Interp(seed=1)
+    M.load_file(it, REF, first_line=23, last_line=last_line, on_test=on_test)
+    return it
+
+
+def to_py(x):
+    if isinstance(x, list):
+        return [to_py(e) for e in x]
+    if x is None or isinstance(x, (int, bool)):
+        return x
+    return str(x)
+
+
+def run_inline_tests():
+    res = []
+    it = None
+
+    def on_test(line, form):
+        t0 = time.time()
+        try:
+            got = it.eval(form[1], None, None)
+            want = it.eval(form[2], None, None)
+            ok = M.truthy(it.fn(form[3])(got, want))
+            rec = {"line": line, "ok": bool(ok)}
+            if not ok:
+                rec["reference_computes"] = M.lisp_repr(got)
+                rec["literal_expected"] = M.lisp_repr(want)
+        except Exception as e:  # noqa: BLE001
+            rec = {"line": line, "ok": False, "error": repr(e)[:200]}
+        rec["seconds"] = round(time.time() - t0, 2)
+        res.append(rec)
+
+    # definitions first (some tests use functions defined further down the file), then the tests in file order
+    it = load(on_test=None)
+    M.load_file(it, REF, first_line=23, last_line=3086, on_test=on_test)
+    return res
+
+
+def rand_deal(rng, k):
+    cards = rng.sample(range(52), 4 * k)
+    hands = []
+    for h in range(4):
+        mine = sorted(cards[h * k:(h + 1) * k])
+        hands.append([[c % 13 for c in mine if c // 13 == s] for s in range(4)])
+    return hands
+
+
+def play_one(job):
+    hands, trump = job
+
+    def run():
+        it = load()
+        hs = [it.make_instance(M.S("HAND"), M.S(":="), [list(s) if s else None for s in h], M.S(":ID"), M.LStr("NESW"[i]))
+              for i, h in enumerate(hands)]
+        t0 = time.time()
+        try:
+            out = it.fn(M.S("PLAY-DEAL"))(M.S("CDHS"[trump]) if trump is not None else None, *hs)
+        except M.LispError as e:
+            return {"hands": hands, "trump": trump, "error": str(e)[:120], "seconds": round(time.time() - t0, 1)}
+        except RecursionError:
+            # `reproduce` (bridge.cl:2395) recurses once per dropped trick of a route; on some deals deeper than this
+            # evaluator's stack (SBCL's control stack would be exhausted much earlier)
+            return {"hands": hands, "trump": trump, "error": "recursion depth", "seconds": round(time.time() - t0, 1)}
+        if out is None:
+            return {"hands": hands, "trump": trump, "nil": True, "seconds": round(time.time() - t0, 1)}
+        return {"hands": hands, "trump": trump, "tricks": to_py(out.slots[M.S("TRICKS")]),
+                "winner_nos": to_py(out.slots[M.S("WINNER-NOS")]), "score": to_py(out.slots[M.S("SCORE")]),
+                "seconds": round(time.time() - t0, 1)}
+    return big_stack(run)
+
+
+def gen_playdeal(n_full):
+    rng = random.Random(20261020)
+    jobs = []
+    for _ in range(n_full):
+        h = rand_deal(rng, 13)
+        lens = [len(h[0][s]) + len(h[2][s]) for s in range(4)]
+        jobs.append((h, None))
+        jobs.append((h, max(range(4), key=lambda s: (lens[s], s))))
+    for k in (2, 3, 4, 5, 6, 8):
+        for _ in range(16):
+            h = rand_deal(rng, k)
+            jobs.append((h, None))
+            jobs.append((h, rng.randrange(4)))
+    with mp.Pool(min(8, os.cpu_count() or 1)) as pool:
+        rows = pool.map(play_one, jobs, chunksize=1)
+    return [r if r is not None else {"hands": j[0], "trump": j[1], "error": "recursion depth"} for r, j in zip(rows, jobs)]
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "tests"
+    if what == "tests":
+        res = big_stack(run_inline_tests)
+        bad = [r for r in res if not r["ok"]]
+        print(f"{len(res)} inline tests of bridge.cl evaluated by the reference's own code: {len(res) - len(bad)} pass, {len(bad)} fail")
+        for r in bad:
+            print("  bridge.cl:%d" % r["line"], r.get("error", ""))
+        json.dump({"source": "bridge.cl:23-3086, evaluated by oracle/minilisp.py", "results": res},
+                  open(os.path.join(GOLDEN, "reference_inline_tests.json"), "w"), indent=0)
+    elif what == "playdeal":
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+        t0 = time.time()
+        rows = gen_playdeal(n)
+        json.dump({"source": "play-deal (bridge.cl:2961) run by oracle/minilisp.py on seeded random deals; "
+                             "hands = declarer, left, dummy, right as 4 ascending rank lists (c d h s); trump 0..3 or null",
+                   "rows": rows}, open(os.path.join(GOLDEN, "playdeal_ref.json"), "w"), separators=(",", ":"))
+        print(f"{len(rows)} play-deal results in {time.time() - t0:.0f} s; errors: {sum(1 for r in rows if 'error' in r)}")
+
+
+if __name__ == "__main__":
+    main()

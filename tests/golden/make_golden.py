@@ -14,6 +14,9 @@ Outputs (all under tests/golden/):
                      [weight, pattern16] pairs; pattern16 bit 15 = club J ...
                      bit 0 = spade A (the order of the 16 0/1 flags in each row)
 
+  playdeal_kats.json  every `(test ...)` form inside the trick estimator
+                     (bridge.cl:1497-2984): play-low ... play-deal
+
 No reference *source* is copied: only the known-answer data of its test forms.
 """
 import json
@@ -65,6 +68,17 @@ def main():
     with open(os.path.join(HERE, "kats.json"), "w", encoding="utf-8") as f:
         json.dump(kats, f, ensure_ascii=False, indent=0)
     print(f"kats.json: {len(kats)} known-answer tests")
+
+    # the trick estimator's inline tests (replayed by tests/test_playdeal_oracle.py through a small form evaluator)
+    pk = []
+    text = open(os.path.join(REF, "bridge.cl"), encoding="utf-8").read()
+    for line, form in sexp.read_all_with_lines(text):
+        if 1497 <= line <= 2984 and head_of(form) == "TEST" and len(form) == 4:
+            pk.append({"file": "bridge.cl", "line": line, "form": sexp.dumps(form[1]),
+                       "expected": sexp.dumps(form[2]), "pred": sexp.dumps(form[3])})
+    with open(os.path.join(HERE, "playdeal_kats.json"), "w", encoding="utf-8") as f:
+        json.dump(pk, f, ensure_ascii=False, indent=0)
+    print(f"playdeal_kats.json: {len(pk)} known-answer tests")
 
     rows = sexp.read_all(open(os.path.join(REF, "test", "distgen-test.dat"), encoding="utf-8").read())
     out = []

@@ -336,14 +336,13 @@ def test_c_abi_from_plain_c(tmp_path):
 
 def test_rest_parsers():
     """rest.cl:279-303: hand-or-def-parser and the shape of measure-parser's result (the trick estimator behind
-    msr-<contract> is an explicit input: play-deal is outside the library)"""
+    msr-<contract> runs on the GPU, tests/test_gpu_playdeal.py; here a stand-in is passed)"""
     from bridge_mc_b200.deal import hand_or_def_parser, measure_parser
     south = "S: ♠ AKJ5 ♥ K1064 ♦ Q87 ♣ A6"
     defs = hand_or_def_parser([(":|hand|", south), ("def", "(:hcp (10 12) :s (4 nil))"), ("def", "NIL"), ("def", "(:hcp 12)")])
     assert defs[0] == cards.str2hand(south)
     assert defs[1:] == [{"hcp": [10, 12], "s": [4, None]}, {}, {"hcp": 12}]
-    with pytest.raises(NotImplementedError):
-        measure_parser(["3NTS"])
+    assert [m.__name__ for m in measure_parser([""])] == ["best_outcomes"]       # the default measure (rest.cl:288)
     ms = measure_parser(["3NTS", "4HNx"], best_tricks=lambda suit, a, b, c, d: 9)
     assert [m.__name__ for m in ms] == ["msr-3NTS", "msr-4HNx"]
 
