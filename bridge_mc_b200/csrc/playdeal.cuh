@@ -18,7 +18,7 @@
 // ffs(mask >> (r + 1))).  No recursion: the four recursive searches of the reference run on explicit stacks.
 //
 // Compiled by nvcc into libbridgemc.so (kernel `play_deal_kernel`, bridgemc.cu) and -- the same text -- by g++ into
-// tests/playdeal_host_selftest, a test-only binary that lets the CPU suite check this file against the oracle.
+// tests/playdeal_host_selftest, a test-only binary with which the CPU suite checks this file without a GPU.
 #pragma once
 #include <stdint.h>
 
@@ -28,6 +28,19 @@
 #else
 #define PD_HD inline
 #define PD_HDN
+#endif
+
+// On the device the 32 lanes of a warp run one deal in lock step (play_deal_kernel, bridgemc.cu): the scalar logic is
+// executed redundantly by every lane on identical data, and the bulk list operations below (copy, scan, compaction of
+// trick lists) are split across the lanes.  On the host there is one lane.
+#if defined(__CUDA_ARCH__)
+#define PD_LANE ((int)(threadIdx.x & 31u))
+#define PD_LANES 32
+#define PD_SYNC() __syncwarp()
+#else
+#define PD_LANE 0
+#define PD_LANES 1
+#define PD_SYNC() ((void)0)
 #endif
 
 namespace pd {
@@ -88,11 +101,13 @@ struct Outcome {                 // bridge.cl:2190-2196; winners = tricks[i][wno
     Hand rem[4];
 };
 
-struct Ctx {                     // per-thread state
+struct Ctx {                     // per-deal state
     uint8_t *arena;
     uint32_t cap, top;
     int status;
     int trump;                   // -1 = no trump
+    uint8_t *sstk;               // stack of the functions' temporaries: shared memory on the device (one per warp), so
+    uint32_t scap, stop, speak;  // that nothing indexed dynamically lives in (lane-interleaved) local memory
 };
 
 PD_HD uint32_t arena_alloc(Ctx &cx, uint32_t bytes)
@@ -109,6 +124,23 @@ PD_HD uint32_t arena_alloc(Ctx &cx, uint32_t bytes)
 template <class T> PD_HD T *at(Ctx &cx, uint32_t off) { return reinterpret_cast<T *>(cx.arena + off); }
 
 PD_HD void fail(Ctx &cx, int code) { if (!cx.status) cx.status = code; }
+
+// temporaries: `T &x = *tmp<T>(cx)` inside a function that opens with `TmpFrame tf(cx);`
+template <class T> PD_HD T *tmp(Ctx &cx, uint32_t count = 1)
+{
+    const uint32_t bytes = ((uint32_t)sizeof(T) * count + 7u) & ~7u;
+    if (cx.stop + bytes > cx.scap) { fail(cx, PD_E_CAP); return reinterpret_cast<T *>(cx.sstk); }   // scap >= any single request
+    T *p = reinterpret_cast<T *>(cx.sstk + cx.stop);
+    cx.stop += bytes;
+    if (cx.stop > cx.speak) cx.speak = cx.stop;
+    return p;
+}
+struct TmpFrame {
+    Ctx &cx;
+    uint32_t mark;
+    PD_HD explicit TmpFrame(Ctx &c) : cx(c), mark(c.stop) {}
+    PD_HD ~TmpFrame() { cx.stop = mark; }
+};
 
 // ---------------------------------------------------------------------------
 // a trick in progress (bridge.cl:1535-1620)
@@ -348,7 +380,8 @@ PD_HD bool outcome_won(const Outcome &o) { return o.n > 0 && (o.wno[0] & 1) == 0
 PD_HDN void simple_trick(Ctx &cx, Outcome &o, int suit, const Hand *h, bool use_highest)
 {
     if (h[0].s[suit] == 0) { outcome_empty(o, h); return; }
-    Trick t;
+    TmpFrame tf(cx);
+    Trick &t = *tmp<Trick>(cx);
     trick_init(t, suit, cx.trump);
     beat_or_low(cx, t, h[0], use_highest);
     if (beats(h[3], h[2], suit, cx.trump)) beat_or_low(cx, t, h[1], false);
@@ -408,6 +441,9 @@ PD_HD void best_update(SearchFrame &f, const Outcome &val)
 // `stack`: MAXD frames in the caller's local memory
 PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int nsuits, const Hand *hands, SearchFrame *stack, Outcome &result)
 {
+    TmpFrame tf(cx);
+    Hand *hs = tmp<Hand>(cx, 4);
+    Outcome &cand = *tmp<Outcome>(cx);
     int sp = 0;
     auto open = [&](SearchFrame &f, const Hand *h) {
         for (int i = 0; i < 4; ++i) f.hands[i] = h[i];
@@ -432,20 +468,16 @@ PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int 
             continue;
         }
         const SearchOpt o = f.opts[f.i++];
-        Hand hs[4];
         if (o.rolled) roll2(f.hands, hs); else for (int i = 0; i < 4; ++i) hs[i] = f.hands[i];
         simple_trick(cx, f.cur, o.suit, hs, o.top != 0);
         const bool follow = f.cur.n > 0 && (kind == PLAY_THROUGH || outcome_won(f.cur));
         if (follow) {
             if (sp + 1 >= MAXD) { fail(cx, PD_E_CAP); outcome_nil(result); return; }
-            Hand next[4];
-            for (int i = 0; i < 4; ++i) next[i] = f.cur.rem[i];
             ++sp;
-            open(stack[sp], next);
+            open(stack[sp], f.cur.rem);
             continue;
         }
         // do-next gave nil
-        Outcome cand;
         if (kind == PLAY_THROUGH) outcome_empty(cand, hs); else outcome_nil(cand);
         best_update(f, cand);
     }
@@ -464,9 +496,10 @@ struct SuitValue {
 
 PD_HDN void suit_value(Ctx &cx, SuitValue &sv, int suit, int trump, const Hand *deal, SearchFrame *stack)
 {
+    TmpFrame tf(cx);
     const int saved = cx.trump;
     cx.trump = trump;
-    Outcome o;
+    Outcome &o = *tmp<Outcome>(cx);
     search(cx, PLAY_THROUGH, suit, nullptr, 0, deal, stack, o);
     cx.trump = saved;
     sv.suit = (int8_t)suit; sv.trump = (int8_t)trump; sv.ngroups = 0;
@@ -502,13 +535,13 @@ struct RootStrategy {            // soonest / establish of a play-strategy: shar
 PD_HDN void find_opp_weakness(Ctx &cx, RootStrategy &rs, const Hand *deal, SearchFrame *stack)
 {
     const int trump = cx.trump;
-    SuitValue vals[4];
+    TmpFrame tf(cx);
+    SuitValue *vals = tmp<SuitValue>(cx, 4);
+    SuitValue &nt = *tmp<SuitValue>(cx), &tr = *tmp<SuitValue>(cx);
     int nv = 0;
     for (int suit = 0; suit < 4 && !cx.status; ++suit) {
-        SuitValue nt;
         suit_value(cx, nt, suit, -1, deal, stack);
         if (trump >= 0) {
-            SuitValue tr;
             suit_value(cx, tr, suit, trump, deal, stack);
             if (tr.ours > nt.ours) nt = tr;                 // better (2326-2327)
         }
@@ -516,8 +549,8 @@ PD_HDN void find_opp_weakness(Ctx &cx, RootStrategy &rs, const Hand *deal, Searc
     }
     // (sort ... (> (ours a) (ours b))): stable
     for (int i = 1; i < nv; ++i)
-        for (int j = i; j > 0 && vals[j].ours > vals[j - 1].ours; --j) { const SuitValue t = vals[j]; vals[j] = vals[j - 1]; vals[j - 1] = t; }
-    int order[12], no = 0;
+        for (int j = i; j > 0 && vals[j].ours > vals[j - 1].ours; --j) { nt = vals[j]; vals[j] = vals[j - 1]; vals[j - 1] = nt; }
+    int *order = tmp<int>(cx, 12), no = 0;
     if (trump >= 0) {
         for (int i = 0; i < nv; ++i) if (vals[i].trump >= 0) order[no++] = i;
         for (int i = 0; i < nv; ++i) if (vals[i].suit == trump) order[no++] = i;
@@ -526,7 +559,7 @@ PD_HDN void find_opp_weakness(Ctx &cx, RootStrategy &rs, const Hand *deal, Searc
     rs.nsoon = rs.nest = 0;
     for (int k = 0; k < no; ++k) {
         const SuitValue &sv = vals[order[k]];
-        Target t;
+        Target &t = *tmp<Target>(cx);
         t.suit = sv.suit; t.diff = (int8_t)(sv.ours - sv.theirs); t.nours = t.ntheirs = t.head = 0;
         for (int g = 0; g < sv.ngroups; ++g)
             for (int j = 0; j < sv.glen[g]; ++j) {
@@ -584,8 +617,9 @@ PD_HDN uint32_t add_at(Ctx &cx, uint32_t route, uint32_t tricks2, uint32_t len2)
     if (cx.status) return route;
     uint32_t *dst = at<uint32_t>(cx, off);
     const uint32_t *a = at<uint32_t>(cx, r.tricks), *b = at<uint32_t>(cx, tricks2);
-    for (uint32_t i = 0; i < r.len; ++i) dst[i] = a[i];
-    for (uint32_t i = 0; i < len2; ++i) dst[r.len + i] = b[i];
+    for (uint32_t i = PD_LANE; i < r.len; i += PD_LANES) dst[i] = a[i];
+    for (uint32_t i = PD_LANE; i < len2; i += PD_LANES) dst[r.len + i] = b[i];
+    PD_SYNC();
     return new_route(cx, r.frm, r.to, r.tvoid, off, len);
 }
 // insert-route (2553-2561): merge into the first route with the same from / to, else push in front
@@ -619,7 +653,8 @@ PD_HDN void reproduce(Ctx &cx, uint32_t route, const Hand *hands, Outcome &ans)
         const uint32_t m0 = hands[0].s[suit];
         bool have = false;
         if (m0) {
-            Trick t;
+            TmpFrame tf(cx);
+            Trick &t = *tmp<Trick>(cx);
             trick_init(t, suit, cx.trump);
             Play p = play_rank(hands[0], suit, ch_closest(m0, crank(ref[0])));
             trick_play(t, p.card, p.rest);
@@ -644,7 +679,10 @@ PD_HDN void reproduce(Ctx &cx, uint32_t route, const Hand *hands, Outcome &ans)
 PD_HDN void mk_route(Ctx &cx, uint32_t com_off, const Hand *hands, Outcome &acc)
 {
     const Com &com = *at<Com>(cx, com_off);
-    RouteList pr[2];
+    TmpFrame tf(cx);
+    RouteList *pr = tmp<RouteList>(cx, 2);
+    Outcome &ans = *tmp<Outcome>(cx);
+    Hand *hs = tmp<Hand>(cx, 4);
     for (int w = 0; w < 2; ++w) {
         const int player = w * 2;
         pr[w].n = 0;
@@ -657,8 +695,6 @@ PD_HDN void mk_route(Ctx &cx, uint32_t com_off, const Hand *hands, Outcome &acc)
     outcome_empty(acc, hands);
     int cur = 0, head[2] = {0, 0};
     while (head[cur] < pr[cur].n && !cx.status) {
-        Outcome ans;
-        Hand hs[4];
         for (int i = 0; i < 4; ++i) hs[i] = acc.rem[i];
         reproduce(cx, pr[cur].r[head[cur]], hs, ans);
         if (!ans.valid) { ++head[cur]; continue; }
@@ -686,14 +722,18 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
 {
     // sections of the classification (2523-2530); each keeps REVERSE input order (divlist conses in front)
     enum { S_GUARD = 0, S_MY_LEFT, S_PARTNER_LEFT, S_MY_TRUMPED, S_PARTNER_TRUMPED, S_MY_LEAD, S_PARTNER_LEAD, S_MY, S_PARTNER, NSEC };
-    uint32_t sec[NSEC][60];
-    int nsec[NSEC];
-    int8_t gs[8]; uint16_t gr[8];
+    TmpFrame tf(cx);
+    uint32_t (*sec)[60] = reinterpret_cast<uint32_t (*)[60]>(tmp<uint32_t>(cx, NSEC * 60));
+    int *nsec = tmp<int>(cx, NSEC);
+    int8_t *gs = tmp<int8_t>(cx, 8);
+    uint16_t *gr = tmp<uint16_t>(cx, 8);
+    Outcome &tops = *tmp<Outcome>(cx);
+    uint32_t *tmpt = tmp<uint32_t>(cx, 60);
+    RouteList &routes = *tmp<RouteList>(cx);
     int ng = 0;
     for (int i = 0; i < NSEC; ++i) nsec[i] = 0;
     for (int k = 0; k < nsuits && !cx.status; ++k) {
         const int suit = suits[k];
-        Outcome tops;
         search(cx, SUIT_TOPS, suit, nullptr, 0, h, stack, tops);
         if (cx.status) break;
         for (int t = 0; t < tops.n; ++t) {
@@ -729,11 +769,10 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
     }
     if (cx.status) return 0;
     // routes in the order of 2542-2549, each section reversed
-    uint32_t tmp[60];
-    RouteList routes; routes.n = 0;
+    routes.n = 0;
     auto section = [&](int s, int frm, int to) {
-        for (int i = 0; i < nsec[s]; ++i) tmp[i] = sec[s][nsec[s] - 1 - i];
-        const uint32_t off = tricks_from(cx, tmp, nsec[s]);
+        for (int i = 0; i < nsec[s]; ++i) tmpt[i] = sec[s][nsec[s] - 1 - i];
+        const uint32_t off = tricks_from(cx, tmpt, nsec[s]);
         rl_push(cx, routes, new_route(cx, frm, to, -1, off, (uint32_t)nsec[s]));
     };
     section(S_MY, -1, 0);
@@ -750,12 +789,12 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
                 const Card c0 = tcard(t, 0);
                 const int led = c0 == NOCARD ? -1 : csuit(c0);
                 const int split = (led >= 0 && led <= 2) ? led : 3;
-                if (split == k) tmp[n++] = t;
+                if (split == k) tmpt[n++] = t;
             }
             if (n == 0) continue;
             // sec[s] is already in input order here; the section list handed to void-vertices is the reversed one and
             // divlist reverses it again: the route's tricks are in input order
-            const uint32_t off = tricks_from(cx, tmp, n);
+            const uint32_t off = tricks_from(cx, tmpt, n);
             rl_push(cx, routes, new_route(cx, frm, to, suits[k], off, (uint32_t)n));
         }
     };
@@ -783,7 +822,12 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
 // first-pass (2568-2590) over the active routes with the cards just played
 PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards_in, RouteList &routes, Card *skipped, int &nskipped)
 {
-    Card cards[56];
+    TmpFrame tf(cx);
+    Card *cards = tmp<Card>(cx, 56), *rest = tmp<Card>(cx, 56);
+    int16_t *pos_first = tmp<int16_t>(cx, 53), *pos_third = tmp<int16_t>(cx, 53);
+    int *rem_id = tmp<int>(cx, 56), *brk_id = tmp<int>(cx, 56), *ids = tmp<int>(cx, 56);
+    uint8_t *is_rem = tmp<uint8_t>(cx, 56), *is_brk = tmp<uint8_t>(cx, 56);
+    uint32_t *brk_tricks = tmp<uint32_t>(cx, 56);
     int ncards = ncards_in;
     for (int i = 0; i < ncards; ++i) cards[i] = cards_in[i];
     bool remaining_nil = ncards == 0;
@@ -793,23 +837,42 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         if (remaining_nil) { rl_push_front(cx, routes, roff); ncards = 0; continue; }
         const Route r = *at<Route>(cx, roff);
         // rem-break-div (2397-2411): first index of each card as a first card / as a third card of the route's tricks
-        int16_t pos_first[53], pos_third[53];
         for (int i = 0; i < 53; ++i) pos_first[i] = pos_third[i] = -1;
+        if (r.len > 32767) { fail(cx, PD_E_CAP); return; }
         {
+            // only the cards just played matter: a 53-bit request mask over the card indices
+            unsigned long long want = 0;
+            for (int i = 0; i < ncards; ++i) want |= 1ull << cidx(cards[i]);
             const uint32_t *tr = at<uint32_t>(cx, r.tricks);
-            int found = 0;
-            for (uint32_t i = 0; i < r.len && found < 106; ++i) {
-                const int c0 = cidx(tcard(tr[i], 0)), c2 = cidx(tcard(tr[i], 2));
-                if (pos_first[c0] < 0) { pos_first[c0] = (int16_t)(i > 32767 ? 32767 : i); ++found; }
-                if (pos_third[c2] < 0) { pos_third[c2] = (int16_t)(i > 32767 ? 32767 : i); ++found; }
+#if defined(__CUDA_ARCH__)
+            // 32 tricks per step, one per lane; the (rare) tricks that hold a wanted card are then visited in order by
+            // every lane, so all lanes end with the same positions
+            for (uint32_t base = 0; base < r.len; base += 32u) {
+                const uint32_t i = base + (uint32_t)PD_LANE;
+                const uint32_t t = i < r.len ? tr[i] : 0u;
+                const bool hit = i < r.len && (((want >> cidx(tcard(t, 0))) | (want >> cidx(tcard(t, 2)))) & 1ull);
+                unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+                while (bal) {
+                    const int b = __ffs((int)bal) - 1;
+                    bal &= bal - 1u;
+                    const uint32_t tt = __shfl_sync(0xFFFFFFFFu, t, b);
+                    const int c0 = cidx(tcard(tt, 0)), c2 = cidx(tcard(tt, 2));
+                    if (((want >> c0) & 1ull) && pos_first[c0] < 0) pos_first[c0] = (int16_t)(base + b);
+                    if (((want >> c2) & 1ull) && pos_third[c2] < 0) pos_third[c2] = (int16_t)(base + b);
+                }
             }
-            if (r.len > 32767) { fail(cx, PD_E_CAP); return; }
+#else
+            for (uint32_t i = 0; i < r.len; ++i) {
+                const uint32_t t = tr[i];
+                const int c0 = cidx(tcard(t, 0)), c2 = cidx(tcard(t, 2));
+                if (((want >> c0) & 1ull) && pos_first[c0] < 0) pos_first[c0] = (int16_t)i;
+                if (((want >> c2) & 1ull) && pos_third[c2] < 0) pos_third[c2] = (int16_t)i;
+            }
+#endif
         }
         const bool no_from = r.frm < 0;
         const bool first_only = no_from || r.frm == r.to;
         // items (card, id) in the three sections, each in REVERSE card order
-        int rem_id[56], brk_id[56];
-        bool is_rem[56], is_brk[56];
         for (int i = 0; i < ncards; ++i) {
             const int ci = cidx(cards[i]);
             const int bid = no_from ? pos_third[ci] : -1;
@@ -831,7 +894,7 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         uint32_t updated_len = r.len;
         if (any_ids) {
             // del-at (2413-2419): the ids, sorted, then one pass over the tricks
-            int ids[56], nid = 0;
+            int nid = 0;
             for (int i = 0; i < ncards; ++i) {
                 if (!is_rem[i] && !is_brk[i]) continue;
                 const int id = is_rem[i] ? rem_id[i] : brk_id[i];
@@ -844,16 +907,30 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
             uint32_t *dst = at<uint32_t>(cx, off);
             const uint32_t *tr = at<uint32_t>(cx, r.tricks);
             uint32_t n = 0;
+#if defined(__CUDA_ARCH__)
+            // order-preserving compaction, 32 tricks per step: the ids are sorted, `lo` = how many lie below this step
+            int lo = 0;
+            for (uint32_t base = 0; base < r.len; base += 32u) {
+                const uint32_t t = base + (uint32_t)PD_LANE;
+                while (lo < nid && (uint32_t)ids[lo] < base) ++lo;
+                bool keep = t < r.len;
+                for (int k = lo; keep && k < nid && (uint32_t)ids[k] < base + 32u; ++k) if ((uint32_t)ids[k] == t) keep = false;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) dst[n + __popc(bal & ((1u << PD_LANE) - 1u))] = tr[t];
+                n += __popc(bal);
+            }
+            PD_SYNC();
+#else
             int k = 0;
             for (uint32_t t = 0; t < r.len; ++t) {
                 while (k < nid && (uint32_t)ids[k] < t) ++k;
                 if (k < nid && (uint32_t)ids[k] == t) continue;
                 dst[n++] = tr[t];
             }
+#endif
             updated = new_route(cx, r.frm, r.to, r.tvoid, off, n);
             updated_len = n;
         }
-        uint32_t brk_tricks[56];
         int nb = 0;
         for (int i = ncards - 1; i >= 0; --i) {                       // section order = reverse card order
             if (!is_brk[i]) continue;
@@ -867,7 +944,6 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         }
         if (updated_len) rl_push_front(cx, routes, updated);
         // what is left of the cards: the absent section, reversed
-        Card rest[56];
         int nr = 0;
         for (int i = ncards - 1; i >= 0; --i) if (!is_rem[i] && !is_brk[i]) rest[nr++] = cards[i];
         for (int i = 0; i < nr; ++i) cards[i] = rest[i];
@@ -881,6 +957,12 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
 // after-tricks of a play-com (2643-2660); returns the new play-com
 PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, SearchFrame *stack)
 {
+    TmpFrame tf(cx);
+    Card *raw = tmp<Card>(cx, 56), *skipped = tmp<Card>(cx, 56);
+    RouteList &base = *tmp<RouteList>(cx), &new_active = *tmp<RouteList>(cx), &new_pending = *tmp<RouteList>(cx);
+    RouteList &act = *tmp<RouteList>(cx), &pend = *tmp<RouteList>(cx);
+    int8_t *broken = tmp<int8_t>(cx, MAXG), *ks = tmp<int8_t>(cx, MAXG);
+    uint16_t *kr = tmp<uint16_t>(cx, MAXG);
     // normalize-hands (2622-2638)
     uint32_t self_off = com_off;
     {
@@ -899,16 +981,12 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
         }
     }
     if (cx.status) return com_off;
-    Card raw[56];
     int nraw = 0;
     for (int t = 0; t < out.n; ++t) for (int i = 0; i < 4; ++i) raw[nraw++] = out.tricks[t][i];
-    RouteList base;
-    Card skipped[56];
     int nskipped = 0;
     first_pass(cx, *at<Com>(cx, self_off), raw, nraw, base, skipped, nskipped);
     if (cx.status) return com_off;
     // second-pass (2592-2596): pending routes whose target hand is now void in the route's suit; both lists reversed
-    RouteList new_active, new_pending;
     new_active.n = new_pending.n = 0;
     {
         const Com &self = *at<Com>(cx, self_off);
@@ -919,11 +997,9 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
         }
     }
     // broken-guards (2598-2615): overwrites the guards of `self` (which is the caller's play-com when offset = 0)
-    int8_t broken[MAXG];
     int nbroken = 0;
     {
         Com &self = *at<Com>(cx, self_off);
-        int8_t ks[MAXG]; uint16_t kr[MAXG];
         int nk = 0;
         for (int g = 0; g < self.nguard; ++g) {
             uint16_t played = 0;
@@ -941,16 +1017,16 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
         if (cx.status) return com_off;
     }
     // the new play-com
-    RouteList act, pend;
     act.n = 0;
     for (int i = base.n - 1; i >= 0; --i) rl_push(cx, act, base.r[i]);                 // (reverse base-routes)
     for (int i = 0; i < new_active.n; ++i) insert_route(cx, act, new_active.r[i]);
-    pend = new_pending;
+    pend.n = new_pending.n;
+    for (int i = 0; i < new_pending.n; ++i) pend.r[i] = new_pending.r[i];
     {
-        const Com self = *at<Com>(cx, self_off);
-        if (refreshed) { const Com rf = *at<Com>(cx, refreshed); for (int i = 0; i < rf.nact; ++i) insert_route(cx, act, rf.act[i]); }
+        const Com &self = *at<Com>(cx, self_off);                                      // the arena never moves: references stay valid
+        if (refreshed) { const Com &rf = *at<Com>(cx, refreshed); for (int i = 0; i < rf.nact; ++i) insert_route(cx, act, rf.act[i]); }
         for (int i = 0; i < self.npend; ++i) insert_route(cx, pend, self.pend[i]);
-        if (refreshed) { const Com rf = *at<Com>(cx, refreshed); for (int i = 0; i < rf.npend; ++i) insert_route(cx, pend, rf.pend[i]); }
+        if (refreshed) { const Com &rf = *at<Com>(cx, refreshed); for (int i = 0; i < rf.npend; ++i) insert_route(cx, pend, rf.pend[i]); }
         if (cx.status) return com_off;
         const uint32_t noff = arena_alloc(cx, sizeof(Com));
         if (cx.status) return com_off;
@@ -977,7 +1053,8 @@ PD_HDN void hunt_card(Ctx &cx, Outcome &o, int suit, int rank, const Hand *h)
     bool top[4] = {false, false, false, false};
     if ((h[1].s[suit] >> rank) & 1u) top[1] = true;
     else if ((h[3].s[suit] >> rank) & 1u) { if (beats(h[1], h[2], suit, cx.trump)) top[0] = true; else top[2] = true; }
-    Trick t;
+    TmpFrame tf(cx);
+    Trick &t = *tmp<Trick>(cx);
     trick_init(t, suit, cx.trump);
     for (int i = 0; i < 4; ++i) beat_or_low(cx, t, h[i], top[i]);
     outcome_of_trick(cx, o, t);
@@ -1027,23 +1104,27 @@ struct PlayFrame {
     uint32_t mark;
 };
 
-struct Result { int status; uint8_t score[2]; uint8_t n; Card tricks[13][4]; uint8_t wno[13]; uint32_t arena_peak; uint32_t nodes; };
+struct Result { int status; uint8_t score[2]; uint8_t n; Card tricks[13][4]; uint8_t wno[13]; uint32_t arena_peak; uint32_t nodes; uint32_t tmp_peak; };
 
 // scratch the caller provides (local memory on the device): the stacks of the two kinds of search
 struct Scratch {
     SearchFrame sstack[MAXD];
     PlayFrame pstack[MAXD];
     RootStrategy roots[2];
+    Result res;
+    alignas(8) uint8_t tmp[7168];    // temporaries of the call chain (deepest: play-deal > after-tricks > play-routes > search > simple-trick)
 };
 
 PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Hand *declarer_left_dummy_right, Scratch &S, Result &res)
 {
     Ctx cx;
     cx.arena = arena; cx.cap = arena_bytes; cx.top = 64; cx.status = PD_OK; cx.trump = trump;
+    cx.sstk = S.tmp; cx.scap = (uint32_t)sizeof(S.tmp); cx.stop = 0; cx.speak = 0;
     res.arena_peak = 0; res.nodes = 0; res.n = 0; res.score[0] = res.score[1] = 0;
-    const Hand *in = declarer_left_dummy_right;
-    Hand rolled[4] = {in[1], in[2], in[3], in[0]};                   // (roll -1 hands): the left-hand opponent leads
-    int8_t all_suits[4] = {0, 1, 2, 3};
+    Hand *in = tmp<Hand>(cx, 4), *rolled = tmp<Hand>(cx, 4);
+    for (int i = 0; i < 4; ++i) { in[i] = declarer_left_dummy_right[i]; rolled[i] = declarer_left_dummy_right[(i + 1) & 3]; }   // (roll -1 hands): the left-hand opponent leads
+    int8_t *all_suits = tmp<int8_t>(cx, 4);
+    for (int i = 0; i < 4; ++i) all_suits[i] = (int8_t)i;
     // active = strategy of the side on lead, passive = declarer's (2923-2926)
     find_opp_weakness(cx, S.roots[0], rolled, S.sstack);
     const uint32_t com_a = cx.status ? 0 : play_routes(cx, rolled, all_suits, 4, S.sstack);
@@ -1057,7 +1138,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         f.active.root = 0; f.active.com = com_a; f.passive.root = 1; f.passive.com = com_p;
         f.opt = 0; f.have_best = 0; outcome_nil(f.best);
     }
-    Outcome final;
+    Outcome &final = *tmp<Outcome>(cx), &ans = *tmp<Outcome>(cx);
     outcome_nil(final);
     bool entering = true;
     while (!cx.status) {
@@ -1084,17 +1165,12 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         }
         const int option = f.opt++;
         f.mark = cx.top;
-        Outcome ans;
         if (option == 0) play_strategy(cx, S.roots[f.active.root], f.hands, S.sstack, ans);
         else if (option == 1) mk_route(cx, f.active.com, f.hands, ans);
         else simple_trick(cx, ans, f.any_suit, f.hands, false);
         if (cx.status) break;
         if (ans.n == 0) {                                            // after-action gave nil
-            Outcome nil;
-            outcome_nil(nil);
-            const int cur = f.outcome.valid ? (f.outcome.roll & 1) : 0;
-            (void)cur;
-            if (!f.have_best) { f.best = nil; f.have_best = 1; }
+            if (!f.have_best) { outcome_nil(f.best); f.have_best = 1; }
             cx.top = f.mark;
             continue;
         }
@@ -1114,6 +1190,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     }
     if (cx.top > res.arena_peak) res.arena_peak = cx.top;
     res.status = cx.status;
+    res.tmp_peak = cx.speak;
     if (!cx.status && !final.valid) res.status = PD_E_NIL;
     if (res.status == PD_OK) {
         res.score[0] = final.score[0]; res.score[1] = final.score[1]; res.n = final.n;

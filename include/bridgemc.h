@@ -342,8 +342,8 @@ int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc
  * (score ...) pair: score[0] = tricks of the side that leads first (the defence), score[1] = tricks of the
  * declaring side, i.e. what `best-tricks` returns (bridge.cl:3028).  cards[t][i] = i-th card played to trick t,
  * suit << 4 | rank (0xFF = nothing played), winner[t] = position in the trick of the winning card
- * (`winner-nos`).  status: 0 ok; 1 the deal's route lists outgrew the per-deal arena (re-run with a larger
- * arena_kb); 2 the reference would signal a Lisp error on this deal; 3 an internal table overflowed;
+ * (`winner-nos`).  status: 0 ok; 1 the deal's route lists outgrew the per-deal arena (only with an explicit
+ * arena_kb, or beyond 8 MB); 2 the reference would signal a Lisp error on this deal; 3 an internal table overflowed;
  * 4 the reference returns nil. */
 typedef struct {
     uint8_t status, n_tricks;
@@ -354,7 +354,8 @@ typedef struct {
 } bmc_play_result;   /* 72 bytes */
 /* One GPU thread plays one deal.  trump[i] in {-1 (no trump), 0..3 = c d h s}; declarer[i] = seat 0..3 (N E S W);
  * the left-hand opponent (seat + 1) leads.  per_deal = 0: trump[0] / declarer[0] apply to every deal.
- * arena_kb: per-deal scratch for the route lists (0 = default 1024).  `bmc_play_deal` takes host buffers,
+ * arena_kb: per-deal scratch for the route lists; 0 = adaptive: 256 KB in a first pass, and the deals that outgrow
+ * it (about 1 % of random deals) are played again with 8 MB each.  `bmc_play_deal` takes host buffers,
  * `bmc_play_deal_dev` device pointers (no copies; runs on the context's stream and synchronises it). */
 int bmc_play_deal(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const int8_t *trump, const uint8_t *declarer,
                   int per_deal, uint32_t arena_kb, bmc_play_result *out);

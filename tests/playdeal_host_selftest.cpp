@@ -22,6 +22,7 @@ int main(int argc, char **argv)
         pd::Result r;
         pd::play_deal(arena.data(), arena_bytes, trump, h, S, r);
         printf("%d %d %d %d %u %u", r.status, r.score[0], r.score[1], r.n, r.arena_peak, r.nodes);
+        if (argc > 2) fprintf(stderr, "tmp_peak %u of %zu\n", r.tmp_peak, sizeof(S.tmp));
         if (r.status == 0) {
             for (int t = 0; t < r.n; ++t) for (int i = 0; i < 4; ++i) printf(" %02x", r.tricks[t][i]);
             for (int t = 0; t < r.n; ++t) printf(" %d", r.wno[t]);
