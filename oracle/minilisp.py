@@ -47,6 +47,14 @@ class Char(str):
     __slots__ = ()
 
 
+class Dotted(list):
+    """(a b . c) with an atom c: the heads, plus `.tail`"""
+
+    def __init__(self, heads, tail):
+        super().__init__(heads)
+        self.tail = tail
+
+
 _SYMS: dict = {}
 
 
@@ -106,6 +114,18 @@ class Reader:
                 if s[self.i] == ")":
                     self.i += 1
                     return items if items else None
+                if s[self.i] == "." and self.i + 1 < len(s) and (s[self.i + 1].isspace() or s[self.i + 1] in "(,'`"):
+                    self.i += 1
+                    tail = self.read()
+                    self.skip()
+                    if s[self.i] != ")":
+                        raise LispError("bad dotted list")
+                    self.i += 1
+                    if tail is None:
+                        return items
+                    if isinstance(tail, list) and not isinstance(tail, Dotted):
+                        return items + tail
+                    return Dotted(items, tail)
                 items.append(self.read())
         if c == ")":
             raise LispError("unexpected )")
@@ -202,6 +222,8 @@ def lisp_repr(x, readably=True):
         return "NIL"
     if x is True:
         return "T"
+    if isinstance(x, Dotted):
+        return "(" + " ".join(lisp_repr(e, readably) for e in x) + " . " + lisp_repr(x.tail, readably) + ")"
     if isinstance(x, list):
         return "(" + " ".join(lisp_repr(e, readably) for e in x) + ")"
     if isinstance(x, Sym):
@@ -211,8 +233,19 @@ def lisp_repr(x, readably=True):
     if isinstance(x, str):
         return '"' + x + '"' if readably else str(x)
     if isinstance(x, Instance):
+        it = x.cls.interp
+        po = it.generics.get(S("PRINT-OBJECT")) if it is not None else None
+        if po is not None and po.has_method_for(x.cls.name):
+            stream = StringStream()
+            po.fn(x, stream)
+            return "".join(stream.parts)
         return "#<%s>" % x.cls.name
     return str(x)
+
+
+class StringStream:
+    def __init__(self):
+        self.parts = []
 
 
 def lisp_format(ctrl, args):
@@ -267,8 +300,9 @@ def lisp_format_consume(ctrl, lst):
 # objects
 # ---------------------------------------------------------------------------
 class LClass:
-    def __init__(self, name, supers, slots):
+    def __init__(self, name, supers, slots, interp=None):
         self.name, self.supers, self.slots = name, supers, slots     # slots: [(name, initargs, initform, has_initform)]
+        self.interp = interp
 
 
 class Instance:
@@ -379,6 +413,8 @@ def equal(a, b):
     if eq(a, b):
         return True
     if isinstance(a, list) and isinstance(b, list):
+        if isinstance(a, Dotted) != isinstance(b, Dotted) or (isinstance(a, Dotted) and not equal(a.tail, b.tail)):
+            return False
         return len(a) == len(b) and all(equal(x, y) for x, y in zip(a, b))
     if isinstance(a, str) and isinstance(b, str) and not isinstance(a, Sym) and not isinstance(b, Sym):
         return str(a) == str(b) and isinstance(a, Char) == isinstance(b, Char)
@@ -621,6 +657,14 @@ class Interp:
         if isinstance(x, list):
             if len(x) == 2 and x[0] is UNQUOTE:
                 return self.eval(x[1], env, fenv)
+            if len(x) >= 3 and x[-2] is UNQUOTE and not isinstance(x, Dotted):      # (a b . ,form)
+                heads = self.quasi(x[:-2], env, fenv) or []
+                tail = self.eval(x[-1], env, fenv)
+                if tail is None:
+                    return lst(heads)
+                if isinstance(tail, list) and not isinstance(tail, Dotted):
+                    return heads + tail
+                return Dotted(heads, tail)
             out = []
             for e in x:
                 if isinstance(e, list) and len(e) == 2 and e[0] is SPLICE:
@@ -795,7 +839,7 @@ class Interp:
                 elif o in (":READER", ":ACCESSOR"):
                     self.generic(v).add_reader(name, sname)
             slots.append((sname, initargs, initform, has))
-        self.classes[name] = LClass(name, supers, slots)
+        self.classes[name] = LClass(name, supers, slots, self)
         return name
 
     def sf_defcondition(self, f, env, fenv):
@@ -1194,8 +1238,36 @@ def install_builtins(it: Interp):
     defb("THIRD", lambda l: nth(2, l))
     defb("FOURTH", lambda l: nth(3, l))
     defb("NTH", nth)
-    defb("CDR", lambda l: lst(need_list(l)[1:]))
-    defb("REST", lambda l: lst(need_list(l)[1:]))
+    def cdr(l):
+        l = need_list(l)
+        if isinstance(l, Dotted):
+            return l.tail if len(l) == 1 else Dotted(l[1:], l.tail)
+        return lst(l[1:])
+    defb("CDR", cdr)
+    defb("REST", cdr)
+
+    def assoc(item, alist, *rest):
+        t = testfn(kwargs(rest, 0))
+        for e in need_list(alist):
+            if e is not None and t(item, e[0]):
+                return e
+        return None
+    defb("ASSOC", assoc)
+
+    def sublis(alist, tree):
+        def walk(x):
+            if isinstance(x, list):
+                out = [walk(e) for e in x]
+                return Dotted(out, walk(x.tail)) if isinstance(x, Dotted) else out
+            if isinstance(x, Sym) or x is True:
+                for e in need_list(alist):
+                    if eq(e[0], x):
+                        return cdr(e)
+            return x
+        return walk(tree)
+    defb("SUBLIS", sublis)
+    defb("STRING-DOWNCASE", lambda x: LStr(str(x).lower()))
+    defb("STRING-UPCASE", lambda x: LStr(str(x).upper()))
     defb("NTHCDR", lambda n, l: lst(need_list(l)[n:]))
     defb("LAST", lambda l: lst(need_list(l)[-1:]))
     defb("LIST", lambda *a: lst(list(a)))
@@ -1366,6 +1438,9 @@ def install_builtins(it: Interp):
         s = lisp_format(ctrl, a)
         if dest is None:
             return s
+        if isinstance(dest, StringStream):
+            dest.parts.append(str(s))
+            return None
         it.out.append(str(s))
         return None
     defb("FORMAT", fmt)

@@ -4,6 +4,7 @@ only) under oracle/minilisp.py and write what they compute into committed fixtur
 
     python oracle/run_reference.py tests            # tests/golden/reference_inline_tests.json
     python oracle/run_reference.py playdeal [N]     # tests/golden/playdeal_ref.json
+    python oracle/run_reference.py tables           # tests/golden/reference_tables.json
 
 `tests` evaluates every inline `(test FORM EXPECTED PRED)` form of bridge.cl (lines 23-3086) with the reference's own
 definitions and records pass / fail and, for failures, the value the reference code really produces.  At this
@@ -11,6 +12,12 @@ snapshot eight tests of the trick estimator fail IN THE REFERENCE ITSELF (their 
 bridge.cl:2694 expects a trick led with a card that was played two tricks earlier, and the TODO above it shows the
 value was pasted from another deal); the oracle's restatement (oracle/playdeal.py) is held to the value the code
 computes, not to the stale literal.
+
+`tables` evaluates, with the reference's own definitions (bridge.cl, bidding.cl, compscore.cl): `contract-score`
+(bridge.cl:3045) over its whole input domain (5 suits x level nil / 1..7 x nil / x / xx x vulnerable x 0..13 tricks --
+the reference has no direct test of it), `match-points`' IMP scale for every |difference| 0..4100 (compscore.cl:123-131),
+and, for seeded random hands, `assess-hand`, `balanced?` (bidding.cl:33-46) and `choose-bid` (146-150: the reference
+`eval`s the rule forms) over `openings`, `(nt-responses 1)`, `(nt-responses 2)` and `2C-responses`.
 
 `playdeal` draws seeded random deals (full 13-card deals and k-card endings), calls the reference's `play-deal`
 (bridge.cl:2961) on each with no trump and with a trump suit, and stores deal, trump, tricks, winners and score.
@@ -136,6 +143,53 @@ def gen_playdeal(n_full):
     return [r if r is not None else {"hands": j[0], "trump": j[1], "error": "recursion depth"} for r, j in zip(rows, jobs)]
 
 
+def gen_tables():
+    it = load()
+    for fn in ("bidding.cl", "compscore.cl"):
+        M.load_file(it, os.path.join(os.path.dirname(REF), fn))
+    f = lambda name: it.fn(M.S(name))  # noqa: E731
+    kw = M.S
+    # contract-score: [suit 0..4][level 0 = nil, 1..7][double 0..2][vulnerable 0..1][tricks 0..13]
+    suits = [M.S("C"), M.S("D"), M.S("H"), M.S("S"), None]
+    dbls = [None, M.S("X"), M.S("XX")]
+    cs = [[[[[f("CONTRACT-SCORE")(su, t, kw(":VULNERABLE"), True if v else None, kw(":DOUBLE"), d, kw(":LEVEL"), lv or None)
+              for t in range(14)] for v in (0, 1)] for d in dbls] for lv in range(8)] for su in suits]
+    nt_sym = [f("CONTRACT-SCORE")(M.S("NT"), t, kw(":LEVEL"), 3) for t in range(14)]
+    assert nt_sym == cs[4][3][0][0]
+    # the IMP scale: position of the first threshold above |diff|, nil (error) from 4000 on
+    pts = it.gvar[M.S("*IMP-PTS*")]
+    imps = [f("POSITION-IF")(f("CURRY")(f("<"), d), pts) for d in range(0, 4101)]
+    # hands
+    rng = random.Random(77)
+    schemes = {"openings": it.gvar[M.S("OPENINGS")], "nt-responses-1": f("NT-RESPONSES")(1), "nt-responses-2": f("NT-RESPONSES")(2),
+               "2c-responses": it.gvar.get(M.S("2C-RESPONSES")) or f("2C-RESPONSES")()}
+    hands = []
+    for i in range(1500):
+        if i % 3 == 0:
+            cards = sorted(rng.sample(range(52), 13))
+        else:                                   # bias towards strong / shapely hands so that every row of the tables fires
+            pool = list(range(52))
+            w = [3.0 if c % 13 >= 9 else 1.0 for c in pool] if i % 3 == 1 else [4.0 if c // 13 == rng.randrange(4) else 1.0 for c in pool]
+            cards = set()
+            while len(cards) < 13:
+                cards.add(rng.choices(pool, w)[0])
+            cards = sorted(cards)
+        suits_l = [[c % 13 for c in cards if c // 13 == s] or None for s in range(4)]
+        h = it.make_instance(M.S("HAND"), M.S(":="), [list(x) if x else None for x in suits_l])
+        lens, power, losers = f("ASSESS-HAND")(h)
+        row = {"hand": [x or [] for x in suits_l], "lens": to_py(lens), "power": to_py(power), "losers": losers,
+               "balanced": bool(M.truthy(f("BALANCED?")(lens, power, None))), "bids": {}}
+        for name, scheme in schemes.items():
+            try:
+                row["bids"][name] = to_py(f("CHOOSE-BID")(h, scheme))
+            except M.LispError as e:
+                row["bids"][name] = "error"
+        hands.append(row)
+    return {"source": "bridge.cl / bidding.cl / compscore.cl evaluated by oracle/minilisp.py",
+            "contract_score": cs, "imps": imps, "hands": hands,
+            "schemes": {k: M.lisp_repr(v) for k, v in schemes.items()}}
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "tests"
     if what == "tests":
@@ -146,6 +200,10 @@ def main():
             print("  bridge.cl:%d" % r["line"], r.get("error", ""))
         json.dump({"source": "bridge.cl:23-3086, evaluated by oracle/minilisp.py", "results": res},
                   open(os.path.join(GOLDEN, "reference_inline_tests.json"), "w"), indent=0)
+    elif what == "tables":
+        out = big_stack(gen_tables)
+        json.dump(out, open(os.path.join(GOLDEN, "reference_tables.json"), "w"), separators=(",", ":"))
+        print("contract-score table, IMP scale and %d hands written" % len(out["hands"]))
     elif what == "playdeal":
         n = int(sys.argv[2]) if len(sys.argv) > 2 else 24
         t0 = time.time()
