@@ -6,7 +6,8 @@ only) under oracle/minilisp.py and write what they compute into committed fixtur
     python oracle/run_reference.py playdeal [N]     # tests/golden/playdeal_ref.json
     python oracle/run_reference.py tables           # tests/golden/reference_tables.json
 
-`tests` evaluates every inline `(test FORM EXPECTED PRED)` form of bridge.cl (lines 23-3086) with the reference's own
+`tests` evaluates every inline `(test FORM EXPECTED PRED)` form of bridge.cl (lines 23-3086), bidding.cl and compscore.cl
+with the reference's own
 definitions and records pass / fail and, for failures, the value the reference code really produces.  At this
 snapshot eight tests of the trick estimator fail IN THE REFERENCE ITSELF (their expected values are stale: e.g.
 bridge.cl:2694 expects a trick led with a card that was played two tricks earlier, and the TODO above it shows the
@@ -69,26 +70,26 @@ def to_py(x):
 
 def run_inline_tests():
     res = []
-    it = None
-
-    def on_test(line, form):
-        t0 = time.time()
-        try:
-            got = it.eval(form[1], None, None)
-            want = it.eval(form[2], None, None)
-            ok = M.truthy(it.fn(form[3])(got, want))
-            rec = {"line": line, "ok": bool(ok)}
-            if not ok:
-                rec["reference_computes"] = M.lisp_repr(got)
-                rec["literal_expected"] = M.lisp_repr(want)
-        except Exception as e:  # noqa: BLE001
-            rec = {"line": line, "ok": False, "error": repr(e)[:200]}
-        rec["seconds"] = round(time.time() - t0, 2)
-        res.append(rec)
-
-    # definitions first (some tests use functions defined further down the file), then the tests in file order
-    it = load(on_test=None)
-    M.load_file(it, REF, first_line=23, last_line=3086, on_test=on_test)
+    it = load()
+    for fn in ("bidding.cl", "compscore.cl"):
+        M.load_file(it, os.path.join(os.path.dirname(REF), fn))         # definitions first: tests use functions defined further down
+    for fn in ("bridge.cl", "bidding.cl", "compscore.cl"):
+        def on_test(line, form, fn=fn):
+            t0 = time.time()
+            try:
+                got = it.eval(form[1], None, None)
+                want = it.eval(form[2], None, None)
+                ok = M.truthy(it.fn(form[3])(got, want))
+                rec = {"file": fn, "line": line, "ok": bool(ok)}
+                if not ok:
+                    rec["reference_computes"] = M.lisp_repr(got)
+                    rec["literal_expected"] = M.lisp_repr(want)
+            except Exception as e:  # noqa: BLE001
+                rec = {"file": fn, "line": line, "ok": False, "error": repr(e)[:200]}
+            rec["seconds"] = round(time.time() - t0, 2)
+            res.append(rec)
+        M.load_file(it, os.path.join(os.path.dirname(REF), fn), first_line=23 if fn == "bridge.cl" else 0,
+                    last_line=3086 if fn == "bridge.cl" else 10 ** 9, on_test=on_test)
     return res
 
 
@@ -195,10 +196,11 @@ def main():
     if what == "tests":
         res = big_stack(run_inline_tests)
         bad = [r for r in res if not r["ok"]]
-        print(f"{len(res)} inline tests of bridge.cl evaluated by the reference's own code: {len(res) - len(bad)} pass, {len(bad)} fail")
+        print(f"{len(res)} inline tests of bridge.cl, bidding.cl, compscore.cl evaluated by the reference's own code: "
+              f"{len(res) - len(bad)} pass, {len(bad)} fail")
         for r in bad:
-            print("  bridge.cl:%d" % r["line"], r.get("error", ""))
-        json.dump({"source": "bridge.cl:23-3086, evaluated by oracle/minilisp.py", "results": res},
+            print("  %s:%d" % (r["file"], r["line"]), r.get("error", ""))
+        json.dump({"source": "bridge.cl:23-3086, bidding.cl, compscore.cl evaluated by oracle/minilisp.py", "results": res},
                   open(os.path.join(GOLDEN, "reference_inline_tests.json"), "w"), indent=0)
     elif what == "tables":
         out = big_stack(gen_tables)

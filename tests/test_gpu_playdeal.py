@@ -82,7 +82,8 @@ def test_host_mirror_play_deal_and_measures(engine):
     code computes (tests/golden/reference_inline_tests.json; the literal in the file is stale), and msr-<contract>."""
     from bridge_mc_b200 import deal, playdeal, sexp
     from bridge_mc_b200.cards import str2hand
-    inline = {r["line"]: r for r in json.load(open(os.path.join(HERE, "golden", "reference_inline_tests.json")))["results"]}
+    inline = {r["line"]: r for r in json.load(open(os.path.join(HERE, "golden", "reference_inline_tests.json")))["results"]
+              if r["file"] == "bridge.cl"}
     hands = [str2hand(t) for t in ("♣ AKQ7 ♦ 10 ♥ QJ632 ♠ 832", "♣ J54 ♦ KJ82 ♥ 8 ♠ KQJ95", "♣ 9832 ♦ A75 ♥ A975 ♠ A10",
                                   "♣ 106 ♦ Q9643 ♥ K104 ♠ 764")]
     out = playdeal.play_deal(None, *hands, engine=engine)
