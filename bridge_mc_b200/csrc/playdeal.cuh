@@ -50,7 +50,7 @@ constexpr Card NOCARD = 0xFF;
 constexpr int MAXR = 40;         // routes per list
 constexpr int MAXG = 8;          // guards per play-com
 constexpr int MAXT = 6;          // targets per strategy
-constexpr int MAXD = 15;         // search depth (13 tricks + root + 1)
+constexpr int MAXD = 14;         // search depth (13 tricks + the root)
 
 enum Status : int { PD_OK = 0, PD_E_ARENA = 1, PD_E_LISP = 2, PD_E_CAP = 3, PD_E_NIL = 4 };
 
@@ -91,7 +91,7 @@ struct Hand {
 };
 PD_HD bool hand_empty(const Hand &h) { return (h.s[0] | h.s[1] | h.s[2] | h.s[3]) == 0; }
 
-struct Outcome {                 // bridge.cl:2190-2196; winners = tricks[i][wno[i]]
+struct alignas(4) Outcome {      // bridge.cl:2190-2196; winners = tricks[i][wno[i]]
     uint8_t n;                   // tricks played
     uint8_t roll;
     uint8_t score[2];
@@ -168,7 +168,7 @@ PD_HD bool card_higher(const Trick &t, int asuit, int arank, int bsuit, int bran
     return arank > brank;
 }
 // (play trick card rest) 1588-1599
-PD_HD void trick_play(Trick &t, Card card, const Hand &rest)
+PD_HDN void trick_play(Trick &t, Card card, const Hand &rest)
 {
     if (card != NOCARD && card_higher(t, csuit(card), crank(card), t.hsuit, t.hrank)) {
         t.hsuit = (int8_t)csuit(card); t.hrank = (int8_t)crank(card); t.winner = (int8_t)t.n;
@@ -188,7 +188,7 @@ PD_HD void hand_take(const Hand &h, int suit, int rank, Card &card, Hand &rest)
 }
 
 // weak-suit (1732-1768): the suit to discard from; -1 when the hand is empty
-PD_HD int weak_suit(const Hand &h, const Trick &t)
+PD_HDN int weak_suit(const Hand &h, const Trick &t)
 {
     int acc = -1;
     for (int suit = 0; suit < 4; ++suit) {
@@ -228,13 +228,13 @@ PD_HD int ch_take_higher(uint32_t m, int high, bool use_highest)
 PD_HD int ch_closest(uint32_t m, int rank) { const uint32_t a = above(m, rank - 1); return a ? lowbit(a) : highbit(m); }
 
 struct Play { bool ok; Card card; Hand rest; };
-PD_HD Play play_rank(const Hand &h, int suit, int rank)
+PD_HDN Play play_rank(const Hand &h, int suit, int rank)
 {
     Play p; p.ok = rank >= 0;
     if (p.ok) hand_take(h, suit, rank, p.card, p.rest); else { p.card = NOCARD; p.rest = h; }
     return p;
 }
-PD_HD Play play_lowest(Ctx &cx, const Hand &h, int suit)
+PD_HDN Play play_lowest(Ctx &cx, const Hand &h, int suit)
 {
     if (suit < 0) { fail(cx, PD_E_LISP); Play p; p.ok = false; p.card = NOCARD; p.rest = h; return p; }   // (nth nil suits)
     return play_rank(h, suit, ch_lowest(h.s[suit]));
@@ -329,7 +329,7 @@ PD_HDN bool finesse_if_possible(Ctx &cx, Trick &t, const Hand &h1, const Hand &h
 }
 
 // beats? (1705-1714)
-PD_HD bool beats(const Hand &a, const Hand &b, int suit, int trump)
+PD_HDN bool beats(const Hand &a, const Hand &b, int suit, int trump)
 {
     const uint32_t ac = a.s[suit], bc = b.s[suit];
     const uint32_t atr = trump >= 0 ? a.s[trump] : 0u, btr = trump >= 0 ? b.s[trump] : 0u;
@@ -342,7 +342,17 @@ PD_HD bool beats(const Hand &a, const Hand &b, int suit, int trump)
 // ---------------------------------------------------------------------------
 // outcomes (bridge.cl:2204-2267)
 // ---------------------------------------------------------------------------
-PD_HD void outcome_empty(Outcome &o, const Hand *hands)
+// struct copies go through one out-of-line routine each: the search is some hundred KB of code with no hot loop, and
+// instruction fetch is a quarter of its time (profiles/r02_prof_playdeal.txt)
+PD_HDN void copy_words(void *dst, const void *src, int words)
+{
+    uint32_t *d = static_cast<uint32_t *>(dst);
+    const uint32_t *s = static_cast<const uint32_t *>(src);
+    for (int i = 0; i < words; ++i) d[i] = s[i];
+}
+PD_HD void outcome_copy(Outcome &dst, const Outcome &src) { if (&dst != &src) copy_words(&dst, &src, (int)(sizeof(Outcome) / 4)); }
+
+PD_HDN void outcome_empty(Outcome &o, const Hand *hands)
 {
     o.n = 0; o.roll = 0; o.score[0] = o.score[1] = 0; o.valid = 1;
     for (int i = 0; i < 4; ++i) o.rem[i] = hands[i];
@@ -350,7 +360,7 @@ PD_HD void outcome_empty(Outcome &o, const Hand *hands)
 PD_HD void outcome_nil(Outcome &o) { o.valid = 0; o.n = 0; o.roll = 0; o.score[0] = o.score[1] = 0; }
 
 // new-outcome of a finished trick (2204-2210)
-PD_HD void outcome_of_trick(Ctx &cx, Outcome &o, const Trick &t)
+PD_HDN void outcome_of_trick(Ctx &cx, Outcome &o, const Trick &t)
 {
     if (t.winner < 0 || t.n != 4) { fail(cx, PD_E_LISP); outcome_nil(o); return; }
     o.valid = 1; o.n = 1; o.roll = (uint8_t)t.winner;
@@ -360,7 +370,7 @@ PD_HD void outcome_of_trick(Ctx &cx, Outcome &o, const Trick &t)
     for (int i = 0; i < 4; ++i) o.rem[i] = t.rem[(i + t.winner) & 3];       // (roll (- winner) remaining)
 }
 // add-outcome (2212-2223): self += other, roll := other's roll.  star = add-outcome* (2225-2235): roll adds up.
-PD_HD void outcome_add(Ctx &cx, Outcome &self, const Outcome &other, bool star)
+PD_HDN void outcome_add(Ctx &cx, Outcome &self, const Outcome &other, bool star)
 {
     if (self.n + other.n > 13) { fail(cx, PD_E_CAP); return; }
     for (int k = 0; k < other.n; ++k) {
@@ -411,7 +421,7 @@ struct SearchFrame {
 PD_HD void roll2(const Hand *h, Hand *out) { out[0] = h[2]; out[1] = h[3]; out[2] = h[0]; out[3] = h[1]; }
 
 // candidate list of immediate-tricks for the hands of a frame
-PD_HD void immediate_opts(const Ctx &cx, SearchFrame &f, const int8_t *suits, int nsuits)
+PD_HDN void immediate_opts(const Ctx &cx, SearchFrame &f, const int8_t *suits, int nsuits)
 {
     f.nopt = 0;
     const Hand &a = f.hands[0], &b = f.hands[1], &d = f.hands[3];
@@ -432,10 +442,10 @@ PD_HD void fourway_opts(SearchFrame &f, int suit)
 }
 
 // acc := (best-outcome acc val) (2253-2258)
-PD_HD void best_update(SearchFrame &f, const Outcome &val)
+PD_HDN void best_update(SearchFrame &f, const Outcome &val)
 {
-    if (!f.have_best) { f.best = val; f.have_best = 1; return; }
-    if (!f.best.valid || (val.valid && f.best.score[0] < val.score[0])) f.best = val;
+    if (!f.have_best) { outcome_copy(f.best, val); f.have_best = 1; return; }
+    if (!f.best.valid || (val.valid && f.best.score[0] < val.score[0])) outcome_copy(f.best, val);
 }
 
 // `stack`: MAXD frames in the caller's local memory
@@ -460,7 +470,7 @@ PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int 
             Outcome &val = f.best;
             if (kind == SUIT_TOPS && !val.valid) outcome_empty(val, f.hands);
             if (kind == PLAY_THROUGH && !f.have_best) outcome_empty(val, f.hands);
-            if (sp == 0) { result = val; return; }
+            if (sp == 0) { outcome_copy(result, val); return; }
             SearchFrame &p = stack[sp - 1];
             outcome_add(cx, p.cur, val, false);          // (add-outcome self (apply if-won remaining))
             best_update(p, p.cur);
@@ -486,7 +496,7 @@ PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int 
 // ---------------------------------------------------------------------------
 // suit-tricks -> suit-value -> deal-plan -> find-opp-weakness (2279-2356, 2745-2759)
 // ---------------------------------------------------------------------------
-struct SuitValue {
+struct alignas(4) SuitValue {
     int8_t suit, trump;          // trump: -1 = evaluated without
     uint8_t ngroups;
     uint8_t glen[15];
@@ -543,13 +553,13 @@ PD_HDN void find_opp_weakness(Ctx &cx, RootStrategy &rs, const Hand *deal, Searc
         suit_value(cx, nt, suit, -1, deal, stack);
         if (trump >= 0) {
             suit_value(cx, tr, suit, trump, deal, stack);
-            if (tr.ours > nt.ours) nt = tr;                 // better (2326-2327)
+            if (tr.ours > nt.ours) copy_words(&nt, &tr, (int)(sizeof(SuitValue) / 4));                 // better (2326-2327)
         }
-        if (nt.ours > 0) vals[nv++] = nt;
+        if (nt.ours > 0) copy_words(&vals[nv++], &nt, (int)(sizeof(SuitValue) / 4));
     }
     // (sort ... (> (ours a) (ours b))): stable
     for (int i = 1; i < nv; ++i)
-        for (int j = i; j > 0 && vals[j].ours > vals[j - 1].ours; --j) { nt = vals[j]; vals[j] = vals[j - 1]; vals[j - 1] = nt; }
+        for (int j = i; j > 0 && vals[j].ours > vals[j - 1].ours; --j) { copy_words(&nt, &vals[j], (int)(sizeof(SuitValue) / 4)); copy_words(&vals[j], &vals[j - 1], (int)(sizeof(SuitValue) / 4)); copy_words(&vals[j - 1], &nt, (int)(sizeof(SuitValue) / 4)); }
     int *order = tmp<int>(cx, 12), no = 0;
     if (trump >= 0) {
         for (int i = 0; i < nv; ++i) if (vals[i].trump >= 0) order[no++] = i;
@@ -593,7 +603,7 @@ struct RouteList { int n; uint32_t r[MAXR]; };
 PD_HD uint32_t pack4(const Card *c) { return (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24); }
 PD_HD Card tcard(uint32_t t, int i) { return (Card)(t >> (8 * i)); }
 
-PD_HD uint32_t new_route(Ctx &cx, int frm, int to, int tvoid, uint32_t tricks, uint32_t len)
+PD_HDN uint32_t new_route(Ctx &cx, int frm, int to, int tvoid, uint32_t tricks, uint32_t len)
 {
     const uint32_t off = arena_alloc(cx, sizeof(Route));
     Route *r = at<Route>(cx, off);
@@ -601,7 +611,7 @@ PD_HD uint32_t new_route(Ctx &cx, int frm, int to, int tvoid, uint32_t tricks, u
     return off;
 }
 PD_HD void rl_push(Ctx &cx, RouteList &l, uint32_t r) { if (l.n < MAXR) l.r[l.n++] = r; else fail(cx, PD_E_CAP); }
-PD_HD void rl_push_front(Ctx &cx, RouteList &l, uint32_t r)
+PD_HDN void rl_push_front(Ctx &cx, RouteList &l, uint32_t r)
 {
     if (l.n >= MAXR) { fail(cx, PD_E_CAP); return; }
     for (int i = l.n; i > 0; --i) l.r[i] = l.r[i - 1];
@@ -709,7 +719,7 @@ struct Item { Card cards[4]; uint8_t wno; uint8_t mine; uint8_t guard; int8_t gs
 
 PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsuits, SearchFrame *stack);
 
-PD_HD uint32_t tricks_from(Ctx &cx, const uint32_t *src, int n)
+PD_HDN uint32_t tricks_from(Ctx &cx, const uint32_t *src, int n)
 {
     const uint32_t off = arena_alloc(cx, (uint32_t)n * 4u);
     if (cx.status) return 0;
@@ -1112,7 +1122,7 @@ struct Scratch {
     PlayFrame pstack[MAXD];
     RootStrategy roots[2];
     Result res;
-    alignas(8) uint8_t tmp[7168];    // temporaries of the call chain (deepest: play-deal > after-tricks > play-routes > search > simple-trick)
+    alignas(8) uint8_t tmp[5120];    // temporaries of the call chain (measured peak 4 248 B) (deepest: play-deal > after-tricks > play-routes > search > simple-trick)
 };
 
 PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Hand *declarer_left_dummy_right, Scratch &S, Result &res)
@@ -1149,15 +1159,15 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
             for (int s = 0; s < 4; ++s) if (f.hands[0].s[s]) { f.any_suit = (int8_t)s; break; }
             f.opt = 0; f.have_best = 0; outcome_nil(f.best);
             entering = false;
-            if (f.any_suit < 0) { f.best = f.outcome; f.opt = 3; }      // (outcome this)
+            if (f.any_suit < 0) { outcome_copy(f.best, f.outcome); f.opt = 3; }      // (outcome this)
         }
         if (f.opt == 3) {
-            if (sp == 0) { final = f.best; break; }
+            if (sp == 0) { outcome_copy(final, f.best); break; }
             // hand the value to the parent: (best-outcome* roll options) (2260-2267)
             PlayFrame &p = S.pstack[sp - 1];
             const int cur = p.outcome.valid ? (p.outcome.roll & 1) : 0;
-            if (!p.have_best) { p.best = f.best; p.have_best = 1; }
-            else if (!p.best.valid || (f.best.valid && p.best.score[cur] < f.best.score[cur])) p.best = f.best;
+            if (!p.have_best) { outcome_copy(p.best, f.best); p.have_best = 1; }
+            else if (!p.best.valid || (f.best.valid && p.best.score[cur] < f.best.score[cur])) outcome_copy(p.best, f.best);
             if (cx.top > res.arena_peak) res.arena_peak = cx.top;
             cx.top = p.mark;                                         // everything the option allocated is unreachable now
             --sp;
@@ -1180,7 +1190,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         if (sp + 1 >= MAXD) { fail(cx, PD_E_CAP); break; }
         PlayFrame &c = S.pstack[sp + 1];
         for (int i = 0; i < 4; ++i) c.hands[i] = ans.rem[i];
-        if (f.outcome.valid) { c.outcome = f.outcome; outcome_add(cx, c.outcome, ans, true); } else c.outcome = ans;
+        if (f.outcome.valid) { outcome_copy(c.outcome, f.outcome); outcome_add(cx, c.outcome, ans, true); } else outcome_copy(c.outcome, ans);
         const bool w = outcome_won(ans);
         Strategy na = {f.active.root, new_a}, np = {f.passive.root, new_p};
         c.active = w ? na : np;

@@ -30,8 +30,10 @@ n = int(next((a for a in sys.argv[1:] if not a.startswith("--")), 32768))
 eng = Engine(0)
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
-rec, tal, stats = eng.sample(cons, n_accept=n, seed=11)
-rec = np.ascontiguousarray(rec[:n])
+# a fixed index range, every accepted deal of it, in a canonical order: the same deal set on every run
+rec, tal, stats = eng.sample(cons, n_raw=int(n / 0.038133), seed=11)
+rec = np.ascontiguousarray(rec[np.lexsort((rec[:, 0], rec[:, 1]))])
+n = rec.shape[0]
 d_rec = torch.from_numpy(rec.view(np.int64).copy()).cuda()
 d_out = torch.empty(n * 72, dtype=torch.uint8, device="cuda")
 d_t = torch.tensor([-1], dtype=torch.int8, device="cuda")
