@@ -188,8 +188,8 @@ int  bmc_constraints_primary(const bmc_constraints *c);
 /* Attaches the contracts to score to a constraint: with BMC_TALLY_SCORE in tally_mask the sampling kernels tally, for
  * every ACCEPTED deal, tricks[c][t] and imps[p][24 + match-points(contracts[pairs[2p]], contracts[pairs[2p+1]])] in the
  * launch that draws the deal -- `msr-<contract>` measures + base-score + histogram of rest.cl:287-303 / compscore.cl in
- * one pass ("compscore tallies over constrained samples").  The trick column comes from a stand-in for the reference's
- * play-deal estimator (not part of this library): eight exactly uniform values 0..13 that are a function of the deal
+ * one pass ("compscore tallies over constrained samples").  The trick column of this fused path is a stand-in for the
+ * play-deal estimator (bmc_play_deal below, about a millisecond of GPU time per deal): eight exactly uniform values 0..13 that are a function of the deal
  * alone (Philox keyed by seed, counter = the deal's record), so tallies do not depend on the dealing mode, the index
  * behind a deal or the split over devices.  n_contracts <= 8, n_pairs <= 8; vulnerable[c] != 0 => :vulnerable t. */
 int  bmc_constraints_set_scoring(bmc_constraints *c, const bmc_contract *contracts, const uint8_t *vulnerable,

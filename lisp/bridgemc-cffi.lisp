@@ -436,3 +436,59 @@ of DEAL and returns (values tricks-hist imps-hist dropped): ((contract (tricks c
         (values (loop for i from 0 below nc collect (cons (nth i contracts) (funcall (rows +tally-tricks+ 14 14 0) i)))
                 (loop for i from 0 below np collect (cons (nth i pairs) (funcall (rows +tally-imps+ 49 49 24) i)))
                 (loop for i from 0 below np collect (cffi:mem-aref tallies :uint64 (+ +tally-imps+ 392 i))))))))
+
+;;; ---- play-deal / best-tricks (bridge.cl:2961-2963, 3027-3028): the trick estimator on the GPU ----------------
+(cffi:defcstruct bmc-play-result
+  (status :uint8) (n-tricks :uint8) (score :uint8 :count 2) (cards :uint8 :count 52) (winner :uint8 :count 13)
+  (reserved :uint8 :count 3))
+(cffi:defcfun "bmc_play_hands" :int
+  (ctx :pointer) (hands :pointer) (n :uint64) (trump :pointer) (per-deal :int) (arena-kb :uint32) (out :pointer))
+(cffi:defcfun "bmc_best_tricks" :int
+  (ctx :pointer) (records :pointer) (n :uint64) (trump :pointer) (declarer :pointer) (per-deal :int)
+  (arena-kb :uint32) (tricks :pointer))
+
+(defun trump-code (trump)
+  "suit symbol (c d h s), suit number, nil or 'nt -> -1 .. 3 (what play-deal's (if (not (eq trump 'nt)) trump) and
+normsuit make of it, bridge.cl:1528-1530, 2963)"
+  (cond ((null trump) -1) ((numberp trump) trump) (t (or (position trump '(c d h s)) -1))))
+
+(defun play-deal (trump declarer left dummy right)
+  "bridge.cl:2961-2963, same lambda list: four hand objects (possibly an ending).  Returns an `outcome` whose tricks,
+winner-nos and score slots are what the reference's search returns -- one bmc_play_hands call."
+  (cffi:with-foreign-objects ((hands :uint64 4) (tr :int8) (out '(:struct bmc-play-result)))
+    (loop for h in (list declarer left dummy right) for k from 0
+          do (setf (cffi:mem-aref hands :uint64 k) (hand->lane-mask h)))
+    (setf (cffi:mem-ref tr :int8) (trump-code trump))
+    (with-gpu-call (bmc-check (bmc-play-hands (bmc-ctx) hands 1 tr 0 0 out)))
+    (let ((status (cffi:foreign-slot-value out '(:struct bmc-play-result) 'status))
+          (n (cffi:foreign-slot-value out '(:struct bmc-play-result) 'n-tricks))
+          (cards (cffi:foreign-slot-pointer out '(:struct bmc-play-result) 'cards))
+          (winner (cffi:foreign-slot-pointer out '(:struct bmc-play-result) 'winner))
+          (score (cffi:foreign-slot-pointer out '(:struct bmc-play-result) 'score)))
+      (case status
+        (4 nil)                                                  ; the reference returns nil
+        (0 (make-instance 'outcome
+             :tricks (loop for tno from 0 below n
+                           collect (loop for i from 0 below 4
+                                         for c = (cffi:mem-aref cards :uint8 (+ (* 4 tno) i))
+                                         collect (if (= c 255) nil (list (ash c -4) (logand c 15)))))
+             :winner-nos (loop for tno from 0 below n collect (cffi:mem-aref winner :uint8 tno))
+             :winners (loop for tno from 0 below n
+                            for w = (cffi:mem-aref winner :uint8 tno)
+                            for c = (cffi:mem-aref cards :uint8 (+ (* 4 tno) w))
+                            collect (list (ash c -4) (logand c 15)))
+             :score (list (cffi:mem-aref score :uint8 0) (cffi:mem-aref score :uint8 1))
+             :remaining nil))
+        (t (error "play-deal: status ~A (~A)" status (bmc-last-error)))))))
+
+(defun best-tricks (trump n e s w)
+  "bridge.cl:3027-3028"
+  (second (score (play-deal trump n e s w))))
+
+(defun records-best-tricks (records n trump declarer)
+  "best-tricks for a whole record buffer (what an `msr-<contract>` measure over an mc-case needs, rest.cl:287-303):
+RECORDS = foreign bmc-record array, TRUMP / DECLARER the same for every deal.  Returns a list of N trick counts."
+  (cffi:with-foreign-objects ((tr :int8) (de :uint8) (tricks :uint8 n))
+    (setf (cffi:mem-ref tr :int8) (trump-code trump) (cffi:mem-ref de :uint8) declarer)
+    (with-gpu-call (bmc-check (bmc-best-tricks (bmc-ctx) records n tr de 0 0 tricks)))
+    (loop for i from 0 below n collect (cffi:mem-aref tricks :uint8 i))))

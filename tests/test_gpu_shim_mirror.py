@@ -248,3 +248,35 @@ def test_score_tallies_and_multi_device_as_the_shim_calls_them(ctx):
     got, st = sample_records(ctx, handle, 5, 0, 1000, devices=devices)
     assert got.shape[0] >= 1000
     L.bmc_constraints_destroy(handle)
+
+
+def test_play_deal_as_the_shim_calls_it(ctx):
+    """lisp/bridgemc-cffi.lisp `play-deal` / `best-tricks` / `records-best-tricks`: bmc_play_hands on four lane masks with
+    one int8 trump, the 72-byte result decoded field by field; bmc_best_tricks on a record buffer with scalar trump /
+    declarer.  Checked against the reference's own run (tests/golden/playdeal_ref.json)."""
+    import json
+    import os
+    L, h = ctx
+    rows = [r for r in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "playdeal_ref.json")))["rows"] if "tricks" in r]
+    for r in rows[:6] + rows[-6:]:
+        hands = (C.c_uint64 * 4)(*[sum(sum(1 << x for x in s) << (16 * i) for i, s in enumerate(hd)) for hd in r["hands"]])
+        tr = C.c_int8(-1 if r["trump"] is None else r["trump"])
+        out = (C.c_uint8 * 72)()
+        assert L.bmc_play_hands(h, hands, 1, C.byref(tr), 0, 0, out) == 0
+        status, n = out[0], out[1]
+        assert status == 0 and n == len(r["tricks"]) and [out[2], out[3]] == r["score"]
+        cards = [[None if out[4 + 4 * t + i] == 255 else [out[4 + 4 * t + i] >> 4, out[4 + 4 * t + i] & 15] for i in range(4)] for t in range(n)]
+        assert cards == r["tricks"] and [out[56 + t] for t in range(n)] == r["winner_nos"]
+    full = [r for r in rows if sum(len(s) for s in r["hands"][0]) == 13][:4]
+    rec = (C.c_uint64 * (2 * len(full)))()
+    for i, r in enumerate(full):                                   # declarer = seat 0: N E S W = declarer, left, dummy, right
+        masks = [sum(sum(1 << x for x in s) << (16 * k) for k, s in enumerate(hd)) for hd in r["hands"]]
+        rec[2 * i] = masks[1] | masks[3]
+        rec[2 * i + 1] = masks[2] | masks[3]
+    tr, de = C.c_int8(-1), C.c_uint8(0)
+    tricks = (C.c_uint8 * len(full))()
+    nt = [r for r in full]
+    assert L.bmc_best_tricks(h, rec, len(full), C.byref(tr), C.byref(de), 0, 0, tricks) == 0
+    for i, r in enumerate(nt):
+        if r["trump"] is None:
+            assert tricks[i] == r["score"][1]
