@@ -162,3 +162,26 @@ def test_device_code_on_host_matches_the_oracle_on_random_deals(host_binary):
     for (hs, t), g in zip(jobs, res):
         o = P.play_deal(t, *[P.Hand(h, id=i) for i, h in enumerate(hs)])
         assert g["status"] == 0 and g["tricks"] == o.tricks and g["score"] == o.score and g["winner_nos"] == o.winner_nos
+
+
+def test_device_code_under_address_and_ub_sanitizers(tmp_path):
+    """compute-sanitizer is closed on the GPU pool; the estimator's memory discipline (arena offsets, the shared
+    temporaries' stack, the fixed-size route / guard / target tables and their overflow paths) is the same code on the
+    host, so it is run under ASan + UBSan here: normal arenas, and arenas small enough that many deals overflow (status 1
+    must be reported, nothing may be touched out of bounds)."""
+    exe = str(tmp_path / "pd_asan")
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe,
+                    os.path.join(HERE, "playdeal_host_selftest.cpp")], check=True)
+    rng = random.Random(23)
+    jobs = [(_rand_deal(rng, 13), rng.choice([None, 0, 1, 2, 3])) for _ in range(40)] + [(_rand_deal(rng, k), None) for k in (1, 2, 5, 9)]
+    text = "".join("%d %s\n" % (-1 if t is None else t, " ".join(str(sum(1 << r for r in s)) for h in hs for s in h)) for hs, t in jobs)
+    full = subprocess.run([exe, str(8 << 20)], input=text, capture_output=True, text=True)
+    assert full.returncode == 0, full.stderr[-2000:]
+    assert all(line.split()[0] == "0" for line in full.stdout.strip().split("\n"))
+    small = subprocess.run([exe, str(48 << 10)], input=text, capture_output=True, text=True)
+    assert small.returncode == 0, small.stderr[-2000:]
+    status = [line.split()[0] for line in small.stdout.strip().split("\n")]
+    assert set(status) <= {"0", "1"} and status.count("1") >= 5
+    for a, b in zip(full.stdout.strip().split("\n"), small.stdout.strip().split("\n")):
+        if b.split()[0] == "0":
+            assert a.split()[:4] == b.split()[:4] and a.split()[6:] == b.split()[6:]      # same outcome when the arena suffices
