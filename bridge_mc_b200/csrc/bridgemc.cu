@@ -31,7 +31,7 @@
 #include "reforder.cuh"
 #include "hist.cuh"
 #include "distgen.cuh"
-#include "playdeal.cuh"
+#include "playdeal_host.h"
 #include "rules.hpp"
 #include "jit.hpp"
 #include "embedded_src.inc"
@@ -2467,92 +2467,7 @@ int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc
 // ---------------------------------------------------------------------------
 // play-deal (bridge.cl:2961): one thread per deal (playdeal.cuh)
 // ---------------------------------------------------------------------------
-constexpr int PD_THREADS = 128;
-__device__ __forceinline__ void play_one_deal(const uint4 *records, const unsigned long long *hands4, unsigned long long i, const int8_t *trump,
-                                              const uint8_t *declarer, int per_deal, uint8_t *arena, uint32_t arena_bytes, pd::Scratch &S,
-                                              bmc_play_result *out)
-{
-    const int tr = trump[per_deal ? i : 0];
-    pd::Hand h[4];
-    if (records) {
-        const uint4 r = records[i];                              // lo plane (x, y), hi plane (z, w)
-        const int dec = declarer[per_deal ? i : 0] & 3;
-        for (int k = 0; k < 4; ++k) {
-            const int seat = (dec + k) & 3;
-            const uint32_t xl = (seat & 1) ? 0u : 0xFFFFFFFFu, xh = (seat & 2) ? 0u : 0xFFFFFFFFu;
-            const uint32_t m0 = (r.x ^ xl) & (r.z ^ xh) & 0x1FFF1FFFu, m1 = (r.y ^ xl) & (r.w ^ xh) & 0x1FFF1FFFu;
-            h[k].s[0] = (uint16_t)(m0 & 0xFFFFu); h[k].s[1] = (uint16_t)(m0 >> 16);
-            h[k].s[2] = (uint16_t)(m1 & 0xFFFFu); h[k].s[3] = (uint16_t)(m1 >> 16);
-            h[k].id = (uint8_t)k;
-        }
-    } else {
-        for (int k = 0; k < 4; ++k) {                            // four lane masks: declarer, left, dummy, right
-            const unsigned long long m = hands4[4 * i + k];
-            for (int s = 0; s < 4; ++s) h[k].s[s] = (uint16_t)((m >> (16 * s)) & 0x1FFFu);
-            h[k].id = (uint8_t)k;
-        }
-    }
-    pd::Result &res = S.res;
-    pd::play_deal(arena, arena_bytes, tr < 0 || tr > 3 ? -1 : tr, h, S, res);
-    if ((threadIdx.x & 31u) != 0u) return;                   // the lanes hold identical results
-    bmc_play_result o;
-    o.status = (uint8_t)res.status; o.n_tricks = res.n; o.score[0] = res.score[0]; o.score[1] = res.score[1];
-    for (int t = 0; t < 13; ++t) {
-        for (int c = 0; c < 4; ++c) o.cards[t][c] = t < res.n ? res.tricks[t][c] : 0xFF;
-        o.winner[t] = t < res.n ? res.wno[t] : 0xFF;
-    }
-    o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
-    out[i] = o;
-}
-
-// One WARP per deal.  The estimator is a long scalar computation whose working set (search stacks, route lists) is a few
-// tens of KB: with one deal per thread a warp drags 32 such working sets through the caches and serialises 32 divergent
-// control flows.  Here the 32 lanes of a warp run the SAME deal in lock step on the same data -- the search stacks sit in
-// shared memory, one copy per warp, the arena in global memory, one per warp -- so there is no divergence, every load is a
-// broadcast and every store a single transaction.  Deals are handed out by an atomic counter (their cost varies 100-fold).
-constexpr int PD_WARPS = PD_THREADS / 32;
-__global__ void __launch_bounds__(PD_THREADS) play_deal_kernel(const uint4 *records, const unsigned long long *hands4, unsigned long long n,
-                                                                 const int8_t *trump, const uint8_t *declarer, int per_deal, uint8_t *arenas,
-                                                                 uint32_t arena_bytes, bmc_play_result *out, unsigned long long *next)
-{
-    extern __shared__ __align__(16) unsigned char pd_smem[];
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    pd::Scratch &S = reinterpret_cast<pd::Scratch *>(pd_smem)[warp];
-    uint8_t *arena = arenas + ((unsigned long long)blockIdx.x * PD_WARPS + warp) * (unsigned long long)arena_bytes;
-    for (;;) {
-        unsigned long long i = 0;
-        if (lane == 0) i = atomicAdd(next, 1ull);
-        i = __shfl_sync(0xFFFFFFFFu, i, 0);
-        if (i >= n) break;
-        play_one_deal(records, hands4, i, trump, declarer, per_deal, arena, arena_bytes, S, out);
-        __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(PD_THREADS) play_deal_retry_kernel(const uint4 *records, const unsigned long long *hands4, const unsigned int *idx,
-                                                                       unsigned int n_idx, const int8_t *trump, const uint8_t *declarer, int per_deal,
-                                                                       uint8_t *arenas, uint32_t arena_bytes, bmc_play_result *out, unsigned long long *next)
-{
-    extern __shared__ __align__(16) unsigned char pd_smem[];
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    pd::Scratch &S = reinterpret_cast<pd::Scratch *>(pd_smem)[warp];
-    uint8_t *arena = arenas + ((unsigned long long)blockIdx.x * PD_WARPS + warp) * (unsigned long long)arena_bytes;
-    for (;;) {
-        unsigned long long k = 0;
-        if (lane == 0) k = atomicAdd(next, 1ull);
-        k = __shfl_sync(0xFFFFFFFFu, k, 0);
-        if (k >= n_idx) break;
-        play_one_deal(records, hands4, idx[k], trump, declarer, per_deal, arena, arena_bytes, S, out);
-        __syncwarp();
-    }
-}
-
-// deals whose route lists outgrew their arena (status 1): their indices, compacted, for the retry pass
-__global__ void play_deal_failed_kernel(const bmc_play_result *out, unsigned long long n, unsigned int *idx, unsigned int *count)
-{
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && out[i].status == 1) idx[atomicAdd(count, 1u)] = (unsigned int)i;
-}
+// the kernels live in their own translation unit (playdeal_kernels.cu): they are compiled for code size
 static int pd_blocks_per_sm()
 {
     const char *e = getenv("BMC_PD_BLOCKS");
@@ -2569,11 +2484,9 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
     const uint64_t arena = (uint64_t)(adaptive ? 256u : arena_kb) * 1024u;
     if (arena > (1ull << 31)) return fail(BMC_E_INVALID, "bmc_play_deal: arena_kb too large");
     if (n > 0xFFFFFFFFull) return fail(BMC_E_INVALID, "bmc_play_deal: more than 2^32 - 1 deals in one call");
-    const size_t smem = PD_WARPS * sizeof(pd::Scratch);
-    CUDA_TRY(cudaFuncSetAttribute(play_deal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(play_deal_retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int PD_WARPS = bmc_pd::WARPS;
     int per_sm = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, play_deal_kernel, PD_THREADS, smem));
+    CUDA_TRY(bmc_pd::configure(&per_sm));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > pd_blocks_per_sm()) per_sm = pd_blocks_per_sm();
     uint64_t blocks = (n + PD_WARPS - 1) / PD_WARPS;
@@ -2594,9 +2507,8 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
         if (blocks <= 1) return fail(BMC_E_NOMEM, "bmc_play_deal: cannot allocate the per-deal arenas");
         blocks = (blocks + 1) / 2;
     }
-    play_deal_kernel<<<(unsigned)blocks, PD_THREADS, smem, ctx->stream>>>(
-        reinterpret_cast<const uint4 *>(d_records), reinterpret_cast<const unsigned long long *>(d_hands4), n, d_trump, d_declarer,
-        per_deal, ctx->d_arena, (uint32_t)arena, reinterpret_cast<bmc_play_result *>(d_out), d_next);
+    bmc_pd::launch((unsigned)blocks, ctx->stream, d_records, d_hands4, nullptr, n, d_trump, d_declarer, per_deal, ctx->d_arena,
+                   (uint32_t)arena, d_out, d_next);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && adaptive) {
@@ -2605,7 +2517,7 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
         if (e == cudaSuccess) e = cudaMalloc(&d_cnt, sizeof(unsigned int));
         if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), ctx->stream);
         if (e == cudaSuccess) {
-            play_deal_failed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const bmc_play_result *>(d_out), n, d_idx, d_cnt);
+            bmc_pd::launch_failed(ctx->stream, d_out, n, d_idx, d_cnt);
             ctx->launches++;
             e = cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream);
         }
@@ -2623,9 +2535,8 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
             const uint64_t want = ((uint64_t)h_cnt + PD_WARPS - 1) / PD_WARPS;
             if (b2 > want) b2 = want;
             if (b2 > max_blocks) b2 = max_blocks;
-            play_deal_retry_kernel<<<(unsigned)b2, PD_THREADS, smem, ctx->stream>>>(
-                reinterpret_cast<const uint4 *>(d_records), reinterpret_cast<const unsigned long long *>(d_hands4), d_idx, h_cnt, d_trump,
-                d_declarer, per_deal, ctx->d_arena, (uint32_t)big, reinterpret_cast<bmc_play_result *>(d_out), d_next + 1);
+            bmc_pd::launch((unsigned)b2, ctx->stream, d_records, d_hands4, d_idx, h_cnt, d_trump, d_declarer, per_deal, ctx->d_arena,
+                           (uint32_t)big, d_out, d_next + 1);
             ctx->launches++;
             e = cudaGetLastError();
         }

@@ -25,9 +25,11 @@
 #if defined(__CUDACC__)
 #define PD_HD __host__ __device__ __forceinline__
 #define PD_HDN __host__ __device__ __noinline__
+#define PD_ROLLED _Pragma("unroll 1")      /* the estimator is bound by instruction fetch: loops stay rolled */
 #else
 #define PD_HD inline
 #define PD_HDN
+#define PD_ROLLED
 #endif
 
 // On the device the 32 lanes of a warp run one deal in lock step (play_deal_kernel, bridgemc.cu): the scalar logic is
@@ -191,6 +193,7 @@ PD_HD void hand_take(const Hand &h, int suit, int rank, Card &card, Hand &rest)
 PD_HDN int weak_suit(const Hand &h, const Trick &t)
 {
     int acc = -1;
+    PD_ROLLED
     for (int suit = 0; suit < 4; ++suit) {
         const uint32_t cards = h.s[suit];
         if (!cards) continue;
@@ -203,6 +206,7 @@ PD_HDN int weak_suit(const Hand &h, const Trick &t)
         if (!hon) { acc = suit; continue; }
         if (!acchon) continue;
         int na = 0, nb = 0;
+        PD_ROLLED
         for (int k = 0; k < t.n; ++k) {
             na += popc(above(t.rem[k].s[suit], highbit(cards)));
             nb += popc(above(t.rem[k].s[acc], highbit(accards)));
@@ -348,6 +352,7 @@ PD_HDN void copy_words(void *dst, const void *src, int words)
 {
     uint32_t *d = static_cast<uint32_t *>(dst);
     const uint32_t *s = static_cast<const uint32_t *>(src);
+    PD_ROLLED
     for (int i = 0; i < words; ++i) d[i] = s[i];
 }
 PD_HD void outcome_copy(Outcome &dst, const Outcome &src) { if (&dst != &src) copy_words(&dst, &src, (int)(sizeof(Outcome) / 4)); }
@@ -355,6 +360,7 @@ PD_HD void outcome_copy(Outcome &dst, const Outcome &src) { if (&dst != &src) co
 PD_HDN void outcome_empty(Outcome &o, const Hand *hands)
 {
     o.n = 0; o.roll = 0; o.score[0] = o.score[1] = 0; o.valid = 1;
+    PD_ROLLED
     for (int i = 0; i < 4; ++i) o.rem[i] = hands[i];
 }
 PD_HD void outcome_nil(Outcome &o) { o.valid = 0; o.n = 0; o.roll = 0; o.score[0] = o.score[1] = 0; }
@@ -365,15 +371,19 @@ PD_HDN void outcome_of_trick(Ctx &cx, Outcome &o, const Trick &t)
     if (t.winner < 0 || t.n != 4) { fail(cx, PD_E_LISP); outcome_nil(o); return; }
     o.valid = 1; o.n = 1; o.roll = (uint8_t)t.winner;
     o.score[0] = (t.winner & 1) ? 0 : 1; o.score[1] = (t.winner & 1) ? 1 : 0;
+    PD_ROLLED
     for (int i = 0; i < 4; ++i) o.tricks[0][i] = t.cards[i];
     o.wno[0] = (uint8_t)t.winner;
+    PD_ROLLED
     for (int i = 0; i < 4; ++i) o.rem[i] = t.rem[(i + t.winner) & 3];       // (roll (- winner) remaining)
 }
 // add-outcome (2212-2223): self += other, roll := other's roll.  star = add-outcome* (2225-2235): roll adds up.
 PD_HDN void outcome_add(Ctx &cx, Outcome &self, const Outcome &other, bool star)
 {
     if (self.n + other.n > 13) { fail(cx, PD_E_CAP); return; }
+    PD_ROLLED
     for (int k = 0; k < other.n; ++k) {
+        PD_ROLLED
         for (int i = 0; i < 4; ++i) self.tricks[self.n + k][i] = other.tricks[k][i];
         self.wno[self.n + k] = other.wno[k];
     }
@@ -382,6 +392,7 @@ PD_HDN void outcome_add(Ctx &cx, Outcome &self, const Outcome &other, bool star)
     self.score[1] = (uint8_t)(self.score[1] + other.score[flip ? 0 : 1]);
     self.n = (uint8_t)(self.n + other.n);
     self.roll = star ? (uint8_t)((self.roll + other.roll) & 3) : other.roll;
+    PD_ROLLED
     for (int i = 0; i < 4; ++i) self.rem[i] = other.rem[i];
 }
 PD_HD bool outcome_won(const Outcome &o) { return o.n > 0 && (o.wno[0] & 1) == 0; }
@@ -425,6 +436,7 @@ PD_HDN void immediate_opts(const Ctx &cx, SearchFrame &f, const int8_t *suits, i
 {
     f.nopt = 0;
     const Hand &a = f.hands[0], &b = f.hands[1], &d = f.hands[3];
+    PD_ROLLED
     for (int k = 0; k < nsuits; ++k) {
         const int suit = suits[k];
         const uint32_t cards = a.s[suit];
@@ -432,12 +444,14 @@ PD_HDN void immediate_opts(const Ctx &cx, SearchFrame &f, const int8_t *suits, i
         if (suit == cx.trump) {
             if (cards && (b.s[suit] || d.s[suit])) n = popc(cards) > 1 ? 2 : 1;
         } else if (cards) n = popc(cards) < 2 ? 1 : 2;
+        PD_ROLLED
         for (int j = 0; j < n && f.nopt < 12; ++j) { f.opts[f.nopt].suit = (int8_t)suit; f.opts[f.nopt].top = (uint8_t)j; f.opts[f.nopt].rolled = 0; ++f.nopt; }
     }
 }
 PD_HD void fourway_opts(SearchFrame &f, int suit)
 {
     f.nopt = 4;
+    PD_ROLLED
     for (int j = 0; j < 4; ++j) { f.opts[j].suit = (int8_t)suit; f.opts[j].top = (uint8_t)(j < 2); f.opts[j].rolled = (uint8_t)(j & 1); }
 }
 
@@ -456,6 +470,7 @@ PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int 
     Outcome &cand = *tmp<Outcome>(cx);
     int sp = 0;
     auto open = [&](SearchFrame &f, const Hand *h) {
+        PD_ROLLED
         for (int i = 0; i < 4; ++i) f.hands[i] = h[i];
         f.i = 0;
         if (kind == IMMEDIATE) { immediate_opts(cx, f, suits, nsuits); outcome_empty(f.best, h); f.have_best = 1; }
@@ -513,11 +528,13 @@ PD_HDN void suit_value(Ctx &cx, SuitValue &sv, int suit, int trump, const Hand *
     search(cx, PLAY_THROUGH, suit, nullptr, 0, deal, stack, o);
     cx.trump = saved;
     sv.suit = (int8_t)suit; sv.trump = (int8_t)trump; sv.ngroups = 0;
+    PD_ROLLED
     for (int i = 0; i < 15; ++i) sv.glen[i] = 0;
     // the reference folds the (leader's side won?, winning card) pairs from the last trick backwards (2289-2296);
     // forwards that is: a lost trick opens the next group, every trick's winning card joins the current group
     int g = 0;
     bool any = false;
+    PD_ROLLED
     for (int k = 0; k < o.n && !cx.status; ++k) {
         const bool first = (o.wno[k] & 1) == 0;
         if (!first) ++g;
@@ -527,6 +544,7 @@ PD_HDN void suit_value(Ctx &cx, SuitValue &sv, int suit, int trump, const Hand *
     }
     sv.ngroups = any ? (uint8_t)(g + 1) : 0;
     sv.ours = sv.theirs = 0;
+    PD_ROLLED
     for (int i = 0; i < sv.ngroups; ++i) { if (i & 1) sv.theirs += sv.glen[i]; else sv.ours += sv.glen[i]; }
 }
 
@@ -549,6 +567,7 @@ PD_HDN void find_opp_weakness(Ctx &cx, RootStrategy &rs, const Hand *deal, Searc
     SuitValue *vals = tmp<SuitValue>(cx, 4);
     SuitValue &nt = *tmp<SuitValue>(cx), &tr = *tmp<SuitValue>(cx);
     int nv = 0;
+    PD_ROLLED
     for (int suit = 0; suit < 4 && !cx.status; ++suit) {
         suit_value(cx, nt, suit, -1, deal, stack);
         if (trump >= 0) {
@@ -558,25 +577,35 @@ PD_HDN void find_opp_weakness(Ctx &cx, RootStrategy &rs, const Hand *deal, Searc
         if (nt.ours > 0) copy_words(&vals[nv++], &nt, (int)(sizeof(SuitValue) / 4));
     }
     // (sort ... (> (ours a) (ours b))): stable
-    for (int i = 1; i < nv; ++i)
+    PD_ROLLED
+    for (int i = 1; i < nv; ++i) {
+        PD_ROLLED
         for (int j = i; j > 0 && vals[j].ours > vals[j - 1].ours; --j) { copy_words(&nt, &vals[j], (int)(sizeof(SuitValue) / 4)); copy_words(&vals[j], &vals[j - 1], (int)(sizeof(SuitValue) / 4)); copy_words(&vals[j - 1], &nt, (int)(sizeof(SuitValue) / 4)); }
+    }
     int *order = tmp<int>(cx, 12), no = 0;
     if (trump >= 0) {
+        PD_ROLLED
         for (int i = 0; i < nv; ++i) if (vals[i].trump >= 0) order[no++] = i;
+        PD_ROLLED
         for (int i = 0; i < nv; ++i) if (vals[i].suit == trump) order[no++] = i;
+        PD_ROLLED
         for (int i = 0; i < nv; ++i) if (!(vals[i].suit == trump || vals[i].trump >= 0)) order[no++] = i;
     } else for (int i = 0; i < nv; ++i) order[no++] = i;
     rs.nsoon = rs.nest = 0;
+    PD_ROLLED
     for (int k = 0; k < no; ++k) {
         const SuitValue &sv = vals[order[k]];
         Target &t = *tmp<Target>(cx);
         t.suit = sv.suit; t.diff = (int8_t)(sv.ours - sv.theirs); t.nours = t.ntheirs = t.head = 0;
-        for (int g = 0; g < sv.ngroups; ++g)
+        PD_ROLLED
+        for (int g = 0; g < sv.ngroups; ++g) {
+            PD_ROLLED
             for (int j = 0; j < sv.glen[g]; ++j) {
                 const Card c = sv.gcards[g][j];
                 if (c == NOCARD || csuit(c) != sv.suit) continue;
                 if (g & 1) t.theirs[t.ntheirs++] = (uint8_t)crank(c); else ++t.nours;
             }
+        }
         if (t.diff == 0 && t.nours == 0) { if (rs.nsoon < MAXT) rs.soonest[rs.nsoon++] = t.suit; else fail(cx, PD_E_CAP); }
         if (t.diff > 0) { if (rs.nest < MAXT) rs.establish[rs.nest++] = t; else fail(cx, PD_E_CAP); }
     }
@@ -614,6 +643,7 @@ PD_HD void rl_push(Ctx &cx, RouteList &l, uint32_t r) { if (l.n < MAXR) l.r[l.n+
 PD_HDN void rl_push_front(Ctx &cx, RouteList &l, uint32_t r)
 {
     if (l.n >= MAXR) { fail(cx, PD_E_CAP); return; }
+    PD_ROLLED
     for (int i = l.n; i > 0; --i) l.r[i] = l.r[i - 1];
     l.r[0] = r; ++l.n;
 }
@@ -627,7 +657,9 @@ PD_HDN uint32_t add_at(Ctx &cx, uint32_t route, uint32_t tricks2, uint32_t len2)
     if (cx.status) return route;
     uint32_t *dst = at<uint32_t>(cx, off);
     const uint32_t *a = at<uint32_t>(cx, r.tricks), *b = at<uint32_t>(cx, tricks2);
+    PD_ROLLED
     for (uint32_t i = PD_LANE; i < r.len; i += PD_LANES) dst[i] = a[i];
+    PD_ROLLED
     for (uint32_t i = PD_LANE; i < len2; i += PD_LANES) dst[r.len + i] = b[i];
     PD_SYNC();
     return new_route(cx, r.frm, r.to, r.tvoid, off, len);
@@ -636,6 +668,7 @@ PD_HDN uint32_t add_at(Ctx &cx, uint32_t route, uint32_t tricks2, uint32_t len2)
 PD_HDN void insert_route(Ctx &cx, RouteList &routes, uint32_t route)
 {
     const Route r = *at<Route>(cx, route);
+    PD_ROLLED
     for (int p = 0; p < routes.n; ++p) {
         const Route *q = at<Route>(cx, routes.r[p]);
         if (q->frm == r.frm && q->to == r.to) { routes.r[p] = add_at(cx, routes.r[p], r.tricks, r.len); return; }
@@ -653,6 +686,7 @@ PD_HDN void reproduce(Ctx &cx, uint32_t route, const Hand *hands, Outcome &ans)
         const uint32_t base = at<uint32_t>(cx, r->tricks)[0];
         r->tricks += 4; r->len -= 1;
         Card ref[4];
+        PD_ROLLED
         for (int i = 0; i < 4; ++i) ref[i] = tcard(base, i);
         if (ref[0] == NOCARD) { fail(cx, PD_E_LISP); outcome_nil(ans); return; }
         if (!((hands[0].s[csuit(ref[0])] >> crank(ref[0])) & 1u)) {          // the partner led it: (roll 2 base)
@@ -693,18 +727,24 @@ PD_HDN void mk_route(Ctx &cx, uint32_t com_off, const Hand *hands, Outcome &acc)
     RouteList *pr = tmp<RouteList>(cx, 2);
     Outcome &ans = *tmp<Outcome>(cx);
     Hand *hs = tmp<Hand>(cx, 4);
+    PD_ROLLED
     for (int w = 0; w < 2; ++w) {
         const int player = w * 2;
         pr[w].n = 0;
         // the reference's sort predicate (2458-2462) is not an ordering; under SBCL's merge sort it yields: routes with
         // from = to in reverse input order, then other routes with a `from` in reverse input order, then the rest
+        PD_ROLLED
         for (int i = com.nact - 1; i >= 0; --i) { const Route *r = at<Route>(cx, com.act[i]); if (r->frm >= 0 && r->frm == player && r->frm == r->to) rl_push(cx, pr[w], com.act[i]); }
+        PD_ROLLED
         for (int i = com.nact - 1; i >= 0; --i) { const Route *r = at<Route>(cx, com.act[i]); if (r->frm >= 0 && r->frm == player && r->frm != r->to) rl_push(cx, pr[w], com.act[i]); }
+        PD_ROLLED
         for (int i = 0; i < com.nact; ++i) { const Route *r = at<Route>(cx, com.act[i]); if (r->frm < 0) rl_push(cx, pr[w], com.act[i]); }
     }
     outcome_empty(acc, hands);
     int cur = 0, head[2] = {0, 0};
+    PD_ROLLED
     while (head[cur] < pr[cur].n && !cx.status) {
+        PD_ROLLED
         for (int i = 0; i < 4; ++i) hs[i] = acc.rem[i];
         reproduce(cx, pr[cur].r[head[cur]], hs, ans);
         if (!ans.valid) { ++head[cur]; continue; }
@@ -724,6 +764,7 @@ PD_HDN uint32_t tricks_from(Ctx &cx, const uint32_t *src, int n)
     const uint32_t off = arena_alloc(cx, (uint32_t)n * 4u);
     if (cx.status) return 0;
     uint32_t *dst = at<uint32_t>(cx, off);
+    PD_ROLLED
     for (int i = 0; i < n; ++i) dst[i] = src[i];
     return off;
 }
@@ -741,11 +782,14 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
     uint32_t *tmpt = tmp<uint32_t>(cx, 60);
     RouteList &routes = *tmp<RouteList>(cx);
     int ng = 0;
+    PD_ROLLED
     for (int i = 0; i < NSEC; ++i) nsec[i] = 0;
+    PD_ROLLED
     for (int k = 0; k < nsuits && !cx.status; ++k) {
         const int suit = suits[k];
         search(cx, SUIT_TOPS, suit, nullptr, 0, h, stack, tops);
         if (cx.status) break;
+        PD_ROLLED
         for (int t = 0; t < tops.n; ++t) {
             const Card *c = tops.tricks[t];
             const int w = tops.wno[t];
@@ -781,6 +825,7 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
     // routes in the order of 2542-2549, each section reversed
     routes.n = 0;
     auto section = [&](int s, int frm, int to) {
+        PD_ROLLED
         for (int i = 0; i < nsec[s]; ++i) tmpt[i] = sec[s][nsec[s] - 1 - i];
         const uint32_t off = tricks_from(cx, tmpt, nsec[s]);
         rl_push(cx, routes, new_route(cx, frm, to, -1, off, (uint32_t)nsec[s]));
@@ -792,8 +837,10 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
     // void-vertices (2509-2518): the tricks are split by the suit LED (0, 1, 2, other) and the k-th split is paired with
     // the k-th element of `suits` -- the reference's pairing, kept as it is
     auto vertices = [&](int s, int frm, int to) {
+        PD_ROLLED
         for (int k = 0; k < nsuits && k < 4; ++k) {
             int n = 0;
+            PD_ROLLED
             for (int i = 0; i < nsec[s]; ++i) {
                 const uint32_t t = sec[s][i];                    // input order; the split reverses it, like the section
                 const Card c0 = tcard(t, 0);
@@ -817,6 +864,7 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
     if (cx.status) return 0;
     Com &com = *at<Com>(cx, coff);
     com.zero_id = h[0].id; com.nact = com.npend = 0;
+    PD_ROLLED
     for (int i = routes.n - 1; i >= 0; --i) {                    // divlist reverses
         const Route *r = at<Route>(cx, routes.r[i]);
         if (r->len == 0) continue;
@@ -825,6 +873,7 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
     }
     // the guards section is reversed too
     com.nguard = (uint8_t)ng;
+    PD_ROLLED
     for (int i = 0; i < ng; ++i) { com.gsuit[i] = gs[ng - 1 - i]; com.granks[i] = gr[ng - 1 - i]; }
     return coff;
 }
@@ -839,29 +888,35 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
     uint8_t *is_rem = tmp<uint8_t>(cx, 56), *is_brk = tmp<uint8_t>(cx, 56);
     uint32_t *brk_tricks = tmp<uint32_t>(cx, 56);
     int ncards = ncards_in;
+    PD_ROLLED
     for (int i = 0; i < ncards; ++i) cards[i] = cards_in[i];
     bool remaining_nil = ncards == 0;
     routes.n = 0;
+    PD_ROLLED
     for (int a = 0; a < com.nact && !cx.status; ++a) {
         const uint32_t roff = com.act[a];
         if (remaining_nil) { rl_push_front(cx, routes, roff); ncards = 0; continue; }
         const Route r = *at<Route>(cx, roff);
         // rem-break-div (2397-2411): first index of each card as a first card / as a third card of the route's tricks
+        PD_ROLLED
         for (int i = 0; i < 53; ++i) pos_first[i] = pos_third[i] = -1;
         if (r.len > 32767) { fail(cx, PD_E_CAP); return; }
         {
             // only the cards just played matter: a 53-bit request mask over the card indices
             unsigned long long want = 0;
+            PD_ROLLED
             for (int i = 0; i < ncards; ++i) want |= 1ull << cidx(cards[i]);
             const uint32_t *tr = at<uint32_t>(cx, r.tricks);
 #if defined(__CUDA_ARCH__)
             // 32 tricks per step, one per lane; the (rare) tricks that hold a wanted card are then visited in order by
             // every lane, so all lanes end with the same positions
+            PD_ROLLED
             for (uint32_t base = 0; base < r.len; base += 32u) {
                 const uint32_t i = base + (uint32_t)PD_LANE;
                 const uint32_t t = i < r.len ? tr[i] : 0u;
                 const bool hit = i < r.len && (((want >> cidx(tcard(t, 0))) | (want >> cidx(tcard(t, 2)))) & 1ull);
                 unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+                PD_ROLLED
                 while (bal) {
                     const int b = __ffs((int)bal) - 1;
                     bal &= bal - 1u;
@@ -872,6 +927,7 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
                 }
             }
 #else
+            PD_ROLLED
             for (uint32_t i = 0; i < r.len; ++i) {
                 const uint32_t t = tr[i];
                 const int c0 = cidx(tcard(t, 0)), c2 = cidx(tcard(t, 2));
@@ -883,6 +939,7 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         const bool no_from = r.frm < 0;
         const bool first_only = no_from || r.frm == r.to;
         // items (card, id) in the three sections, each in REVERSE card order
+        PD_ROLLED
         for (int i = 0; i < ncards; ++i) {
             const int ci = cidx(cards[i]);
             const int bid = no_from ? pos_third[ci] : -1;
@@ -899,16 +956,19 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         }
         // ids to delete; break ids (those of the break section not also in the remove section), in section order
         bool any_ids = false;
+        PD_ROLLED
         for (int i = 0; i < ncards; ++i) any_ids = any_ids || is_rem[i] || is_brk[i];
         uint32_t updated = roff;
         uint32_t updated_len = r.len;
         if (any_ids) {
             // del-at (2413-2419): the ids, sorted, then one pass over the tricks
             int nid = 0;
+            PD_ROLLED
             for (int i = 0; i < ncards; ++i) {
                 if (!is_rem[i] && !is_brk[i]) continue;
                 const int id = is_rem[i] ? rem_id[i] : brk_id[i];
                 int j = nid++;
+                PD_ROLLED
                 while (j > 0 && ids[j - 1] > id) { ids[j] = ids[j - 1]; --j; }
                 ids[j] = id;
             }
@@ -920,10 +980,13 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
 #if defined(__CUDA_ARCH__)
             // order-preserving compaction, 32 tricks per step: the ids are sorted, `lo` = how many lie below this step
             int lo = 0;
+            PD_ROLLED
             for (uint32_t base = 0; base < r.len; base += 32u) {
                 const uint32_t t = base + (uint32_t)PD_LANE;
+                PD_ROLLED
                 while (lo < nid && (uint32_t)ids[lo] < base) ++lo;
                 bool keep = t < r.len;
+                PD_ROLLED
                 for (int k = lo; keep && k < nid && (uint32_t)ids[k] < base + 32u; ++k) if ((uint32_t)ids[k] == t) keep = false;
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
                 if (keep) dst[n + __popc(bal & ((1u << PD_LANE) - 1u))] = tr[t];
@@ -932,7 +995,9 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
             PD_SYNC();
 #else
             int k = 0;
+            PD_ROLLED
             for (uint32_t t = 0; t < r.len; ++t) {
+                PD_ROLLED
                 while (k < nid && (uint32_t)ids[k] < t) ++k;
                 if (k < nid && (uint32_t)ids[k] == t) continue;
                 dst[n++] = tr[t];
@@ -942,9 +1007,11 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
             updated_len = n;
         }
         int nb = 0;
+        PD_ROLLED
         for (int i = ncards - 1; i >= 0; --i) {                       // section order = reverse card order
             if (!is_brk[i]) continue;
             bool in_remove = false;
+            PD_ROLLED
             for (int j = 0; j < ncards && !in_remove; ++j) in_remove = is_rem[j] && rem_id[j] == brk_id[i];
             if (!in_remove) brk_tricks[nb++] = at<uint32_t>(cx, r.tricks)[brk_id[i]];
         }
@@ -955,12 +1022,15 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         if (updated_len) rl_push_front(cx, routes, updated);
         // what is left of the cards: the absent section, reversed
         int nr = 0;
+        PD_ROLLED
         for (int i = ncards - 1; i >= 0; --i) if (!is_rem[i] && !is_brk[i]) rest[nr++] = cards[i];
+        PD_ROLLED
         for (int i = 0; i < nr; ++i) cards[i] = rest[i];
         ncards = nr;
         if (ncards == 0) remaining_nil = true;
     }
     nskipped = ncards;
+    PD_ROLLED
     for (int i = 0; i < ncards; ++i) skipped[i] = cards[i];
 }
 
@@ -978,6 +1048,7 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
     {
         const Com &com = *at<Com>(cx, com_off);
         int offset = -1;
+        PD_ROLLED
         for (int i = 0; i < 4; ++i) if (out.rem[i].id == com.zero_id) { offset = i; break; }
         if (offset < 0) { fail(cx, PD_E_LISP); return com_off; }
         if (offset > 0) {
@@ -986,13 +1057,19 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
             Com &n = *at<Com>(cx, self_off);
             const Com &c = *at<Com>(cx, com_off);
             n.zero_id = out.rem[0].id; n.nact = c.nact; n.npend = c.npend; n.nguard = 0;
+            PD_ROLLED
             for (int i = 0; i < c.nact; ++i) { const Route r = *at<Route>(cx, c.act[i]); n.act[i] = new_route(cx, r.frm >= 0 ? (r.frm + offset) & 3 : -1, (r.to + offset) & 3, r.tvoid, r.tricks, r.len); }
+            PD_ROLLED
             for (int i = 0; i < c.npend; ++i) { const Route r = *at<Route>(cx, c.pend[i]); n.pend[i] = new_route(cx, r.frm >= 0 ? (r.frm + offset) & 3 : -1, (r.to + offset) & 3, r.tvoid, r.tricks, r.len); }
         }
     }
     if (cx.status) return com_off;
     int nraw = 0;
-    for (int t = 0; t < out.n; ++t) for (int i = 0; i < 4; ++i) raw[nraw++] = out.tricks[t][i];
+    PD_ROLLED
+    for (int t = 0; t < out.n; ++t) {
+        PD_ROLLED
+        for (int i = 0; i < 4; ++i) raw[nraw++] = out.tricks[t][i];
+    }
     int nskipped = 0;
     first_pass(cx, *at<Com>(cx, self_off), raw, nraw, base, skipped, nskipped);
     if (cx.status) return com_off;
@@ -1000,6 +1077,7 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
     new_active.n = new_pending.n = 0;
     {
         const Com &self = *at<Com>(cx, self_off);
+        PD_ROLLED
         for (int i = self.npend - 1; i >= 0; --i) {
             const Route *r = at<Route>(cx, self.pend[i]);
             if (r->tvoid < 0) { fail(cx, PD_E_LISP); return com_off; }
@@ -1011,14 +1089,25 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
     {
         Com &self = *at<Com>(cx, self_off);
         int nk = 0;
+        PD_ROLLED
         for (int g = 0; g < self.nguard; ++g) {
             uint16_t played = 0;
+            PD_ROLLED
             for (int i = 0; i < nskipped; ++i) if (skipped[i] != NOCARD && csuit(skipped[i]) == self.gsuit[g]) played |= (uint16_t)(1u << crank(skipped[i]));
             const uint16_t left = (uint16_t)(self.granks[g] & ~played);
-            if (left) { for (int i = nk; i > 0; --i) { ks[i] = ks[i - 1]; kr[i] = kr[i - 1]; } ks[0] = self.gsuit[g]; kr[0] = left; ++nk; }
-            else { for (int i = nbroken; i > 0; --i) broken[i] = broken[i - 1]; broken[0] = self.gsuit[g]; ++nbroken; }
+            if (left) {
+                PD_ROLLED
+                for (int i = nk; i > 0; --i) { ks[i] = ks[i - 1]; kr[i] = kr[i - 1]; }
+                ks[0] = self.gsuit[g]; kr[0] = left; ++nk;
+            }
+            else {
+                PD_ROLLED
+                for (int i = nbroken; i > 0; --i) broken[i] = broken[i - 1];
+                broken[0] = self.gsuit[g]; ++nbroken;
+            }
         }
         self.nguard = (uint8_t)nk;
+        PD_ROLLED
         for (int i = 0; i < nk; ++i) { self.gsuit[i] = ks[i]; self.granks[i] = kr[i]; }
     }
     uint32_t refreshed = 0;
@@ -1028,26 +1117,42 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
     }
     // the new play-com
     act.n = 0;
+    PD_ROLLED
     for (int i = base.n - 1; i >= 0; --i) rl_push(cx, act, base.r[i]);                 // (reverse base-routes)
+    PD_ROLLED
     for (int i = 0; i < new_active.n; ++i) insert_route(cx, act, new_active.r[i]);
     pend.n = new_pending.n;
+    PD_ROLLED
     for (int i = 0; i < new_pending.n; ++i) pend.r[i] = new_pending.r[i];
     {
         const Com &self = *at<Com>(cx, self_off);                                      // the arena never moves: references stay valid
-        if (refreshed) { const Com &rf = *at<Com>(cx, refreshed); for (int i = 0; i < rf.nact; ++i) insert_route(cx, act, rf.act[i]); }
+        if (refreshed) {
+            const Com &rf = *at<Com>(cx, refreshed);
+            PD_ROLLED
+            for (int i = 0; i < rf.nact; ++i) insert_route(cx, act, rf.act[i]);
+        }
+        PD_ROLLED
         for (int i = 0; i < self.npend; ++i) insert_route(cx, pend, self.pend[i]);
-        if (refreshed) { const Com &rf = *at<Com>(cx, refreshed); for (int i = 0; i < rf.npend; ++i) insert_route(cx, pend, rf.pend[i]); }
+        if (refreshed) {
+            const Com &rf = *at<Com>(cx, refreshed);
+            PD_ROLLED
+            for (int i = 0; i < rf.npend; ++i) insert_route(cx, pend, rf.pend[i]);
+        }
         if (cx.status) return com_off;
         const uint32_t noff = arena_alloc(cx, sizeof(Com));
         if (cx.status) return com_off;
         Com &n = *at<Com>(cx, noff);
         n.zero_id = self.zero_id; n.nact = (uint8_t)act.n; n.npend = (uint8_t)pend.n;
+        PD_ROLLED
         for (int i = 0; i < act.n; ++i) n.act[i] = act.r[i];
+        PD_ROLLED
         for (int i = 0; i < pend.n; ++i) n.pend[i] = pend.r[i];
         int ng = 0;
+        PD_ROLLED
         for (int i = 0; i < self.nguard; ++i) { n.gsuit[ng] = self.gsuit[i]; n.granks[ng] = self.granks[i]; ++ng; }
         if (refreshed) {
             const Com &rf = *at<Com>(cx, refreshed);
+            PD_ROLLED
             for (int i = 0; i < rf.nguard; ++i) { if (ng >= MAXG) { fail(cx, PD_E_CAP); break; } n.gsuit[ng] = rf.gsuit[i]; n.granks[ng] = rf.granks[i]; ++ng; }
         }
         n.nguard = (uint8_t)ng;
@@ -1066,6 +1171,7 @@ PD_HDN void hunt_card(Ctx &cx, Outcome &o, int suit, int rank, const Hand *h)
     TmpFrame tf(cx);
     Trick &t = *tmp<Trick>(cx);
     trick_init(t, suit, cx.trump);
+    PD_ROLLED
     for (int i = 0; i < 4; ++i) beat_or_low(cx, t, h[i], top[i]);
     outcome_of_trick(cx, o, t);
 }
@@ -1075,11 +1181,13 @@ PD_HDN void play_strategy(Ctx &cx, RootStrategy &rs, const Hand *h, SearchFrame 
     const int trump = cx.trump;
     int8_t suits[MAXT + 1];
     int ns = 0;
+    PD_ROLLED
     for (int i = 0; i < rs.nsoon; ++i) if (h[0].s[rs.soonest[i]]) suits[ns++] = rs.soonest[i];
     if (ns > 2) ns = 2;                                              // (list-lead 2 suits)
     search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
     if (cx.status || out.n > 0) return;
     Target *target = nullptr;
+    PD_ROLLED
     for (int i = 0; i < rs.nest && !target; ++i) {
         const int suit = rs.establish[i].suit;
         const bool ok = h[0].s[suit] && (suit != trump || h[1].s[suit] || h[3].s[suit])
@@ -1090,6 +1198,7 @@ PD_HDN void play_strategy(Ctx &cx, RootStrategy &rs, const Hand *h, SearchFrame 
     const int suit = target->suit;
     suits[0] = (int8_t)suit;
     ns = 1;
+    PD_ROLLED
     for (int i = 0; i < rs.nsoon; ++i) suits[ns++] = rs.soonest[i];
     search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
     if (cx.status || out.n > 0) return;
@@ -1132,8 +1241,10 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     cx.sstk = S.tmp; cx.scap = (uint32_t)sizeof(S.tmp); cx.stop = 0; cx.speak = 0;
     res.arena_peak = 0; res.nodes = 0; res.n = 0; res.score[0] = res.score[1] = 0;
     Hand *in = tmp<Hand>(cx, 4), *rolled = tmp<Hand>(cx, 4);
+    PD_ROLLED
     for (int i = 0; i < 4; ++i) { in[i] = declarer_left_dummy_right[i]; rolled[i] = declarer_left_dummy_right[(i + 1) & 3]; }   // (roll -1 hands): the left-hand opponent leads
     int8_t *all_suits = tmp<int8_t>(cx, 4);
+    PD_ROLLED
     for (int i = 0; i < 4; ++i) all_suits[i] = (int8_t)i;
     // active = strategy of the side on lead, passive = declarer's (2923-2926)
     find_opp_weakness(cx, S.roots[0], rolled, S.sstack);
@@ -1143,6 +1254,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     int sp = 0;
     {
         PlayFrame &f = S.pstack[0];
+        PD_ROLLED
         for (int i = 0; i < 4; ++i) f.hands[i] = rolled[i];
         outcome_nil(f.outcome);
         f.active.root = 0; f.active.com = com_a; f.passive.root = 1; f.passive.com = com_p;
@@ -1151,11 +1263,13 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     Outcome &final = *tmp<Outcome>(cx), &ans = *tmp<Outcome>(cx);
     outcome_nil(final);
     bool entering = true;
+    PD_ROLLED
     while (!cx.status) {
         PlayFrame &f = S.pstack[sp];
         if (entering) {
             ++res.nodes;
             f.any_suit = -1;
+            PD_ROLLED
             for (int s = 0; s < 4; ++s) if (f.hands[0].s[s]) { f.any_suit = (int8_t)s; break; }
             f.opt = 0; f.have_best = 0; outcome_nil(f.best);
             entering = false;
@@ -1189,6 +1303,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         if (cx.status) break;
         if (sp + 1 >= MAXD) { fail(cx, PD_E_CAP); break; }
         PlayFrame &c = S.pstack[sp + 1];
+        PD_ROLLED
         for (int i = 0; i < 4; ++i) c.hands[i] = ans.rem[i];
         if (f.outcome.valid) { outcome_copy(c.outcome, f.outcome); outcome_add(cx, c.outcome, ans, true); } else outcome_copy(c.outcome, ans);
         const bool w = outcome_won(ans);
@@ -1204,7 +1319,12 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     if (!cx.status && !final.valid) res.status = PD_E_NIL;
     if (res.status == PD_OK) {
         res.score[0] = final.score[0]; res.score[1] = final.score[1]; res.n = final.n;
-        for (int t = 0; t < final.n; ++t) { for (int i = 0; i < 4; ++i) res.tricks[t][i] = final.tricks[t][i]; res.wno[t] = final.wno[t]; }
+        PD_ROLLED
+        for (int t = 0; t < final.n; ++t) {
+            PD_ROLLED
+            for (int i = 0; i < 4; ++i) res.tricks[t][i] = final.tricks[t][i];
+            res.wno[t] = final.wno[t];
+        }
     }
 }
 

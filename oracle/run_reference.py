@@ -5,6 +5,7 @@ only) under oracle/minilisp.py and write what they compute into committed fixtur
     python oracle/run_reference.py tests            # tests/golden/reference_inline_tests.json
     python oracle/run_reference.py playdeal [N]     # tests/golden/playdeal_ref.json
     python oracle/run_reference.py tables           # tests/golden/reference_tables.json
+    python oracle/run_reference.py build [N]        # tests/golden/reference_build_samples.json
 
 `tests` evaluates every inline `(test FORM EXPECTED PRED)` form of bridge.cl (lines 23-3086), bidding.cl and compscore.cl
 with the reference's own
@@ -19,6 +20,10 @@ computes, not to the stale literal.
 the reference has no direct test of it), `match-points`' IMP scale for every |difference| 0..4100 (compscore.cl:123-131),
 and, for seeded random hands, `assess-hand`, `balanced?` (bidding.cl:33-46) and `choose-bid` (146-150: the reference
 `eval`s the rule forms) over `openings`, `(nt-responses 1)`, `(nt-responses 2)` and `2C-responses`.
+
+`build` draws N deals with the reference's own `build` (bridge.cl:1292-1319: `distgen` + `infer-distgen-params`, the
+sequential seat-by-seat semantics) for one fixed hand and two ranged seats -- the reference has no test of a sampling
+DISTRIBUTION; these samples are what the reference-order sampler (mode 3) and the oracle's restatement are compared with.
 
 `playdeal` draws seeded random deals (full 13-card deals and k-card endings), calls the reference's `play-deal`
 (bridge.cl:2961) on each with no trump and with a trump suit, and stores deal, trump, tricks, winners and score.
@@ -191,6 +196,33 @@ def gen_tables():
             "schemes": {k: M.lisp_repr(v) for k, v in schemes.items()}}
 
 
+BUILD_FORM = """(make-instance 'deal :~ '((:hcp (15 17) :s (5 nil)) (:hcp (10 11) :h (4 nil)))
+                                    := '(((A J 7) (A K 5 4) (6 5 4 3) (6 4))))"""
+
+
+def build_worker(job):
+    seed, n = job
+
+    def run():
+        it = M.Interp(seed=seed)
+        M.load_file(it, REF, first_line=23, last_line=3086)
+        dg = it.eval(M.read_from_string(BUILD_FORM), None, None)
+        out = []
+        for _ in range(n):
+            hands = it.fn(M.S("BUILD"))(dg)
+            out.append([[list(x) if x else [] for x in it.fn(M.S("SUITS"))(h)] for h in hands])
+        return out
+    return big_stack(run)
+
+
+def gen_build(n_total):
+    procs = min(8, os.cpu_count() or 1)
+    per = (n_total + procs - 1) // procs
+    with mp.Pool(procs) as pool:
+        parts = pool.map(build_worker, [(1000 + i, per) for i in range(procs)], chunksize=1)
+    return [d for p in parts for d in p]
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "tests"
     if what == "tests":
@@ -206,6 +238,15 @@ def main():
         out = big_stack(gen_tables)
         json.dump(out, open(os.path.join(GOLDEN, "reference_tables.json"), "w"), separators=(",", ":"))
         print("contract-score table, IMP scale and %d hands written" % len(out["hands"]))
+    elif what == "build":
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 3200
+        t0 = time.time()
+        deals = gen_build(n)
+        json.dump({"source": "(build deal) of bridge.cl:1292-1319 run by oracle/minilisp.py; result order = the fixed hand, "
+                             "the two ranged seats in def order, the leftover hand; each hand = 4 ascending rank lists (c d h s)",
+                   "form": " ".join(BUILD_FORM.split()), "deals": deals},
+                  open(os.path.join(GOLDEN, "reference_build_samples.json"), "w"), separators=(",", ":"))
+        print(f"{len(deals)} deals built by the reference in {time.time() - t0:.0f} s")
     elif what == "playdeal":
         n = int(sys.argv[2]) if len(sys.argv) > 2 else 24
         t0 = time.time()
