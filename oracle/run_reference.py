@@ -22,7 +22,7 @@ and, for seeded random hands, `assess-hand`, `balanced?` (bidding.cl:33-46) and 
 `eval`s the rule forms) over `openings`, `(nt-responses 1)`, `(nt-responses 2)` and `2C-responses`.
 
 `build` draws N deals with the reference's own `build` (bridge.cl:1292-1319: `distgen` + `infer-distgen-params`, the
-sequential seat-by-seat semantics) for one fixed hand and two ranged seats -- the reference has no test of a sampling
+sequential seat-by-seat semantics) for two fixed hands and two ranged seats -- the reference has no test of a sampling
 DISTRIBUTION; these samples are what the reference-order sampler (mode 3) and the oracle's restatement are compared with.
 
 `playdeal` draws seeded random deals (full 13-card deals and k-card endings), calls the reference's `play-deal`
@@ -196,8 +196,12 @@ def gen_tables():
             "schemes": {k: M.lisp_repr(v) for k, v in schemes.items()}}
 
 
-BUILD_FORM = """(make-instance 'deal :~ '((:hcp (15 17) :s (5 nil)) (:hcp (10 11) :h (4 nil)))
-                                    := '(((A J 7) (A K 5 4) (6 5 4 3) (6 4))))"""
+# two fixed hands, two ranged seats: all four seats are defined, so infer-distgen-params also infers LOWER bounds
+# (bridge.cl:1128,1194), and the last ranged seat is never sampled (1303): it receives the 13 cards left over.  (One
+# fixed hand would be the more usual request, but its root generator walks 4 096 honour patterns per build: 20-100 s per
+# deal under the evaluator against 0.2 s here.)
+BUILD_FORM = """(make-instance 'deal :~ '((:hcp (2 4) :h (3 nil)) (:hcp (2 4) :s (2 nil)))
+                                    := '(((A K Q J) (A K Q J) (4 3 2) (3 2)) ((10 9 8) (10 9 8) (A K 5) (A K 5 4))))"""
 
 
 def build_worker(job):
@@ -239,12 +243,20 @@ def main():
         json.dump(out, open(os.path.join(GOLDEN, "reference_tables.json"), "w"), separators=(",", ":"))
         print("contract-score table, IMP scale and %d hands written" % len(out["hands"]))
     elif what == "build":
-        n = int(sys.argv[2]) if len(sys.argv) > 2 else 3200
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
         t0 = time.time()
         deals = gen_build(n)
-        json.dump({"source": "(build deal) of bridge.cl:1292-1319 run by oracle/minilisp.py; result order = the fixed hand, "
-                             "the two ranged seats in def order, the leftover hand; each hand = 4 ascending rank lists (c d h s)",
-                   "form": " ".join(BUILD_FORM.split()), "deals": deals},
+        fixed = deals[0][:2]
+        masks = []
+        for d in deals:
+            assert d[:2] == fixed
+            masks.append(sum(1 << (13 * s + r) for s in range(4) for r in d[2][s]))
+        json.dump({"source": "(build deal) of bridge.cl:1292-1319 run by oracle/minilisp.py; result order = the two fixed hands, "
+                             "the sampled ranged seat, the leftover hand (the second ranged seat, never sampled)",
+                   "form": " ".join(BUILD_FORM.split()), "fixed": fixed,
+                   "encoding": "third_hand[i] = 52-bit mask (bit 13*suit + rank) of the sampled ranged seat of deal i; "
+                               "the fourth hand is what the other three leave",
+                   "third_hand": masks},
                   open(os.path.join(GOLDEN, "reference_build_samples.json"), "w"), separators=(",", ":"))
         print(f"{len(deals)} deals built by the reference in {time.time() - t0:.0f} s")
     elif what == "playdeal":
