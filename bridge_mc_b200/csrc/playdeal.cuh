@@ -60,6 +60,8 @@ PD_HD Card mk(int suit, int rank) { return (Card)((suit << 4) | rank); }
 PD_HD int csuit(Card c) { return c >> 4; }
 PD_HD int crank(Card c) { return c & 15; }
 PD_HD int cidx(Card c) { return c == NOCARD ? 52 : csuit(c) * 13 + crank(c); }
+PD_HD uint32_t pack4(const Card *c) { return (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24); }
+PD_HD Card tcard(uint32_t t, int i) { return (Card)(t >> (8 * i)); }
 PD_HD int lowbit(uint32_t m)
 {
 #if defined(__CUDA_ARCH__)
@@ -87,19 +89,27 @@ PD_HD int popc(uint32_t m)
 // ranks of `m` strictly above r (r may be -1)
 PD_HD uint32_t above(uint32_t m, int r) { return r < 0 ? m : (r >= 12 ? 0u : (m & ~((2u << r) - 1u))); }
 
-struct Hand {
-    uint16_t s[4];
-    uint8_t id;
+// A hand is ONE 64-bit word: suit s in bits [16 s, 16 s + 13), the seat it descends from in bits 62..63 -- copying a hand
+// is a register move and taking a card one AND.  `h.s[suit]` reads a suit's 13-bit rank mask.
+struct Suits {
+    uint64_t m;
+    PD_HD uint32_t operator[](int suit) const { return (uint32_t)(m >> (16 * suit)) & 0x1FFFu; }
 };
-PD_HD bool hand_empty(const Hand &h) { return (h.s[0] | h.s[1] | h.s[2] | h.s[3]) == 0; }
+struct Hand {
+    Suits s;
+    PD_HD int id() const { return (int)(s.m >> 62) & 3; }
+    PD_HD void set_id(int k) { s.m = (s.m & ~(3ull << 62)) | ((uint64_t)(k & 3) << 62); }
+    PD_HD void set(int suit, uint32_t mask) { s.m = (s.m & ~(0x1FFFull << (16 * suit))) | ((uint64_t)(mask & 0x1FFFu) << (16 * suit)); }
+};
+PD_HD bool hand_empty(const Hand &h) { return (h.s.m & 0x1FFF1FFF1FFF1FFFull) == 0; }
 
-struct alignas(4) Outcome {      // bridge.cl:2190-2196; winners = tricks[i][wno[i]]
+struct alignas(16) Outcome {     // bridge.cl:2190-2196; winners = card wno[i] of tricks[i]
     uint8_t n;                   // tricks played
     uint8_t roll;
     uint8_t score[2];
     uint8_t valid;               // 0 = nil (no outcome)
-    Card tricks[13][4];
     uint8_t wno[13];
+    uint32_t tricks[13];         // four cards in play order, one byte each (pack4 / tcard)
     Hand rem[4];
 };
 
@@ -130,7 +140,7 @@ PD_HD void fail(Ctx &cx, int code) { if (!cx.status) cx.status = code; }
 // temporaries: `T &x = *tmp<T>(cx)` inside a function that opens with `TmpFrame tf(cx);`
 template <class T> PD_HD T *tmp(Ctx &cx, uint32_t count = 1)
 {
-    const uint32_t bytes = ((uint32_t)sizeof(T) * count + 7u) & ~7u;
+    const uint32_t bytes = ((uint32_t)sizeof(T) * count + 15u) & ~15u;
     if (cx.stop + bytes > cx.scap) { fail(cx, PD_E_CAP); return reinterpret_cast<T *>(cx.sstk); }   // scap >= any single request
     T *p = reinterpret_cast<T *>(cx.sstk + cx.stop);
     cx.stop += bytes;
@@ -185,7 +195,7 @@ PD_HD bool winnerp(const Trick &t) { return t.winner >= 0 && (t.n & 1) == (t.win
 PD_HD void hand_take(const Hand &h, int suit, int rank, Card &card, Hand &rest)
 {
     rest = h;
-    rest.s[suit] = (uint16_t)(h.s[suit] & ~(1u << rank));
+    rest.s.m = h.s.m & ~(1ull << (16 * suit + rank));
     card = mk(suit, rank);
 }
 
@@ -355,7 +365,15 @@ PD_HDN void copy_words(void *dst, const void *src, int words)
     PD_ROLLED
     for (int i = 0; i < words; ++i) d[i] = s[i];
 }
-PD_HD void outcome_copy(Outcome &dst, const Outcome &src) { if (&dst != &src) copy_words(&dst, &src, (int)(sizeof(Outcome) / 4)); }
+PD_HDN void outcome_copy(Outcome &dst, const Outcome &src)
+{
+    static_assert(sizeof(Outcome) % 16 == 0, "Outcome is copied in 16-byte pieces");
+    if (&dst == &src) return;
+    struct alignas(16) Q { uint32_t w[4]; };
+    Q *d = reinterpret_cast<Q *>(&dst);
+    const Q *q = reinterpret_cast<const Q *>(&src);
+    for (int i = 0; i < (int)(sizeof(Outcome) / 16); ++i) d[i] = q[i];
+}
 
 PD_HDN void outcome_empty(Outcome &o, const Hand *hands)
 {
@@ -372,7 +390,7 @@ PD_HDN void outcome_of_trick(Ctx &cx, Outcome &o, const Trick &t)
     o.valid = 1; o.n = 1; o.roll = (uint8_t)t.winner;
     o.score[0] = (t.winner & 1) ? 0 : 1; o.score[1] = (t.winner & 1) ? 1 : 0;
     PD_ROLLED
-    for (int i = 0; i < 4; ++i) o.tricks[0][i] = t.cards[i];
+    o.tricks[0] = pack4(t.cards);
     o.wno[0] = (uint8_t)t.winner;
     PD_ROLLED
     for (int i = 0; i < 4; ++i) o.rem[i] = t.rem[(i + t.winner) & 3];       // (roll (- winner) remaining)
@@ -383,8 +401,7 @@ PD_HDN void outcome_add(Ctx &cx, Outcome &self, const Outcome &other, bool star)
     if (self.n + other.n > 13) { fail(cx, PD_E_CAP); return; }
     PD_ROLLED
     for (int k = 0; k < other.n; ++k) {
-        PD_ROLLED
-        for (int i = 0; i < 4; ++i) self.tricks[self.n + k][i] = other.tricks[k][i];
+        self.tricks[self.n + k] = other.tricks[k];
         self.wno[self.n + k] = other.wno[k];
     }
     const bool flip = (self.roll & 1) != 0;
@@ -539,7 +556,7 @@ PD_HDN void suit_value(Ctx &cx, SuitValue &sv, int suit, int trump, const Hand *
         const bool first = (o.wno[k] & 1) == 0;
         if (!first) ++g;
         if (g >= 15) { fail(cx, PD_E_CAP); break; }
-        sv.gcards[g][sv.glen[g]++] = o.tricks[k][o.wno[k]];
+        sv.gcards[g][sv.glen[g]++] = tcard(o.tricks[k], o.wno[k]);
         any = true;
     }
     sv.ngroups = any ? (uint8_t)(g + 1) : 0;
@@ -629,8 +646,6 @@ struct Com {                     // play-com
 };
 struct RouteList { int n; uint32_t r[MAXR]; };
 
-PD_HD uint32_t pack4(const Card *c) { return (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24); }
-PD_HD Card tcard(uint32_t t, int i) { return (Card)(t >> (8 * i)); }
 
 PD_HDN uint32_t new_route(Ctx &cx, int frm, int to, int tvoid, uint32_t tricks, uint32_t len)
 {
@@ -791,7 +806,8 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
         if (cx.status) break;
         PD_ROLLED
         for (int t = 0; t < tops.n; ++t) {
-            const Card *c = tops.tricks[t];
+            Card c[4];
+            c[0] = tcard(tops.tricks[t], 0); c[1] = tcard(tops.tricks[t], 1); c[2] = tcard(tops.tricks[t], 2); c[3] = tcard(tops.tricks[t], 3);
             const int w = tops.wno[t];
             const Card win = c[w];
             const bool mine = win != NOCARD && ((h[0].s[csuit(win)] >> crank(win)) & 1u);
@@ -863,7 +879,7 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
     const uint32_t coff = arena_alloc(cx, sizeof(Com));
     if (cx.status) return 0;
     Com &com = *at<Com>(cx, coff);
-    com.zero_id = h[0].id; com.nact = com.npend = 0;
+    com.zero_id = (uint8_t)h[0].id(); com.nact = com.npend = 0;
     PD_ROLLED
     for (int i = routes.n - 1; i >= 0; --i) {                    // divlist reverses
         const Route *r = at<Route>(cx, routes.r[i]);
@@ -1049,14 +1065,14 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
         const Com &com = *at<Com>(cx, com_off);
         int offset = -1;
         PD_ROLLED
-        for (int i = 0; i < 4; ++i) if (out.rem[i].id == com.zero_id) { offset = i; break; }
+        for (int i = 0; i < 4; ++i) if (out.rem[i].id() == com.zero_id) { offset = i; break; }
         if (offset < 0) { fail(cx, PD_E_LISP); return com_off; }
         if (offset > 0) {
             self_off = arena_alloc(cx, sizeof(Com));
             if (cx.status) return com_off;
             Com &n = *at<Com>(cx, self_off);
             const Com &c = *at<Com>(cx, com_off);
-            n.zero_id = out.rem[0].id; n.nact = c.nact; n.npend = c.npend; n.nguard = 0;
+            n.zero_id = (uint8_t)out.rem[0].id(); n.nact = c.nact; n.npend = c.npend; n.nguard = 0;
             PD_ROLLED
             for (int i = 0; i < c.nact; ++i) { const Route r = *at<Route>(cx, c.act[i]); n.act[i] = new_route(cx, r.frm >= 0 ? (r.frm + offset) & 3 : -1, (r.to + offset) & 3, r.tvoid, r.tricks, r.len); }
             PD_ROLLED
@@ -1068,7 +1084,7 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
     PD_ROLLED
     for (int t = 0; t < out.n; ++t) {
         PD_ROLLED
-        for (int i = 0; i < 4; ++i) raw[nraw++] = out.tricks[t][i];
+        for (int i = 0; i < 4; ++i) raw[nraw++] = tcard(out.tricks[t], i);
     }
     int nskipped = 0;
     first_pass(cx, *at<Com>(cx, self_off), raw, nraw, base, skipped, nskipped);
@@ -1231,7 +1247,7 @@ struct Scratch {
     PlayFrame pstack[MAXD];
     RootStrategy roots[2];
     Result res;
-    alignas(8) uint8_t tmp[5120];    // temporaries of the call chain (measured peak 4 248 B) (deepest: play-deal > after-tricks > play-routes > search > simple-trick)
+    alignas(16) uint8_t tmp[4736];    // temporaries of the call chain (structural peak 4 320 B: play-deal > after-tricks > play-routes > search > simple-trick)
 };
 
 PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Hand *declarer_left_dummy_right, Scratch &S, Result &res)
@@ -1322,7 +1338,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         PD_ROLLED
         for (int t = 0; t < final.n; ++t) {
             PD_ROLLED
-            for (int i = 0; i < 4; ++i) res.tricks[t][i] = final.tricks[t][i];
+            for (int i = 0; i < 4; ++i) res.tricks[t][i] = tcard(final.tricks[t], i);
             res.wno[t] = final.wno[t];
         }
     }

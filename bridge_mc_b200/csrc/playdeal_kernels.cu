@@ -22,15 +22,13 @@ __device__ __noinline__ void play_one_deal(const uint4 *records, const unsigned 
             const int seat = (dec + k) & 3;
             const uint32_t xl = (seat & 1) ? 0u : 0xFFFFFFFFu, xh = (seat & 2) ? 0u : 0xFFFFFFFFu;
             const uint32_t m0 = (r.x ^ xl) & (r.z ^ xh) & 0x1FFF1FFFu, m1 = (r.y ^ xl) & (r.w ^ xh) & 0x1FFF1FFFu;
-            h[k].s[0] = (uint16_t)(m0 & 0xFFFFu); h[k].s[1] = (uint16_t)(m0 >> 16);
-            h[k].s[2] = (uint16_t)(m1 & 0xFFFFu); h[k].s[3] = (uint16_t)(m1 >> 16);
-            h[k].id = (uint8_t)k;
+            h[k].s.m = (unsigned long long)m0 | ((unsigned long long)m1 << 32);      // the record's lane layout is the hand's
+            h[k].set_id(k);
         }
     } else {
         for (int k = 0; k < 4; ++k) {                            // four lane masks: declarer, left, dummy, right
-            const unsigned long long m = hands4[4 * i + k];
-            for (int s = 0; s < 4; ++s) h[k].s[s] = (uint16_t)((m >> (16 * s)) & 0x1FFFu);
-            h[k].id = (uint8_t)k;
+            h[k].s.m = hands4[4 * i + k] & 0x1FFF1FFF1FFF1FFFull;
+            h[k].set_id(k);
         }
     }
     pd::Result &res = S.res;

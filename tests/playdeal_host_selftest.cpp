@@ -16,8 +16,9 @@ int main(int argc, char **argv)
     while (scanf("%d", &trump) == 1) {
         pd::Hand h[4];
         for (int i = 0; i < 4; ++i) {
-            for (int s = 0; s < 4; ++s) { unsigned m; if (scanf("%u", &m) != 1) return 1; h[i].s[s] = (uint16_t)m; }
-            h[i].id = (uint8_t)i;
+            h[i].s.m = 0;
+            for (int s = 0; s < 4; ++s) { unsigned m; if (scanf("%u", &m) != 1) return 1; h[i].set(s, m); }
+            h[i].set_id(i);
         }
         pd::Result r;
         pd::play_deal(arena.data(), arena_bytes, trump, h, S, r);
