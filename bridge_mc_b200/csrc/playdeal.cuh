@@ -695,11 +695,25 @@ PD_HDN void insert_route(Ctx &cx, RouteList &routes, uint32_t route)
 // won is dropped and the next one tried.  Pops the route IN PLACE.
 PD_HDN void reproduce(Ctx &cx, uint32_t route, const Hand *hands, Outcome &ans)
 {
+    // The hands do not change while tricks are dropped, and a route is mostly copies of a few tricks (the pending lists
+    // are merged with themselves at every trick): a trick that failed once in this call fails again -- remember the last
+    // few and drop their copies without replaying them.
+    constexpr int NTRIED = 24;
+    TmpFrame tried_frame(cx);
+    uint32_t *tried = tmp<uint32_t>(cx, NTRIED);
+    int ntried = 0;
     for (;;) {
         Route *r = at<Route>(cx, route);
         if (r->len == 0 || cx.status) { outcome_nil(ans); return; }
         const uint32_t base = at<uint32_t>(cx, r->tricks)[0];
         r->tricks += 4; r->len -= 1;
+        {
+            bool seen = false;
+            PD_ROLLED
+            for (int i = 0; i < ntried && !seen; ++i) seen = tried[i] == base;
+            if (seen) continue;
+            if (ntried < NTRIED) tried[ntried++] = base;
+        }
         Card ref[4];
         PD_ROLLED
         for (int i = 0; i < 4; ++i) ref[i] = tcard(base, i);
@@ -915,7 +929,7 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         const Route r = *at<Route>(cx, roff);
         // rem-break-div (2397-2411): first index of each card as a first card / as a third card of the route's tricks
         PD_ROLLED
-        for (int i = 0; i < 53; ++i) pos_first[i] = pos_third[i] = -1;
+        for (int i = 0; i < ncards; ++i) { const int ci = cidx(cards[i]); pos_first[ci] = -1; pos_third[ci] = -1; }   // only these are read
         if (r.len > 32767) { fail(cx, PD_E_CAP); return; }
         {
             // only the cards just played matter: a 53-bit request mask over the card indices
