@@ -123,7 +123,7 @@ def main():
         cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
         cons.set_scoring(cs, [0, 0, 0, 0, 1, 1, 1, 1], [0, 1, 1, 2, 2, 3, 4, 5, 5, 6, 6, 7])
         t = run("C4", cons, int(8 * 10 * (1 << 28) * scale), "South test-bid (1 NT) sample scored in stage B: tricks x base-score per "
-                "contract, match-points per pair (stand-in trick source keyed on the deal; play-deal is out of scope)",
+                "contract, match-points per pair (stand-in trick source keyed on the deal; real tricks: tools/run_playdeal.py)",
                 tally_mask=TALLY_ALL | TALLY_SCORE)
         if rank == 0:
             print(json.dumps({"config": "C4-tallies", "n_gpus": world, "accepted": t["accepted"],
