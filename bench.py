@@ -372,10 +372,15 @@ def run_gpu(args):
             raise SystemExit("bench.py: bmc_host_alloc failed")
         host_rec = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint64)), shape=(cap, 2))
         host_off = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(cap,))
+        host_bytes = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(cap * 2,))
 
         def e2e_leg(kind, k, base):
             def one(i):
                 first = bdist.step_first_index(base + i, rank, world)
+                if kind == "packed":
+                    pk, t_h, st = eng.sample_packed(cons, n_accept=target, wave=args.wave, first_index=first, seed=SEED, out=host_bytes)
+                    st.stored = pk.size                          # bytes that crossed the bus
+                    return pk, t_h, st
                 if kind == "indices":
                     return eng.sample_indices(cons, n_accept=target, wave=args.wave, first_index=first, seed=SEED, cap=cap, offsets=host_off)
                 if kind == "records":
@@ -396,16 +401,19 @@ def run_gpu(args):
                 dist.all_reduce(emx, op=dist.ReduceOp.MAX)
                 dist.all_reduce(et, op=dist.ReduceOp.SUM)
                 dt = float(emx[2])
-            per = {"indices": 4, "records": 16, "tallies": 0}[kind]
+            per = {"packed": 1, "indices": 4, "records": 16, "tallies": 0}[kind]
             d2h = int(e_stored // k * per + _lib.TALLY_WORDS * 8)
             return {"value": float(et[0]) / dt, "unit": UNIT, "accepted_per_s": float(et[1]) / dt,
                     "h2d_bytes_per_step": 4096, "d2h_bytes_per_step": d2h, "steps": k, "ms_per_step": 1e3 * dt / k,
                     "d2h_gb_per_s_all_ranks": d2h * world * k / dt / 1e9,
-                    "api": {"indices": "bmc_sample_indices (host buffer of 32-bit index offsets, pinned; bmc_expand regenerates records on demand)",
+                    "api": {"packed": "bmc_sample_packed (host buffer of gap bytes, pinned: about one byte per accepted deal; "
+                                      "bmc_unpack_indices + bmc_expand regenerate offsets / records on demand)",
+                            "indices": "bmc_sample_indices (host buffer of 32-bit index offsets, pinned; bmc_expand regenerates records on demand)",
                             "records": "bmc_sample (host buffer of 16-byte records, pinned)",
                             "tallies": "bmc_sample with records = NULL (tally buffer only)"}[kind]}
 
         k = max(10, args.steps)
+        e2e["packed"] = e2e_leg("packed", k, 500)
         e2e["indices"] = e2e_leg("indices", k, 1000)
         e2e["records"] = e2e_leg("records", max(3, min(args.steps, 5)), 2000)
         e2e["tallies"] = e2e_leg("tallies", k, 3000)
@@ -433,9 +441,11 @@ def run_gpu(args):
             "config": {"workload": f"C2: South test-bid (1 NT) rejection sampling, {target:.0e} accepted deals per GPU per step "
                                    f"(waves of {args.wave} Philox indices)",
                        "l2": "no input buffers (counter-based RNG); 1.6 GB of records written per step >> 126 MB L2",
-                       "e2e_note": "e2e = bmc_sample_indices with a pinned host buffer: every accepted deal leaves the device as the 32-bit "
-                                   "offset of its Philox index (the deal is a pure function of seed and index; bmc_expand regenerates "
-                                   "records); e2e_full_records ships the 16-byte records, e2e_tallies_only the tally buffer alone",
+                       "e2e_note": "every accepted deal leaves the device as its Philox index (the deal is a pure function of seed and "
+                                   "index; bmc_expand regenerates records): e2e_packed_records = bmc_sample_packed, gap bytes, about one "
+                                   "byte per deal; e2e_index_records = bmc_sample_indices, 32-bit offsets; e2e = the faster of the two on "
+                                   "this run (e2e.chosen); e2e_full_records ships the 16-byte records, e2e_tallies_only the tally "
+                                   "buffer alone; pinned host buffers",
                        "parallelism": f"dp{world}: disjoint Philox index ranges + NCCL all-reduce of the {_lib.TALLY_WORDS * 8} B tally buffer",
                        "host_binding_rank0": numa},
             "accepted_per_s": acc_all / (ms * 1e-3),
@@ -459,7 +469,12 @@ def run_gpu(args):
             "tally_check": {"accepted": final["accepted"], "south_hcp_15_16_17": [int(x) for x in final["hcp"][2][15:18]]},
         }
         if e2e:
-            line["e2e"] = e2e["indices"]
+            # two result forms deliver every accepted deal to the host (gap bytes / 32-bit offsets): the headline is the one
+            # that is faster on this box at this N -- offsets on one GPU, gap bytes once the ranks share the host's ingest
+            best = "packed" if e2e["packed"]["value"] >= e2e["indices"]["value"] else "indices"
+            line["e2e"] = dict(e2e[best], chosen=best)
+            line["e2e_packed_records"] = e2e["packed"]
+            line["e2e_index_records"] = e2e["indices"]
             line["e2e_full_records"] = e2e["records"]
             line["e2e_tallies_only"] = e2e["tallies"]
         if world == 1 and not args.no_cpu_baseline:

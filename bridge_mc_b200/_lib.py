@@ -76,7 +76,7 @@ EXPORTS = [
     "bmc_constraints_set_scoring", "bmc_constraints_primary_acceptance", "bmc_distgen", "bmc_sample_indices", "bmc_sample_indices_dev", "bmc_expand", "bmc_expand_dev", "bmc_sample_multi",
     "bmc_scheme_size", "bmc_scheme_destroy", "bmc_sample", "bmc_sample_dev", "bmc_filter", "bmc_score",
     "bmc_match_points", "bmc_score_tally", "bmc_hist_base", "bmc_int_peak", "bmc_launch_count", "bmc_set_stream",
-    "bmc_play_deal", "bmc_play_deal_dev", "bmc_play_hands", "bmc_best_tricks",
+    "bmc_play_deal", "bmc_play_deal_dev", "bmc_play_hands", "bmc_best_tricks", "bmc_sample_packed", "bmc_unpack_indices",
 ]
 
 _lib = None
@@ -148,6 +148,8 @@ def load():
     L.bmc_play_deal_dev.argtypes = [vp, vp, u64, vp, vp, C.c_int, u32, vp]
     L.bmc_best_tricks.argtypes = [vp, vp, u64, vp, vp, C.c_int, u32, vp]
     L.bmc_play_hands.argtypes = [vp, vp, u64, vp, C.c_int, u32, vp]
+    L.bmc_sample_packed.argtypes = [vp, vp, u64, u64, u64, u64, u64, u32, vp, u64, C.POINTER(u64), C.POINTER(Tallies), C.POINTER(Stats)]
+    L.bmc_unpack_indices.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
     _lib = L
     return L
 

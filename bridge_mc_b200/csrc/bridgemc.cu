@@ -32,6 +32,7 @@
 #include "hist.cuh"
 #include "distgen.cuh"
 #include "playdeal_host.h"
+#include "pack.cuh"
 #include "rules.hpp"
 #include "jit.hpp"
 #include "embedded_src.inc"
@@ -491,9 +492,10 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t seed, uint32_t *
 // records) and without synchronising the stream -- and snapshots the accepted counter for the next wave's
 // cancellation test (wave_cancelled, kernels.cuh).
 __global__ void publish_counters_kernel(const unsigned long long *__restrict__ tallies, volatile unsigned long long *mapped,
-                                        unsigned long long *snap, unsigned long long seq)
+                                        unsigned long long *snap, unsigned long long seq, const unsigned long long *extra)
 {
     if (threadIdx.x < 4) mapped[threadIdx.x] = tallies[threadIdx.x];
+    if (threadIdx.x == 4) mapped[5] = extra ? *extra : 0ull;          // byte cursor of the packed index records
     if (threadIdx.x == 0) *snap = tallies[2];
     __threadfence_system();
     __syncwarp();
@@ -528,6 +530,11 @@ struct bmc_ctx {
     unsigned long long *d_tallies = nullptr;     // scratch tallies for the host-buffer API
     uint8_t *d_arena = nullptr;                  // grow-only per-deal arenas of the trick estimator (bmc_play_deal)
     uint64_t arena_bytes = 0;
+    uint32_t *d_bitmap = nullptr;                // packed index records (bmc_sample_packed): one wave's bitmap,
+    uint64_t bitmap_bytes = 0;
+    uint8_t *d_packed = nullptr;                 // the byte stream,
+    uint64_t packed_bytes = 0;
+    PackState *d_pack = nullptr;                 // and the cursors
     uint64_t launches = 0;
     std::mutex mu;
 };
@@ -664,6 +671,9 @@ void bmc_shutdown(bmc_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->d_tallies) cudaFree(c->d_tallies);
     if (c->d_arena) cudaFree(c->d_arena);
+    if (c->d_bitmap) cudaFree(c->d_bitmap);
+    if (c->d_packed) cudaFree(c->d_packed);
+    if (c->d_pack) cudaFree(c->d_pack);
     if (c->d_snap) cudaFree(c->d_snap);
     if (c->h_head) cudaFreeHost(c->h_head);
     if (c->d_rec) cudaFree(c->d_rec);
@@ -1618,13 +1628,17 @@ static int resolve_cfg(bmc_ctx *ctx, const bmc_constraints *cons, WaveCfg &w)
     return BMC_OK;
 }
 
-static int publish(bmc_ctx *ctx, const void *tallies_dev, unsigned long long seq)
+static int publish(bmc_ctx *ctx, const void *tallies_dev, unsigned long long seq, const unsigned long long *extra = nullptr)
 {
-    publish_counters_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)tallies_dev, ctx->h_head_dev, ctx->d_snap, seq);
+    publish_counters_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)tallies_dev, ctx->h_head_dev, ctx->d_snap, seq, extra);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return BMC_OK;
 }
+
+// packed index records (pack.cuh): the waves' 32-bit offsets (rec_mode 1, `records_dev`) are turned into gap bytes wave
+// by wave, and the BYTES are what is streamed to the host
+struct PackCfg { uint8_t *bytes_dev; uint64_t cap_bytes; uint8_t *host_bytes; uint64_t *n_bytes; };
 
 // Common driver.  An accept-target job enqueues its waves back to back in batches sized from the acceptance seen so
 // far: a wave that starts after the target was met cancels itself on the device (wave_cancelled), so the accepted
@@ -1633,7 +1647,7 @@ static int publish(bmc_ctx *ctx, const void *tallies_dev, unsigned long long seq
 // later waves compute; the host follows the waves through the counters each one publishes in mapped memory.
 static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
                        uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, void *records_dev, uint64_t cap,
-                       void *tallies_dev, bmc_stats *stats, void *host_out, uint32_t rec_mode)
+                       void *tallies_dev, bmc_stats *stats, void *host_out, uint32_t rec_mode, const PackCfg *pack = nullptr)
 {
     if (n_accept_target == 0 && n_raw == 0) return fail(BMC_E_INVALID, "nothing to do: n_raw == 0 and no accept target");
     if ((tally_mask & BMC_TALLY_SCORE) && (!cons || cons->score.n == 0))
@@ -1649,7 +1663,7 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
         if (n_raw > (1ull << 32)) return fail(BMC_E_INVALID, "index records: at most 2^32 indices per call");
         if (n_raw == 0) n_raw = 1ull << 32;
     }
-    const bool stream_copy = host_out && records_dev && cap;
+    const bool stream_copy = pack ? true : (host_out && records_dev && cap);
     const bool stepwise = n_accept_target != 0 || stream_copy;
     if (wave == 0) wave = 1ull << 26;
     // 32-bit offsets from the launch's first index travel through the kernels' queues: 2^32 indices per launch
@@ -1661,8 +1675,9 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     volatile unsigned long long *head = ctx->h_head;
     for (int i = 0; i < 5; ++i) head[i] = 0;
     unsigned long long seq = 0;
+    const unsigned long long *cursor = pack ? &ctx->d_pack->bytes : nullptr;
     auto sync_head = [&]() -> int {                      // publish, wait for the stream, the counters are in `head`
-        int rc = publish(ctx, tallies_dev, ++seq);
+        int rc = publish(ctx, tallies_dev, ++seq, cursor);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return BMC_OK;
@@ -1672,7 +1687,34 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     w.target = n_accept_target;
     w.start_acc = start_acc;
     uint64_t copied = start_acc < cap ? start_acc : cap;
+    if (pack) {
+        copied = 0;
+        const PackState init = {start_acc < cap ? start_acc : cap, 0ull, 0ull, 0ull};
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_pack, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // after a wave: its new offsets -> bitmap -> gap bytes appended to the byte stream
+    auto pack_wave = [&](uint64_t wave_done, uint64_t n) -> int {
+        const uint64_t words = (n + 31) / 32;
+        CUDA_TRY(cudaMemsetAsync(ctx->d_bitmap, 0, words * 4, ctx->stream));
+        pack_scatter_kernel<<<ctx->sms * 8, 256, 0, ctx->stream>>>((const uint32_t *)records_dev, (const unsigned long long *)tallies_dev,
+                                                                   ctx->d_pack, cap, (uint32_t)wave_done, (uint32_t)n, ctx->d_bitmap);
+        pack_tiles_kernel<<<(unsigned)((n + PACK_TILE_BITS - 1) / PACK_TILE_BITS), PACK_THREADS, 0, ctx->stream>>>(
+            ctx->d_bitmap, (uint32_t)wave_done, (uint32_t)n, pack->bytes_dev, pack->cap_bytes, ctx->d_pack);
+        pack_advance_kernel<<<1, 1, 0, ctx->stream>>>((const unsigned long long *)tallies_dev, ctx->d_pack, cap);
+        ctx->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        return BMC_OK;
+    };
     auto copy_upto = [&](unsigned long long accepted) -> int {
+        if (pack) {                                      // bytes, not records: the cursor travels in head[5]
+            unsigned long long upto = head[5];
+            if (upto > pack->cap_bytes) upto = pack->cap_bytes;
+            if (upto > copied) {
+                CUDA_TRY(cudaMemcpyAsync(pack->host_bytes + copied, pack->bytes_dev + copied, upto - copied, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                copied = upto;
+            }
+            return BMC_OK;
+        }
         const uint64_t upto = accepted < cap ? accepted : cap;
         if (stream_copy && upto > copied) {
             CUDA_TRY(cudaMemcpyAsync((char *)host_out + copied * elem, (const char *)records_dev + copied * elem,
@@ -1706,7 +1748,8 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
                 if (n_raw && n_raw - done < n) n = n_raw - done;
                 int rc = launch_wave(ctx, w, first_index + done, n);
                 if (rc) return rc;
-                rc = publish(ctx, tallies_dev, ++seq);
+                if (pack) { rc = pack_wave(done, n); if (rc) return rc; }
+                rc = publish(ctx, tallies_dev, ++seq, cursor);
                 if (rc) return rc;
                 done += n;
             }
@@ -1757,6 +1800,14 @@ static int sample_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed,
     }
     if (!stepwise && cc && w.interp) { std::lock_guard<std::mutex> jl(cc->cal_mu); cc->interp_ms += kernel_ms; }
     if (stream_copy) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    if (pack) {
+        PackState fin;
+        CUDA_TRY(cudaMemcpyAsync(&fin, ctx->d_pack, sizeof fin, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (pack->n_bytes) *pack->n_bytes = fin.bytes;
+        if (fin.overflow || fin.bytes > pack->cap_bytes || head[2] > cap)
+            return fail(BMC_E_CAPACITY, "bmc_sample_packed: the byte buffer (or the internal offset scratch) is too small; *n_bytes = bytes needed");
+    }
     if (stats) {
         stats->raw = head[0] - start_raw; stats->voided = head[1]; stats->accepted = head[2];
         stats->stored = records_dev ? (head[2] < cap ? head[2] : cap) : 0;
@@ -1843,6 +1894,81 @@ int bmc_sample_indices_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t s
     CUDA_TRY(cudaSetDevice(ctx->device));
     return sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, offsets_dev, cap, tallies_dev,
                        stats, nullptr, 1u);
+}
+
+// ---- packed index records: about one byte per accepted deal (pack.cuh) ------------------------------------------
+int bmc_sample_packed(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                      uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, uint8_t *bytes, uint64_t cap_bytes,
+                      uint64_t *n_bytes, bmc_tallies *tallies, bmc_stats *stats)
+{
+    if (!ctx || !bytes || cap_bytes == 0) return fail(BMC_E_INVALID, "bmc_sample_packed: ctx / bytes is NULL");
+    auto t0 = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (wave == 0) wave = 1ull << 26;
+    if (wave > (1ull << 31)) wave = 1ull << 31;
+    // scratch: the call's offsets (a byte of the stream stands for at least one deal: cap_bytes offsets suffice), one
+    // wave's bitmap, the byte stream, the cursors
+    const uint64_t cap_off = cap_bytes;
+    { int rc = ensure_scratch(ctx, cap_off * sizeof(uint32_t)); if (rc) return rc; }
+    if (wave / 8 + 4 > ctx->bitmap_bytes) {
+        if (ctx->d_bitmap) cudaFree(ctx->d_bitmap);
+        ctx->d_bitmap = nullptr; ctx->bitmap_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_bitmap, wave / 8 + 4));
+        ctx->bitmap_bytes = wave / 8 + 4;
+    }
+    if (cap_bytes > ctx->packed_bytes) {
+        if (ctx->d_packed) cudaFree(ctx->d_packed);
+        ctx->d_packed = nullptr; ctx->packed_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_packed, cap_bytes));
+        ctx->packed_bytes = cap_bytes;
+    }
+    if (!ctx->d_pack) CUDA_TRY(cudaMalloc(&ctx->d_pack, sizeof(PackState)));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_tallies, 0, sizeof(bmc_tallies), ctx->stream));
+    bmc_stats st{};
+    uint64_t nb = 0;
+    const PackCfg pack = {ctx->d_packed, cap_bytes, bytes, &nb};
+    const int rc = sample_core(ctx, cons, seed, first_index, n_raw, n_accept_target, wave, tally_mask, ctx->d_rec, cap_off,
+                               ctx->d_tallies, &st, nullptr, 1u, &pack);
+    if (n_bytes) *n_bytes = nb;
+    if (rc != BMC_OK) return rc;
+    bmc_tallies host_t;
+    CUDA_TRY(cudaMemcpyAsync(&host_t, ctx->d_tallies, sizeof host_t, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    host_t.stored = st.accepted;
+    if (tallies) *tallies = host_t;
+    if (stats) {
+        *stats = st;
+        stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return BMC_OK;
+}
+
+// the byte stream -> 32-bit offsets from the call's first index (host side: a format decoder, no sampling)
+int bmc_unpack_indices(const uint8_t *bytes, uint64_t n_bytes, uint32_t *offsets, uint64_t cap, uint64_t *n)
+{
+    if (!bytes || !n) return fail(BMC_E_INVALID, "bmc_unpack_indices: NULL argument");
+    uint64_t pos = 0, count = 0;
+    while (pos + 8 <= n_bytes) {
+        uint32_t base = 0, len = 0;
+        for (int i = 0; i < 4; ++i) { base |= (uint32_t)bytes[pos + i] << (8 * i); len |= (uint32_t)bytes[pos + 4 + i] << (8 * i); }
+        pos += 8;
+        if (pos + len > n_bytes) return fail(BMC_E_INVALID, "bmc_unpack_indices: truncated chunk");
+        uint64_t cur = (uint64_t)base;                   // one past the "index before the tile"
+        for (uint32_t k = 0; k < len; ++k) {
+            const uint8_t b = bytes[pos + k];
+            if (b == 255) { cur += 255; continue; }
+            cur += b;
+            if (offsets && count < cap) offsets[count] = (uint32_t)cur;
+            ++count;
+            cur += 1;
+        }
+        pos += len;
+    }
+    *n = count;
+    if (pos != n_bytes) return fail(BMC_E_INVALID, "bmc_unpack_indices: trailing bytes");
+    if (offsets && count > cap) return fail(BMC_E_CAPACITY, "bmc_unpack_indices: more indices than cap");
+    return BMC_OK;
 }
 
 static int expand_core(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, const uint32_t *d_off,

@@ -266,6 +266,34 @@ class Engine:
         out = offsets[:st.stored] if cap else np.empty(0, dtype=np.uint32)
         return out, tallies_to_dict(t), st
 
+    def sample_packed(self, cons: Constraints | None = None, *, n_raw: int = 0, n_accept: int = 0, seed: int = DEFAULT_SEED,
+                      first_index: int = 0, wave: int = 0, tally_mask: int = TALLY_ALL, cap_bytes: int | None = None,
+                      out: np.ndarray | None = None):
+        """bmc_sample_packed: like sample_indices(), but the accepted indices come back as gap bytes (about one byte per
+        deal; include/bridgemc.h).  Returns (uint8[n_bytes], tallies, stats); unpack_indices() gives the offsets."""
+        if out is not None:
+            cap_bytes = out.nbytes
+        elif cap_bytes is None:
+            expect = n_accept + n_accept // 4 if n_accept else n_raw
+            cap_bytes = int(expect * 1.2) + (max(n_raw, 1 << 26) >> 16) * 8 + (1 << 20)
+        if out is None:
+            out = np.empty(cap_bytes, dtype=np.uint8)
+        t, st, nb = Tallies(), Stats(), C.c_uint64()
+        check(self._L.bmc_sample_packed(self._h, cons._h if cons else None, seed, first_index, n_raw, n_accept, wave, tally_mask,
+                                        out.ctypes.data, cap_bytes, C.byref(nb), C.byref(t), C.byref(st)))
+        return out[:nb.value], tallies_to_dict(t), st
+
+    def unpack_indices(self, packed: np.ndarray, cap: int | None = None) -> np.ndarray:
+        """bmc_unpack_indices: gap bytes -> uint32 offsets from first_index (chunk order; sort for index order)."""
+        b = np.ascontiguousarray(packed, dtype=np.uint8)
+        n = C.c_uint64()
+        if cap is None:
+            check(self._L.bmc_unpack_indices(b.ctypes.data, b.size, None, 0, C.byref(n)))
+            cap = n.value
+        offs = np.empty(cap, dtype=np.uint32)
+        check(self._L.bmc_unpack_indices(b.ctypes.data, b.size, offs.ctypes.data, cap, C.byref(n)))
+        return offs[:n.value]
+
     def sample_indices_dev(self, cons: Constraints | None, offsets_ptr: int, cap: int, tallies_ptr: int, *, n_raw: int = 0,
                            n_accept: int = 0, seed: int = DEFAULT_SEED, first_index: int = 0, wave: int = 0,
                            tally_mask: int = TALLY_ALL) -> Stats:

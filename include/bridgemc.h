@@ -255,6 +255,19 @@ int bmc_expand(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_
 int bmc_expand_dev(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index,
                    const void *offsets_dev, uint64_t n, void *records_dev);
 
+/* Packed index records: the accepted deals' Philox indices as GAP BYTES, about one byte per deal (1.03 at an acceptance of
+ * 3.8 %) instead of four -- for hosts whose ingest bandwidth is shared by several GPUs.  The stream is a sequence of
+ * chunks, in no particular order: 8-byte header (little endian: u32 offset of the chunk's first index from first_index,
+ * u32 payload length), then the payload: with cur = that offset - 1, a byte b < 255 accepts index cur += b + 1 and
+ * b = 255 skips: cur += 255.  *n_bytes = bytes written (bytes needed, with BMC_E_CAPACITY, if cap_bytes was too small;
+ * cap_bytes >= 1.1 x the expected number of accepted deals + 8 per 65 536 raw indices is safe).  Same sampling, same
+ * accepted set and tallies as bmc_sample_indices; bmc_unpack_indices (host, a format decoder) returns the 32-bit
+ * offsets, which bmc_expand turns into records.  At most 2^32 indices per call. */
+int bmc_sample_packed(bmc_ctx *ctx, const bmc_constraints *cons, uint64_t seed, uint64_t first_index, uint64_t n_raw,
+                      uint64_t n_accept_target, uint64_t wave, uint32_t tally_mask, uint8_t *bytes, uint64_t cap_bytes,
+                      uint64_t *n_bytes, bmc_tallies *tallies, bmc_stats *stats);
+int bmc_unpack_indices(const uint8_t *bytes, uint64_t n_bytes, uint32_t *offsets, uint64_t cap, uint64_t *n);
+
 /* One call, several GPUs of the box: devices[0..n_devices) each get a contiguous share of
  * [first_index, first_index + n_raw), one host thread and one internal context per device; the only exchange is the
  * sum of the tally buffers (device 0 reads its peers' buffers over NVLink when peer access is available, else the

@@ -634,3 +634,29 @@ def test_play_training_setup(engine):
     # longest-suit: later suits win ties (bridge.cl:3032 `>=`)
     h = [str2hand("♣ AKQ2 ♦ 432 ♥ 432 ♠ 432"), None, str2hand("♣ 43 ♦ 765 ♥ 8765 ♠ 8765"), None]
     assert training.longest_suit(*h) == "S"
+
+
+def test_packed_index_records_round_trip(engine):
+    """bmc_sample_packed / bmc_unpack_indices: the gap-byte stream decodes to exactly the offsets bmc_sample_indices
+    returns (same set, same tallies), for a sparse and a dense constraint, whole-range and accept-target jobs, small
+    waves (many chunks, gaps across tiles) and the 255-escape (rare constraint: gaps of thousands)."""
+    from bridge_mc_b200 import bidding
+    cons_1nt = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+    cons_rare = Constraints(None, [bidding.nt_responses(2).chooses((6, "NT")), None, bidding.openings.chooses((2, "NT")), None])
+    for cons, kw in ((cons_1nt, dict(n_raw=3_000_017, wave=1 << 20)), (None, dict(n_raw=200_003, wave=1 << 16)),
+                     (cons_rare, dict(n_raw=50_000_000, wave=1 << 24)), (cons_1nt, dict(n_accept=40_000, wave=1 << 18))):
+        offs, tal_a, st_a = engine.sample_indices(cons, seed=17, first_index=12345, cap=4_000_000, **kw)
+        packed, tal_b, st_b = engine.sample_packed(cons, seed=17, first_index=12345, cap_bytes=8_000_000, **kw)
+        got = engine.unpack_indices(packed)
+        assert st_a.accepted == st_b.accepted == got.size == offs.size and st_a.raw == st_b.raw
+        assert np.array_equal(np.sort(got), np.sort(offs))
+        assert tal_a["hcp"].tolist() == tal_b["hcp"].tolist()
+        if cons is cons_1nt and "n_raw" in kw:
+            assert packed.size < 1.15 * got.size                      # about one byte per accepted deal
+        if cons is cons_rare:
+            assert (packed == 255).any()                              # the skip byte is exercised
+    # too small a buffer is an error with the size needed, never a silent truncation
+    import ctypes as C
+    from bridge_mc_b200._lib import BridgeMcError
+    with pytest.raises(BridgeMcError):
+        engine.sample_packed(cons_1nt, n_raw=3_000_017, seed=17, cap_bytes=50_000)
