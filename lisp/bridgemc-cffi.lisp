@@ -492,3 +492,21 @@ RECORDS = foreign bmc-record array, TRUMP / DECLARER the same for every deal.  R
     (setf (cffi:mem-ref tr :int8) (trump-code trump) (cffi:mem-ref de :uint8) declarer)
     (with-gpu-call (bmc-check (bmc-best-tricks (bmc-ctx) records n tr de 0 0 tricks)))
     (loop for i from 0 below n collect (cffi:mem-aref tricks :uint8 i))))
+
+;;; ---- packed index records: about one byte per accepted deal on the way to the host ---------------------------------
+(cffi:defcfun "bmc_sample_packed" :int
+  (ctx :pointer) (cons :pointer) (seed :uint64) (first-index :uint64) (n-raw :uint64) (n-accept :uint64) (wave :uint64)
+  (tally-mask :uint32) (bytes :pointer) (cap-bytes :uint64) (n-bytes :pointer) (tallies :pointer) (stats :pointer))
+(cffi:defcfun "bmc_unpack_indices" :int
+  (bytes :pointer) (n-bytes :uint64) (offsets :pointer) (cap :uint64) (n :pointer))
+
+(defun sample-packed-offsets (handle seed first-index n-accept)
+  "N-ACCEPT deals of HANDLE as the offsets of their Philox indices from FIRST-INDEX (a list, chunk order): the deals
+cross the bus as gap bytes; `bmc_expand` regenerates records from offsets where they are needed."
+  (let* ((cap-bytes (+ (* 2 n-accept) (ash 1 20))) (cap (+ n-accept (ash n-accept -2) 4096)))
+    (cffi:with-foreign-objects ((bytes :uint8 cap-bytes) (nb :uint64) (offs :uint32 cap) (n :uint64)
+                                (tallies :uint64 +tally-words+) (stats '(:struct bmc-stats)))
+      (with-gpu-call
+        (bmc-check (bmc-sample-packed (bmc-ctx) handle seed first-index 0 n-accept 0 0 bytes cap-bytes nb tallies stats))
+        (bmc-check (bmc-unpack-indices bytes (cffi:mem-ref nb :uint64) offs cap n)))
+      (loop for i from 0 below (cffi:mem-ref n :uint64) collect (cffi:mem-aref offs :uint32 i)))))

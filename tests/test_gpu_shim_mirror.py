@@ -280,3 +280,33 @@ def test_play_deal_as_the_shim_calls_it(ctx):
     for i, r in enumerate(nt):
         if r["trump"] is None:
             assert tricks[i] == r["score"][1]
+
+
+def test_packed_offsets_as_the_shim_calls_them(ctx):
+    """lisp/bridgemc-cffi.lisp `sample-packed-offsets`: bmc_sample_packed with n_raw 0, an accept target, wave 0, tally mask 0,
+    then bmc_unpack_indices; the offsets expand to deals that satisfy the constraint."""
+    L, h = ctx
+    specs = (SeatSpec * 4)()
+    for k in range(4):
+        for f in ("hcp", "losers"):
+            getattr(specs[k], f)[0] = getattr(specs[k], f)[1] = -1
+        for s in range(4):
+            specs[k].len[s][0] = specs[k].len[s][1] = specs[k].suit_hcp[s][0] = specs[k].suit_hcp[s][1] = -1
+    specs[2].hcp[0], specs[2].hcp[1] = 20, 22
+    cons = C.c_void_p()
+    assert L.bmc_constraints_create(specs, None, C.byref(cons)) == 0
+    n_accept = 5000
+    cap_bytes, cap = 2 * n_accept + (1 << 20), n_accept + n_accept // 4 + 4096
+    buf = (C.c_uint8 * cap_bytes)()
+    nb, n = C.c_uint64(), C.c_uint64()
+    tallies, stats = _lib.Tallies(), Stats()
+    assert L.bmc_sample_packed(h, cons, 7, 1000, 0, n_accept, 0, 0, buf, cap_bytes, C.byref(nb), C.byref(tallies), C.byref(stats)) == 0
+    offs = (C.c_uint32 * cap)()
+    assert L.bmc_unpack_indices(buf, nb.value, offs, cap, C.byref(n)) == 0
+    assert n.value == stats.accepted >= n_accept
+    rec = (C.c_uint64 * (2 * n.value))()
+    assert L.bmc_expand(h, cons, 7, 1000, offs, n.value, rec) == 0
+    records = np.frombuffer(rec, dtype=np.uint64).reshape(-1, 2)
+    f = O.features_batch(seat_masks(records)[:, 2].copy()).reshape(-1, 11)
+    assert ((f[:, 8] >= 20) & (f[:, 8] <= 22)).all()
+    L.bmc_constraints_destroy(cons)
