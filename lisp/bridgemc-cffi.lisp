@@ -500,13 +500,14 @@ RECORDS = foreign bmc-record array, TRUMP / DECLARER the same for every deal.  R
 (cffi:defcfun "bmc_unpack_indices" :int
   (bytes :pointer) (n-bytes :uint64) (offsets :pointer) (cap :uint64) (n :pointer))
 
-(defun sample-packed-offsets (handle seed first-index n-accept)
-  "N-ACCEPT deals of HANDLE as the offsets of their Philox indices from FIRST-INDEX (a list, chunk order): the deals
-cross the bus as gap bytes; `bmc_expand` regenerates records from offsets where they are needed."
-  (let* ((cap-bytes (+ (* 2 n-accept) (ash 1 20))) (cap (+ n-accept (ash n-accept -2) 4096)))
+(defun sample-packed-offsets (handle seed first-index n-accept &key (wave 262144))
+  "N-ACCEPT deals of HANDLE (whole waves of WAVE indices until that many are accepted) as the offsets of their Philox
+indices from FIRST-INDEX (a list, chunk order): the deals cross the bus as gap bytes; `bmc_expand` regenerates records
+from offsets where they are needed."
+  (let* ((cap (+ n-accept wave)) (cap-bytes (+ (* 2 cap) (ash 1 16))))
     (cffi:with-foreign-objects ((bytes :uint8 cap-bytes) (nb :uint64) (offs :uint32 cap) (n :uint64)
                                 (tallies :uint64 +tally-words+) (stats '(:struct bmc-stats)))
       (with-gpu-call
-        (bmc-check (bmc-sample-packed (bmc-ctx) handle seed first-index 0 n-accept 0 0 bytes cap-bytes nb tallies stats))
+        (bmc-check (bmc-sample-packed (bmc-ctx) handle seed first-index 0 n-accept wave 0 bytes cap-bytes nb tallies stats))
         (bmc-check (bmc-unpack-indices bytes (cffi:mem-ref nb :uint64) offs cap n)))
       (loop for i from 0 below (cffi:mem-ref n :uint64) collect (cffi:mem-aref offs :uint32 i)))))

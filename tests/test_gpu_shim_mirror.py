@@ -283,8 +283,9 @@ def test_play_deal_as_the_shim_calls_it(ctx):
 
 
 def test_packed_offsets_as_the_shim_calls_them(ctx):
-    """lisp/bridgemc-cffi.lisp `sample-packed-offsets`: bmc_sample_packed with n_raw 0, an accept target, wave 0, tally mask 0,
-    then bmc_unpack_indices; the offsets expand to deals that satisfy the constraint."""
+    """lisp/bridgemc-cffi.lisp `sample-packed-offsets`: bmc_sample_packed with n_raw 0, an accept target, waves of 262 144,
+    tally mask 0, buffers sized for the target plus one whole wave, then bmc_unpack_indices; the offsets expand to deals
+    that satisfy the constraint."""
     L, h = ctx
     specs = (SeatSpec * 4)()
     for k in range(4):
@@ -295,12 +296,13 @@ def test_packed_offsets_as_the_shim_calls_them(ctx):
     specs[2].hcp[0], specs[2].hcp[1] = 20, 22
     cons = C.c_void_p()
     assert L.bmc_constraints_create(specs, None, C.byref(cons)) == 0
-    n_accept = 5000
-    cap_bytes, cap = 2 * n_accept + (1 << 20), n_accept + n_accept // 4 + 4096
+    n_accept, wave = 5000, 262144
+    cap = n_accept + wave
+    cap_bytes = 2 * cap + (1 << 16)
     buf = (C.c_uint8 * cap_bytes)()
     nb, n = C.c_uint64(), C.c_uint64()
     tallies, stats = _lib.Tallies(), Stats()
-    assert L.bmc_sample_packed(h, cons, 7, 1000, 0, n_accept, 0, 0, buf, cap_bytes, C.byref(nb), C.byref(tallies), C.byref(stats)) == 0
+    assert L.bmc_sample_packed(h, cons, 7, 1000, 0, n_accept, wave, 0, buf, cap_bytes, C.byref(nb), C.byref(tallies), C.byref(stats)) == 0
     offs = (C.c_uint32 * cap)()
     assert L.bmc_unpack_indices(buf, nb.value, offs, cap, C.byref(n)) == 0
     assert n.value == stats.accepted >= n_accept
