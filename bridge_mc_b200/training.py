@@ -3,11 +3,11 @@
 the trick estimator evaluate the four candidate contracts (N/S in their suit, N/S in no-trump, E/W in theirs, E/W in
 no-trump) and keep the best one for the drill.
 
-The deal comes from the library (`Deal.build`, bmc_sample).  The trick estimator is the reference's `play-deal`
-(bridge.cl:1488-2984), which this library does not contain: the caller passes it as
-`play_deal(trump, declarer, left, dummy, right) -> outcome` with `outcome.tricks` (declarer's line) and, for the
-drill's opening lead, `outcome.first_lead`; any object with those attributes will do.  The interactive card-by-card
-part (`manual-play`, reading cards from the terminal) stays where it is."""
+The deal comes from the library (`Deal.build`, bmc_sample) and the trick estimator is the reference's `play-deal`
+(bridge.cl:2961) on the GPU (`playdeal.play_deal`, bmc_play_hands).  A stand-in may be passed as
+`play_deal(trump, declarer, left, dummy, right) -> outcome` (an object with `score` = (defence, declaring line), or with
+a number in `tricks`).  The interactive card-by-card part (`manual-play`, reading cards from the terminal) stays where it
+is."""
 from __future__ import annotations
 
 from .cards import SUIT_SYMS
@@ -31,7 +31,9 @@ def longest_suit(*hands):
 
 def better_score(a, b) -> bool:
     """training.cl:3-4: `(> (second (score a)) (second (score b)))` -- more tricks for the declaring line"""
-    return a.tricks > b.tricks
+    def line_tricks(o):
+        return o.score[1] if hasattr(o, "score") else o.tricks
+    return line_tricks(a) > line_tricks(b)
 
 
 def drill_candidates(deal):
@@ -41,10 +43,16 @@ def drill_candidates(deal):
     return [(list(deal), ns), (list(deal), None), (roll(1, deal), we), (roll(1, deal), None)]
 
 
-def play_training(play_deal, dealgen: Deal | None = None):
+def play_training(play_deal=None, dealgen: Deal | None = None, engine=None):
     """training.cl:58-79 up to the point where the user starts playing: returns dict(deal, hands, trump, outcome, lead)
-    for the candidate the estimator likes best (the FIRST best one: `fold` only replaces on a strictly better score)."""
-    deal = (dealgen or full_random()).build()
+    for the candidate the estimator likes best (the FIRST best one: `fold` only replaces on a strictly better score).
+    lead = `(first (first (tricks outcome)))`, the card the drill opens with (training.cl:75)."""
+    if play_deal is None:
+        from . import playdeal
+
+        def play_deal(trump, *hands):
+            return playdeal.play_deal(trump, *hands, engine=engine)
+    deal = (dealgen or full_random(engine)).build()
     chosen = None
     for hands, trump in drill_candidates(deal):
         outcome = play_deal(trump, *hands)
@@ -52,4 +60,5 @@ def play_training(play_deal, dealgen: Deal | None = None):
             chosen = (hands, trump, outcome)
     hands, trump, outcome = chosen
     return {"deal": deal, "hands": hands, "dummy": hands[2], "hand": hands[0], "trump": trump, "outcome": outcome,
-            "lead": getattr(outcome, "first_lead", None)}
+            "lead": getattr(outcome, "first_lead", None) if not isinstance(getattr(outcome, "tricks", None), list)
+            else (outcome.tricks[0][0] if outcome.tricks else None)}

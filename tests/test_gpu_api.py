@@ -612,8 +612,8 @@ def test_auction_driver_kernel(engine):
 
 
 def test_play_training_setup(engine):
-    """training.cl:58-79 (a22): build + longest-suit x 2 + four estimator calls + better-score; the estimator is passed
-    in (play-deal is not part of the library) -- here a stand-in that counts the declaring line's HCP"""
+    """training.cl:58-79 (a22): build + longest-suit x 2 + four estimator calls + better-score, first with a stand-in
+    estimator that counts the declaring line's HCP (to pin the order of the calls), then with the library's play-deal"""
     from types import SimpleNamespace
     from bridge_mc_b200 import training
     calls = []
@@ -631,6 +631,13 @@ def test_play_training_setup(engine):
     best = max(range(4), key=lambda i: ([sum(max(r - 8, 0) for h in (c[0][0], c[0][2]) for s in h.suits for r in s) // 3
                                          + (1 if c[1] else 0) for c in training.drill_candidates(deal)][i], -i))
     assert (drill["hands"], drill["trump"]) == training.drill_candidates(deal)[best]
+    # the real estimator (bmc_play_hands): the chosen candidate has the most declarer tricks, the first one on ties
+    from bridge_mc_b200 import playdeal
+    real = training.play_training(dealgen=training.full_random(engine, seed=78), engine=engine)
+    outs = [playdeal.play_deal(t, *hs, engine=engine) for hs, t in training.drill_candidates(real["deal"])]
+    tr = [o.score[1] for o in outs]
+    assert real["outcome"].score[1] == max(tr) and (real["hands"], real["trump"]) == training.drill_candidates(real["deal"])[tr.index(max(tr))]
+    assert real["lead"] == real["outcome"].tricks[0][0]
     # longest-suit: later suits win ties (bridge.cl:3032 `>=`)
     h = [str2hand("♣ AKQ2 ♦ 432 ♥ 432 ♠ 432"), None, str2hand("♣ 43 ♦ 765 ♥ 8765 ♠ 8765"), None]
     assert training.longest_suit(*h) == "S"
