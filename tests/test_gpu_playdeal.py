@@ -107,3 +107,21 @@ def test_arena_overflow_is_reported_not_silent(engine):
     assert (out["status"] == 1).any() and (out["n_tricks"][out["status"] != 0] == 0).all()
     ok = engine.play_hands(hands, -1)
     assert (ok["status"] == 0).all()
+
+
+def test_edge_cases_follow_the_reference(engine):
+    """hands of unequal size: the reference signals a Lisp error when an empty hand has to play (status 2); a longer
+    declarer hand just keeps its extra card; four empty hands: play-deal returns nil (status 4) -- as the oracle does"""
+    from oracle import playdeal as P
+    cases = [[[[0], [], [], []], [[], [], [], []], [[1], [], [], []], [[2], [], [], []]],
+             [[[0, 1], [], [], []], [[2], [], [], []], [[3], [], [], []], [[4], [], [], []]],
+             [[[], [], [], []]] * 4]
+    out = engine.play_hands(np.array([[lane_mask(h) for h in hs] for hs in cases], dtype=np.uint64), -1)
+    assert out["status"].tolist() == [2, 0, 4]
+    with pytest.raises(P.LispError):
+        P.play_deal(None, *[P.Hand(h, id=i) for i, h in enumerate(cases[0])])
+    ref = P.play_deal(None, *[P.Hand(h, id=i) for i, h in enumerate(cases[1])])
+    tricks, wno, score = decode(out[1])
+    assert tricks == ref.tricks and score == ref.score
+    assert P.play_deal(None, *[P.Hand(h, id=i) for i, h in enumerate(cases[2])]) is None
+    assert engine.play_hands(np.empty((0, 4), dtype=np.uint64), -1).size == 0
