@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-deals", type=int, default=1500, help="reference arm: builds per thread per step")
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 full deal, 2 seat-first (bmc_constraints_set_mode)")
+    ap.add_argument("--workload", default="c2", help="c2 (the headline) or n1: the trick-estimator pipeline, one GPU")
+    ap.add_argument("--n1-deals", type=int, default=32768)
     return ap.parse_args()
 
 
@@ -499,10 +501,41 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_n1(args):
+    """C2 sample -> play-deal -> base-score (tools/run_playdeal.py), with the CPU restatement of the
+    reference's list algorithm (oracle/playdeal.py, the `port`) timed beside it on a bounded sample of the same deals."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import run_playdeal
+    res, rec, tricks = run_playdeal.run(args.n1_deals, with_host_build=not args.no_cpu_baseline)
+    line = {"metric": "play-deal deals/sec (C2 sample -> trick estimator in no trump, South declares -> base-score)",
+            "value": res["deals_per_s"], "unit": "deals/s", "n_gpus": 1, "steps": 1, "warmup": 1,
+            "ms_per_step": res["play_deal_kernel_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": {"workload": res["config"], "deals": res["deals"]},
+            "roofline": {"bound": "instruction fetch (no applicable HBM / tensor roofline): see profiles/r02_prof_playdeal_final.txt",
+                         "achieved": None, "peak": None, "frac": None, "traffic": None},
+            "result": {k: res[k] for k in ("status_counts", "tricks_hist", "mean_tricks", "p_3nt_makes", "mean_score")},
+            "cpu_same_algorithm_one_core": res.get("cpu_same_algorithm_one_core")}
+    if not args.no_cpu_baseline:
+        from bridge_mc_b200 import cards
+        from oracle import playdeal as P                      # the checker, as the CPU baseline: bench.py only
+        masks = cards.seat_masks(rec[:8])
+        k, t0 = 6, time.perf_counter()
+        for i in range(k):
+            hs = [P.Hand([[r for r in range(13) if (int(masks[i, (2 + j) % 4]) >> (16 * s + r)) & 1] for s in range(4)], id=j) for j in range(4)]
+            assert P.play_deal(None, *hs).score[1] == tricks[i], "the oracle disagrees with the GPU"
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": k / dt, "unit": "deals/s", "cores": 1, "kind": "port",
+                                "sample": f"{k} of the same deals by oracle/playdeal.py, the reference's list algorithm restated in "
+                                          "Python (the reference's own Lisp under oracle/minilisp.py: 75 s per deal on the build box)"}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "n1":
+        run_n1(args)
     else:
         run_gpu(args)
 
