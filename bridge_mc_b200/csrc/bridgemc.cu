@@ -2604,10 +2604,14 @@ static int pd_blocks_per_sm()
 static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_hands4, uint64_t n, const int8_t *d_trump,
                             const uint8_t *d_declarer, int per_deal, uint32_t arena_kb, void *d_out)
 {
-    // arena_kb = 0: 256 KB per deal in the first pass (99 % of random deals need less), and the deals that outgrow it
-    // are played again with 8 MB each; an explicit arena_kb is used as it is, without a retry
+    // arena_kb = 0: 1 MB per resident deal in the first pass (2.4 GB of HBM for 148 x 16 deals; the largest of 3 000
+    // random deals needs 0.5 MB), and the deals that outgrow it are played again with 8 MB each -- a second, nearly empty
+    // launch, which is why the first pass is sized to make it rare; an explicit arena_kb is used as it is, without a retry
     const bool adaptive = arena_kb == 0;
-    const uint64_t arena = (uint64_t)(adaptive ? 256u : arena_kb) * 1024u;
+    const char *env_kb = getenv("BMC_PD_ARENA_KB");
+    const uint32_t first_kb = env_kb && atoi(env_kb) >= 16 ? (uint32_t)atoi(env_kb) : 1024u;
+    const int timing = getenv("BMC_PD_TIMING") != nullptr;
+    const uint64_t arena = (uint64_t)(adaptive ? first_kb : arena_kb) * 1024u;
     if (arena > (1ull << 31)) return fail(BMC_E_INVALID, "bmc_play_deal: arena_kb too large");
     if (n > 0xFFFFFFFFull) return fail(BMC_E_INVALID, "bmc_play_deal: more than 2^32 - 1 deals in one call");
     constexpr int PD_WARPS = bmc_pd::WARPS;
@@ -2634,7 +2638,7 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
         blocks = (blocks + 1) / 2;
     }
     bmc_pd::launch((unsigned)blocks, ctx->stream, d_records, d_hands4, nullptr, n, d_trump, d_declarer, per_deal, ctx->d_arena,
-                   (uint32_t)arena, d_out, d_next);
+                   (uint32_t)arena, d_out, d_next, timing);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && adaptive) {
@@ -2662,7 +2666,7 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
             if (b2 > want) b2 = want;
             if (b2 > max_blocks) b2 = max_blocks;
             bmc_pd::launch((unsigned)b2, ctx->stream, d_records, d_hands4, d_idx, h_cnt, d_trump, d_declarer, per_deal, ctx->d_arena,
-                           (uint32_t)big, d_out, d_next + 1);
+                           (uint32_t)big, d_out, d_next + 1, timing);
             ctx->launches++;
             e = cudaGetLastError();
         }

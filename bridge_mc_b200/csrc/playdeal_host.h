@@ -10,7 +10,7 @@ cudaError_t configure(int *blocks_per_sm);
 // idx == nullptr: deals 0..n-1; else the n deals idx[0..n)
 void launch(unsigned blocks, cudaStream_t stream, const void *d_records, const void *d_hands4, const unsigned int *d_idx, uint64_t n,
             const int8_t *d_trump, const uint8_t *d_declarer, int per_deal, uint8_t *d_arenas, uint32_t arena_bytes, void *d_out,
-            unsigned long long *d_next);
+            unsigned long long *d_next, int timing);
 // idx / count of the deals whose status is 1 (arena outgrown)
 void launch_failed(cudaStream_t stream, const void *d_out, uint64_t n, unsigned int *d_idx, unsigned int *d_count);
 }

@@ -11,8 +11,9 @@ namespace {
 
 __device__ __noinline__ void play_one_deal(const uint4 *records, const unsigned long long *hands4, unsigned long long i, const int8_t *trump,
                                            const uint8_t *declarer, int per_deal, uint8_t *arena, uint32_t arena_bytes, pd::Scratch &S,
-                                           bmc_play_result *out)
+                                           bmc_play_result *out, int timing)
 {
+    const long long t0 = timing ? clock64() : 0ll;
     const int tr = trump[per_deal ? i : 0];
     pd::Hand h[4];
     if (records) {
@@ -40,7 +41,10 @@ __device__ __noinline__ void play_one_deal(const uint4 *records, const unsigned 
         for (int c = 0; c < 4; ++c) o.cards[t][c] = t < res.n ? res.tricks[t][c] : 0xFF;
         o.winner[t] = t < res.n ? res.wno[t] : 0xFF;
     }
-    o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
+    // diagnostic (BMC_PD_TIMING=1): SM cycles spent on this deal, in units of 4096, 24 bits little endian; else zero
+    const unsigned long long dt = timing ? (unsigned long long)(clock64() - t0) >> 12 : 0ull;
+    const unsigned int d24 = dt > 0xFFFFFFull ? 0xFFFFFFu : (unsigned int)dt;
+    o.reserved[0] = (uint8_t)d24; o.reserved[1] = (uint8_t)(d24 >> 8); o.reserved[2] = (uint8_t)(d24 >> 16);
     out[i] = o;
 }
 
@@ -52,7 +56,7 @@ __device__ __noinline__ void play_one_deal(const uint4 *records, const unsigned 
 __global__ void __launch_bounds__(bmc_pd::THREADS) play_deal_kernel(const uint4 *records, const unsigned long long *hands4, const unsigned int *idx,
                                                                       unsigned long long n, const int8_t *trump, const uint8_t *declarer,
                                                                       int per_deal, uint8_t *arenas, uint32_t arena_bytes, bmc_play_result *out,
-                                                                      unsigned long long *next)
+                                                                      unsigned long long *next, int timing)
 {
     extern __shared__ __align__(16) unsigned char pd_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(bmc_pd::THREADS) play_deal_kernel(const uint4 
         if (lane == 0) k = atomicAdd(next, 1ull);
         k = __shfl_sync(0xFFFFFFFFu, k, 0);
         if (k >= n) break;
-        play_one_deal(records, hands4, idx ? idx[k] : k, trump, declarer, per_deal, arena, arena_bytes, S, out);
+        play_one_deal(records, hands4, idx ? idx[k] : k, trump, declarer, per_deal, arena, arena_bytes, S, out, timing);
         __syncwarp();
     }
 }
@@ -89,11 +93,11 @@ cudaError_t configure(int *blocks_per_sm)
 
 void launch(unsigned blocks, cudaStream_t stream, const void *d_records, const void *d_hands4, const unsigned int *d_idx, uint64_t n,
             const int8_t *d_trump, const uint8_t *d_declarer, int per_deal, uint8_t *d_arenas, uint32_t arena_bytes, void *d_out,
-            unsigned long long *d_next)
+            unsigned long long *d_next, int timing)
 {
     play_deal_kernel<<<blocks, THREADS, WARPS * sizeof(pd::Scratch), stream>>>(
         reinterpret_cast<const uint4 *>(d_records), reinterpret_cast<const unsigned long long *>(d_hands4), d_idx, n, d_trump, d_declarer,
-        per_deal, d_arenas, arena_bytes, reinterpret_cast<bmc_play_result *>(d_out), d_next);
+        per_deal, d_arenas, arena_bytes, reinterpret_cast<bmc_play_result *>(d_out), d_next, timing);
 }
 
 void launch_failed(cudaStream_t stream, const void *d_out, uint64_t n, unsigned int *d_idx, unsigned int *d_count)

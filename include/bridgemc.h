@@ -367,8 +367,9 @@ typedef struct {
 } bmc_play_result;   /* 72 bytes */
 /* One GPU thread plays one deal.  trump[i] in {-1 (no trump), 0..3 = c d h s}; declarer[i] = seat 0..3 (N E S W);
  * the left-hand opponent (seat + 1) leads.  per_deal = 0: trump[0] / declarer[0] apply to every deal.
- * arena_kb: per-deal scratch for the route lists; 0 = adaptive: 256 KB in a first pass, and the deals that outgrow
- * it (about 1 % of random deals) are played again with 8 MB each.  `bmc_play_deal` takes host buffers,
+ * arena_kb: per-deal scratch for the route lists; 0 = adaptive: 1 MB per resident deal in a first pass (environment
+ * BMC_PD_ARENA_KB overrides), and the rare deals that outgrow it are played again with 8 MB each.  `reserved` is zero
+ * unless BMC_PD_TIMING is set (diagnostic: SM cycles spent on the deal / 4096, 24 bits little endian).  `bmc_play_deal` takes host buffers,
  * `bmc_play_deal_dev` device pointers (no copies; runs on the context's stream and synchronises it). */
 int bmc_play_deal(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const int8_t *trump, const uint8_t *declarer,
                   int per_deal, uint32_t arena_kb, bmc_play_result *out);

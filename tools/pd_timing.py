@@ -1,0 +1,42 @@
+"""Diagnostic: per-deal device time of the trick estimator (BMC_PD_TIMING=1) on the N1 sample, for two first-pass arena
+sizes.  python tools/pd_timing.py [n] -> gpurun_out/pd_timing.npz + one JSON line."""
+import json
+import os
+import sys
+
+os.environ["BMC_PD_TIMING"] = "1"
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bridge_mc_b200 import _lib, bidding  # noqa: E402
+from bridge_mc_b200.engine import Constraints, Engine  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+eng = Engine(0)
+eng.set_stream(torch.cuda.current_stream().cuda_stream)
+cons = Constraints(None, [None, None, bidding.openings.form((1, "NT")), None])
+rec, tal, stats = eng.sample(cons, n_raw=int(n / 0.038133), seed=11)
+rec = np.ascontiguousarray(rec[np.lexsort((rec[:, 0], rec[:, 1]))])
+n = rec.shape[0]
+d_rec = torch.from_numpy(rec.view(np.int64).copy()).cuda()
+d_out = torch.empty(n * 72, dtype=torch.uint8, device="cuda")
+d_t = torch.tensor([-1], dtype=torch.int8, device="cuda")
+d_d = torch.tensor([2], dtype=torch.uint8, device="cuda")
+eng.play_deal_dev(d_rec.data_ptr(), min(n, 2048), d_t.data_ptr(), d_d.data_ptr(), False, d_out.data_ptr())
+res = {"deals": n}
+for kb in (sys.argv[2:] or ["256", "1024"]):
+    os.environ["BMC_PD_ARENA_KB"] = kb
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.play_deal_dev(d_rec.data_ptr(), n, d_t.data_ptr(), d_d.data_ptr(), False, d_out.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy().view(_lib.PLAY_DTYPE)
+    cyc = (out["reserved"].astype(np.uint32) * np.array([1, 256, 65536], dtype=np.uint32)).sum(axis=1).astype(np.float64) * 4096
+    res[f"arena_{kb}kb"] = {"ms": e0.elapsed_time(e1), "deals_per_s": n / e0.elapsed_time(e1) * 1e3, "status": np.bincount(out["status"], minlength=5).tolist(),
+                            "sum_cycles": float(cyc.sum()), "max_cycles": float(cyc.max()), "mean_cycles": float(cyc.mean()),
+                            "p99_cycles": float(np.percentile(cyc, 99))}
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"pd_timing_{kb}.npz"), rec=rec, cyc=cyc, status=out["status"], tricks=out["score"][:, 1])
+print(json.dumps(res))
