@@ -413,19 +413,165 @@ PD_HDN void outcome_add(Ctx &cx, Outcome &self, const Outcome &other, bool star)
 }
 PD_HD bool outcome_won(const Outcome &o) { return o.n > 0 && (o.wno[0] & 1) == 0; }
 
-// simple-trick (2269-2277)
+// simple-trick (2269-2277).  This is the estimator's inner loop (18 000 calls per deal): the trick is kept in REGISTERS
+// (`TrickR`) and the four plays run through one rolled loop that holds a single inlined copy of beat-or-low and of
+// finesse-if-possible -- a third of the instructions and half of the code of four calls on a `Trick` in memory, which
+// is what the colder callers (hunt-card, reproduce) still use.  Same decisions, statement by statement.
+struct TrickR {
+    int suit, trump, hsuit, hrank, winner, n;
+    uint32_t cards;              // card i in byte i
+    uint64_t rem0, rem1, rem2, rem3;    // the hands after each play: scalars, so that they stay in registers
+};
+PD_HD uint32_t hsuit_of(uint64_t h, int suit) { return (uint32_t)(h >> (16 * suit)) & 0x1FFFu; }
+PD_HD bool winnerp_r(const TrickR &t) { return t.winner >= 0 && (t.n & 1) == (t.winner & 1); }
+PD_HD void play_r(TrickR &t, int psuit, int prank, uint64_t hand)
+{
+    const bool atr = psuit == t.trump, as = psuit == t.suit, btr = t.hsuit == t.trump, bs = t.hsuit == t.suit;
+    bool higher;                                                     // card-higher (1556-1570)
+    if (atr != btr) higher = atr;
+    else if (as != bs) higher = as;
+    else if (!(as || atr)) higher = false;
+    else if (!(bs || btr)) higher = true;
+    else higher = prank > t.hrank;
+    if (higher) { t.hsuit = psuit; t.hrank = prank; t.winner = t.n; }
+    const uint64_t rest = hand & ~(1ull << (16 * psuit + prank));
+    t.rem0 = t.n == 0 ? rest : t.rem0; t.rem1 = t.n == 1 ? rest : t.rem1;
+    t.rem2 = t.n == 2 ? rest : t.rem2; t.rem3 = t.n == 3 ? rest : t.rem3;
+    t.cards |= (uint32_t)mk(psuit, prank) << (8 * t.n);
+    ++t.n;
+}
+// weak-suit (1732-1768) on a hand word
+PD_HD int weak_suit_r(uint64_t h, const TrickR &t)
+{
+    int acc = -1;
+    PD_ROLLED
+    for (int suit = 0; suit < 4; ++suit) {
+        const uint32_t cards = hsuit_of(h, suit);
+        if (!cards) continue;
+        if (acc < 0) { acc = suit; continue; }
+        const uint32_t accards = hsuit_of(h, acc);
+        if (suit == t.trump) continue;
+        const bool hon = (cards >> 9) != 0, acchon = (accards >> 9) != 0;
+        if (acc == t.trump) { acc = suit; continue; }
+        if (!hon && !acchon) { if (popc(cards) < popc(accards)) acc = suit; continue; }
+        if (!hon) { acc = suit; continue; }
+        if (!acchon) continue;
+        int na = 0, nb = 0;
+        const int ha = highbit(cards), hb = highbit(accards);
+        if (t.n > 0) { na += popc(above(hsuit_of(t.rem0, suit), ha)); nb += popc(above(hsuit_of(t.rem0, acc), hb)); }
+        if (t.n > 1) { na += popc(above(hsuit_of(t.rem1, suit), ha)); nb += popc(above(hsuit_of(t.rem1, acc), hb)); }
+        if (t.n > 2) { na += popc(above(hsuit_of(t.rem2, suit), ha)); nb += popc(above(hsuit_of(t.rem2, acc), hb)); }
+        if (t.n > 3) { na += popc(above(hsuit_of(t.rem3, suit), ha)); nb += popc(above(hsuit_of(t.rem3, acc), hb)); }
+        const int buf_a = popc(cards) - na, buf_b = popc(accards) - nb;
+        if (buf_a == buf_b) { if (lowbit(cards) < lowbit(accards)) acc = suit; }
+        else if ((buf_a > 0 && buf_b > 0) || (buf_a < 0 && buf_b < 0)) { if (buf_a > buf_b) acc = suit; }
+        else if (buf_a > 0) acc = suit;
+    }
+    return acc;
+}
+// the discard both routines end with: lowest card of the weak suit ((nth nil suits) is a Lisp error)
+PD_HD void discard_r(Ctx &cx, const TrickR &t, uint64_t h, int &ps, int &pr)
+{
+    const int ws = weak_suit_r(h, t);
+    if (ws < 0) { fail(cx, PD_E_LISP); return; }
+    const uint32_t m = hsuit_of(h, ws);
+    if (m) { ps = ws; pr = lowbit(m); }
+}
+PD_HD void lowest_r(uint64_t h, int suit, int &ps, int &pr)
+{
+    const uint32_t m = hsuit_of(h, suit);
+    if (m) { ps = suit; pr = lowbit(m); }
+}
+// beat-or-low (1804-1834) up to its last resort, the discard: which card; -1 = none
+PD_HD void beat_or_low_r(Ctx &cx, const TrickR &t, uint64_t h, bool use_highest, int &ps, int &pr)
+{
+    const int suit = t.suit, trump = t.trump, hsuit = t.hsuit, hrank = t.hrank;
+    const bool wp = winnerp_r(t);
+    ps = pr = -1;
+    if (hsuit >= 0 && hsuit == trump && suit != trump) {
+        if (suit < 0) fail(cx, PD_E_LISP); else lowest_r(h, suit, ps, pr);
+        if (pr < 0 && !wp) { const int r = ch_first_above(hsuit_of(h, trump), hrank); if (r >= 0) { ps = trump; pr = r; } }
+    } else {
+        const bool follow = hsuit >= 0 && hsuit == suit;
+        if (!follow && suit < 0) { fail(cx, PD_E_LISP); return; }
+        const uint32_t m = hsuit_of(h, suit);
+        if (m) {
+            int r = -1;
+            if (!follow || !wp) r = ch_take_higher(m, follow ? hrank : -1, use_highest);
+            ps = suit; pr = r < 0 ? lowbit(m) : r;
+        }
+        if (pr < 0 && trump >= 0) lowest_r(h, trump, ps, pr);
+    }
+    // the caller discards when nothing was picked (and then tries the lowest trump)
+}
+// finesse-if-possible (1905-1947) up to its last resort, the discard: which card; -1 = none
+PD_HD void finesse_r(Ctx &cx, const TrickR &t, uint64_t h1, uint64_t h2, int &ps, int &pr)
+{
+    const int suit = t.suit, trump = t.trump;
+    ps = pr = -1;
+    if (suit < 0) { fail(cx, PD_E_LISP); return; }
+    const bool wp = winnerp_r(t);
+    const int hsuit = wp ? -1 : t.hsuit, hrank = wp ? -1 : t.hrank;
+    const uint32_t h2suit = hsuit_of(h2, suit);
+    bool trump_clause = false;
+    if (hsuit >= 0 && hsuit == trump && trump != suit) {
+        lowest_r(h1, suit, ps, pr);
+        if (pr < 0) {
+            int over = hrank;
+            if (!(h2suit && suit != trump)) { const uint32_t h2t = hsuit_of(h2, trump); const int h2max = h2t ? highbit(h2t) : -1; if (h2max > over) over = h2max; }
+            const int r = ch_first_above(hsuit_of(h1, trump), over);
+            if (r >= 0) { ps = trump; pr = r; }
+        }
+    } else {
+        const bool follow = hsuit >= 0 && hsuit == suit;
+        const uint32_t m = hsuit_of(h1, suit);
+        if (m) {
+            int r = -1;
+            if (h2suit) { const int h2max = highbit(h2suit); r = ch_first_above(m, follow && hrank > h2max ? hrank : h2max); }
+            if (r < 0 && follow) r = ch_first_above(m, hrank);
+            ps = suit; pr = r < 0 ? lowbit(m) : r;
+        }
+        trump_clause = true;
+    }
+    if (pr < 0 && trump_clause && trump >= 0) {
+        const uint32_t h2t = hsuit_of(h2, trump);
+        if (!h2suit && h2t) { const int r = ch_first_above(hsuit_of(h1, trump), highbit(h2t)); if (r >= 0) { ps = trump; pr = r; } }
+        else if (!wp) lowest_r(h1, trump, ps, pr);
+    }
+    // the caller discards when nothing was picked
+}
+
 PD_HDN void simple_trick(Ctx &cx, Outcome &o, int suit, const Hand *h, bool use_highest)
 {
     if (h[0].s[suit] == 0) { outcome_empty(o, h); return; }
-    TmpFrame tf(cx);
-    Trick &t = *tmp<Trick>(cx);
-    trick_init(t, suit, cx.trump);
-    beat_or_low(cx, t, h[0], use_highest);
-    if (beats(h[3], h[2], suit, cx.trump)) beat_or_low(cx, t, h[1], false);
-    else finesse_if_possible(cx, t, h[1], h[2]);
-    finesse_if_possible(cx, t, h[2], h[3]);
-    beat_or_low(cx, t, h[3], false);
-    outcome_of_trick(cx, o, t);
+    TrickR t;
+    t.suit = suit; t.trump = cx.trump; t.hsuit = suit; t.hrank = -1; t.winner = -1; t.n = 0; t.cards = 0;
+    t.rem0 = t.rem1 = t.rem2 = t.rem3 = 0;
+    const bool cover = beats(h[3], h[2], suit, cx.trump);            // second hand: beat-or-low instead of a finesse
+    PD_ROLLED
+    for (int pos = 0; pos < 4; ++pos) {
+        const uint64_t hand = h[pos].s.m;
+        int ps, pr;
+        const bool fin = pos == 2 || (pos == 1 && !cover);
+        if (fin) finesse_r(cx, t, hand, h[(pos + 1) & 3].s.m, ps, pr);
+        else beat_or_low_r(cx, t, hand, pos == 0 && use_highest, ps, pr);
+        if (pr < 0 && !cx.status) {                                  // both end with a discard from the weak suit
+            discard_r(cx, t, hand, ps, pr);
+            if (pr < 0 && !fin && t.trump >= 0) lowest_r(hand, t.trump, ps, pr);
+        }
+        if (pr >= 0) play_r(t, ps, pr, hand);
+    }
+    // new-outcome of the finished trick (2204-2210)
+    if (t.winner < 0 || t.n != 4) { fail(cx, PD_E_LISP); outcome_nil(o); return; }
+    o.valid = 1; o.n = 1; o.roll = (uint8_t)t.winner;
+    o.score[0] = (t.winner & 1) ? 0 : 1; o.score[1] = (t.winner & 1) ? 1 : 0;
+    o.tricks[0] = t.cards;
+    o.wno[0] = (uint8_t)t.winner;
+    {                                                                // (roll (- winner) remaining)
+        const bool by2 = (t.winner & 2) != 0, by1 = (t.winner & 1) != 0;
+        const uint64_t a0 = by2 ? t.rem2 : t.rem0, a1 = by2 ? t.rem3 : t.rem1, a2 = by2 ? t.rem0 : t.rem2, a3 = by2 ? t.rem1 : t.rem3;
+        o.rem[0].s.m = by1 ? a1 : a0; o.rem[1].s.m = by1 ? a2 : a1; o.rem[2].s.m = by1 ? a3 : a2; o.rem[3].s.m = by1 ? a0 : a3;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -704,6 +850,24 @@ PD_HDN void reproduce(Ctx &cx, uint32_t route, const Hand *hands, Outcome &ans)
     for (;;) {
         Route *r = at<Route>(cx, route);
         if (r->len == 0 || cx.status) { outcome_nil(ans); return; }
+#if defined(__CUDA_ARCH__)
+        // 99.6 % of the pops drop a copy of a trick that has failed already: 32 tricks per step, one per lane, up to the
+        // first one not seen yet (every lane pops the same count, so the route record stays identical across the lanes)
+        uint32_t base;
+        {
+            const uint32_t len = r->len, list = r->tricks, mine = len > (uint32_t)PD_LANE ? at<uint32_t>(cx, list)[PD_LANE] : 0u;
+            bool fresh = len > (uint32_t)PD_LANE;
+            PD_ROLLED
+            for (int i = 0; i < ntried && fresh; ++i) fresh = tried[i] != mine;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, fresh);
+            const uint32_t drop = bal ? (uint32_t)__ffs((int)bal) : (len < 32u ? len : 32u);     // tricks popped, the fresh one included
+            base = __shfl_sync(0xFFFFFFFFu, mine, bal ? (int)drop - 1 : 0);
+            r->tricks = list + 4u * drop; r->len = len - drop;           // every lane stores the same values
+            __syncwarp();
+            if (!bal) continue;
+            if (ntried < NTRIED) tried[ntried++] = base;
+        }
+#else
         const uint32_t base = at<uint32_t>(cx, r->tricks)[0];
         r->tricks += 4; r->len -= 1;
         {
@@ -713,6 +877,7 @@ PD_HDN void reproduce(Ctx &cx, uint32_t route, const Hand *hands, Outcome &ans)
             if (seen) continue;
             if (ntried < NTRIED) tried[ntried++] = base;
         }
+#endif
         Card ref[4];
         PD_ROLLED
         for (int i = 0; i < 4; ++i) ref[i] = tcard(base, i);
