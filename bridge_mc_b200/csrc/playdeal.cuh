@@ -624,6 +624,47 @@ PD_HDN void best_update(SearchFrame &f, const Outcome &val)
     if (!f.best.valid || (val.valid && f.best.score[0] < val.score[0])) outcome_copy(f.best, val);
 }
 
+// The two exhaustive look-aheads (PLAY_THROUGH, SUIT_TOPS) reach the same four hands along many orders of play -- ten
+// frames for every distinct position, and with them more than half of all simple-tricks of a deal -- and the value of a
+// frame is a function of its hands alone (same suit, same trump, no state outside the frame).  Each such search
+// therefore keeps the values of the positions it has finished, keyed by the four hand words, in the arena: a chained
+// hash table that lives as long as the call.
+struct MemoEntry { uint64_t key[4]; uint32_t next; uint32_t pad[3]; Outcome val; };
+constexpr uint32_t MEMO_BUCKETS = 256;
+PD_HD uint32_t memo_bucket(const Hand *h)
+{
+    uint64_t x = h[0].s.m ^ (h[1].s.m << 13 | h[1].s.m >> 51) ^ (h[2].s.m << 29 | h[2].s.m >> 35) ^ (h[3].s.m << 43 | h[3].s.m >> 21);
+    x *= 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(x >> 56) & (MEMO_BUCKETS - 1u);
+}
+PD_HDN const Outcome *memo_find(Ctx &cx, uint32_t buckets, const Hand *h)
+{
+    uint32_t e = at<uint32_t>(cx, buckets)[memo_bucket(h)];
+    PD_ROLLED
+    while (e) {
+        const MemoEntry *m = at<MemoEntry>(cx, e);
+        if (m->key[0] == h[0].s.m && m->key[1] == h[1].s.m && m->key[2] == h[2].s.m && m->key[3] == h[3].s.m) return &m->val;
+        e = m->next;
+    }
+    return nullptr;
+}
+PD_HDN void memo_put(Ctx &cx, uint32_t buckets, const Hand *h, const Outcome &val)
+{
+    const uint32_t pad = (16u - (cx.top & 15u)) & 15u;
+    const uint32_t raw = arena_alloc(cx, (uint32_t)sizeof(MemoEntry) + pad);
+    if (cx.status) return;
+    const uint32_t off = raw + pad;
+    MemoEntry *m = at<MemoEntry>(cx, off);
+    uint32_t *head = at<uint32_t>(cx, buckets) + memo_bucket(h);
+    PD_ROLLED
+    for (int i = 0; i < 4; ++i) m->key[i] = h[i].s.m;
+    m->next = *head;
+    outcome_copy(m->val, val);
+    PD_SYNC();
+    *head = off;
+    PD_SYNC();
+}
+
 // `stack`: MAXD frames in the caller's local memory
 PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int nsuits, const Hand *hands, SearchFrame *stack, Outcome &result)
 {
@@ -631,6 +672,17 @@ PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int 
     Hand *hs = tmp<Hand>(cx, 4);
     Outcome &cand = *tmp<Outcome>(cx);
     int sp = 0;
+    const bool memo = kind != IMMEDIATE;
+    const uint32_t mark = cx.top;
+    uint32_t buckets = 0;
+    if (memo) {
+        buckets = arena_alloc(cx, MEMO_BUCKETS * 4u);
+        if (cx.status) { outcome_nil(result); return; }
+        uint32_t *b = at<uint32_t>(cx, buckets);
+        PD_ROLLED
+        for (uint32_t i = PD_LANE; i < MEMO_BUCKETS; i += PD_LANES) b[i] = 0u;
+        PD_SYNC();
+    }
     auto open = [&](SearchFrame &f, const Hand *h) {
         PD_ROLLED
         for (int i = 0; i < 4; ++i) f.hands[i] = h[i];
@@ -647,7 +699,8 @@ PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int 
             Outcome &val = f.best;
             if (kind == SUIT_TOPS && !val.valid) outcome_empty(val, f.hands);
             if (kind == PLAY_THROUGH && !f.have_best) outcome_empty(val, f.hands);
-            if (sp == 0) { outcome_copy(result, val); return; }
+            if (sp == 0) { outcome_copy(result, val); cx.top = mark; return; }
+            if (memo) memo_put(cx, buckets, f.hands, val);
             SearchFrame &p = stack[sp - 1];
             outcome_add(cx, p.cur, val, false);          // (add-outcome self (apply if-won remaining))
             best_update(p, p.cur);
@@ -659,6 +712,10 @@ PD_HDN void search(Ctx &cx, SearchKind kind, int suit, const int8_t *suits, int 
         simple_trick(cx, f.cur, o.suit, hs, o.top != 0);
         const bool follow = f.cur.n > 0 && (kind == PLAY_THROUGH || outcome_won(f.cur));
         if (follow) {
+            if (memo) {
+                const Outcome *known = memo_find(cx, buckets, f.cur.rem);
+                if (known) { outcome_add(cx, f.cur, *known, false); best_update(f, f.cur); continue; }
+            }
             if (sp + 1 >= MAXD) { fail(cx, PD_E_CAP); outcome_nil(result); return; }
             ++sp;
             open(stack[sp], f.cur.rem);
