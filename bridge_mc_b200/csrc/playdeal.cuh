@@ -45,6 +45,18 @@
 #define PD_SYNC() ((void)0)
 #endif
 
+// -DPD_PROFILE (diagnostic builds only): SM cycles per phase of a deal, summed over the deals of a launch
+#if defined(PD_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long g_pd_prof[8];
+#endif
+#if defined(PD_PROFILE) && defined(__CUDA_ARCH__)
+#define PD_PROF_T0() long long pd_prof_t0 = clock64()
+#define PD_PROF_ADD(slot) do { const long long pd_now = clock64(); if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_pd_prof[slot], (unsigned long long)(pd_now - pd_prof_t0)); pd_prof_t0 = pd_now; } while (0)
+#else
+#define PD_PROF_T0() ((void)0)
+#define PD_PROF_ADD(slot) ((void)0)
+#endif
+
 namespace pd {
 
 typedef uint8_t Card;
@@ -838,7 +850,9 @@ struct Route {                   // play-route; lives in the arena, identity = i
     uint8_t pad;
     uint32_t tricks;             // arena offset of len packed tricks
     uint32_t len;
-};
+    uint32_t mlo, mhi;           // bit cidx(c) for every card c that leads or is third in a trick of the route -- or was,
+};                               // before tricks were dropped (a superset): first-pass skips routes the cards played miss
+PD_HD uint64_t route_mask(const Route &r) { return (uint64_t)r.mlo | ((uint64_t)r.mhi << 32); }
 struct Com {                     // play-com
     uint8_t zero_id;
     uint8_t nact, npend, nguard;
@@ -849,11 +863,20 @@ struct Com {                     // play-com
 struct RouteList { int n; uint32_t r[MAXR]; };
 
 
-PD_HDN uint32_t new_route(Ctx &cx, int frm, int to, int tvoid, uint32_t tricks, uint32_t len)
+PD_HD uint64_t trick_mask(uint32_t t) { return (1ull << cidx(tcard(t, 0))) | (1ull << cidx(tcard(t, 2))); }
+PD_HDN uint64_t tricks_mask(const uint32_t *src, int n)
+{
+    uint64_t m = 0;
+    PD_ROLLED
+    for (int i = 0; i < n; ++i) m |= trick_mask(src[i]);
+    return m;
+}
+PD_HDN uint32_t new_route(Ctx &cx, int frm, int to, int tvoid, uint32_t tricks, uint32_t len, uint64_t mask)
 {
     const uint32_t off = arena_alloc(cx, sizeof(Route));
     Route *r = at<Route>(cx, off);
     r->frm = (int8_t)frm; r->to = (int8_t)to; r->tvoid = (int8_t)tvoid; r->pad = 0; r->tricks = tricks; r->len = len;
+    r->mlo = (uint32_t)mask; r->mhi = (uint32_t)(mask >> 32);
     return off;
 }
 PD_HD void rl_push(Ctx &cx, RouteList &l, uint32_t r) { if (l.n < MAXR) l.r[l.n++] = r; else fail(cx, PD_E_CAP); }
@@ -865,8 +888,20 @@ PD_HDN void rl_push_front(Ctx &cx, RouteList &l, uint32_t r)
     l.r[0] = r; ++l.n;
 }
 
+// the lanes copy a trick list together, four loads in flight per lane (the lists sit in L2)
+PD_HD void copy_tricks(uint32_t *dst, const uint32_t *src, uint32_t n)
+{
+    uint32_t i = (uint32_t)PD_LANE;
+    PD_ROLLED
+    for (; i + 3u * PD_LANES < n; i += 4u * PD_LANES) {
+        const uint32_t a = src[i], b = src[i + PD_LANES], c = src[i + 2u * PD_LANES], d = src[i + 3u * PD_LANES];
+        dst[i] = a; dst[i + PD_LANES] = b; dst[i + 2u * PD_LANES] = c; dst[i + 3u * PD_LANES] = d;
+    }
+    PD_ROLLED
+    for (; i < n; i += PD_LANES) dst[i] = src[i];
+}
 // add-at (2421-2425): a new route whose tricks are the concatenation
-PD_HDN uint32_t add_at(Ctx &cx, uint32_t route, uint32_t tricks2, uint32_t len2)
+PD_HDN uint32_t add_at(Ctx &cx, uint32_t route, uint32_t tricks2, uint32_t len2, uint64_t mask2)
 {
     const Route r = *at<Route>(cx, route);
     const uint32_t len = r.len + len2;
@@ -874,12 +909,10 @@ PD_HDN uint32_t add_at(Ctx &cx, uint32_t route, uint32_t tricks2, uint32_t len2)
     if (cx.status) return route;
     uint32_t *dst = at<uint32_t>(cx, off);
     const uint32_t *a = at<uint32_t>(cx, r.tricks), *b = at<uint32_t>(cx, tricks2);
-    PD_ROLLED
-    for (uint32_t i = PD_LANE; i < r.len; i += PD_LANES) dst[i] = a[i];
-    PD_ROLLED
-    for (uint32_t i = PD_LANE; i < len2; i += PD_LANES) dst[r.len + i] = b[i];
+    copy_tricks(dst, a, r.len);
+    copy_tricks(dst + r.len, b, len2);
     PD_SYNC();
-    return new_route(cx, r.frm, r.to, r.tvoid, off, len);
+    return new_route(cx, r.frm, r.to, r.tvoid, off, len, route_mask(r) | mask2);
 }
 // insert-route (2553-2561): merge into the first route with the same from / to, else push in front
 PD_HDN void insert_route(Ctx &cx, RouteList &routes, uint32_t route)
@@ -888,7 +921,7 @@ PD_HDN void insert_route(Ctx &cx, RouteList &routes, uint32_t route)
     PD_ROLLED
     for (int p = 0; p < routes.n; ++p) {
         const Route *q = at<Route>(cx, routes.r[p]);
-        if (q->frm == r.frm && q->to == r.to) { routes.r[p] = add_at(cx, routes.r[p], r.tricks, r.len); return; }
+        if (q->frm == r.frm && q->to == r.to) { routes.r[p] = add_at(cx, routes.r[p], r.tricks, r.len, route_mask(r)); return; }
     }
     rl_push_front(cx, routes, route);
 }
@@ -1079,7 +1112,7 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
         PD_ROLLED
         for (int i = 0; i < nsec[s]; ++i) tmpt[i] = sec[s][nsec[s] - 1 - i];
         const uint32_t off = tricks_from(cx, tmpt, nsec[s]);
-        rl_push(cx, routes, new_route(cx, frm, to, -1, off, (uint32_t)nsec[s]));
+        rl_push(cx, routes, new_route(cx, frm, to, -1, off, (uint32_t)nsec[s], tricks_mask(tmpt, nsec[s])));
     };
     section(S_MY, -1, 0);
     section(S_PARTNER, -1, 2);
@@ -1103,7 +1136,7 @@ PD_HDN uint32_t play_routes(Ctx &cx, const Hand *h, const int8_t *suits, int nsu
             // sec[s] is already in input order here; the section list handed to void-vertices is the reversed one and
             // divlist reverses it again: the route's tricks are in input order
             const uint32_t off = tricks_from(cx, tmpt, n);
-            rl_push(cx, routes, new_route(cx, frm, to, suits[k], off, (uint32_t)n));
+            rl_push(cx, routes, new_route(cx, frm, to, suits[k], off, (uint32_t)n, tricks_mask(tmpt, n)));
         }
     };
     vertices(S_MY_LEFT, 0, 0);
@@ -1143,20 +1176,34 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
     for (int i = 0; i < ncards; ++i) cards[i] = cards_in[i];
     bool remaining_nil = ncards == 0;
     routes.n = 0;
+    unsigned long long want = 0;
+    bool have_want = false;
     PD_ROLLED
     for (int a = 0; a < com.nact && !cx.status; ++a) {
         const uint32_t roff = com.act[a];
         if (remaining_nil) { rl_push_front(cx, routes, roff); ncards = 0; continue; }
         const Route r = *at<Route>(cx, roff);
+        // only the cards just played matter: a 53-bit request mask over the card indices
+        if (!have_want) {
+            want = 0;
+            PD_ROLLED
+            for (int i = 0; i < ncards; ++i) want |= 1ull << cidx(cards[i]);
+            have_want = true;
+        }
+        if ((route_mask(r) & want) == 0) {
+            // none of the cards leads or is third in any trick of this route (94 % of the routes visited): nothing to
+            // remove or break, the route stays as it is and the card list is handed on REVERSED (divlist, 2403)
+            if (r.len) rl_push_front(cx, routes, roff);
+            PD_ROLLED
+            for (int i = 0, j = ncards - 1; i < j; ++i, --j) { const Card c = cards[i]; cards[i] = cards[j]; cards[j] = c; }
+            continue;
+        }
+        have_want = false;                                           // cards may leave the list below
         // rem-break-div (2397-2411): first index of each card as a first card / as a third card of the route's tricks
         PD_ROLLED
         for (int i = 0; i < ncards; ++i) { const int ci = cidx(cards[i]); pos_first[ci] = -1; pos_third[ci] = -1; }   // only these are read
         if (r.len > 32767) { fail(cx, PD_E_CAP); return; }
         {
-            // only the cards just played matter: a 53-bit request mask over the card indices
-            unsigned long long want = 0;
-            PD_ROLLED
-            for (int i = 0; i < ncards; ++i) want |= 1ull << cidx(cards[i]);
             const uint32_t *tr = at<uint32_t>(cx, r.tricks);
 #if defined(__CUDA_ARCH__)
             // 32 tricks per step, one per lane; the (rare) tricks that hold a wanted card are then visited in order by
@@ -1254,7 +1301,7 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
                 dst[n++] = tr[t];
             }
 #endif
-            updated = new_route(cx, r.frm, r.to, r.tvoid, off, n);
+            updated = new_route(cx, r.frm, r.to, r.tvoid, off, n, route_mask(r));
             updated_len = n;
         }
         int nb = 0;
@@ -1268,7 +1315,7 @@ PD_HDN void first_pass(Ctx &cx, const Com &com, const Card *cards_in, int ncards
         }
         if (nb) {
             const uint32_t off = tricks_from(cx, brk_tricks, nb);
-            insert_route(cx, routes, new_route(cx, r.to, r.to, -1, off, (uint32_t)nb));
+            insert_route(cx, routes, new_route(cx, r.to, r.to, -1, off, (uint32_t)nb, route_mask(r)));
         }
         if (updated_len) rl_push_front(cx, routes, updated);
         // what is left of the cards: the absent section, reversed
@@ -1295,6 +1342,7 @@ PD_HDN uint32_t com_after_tricks_full(Ctx &cx, uint32_t com_off, const Outcome &
     int8_t *broken = tmp<int8_t>(cx, MAXG), *ks = tmp<int8_t>(cx, MAXG);
     uint16_t *kr = tmp<uint16_t>(cx, MAXG);
     // normalize-hands (2622-2638)
+    PD_PROF_T0();
     uint32_t self_off = com_off;
     {
         const Com &com = *at<Com>(cx, com_off);
@@ -1309,9 +1357,9 @@ PD_HDN uint32_t com_after_tricks_full(Ctx &cx, uint32_t com_off, const Outcome &
             const Com &c = *at<Com>(cx, com_off);
             n.zero_id = (uint8_t)out.rem[0].id(); n.nact = c.nact; n.npend = c.npend; n.nguard = 0;
             PD_ROLLED
-            for (int i = 0; i < c.nact; ++i) { const Route r = *at<Route>(cx, c.act[i]); n.act[i] = new_route(cx, r.frm >= 0 ? (r.frm + offset) & 3 : -1, (r.to + offset) & 3, r.tvoid, r.tricks, r.len); }
+            for (int i = 0; i < c.nact; ++i) { const Route r = *at<Route>(cx, c.act[i]); n.act[i] = new_route(cx, r.frm >= 0 ? (r.frm + offset) & 3 : -1, (r.to + offset) & 3, r.tvoid, r.tricks, r.len, route_mask(r)); }
             PD_ROLLED
-            for (int i = 0; i < c.npend; ++i) { const Route r = *at<Route>(cx, c.pend[i]); n.pend[i] = new_route(cx, r.frm >= 0 ? (r.frm + offset) & 3 : -1, (r.to + offset) & 3, r.tvoid, r.tricks, r.len); }
+            for (int i = 0; i < c.npend; ++i) { const Route r = *at<Route>(cx, c.pend[i]); n.pend[i] = new_route(cx, r.frm >= 0 ? (r.frm + offset) & 3 : -1, (r.to + offset) & 3, r.tvoid, r.tricks, r.len, route_mask(r)); }
         }
     }
     if (cx.status) return com_off;
@@ -1322,12 +1370,14 @@ PD_HDN uint32_t com_after_tricks_full(Ctx &cx, uint32_t com_off, const Outcome &
         for (int i = 0; i < 4; ++i) raw[nraw++] = tcard(out.tricks[t], i);
     }
     int nskipped = 0;
+    PD_PROF_ADD(5);
     if (at<Com>(cx, self_off)->nact == 0) {                          // no active route: every card is skipped (7 calls in 10)
         base.n = 0; nskipped = nraw;
         PD_ROLLED
         for (int i = 0; i < nraw; ++i) skipped[i] = raw[i];
     } else first_pass(cx, *at<Com>(cx, self_off), raw, nraw, base, skipped, nskipped);
     if (cx.status) return com_off;
+    PD_PROF_ADD(6);
     // second-pass (2592-2596): pending routes whose target hand is now void in the route's suit; both lists reversed
     new_active.n = new_pending.n = 0;
     {
@@ -1411,6 +1461,7 @@ PD_HDN uint32_t com_after_tricks_full(Ctx &cx, uint32_t com_off, const Outcome &
             for (int i = 0; i < rf.nguard; ++i) { if (ng >= MAXG) { fail(cx, PD_E_CAP); break; } n.gsuit[ng] = rf.gsuit[i]; n.granks[ng] = rf.granks[i]; ++ng; }
         }
         n.nguard = (uint8_t)ng;
+        PD_PROF_ADD(7);
         return noff;
     }
 }
@@ -1457,7 +1508,8 @@ PD_HDN void play_strategy(Ctx &cx, RootStrategy &rs, const Hand *h, SearchFrame 
     PD_ROLLED
     for (int i = 0; i < rs.nsoon; ++i) if (h[0].s[rs.soonest[i]]) suits[ns++] = rs.soonest[i];
     if (ns > 2) ns = 2;                                              // (list-lead 2 suits)
-    search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
+    if (ns) search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
+    else outcome_empty(out, h);                                      // nothing to try: what the search returns for no options
     if (cx.status || out.n > 0) return;
     Target *target = nullptr;
     PD_ROLLED
@@ -1520,10 +1572,12 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     PD_ROLLED
     for (int i = 0; i < 4; ++i) all_suits[i] = (int8_t)i;
     // active = strategy of the side on lead, passive = declarer's (2923-2926)
+    PD_PROF_T0();
     find_opp_weakness(cx, S.roots[0], rolled, S.sstack);
     const uint32_t com_a = cx.status ? 0 : play_routes(cx, rolled, all_suits, 4, S.sstack);
     if (!cx.status) find_opp_weakness(cx, S.roots[1], in, S.sstack);
     const uint32_t com_p = cx.status ? 0 : play_routes(cx, in, all_suits, 4, S.sstack);
+    PD_PROF_ADD(0);
     int sp = 0;
     {
         PlayFrame &f = S.pstack[0];
@@ -1562,17 +1616,26 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         }
         const int option = f.opt++;
         f.mark = cx.top;
-        if (option == 0) play_strategy(cx, S.roots[f.active.root], f.hands, S.sstack, ans);
-        else if (option == 1) { if (at<Com>(cx, f.active.com)->nact) mk_route(cx, f.active.com, f.hands, ans); else outcome_empty(ans, f.hands); }   // no route to follow: nil
-        else simple_trick(cx, ans, f.any_suit, f.hands, false);
+        {
+            PD_PROF_T0();
+            if (option == 0) play_strategy(cx, S.roots[f.active.root], f.hands, S.sstack, ans);
+            else if (option == 1) { if (at<Com>(cx, f.active.com)->nact) mk_route(cx, f.active.com, f.hands, ans); else outcome_empty(ans, f.hands); }   // no route to follow: nil
+            else simple_trick(cx, ans, f.any_suit, f.hands, false);
+            PD_PROF_ADD(1 + option);
+        }
         if (cx.status) break;
         if (ans.n == 0) {                                            // after-action gave nil
             if (!f.have_best) { outcome_nil(f.best); f.have_best = 1; }
             cx.top = f.mark;
             continue;
         }
-        const uint32_t new_a = com_after_tricks(cx, f.active.com, ans, S.sstack);
-        const uint32_t new_p = cx.status ? 0 : com_after_tricks(cx, f.passive.com, ans, S.sstack);
+        uint32_t new_a, new_p;
+        {
+            PD_PROF_T0();
+            new_a = com_after_tricks(cx, f.active.com, ans, S.sstack);
+            new_p = cx.status ? 0 : com_after_tricks(cx, f.passive.com, ans, S.sstack);
+            PD_PROF_ADD(4);
+        }
         if (cx.status) break;
         if (sp + 1 >= MAXD) { fail(cx, PD_E_CAP); break; }
         PlayFrame &c = S.pstack[sp + 1];

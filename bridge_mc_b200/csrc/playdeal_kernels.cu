@@ -106,3 +106,13 @@ void launch_failed(cudaStream_t stream, const void *d_out, uint64_t n, unsigned 
 }
 
 }  // namespace bmc_pd
+
+#if defined(PD_PROFILE)
+// diagnostic builds only: reads and clears the per-phase cycle sums
+extern "C" __attribute__((visibility("default"))) int bmc_pd_debug_profile(unsigned long long *out8)
+{
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, g_pd_prof, sizeof(zero)) != cudaSuccess) return 1;
+    return cudaMemcpyToSymbol(g_pd_prof, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif

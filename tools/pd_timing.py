@@ -25,6 +25,9 @@ d_out = torch.empty(n * 72, dtype=torch.uint8, device="cuda")
 d_t = torch.tensor([-1], dtype=torch.int8, device="cuda")
 d_d = torch.tensor([2], dtype=torch.uint8, device="cuda")
 eng.play_deal_dev(d_rec.data_ptr(), min(n, 2048), d_t.data_ptr(), d_d.data_ptr(), False, d_out.data_ptr())
+if hasattr(_lib.load(), "bmc_pd_debug_profile"):
+    import ctypes
+    _lib.load().bmc_pd_debug_profile((ctypes.c_ulonglong * 8)())          # clear what the warm-up added
 res = {"deals": n}
 for kb in (sys.argv[2:] or ["256", "1024"]):
     os.environ["BMC_PD_ARENA_KB"] = kb
@@ -38,5 +41,11 @@ for kb in (sys.argv[2:] or ["256", "1024"]):
     res[f"arena_{kb}kb"] = {"ms": e0.elapsed_time(e1), "deals_per_s": n / e0.elapsed_time(e1) * 1e3, "status": np.bincount(out["status"], minlength=5).tolist(),
                             "sum_cycles": float(cyc.sum()), "max_cycles": float(cyc.max()), "mean_cycles": float(cyc.mean()),
                             "p99_cycles": float(np.percentile(cyc, 99))}
+    L = _lib.load()
+    if hasattr(L, "bmc_pd_debug_profile"):                      # a -DPD_PROFILE build: cycles per phase
+        import ctypes
+        buf = (ctypes.c_ulonglong * 8)()
+        L.bmc_pd_debug_profile(buf)
+        res[f"arena_{kb}kb"]["phase_cycles"] = dict(zip(["setup", "play_strategy", "mk_route", "simple_trick", "after_tricks", "at_normalise", "at_first_pass", "at_rest"], [int(x) for x in buf[:8]]))
     np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"pd_timing_{kb}.npz"), rec=rec, cyc=cyc, status=out["status"], tricks=out["score"][:, 1])
 print(json.dumps(res))
