@@ -2623,9 +2623,9 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
     const uint64_t max_blocks = (uint64_t)ctx->sms * per_sm;
     if (blocks > max_blocks) blocks = max_blocks;
     unsigned long long *d_next = nullptr;
-    CUDA_TRY(cudaMalloc(&d_next, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d_next, 3 * sizeof(unsigned long long)));
     struct Free { unsigned long long *p; ~Free() { cudaFree(p); } } free_next{d_next};
-    CUDA_TRY(cudaMemsetAsync(d_next, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_next, 0, 3 * sizeof(unsigned long long), ctx->stream));
     // the arenas (one per resident warp): grow-only, halving the number of concurrent deals if the device cannot hold them
     for (;;) {
         const uint64_t need = blocks * PD_WARPS * arena;
@@ -2637,7 +2637,30 @@ static int play_deal_launch(bmc_ctx *ctx, const void *d_records, const void *d_h
         if (blocks <= 1) return fail(BMC_E_NOMEM, "bmc_play_deal: cannot allocate the per-deal arenas");
         blocks = (blocks + 1) / 2;
     }
-    bmc_pd::launch((unsigned)blocks, ctx->stream, d_records, d_hands4, nullptr, n, d_trump, d_declarer, per_deal, ctx->d_arena,
+    // A batch ends with its longest deal, and a deal takes anything from a hundredth to fifteen times the mean.  When the
+    // batch is more than a few rounds of the resident warps, a probe pass (the set-up of the two strategies, 5 % of the
+    // work) scores every deal, and the deals are played longest-expected first: 1.3 x on 32 768 deals.
+    unsigned int *d_order = nullptr;
+    struct FreeU { unsigned int *&p; ~FreeU() { if (p) cudaFree(p); } } free_order{d_order};
+    const char *env_order = getenv("BMC_PD_ORDER");
+    const bool ordered = env_order ? atoi(env_order) != 0 : n >= 2ull * blocks * PD_WARPS;
+    if (ordered) {
+        unsigned int *d_score = nullptr;
+        CUDA_TRY(cudaMalloc(&d_score, n * sizeof(unsigned int)));
+        struct FreeS { unsigned int *p; ~FreeS() { cudaFree(p); } } free_score{d_score};
+        bmc_pd::launch((unsigned)blocks, ctx->stream, d_records, d_hands4, nullptr, n, d_trump, d_declarer, per_deal, ctx->d_arena,
+                       (uint32_t)arena, d_out, d_next + 2, 0, d_score);
+        ctx->launches++;
+        std::vector<unsigned int> score(n), order(n);
+        CUDA_TRY(cudaMemcpyAsync(score.data(), d_score, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        for (uint64_t i = 0; i < n; ++i) order[i] = (unsigned int)i;
+        std::stable_sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) { return score[a] > score[b]; });
+        CUDA_TRY(cudaMalloc(&d_order, n * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemcpyAsync(d_order, order.data(), n * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));            // `order` leaves scope
+    }
+    bmc_pd::launch((unsigned)blocks, ctx->stream, d_records, d_hands4, d_order, n, d_trump, d_declarer, per_deal, ctx->d_arena,
                    (uint32_t)arena, d_out, d_next, timing);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

@@ -1559,7 +1559,10 @@ struct Scratch {
     alignas(16) uint8_t tmp[4736];    // temporaries of the call chain (structural peak 4 320 B: play-deal > after-tricks > play-routes > search > simple-trick)
 };
 
-PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Hand *declarer_left_dummy_right, Scratch &S, Result &res)
+// probe = true: only the two strategies are set up, and res.nodes receives a score that grows with the expected size of the
+// search (fitted on measured device cycles, profiles/r02_playdeal_schedule.md): the launcher plays the deals it expects to
+// be long first, because a batch ends with its longest deal (the cost of a deal varies by a factor of 100).
+PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Hand *declarer_left_dummy_right, Scratch &S, Result &res, bool probe = false)
 {
     Ctx cx;
     cx.arena = arena; cx.cap = arena_bytes; cx.top = 64; cx.status = PD_OK; cx.trump = trump;
@@ -1578,6 +1581,15 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     if (!cx.status) find_opp_weakness(cx, S.roots[1], in, S.sstack);
     const uint32_t com_p = cx.status ? 0 : play_routes(cx, in, all_suits, 4, S.sstack);
     PD_PROF_ADD(0);
+    if (probe) {
+        res.status = cx.status; res.tmp_peak = cx.speak; res.arena_peak = cx.top;
+        if (cx.status) { res.nodes = 0xFFFFu; return; }                   // outgrew the arena already: a long one
+        const Com &a = *at<Com>(cx, com_a), &p = *at<Com>(cx, com_p);
+        const int score = 2 * a.nact + 10 * a.npend + 12 * a.nguard - 2 * p.nact + 7 * p.npend + 7 * p.nguard
+                          + 19 * S.roots[0].nest + 13 * S.roots[1].nest;
+        res.nodes = (uint32_t)(score < 0 ? 0 : score);
+        return;
+    }
     int sp = 0;
     {
         PlayFrame &f = S.pstack[0];

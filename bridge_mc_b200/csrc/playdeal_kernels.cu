@@ -11,7 +11,7 @@ namespace {
 
 __device__ __noinline__ void play_one_deal(const uint4 *records, const unsigned long long *hands4, unsigned long long i, const int8_t *trump,
                                            const uint8_t *declarer, int per_deal, uint8_t *arena, uint32_t arena_bytes, pd::Scratch &S,
-                                           bmc_play_result *out, int timing)
+                                           bmc_play_result *out, int timing, unsigned int *probe)
 {
     const long long t0 = timing ? clock64() : 0ll;
     const int tr = trump[per_deal ? i : 0];
@@ -33,8 +33,9 @@ __device__ __noinline__ void play_one_deal(const uint4 *records, const unsigned 
         }
     }
     pd::Result &res = S.res;
-    pd::play_deal(arena, arena_bytes, tr < 0 || tr > 3 ? -1 : tr, h, S, res);
+    pd::play_deal(arena, arena_bytes, tr < 0 || tr > 3 ? -1 : tr, h, S, res, probe != nullptr);
     if ((threadIdx.x & 31u) != 0u) return;                   // the lanes hold identical results
+    if (probe) { probe[i] = res.nodes; return; }
     bmc_play_result o;
     o.status = (uint8_t)res.status; o.n_tricks = res.n; o.score[0] = res.score[0]; o.score[1] = res.score[1];
     for (int t = 0; t < 13; ++t) {
@@ -56,7 +57,7 @@ __device__ __noinline__ void play_one_deal(const uint4 *records, const unsigned 
 __global__ void __launch_bounds__(bmc_pd::THREADS) play_deal_kernel(const uint4 *records, const unsigned long long *hands4, const unsigned int *idx,
                                                                       unsigned long long n, const int8_t *trump, const uint8_t *declarer,
                                                                       int per_deal, uint8_t *arenas, uint32_t arena_bytes, bmc_play_result *out,
-                                                                      unsigned long long *next, int timing)
+                                                                      unsigned long long *next, int timing, unsigned int *probe)
 {
     extern __shared__ __align__(16) unsigned char pd_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(bmc_pd::THREADS) play_deal_kernel(const uint4 
         if (lane == 0) k = atomicAdd(next, 1ull);
         k = __shfl_sync(0xFFFFFFFFu, k, 0);
         if (k >= n) break;
-        play_one_deal(records, hands4, idx ? idx[k] : k, trump, declarer, per_deal, arena, arena_bytes, S, out, timing);
+        play_one_deal(records, hands4, idx ? idx[k] : k, trump, declarer, per_deal, arena, arena_bytes, S, out, timing, probe);
         __syncwarp();
     }
 }
@@ -93,11 +94,11 @@ cudaError_t configure(int *blocks_per_sm)
 
 void launch(unsigned blocks, cudaStream_t stream, const void *d_records, const void *d_hands4, const unsigned int *d_idx, uint64_t n,
             const int8_t *d_trump, const uint8_t *d_declarer, int per_deal, uint8_t *d_arenas, uint32_t arena_bytes, void *d_out,
-            unsigned long long *d_next, int timing)
+            unsigned long long *d_next, int timing, unsigned int *d_probe)
 {
     play_deal_kernel<<<blocks, THREADS, WARPS * sizeof(pd::Scratch), stream>>>(
         reinterpret_cast<const uint4 *>(d_records), reinterpret_cast<const unsigned long long *>(d_hands4), d_idx, n, d_trump, d_declarer,
-        per_deal, d_arenas, arena_bytes, reinterpret_cast<bmc_play_result *>(d_out), d_next, timing);
+        per_deal, d_arenas, arena_bytes, reinterpret_cast<bmc_play_result *>(d_out), d_next, timing, d_probe);
 }
 
 void launch_failed(cudaStream_t stream, const void *d_out, uint64_t n, unsigned int *d_idx, unsigned int *d_count)

@@ -109,6 +109,22 @@ def test_arena_overflow_is_reported_not_silent(engine):
     assert (ok["status"] == 0).all()
 
 
+def test_longest_expected_first_order_changes_nothing(engine, monkeypatch):
+    """Large batches are played in the order of a probe pass's length estimate (play_deal_launch); the results must
+    not depend on it: the same 1 200 deals with the order forced on, forced off, and with small arenas + retry."""
+    rng = random.Random(17)
+    hands = np.array([[lane_mask(h) for h in rand_deal(rng, 13)] for _ in range(1200)], dtype=np.uint64)
+    trump = np.array([rng.choice([-1, 0, 1, 2, 3]) for _ in range(1200)], dtype=np.int8)
+    monkeypatch.setenv("BMC_PD_ORDER", "0")
+    plain = engine.play_hands(hands, trump)
+    monkeypatch.setenv("BMC_PD_ORDER", "1")
+    ordered = engine.play_hands(hands, trump)
+    monkeypatch.setenv("BMC_PD_ARENA_KB", "64")                   # many deals outgrow 64 KB: the retry pass runs too
+    retried = engine.play_hands(hands, trump)
+    assert (plain["status"] == 0).all()
+    assert plain.tobytes() == ordered.tobytes() == retried.tobytes()
+
+
 def test_edge_cases_follow_the_reference(engine):
     """hands of unequal size: the reference signals a Lisp error when an empty hand has to play (status 2); a longer
     declarer hand just keeps its extra card; four empty hands: play-deal returns nil (status 4) -- as the oracle does"""

@@ -29,8 +29,9 @@ if hasattr(_lib.load(), "bmc_pd_debug_profile"):
     import ctypes
     _lib.load().bmc_pd_debug_profile((ctypes.c_ulonglong * 8)())          # clear what the warm-up added
 res = {"deals": n}
-for kb in (sys.argv[2:] or ["256", "1024"]):
-    os.environ["BMC_PD_ARENA_KB"] = kb
+for kb in (sys.argv[2:] or ["1024", "1024:0"]):                 # "<first-pass arena KB>[:0]", :0 = submission order (no probe pass)
+    os.environ["BMC_PD_ARENA_KB"] = kb.split(":")[0]
+    os.environ["BMC_PD_ORDER"] = "0" if kb.endswith(":0") else "1"
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     eng.play_deal_dev(d_rec.data_ptr(), n, d_t.data_ptr(), d_d.data_ptr(), False, d_out.data_ptr())
@@ -47,5 +48,5 @@ for kb in (sys.argv[2:] or ["256", "1024"]):
         buf = (ctypes.c_ulonglong * 8)()
         L.bmc_pd_debug_profile(buf)
         res[f"arena_{kb}kb"]["phase_cycles"] = dict(zip(["setup", "play_strategy", "mk_route", "simple_trick", "after_tricks", "at_normalise", "at_first_pass", "at_rest"], [int(x) for x in buf[:8]]))
-    np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"pd_timing_{kb}.npz"), rec=rec, cyc=cyc, status=out["status"], tricks=out["score"][:, 1])
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"pd_timing_{kb.replace(':', '_')}.npz"), rec=rec, cyc=cyc, status=out["status"], tricks=out["score"][:, 1])
 print(json.dumps(res))
