@@ -1559,10 +1559,65 @@ struct Scratch {
     alignas(16) uint8_t tmp[4736];    // temporaries of the call chain (structural peak 4 320 B: play-deal > after-tricks > play-routes > search > simple-trick)
 };
 
-// probe = true: only the two strategies are set up, and res.nodes receives a score that grows with the expected size of the
-// search (fitted on measured device cycles, profiles/r02_playdeal_schedule.md): the launcher plays the deals it expects to
-// be long first, because a batch ends with its longest deal (the cost of a deal varies by a factor of 100).
-PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Hand *declarer_left_dummy_right, Scratch &S, Result &res, bool probe = false)
+// Probe mode: only the two strategies are set up, and res.nodes receives a score that grows with the expected length of the
+// search.  The launcher plays the deals it expects to be long first, because a batch ends with its longest deal and the
+// cost of a deal varies by a factor of 100.  The score is a small boosted-tree model over ORDER_FEATURES numbers read off
+// the two root strategies and the four hands, fitted on measured device cycles (tools/fit_playdeal_order.py writes
+// playdeal_order_model.inc; profiles/r02_playdeal_schedule.md).  It decides the ORDER of play only, never a result.
+#if defined(__CUDA_ARCH__)
+#define PD_TABLE __device__ const
+#else
+#define PD_TABLE static const
+#endif
+constexpr int ORDER_FEATURES = 74;
+#include "playdeal_order_model.inc"
+
+PD_HDN void order_features(Ctx &cx, const Scratch &S, uint32_t com_a, uint32_t com_p, const Hand *hands, int *F)
+{
+    int k = 0;
+    PD_ROLLED
+    for (int w = 0; w < 2; ++w) {
+        const Com &c = *at<Com>(cx, w ? com_p : com_a);
+        const RootStrategy &rs = S.roots[w];
+        int tl = 0, pl = 0, mx = 0, selfr = 0, nofrom = 0, sd = 0, so = 0, st = 0;
+        PD_ROLLED
+        for (int i = 0; i < c.nact; ++i) {
+            const Route *r = at<Route>(cx, c.act[i]);
+            tl += (int)r->len; if ((int)r->len > mx) mx = (int)r->len;
+            if (r->frm == r->to) ++selfr;
+            if (r->frm < 0) ++nofrom;
+        }
+        PD_ROLLED
+        for (int i = 0; i < c.npend; ++i) pl += (int)at<Route>(cx, c.pend[i])->len;
+        PD_ROLLED
+        for (int i = 0; i < rs.nest; ++i) { sd += rs.establish[i].diff; so += rs.establish[i].nours; st += rs.establish[i].ntheirs; }
+        F[k++] = c.nact; F[k++] = c.npend; F[k++] = c.nguard; F[k++] = tl; F[k++] = pl; F[k++] = mx; F[k++] = selfr; F[k++] = nofrom;
+        F[k++] = rs.nsoon; F[k++] = rs.nest; F[k++] = sd; F[k++] = so; F[k++] = st;
+    }
+    PD_ROLLED
+    for (int h = 0; h < 4; ++h) {
+        PD_ROLLED
+        for (int suit = 0; suit < 4; ++suit) {
+            const uint32_t v = hands[h].s[suit];
+            F[k++] = popc(v); F[k++] = (int)(v >> 9); F[k++] = (int)(v >> 7);
+        }
+    }
+}
+PD_HDN uint32_t order_score(const int *F)
+{
+    int score = 0;
+    PD_ROLLED
+    for (int t = 0; t < PD_ORDER_TREES; ++t) {
+        int k = PD_ORDER_ROOT[t];
+        PD_ROLLED
+        while (PD_ORDER_NODE[k][0] >= 0) k = F[PD_ORDER_NODE[k][0]] <= PD_ORDER_NODE[k][1] ? PD_ORDER_NODE[k][2] : PD_ORDER_NODE[k][3];
+        score += PD_ORDER_LEAF[k];
+    }
+    return (uint32_t)(score + (1 << 30));
+}
+
+PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Hand *declarer_left_dummy_right, Scratch &S, Result &res,
+                      bool probe = false, int *features_out = nullptr)
 {
     Ctx cx;
     cx.arena = arena; cx.cap = arena_bytes; cx.top = 64; cx.status = PD_OK; cx.trump = trump;
@@ -1583,11 +1638,11 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
     PD_PROF_ADD(0);
     if (probe) {
         res.status = cx.status; res.tmp_peak = cx.speak; res.arena_peak = cx.top;
-        if (cx.status) { res.nodes = 0xFFFFu; return; }                   // outgrew the arena already: a long one
-        const Com &a = *at<Com>(cx, com_a), &p = *at<Com>(cx, com_p);
-        const int score = 2 * a.nact + 10 * a.npend + 12 * a.nguard - 2 * p.nact + 7 * p.npend + 7 * p.nguard
-                          + 19 * S.roots[0].nest + 13 * S.roots[1].nest;
-        res.nodes = (uint32_t)(score < 0 ? 0 : score);
+        if (cx.status) { res.nodes = 0xFFFFFFFFu; return; }               // outgrew the arena already: a long one
+        int *F = tmp<int>(cx, ORDER_FEATURES);
+        order_features(cx, S, com_a, com_p, in, F);
+        res.nodes = order_score(F);
+        if (features_out) { PD_ROLLED for (int i = 0; i < ORDER_FEATURES; ++i) features_out[i] = F[i]; }
         return;
     }
     int sp = 0;

@@ -4,6 +4,7 @@
 // stdout: status score0 score1 n then n*4 cards (hex) and the winner numbers.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #include "../bridge_mc_b200/csrc/playdeal.cuh"
 
@@ -21,6 +22,15 @@ int main(int argc, char **argv)
             h[i].set_id(i);
         }
         pd::Result r;
+        if (argc > 2 && std::string(argv[2]) == "probe") {           // the scheduling probe: status score features...
+            int feat[pd::ORDER_FEATURES] = {0};
+            pd::play_deal(arena.data(), arena_bytes, trump, h, S, r, true, feat);
+            printf("%d %u", r.status, r.nodes);
+            for (int i = 0; i < pd::ORDER_FEATURES; ++i) printf(" %d", feat[i]);
+            printf("\n");
+            fflush(stdout);
+            continue;
+        }
         pd::play_deal(arena.data(), arena_bytes, trump, h, S, r);
         printf("%d %d %d %d %u %u", r.status, r.score[0], r.score[1], r.n, r.arena_peak, r.nodes);
         if (argc > 2) fprintf(stderr, "tmp_peak %u of %zu\n", r.tmp_peak, sizeof(S.tmp));

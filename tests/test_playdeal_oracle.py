@@ -15,6 +15,7 @@ import json
 import os
 import sys
 
+import numpy as np
 import pytest
 
 from bridge_mc_b200 import sexp
@@ -185,3 +186,20 @@ def test_device_code_under_address_and_ub_sanitizers(tmp_path):
     for a, b in zip(full.stdout.strip().split("\n"), small.stdout.strip().split("\n")):
         if b.split()[0] == "0":
             assert a.split()[:4] == b.split()[:4] and a.split()[6:] == b.split()[6:]      # same outcome when the arena suffices
+
+
+def test_scheduling_probe_ranks_deals_by_measured_length(host_binary):
+    """play_deal's probe mode (the launcher plays the deals it scores highest first) against the device cycles measured
+    for 32 559 deals on a B200 (profiles/r02_playdeal_order_train.npz; the model was fitted on them by
+    tools/fit_playdeal_order.py): the score must rank the deals well, and most of the hundred longest must sit in its top decile.
+    The order never changes a result (tests/test_gpu_playdeal.py); this guards the speed-up against a stale model."""
+    from scipy.stats import spearmanr
+    d = np.load(os.path.join(HERE, "..", "profiles", "r02_playdeal_order_train.npz"))
+    hands, cyc = d["hands"][:6000], d["cycles"][:6000]
+    text = "".join("-1 " + " ".join(str((int(h) >> (16 * s)) & 0x1FFF) for h in hs for s in range(4)) + "\n" for hs in hands)
+    out = subprocess.run([host_binary, str(64 << 20), "probe"], input=text, capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    assert len(out) == len(hands) and all(line.split()[0] == "0" and len(line.split()) == 2 + 74 for line in out)
+    score = np.array([int(line.split()[1]) for line in out], dtype=np.float64)
+    assert spearmanr(score, cyc)[0] > 0.7
+    top = set(np.argsort(-score)[:600].tolist())
+    assert sum(int(i) in top for i in np.argsort(-cyc)[:100]) >= 50
