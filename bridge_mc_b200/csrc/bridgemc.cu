@@ -2591,7 +2591,7 @@ int bmc_hist_base(bmc_ctx *ctx, const bmc_record *records, uint64_t n, const bmc
 
 // ---- measurement ------------------------------------------------------------------
 // ---------------------------------------------------------------------------
-// play-deal (bridge.cl:2961): one thread per deal (playdeal.cuh)
+// play-deal (bridge.cl:2961): one warp per deal (playdeal.cuh)
 // ---------------------------------------------------------------------------
 // the kernels live in their own translation unit (playdeal_kernels.cu): they are compiled for code size
 static int pd_blocks_per_sm()

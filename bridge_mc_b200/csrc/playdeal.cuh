@@ -1,4 +1,4 @@
-// playdeal.cuh -- the reference's trick estimator `play-deal` (bridge.cl:1497-2963), one deal per thread.
+// playdeal.cuh -- the reference's trick estimator `play-deal` (bridge.cl:1497-2963), one deal per warp.
 //
 // `play-deal trump declarer left dummy right` is a heuristic search: at every lead it tries three ways of playing on
 // (`play-strategy`, `mk-route`, a plain trick in the leader's first suit, bridge.cl:2949-2959), each of which rests on
@@ -6,14 +6,14 @@
 // `simple-trick` (2269): second hand covers or finesses, third hand finesses, fourth hand beats or plays low.  The answer
 // depends on evaluation order and on state the reference mutates in place and shares between branches of the search
 // (routes are popped by `reproduce`, 2372; the ranks to hunt are popped by `play-strategy`, 2863; a play-com's guards
-// are overwritten, 2614), so this file keeps the reference's objects as records in a per-thread arena, referenced by
+// are overwritten, 2614), so this file keeps the reference's objects as records in a per-deal arena, referenced by
 // offset, created exactly where the reference calls make-instance, and keeps its evaluation order.
 //
 // Layout
 //   card    one byte, suit << 4 | rank (suit c d h s = 0..3, rank 0..12 = 2..A); 0xFF = nil
 //   hand    four 13-bit rank masks + the seat it descends from (the reference compares hand ids with `eq`)
 //   trick   four cards in play order, packed in one 32-bit word inside routes
-//   arena   per-thread bump allocator (global memory); the search releases it when it backtracks
+//   arena   per-deal bump allocator (global memory); the search releases it when it backtracks
 // Every helper that picks a card is bit arithmetic on a 13-bit mask (lowest = ffs, highest = 31 - clz, first above r =
 // ffs(mask >> (r + 1))).  No recursion: the four recursive searches of the reference run on explicit stacks.
 //

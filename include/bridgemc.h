@@ -365,7 +365,8 @@ typedef struct {
     uint8_t winner[13];
     uint8_t reserved[3];
 } bmc_play_result;   /* 72 bytes */
-/* One GPU thread plays one deal.  trump[i] in {-1 (no trump), 0..3 = c d h s}; declarer[i] = seat 0..3 (N E S W);
+/* One warp plays one deal; batches of more than two rounds of the resident warps are played longest-expected first
+ * (a probe pass scores every deal; environment BMC_PD_ORDER=0/1 forces it off/on; no result depends on it).  trump[i] in {-1 (no trump), 0..3 = c d h s}; declarer[i] = seat 0..3 (N E S W);
  * the left-hand opponent (seat + 1) leads.  per_deal = 0: trump[0] / declarer[0] apply to every deal.
  * arena_kb: per-deal scratch for the route lists; 0 = adaptive: 1 MB per resident deal in a first pass (environment
  * BMC_PD_ARENA_KB overrides), and the rare deals that outgrow it are played again with 8 MB each.  `reserved` is zero

@@ -11,6 +11,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bridge_mc_b200 import _lib, bidding  # noqa: E402
+if os.environ.get("PD_TIMING_LIB"):                              # a -DPD_PROFILE build kept beside the product
+    _lib.LIB_PATH = os.environ["PD_TIMING_LIB"]
 from bridge_mc_b200.engine import Constraints, Engine  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
