@@ -132,6 +132,7 @@ struct Ctx {                     // per-deal state
     int trump;                   // -1 = no trump
     uint8_t *sstk;               // stack of the functions' temporaries: shared memory on the device (one per warp), so
     uint32_t scap, stop, speak;  // that nothing indexed dynamically lives in (lane-interleaved) local memory
+    uint32_t pos;                // bucket table of the deal's position cache (grows down from the arena's end); 0 = none
 };
 
 PD_HD uint32_t arena_alloc(Ctx &cx, uint32_t bytes)
@@ -1484,6 +1485,61 @@ PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, 
     return noff;
 }
 
+// The search over a deal's play reaches the same four hands by many orders of play: 3 500 nodes for 250 distinct positions
+// in an average deal.  A node's value is NOT a function of its hands (it depends on the routes left, the guards and the
+// ranks already hunted), but two of the three things tried at every node are: the look-ahead part of play-strategy (its
+// immediate-tricks searches and the choice of the target suit: hands, trump and the root strategy's fixed lists) and the
+// plain trick in the leader's first suit.  Those are cached per deal, keyed by the four hand words and a tag (root strategy
+// 0 / 1, or 2 for the plain trick).  Entries are carved from the END of the arena downwards, so they survive the
+// backtracking of the bump allocator at its start; when the two meet, caching stops -- it is never an error.
+struct PosEntry { uint64_t key[4]; uint32_t next; uint8_t tag, stage; int8_t target; uint8_t pad; uint32_t pad2[2]; Outcome val; };
+constexpr uint32_t POS_BUCKETS = 1024;
+PD_HD uint32_t pos_bucket(const Hand *h, int tag)
+{
+    uint64_t x = h[0].s.m ^ (h[1].s.m << 13 | h[1].s.m >> 51) ^ (h[2].s.m << 29 | h[2].s.m >> 35) ^ (h[3].s.m << 43 | h[3].s.m >> 21);
+    x = (x + (uint64_t)tag) * 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(x >> 54) & (POS_BUCKETS - 1u);
+}
+PD_HDN void pos_init(Ctx &cx)
+{
+    cx.pos = 0;
+    if (cx.cap < (1u << 16)) return;                                 // small explicit arenas: no cache
+    cx.cap = (cx.cap - POS_BUCKETS * 4u) & ~15u;
+    cx.pos = cx.cap;
+    uint32_t *b = at<uint32_t>(cx, cx.pos);
+    PD_ROLLED
+    for (uint32_t i = PD_LANE; i < POS_BUCKETS; i += PD_LANES) b[i] = 0u;
+    PD_SYNC();
+}
+PD_HDN const PosEntry *pos_find(Ctx &cx, const Hand *h, int tag)
+{
+    if (!cx.pos) return nullptr;
+    uint32_t e = at<uint32_t>(cx, cx.pos)[pos_bucket(h, tag)];
+    PD_ROLLED
+    while (e) {
+        const PosEntry *m = at<PosEntry>(cx, e);
+        if (m->tag == tag && m->key[0] == h[0].s.m && m->key[1] == h[1].s.m && m->key[2] == h[2].s.m && m->key[3] == h[3].s.m) return m;
+        e = m->next;
+    }
+    return nullptr;
+}
+PD_HDN void pos_put(Ctx &cx, const Hand *h, int tag, int stage, int target, const Outcome *val)
+{
+    if (!cx.pos || cx.status) return;
+    if (cx.cap < cx.top + (uint32_t)sizeof(PosEntry) + (64u << 10)) return;       // keep 64 KB clear for the routes: stop caching
+    cx.cap -= (uint32_t)sizeof(PosEntry);
+    const uint32_t off = cx.cap;
+    PosEntry *m = at<PosEntry>(cx, off);
+    uint32_t *head = at<uint32_t>(cx, cx.pos) + pos_bucket(h, tag);
+    PD_ROLLED
+    for (int i = 0; i < 4; ++i) m->key[i] = h[i].s.m;
+    m->next = *head; m->tag = (uint8_t)tag; m->stage = (uint8_t)stage; m->target = (int8_t)target; m->pad = 0;
+    if (val) outcome_copy(m->val, *val);
+    PD_SYNC();
+    *head = off;
+    PD_SYNC();
+}
+
 // ---------------------------------------------------------------------------
 // play-strategy (2847-2866), hunt-card (2788-2812)
 // ---------------------------------------------------------------------------
@@ -1500,33 +1556,48 @@ PD_HDN void hunt_card(Ctx &cx, Outcome &o, int suit, int rank, const Hand *h)
     outcome_of_trick(cx, o, t);
 }
 
-PD_HDN void play_strategy(Ctx &cx, RootStrategy &rs, const Hand *h, SearchFrame *stack, Outcome &out)
+// `tag`: which root strategy `rs` is (0 / 1), the position cache's key beside the hands.  Everything up to the hunt
+// for a card is a function of the hands, the trump and rs's fixed lists; stage = where that part ended:
+// 1 the first search found tricks, 2 no target suit, 3 the second search found tricks, 4 neither (target chosen).
+PD_HDN void play_strategy(Ctx &cx, RootStrategy &rs, int tag, const Hand *h, SearchFrame *stack, Outcome &out)
 {
     const int trump = cx.trump;
-    int8_t suits[MAXT + 1];
-    int ns = 0;
-    PD_ROLLED
-    for (int i = 0; i < rs.nsoon; ++i) if (h[0].s[rs.soonest[i]]) suits[ns++] = rs.soonest[i];
-    if (ns > 2) ns = 2;                                              // (list-lead 2 suits)
-    if (ns) search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
-    else outcome_empty(out, h);                                      // nothing to try: what the search returns for no options
-    if (cx.status || out.n > 0) return;
     Target *target = nullptr;
-    PD_ROLLED
-    for (int i = 0; i < rs.nest && !target; ++i) {
-        const int suit = rs.establish[i].suit;
-        const bool ok = h[0].s[suit] && (suit != trump || h[1].s[suit] || h[3].s[suit])
-                        && (trump < 0 || trump == suit || (h[1].s[suit] && h[3].s[suit]));
-        if (ok) target = &rs.establish[i];
+    const PosEntry *known = pos_find(cx, h, tag);
+    if (known) {
+        if (known->stage == 2) { outcome_empty(out, h); return; }
+        if (known->stage != 4) { outcome_copy(out, known->val); return; }
+        target = &rs.establish[known->target];
+    } else {
+        int8_t suits[MAXT + 1];
+        int ns = 0;
+        PD_ROLLED
+        for (int i = 0; i < rs.nsoon; ++i) if (h[0].s[rs.soonest[i]]) suits[ns++] = rs.soonest[i];
+        if (ns > 2) ns = 2;                                              // (list-lead 2 suits)
+        if (ns) search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
+        else outcome_empty(out, h);                                      // nothing to try: what the search returns for no options
+        if (cx.status) return;
+        if (out.n > 0) { pos_put(cx, h, tag, 1, -1, &out); return; }
+        int ti = -1;
+        PD_ROLLED
+        for (int i = 0; i < rs.nest && ti < 0; ++i) {
+            const int suit = rs.establish[i].suit;
+            const bool ok = h[0].s[suit] && (suit != trump || h[1].s[suit] || h[3].s[suit])
+                            && (trump < 0 || trump == suit || (h[1].s[suit] && h[3].s[suit]));
+            if (ok) ti = i;
+        }
+        if (ti < 0) { outcome_empty(out, h); pos_put(cx, h, tag, 2, -1, nullptr); return; }
+        target = &rs.establish[ti];
+        suits[0] = target->suit;
+        ns = 1;
+        PD_ROLLED
+        for (int i = 0; i < rs.nsoon; ++i) suits[ns++] = rs.soonest[i];
+        search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
+        if (cx.status) return;
+        if (out.n > 0) { pos_put(cx, h, tag, 3, ti, &out); return; }
+        pos_put(cx, h, tag, 4, ti, nullptr);
     }
-    if (!target) { outcome_empty(out, h); return; }
     const int suit = target->suit;
-    suits[0] = (int8_t)suit;
-    ns = 1;
-    PD_ROLLED
-    for (int i = 0; i < rs.nsoon; ++i) suits[ns++] = rs.soonest[i];
-    search(cx, IMMEDIATE, -1, suits, ns, h, stack, out);
-    if (cx.status || out.n > 0) return;
     if (target->head < target->ntheirs) {
         const int rank = target->theirs[target->head++];             // (pop (fourth target))
         hunt_card(cx, out, suit, rank, h);
@@ -1621,7 +1692,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
 {
     Ctx cx;
     cx.arena = arena; cx.cap = arena_bytes; cx.top = 64; cx.status = PD_OK; cx.trump = trump;
-    cx.sstk = S.tmp; cx.scap = (uint32_t)sizeof(S.tmp); cx.stop = 0; cx.speak = 0;
+    cx.sstk = S.tmp; cx.scap = (uint32_t)sizeof(S.tmp); cx.stop = 0; cx.speak = 0; cx.pos = 0;
     res.arena_peak = 0; res.nodes = 0; res.n = 0; res.score[0] = res.score[1] = 0;
     Hand *in = tmp<Hand>(cx, 4), *rolled = tmp<Hand>(cx, 4);
     PD_ROLLED
@@ -1645,6 +1716,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         if (features_out) { PD_ROLLED for (int i = 0; i < ORDER_FEATURES; ++i) features_out[i] = F[i]; }
         return;
     }
+    if (!cx.status) pos_init(cx);
     int sp = 0;
     {
         PlayFrame &f = S.pstack[0];
@@ -1685,9 +1757,13 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         f.mark = cx.top;
         {
             PD_PROF_T0();
-            if (option == 0) play_strategy(cx, S.roots[f.active.root], f.hands, S.sstack, ans);
+            if (option == 0) play_strategy(cx, S.roots[f.active.root], f.active.root, f.hands, S.sstack, ans);
             else if (option == 1) { if (at<Com>(cx, f.active.com)->nact) mk_route(cx, f.active.com, f.hands, ans); else outcome_empty(ans, f.hands); }   // no route to follow: nil
-            else simple_trick(cx, ans, f.any_suit, f.hands, false);
+            else {                                                   // the plain trick: a function of the hands
+                const PosEntry *known = pos_find(cx, f.hands, 2);
+                if (known) outcome_copy(ans, known->val);
+                else { simple_trick(cx, ans, f.any_suit, f.hands, false); pos_put(cx, f.hands, 2, 0, -1, &ans); }
+            }
             PD_PROF_ADD(1 + option);
         }
         if (cx.status) break;
