@@ -133,6 +133,7 @@ struct Ctx {                     // per-deal state
     uint8_t *sstk;               // stack of the functions' temporaries: shared memory on the device (one per warp), so
     uint32_t scap, stop, speak;  // that nothing indexed dynamically lives in (lane-interleaved) local memory
     uint32_t pos;                // bucket table of the deal's position cache (grows down from the arena's end); 0 = none
+    uint32_t empties;            // four play-coms without routes or guards, one per hand on lead; 0 = not made yet
 };
 
 PD_HD uint32_t arena_alloc(Ctx &cx, uint32_t bytes)
@@ -1468,21 +1469,35 @@ PD_HDN uint32_t com_after_tricks_full(Ctx &cx, uint32_t com_off, const Outcome &
 }
 
 // Half of all calls are made on a play-com with no routes and no guards (the strategy has run out of plans): what comes
-// back is another empty play-com for the hand now on lead.  That case stays out of the large routine above -- the
-// estimator is bound by instruction fetch, and this keeps 30 KB of code out of most nodes' working set.
-PD_HDN uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, SearchFrame *stack)
+// back is another empty play-com for the hand now on lead.  Nothing ever writes to such a play-com, so the deal keeps
+// four of them (cx.empties, one per hand id) and hands those out: no allocation, and for a play-com that is already one
+// of the four not even a load.  That case stays out of the large routine above -- the estimator is bound by instruction
+// fetch, and this keeps 30 KB of code out of most nodes' working set.
+PD_HDN uint32_t com_after_tricks_loaded(Ctx &cx, uint32_t com_off, const Outcome &out, SearchFrame *stack)
 {
     const Com &c = *at<Com>(cx, com_off);
-    if ((c.nact | c.npend | c.nguard) != 0) return com_after_tricks_full(cx, com_off, out, stack);
+    if ((c.nact | c.npend | c.nguard) != 0 || !cx.empties) return com_after_tricks_full(cx, com_off, out, stack);
     bool found = false;
     PD_ROLLED
     for (int i = 0; i < 4 && !found; ++i) found = out.rem[i].id() == c.zero_id;      // normalize-hands (2622-2638)
     if (!found) { fail(cx, PD_E_LISP); return com_off; }
-    const uint32_t noff = arena_alloc(cx, sizeof(Com));
-    if (cx.status) return com_off;
-    Com &n = *at<Com>(cx, noff);
-    n.zero_id = (uint8_t)out.rem[0].id(); n.nact = n.npend = n.nguard = 0;
-    return noff;
+    return cx.empties + (uint32_t)sizeof(Com) * (uint32_t)out.rem[0].id();
+}
+PD_HD uint32_t com_after_tricks(Ctx &cx, uint32_t com_off, const Outcome &out, SearchFrame *stack)
+{
+    if (cx.empties && com_off - cx.empties < 4u * (uint32_t)sizeof(Com))             // one of the four: the hand ids are a
+        return cx.empties + (uint32_t)sizeof(Com) * (uint32_t)out.rem[0].id();      // permutation of 0..3, so its hand is there
+    return com_after_tricks_loaded(cx, com_off, out, stack);
+}
+PD_HDN void empties_init(Ctx &cx)
+{
+    cx.empties = 0;
+    const uint32_t off = arena_alloc(cx, 4u * (uint32_t)sizeof(Com));
+    if (cx.status) return;
+    PD_ROLLED
+    for (int k = 0; k < 4; ++k) { Com &n = *at<Com>(cx, off + (uint32_t)sizeof(Com) * k); n.zero_id = (uint8_t)k; n.nact = n.npend = n.nguard = 0; }
+    PD_SYNC();
+    cx.empties = off;
 }
 
 // The search over a deal's play reaches the same four hands by many orders of play: 3 500 nodes for 250 distinct positions
@@ -1692,7 +1707,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
 {
     Ctx cx;
     cx.arena = arena; cx.cap = arena_bytes; cx.top = 64; cx.status = PD_OK; cx.trump = trump;
-    cx.sstk = S.tmp; cx.scap = (uint32_t)sizeof(S.tmp); cx.stop = 0; cx.speak = 0; cx.pos = 0;
+    cx.sstk = S.tmp; cx.scap = (uint32_t)sizeof(S.tmp); cx.stop = 0; cx.speak = 0; cx.pos = 0; cx.empties = 0;
     res.arena_peak = 0; res.nodes = 0; res.n = 0; res.score[0] = res.score[1] = 0;
     Hand *in = tmp<Hand>(cx, 4), *rolled = tmp<Hand>(cx, 4);
     PD_ROLLED
@@ -1717,6 +1732,7 @@ PD_HDN void play_deal(uint8_t *arena, uint32_t arena_bytes, int trump, const Han
         return;
     }
     if (!cx.status) pos_init(cx);
+    if (!cx.status) empties_init(cx);
     int sp = 0;
     {
         PlayFrame &f = S.pstack[0];
