@@ -1,5 +1,10 @@
-"""Diagnostic: per-deal device time of the trick estimator (BMC_PD_TIMING=1) on the N1 sample, for two first-pass arena
-sizes.  python tools/pd_timing.py [n] -> gpurun_out/pd_timing.npz + one JSON line."""
+"""Diagnostic: per-deal device time of the trick estimator (BMC_PD_TIMING=1) on the N1 sample.
+
+    python tools/pd_timing.py [n] ["<first-pass arena KB>[:0]" ...]      (":0" = submission order, no probe pass)
+
+One JSON line (batch time, deals/s, sum / mean / p99 / max of the per-deal SM cycles; with a -DPD_PROFILE build named by
+PD_TIMING_LIB also the cycles per phase) and gpurun_out/pd_timing_<arena>.npz (records + cycles: the training data of
+tools/fit_playdeal_order.py)."""
 import json
 import os
 import sys
