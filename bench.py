@@ -511,8 +511,13 @@ def run_n1(args):
             "value": res["deals_per_s"], "unit": "deals/s", "n_gpus": 1, "steps": 1, "warmup": 1,
             "ms_per_step": res["play_deal_kernel_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": {"workload": res["config"], "deals": res["deals"]},
-            "roofline": {"bound": "instruction fetch (no applicable HBM / tensor roofline): see profiles/r02_prof_playdeal_final.txt",
-                         "achieved": None, "peak": None, "frac": None, "traffic": None},
+            # the estimator is bound by instruction issue / fetch, not by HBM or the tensor cores: achieved = warp instructions
+            # per deal (ncu, profiles/r02_prof_playdeal_v3.txt: 5.158e10 for 4 736 random deals) x deals/s; peak = one warp
+            # instruction per scheduler and cycle (148 SMs x 4 x 1.965 GHz)
+            "roofline": {"bound": "issue", "achieved": 5.158e10 / 4736 * res["deals_per_s"], "peak": 148 * 4 * 1.965e9,
+                         "unit": "warp-instr/s", "frac": 5.158e10 / 4736 * res["deals_per_s"] / (148 * 4 * 1.965e9), "traffic": None,
+                         "note": "instruction-fetch bound: 16.0 of 24.1 cycles per issued instruction are no_instruction stalls "
+                                 "(profiles/r02_prof_playdeal_v3.txt); instructions per deal from that capture, not measured live"},
             "result": {k: res[k] for k in ("status_counts", "tricks_hist", "mean_tricks", "p_3nt_makes", "mean_score")},
             "cpu_same_algorithm_one_core": res.get("cpu_same_algorithm_one_core")}
     if not args.no_cpu_baseline:
