@@ -125,6 +125,18 @@ def test_longest_expected_first_order_changes_nothing(engine, monkeypatch):
     assert plain.tobytes() == ordered.tobytes() == retried.tobytes()
 
 
+def test_outcomes_of_the_frozen_deal_set(engine):
+    """1 500 seeded deals and endings with random trumps against the digest frozen in tests/test_playdeal_oracle.py."""
+    from test_playdeal_oracle import FROZEN_DIGEST, frozen_deals, frozen_digest
+    jobs = frozen_deals()
+    hands = np.array([[sum(int(m[4 * j + s]) << (16 * s) for s in range(4)) for j in range(4)] for _, m in jobs], dtype=np.uint64)
+    out = engine.play_hands(hands, np.array([t for t, _ in jobs], dtype=np.int8))
+    assert (out["status"] == 0).all()
+    rows = [(0, int(o["score"][0]), int(o["score"][1]), int(o["n_tricks"]), [[int(c) for c in o["cards"][t]] for t in range(int(o["n_tricks"]))],
+             [int(w) for w in o["winner"][:int(o["n_tricks"])]]) for o in out]
+    assert frozen_digest(rows) == FROZEN_DIGEST
+
+
 def test_edge_cases_follow_the_reference(engine):
     """hands of unequal size: the reference signals a Lisp error when an empty hand has to play (status 2); a longer
     declarer hand just keeps its extra card; four empty hands: play-deal returns nil (status 4) -- as the oracle does"""

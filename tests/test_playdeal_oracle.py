@@ -203,3 +203,43 @@ def test_scheduling_probe_ranks_deals_by_measured_length(host_binary):
     assert spearmanr(score, cyc)[0] > 0.7
     top = set(np.argsort(-score)[:600].tolist())
     assert sum(int(i) in top for i in np.argsort(-cyc)[:100]) >= 50
+
+
+FROZEN_DIGEST = "6da7e2647984f06fe253df57709895e5ad9811681f2f9cb1d75f1fcb6f023f05"
+
+
+def frozen_deals():
+    """1 000 seeded full deals and 500 endings of 3 / 5 / 8 / 10 cards, each with a random trump (or none): the set whose
+    outcomes are frozen in FROZEN_DIGEST (also used by tests/test_gpu_playdeal.py)."""
+    rng, jobs = random.Random(77), []
+    for i in range(1500):
+        d = list(range(52))
+        rng.shuffle(d)
+        k = 13 if i < 1000 else rng.choice([3, 5, 8, 10])
+        masks = [sum(1 << (c % 13) for c in d[k * j:k * j + k] if c // 13 == s) for j in range(4) for s in range(4)]
+        jobs.append((rng.choice([0, 1, 2, 3, -1]), masks))
+    return jobs
+
+
+def frozen_digest(rows):
+    """rows: (status, score0, score1, n, cards[n][4], winners[n])"""
+    import hashlib
+    text = "\n".join(" ".join([str(st), str(s0), str(s1), str(n)] + ["%02x" % c for t in cards for c in t] + [str(w) for w in wno])
+                     for st, s0, s1, n, cards, wno in rows)
+    return hashlib.sha256(text.encode()).hexdigest()
+
+
+def test_outcomes_of_the_frozen_deal_set(host_binary):
+    """Every card of 1 500 deals and endings with random trumps, as a digest.  The digest was taken from the build that the
+    tests above tie to the reference's own run and to the restatement, before the estimator was restructured (the trick in
+    registers, memoised look-aheads, route masks, the position cache), and every later build has to reproduce it."""
+    text = "".join(f"{t} " + " ".join(map(str, m)) + "\n" for t, m in frozen_deals())
+    out = subprocess.run([host_binary], input=text, capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    rows = []
+    for line in out:
+        f = line.split()
+        n = int(f[3])
+        assert f[0] == "0"
+        cards = [[int(x, 16) for x in f[6 + 4 * t:10 + 4 * t]] for t in range(n)]
+        rows.append((0, int(f[1]), int(f[2]), n, cards, [int(x) for x in f[6 + 4 * n:6 + 5 * n]]))
+    assert frozen_digest(rows) == FROZEN_DIGEST
